@@ -1,0 +1,138 @@
+"""The oracle (oracle/jacks_oracle.py) against fixtures produced by the unmodified reference
+(tests/golden/make_golden.py).  CPU only.  Bit-exact unless a tolerance is written."""
+import random
+
+import numpy as np
+import pytest
+
+from conftest import edge_case_tags, load_golden, small_screen
+from oracle import jacks_oracle as O
+from jacks_b200 import synth
+
+
+def same(a, b):
+    a, b = np.asarray(a), np.asarray(b)
+    return a.shape == b.shape and np.array_equal(a, b, equal_nan=True)
+
+
+def test_em_edge_cases_bit_exact():
+    z = load_golden('edge_em.npz')
+    tags = edge_case_tags(z)
+    assert len(tags) >= 20
+    for tag in tags:
+        kw = {k.split('.kw_')[1]: float(z[k]) for k in z.files if k.startswith(tag + '.kw_')}
+        if 'apply_w_hp' in kw:
+            kw['apply_w_hp'] = bool(kw['apply_w_hp'])
+        if tag + '.fx1' in z.files:
+            kw['fixed_x'] = {'X1': z[tag + '.fx1'], 'X2': z[tag + '.fx2']}
+        info = {}
+        with np.errstate(all='ignore'):
+            y, tau, x1, x2, w1, w2 = O.em_gene(z[tag + '.data'], z[tag + '.data_err'], z[tag + '.ctrl'],
+                                               z[tag + '.ctrl_err'], int(z[tag + '.n_iter']), info=info, **kw)
+        assert info['n_iters'] == int(z[tag + '.iters']), tag
+        for name, val in dict(y=y, tau=tau, x1=x1, x2=x2, w1=w1, w2=w2).items():
+            assert same(val, z[tag + '.' + name]), (tag, name)
+
+
+def test_em_example_small_sample_bit_exact():
+    gene_index, testdata, ctrldata, pre = small_screen()
+    em = load_golden('small_em.npz')
+    genes = list(gene_index)
+    offs = pre['gene_offsets']
+    pick = list(range(0, len(genes), 9)) + [i for i, g in enumerate(genes) if len(gene_index[g]) not in (5,)]
+    sub = {genes[i]: gene_index[genes[i]] for i in sorted(set(pick))}
+    iters = {}
+    res = O.em_genes(sub, testdata, ctrldata, iters_out=iters)
+    for g in sub:
+        i = genes.index(g)
+        assert iters[g] == em['iters'][i]
+        assert same(res[g][4], em['w1'][i]) and same(res[g][5], em['w2'][i])
+        assert same(res[g][2], em['x1'][offs[i]:offs[i + 1]]) and same(res[g][3], em['x2'][offs[i]:offs[i + 1]])
+        assert same(res[g][1], em['tau'][offs[i]:offs[i + 1]])
+    # hierarchical prior and fixed-x on a thinner sample
+    sub2 = {genes[i]: gene_index[genes[i]] for i in range(0, len(genes), 40)}
+    it_hp, it_fx = {}, {}
+    res_hp = O.em_genes(sub2, testdata, ctrldata, apply_w_hp=True, iters_out=it_hp)
+    res_fx = O.em_genes(sub2, testdata, ctrldata, fixed_x={'X1': em['fx_X1'], 'X2': em['fx_X2']}, iters_out=it_fx)
+    for g in sub2:
+        i = genes.index(g)
+        assert it_hp[g] == em['hp_iters'][i] and same(res_hp[g][4], em['hp_w1'][i]) and same(res_hp[g][5], em['hp_w2'][i])
+        assert it_fx[g] == em['fx_iters'][i] and same(res_fx[g][4], em['fx_w1'][i]) and same(res_fx[g][5], em['fx_w2'][i])
+
+
+def test_em_avana_shape_bit_exact():
+    z = load_golden('avana_em.npz')
+    gene_index, testdata, ctrldata, _ = synth.make_condensed_screen(n_genes=48, n_ctrl_genes=8)
+    iters = {}
+    res = O.em_genes(gene_index, testdata, ctrldata, iters_out=iters)
+    genes = list(gene_index)
+    assert [iters[g] for g in genes] == z['iters'].tolist()
+    assert same(np.stack([res[g][4] for g in genes]), z['w1'])
+    assert same(np.stack([res[g][5] for g in genes]), z['w2'])
+    assert same(np.concatenate([res[g][2] for g in genes]), z['x1'])
+    assert same(np.concatenate([res[g][3] for g in genes]), z['x2'])
+    assert same(np.concatenate([res[g][1] for g in genes])[:16], z['tau_head'])
+    it2 = {}
+    res2 = O.em_genes(gene_index, testdata, ctrldata, fixed_x={'X1': z['fx_X1'], 'X2': z['fx_X2']}, w_only=True,
+                      iters_out=it2)
+    assert res2[genes[0]][:4] == (None, None, None, None)
+    assert [it2[g] for g in genes] == z['fx_iters'].tolist()
+    assert same(np.stack([res2[g][4] for g in genes]), z['fx_w1'])
+
+
+def test_unmatched_control_raises():
+    gene_index, testdata, ctrldata, _ = synth.make_condensed_screen(n_genes=2, n_lines=3)
+    with pytest.raises(Exception, match='matched size'):
+        O.em_genes(gene_index, testdata, ctrldata[:, :2])
+
+
+def test_sd_model_bit_exact():
+    z = load_golden('sd_model.npz')
+    for tag in ['n300r2', 'n4000r3', 'n9000r2', 'n100r4']:
+        lc = O.log_counts(z[tag + '.counts'], 32)
+        for nt in ['median', 'zmad', 'mode']:
+            assert same(O.normalize_log_counts(lc, nt), z[tag + '.norm_' + nt]), (tag, nt)
+        norm = z[tag + '.norm_median']
+        assert same(O.posterior_sd(norm), z[tag + '.sd']), tag
+        assert same(O.posterior_sd(norm, guideset_indexs=z[tag + '.subset'].tolist()), z[tag + '.sd_subset']), tag
+    assert same(O.sliding_mean_shifted(z['win.x'], 30), z['win.w30'])
+    assert same(O.suffix_max_nanreset(z['win.w30']), z['win.mono'])
+    assert same(O.suffix_max_nanreset(z['mono.nan_in']), z['mono.nan_out'])
+    assert np.isnan(O.posterior_sd(np.ones((5, 1)))).all()
+
+
+def test_preprocess_example_small_bit_exact():
+    inp, pre = load_golden('small_inputs.npz'), load_golden('small_preproc.npz')
+    lc = O.normalize_log_counts(O.log_counts(inp['counts'], 32), 'median')
+    order = np.argsort(inp['guides'])
+    assert (inp['guides'][order] == pre['meta'][:, 0]).all()
+    lc = lc[order]
+    cols = [str(c) for c in inp['columns']]
+    rep2s = dict(zip([str(r) for r in inp['rep_names']], [str(s) for s in inp['rep_samples']]))
+    samples = [rep2s[c] for c in cols]
+    sample_ids = sorted(set(samples))
+    assert sample_ids == [str(s) for s in pre['sample_ids']]
+    Iscreens = [[i for i, s in enumerate(samples) if s == sid] for sid in sample_ids]
+    assert same(O.condense(lc, Iscreens), pre['data'])
+
+
+def test_pseudo_index_and_pvalues():
+    z = load_golden('pvals.npz')
+    gene_index, _, _, _ = small_screen()
+    random.seed(int(z['seed']))
+    pidx = O.pseudo_gene_index(gene_index, [str(g) for g in z['ctrl_sorted']], 50)
+    offs, rows = z['pseudo_offsets'], z['pseudo_rows']
+    assert list(pidx) == ['JACKS_PSEUDO_GENE_%d' % i for i in range(50)]
+    for i, name in enumerate(pidx):
+        assert pidx[name] == rows[offs[i]:offs[i + 1]].tolist()
+    n_p = z['pseudo_w1'].shape[0]
+    all_w1 = np.concatenate([z['pseudo_w1'], z['gene_w1']])
+    for key, positive in [('pv_neg', False), ('pv_pos', True)]:
+        pv = O.kde_pvalues(all_w1, z['pseudo_w1'], positive=positive)
+        ref = z[key]
+        ok = np.isclose(pv, ref, rtol=1e-13, atol=0) | (np.isnan(pv) & np.isnan(ref))   # vecdot (BLAS) order is alignment dependent
+        assert ok.all(), key
+    pv = {str(g): z['pv_neg'][i] for i, g in enumerate(z['order'])}
+    sets = O.fdr_gene_sets(pv, 0.2)
+    assert ['|'.join(sorted(s)) for s in sets] == [str(s) for s in z['fdr_sets']]
+    assert n_p == 400
