@@ -13,7 +13,7 @@ Parity status: PINNED.  ``tests/golden/make_golden.py`` runs the unmodified refe
 (imported from /root/reference with the scipy-alias shim of SURVEY.md section 8c) and
 stores its outputs under ``tests/golden/``; ``tests/test_oracle_golden.py`` checks
 every function here against those files (bit-exact for the EM and the error model,
-<=1e-13 relative for KDE p-values against scipy 1.18.1).
+<=1e-12 relative for KDE p-values against scipy 1.18.1).
 """
 import random as _random
 

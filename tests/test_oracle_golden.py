@@ -130,7 +130,7 @@ def test_pseudo_index_and_pvalues():
     for key, positive in [('pv_neg', False), ('pv_pos', True)]:
         pv = O.kde_pvalues(all_w1, z['pseudo_w1'], positive=positive)
         ref = z[key]
-        ok = np.isclose(pv, ref, rtol=1e-13, atol=0) | (np.isnan(pv) & np.isnan(ref))   # vecdot (BLAS) order is alignment dependent
+        ok = np.isclose(pv, ref, rtol=1e-12, atol=0) | (np.isnan(pv) & np.isnan(ref))   # BLAS dot order is alignment dependent; far tails amplify 1 ulp of h by z^2
         assert ok.all(), key
     pv = {str(g): z['pv_neg'][i] for i, g in enumerate(z['order'])}
     sets = O.fdr_gene_sets(pv, 0.2)
