@@ -1,0 +1,201 @@
+/*
+ * jacks_b200 -- C-ABI of the B200-native JACKS inference engine.
+ *
+ * This is the drop-in boundary for the JACKS hot path.  Every entry point takes plain
+ * pointers and sizes (no torch / numpy types) and returns 0 on success or a non-zero
+ * JACKS_E_* code; jacks_last_error() then holds a message for the calling thread.
+ * The reference (felicityallen/JACKS) is pure Python, so "the reference's FFI for this
+ * path" is the set of Python functions below; INTEGRATION.md shows the ctypes stub a
+ * maintainer would add to the reference to route them here.
+ *
+ *   reference function (file:line)                            entry point(s) here
+ *   -------------------------------------------------------   ---------------------------------
+ *   jacks/jacks/infer.py:18   inferJACKS (gene loop)           jacks_em_plan_create + jacks_em_run_device,
+ *   jacks/jacks/infer.py:55   inferJACKSGene (per-gene EM)     jacks_em_batched_host
+ *   jacks/jacks/jacks_io.py:416  pseudo-gene EM                same, with a row-gather CSR index
+ *   jacks/jacks/jacks_io.py:69   computeW1PvalsAndFDRs         jacks_kde_pvalues_device / _host
+ *   jacks/jacks/preprocess.py:77 normalizeLogCounts (median)   jacks_preprocess_host (step 1-2)
+ *   jacks/jacks/preprocess.py:61 condense_normalised_counts    jacks_preprocess_host (step 3)
+ *   jacks/jacks/preprocess.py:25 calc_posterior_sd             jacks_posterior_sd_host / jacks_preprocess_host
+ *
+ * All floating point data is IEEE float64.  All arrays are dense, C order.  "device"
+ * entry points take pointers into the current CUDA device's memory and enqueue work on
+ * the given stream without synchronising; "host" entry points take host pointers, do
+ * their own host<->device copies (directly when the buffers are pinned, through an
+ * internal pinned ring otherwise) and return when the outputs are complete.
+ *
+ * There is no CPU fallback: without a CUDA device every compute entry point fails with
+ * JACKS_E_CUDA.
+ */
+#ifndef JACKS_B200_H
+#define JACKS_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define JACKS_B200_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define JACKS_API __attribute__((visibility("default")))
+#else
+#define JACKS_API
+#endif
+
+enum {
+    JACKS_OK = 0,
+    JACKS_E_INVALID = 1,  /* bad argument (null pointer, negative size, inconsistent CSR ...) */
+    JACKS_E_CUDA = 2,     /* CUDA runtime error or no usable device */
+    JACKS_E_NOMEM = 3,    /* host or device allocation failed */
+    JACKS_E_SHAPE = 4     /* "Expecting matched size between control and test data" (infer.py:26) */
+};
+
+/* Hyper-parameters of the per-gene EM; defaults are those of inferJACKS / inferJACKSGene
+ * (infer.py:18, :55).  Fill with jacks_em_default_params() and override as needed. */
+typedef struct JacksEmParams {
+    int32_t n_iter;              /* 50   */
+    int32_t apply_w_hp;          /* 0    hierarchical prior on w (infer.py:92) */
+    double tol;                  /* 0.1  absolute change of the bound that stops the loop */
+    double mu0_x;                /* 1.0  */
+    double var0_x;               /* 1.0  */
+    double mu0_w;                /* 0.0  */
+    double var0_w;               /* 1e4  */
+    double tau_prior_strength;   /* 0.5  */
+} JacksEmParams;
+
+/* Opaque per-device context: streams, scratch, pinned staging ring. */
+typedef struct JacksCtx JacksCtx;
+/* Opaque batched-EM plan: the gene -> guide-row CSR index on the device, bucketed by guide count. */
+typedef struct JacksEmPlan JacksEmPlan;
+
+/* Message of the last failure on the calling thread ("" if none). */
+JACKS_API const char* jacks_last_error(void);
+JACKS_API int jacks_abi_version(void);
+/* Number of CUDA devices visible (0 when there is no driver / device). Never fails. */
+JACKS_API int jacks_device_count(void);
+
+JACKS_API int jacks_ctx_create(int device, JacksCtx** out);
+JACKS_API void jacks_ctx_destroy(JacksCtx* ctx);
+/* Kernel launches enqueued through this context since creation (bench.py's gpu_launches). */
+JACKS_API int64_t jacks_ctx_launch_count(const JacksCtx* ctx);
+
+JACKS_API void jacks_em_default_params(JacksEmParams* p);
+
+/* Pinned host memory for callers that want direct DMA on the host entry points. */
+JACKS_API int jacks_host_alloc(void** out, uint64_t bytes);
+JACKS_API void jacks_host_free(void* p);
+
+/*
+ * Build a plan for a gene index (the gene_index dict of inferJACKS, infer.py:18-21, in CSR form).
+ *   gene_offsets[n_genes+1]   int64, gene g owns guide_rows[gene_offsets[g] .. gene_offsets[g+1])
+ *   guide_rows[sum G]         int32 row numbers into the [N, L, 2] data cubes; rows may repeat
+ *                             (pseudo-genes, jacks_io.py:261-262); every row must be < n_rows
+ *   n_lines                   L, number of test cell lines
+ * Host pointers.  A gene with no guides is rejected with JACKS_E_INVALID (the reference cannot
+ * infer it either: nanmedian over an empty axis).
+ */
+JACKS_API int jacks_em_plan_create(JacksCtx* ctx, const int64_t* gene_offsets, const int32_t* guide_rows,
+                         int64_t n_genes, int64_t n_rows, int32_t n_lines, JacksEmPlan** out);
+JACKS_API void jacks_em_plan_destroy(JacksEmPlan* plan);
+
+/* Device buffers of one batched EM run.  Optional pointers may be NULL (output not wanted). */
+typedef struct JacksEmDeviceIO {
+    const double* test;       /* [N, L, 2]  (mean, sd) per guide and line -- testdata of infer.py:18 */
+    const double* ctrl;       /* [N, ctrl_lines, 2]; ctrl_lines == L (matched control, infer.py:66-70)
+                                 or 1 (one control column shared by all lines) */
+    int32_t ctrl_lines;
+    int32_t ctrl_rowmean_fill; /* only with ctrl_lines == 1: fill a NaN control sd with the row mean of the
+                                  test sds (1-D control branch, infer.py:61-65) instead of the per-element
+                                  test sd (matched branch, infer.py:68) */
+    const double* fixed_x1;   /* optional [N]: reference efficacies by row (infer.py:22-23, :77-79) */
+    const double* fixed_x2;   /* optional [N] */
+    double* x1;               /* optional [sum G]   E[x],   in CSR order */
+    double* x2;               /* optional [sum G]   E[x^2] */
+    double* w1;               /* required [n_genes, L]  E[w] */
+    double* w2;               /* optional [n_genes, L]  E[w^2] */
+    double* y;                /* optional [sum G, L]  log-fold changes */
+    double* tau;              /* optional [sum G, L]  final noise precisions */
+    int32_t* n_iters;         /* optional [n_genes]  EM loop passes executed */
+    double* bound;            /* optional [n_genes]  final value of the convergence statistic (infer.py:123) */
+} JacksEmDeviceIO;
+
+/* Enqueue the batched EM on `stream` (a cudaStream_t, may be NULL for the default stream). */
+JACKS_API int jacks_em_run_device(JacksCtx* ctx, const JacksEmPlan* plan, const JacksEmParams* params,
+                        const JacksEmDeviceIO* io, void* stream);
+
+/* Host buffers of one batched EM call; same meaning as JacksEmDeviceIO. */
+typedef struct JacksEmHostIO {
+    const double* test;
+    const double* ctrl;
+    int64_t n_rows;           /* N */
+    int32_t n_lines;          /* L */
+    int32_t ctrl_lines;
+    int32_t ctrl_rowmean_fill;
+    int32_t reserved;
+    const double* fixed_x1;
+    const double* fixed_x2;
+    double* x1;
+    double* x2;
+    double* w1;
+    double* w2;
+    double* y;
+    double* tau;
+    int32_t* n_iters;
+    double* bound;
+} JacksEmHostIO;
+
+/*
+ * inferJACKS in one call on host buffers (infer.py:18-30): uploads the data cubes, runs the EM for
+ * every gene of the CSR index, downloads the requested outputs.  If `keep_resident` is non-zero the
+ * uploaded cubes stay on the device inside ctx and a following call with test == NULL reuses them
+ * (the pseudo-gene pass of jacks_io.py:416 reads the same cubes through another index).
+ */
+JACKS_API int jacks_em_batched_host(JacksCtx* ctx, const JacksEmParams* params,
+                          const int64_t* gene_offsets, const int32_t* guide_rows, int64_t n_genes,
+                          const JacksEmHostIO* io, int32_t keep_resident);
+
+/*
+ * KDE p-values of gene effects against the pseudo-gene null (computeW1PvalsAndFDRs with pseudo=True,
+ * jacks_io.py:69-89 + scipy.stats.gaussian_kde.integrate_box_1d): for every line l, bandwidth
+ * h_l = std(s_l, ddof=1) * n_l^(-1/5) over the non-NaN pseudo values s_l, and
+ *   negative selection: p[g,l] = mean_i( Phi((w[g,l]-s_i)/h_l) - Phi((-100-s_i)/h_l) )
+ *   positive selection: p[g,l] = mean_i( Phi(( 100-s_i)/h_l) - Phi((w[g,l]-s_i)/h_l) )
+ *   w1_genes [n_genes, L], w1_pseudo [n_pseudo, L], pvals [n_genes, L]
+ */
+JACKS_API int jacks_kde_pvalues_device(JacksCtx* ctx, const double* w1_genes, int64_t n_genes,
+                             const double* w1_pseudo, int64_t n_pseudo, int32_t n_lines,
+                             int32_t positive, double* pvals, void* stream);
+JACKS_API int jacks_kde_pvalues_host(JacksCtx* ctx, const double* w1_genes, int64_t n_genes,
+                           const double* w1_pseudo, int64_t n_pseudo, int32_t n_lines,
+                           int32_t positive, double* pvals);
+
+/*
+ * Mean-variance error model for one or more samples (calc_posterior_sd with the default arguments,
+ * preprocess.py:25-58, as called from condense_normalised_counts, preprocess.py:61-67).
+ *   logcounts [n_guides, n_cols]   normalised log2 counts
+ *   sample_col_offsets[n_samples+1], sample_cols[...]   CSR list of the replicate columns of each sample
+ *   data [n_guides, n_samples, 2]  out: (mean over replicates, posterior sd); sd is NaN for a
+ *                                  single-replicate sample (preprocess.py:32)
+ */
+JACKS_API int jacks_condense_host(JacksCtx* ctx, const double* logcounts, int64_t n_guides, int32_t n_cols,
+                        const int32_t* sample_col_offsets, const int32_t* sample_cols, int32_t n_samples,
+                        double* data);
+
+/*
+ * Counts -> normalised log counts (preprocess.py:147 and normalizeLogCounts with normtype 'median',
+ * preprocess.py:77-81): out[i,c] = log2(counts[i,c] + prior) - nanmedian_i(log2(counts[.,c] + prior)).
+ *   counts [n_guides, n_cols] float64 (the reference eval()s each cell, so non-integers are legal)
+ */
+JACKS_API int jacks_lognorm_median_host(JacksCtx* ctx, const double* counts, int64_t n_guides, int32_t n_cols,
+                              double prior, double* logcounts);
+
+/* FP64 FMA-pipe peak of the current device in FLOP/s (dependent-chain-free DFMA microbenchmark);
+ * bench.py uses it as the roofline denominator because MEASURED_PEAKS.json has no FP64 entry. */
+JACKS_API int jacks_fp64_peak_flops(JacksCtx* ctx, double* flops_out, double* seconds_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* JACKS_B200_H */

@@ -1,0 +1,301 @@
+"""ctypes binding of libjacks_b200.so (the C-ABI declared in include/jacks_b200.h).
+
+This is the only door between the Python host code and the CUDA kernels.  There is no
+CPU fallback: if the shared library is missing, or no CUDA device is visible, the calls
+raise -- they never silently compute on the host.
+"""
+import ctypes as C
+import os
+import threading
+
+import numpy as np
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_PKG, 'libjacks_b200.so')
+
+JACKS_OK, JACKS_E_INVALID, JACKS_E_CUDA, JACKS_E_NOMEM, JACKS_E_SHAPE = 0, 1, 2, 3, 4
+
+
+class JacksError(Exception):
+    """Raised for any non-zero return code of the C-ABI (the reference raises plain Exception too)."""
+
+    def __init__(self, code, msg):
+        Exception.__init__(self, msg)
+        self.code = code
+
+
+class EmParams(C.Structure):
+    _fields_ = [('n_iter', C.c_int32), ('apply_w_hp', C.c_int32), ('tol', C.c_double), ('mu0_x', C.c_double),
+                ('var0_x', C.c_double), ('mu0_w', C.c_double), ('var0_w', C.c_double),
+                ('tau_prior_strength', C.c_double)]
+
+
+class EmDeviceIO(C.Structure):
+    _fields_ = [('test', C.c_void_p), ('ctrl', C.c_void_p), ('ctrl_lines', C.c_int32),
+                ('ctrl_rowmean_fill', C.c_int32), ('fixed_x1', C.c_void_p), ('fixed_x2', C.c_void_p),
+                ('x1', C.c_void_p), ('x2', C.c_void_p), ('w1', C.c_void_p), ('w2', C.c_void_p),
+                ('y', C.c_void_p), ('tau', C.c_void_p), ('n_iters', C.c_void_p), ('bound', C.c_void_p)]
+
+
+class EmHostIO(C.Structure):
+    _fields_ = [('test', C.c_void_p), ('ctrl', C.c_void_p), ('n_rows', C.c_int64), ('n_lines', C.c_int32),
+                ('ctrl_lines', C.c_int32), ('ctrl_rowmean_fill', C.c_int32), ('reserved', C.c_int32),
+                ('fixed_x1', C.c_void_p), ('fixed_x2', C.c_void_p), ('x1', C.c_void_p), ('x2', C.c_void_p),
+                ('w1', C.c_void_p), ('w2', C.c_void_p), ('y', C.c_void_p), ('tau', C.c_void_p),
+                ('n_iters', C.c_void_p), ('bound', C.c_void_p)]
+
+
+_lib = None
+_lock = threading.Lock()
+
+
+def lib():
+    """Load the shared library (once).  Raises if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        if not os.path.exists(LIB_PATH):
+            raise JacksError(JACKS_E_CUDA, 'jacks_b200: %s is missing; run `python -m jacks_b200.build` '
+                             '(needs nvcc). There is no CPU fallback.' % LIB_PATH)
+        L = C.CDLL(LIB_PATH)
+        vp, i32, i64, dbl = C.c_void_p, C.c_int32, C.c_int64, C.c_double
+        L.jacks_last_error.restype = C.c_char_p
+        L.jacks_abi_version.restype = C.c_int
+        L.jacks_device_count.restype = C.c_int
+        L.jacks_ctx_create.argtypes = [C.c_int, C.POINTER(vp)]
+        L.jacks_ctx_destroy.argtypes = [vp]
+        L.jacks_ctx_destroy.restype = None
+        L.jacks_ctx_launch_count.argtypes = [vp]
+        L.jacks_ctx_launch_count.restype = i64
+        L.jacks_em_default_params.argtypes = [C.POINTER(EmParams)]
+        L.jacks_em_default_params.restype = None
+        L.jacks_host_alloc.argtypes = [C.POINTER(vp), C.c_uint64]
+        L.jacks_host_free.argtypes = [vp]
+        L.jacks_host_free.restype = None
+        L.jacks_em_plan_create.argtypes = [vp, vp, vp, i64, i64, i32, C.POINTER(vp)]
+        L.jacks_em_plan_destroy.argtypes = [vp]
+        L.jacks_em_plan_destroy.restype = None
+        L.jacks_em_run_device.argtypes = [vp, vp, C.POINTER(EmParams), C.POINTER(EmDeviceIO), vp]
+        L.jacks_em_batched_host.argtypes = [vp, C.POINTER(EmParams), vp, vp, i64, C.POINTER(EmHostIO), i32]
+        L.jacks_fp64_peak_flops.argtypes = [vp, C.POINTER(dbl), C.POINTER(dbl)]
+        if hasattr(L, 'jacks_kde_pvalues_device'):
+            L.jacks_kde_pvalues_device.argtypes = [vp, vp, i64, vp, i64, i32, i32, vp, vp]
+            L.jacks_kde_pvalues_host.argtypes = [vp, vp, i64, vp, i64, i32, i32, vp]
+        if hasattr(L, 'jacks_condense_host'):
+            L.jacks_condense_host.argtypes = [vp, vp, i64, i32, vp, vp, i32, vp]
+            L.jacks_lognorm_median_host.argtypes = [vp, vp, i64, i32, dbl, vp]
+        _lib = L
+    return _lib
+
+
+def check(rc):
+    if rc != JACKS_OK:
+        msg = lib().jacks_last_error().decode('utf-8', 'replace')
+        raise JacksError(rc, msg or ('jacks_b200 error %d' % rc))
+
+
+def default_params(**over):
+    p = EmParams()
+    lib().jacks_em_default_params(C.byref(p))
+    for k, v in over.items():
+        if not hasattr(p, k):
+            raise TypeError('unknown EM parameter %s' % k)
+        setattr(p, k, v)
+    return p
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data
+
+
+class PinnedArray(object):
+    """A numpy array backed by pinned (page-locked) host memory from jacks_host_alloc."""
+
+    def __init__(self, shape, dtype=np.float64):
+        self.shape = tuple(int(s) for s in np.atleast_1d(shape))
+        self.dtype = np.dtype(dtype)
+        nbytes = int(np.prod(self.shape, dtype=np.int64)) * self.dtype.itemsize
+        p = C.c_void_p()
+        check(lib().jacks_host_alloc(C.byref(p), max(nbytes, 1)))
+        self._p = p
+        buf = (C.c_char * max(nbytes, 1)).from_address(p.value)
+        self.array = np.frombuffer(buf, dtype=self.dtype, count=int(np.prod(self.shape, dtype=np.int64))).reshape(self.shape)
+
+    def free(self):
+        if self._p is not None:
+            self.array = None
+            lib().jacks_host_free(self._p)
+            self._p = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class Context(object):
+    """One per GPU: streams, scratch and resident buffers (JacksCtx)."""
+
+    def __init__(self, device=0):
+        h = C.c_void_p()
+        check(lib().jacks_ctx_create(int(device), C.byref(h)))
+        self.h = h
+        self.device = int(device)
+
+    def close(self):
+        if self.h is not None:
+            lib().jacks_ctx_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def launch_count(self):
+        return int(lib().jacks_ctx_launch_count(self.h))
+
+    def fp64_peak_flops(self):
+        f, s = C.c_double(), C.c_double()
+        check(lib().jacks_fp64_peak_flops(self.h, C.byref(f), C.byref(s)))
+        return f.value
+
+
+_ctx = {}
+
+
+def context(device=0):
+    """Process-wide context of a device (created on first use)."""
+    device = int(device)
+    if device not in _ctx:
+        _ctx[device] = Context(device)
+    return _ctx[device]
+
+
+def as_csr(gene_index):
+    """gene_index {gene: [rows]} -> (names, offsets int64[n+1], rows int32[sum G]) in dict order."""
+    names = list(gene_index)
+    counts = np.fromiter((len(gene_index[g]) for g in names), dtype=np.int64, count=len(names))
+    offsets = np.zeros(len(names) + 1, dtype=np.int64)
+    np.cumsum(counts, out=offsets[1:])
+    if len(names):
+        rows = np.fromiter((r for g in names for r in gene_index[g]), dtype=np.int64, count=int(offsets[-1]))
+    else:
+        rows = np.zeros(0, dtype=np.int64)
+    return names, offsets, rows
+
+
+class EmPlan(object):
+    """Device-resident gene index (JacksEmPlan)."""
+
+    def __init__(self, ctx, offsets, rows, n_rows, n_lines):
+        self.ctx = ctx
+        self.offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+        rows = np.asarray(rows)
+        if rows.size and (rows.min() < 0 or rows.max() >= n_rows):
+            raise IndexError('guide row index out of bounds for %d rows' % n_rows)
+        self.rows = np.ascontiguousarray(rows, dtype=np.int32)
+        self.n_genes = len(self.offsets) - 1
+        self.total_guides = int(self.offsets[-1]) if self.n_genes >= 0 and len(self.offsets) else 0
+        self.n_lines = int(n_lines)
+        h = C.c_void_p()
+        check(lib().jacks_em_plan_create(ctx.h, _ptr(self.offsets), _ptr(self.rows), self.n_genes, int(n_rows),
+                                         int(n_lines), C.byref(h)))
+        self.h = h
+
+    def close(self):
+        if self.h is not None:
+            lib().jacks_em_plan_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def run_device(self, params, io, stream=0):
+        """Enqueue the batched EM on `stream` (an int cudaStream_t handle); io is an EmDeviceIO of device pointers."""
+        check(lib().jacks_em_run_device(self.ctx.h, self.h, C.byref(params), C.byref(io), C.c_void_p(stream or None)))
+
+
+def em_batched_host(ctx, offsets, rows, test, ctrl, params=None, fixed_x1=None, fixed_x2=None,
+                    want=('x1', 'x2', 'w1', 'w2', 'y', 'tau', 'n_iters', 'bound'), ctrl_rowmean_fill=False,
+                    keep_resident=False, n_rows=None, n_lines=None, ctrl_lines=None, out=None):
+    """jacks_em_batched_host on numpy arrays.  test [N,L,2], ctrl [N,L,2] or [N,1,2] float64 C-contiguous
+    (or test=None to reuse the cubes a previous keep_resident call left on the device, with
+    n_rows/n_lines/ctrl_lines given).  Returns a dict of the requested outputs."""
+    params = params or default_params()
+    offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+    rows = np.asarray(rows)
+    if test is not None:
+        test = np.ascontiguousarray(test, dtype=np.float64)
+        ctrl = np.ascontiguousarray(ctrl, dtype=np.float64)
+        if test.ndim != 3 or test.shape[2] != 2 or ctrl.ndim != 3 or ctrl.shape[2] != 2 or ctrl.shape[0] != test.shape[0]:
+            raise JacksError(JACKS_E_SHAPE, 'Expecting matched size between control and test data')
+        n_rows, n_lines, ctrl_lines = test.shape[0], test.shape[1], ctrl.shape[1]
+    if rows.size and (rows.min() < 0 or rows.max() >= n_rows):
+        raise IndexError('guide row index out of bounds for %d rows' % n_rows)
+    rows = np.ascontiguousarray(rows, dtype=np.int32)
+    n_genes = len(offsets) - 1
+    T = int(offsets[-1]) if n_genes > 0 else 0
+    shapes = dict(x1=((T,), np.float64), x2=((T,), np.float64), w1=((n_genes, n_lines), np.float64),
+                  w2=((n_genes, n_lines), np.float64), y=((T, n_lines), np.float64), tau=((T, n_lines), np.float64),
+                  n_iters=((n_genes,), np.int32), bound=((n_genes,), np.float64))
+    res = {}
+    for k in set(want) | {'w1'}:
+        if out is not None and k in out:
+            assert out[k].shape == shapes[k][0] and out[k].dtype == shapes[k][1] and out[k].flags.c_contiguous
+            res[k] = out[k]
+        else:
+            res[k] = np.empty(shapes[k][0], dtype=shapes[k][1])
+    io = EmHostIO()
+    io.test, io.ctrl = _ptr(test), _ptr(ctrl)
+    io.n_rows, io.n_lines, io.ctrl_lines = int(n_rows), int(n_lines), int(ctrl_lines)
+    io.ctrl_rowmean_fill = int(bool(ctrl_rowmean_fill))
+    if fixed_x1 is not None:
+        fixed_x1 = np.ascontiguousarray(fixed_x1, dtype=np.float64)
+        fixed_x2 = np.ascontiguousarray(fixed_x2, dtype=np.float64)
+        if fixed_x1.shape != (n_rows,) or fixed_x2.shape != (n_rows,):
+            raise JacksError(JACKS_E_INVALID, 'fixed_x arrays must have one entry per data row')
+        io.fixed_x1, io.fixed_x2 = _ptr(fixed_x1), _ptr(fixed_x2)
+    for k in res:
+        setattr(io, k, _ptr(res[k]))
+    check(lib().jacks_em_batched_host(ctx.h, C.byref(params), _ptr(offsets), _ptr(rows), n_genes, C.byref(io),
+                                      int(bool(keep_resident))))
+    return res
+
+
+def kde_pvalues_host(ctx, w1_genes, w1_pseudo, positive=False):
+    w1_genes = np.ascontiguousarray(w1_genes, dtype=np.float64)
+    w1_pseudo = np.ascontiguousarray(w1_pseudo, dtype=np.float64)
+    if w1_genes.ndim != 2 or w1_pseudo.ndim != 2 or w1_genes.shape[1] != w1_pseudo.shape[1]:
+        raise JacksError(JACKS_E_INVALID, 'w1_genes [n_genes, L] and w1_pseudo [n_pseudo, L] expected')
+    out = np.empty(w1_genes.shape, dtype=np.float64)
+    check(lib().jacks_kde_pvalues_host(ctx.h, _ptr(w1_genes), w1_genes.shape[0], _ptr(w1_pseudo), w1_pseudo.shape[0],
+                                       w1_genes.shape[1], int(bool(positive)), _ptr(out)))
+    return out
+
+
+def lognorm_median_host(ctx, counts, prior):
+    counts = np.ascontiguousarray(counts, dtype=np.float64)
+    out = np.empty(counts.shape, dtype=np.float64)
+    check(lib().jacks_lognorm_median_host(ctx.h, _ptr(counts), counts.shape[0], counts.shape[1], float(prior), _ptr(out)))
+    return out
+
+
+def condense_host(ctx, logcounts, Iscreens):
+    logcounts = np.ascontiguousarray(logcounts, dtype=np.float64)
+    offs = np.zeros(len(Iscreens) + 1, dtype=np.int32)
+    offs[1:] = np.cumsum([len(c) for c in Iscreens])
+    cols = np.ascontiguousarray(np.concatenate([np.asarray(c, dtype=np.int32) for c in Iscreens]) if len(Iscreens) else np.zeros(0, np.int32), dtype=np.int32)
+    data = np.empty((logcounts.shape[0], len(Iscreens), 2), dtype=np.float64)
+    check(lib().jacks_condense_host(ctx.h, _ptr(logcounts), logcounts.shape[0], logcounts.shape[1], _ptr(offs),
+                                    _ptr(cols), len(Iscreens), _ptr(data)))
+    return data

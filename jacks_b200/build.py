@@ -1,0 +1,85 @@
+"""Build recipe for libjacks_b200.so (nvcc, sm_100a only) and the C oracle (gcc).
+
+    python -m jacks_b200.build          # build if stale
+    python -m jacks_b200.build --force
+
+The shared library is built IN-TREE (jacks_b200/libjacks_b200.so) so that it travels to the
+GPU box with the repository snapshot.  nvcc cross-compiles without a GPU.
+"""
+import os
+import subprocess
+import sys
+from concurrent.futures import ThreadPoolExecutor
+
+PKG = os.path.dirname(os.path.abspath(__file__))
+REPO = os.path.dirname(PKG)
+CSRC = os.path.join(PKG, 'csrc')
+OBJ = os.path.join(PKG, 'csrc', 'build')
+LIB = os.path.join(PKG, 'libjacks_b200.so')
+NVCC = os.environ.get('NVCC', '/usr/local/cuda/bin/nvcc')
+ARCH = ['-gencode', 'arch=compute_100a,code=sm_100a']
+FLAGS = ['-O3', '-std=c++17', '-lineinfo', '-Xcompiler', '-fPIC,-fvisibility=hidden']
+FAST_G = list(range(1, 9))
+
+UNITS = [('capi.cu', 'capi.o', []), ('em_dispatch.cu', 'em_dispatch.o', []), ('em_generic.cu', 'em_generic.o', []),
+         ('fp64_probe.cu', 'fp64_probe.o', []), ('kde_pvalues.cu', 'kde_pvalues.o', []),
+         ('preprocess_kernels.cu', 'preprocess_kernels.o', [])] + \
+        [('em_fast_inst.cu', 'em_fast_g%d.o' % g, ['-DJACKS_G=%d' % g]) for g in FAST_G]
+
+
+def _sources():
+    out = [os.path.join(REPO, 'include', 'jacks_b200.h')]
+    for f in sorted(os.listdir(CSRC)):
+        if f.endswith(('.cu', '.cuh', '.h')):
+            out.append(os.path.join(CSRC, f))
+    return out
+
+
+def _stale(target, deps):
+    if not os.path.exists(target):
+        return True
+    t = os.path.getmtime(target)
+    return any(os.path.getmtime(d) > t for d in deps)
+
+
+def _run(cmd):
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError('build failed: %s\n%s\n%s' % (' '.join(cmd), r.stdout, r.stderr))
+    return r.stdout + r.stderr
+
+
+def build_library(force=False, verbose=False):
+    deps = _sources()
+    units = [u for u in UNITS if os.path.exists(os.path.join(CSRC, u[0]))]
+    if not force and not _stale(LIB, deps):
+        return LIB
+    os.makedirs(OBJ, exist_ok=True)
+    hdrs = [d for d in deps if not d.endswith('.cu')]
+
+    def compile_one(u):
+        src, obj, extra = os.path.join(CSRC, u[0]), os.path.join(OBJ, u[1]), u[2]
+        if force or _stale(obj, [src] + hdrs):
+            log = _run([NVCC] + ARCH + FLAGS + (['-Xptxas', '-v'] if verbose else []) + extra + ['-c', src, '-o', obj])
+            if verbose:
+                print(log)
+        return obj
+    with ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1)) as ex:
+        objs = list(ex.map(compile_one, units))
+    _run([NVCC] + ARCH + ['-shared', '-Xcompiler', '-fPIC', '-o', LIB] + objs + ['-cudart', 'static'])
+    return LIB
+
+
+def build_oracle(force=False):
+    """gcc build of the C restatement of the EM (oracle/em_oracle.c) -- test infrastructure."""
+    src = os.path.join(REPO, 'oracle', 'em_oracle.c')
+    out = os.path.join(REPO, 'oracle', 'libem_oracle.so')
+    if os.path.exists(src) and (force or _stale(out, [src])):
+        _run(['gcc', '-O2', '-fPIC', '-shared', '-fopenmp', '-ffp-contract=off', '-o', out, src, '-lm'])
+    return out
+
+
+if __name__ == '__main__':
+    force = '--force' in sys.argv
+    print(build_library(force=force, verbose='-v' in sys.argv))
+    print(build_oracle(force=force))

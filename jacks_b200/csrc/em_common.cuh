@@ -1,0 +1,65 @@
+// Shared declarations of the batched EM kernels (host dispatcher <-> kernel translation units).
+//
+// The EM being computed is the per-gene variational loop of the reference,
+// jacks/jacks/infer.py:55-125 (inferJACKSGene, updateX, updateW, updateTau, lowerBound).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace jacks {
+
+// Everything one EM launch needs.  Passed by value as a kernel argument.
+struct EmLaunch {
+    // inputs
+    const double2* test;          // [N][L]           (mean, sd)
+    const double2* ctrl;          // [N][ctrl_lines]  (mean, sd)
+    int L;
+    int ctrl_lines;               // L or 1
+    int ctrl_rowmean_fill;        // 1-D control NaN-sd rule (infer.py:63)
+    const long long* gene_offsets;  // [n_genes+1] CSR
+    const int* guide_rows;        // [sum G]
+    const int* gene_ids;          // [n_work] genes of this bucket (indices into the CSR)
+    int n_work;
+    const int* n_work_dev;        // if non-null the work count is read from here (deferred queue)
+    const double* fixed_x1;       // by row, or null
+    const double* fixed_x2;
+    // outputs (nullable except w1)
+    double* x1; double* x2;       // [sum G] CSR order
+    double* w1; double* w2;       // [n_genes][L]
+    double* y;  double* tau;      // [sum G][L]
+    int* n_iters; double* bound;  // [n_genes]
+    // work distribution
+    int* work_counter;            // zeroed before the launch; teams pull bucket slots from it
+    int* deferred_ids;            // fast kernels push genes holding NaN here ...
+    int* deferred_count;          // ... and count them here; the generic kernel drains the list
+    // hyper-parameters (infer.py:55 defaults)
+    int n_iter; int apply_w_hp;
+    double tol, mu0_x, var0_x, mu0_w, var0_w, tps;
+    // generic kernel only: global scratch when a gene's working set exceeds shared memory
+    double* scratch; long long scratch_stride;   // doubles per warp
+};
+
+// Fast path: compile-time guide count G, KL line-strips per lane, W warps per gene.
+// Returns cudaErrorInvalidValue if (G, KL, W) was not instantiated.
+cudaError_t launch_em_fast(int G, int KL, int W, const EmLaunch& a, int n_sm, int grid_limit, cudaStream_t st,
+                           int* grid_out);
+// Is (G, KL, W) compiled in?
+bool em_fast_available(int G, int KL, int W);
+// Occupancy (CTAs per SM) of a fast instantiation on the current device, 0 if unavailable.
+int em_fast_occupancy(int G, int KL, int W);
+
+// Generic path: any G and L, NaN-safe, one warp per gene, working set in shared memory when it
+// fits and in `scratch` (EmLaunch::scratch, one slab per warp of the grid) otherwise.
+struct EmGenericConfig {
+    int warps_per_cta;
+    int grid;
+    long long smem_doubles_per_warp;
+    size_t smem_bytes;
+    long long scratch_doubles_per_warp;   // 0: everything fits shared memory
+};
+// Working-set size (doubles) of one gene in the generic kernel.
+__host__ __device__ long long em_generic_work_doubles(int G, int L);
+cudaError_t em_generic_configure(int maxG, int L, long long n_work_cap, int n_sm, EmGenericConfig* cfg);
+cudaError_t launch_em_generic(const EmGenericConfig& cfg, const EmLaunch& a, cudaStream_t st);
+
+}  // namespace jacks
