@@ -57,7 +57,7 @@ using namespace jacks;
 // ------------------------------------------------------------------------------------------------
 struct EmBucket {
     int G;            // guide count (fast buckets); 0 for the generic bucket
-    int KL, W;        // fast kernel shape
+    int W;            // warps per gene of the fast kernel
     int n;            // genes in the bucket
     int ids_off;      // offset into JacksEmPlan::d_ids
 };
@@ -77,22 +77,18 @@ struct JacksEmPlan {
 
 namespace {
 
-// Shape of the fast kernel for (G, L): KL strips per lane x W warps per gene; {0,0} = generic kernel.
-void choose_shape(int G, int L, int* KL, int* W) {
-    *KL = 0; *W = 0;
-    if (G < 1 || G > 8) return;
-    const char* env = getenv("JACKS_EM_SHAPE");     // tuning override "KL,W"
-    if (env) {
-        int kl = 0, w = 0;
-        if (sscanf(env, "%d,%d", &kl, &w) == 2 && kl * w * 32 >= L && em_fast_available(G, kl, w)) {
-            *KL = kl; *W = w;
-            return;
-        }
+// Warps per gene of the fast kernel for (G, L); 0 = use the generic kernel.
+int choose_team(int G, int L) {
+    if (G < 1 || G > 8) return 0;
+    const char* env = getenv("JACKS_EM_W");          // tuning override
+    int W = 0;
+    if (env) W = atoi(env);
+    if (!(W == 1 || W == 2 || W == 4)) {
+        const int strips = (L + 31) / 32;
+        W = strips >= 12 ? 4 : (strips >= 6 ? 2 : 1);
     }
-    static const int cand[][2] = {{1, 1}, {4, 1}, {13, 1}, {7, 2}, {4, 4}};
-    for (auto& c : cand) {
-        if (c[0] * c[1] * 32 >= L && em_fast_available(G, c[0], c[1])) { *KL = c[0]; *W = c[1]; return; }
-    }
+    if (!em_fast_available(G, W) || em_fast_smem_bytes(G, W, L) > kMaxDynSmem) return 0;
+    return W;
 }
 
 }  // namespace
@@ -187,17 +183,17 @@ int jacks_em_plan_create(JacksCtx* ctx, const int64_t* gene_offsets, const int32
 
     JacksEmPlan* p = new JacksEmPlan();
     p->ctx = ctx; p->n_genes = n_genes; p->n_rows = n_rows; p->total_guides = total; p->L = n_lines;
-    p->generic = EmBucket{0, 0, 0, 0, 0};
+    p->generic = EmBucket{0, 0, 0, 0};
     p->generic_maxG = 0; p->fast_maxG = 0; p->n_fast_genes = 0;
 
     // bucket genes by guide count, keeping the caller's order inside each bucket
     std::vector<std::vector<int>> byG(9);
     std::vector<int> gen;
-    int shapeKL[9] = {0}, shapeW[9] = {0};
-    for (int G = 1; G <= 8; ++G) choose_shape(G, n_lines, &shapeKL[G], &shapeW[G]);
+    int teamW[9] = {0};
+    for (int G = 1; G <= 8; ++G) teamW[G] = choose_team(G, n_lines);
     for (int64_t g = 0; g < n_genes; ++g) {
         const int G = (int)(gene_offsets[g + 1] - gene_offsets[g]);
-        if (G <= 8 && shapeKL[G] > 0) byG[G].push_back((int)g);
+        if (G <= 8 && teamW[G] > 0) byG[G].push_back((int)g);
         else { gen.push_back((int)g); p->generic_maxG = std::max(p->generic_maxG, G); }
     }
     std::vector<int> ids;
@@ -205,14 +201,14 @@ int jacks_em_plan_create(JacksCtx* ctx, const int64_t* gene_offsets, const int32
     // larger G first: the heavier buckets start while the GPU is empty
     for (int G = 8; G >= 1; --G) {
         if (byG[G].empty()) continue;
-        EmBucket b{G, shapeKL[G], shapeW[G], (int)byG[G].size(), (int)ids.size()};
+        EmBucket b{G, teamW[G], (int)byG[G].size(), (int)ids.size()};
         ids.insert(ids.end(), byG[G].begin(), byG[G].end());
         p->fast.push_back(b);
         p->fast_maxG = std::max(p->fast_maxG, G);
         p->n_fast_genes += b.n;
     }
     if (!gen.empty()) {
-        p->generic = EmBucket{0, 0, 0, (int)gen.size(), (int)ids.size()};
+        p->generic = EmBucket{0, 0, (int)gen.size(), (int)ids.size()};
         ids.insert(ids.end(), gen.begin(), gen.end());
     }
 
@@ -298,7 +294,7 @@ int jacks_em_run_device(JacksCtx* ctx, const JacksEmPlan* plan, const JacksEmPar
         a.n_work = b.n; a.n_work_dev = nullptr;
         a.work_counter = counters + slot++;
         int grid = 0;
-        e = launch_em_fast(b.G, b.KL, b.W, a, ctx->n_sm, 0, st, &grid);
+        e = launch_em_fast(b.G, b.W, a, ctx->n_sm, 0, st, &grid);
         if (e != cudaSuccess) return cuda_fail(e, "em_fast_kernel launch");
         ctx->launches++;
     }

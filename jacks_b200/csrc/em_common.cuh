@@ -39,14 +39,16 @@ struct EmLaunch {
     double* scratch; long long scratch_stride;   // doubles per warp
 };
 
-// Fast path: compile-time guide count G, KL line-strips per lane, W warps per gene.
-// Returns cudaErrorInvalidValue if (G, KL, W) was not instantiated.
-cudaError_t launch_em_fast(int G, int KL, int W, const EmLaunch& a, int n_sm, int grid_limit, cudaStream_t st,
+// Fast path: compile-time guide count G (1..8), W (1, 2 or 4) warps per gene, finite data only.
+// Returns cudaErrorInvalidValue if (G, W) was not instantiated.
+cudaError_t launch_em_fast(int G, int W, const EmLaunch& a, int n_sm, int grid_limit, cudaStream_t st,
                            int* grid_out);
-// Is (G, KL, W) compiled in?
-bool em_fast_available(int G, int KL, int W);
-// Occupancy (CTAs per SM) of a fast instantiation on the current device, 0 if unavailable.
-int em_fast_occupancy(int G, int KL, int W);
+// Is (G, W) compiled in?
+bool em_fast_available(int G, int W);
+// Bytes of dynamic shared memory one gene team needs (y, tau_pr_den, tau, w1, w2 + reduction buffer).
+size_t em_fast_smem_bytes(int G, int W, int L);
+// Largest dynamic shared memory a CTA may request on sm_100a (227 KB minus the static words we use).
+constexpr size_t kMaxDynSmem = 227 * 1024 - 64;
 
 // Generic path: any G and L, NaN-safe, one warp per gene, working set in shared memory when it
 // fits and in `scratch` (EmLaunch::scratch, one slab per warp of the grid) otherwise.

@@ -1,4 +1,4 @@
-// Fast batched EM kernel: one gene per team of W warps, compile-time guide count G.
+// Fast batched EM kernel: one gene per team (CTA) of W warps, compile-time guide count G.
 //
 // Restates the reference's per-gene loop (jacks/jacks/infer.py:55-99) for finite data:
 //   set-up   y = test - ctrl, tau_pr_den = tps*(sd_t^2 + sd_c^2 + 1e-2)          infer.py:58-70
@@ -8,13 +8,22 @@
 //   X step   infer.py:103-110    W step  infer.py:112-116
 //   tau step infer.py:118-121    bound   infer.py:123-125
 //
-// Data layout.  Each lane owns KL "strips": line l = (k*W + warp')*32 + lane for k < KL.  The
-// gene's y and tau_pr_den blocks ([G][Lp], Lp = KL*W*32) are staged once in shared memory; the
-// evolving state (tau for the lane's G*KL elements, w1/w2 for its KL lines, x1/x2 replicated) lives
-// in registers.  Per EM pass the only cross-lane traffic is ONE all-reduce of 2G+1 doubles: the
-// bound of this pass and the 2G row sums the next X step needs are formed from the same fresh
-// tau in the same sweep.  Lines beyond L are padded with y = 0, tau_pr_den = +inf, which makes
-// every padded element contribute an exact 0 everywhere (tau = 0), so the sweeps need no masks.
+// Layout.  The gene's working set -- y, tau_pr_den, tau as [G][L] and w1, w2 as [L] -- is staged in
+// shared memory once ((3G+2)*L doubles, 44.8 KB at G=4, L=400) and never leaves the SM until the
+// gene has converged.  Lane `lane` of warp `wv` owns lines l = wv*32 + lane + k*32*W; every line's
+// W step, tau step and bound contribution are lane-local (G is a compile-time constant, so the G
+// values of a line sit in registers while the line is processed), and per EM pass there is exactly
+// ONE cross-lane operation: an all-reduce of 2G+1 doubles carrying the bound of this pass and the
+// 2G row sums the next X step needs, both formed from the same fresh tau in the same sweep.
+// The sweep is a rolled loop over lines (a few hundred instructions), so the hot code stays inside
+// the instruction cache; the FP64 pipe is the intended limiter ("EM kernel").
+//
+// Arithmetic notes (all FP64).  b* = y^2 - 2*y*x1*w1 + x2*w2 is formed as fma(y, y - 2*x1*w1,
+// x2*w2); the bound term tau*(y^2 + x2*w2 - 2*x1*w1*y) (infer.py:125) is the same quantity, so it
+// is accumulated as tau*b*.  Reciprocals (1/den of the W step, tau = c/(...)) use MUFU.RCP64H plus
+// a cubic Newton step (<= 1 ulp), not IEEE division: agreement with the reference stays ~1e-13,
+// far inside the 1e-6 tolerance, and the convergence test |d bound| < 0.1 is insensitive to it
+// (closest approach over all reference runs: 6.6e-5).
 //
 // Genes whose y block holds a NaN/inf (missing measurements) are not handled here: the team
 // appends the gene to the deferred queue and the NaN-safe generic kernel (em_generic.cu) runs it.
@@ -29,6 +38,15 @@ __device__ __forceinline__ double warp_allsum(double v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(JACKS_FULL_MASK, v, o);
     return v;
+}
+
+// 1/d for normal, finite d: hardware seed (>= 20 bits) + one cubic step r*(1 + e + e^2), e = 1 - d*r.
+__device__ __forceinline__ double fast_rcp(double d) {
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(d));
+    const double e = fma(-d, r, 1.0);
+    const double t = fma(e, e, e);
+    return fma(r, t, r);
 }
 
 // Median of G finite values held in registers (numpy semantics: mean of the two middle values
@@ -78,25 +96,32 @@ __device__ __forceinline__ void team_allsum(double (&v)[NV], double* red, int& p
     }
 }
 
-template <int G, int KL, int W, int MINB>
-__global__ void __launch_bounds__(W * 32, MINB) em_fast_kernel(const EmLaunch a) {
-    constexpr int Lp = KL * W * 32;
+// Shared-memory doubles of one team: y, tau_pr_den, tau [G][L]; w1, w2 [L]; reduction buffer.
+__host__ __device__ constexpr long long em_fast_smem_doubles(int G, int W, int L) {
+    return (3LL * G + 2) * L + (W > 1 ? 2LL * W * (2 * G + 1) : 0);
+}
+
+template <int G, int W, bool UNIT_C>
+__global__ void __launch_bounds__(W * 32) em_fast_kernel(const EmLaunch a) {
     constexpr int NV = 2 * G + 1;
+    constexpr int STEP = 32 * W;
     extern __shared__ double smem[];
-    double* ys = smem;                 // [G][Lp]
-    double* tpds = smem + G * Lp;      // [G][Lp]
-    double* red = tpds + G * Lp;       // [2][W][NV]   (W > 1 only)
+    const int L = a.L;
+    double* ys = smem;                       // [G][L]
+    double* tpds = ys + (size_t)G * L;       // [G][L]
+    double* taus = tpds + (size_t)G * L;     // [G][L]
+    double* w1s = taus + (size_t)G * L;      // [L]
+    double* w2s = w1s + L;                   // [L]
+    double* red = w2s + L;                   // [2][W][NV]   (W > 1 only)
     __shared__ int s_slot;
 
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
-    const int L = a.L;
     const double tps = a.tps;
     const double c_tau = a.tps + 0.5;            // infer.py:120
     const double ivx = 1.0 / a.var0_x;           // infer.py:104
     const double mx = a.mu0_x / a.var0_x;
     const bool fixed = (a.fixed_x1 != nullptr);
-    const double inf = __longlong_as_double(0x7ff0000000000000LL);
     int parity = 0;
 
     for (;;) {
@@ -114,7 +139,8 @@ __global__ void __launch_bounds__(W * 32, MINB) em_fast_kernel(const EmLaunch a)
         if (slot >= a.n_work) break;
         const int gid = a.gene_ids[slot];
         const long long off = a.gene_offsets[gid];
-        const int wv = (W == 1) ? 0 : (warp + slot) % W;   // rotate the warp that owns the partial strip
+        // rotate which warp owns the (possibly partial) last strip so the SM sub-partitions stay even
+        const int l0 = ((W == 1) ? 0 : ((warp + slot) % W) * 32) + lane;
 
         // ---- stage y and tau_pr_den (infer.py:58-70) ---------------------------------------
         bool bad = false;
@@ -132,32 +158,27 @@ __global__ void __launch_bounds__(W * 32, MINB) em_fast_kernel(const EmLaunch a)
                 c0 = cr[0];
                 if (a.ctrl_rowmean_fill && c0.y != c0.y) {
                     // 1-D control with an undefined sd: row mean of the (NaN -> 2.0) test sds, infer.py:63
-                    double acc = 0.0;
-                    for (int l = threadIdx.x; l < L; l += W * 32) {
-                        double e = tr[l].y;
-                        acc += (e != e) ? 2.0 : e;
+                    double one[1] = {0.0};
+                    for (int l = l0; l < L; l += STEP) {
+                        const double e = tr[l].y;
+                        one[0] += (e != e) ? 2.0 : e;
                     }
-                    double one[1] = {acc};
                     team_allsum<1, NV, W>(one, red, parity, warp, lane);
                     fill = one[0] / (double)L;
                 }
             }
-#pragma unroll
-            for (int k = 0; k < KL; ++k) {
-                const int l = (k * W + wv) * 32 + lane;
-                double yv = 0.0, pd = inf;
-                if (l < L) {
-                    const double2 t = tr[l];
-                    const double2 c = (a.ctrl_lines == 1) ? c0 : cr[l];
-                    const double te = (t.y != t.y) ? 2.0 : t.y;                     // infer.py:58
-                    double ce = c.y;
-                    if (ce != ce) ce = (a.ctrl_lines == 1 && a.ctrl_rowmean_fill) ? fill : te;   // :63 / :68
-                    yv = t.x - c.x;
-                    pd = tps * (te * te + ce * ce + 1e-2);
-                    bad |= !(fabs(yv) < inf) || !(pd == pd);
-                }
-                ys[g * Lp + l] = yv;
-                tpds[g * Lp + l] = pd;
+#pragma unroll 4
+            for (int l = l0; l < L; l += STEP) {
+                const double2 t = tr[l];
+                const double2 c = (a.ctrl_lines == 1) ? c0 : cr[l];
+                const double te = (t.y != t.y) ? 2.0 : t.y;                     // infer.py:58
+                double ce = c.y;
+                if (ce != ce) ce = (a.ctrl_lines == 1 && a.ctrl_rowmean_fill) ? fill : te;   // :63 / :68
+                const double yv = t.x - c.x;
+                const double pd = tps * (te * te + ce * ce + 1e-2);
+                bad |= !(fabs(yv) <= 1.79769313486231570e308) || !(pd <= 1.79769313486231570e308);
+                ys[g * L + l] = yv;
+                tpds[g * L + l] = pd;
             }
         }
         const int any_bad = (W == 1) ? __any_sync(JACKS_FULL_MASK, bad) : __syncthreads_or(bad);
@@ -171,35 +192,25 @@ __global__ void __launch_bounds__(W * 32, MINB) em_fast_kernel(const EmLaunch a)
         // every lane reads back only the shared-memory words it wrote itself: no barrier needed
 
         // ---- initial w, tau, bound and the first X-step sums (infer.py:81-86) --------------
-        double tau_r[KL][G], w1_r[KL], w2_r[KL];
         double acc[NV];
 #pragma unroll
         for (int i = 0; i < NV; ++i) acc[i] = 0.0;
+        for (int l = l0; l < L; l += STEP) {
+            double yv[G];
 #pragma unroll
-        for (int k = 0; k < KL; ++k) {
-            const int s = k * W + wv;
-            w1_r[k] = 0.0; w2_r[k] = 0.0;
-            if (s * 32 < L) {
-                const int l = s * 32 + lane;
-                double yv[G];
+            for (int g = 0; g < G; ++g) yv[g] = ys[g * L + l];
+            const double w1 = median_small<G>(yv);
+            const double w2 = w1 * w1;
 #pragma unroll
-                for (int g = 0; g < G; ++g) yv[g] = ys[g * Lp + l];
-                const double w1 = median_small<G>(yv);
-                const double w2 = w1 * w1;
-#pragma unroll
-                for (int g = 0; g < G; ++g) {
-                    const double t = tps / tpds[g * Lp + l];
-                    tau_r[k][g] = t;
-                    const double xw = x1r[g] * w1;
-                    acc[2 * G] += t * (yv[g] * yv[g] + x2r[g] * w2 - 2.0 * xw * yv[g]);
-                    acc[g] += yv[g] * t * w1;
-                    acc[G + g] += t * w2;
-                }
-                w1_r[k] = w1; w2_r[k] = w2;
-            } else {
-#pragma unroll
-                for (int g = 0; g < G; ++g) tau_r[k][g] = 0.0;
+            for (int g = 0; g < G; ++g) {
+                const double t = tps / tpds[g * L + l];
+                taus[g * L + l] = t;
+                const double xw = x1r[g] * w1;
+                acc[2 * G] += t * (yv[g] * yv[g] + x2r[g] * w2 - 2.0 * xw * yv[g]);
+                acc[g] += yv[g] * t * w1;
+                acc[G + g] += t * w2;
             }
+            w1s[l] = w1; w2s[l] = w2;
         }
         team_allsum<NV, NV, W>(acc, red, parity, warp, lane);
         double bound = acc[2 * G];
@@ -214,9 +225,9 @@ __global__ void __launch_bounds__(W * 32, MINB) em_fast_kernel(const EmLaunch a)
                 double s1 = acc[0], s2 = acc[G];
 #pragma unroll
                 for (int g = 1; g < G; ++g) if (lane == g) { s1 = acc[g]; s2 = acc[G + g]; }
-                const double den = s2 + ivx;
-                const double x1u = (mx + s1) / den;
-                const double x2u = x1u * x1u + 1.0 / den;
+                const double rden = fast_rcp(s2 + ivx);
+                const double x1u = (mx + s1) * rden;
+                const double x2u = fma(x1u, x1u, rden);
                 double xa[G];
 #pragma unroll
                 for (int g = 0; g < G; ++g) xa[g] = __shfl_sync(JACKS_FULL_MASK, x1u, g);
@@ -224,9 +235,10 @@ __global__ void __launch_bounds__(W * 32, MINB) em_fast_kernel(const EmLaunch a)
 #pragma unroll
                 for (int g = 1; g < G; ++g) { sum += xa[g]; hi = fmax(hi, xa[g]); lo = fmin(lo, xa[g]); }
                 const double wadj = 0.5 / G;
-                const double x1m = sum / G + 2 * wadj * median_small<G>(xa) - wadj * hi - wadj * lo;
-                const double x1n = x1u / x1m;
-                const double x2n = x2u / x1m / x1m;
+                const double x1m = sum * (1.0 / G) + 2 * wadj * median_small<G>(xa) - wadj * hi - wadj * lo;
+                const double rm = 1.0 / x1m;         // x1m may be tiny or negative: IEEE division
+                const double x1n = x1u * rm;
+                const double x2n = x2u * rm * rm;
 #pragma unroll
                 for (int g = 0; g < G; ++g) {
                     x1r[g] = __shfl_sync(JACKS_FULL_MASK, x1n, g);
@@ -236,19 +248,11 @@ __global__ void __launch_bounds__(W * 32, MINB) em_fast_kernel(const EmLaunch a)
             if (a.apply_w_hp && L > 1) {
                 // hierarchical prior from the current w1, infer.py:92 (population variance)
                 double m[1] = {0.0};
-#pragma unroll
-                for (int k = 0; k < KL; ++k) {
-                    const int l = (k * W + wv) * 32 + lane;
-                    if (l < L) m[0] += w1_r[k];
-                }
+                for (int l = l0; l < L; l += STEP) m[0] += w1s[l];
                 team_allsum<1, NV, W>(m, red, parity, warp, lane);
                 const double mean = m[0] / (double)L;
                 double v[1] = {0.0};
-#pragma unroll
-                for (int k = 0; k < KL; ++k) {
-                    const int l = (k * W + wv) * 32 + lane;
-                    if (l < L) { const double d = w1_r[k] - mean; v[0] += d * d; }
-                }
+                for (int l = l0; l < L; l += STEP) { const double d = w1s[l] - mean; v[0] += d * d; }
                 team_allsum<1, NV, W>(v, red, parity, warp, lane);
                 mu0_w = mean;
                 var0_w = (v[0] / (double)L) * 3 + 1e-4;
@@ -257,39 +261,35 @@ __global__ void __launch_bounds__(W * 32, MINB) em_fast_kernel(const EmLaunch a)
             const double mw = mu0_w / var0_w;
 #pragma unroll
             for (int i = 0; i < NV; ++i) acc[i] = 0.0;
+#pragma unroll 2
+            for (int l = l0; l < L; l += STEP) {
+                double yv[G], tv[G];
 #pragma unroll
-            for (int k = 0; k < KL; ++k) {
-                const int s = k * W + wv;
-                if (s * 32 < L) {
-                    const int l = s * 32 + lane;
-                    double yv[G];
-                    double sa = 0.0, sb = 0.0;
-                    // W step for this line, infer.py:112-116 (old tau, new x)
+                for (int g = 0; g < G; ++g) { yv[g] = ys[g * L + l]; tv[g] = taus[g * L + l]; }
+                // W step for this line, infer.py:112-116 (old tau, new x)
+                double sa = ivw, sb = mw;
 #pragma unroll
-                    for (int g = 0; g < G; ++g) {
-                        yv[g] = ys[g * Lp + l];
-                        const double t = tau_r[k][g];
-                        sa += x2r[g] * t;
-                        sb += x1r[g] * (yv[g] * t);
-                    }
-                    const double den = sa + ivw;
-                    const double w1 = (mw + sb) / den;
-                    const double w2 = w1 * w1 + 1.0 / den;
-                    // tau step (infer.py:118-121), bound (infer.py:123-125) and next X-step sums
-#pragma unroll
-                    for (int g = 0; g < G; ++g) {
-                        const double xw = x1r[g] * w1;
-                        const double xw2 = x2r[g] * w2;
-                        const double y2 = yv[g] * yv[g];
-                        const double bstar = y2 - 2 * yv[g] * xw + xw2;
-                        const double t = c_tau / (tpds[g * Lp + l] + 0.5 * bstar);
-                        tau_r[k][g] = t;
-                        acc[2 * G] += t * (y2 + xw2 - 2 * xw * yv[g]);
-                        acc[g] += yv[g] * t * w1;
-                        acc[G + g] += t * w2;
-                    }
-                    w1_r[k] = w1; w2_r[k] = w2;
+                for (int g = 0; g < G; ++g) {
+                    sa = fma(x2r[g], tv[g], sa);
+                    sb = fma(x1r[g], yv[g] * tv[g], sb);
                 }
+                const double r = fast_rcp(sa);
+                const double w1 = sb * r;
+                const double w2 = fma(w1, w1, r);
+                const double m2w1 = -2.0 * w1;
+                // tau step (infer.py:118-121), bound (infer.py:123-125) and next X-step sums
+#pragma unroll
+                for (int g = 0; g < G; ++g) {
+                    const double t1 = fma(x1r[g], m2w1, yv[g]);            // y - 2*x1*w1
+                    const double bstar = fma(yv[g], t1, x2r[g] * w2);      // y^2 - 2*y*x1*w1 + x2*w2
+                    const double rd = fast_rcp(fma(0.5, bstar, tpds[g * L + l]));
+                    const double t = UNIT_C ? rd : c_tau * rd;
+                    taus[g * L + l] = t;
+                    acc[2 * G] = fma(t, bstar, acc[2 * G]);
+                    acc[g] = fma(yv[g] * t, w1, acc[g]);
+                    acc[G + g] = fma(t, w2, acc[G + g]);
+                }
+                w1s[l] = w1; w2s[l] = w2;
             }
             team_allsum<NV, NV, W>(acc, red, parity, warp, lane);
             bound = acc[2 * G];
@@ -298,20 +298,16 @@ __global__ void __launch_bounds__(W * 32, MINB) em_fast_kernel(const EmLaunch a)
         }
 
         // ---- write results ------------------------------------------------------------------
+        for (int l = l0; l < L; l += STEP) {
+            a.w1[(long long)gid * L + l] = w1s[l];
+            if (a.w2) a.w2[(long long)gid * L + l] = w2s[l];
+            if (a.tau) {
 #pragma unroll
-        for (int k = 0; k < KL; ++k) {
-            const int l = (k * W + wv) * 32 + lane;
-            if (l < L) {
-                a.w1[(long long)gid * L + l] = w1_r[k];
-                if (a.w2) a.w2[(long long)gid * L + l] = w2_r[k];
-                if (a.tau) {
+                for (int g = 0; g < G; ++g) a.tau[(off + g) * L + l] = taus[g * L + l];
+            }
+            if (a.y) {
 #pragma unroll
-                    for (int g = 0; g < G; ++g) a.tau[(off + g) * L + l] = tau_r[k][g];
-                }
-                if (a.y) {
-#pragma unroll
-                    for (int g = 0; g < G; ++g) a.y[(off + g) * L + l] = ys[g * Lp + l];
-                }
+                for (int g = 0; g < G; ++g) a.y[(off + g) * L + l] = ys[g * L + l];
             }
         }
         if (warp == 0) {
@@ -328,11 +324,6 @@ __global__ void __launch_bounds__(W * 32, MINB) em_fast_kernel(const EmLaunch a)
             }
         }
     }
-}
-
-template <int G, int KL, int W>
-constexpr size_t em_fast_smem_bytes() {
-    return (size_t)(2 * G * KL * W * 32 + (W > 1 ? 2 * W * (2 * G + 1) : 0)) * sizeof(double);
 }
 
 }  // namespace jacks

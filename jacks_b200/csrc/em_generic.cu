@@ -311,6 +311,9 @@ cudaError_t em_generic_configure(int maxG, int L, long long n_work_cap, int n_sm
 }
 
 cudaError_t launch_em_generic(const EmGenericConfig& cfg, const EmLaunch& a, cudaStream_t st) {
+    // the attribute is per kernel, and two configurations (generic bucket, deferred queue) share it
+    cudaError_t e = cudaFuncSetAttribute(em_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg.smem_bytes);
+    if (e != cudaSuccess) return e;
     em_generic_kernel<<<cfg.grid, cfg.warps_per_cta * 32, cfg.smem_bytes, st>>>(a, cfg.warps_per_cta,
                                                                                cfg.smem_doubles_per_warp);
     return cudaGetLastError();

@@ -150,11 +150,11 @@ def test_avana_shape_vs_reference_golden(nat):
     gene_index, testdata, ctrldata, _ = synth.make_condensed_screen(n_genes=48, n_ctrl_genes=8)
     names, offs, rows = nat.as_csr(gene_index)
     problems = []
-    for shape in (None, '13,1', '7,2', '4,4'):
+    for shape in (None, '1', '2', '4'):
         if shape is None:
-            os.environ.pop('JACKS_EM_SHAPE', None)
+            os.environ.pop('JACKS_EM_W', None)
         else:
-            os.environ['JACKS_EM_SHAPE'] = shape
+            os.environ['JACKS_EM_W'] = shape
         try:
             r = run(nat, offs, rows, testdata, ctrldata)
             if r['n_iters'].tolist() != z['iters'].tolist():
@@ -177,7 +177,7 @@ def test_avana_shape_vs_reference_golden(nat):
                 if not ok:
                     problems.append((shape, 'fixed_x', k, worst))
         finally:
-            os.environ.pop('JACKS_EM_SHAPE', None)
+            os.environ.pop('JACKS_EM_W', None)
     report(problems)
 
 

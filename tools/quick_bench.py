@@ -14,7 +14,7 @@ from jacks_b200 import _native, synth
 def main():
     n_genes = int(os.environ.get('QB_GENES', 18000))
     n_pseudo = int(os.environ.get('QB_PSEUDO', 100000))
-    shapes = os.environ.get('QB_SHAPES', 'default;13,1;7,2;4,4').split(';')
+    shapes = os.environ.get('QB_SHAPES', 'default;1;2;4').split(';')
     dev = torch.device('cuda:0')
     ctx = _native.context(0)
     print('fp64 peak TFLOP/s', ctx.fp64_peak_flops() / 1e12, flush=True)
@@ -39,9 +39,9 @@ def main():
     stream = torch.cuda.current_stream().cuda_stream
     for shape in shapes:
         if shape == 'default':
-            os.environ.pop('JACKS_EM_SHAPE', None)
+            os.environ.pop('JACKS_EM_W', None)
         else:
-            os.environ['JACKS_EM_SHAPE'] = shape
+            os.environ['JACKS_EM_W'] = shape
         plan = _native.EmPlan(ctx, aoffs, arows, N, L)
         io = _native.EmDeviceIO()
         io.test, io.ctrl, io.ctrl_lines = d_test.data_ptr(), d_ctrl.data_ptr(), L
