@@ -59,14 +59,15 @@ struct EmBucket {
     int G;            // guide count (fast buckets); 0 for the generic bucket
     int W;            // warps per gene of the fast kernel
     int n;            // genes in the bucket
-    int ids_off;      // offset into JacksEmPlan::d_ids
+    int ids_off;      // offset into JacksEmPlan::d_ids / d_slot_off
+    long long rows_off;   // offset into JacksEmPlan::d_slot_rows (fast buckets)
 };
 
 struct JacksEmPlan {
     JacksCtx* ctx;
     int64_t n_genes, n_rows, total_guides;
     int L;
-    DevBuf d_offsets, d_rows, d_ids, d_deferred, d_counters, d_scratch;
+    DevBuf d_offsets, d_rows, d_ids, d_slot_off, d_slot_rows, d_deferred, d_counters, d_scratch;
     std::vector<EmBucket> fast;
     EmBucket generic;          // n == 0 if empty
     int generic_maxG;
@@ -183,7 +184,7 @@ int jacks_em_plan_create(JacksCtx* ctx, const int64_t* gene_offsets, const int32
 
     JacksEmPlan* p = new JacksEmPlan();
     p->ctx = ctx; p->n_genes = n_genes; p->n_rows = n_rows; p->total_guides = total; p->L = n_lines;
-    p->generic = EmBucket{0, 0, 0, 0};
+    p->generic = EmBucket{0, 0, 0, 0, 0};
     p->generic_maxG = 0; p->fast_maxG = 0; p->n_fast_genes = 0;
 
     // bucket genes by guide count, keeping the caller's order inside each bucket
@@ -198,17 +199,25 @@ int jacks_em_plan_create(JacksCtx* ctx, const int64_t* gene_offsets, const int32
     }
     std::vector<int> ids;
     ids.reserve((size_t)n_genes);
+    std::vector<long long> slot_off;       // gene_offsets[] in bucket-slot order
+    std::vector<int> slot_rows;            // guide rows in bucket-slot order (fast buckets)
+    slot_off.reserve((size_t)n_genes);
+    slot_rows.reserve((size_t)total);
     // larger G first: the heavier buckets start while the GPU is empty
     for (int G = 8; G >= 1; --G) {
         if (byG[G].empty()) continue;
-        EmBucket b{G, teamW[G], (int)byG[G].size(), (int)ids.size()};
+        EmBucket b{G, teamW[G], (int)byG[G].size(), (int)ids.size(), (long long)slot_rows.size()};
         ids.insert(ids.end(), byG[G].begin(), byG[G].end());
+        for (int g : byG[G]) {
+            slot_off.push_back(gene_offsets[g]);
+            for (int k = 0; k < G; ++k) slot_rows.push_back(guide_rows[gene_offsets[g] + k]);
+        }
         p->fast.push_back(b);
         p->fast_maxG = std::max(p->fast_maxG, G);
         p->n_fast_genes += b.n;
     }
     if (!gen.empty()) {
-        p->generic = EmBucket{0, 0, (int)gen.size(), (int)ids.size()};
+        p->generic = EmBucket{0, 0, (int)gen.size(), (int)ids.size(), 0};
         ids.insert(ids.end(), gen.begin(), gen.end());
     }
 
@@ -224,6 +233,8 @@ int jacks_em_plan_create(JacksCtx* ctx, const int64_t* gene_offsets, const int32
     up(p->d_offsets, gene_offsets, (size_t)(n_genes + 1) * sizeof(int64_t));
     up(p->d_rows, guide_rows, (size_t)total * sizeof(int32_t));
     up(p->d_ids, ids.data(), ids.size() * sizeof(int));
+    up(p->d_slot_off, slot_off.data(), slot_off.size() * sizeof(long long));
+    up(p->d_slot_rows, slot_rows.data(), slot_rows.size() * sizeof(int));
     if (rc == JACKS_OK) rc = p->d_deferred.reserve((size_t)std::max<int64_t>(n_genes, 1) * sizeof(int));
     if (rc == JACKS_OK) rc = p->d_counters.reserve(64 * sizeof(int));
     // generic kernel configurations (and global scratch if a gene's working set exceeds shared memory)
@@ -253,7 +264,8 @@ int jacks_em_plan_create(JacksCtx* ctx, const int64_t* gene_offsets, const int32
 void jacks_em_plan_destroy(JacksEmPlan* p) {
     if (!p) return;
     cudaSetDevice(p->ctx->device);
-    p->d_offsets.release(); p->d_rows.release(); p->d_ids.release(); p->d_deferred.release();
+    p->d_offsets.release(); p->d_rows.release(); p->d_ids.release(); p->d_slot_off.release();
+    p->d_slot_rows.release(); p->d_deferred.release();
     p->d_counters.release(); p->d_scratch.release();
     delete p;
 }
@@ -291,6 +303,8 @@ int jacks_em_run_device(JacksCtx* ctx, const JacksEmPlan* plan, const JacksEmPar
     int slot = 1;
     for (const EmBucket& b : plan->fast) {
         a.gene_ids = (const int*)plan->d_ids.p + b.ids_off;
+        a.slot_off = (const long long*)plan->d_slot_off.p + b.ids_off;
+        a.slot_rows = (const int*)plan->d_slot_rows.p + b.rows_off;
         a.n_work = b.n; a.n_work_dev = nullptr;
         a.work_counter = counters + slot++;
         int grid = 0;

@@ -19,6 +19,8 @@ struct EmLaunch {
     const long long* gene_offsets;  // [n_genes+1] CSR
     const int* guide_rows;        // [sum G]
     const int* gene_ids;          // [n_work] genes of this bucket (indices into the CSR)
+    const long long* slot_off;    // [n_work] gene_offsets[gene_ids[slot]]      (fast kernels)
+    const int* slot_rows;         // [n_work][G] guide rows of the bucket's genes (fast kernels)
     int n_work;
     const int* n_work_dev;        // if non-null the work count is read from here (deferred queue)
     const double* fixed_x1;       // by row, or null

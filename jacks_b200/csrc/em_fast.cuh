@@ -49,12 +49,29 @@ __device__ __forceinline__ double fast_rcp(double d) {
     return fma(r, t, r);
 }
 
-// Median of G finite values held in registers (numpy semantics: mean of the two middle values
-// for even G).  Rank selection with index tie-break, O(G^2) compares, no data movement.
+// Median of G finite values held in registers (numpy semantics: mean of the two middle values for
+// even G).  G <= 5 use min/max networks (the median stays an exact element / exact pair mean);
+// larger G use rank selection with index tie-break, O(G^2) compares, no data movement.
 template <int G>
 __device__ __forceinline__ double median_small(const double (&v)[G]) {
     if (G == 1) return v[0];
     if (G == 2) return 0.5 * (v[0] + v[1]);
+    if (G == 3) return fmax(fmin(v[0], v[1]), fmin(fmax(v[0], v[1]), v[2]));
+    if (G == 4) {
+        const double lo1 = fmin(v[0], v[1]), hi1 = fmax(v[0], v[1]);
+        const double lo2 = fmin(v[2], v[3]), hi2 = fmax(v[2], v[3]);
+        return 0.5 * (fmax(lo1, lo2) + fmin(hi1, hi2));
+    }
+    if (G == 5) {
+        // median of five in 6 compare-exchange layers
+        double a = fmin(v[0], v[1]), b = fmax(v[0], v[1]);
+        double c = fmin(v[2], v[3]), d = fmax(v[2], v[3]);
+        const double lo = fmax(a, c);         // drop the smaller of the two minima
+        const double hi = fmin(b, d);         // drop the larger of the two maxima
+        // median of {lo, hi, v[4]} -- lo and hi may be in either order
+        const double p = fmin(lo, hi), q = fmax(lo, hi);
+        return fmax(p, fmin(q, v[4]));
+    }
     const int k_lo = (G - 1) / 2, k_hi = G / 2;
     double lo = v[0], hi = v[0];
 #pragma unroll
@@ -71,34 +88,249 @@ __device__ __forceinline__ double median_small(const double (&v)[G]) {
     return (k_lo == k_hi) ? lo : 0.5 * (lo + hi);
 }
 
-// All-reduce of NV doubles over the team (W warps).  Every thread of the team ends up with
-// bit-identical sums (xor butterfly inside the warp, fixed-order sum over warps), which keeps the
-// convergence test uniform.  `red` is a [2][W][NV_MAX] shared buffer, `parity` flips per call.
+// All-reduce of NV doubles over the team (W warps); every thread ends up with bit-identical sums
+// (fixed summation order), which keeps the convergence test uniform.
+// A butterfly over 32 lanes costs 5*NV shuffle pairs + 5*NV DADDs plus register moves (~320
+// instructions at NV = 9) of mostly exposed latency for a lone warp.  Instead the lanes park their
+// partials in a padded [NV][33] shared tile, H = 1, 2 or 4 lanes per value sum 32/H of them, one or
+// two shuffles finish the value, and the NV totals are broadcast back through shared memory:
+// ~60 instructions.  `scr`: this warp's [NV_MAX][33] tile; `tot`: [2][W][NV_MAX]; `parity` flips per call.
 template <int NV, int NV_MAX, int W>
-__device__ __forceinline__ void team_allsum(double (&v)[NV], double* red, int& parity, int warp, int lane) {
+__device__ __forceinline__ void team_allsum(double (&v)[NV], double* scr, double* tot, int& parity, int warp, int lane) {
+    constexpr int H = (NV <= 8) ? 4 : ((NV <= 16) ? 2 : 1);
+    constexpr int CH = 32 / H;
 #pragma unroll
-    for (int i = 0; i < NV; ++i) v[i] = warp_allsum(v[i]);
-    if (W > 1) {
-        double* buf = red + parity * (W * NV_MAX);
-        if (lane == 0) {
+    for (int i = 0; i < NV; ++i) scr[i * 33 + lane] = v[i];
+    __syncwarp();
+    const int q = (H == 4) ? (lane & 7) : ((H == 2) ? (lane & 15) : lane);
+    const int h = (H == 4) ? (lane >> 3) : ((H == 2) ? (lane >> 4) : 0);
+    double s0 = 0.0, s1 = 0.0;
+    if (q < NV) {
+        const double* row = scr + q * 33 + h * CH;
 #pragma unroll
-            for (int i = 0; i < NV; ++i) buf[warp * NV_MAX + i] = v[i];
-        }
-        __syncthreads();
-#pragma unroll
-        for (int i = 0; i < NV; ++i) {
-            double s = buf[i];
-#pragma unroll
-            for (int w = 1; w < W; ++w) s += buf[w * NV_MAX + i];
-            v[i] = s;
-        }
-        parity ^= 1;
+        for (int k = 0; k < CH; k += 2) { s0 += row[k]; s1 += row[k + 1]; }
     }
+    s0 += s1;
+    if (H >= 2) s0 += __shfl_xor_sync(JACKS_FULL_MASK, s0, (H == 4) ? 8 : 16);
+    if (H == 4) s0 += __shfl_xor_sync(JACKS_FULL_MASK, s0, 16);
+    double* mine = tot + parity * (W * NV_MAX) + warp * NV_MAX;
+    if (q < NV && h == 0) mine[q] = s0;
+    if (W > 1) __syncthreads(); else __syncwarp();
+    const double* all = tot + parity * (W * NV_MAX);
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        double s = all[i];
+#pragma unroll
+        for (int w = 1; w < W; ++w) s += all[w * NV_MAX + i];
+        v[i] = s;
+    }
+    parity ^= 1;
+}
+
+// One sweep step over U lines of a lane (l, l+step, ...): W step, tau step, bound and next-X sums.
+// Written stage by stage over the U*G independent elements so that consecutive instructions are
+// independent (a dependent DFMA issues every ~9 cycles on sm_100a, an independent one every 2):
+// with U*G >= 8 each stage is long enough to cover the latency of the previous one.
+//
+// MASKED: the step's last line (u = U-1) may lie beyond L for some lanes (`valid` false).  Those
+// lanes still execute the arithmetic on whatever the shared-memory words past the line hold (the
+// allocation carries one step of slack, see em_fast_smem_doubles), but neither store nor
+// accumulate it: the stores and the three accumulating FMAs of that line are predicated.
+template <int G, int U, bool UNIT_C, bool MASKED>
+__device__ __forceinline__ void em_sweep(const double* __restrict__ ys, const double* __restrict__ tpds,
+                                         double* __restrict__ taus, double* __restrict__ w1s,
+                                         double* __restrict__ w2g, const int L, const int l, const int step,
+                                         const double (&x1r)[G], const double (&x2r)[G], const double ivw,
+                                         const double mw, const double c_tau, double (&a1)[G], double (&a2)[G],
+                                         double (&ab)[G], const bool valid) {
+    double yv[U][G], tv[U][G], pd[U][G];
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+#pragma unroll
+        for (int g = 0; g < G; ++g) {
+            yv[u][g] = ys[g * L + l + u * step];
+            tv[u][g] = taus[g * L + l + u * step];
+        }
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+#pragma unroll
+        for (int g = 0; g < G; ++g) pd[u][g] = tpds[g * L + l + u * step];
+    // W step, infer.py:112-116 (old tau, new x): den = 1/var0_w + sum_g x2*tau, num = mu0_w/var0_w + sum_g x1*y*tau
+    double yt[U][G];
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+#pragma unroll
+        for (int g = 0; g < G; ++g) yt[u][g] = yv[u][g] * tv[u][g];
+    double sa[U], sb[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) { sa[u] = ivw; sb[u] = mw; }
+#pragma unroll
+    for (int g = 0; g < G; ++g)
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            sa[u] = fma(x2r[g], tv[u][g], sa[u]);
+            sb[u] = fma(x1r[g], yt[u][g], sb[u]);
+        }
+    double r[U], e[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r[u]) : "d"(sa[u]));
+#pragma unroll
+    for (int u = 0; u < U; ++u) e[u] = fma(-sa[u], r[u], 1.0);
+#pragma unroll
+    for (int u = 0; u < U; ++u) e[u] = fma(e[u], e[u], e[u]);
+#pragma unroll
+    for (int u = 0; u < U; ++u) r[u] = fma(r[u], e[u], r[u]);
+    double w1[U], w2[U], m2w1[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) w1[u] = sb[u] * r[u];
+#pragma unroll
+    for (int u = 0; u < U; ++u) { w2[u] = fma(w1[u], w1[u], r[u]); m2w1[u] = -2.0 * w1[u]; }
+    // tau step, infer.py:118-121: b* = y^2 - 2*y*x1*w1 + x2*w2 ; tau = c / (tau_pr_den + b*/2)
+    double bs[U][G], d[U][G], rd[U][G], ee[U][G];
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+#pragma unroll
+        for (int g = 0; g < G; ++g) { d[u][g] = fma(x1r[g], m2w1[u], yv[u][g]); bs[u][g] = x2r[g] * w2[u]; }
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+#pragma unroll
+        for (int g = 0; g < G; ++g) bs[u][g] = fma(yv[u][g], d[u][g], bs[u][g]);
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+#pragma unroll
+        for (int g = 0; g < G; ++g) d[u][g] = fma(0.5, bs[u][g], pd[u][g]);
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+#pragma unroll
+        for (int g = 0; g < G; ++g) asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(rd[u][g]) : "d"(d[u][g]));
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+#pragma unroll
+        for (int g = 0; g < G; ++g) ee[u][g] = fma(-d[u][g], rd[u][g], 1.0);
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+#pragma unroll
+        for (int g = 0; g < G; ++g) ee[u][g] = fma(ee[u][g], ee[u][g], ee[u][g]);
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+#pragma unroll
+        for (int g = 0; g < G; ++g) {
+            rd[u][g] = fma(rd[u][g], ee[u][g], rd[u][g]);
+            if (!UNIT_C) rd[u][g] *= c_tau;
+        }
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+#pragma unroll
+        for (int g = 0; g < G; ++g)
+            if (!MASKED || u < U - 1 || valid) taus[g * L + l + u * step] = rd[u][g];
+    // bound (infer.py:123-125: tau*(y^2 + x2*w2 - 2*x1*w1*y) = tau*b*) and the next X step's row sums
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+#pragma unroll
+        for (int g = 0; g < G; ++g) {
+            if (!MASKED || u < U - 1 || valid) ab[g] = fma(rd[u][g], bs[u][g], ab[g]);
+            yt[u][g] = yv[u][g] * rd[u][g];
+        }
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+#pragma unroll
+        for (int g = 0; g < G; ++g) {
+            if (!MASKED || u < U - 1 || valid) {
+                a1[g] = fma(yt[u][g], w1[u], a1[g]);
+                a2[g] = fma(rd[u][g], w2[u], a2[g]);
+            }
+        }
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+        if (!MASKED || u < U - 1 || valid) {
+            w1s[l + u * step] = w1[u];
+            if (w2g) w2g[l + u * step] = w2[u];      // E[w^2] is write-only state: straight to the output row
+        }
+}
+
+// Guide efficacies as the sweep consumes them, and the sums it returns (register-passed structs).
+template <int G> struct EmX { double x1[G], x2[G]; };
+template <int G> struct EmSums { double a1[G], a2[G], ab; };
+
+// One EM pass over all lines of a warp.  Deliberately NOT inlined: compiled on its own, ptxas
+// interleaves the U*G independent element chains of a step (a lone warp then keeps the FP64 pipe
+// ~75 % busy, tools/sass_sim.py); inlined into the kernel it serialises them line by line.
+// The step plan is warp-uniform (no divergence): `n` = lines of the warp's fullest lane, taken
+// U at a time while more than U remain, then one final MASKED step of 1..U lines whose last line
+// is live only in the lanes with l < L.
+template <int G, int STEP, bool UNIT_C>
+__device__ __noinline__ EmSums<G> em_sweep_all(const double* ys, const double* tpds, double* taus, double* w1s,
+                                               double* w2g, const int L, const int l0, const int n_warp,
+                                               const EmX<G> x, const double ivw, const double mw,
+                                               const double c_tau) {
+    double a1[G], a2[G], ab[G];
+#pragma unroll
+    for (int g = 0; g < G; ++g) { a1[g] = 0.0; a2[g] = 0.0; ab[g] = 0.0; }
+    constexpr int U = (G >= 7) ? 2 : 4;       // lines per step: U*G >= 8 independent elements
+    int l = l0;
+    int n = n_warp;
+    for (; n > U; n -= U, l += U * STEP)
+        em_sweep<G, U, UNIT_C, false>(ys, tpds, taus, w1s, w2g, L, l, STEP, x.x1, x.x2, ivw, mw, c_tau, a1, a2, ab, true);
+    const bool valid = (l + (n - 1) * STEP) < L;
+    if (n == 1) em_sweep<G, 1, UNIT_C, true>(ys, tpds, taus, w1s, w2g, L, l, STEP, x.x1, x.x2, ivw, mw, c_tau, a1, a2, ab, valid);
+    else if (n == 2) em_sweep<G, 2, UNIT_C, true>(ys, tpds, taus, w1s, w2g, L, l, STEP, x.x1, x.x2, ivw, mw, c_tau, a1, a2, ab, valid);
+    else if (U == 4 && n == 3) em_sweep<G, (U == 4 ? 3 : 1), UNIT_C, true>(ys, tpds, taus, w1s, w2g, L, l, STEP, x.x1, x.x2, ivw, mw, c_tau, a1, a2, ab, valid);
+    else if (U == 4 && n == 4) em_sweep<G, (U == 4 ? 4 : 1), UNIT_C, true>(ys, tpds, taus, w1s, w2g, L, l, STEP, x.x1, x.x2, ivw, mw, c_tau, a1, a2, ab, valid);
+    EmSums<G> r;
+    r.ab = ab[0];
+#pragma unroll
+    for (int g = 1; g < G; ++g) r.ab += ab[g];
+#pragma unroll
+    for (int g = 0; g < G; ++g) { r.a1[g] = a1[g]; r.a2[g] = a2[g]; }
+    return r;
+}
+
+// Stage one guide row: y = test - ctrl and tau_pr_den (infer.py:58-70) for the lane's lines.
+// Not inlined (one copy serves the G rows; it runs once per gene).  Returns true if a staged value
+// is not finite.
+template <int STEP>
+__device__ __noinline__ bool em_stage_row(const double2* __restrict__ tr, const double2* __restrict__ cr,
+                                          double* __restrict__ ys_g, double* __restrict__ tpds_g, const int L,
+                                          const int l0, const int ctrl_lines, const int rowmean_fill,
+                                          const double fill, const double tps) {
+    bool bad = false;
+    double2 c0 = make_double2(0.0, 0.0);
+    if (ctrl_lines == 1) c0 = cr[0];
+#pragma unroll 4
+    for (int l = l0; l < L; l += STEP) {
+        const double2 t = tr[l];
+        const double2 c = (ctrl_lines == 1) ? c0 : cr[l];
+        const double te = (t.y != t.y) ? 2.0 : t.y;                     // infer.py:58
+        double ce = c.y;
+        if (ce != ce) ce = (ctrl_lines == 1 && rowmean_fill) ? fill : te;   // :63 / :68
+        const double yv = t.x - c.x;
+        const double pd = tps * (te * te + ce * ce + 1e-2);
+        bad |= !(fabs(yv) <= 1.79769313486231570e308) || !(pd <= 1.79769313486231570e308);
+        ys_g[l] = yv;
+        tpds_g[l] = pd;
+    }
+    return bad;
 }
 
 // Shared-memory doubles of one team: y, tau_pr_den, tau [G][L]; w1, w2 [L]; reduction buffer.
+// One step of slack (32*W doubles) follows w2 so that the masked last line of a sweep may READ past
+// L without leaving the allocation (it never writes there).
 __host__ __device__ constexpr long long em_fast_smem_doubles(int G, int W, int L) {
-    return (3LL * G + 2) * L + (W > 1 ? 2LL * W * (2 * G + 1) : 0);
+    return (3LL * G + 1) * L + 32LL * W        /* y, tau_pr_den, tau, w1 + read slack */
+           + (long long)W * (2 * G + 1) * 33   /* reduction tiles */
+           + 2LL * W * (2 * G + 1);            /* reduction totals, double buffered */
+}
+
+// L2 prefetch of one guide row pair (test + control) of the gene a team will run next.
+__device__ __forceinline__ void prefetch_row_l2(const double2* tr, const double2* cr, int L, int ctrl_lines,
+                                                int tid, int nthreads) {
+    const char* pt = reinterpret_cast<const char*>(tr);
+    const int nbytes = L * 16;
+    for (int b = tid * 128; b < nbytes; b += nthreads * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(pt + b));
+    if (ctrl_lines > 1) {
+        const char* pc = reinterpret_cast<const char*>(cr);
+        for (int b = tid * 128; b < nbytes; b += nthreads * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(pc + b));
+    }
 }
 
 template <int G, int W, bool UNIT_C>
@@ -111,9 +343,9 @@ __global__ void __launch_bounds__(W * 32) em_fast_kernel(const EmLaunch a) {
     double* tpds = ys + (size_t)G * L;       // [G][L]
     double* taus = tpds + (size_t)G * L;     // [G][L]
     double* w1s = taus + (size_t)G * L;      // [L]
-    double* w2s = w1s + L;                   // [L]
-    double* red = w2s + L;                   // [2][W][NV]   (W > 1 only)
-    __shared__ int s_slot;
+    double* scr = w1s + L + 32 * W + (threadIdx.x >> 5) * (NV * 33);   // this warp's reduction tile, after the read slack
+    double* red = w1s + L + 32 * W + W * (NV * 33);                    // [2][W][NV] totals
+    __shared__ int s_slot[2];
 
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
@@ -124,205 +356,217 @@ __global__ void __launch_bounds__(W * 32) em_fast_kernel(const EmLaunch a) {
     const bool fixed = (a.fixed_x1 != nullptr);
     int parity = 0;
 
-    for (;;) {
-        // ---- fetch the next gene of this bucket --------------------------------------------
-        int slot;
+    // Work distribution: teams pull bucket slots from a global counter one gene AHEAD of the one they
+    // are computing.  The atomic is issued at the top of a gene and consumed after its staging phase;
+    // the next gene's index entries are loaded then and consumed after the init phase, where an L2
+    // prefetch of its rows is issued -- a team has only its own warps to hide latency behind.
+    int slot, gid = 0, rows[G];
+    long long off = 0;
+    {
+        int first = 0;
         if (W == 1) {
-            slot = 0;
-            if (lane == 0) slot = atomicAdd(a.work_counter, 1);
-            slot = __shfl_sync(JACKS_FULL_MASK, slot, 0);
+            if (lane == 0) first = atomicAdd(a.work_counter, 1);
+            first = __shfl_sync(JACKS_FULL_MASK, first, 0);
         } else {
-            if (threadIdx.x == 0) s_slot = atomicAdd(a.work_counter, 1);
+            if (threadIdx.x == 0) s_slot[0] = atomicAdd(a.work_counter, 1);
             __syncthreads();
-            slot = s_slot;
+            first = s_slot[0];
         }
-        if (slot >= a.n_work) break;
-        const int gid = a.gene_ids[slot];
-        const long long off = a.gene_offsets[gid];
+        slot = first;
+        if (slot < a.n_work) {
+            gid = a.gene_ids[slot];
+            off = a.slot_off[slot];
+#pragma unroll
+            for (int g = 0; g < G; ++g) rows[g] = a.slot_rows[(long long)slot * G + g];
+        }
+    }
+    int pipe = 1;
+
+    while (slot < a.n_work) {
+        int pending = 0;                       // raw result of the look-ahead atomic (thread 0 only)
+        if (threadIdx.x == 0) pending = atomicAdd(a.work_counter, 1);
         // rotate which warp owns the (possibly partial) last strip so the SM sub-partitions stay even
-        const int l0 = ((W == 1) ? 0 : ((warp + slot) % W) * 32) + lane;
+        const int wv = (W == 1) ? 0 : (warp + slot) % W;
+        const int l0 = wv * 32 + lane;
+        const int n_warp = (L - wv * 32 + STEP - 1) / STEP;     // lines of this warp's fullest lane (lane 0)
 
         // ---- stage y and tau_pr_den (infer.py:58-70) ---------------------------------------
         bool bad = false;
         double x1r[G], x2r[G];
 #pragma unroll
         for (int g = 0; g < G; ++g) {
-            const int row = a.guide_rows[off + g];
+            const int row = rows[g];
             const double2* tr = a.test + (long long)row * L;
             const double2* cr = a.ctrl + (long long)row * a.ctrl_lines;
             if (fixed) { x1r[g] = a.fixed_x1[row]; x2r[g] = a.fixed_x2[row]; }
             else { x1r[g] = a.mu0_x; x2r[g] = a.mu0_x * a.mu0_x; }
-            double2 c0 = make_double2(0.0, 0.0);
             double fill = 0.0;
-            if (a.ctrl_lines == 1) {
-                c0 = cr[0];
-                if (a.ctrl_rowmean_fill && c0.y != c0.y) {
+            if (a.ctrl_lines == 1 && a.ctrl_rowmean_fill) {
+                const double cs = cr[0].y;
+                if (cs != cs) {
                     // 1-D control with an undefined sd: row mean of the (NaN -> 2.0) test sds, infer.py:63
                     double one[1] = {0.0};
+#pragma unroll 1
                     for (int l = l0; l < L; l += STEP) {
                         const double e = tr[l].y;
                         one[0] += (e != e) ? 2.0 : e;
                     }
-                    team_allsum<1, NV, W>(one, red, parity, warp, lane);
+                    team_allsum<1, NV, W>(one, scr, red, parity, warp, lane);
                     fill = one[0] / (double)L;
                 }
             }
-#pragma unroll 4
-            for (int l = l0; l < L; l += STEP) {
-                const double2 t = tr[l];
-                const double2 c = (a.ctrl_lines == 1) ? c0 : cr[l];
-                const double te = (t.y != t.y) ? 2.0 : t.y;                     // infer.py:58
-                double ce = c.y;
-                if (ce != ce) ce = (a.ctrl_lines == 1 && a.ctrl_rowmean_fill) ? fill : te;   // :63 / :68
-                const double yv = t.x - c.x;
-                const double pd = tps * (te * te + ce * ce + 1e-2);
-                bad |= !(fabs(yv) <= 1.79769313486231570e308) || !(pd <= 1.79769313486231570e308);
-                ys[g * L + l] = yv;
-                tpds[g * L + l] = pd;
-            }
+            bad |= em_stage_row<STEP>(tr, cr, ys + g * L, tpds + g * L, L, l0, a.ctrl_lines, a.ctrl_rowmean_fill, fill, tps);
         }
         const int any_bad = (W == 1) ? __any_sync(JACKS_FULL_MASK, bad) : __syncthreads_or(bad);
+        // the look-ahead atomic has landed by now: share it and start loading the next gene's index
+        int nslot;
+        if (W == 1) {
+            nslot = __shfl_sync(JACKS_FULL_MASK, pending, 0);
+        } else {
+            if (threadIdx.x == 0) s_slot[pipe] = pending;
+            __syncthreads();
+            nslot = s_slot[pipe];
+            pipe ^= 1;
+        }
+        int ngid = 0, nrows[G];
+        long long noff = 0;
+#pragma unroll
+        for (int g = 0; g < G; ++g) nrows[g] = 0;
+        if (nslot < a.n_work) {
+            ngid = a.gene_ids[nslot];
+            noff = a.slot_off[nslot];
+#pragma unroll
+            for (int g = 0; g < G; ++g) nrows[g] = a.slot_rows[(long long)nslot * G + g];
+        }
         if (any_bad) {
             if (threadIdx.x == 0) {
                 const int p = atomicAdd(a.deferred_count, 1);
                 a.deferred_ids[p] = gid;
             }
-            continue;
-        }
-        // every lane reads back only the shared-memory words it wrote itself: no barrier needed
+        } else {
+            // every lane reads back only the shared-memory words it wrote itself: no barrier needed
 
-        // ---- initial w, tau, bound and the first X-step sums (infer.py:81-86) --------------
-        double acc[NV];
-#pragma unroll
-        for (int i = 0; i < NV; ++i) acc[i] = 0.0;
-        for (int l = l0; l < L; l += STEP) {
-            double yv[G];
-#pragma unroll
-            for (int g = 0; g < G; ++g) yv[g] = ys[g * L + l];
-            const double w1 = median_small<G>(yv);
-            const double w2 = w1 * w1;
-#pragma unroll
-            for (int g = 0; g < G; ++g) {
-                const double t = tps / tpds[g * L + l];
-                taus[g * L + l] = t;
-                const double xw = x1r[g] * w1;
-                acc[2 * G] += t * (yv[g] * yv[g] + x2r[g] * w2 - 2.0 * xw * yv[g]);
-                acc[g] += yv[g] * t * w1;
-                acc[G + g] += t * w2;
-            }
-            w1s[l] = w1; w2s[l] = w2;
-        }
-        team_allsum<NV, NV, W>(acc, red, parity, warp, lane);
-        double bound = acc[2 * G];
-        double mu0_w = a.mu0_w, var0_w = a.var0_w;
-        int iters = 0;
-
-        // ---- EM passes (infer.py:89-98) ------------------------------------------------------
-        for (int it = 0; it < a.n_iter; ++it) {
-            const double last = bound;
-            if (!fixed) {
-                // X step, infer.py:103-110.  Lane g (< G) owns guide g; results are broadcast.
-                double s1 = acc[0], s2 = acc[G];
-#pragma unroll
-                for (int g = 1; g < G; ++g) if (lane == g) { s1 = acc[g]; s2 = acc[G + g]; }
-                const double rden = fast_rcp(s2 + ivx);
-                const double x1u = (mx + s1) * rden;
-                const double x2u = fma(x1u, x1u, rden);
-                double xa[G];
-#pragma unroll
-                for (int g = 0; g < G; ++g) xa[g] = __shfl_sync(JACKS_FULL_MASK, x1u, g);
-                double sum = xa[0], hi = xa[0], lo = xa[0];
-#pragma unroll
-                for (int g = 1; g < G; ++g) { sum += xa[g]; hi = fmax(hi, xa[g]); lo = fmin(lo, xa[g]); }
-                const double wadj = 0.5 / G;
-                const double x1m = sum * (1.0 / G) + 2 * wadj * median_small<G>(xa) - wadj * hi - wadj * lo;
-                const double rm = 1.0 / x1m;         // x1m may be tiny or negative: IEEE division
-                const double x1n = x1u * rm;
-                const double x2n = x2u * rm * rm;
-#pragma unroll
-                for (int g = 0; g < G; ++g) {
-                    x1r[g] = __shfl_sync(JACKS_FULL_MASK, x1n, g);
-                    x2r[g] = __shfl_sync(JACKS_FULL_MASK, x2n, g);
-                }
-            }
-            if (a.apply_w_hp && L > 1) {
-                // hierarchical prior from the current w1, infer.py:92 (population variance)
-                double m[1] = {0.0};
-                for (int l = l0; l < L; l += STEP) m[0] += w1s[l];
-                team_allsum<1, NV, W>(m, red, parity, warp, lane);
-                const double mean = m[0] / (double)L;
-                double v[1] = {0.0};
-                for (int l = l0; l < L; l += STEP) { const double d = w1s[l] - mean; v[0] += d * d; }
-                team_allsum<1, NV, W>(v, red, parity, warp, lane);
-                mu0_w = mean;
-                var0_w = (v[0] / (double)L) * 3 + 1e-4;
-            }
-            const double ivw = 1.0 / var0_w;        // infer.py:113
-            const double mw = mu0_w / var0_w;
+            // ---- initial w, tau, bound and the first X-step sums (infer.py:81-86) --------------
+            double* const w2g = a.w2 ? a.w2 + (long long)gid * L : nullptr;
+            double acc[NV];
 #pragma unroll
             for (int i = 0; i < NV; ++i) acc[i] = 0.0;
 #pragma unroll 2
             for (int l = l0; l < L; l += STEP) {
-                double yv[G], tv[G];
+                double yv[G];
 #pragma unroll
-                for (int g = 0; g < G; ++g) { yv[g] = ys[g * L + l]; tv[g] = taus[g * L + l]; }
-                // W step for this line, infer.py:112-116 (old tau, new x)
-                double sa = ivw, sb = mw;
-#pragma unroll
-                for (int g = 0; g < G; ++g) {
-                    sa = fma(x2r[g], tv[g], sa);
-                    sb = fma(x1r[g], yv[g] * tv[g], sb);
-                }
-                const double r = fast_rcp(sa);
-                const double w1 = sb * r;
-                const double w2 = fma(w1, w1, r);
-                const double m2w1 = -2.0 * w1;
-                // tau step (infer.py:118-121), bound (infer.py:123-125) and next X-step sums
+                for (int g = 0; g < G; ++g) yv[g] = ys[g * L + l];
+                const double w1 = median_small<G>(yv);
+                const double w2 = w1 * w1;
 #pragma unroll
                 for (int g = 0; g < G; ++g) {
-                    const double t1 = fma(x1r[g], m2w1, yv[g]);            // y - 2*x1*w1
-                    const double bstar = fma(yv[g], t1, x2r[g] * w2);      // y^2 - 2*y*x1*w1 + x2*w2
-                    const double rd = fast_rcp(fma(0.5, bstar, tpds[g * L + l]));
-                    const double t = UNIT_C ? rd : c_tau * rd;
+                    const double t = tps * fast_rcp(tpds[g * L + l]);
                     taus[g * L + l] = t;
-                    acc[2 * G] = fma(t, bstar, acc[2 * G]);
-                    acc[g] = fma(yv[g] * t, w1, acc[g]);
-                    acc[G + g] = fma(t, w2, acc[G + g]);
+                    const double xw = x1r[g] * w1;
+                    acc[2 * G] += t * (yv[g] * yv[g] + x2r[g] * w2 - 2.0 * xw * yv[g]);
+                    acc[g] += yv[g] * t * w1;
+                    acc[G + g] += t * w2;
                 }
-                w1s[l] = w1; w2s[l] = w2;
+                w1s[l] = w1;
+                if (w2g) w2g[l] = w2;
             }
-            team_allsum<NV, NV, W>(acc, red, parity, warp, lane);
-            bound = acc[2 * G];
-            ++iters;
-            if (fabs(last - bound) < a.tol) break;
-        }
+            team_allsum<NV, NV, W>(acc, scr, red, parity, warp, lane);
+            double bound = acc[2 * G];
+            double mu0_w = a.mu0_w, var0_w = a.var0_w;
+            double ivw = 1.0 / var0_w;              // infer.py:113
+            double mw = mu0_w / var0_w;
+            int iters = 0;
 
-        // ---- write results ------------------------------------------------------------------
-        for (int l = l0; l < L; l += STEP) {
-            a.w1[(long long)gid * L + l] = w1s[l];
-            if (a.w2) a.w2[(long long)gid * L + l] = w2s[l];
-            if (a.tau) {
+            // next gene: its index entries have arrived during the init sweep; pull its rows towards L2
+            if (nslot < a.n_work) {
 #pragma unroll
-                for (int g = 0; g < G; ++g) a.tau[(off + g) * L + l] = taus[g * L + l];
+                for (int g = 0; g < G; ++g)
+                    prefetch_row_l2(a.test + (long long)nrows[g] * L, a.ctrl + (long long)nrows[g] * a.ctrl_lines, L,
+                                    a.ctrl_lines, threadIdx.x, STEP);
             }
-            if (a.y) {
+
+            // ---- EM passes (infer.py:89-98) ------------------------------------------------------
+            for (int it = 0; it < a.n_iter; ++it) {
+                const double last = bound;
+                if (!fixed) {
+                    // X step, infer.py:103-110, evaluated redundantly by every lane (all lanes hold all sums)
+                    double xu[G], x2u[G];
 #pragma unroll
-                for (int g = 0; g < G; ++g) a.y[(off + g) * L + l] = ys[g * L + l];
+                    for (int g = 0; g < G; ++g) {
+                        const double rden = fast_rcp(acc[G + g] + ivx);
+                        xu[g] = (mx + acc[g]) * rden;
+                        x2u[g] = fma(xu[g], xu[g], rden);
+                    }
+                    double sum = xu[0], hi = xu[0], lo = xu[0];
+#pragma unroll
+                    for (int g = 1; g < G; ++g) { sum += xu[g]; hi = fmax(hi, xu[g]); lo = fmin(lo, xu[g]); }
+                    const double wadj = 0.5 / G;
+                    const double x1m = sum * (1.0 / G) + 2 * wadj * median_small<G>(xu) - wadj * hi - wadj * lo;
+                    const double rm = fast_rcp(x1m);
+                    const double rm2 = rm * rm;
+#pragma unroll
+                    for (int g = 0; g < G; ++g) { x1r[g] = xu[g] * rm; x2r[g] = x2u[g] * rm2; }
+                }
+                if (a.apply_w_hp && L > 1) {
+                    // hierarchical prior from the current w1, infer.py:92 (population variance)
+                    double m[1] = {0.0};
+                    for (int l = l0; l < L; l += STEP) m[0] += w1s[l];
+                    team_allsum<1, NV, W>(m, scr, red, parity, warp, lane);
+                    const double mean = m[0] / (double)L;
+                    double v[1] = {0.0};
+                    for (int l = l0; l < L; l += STEP) { const double d = w1s[l] - mean; v[0] += d * d; }
+                    team_allsum<1, NV, W>(v, scr, red, parity, warp, lane);
+                    mu0_w = mean;
+                    var0_w = (v[0] / (double)L) * 3 + 1e-4;
+                    ivw = 1.0 / var0_w;
+                    mw = mu0_w / var0_w;
+                }
+                {
+                    EmX<G> xv;
+#pragma unroll
+                    for (int g = 0; g < G; ++g) { xv.x1[g] = x1r[g]; xv.x2[g] = x2r[g]; }
+                    const EmSums<G> r = em_sweep_all<G, STEP, UNIT_C>(ys, tpds, taus, w1s, w2g, L, l0, n_warp, xv, ivw, mw, c_tau);
+#pragma unroll
+                    for (int g = 0; g < G; ++g) { acc[g] = r.a1[g]; acc[G + g] = r.a2[g]; }
+                    acc[2 * G] = r.ab;
+                }
+                team_allsum<NV, NV, W>(acc, scr, red, parity, warp, lane);
+                bound = acc[2 * G];
+                ++iters;
+                if (fabs(last - bound) < a.tol) break;
+            }
+
+            // ---- write results ------------------------------------------------------------------
+            for (int l = l0; l < L; l += STEP) {
+                a.w1[(long long)gid * L + l] = w1s[l];
+                if (a.tau) {
+#pragma unroll
+                    for (int g = 0; g < G; ++g) a.tau[(off + g) * L + l] = taus[g * L + l];
+                }
+                if (a.y) {
+#pragma unroll
+                    for (int g = 0; g < G; ++g) a.y[(off + g) * L + l] = ys[g * L + l];
+                }
+            }
+            if (warp == 0) {
+                double xo1 = x1r[0], xo2 = x2r[0];
+#pragma unroll
+                for (int g = 1; g < G; ++g) if (lane == g) { xo1 = x1r[g]; xo2 = x2r[g]; }
+                if (lane < G) {
+                    if (a.x1) a.x1[off + lane] = xo1;
+                    if (a.x2) a.x2[off + lane] = xo2;
+                }
+                if (lane == 0) {
+                    if (a.n_iters) a.n_iters[gid] = iters;
+                    if (a.bound) a.bound[gid] = bound;
+                }
             }
         }
-        if (warp == 0) {
-            double xo1 = x1r[0], xo2 = x2r[0];
+        // ---- rotate the software pipeline: the prefetched gene becomes current -----------------
+        if (W > 1) __syncthreads();            // lanes change line ownership between genes (rotation)
+        slot = nslot; gid = ngid; off = noff;
 #pragma unroll
-            for (int g = 1; g < G; ++g) if (lane == g) { xo1 = x1r[g]; xo2 = x2r[g]; }
-            if (lane < G) {
-                if (a.x1) a.x1[off + lane] = xo1;
-                if (a.x2) a.x2[off + lane] = xo2;
-            }
-            if (lane == 0) {
-                if (a.n_iters) a.n_iters[gid] = iters;
-                if (a.bound) a.bound[gid] = bound;
-            }
-        }
+        for (int g = 0; g < G; ++g) rows[g] = nrows[g];
     }
 }
 

@@ -51,3 +51,52 @@ extern "C" int jacks_fp64_peak_flops(JacksCtx* ctx, double* flops_out, double* s
     if (seconds_out) *seconds_out = best;
     return JACKS_OK;
 }
+
+// ---- developer probe: dependent-issue latencies of DFMA and MUFU.RCP64H (cycles) ----------------
+namespace {
+__global__ void latency_kernel(double* out, long long* cyc, double a, double b) {
+    double x = (double)threadIdx.x;
+    long long t0 = clock64();
+#pragma unroll 1
+    for (int i = 0; i < 64; ++i) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) x = fma(x, a, b);
+    }
+    long long t1 = clock64();
+    double r = x + 1.5;
+#pragma unroll 1
+    for (int i = 0; i < 64; ++i) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) { double q; asm volatile("rcp.approx.ftz.f64 %0, %1;" : "=d"(q) : "d"(r)); r = q; }
+    }
+    long long t2 = clock64();
+    // 4 independent chains: throughput-limited issue interval for one warp
+    double y0 = x, y1 = x + 1, y2 = x + 2, y3 = x + 3;
+#pragma unroll 1
+    for (int i = 0; i < 64; ++i) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { y0 = fma(y0, a, b); y1 = fma(y1, a, b); y2 = fma(y2, a, b); y3 = fma(y3, a, b); }
+    }
+    long long t3 = clock64();
+    if (threadIdx.x == 0) { cyc[0] = t1 - t0; cyc[1] = t2 - t1; cyc[2] = t3 - t2; }
+    out[threadIdx.x] = x + r + y0 + y1 + y2 + y3;
+}
+}  // namespace
+
+extern "C" __attribute__((visibility("default"))) int jacks_debug_latency_probe(JacksCtx* ctx, double* dfma_cycles,
+                                                                               double* rcp_cycles, double* dfma4_cycles) {
+    using namespace jacks;
+    cudaSetDevice(ctx->device);
+    int rc = ctx->tmp.reserve(4096);
+    if (rc != JACKS_OK) return rc;
+    double* out = (double*)ctx->tmp.p;
+    long long* cyc = (long long*)((char*)ctx->tmp.p + 2048);
+    latency_kernel<<<1, 32, 0, ctx->stream>>>(out, cyc, 0.999999, 1e-9);
+    latency_kernel<<<1, 32, 0, ctx->stream>>>(out, cyc, 0.999999, 1e-9);
+    long long h[3];
+    cudaError_t e = cudaMemcpyAsync(h, cyc, sizeof h, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) return cuda_fail(e, "latency_kernel");
+    *dfma_cycles = h[0] / 1024.0; *rcp_cycles = h[1] / 1024.0; *dfma4_cycles = h[2] / 1024.0;
+    return JACKS_OK;
+}
