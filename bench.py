@@ -1,0 +1,377 @@
+#!/usr/bin/env python
+"""Headline benchmark of jacks_b200: gene-inferences/sec of the batched EM on the Avana shape.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--scaling weak|strong]
+
+One "step" is one pass of the hot path (the per-gene variational EM of jacks/jacks/infer.py:18-125)
+over one synthetic Avana-shaped screen: 18,000 real genes x 4 gRNAs x 400 cell lines plus 100,000
+pseudo-genes drawn from 1,000 control genes, i.e. 118,000 gene-inferences.
+
+  value     whole-job gene-inferences/s with the data cubes already resident in HBM (CUDA events on
+            the launching stream, barrier + synchronize on both sides, max over ranks).
+  e2e       the same metric through the C-ABI host entry point (jacks_em_batched_host) on PINNED HOST
+            buffers: every step uploads the two [N,L,2] cubes and downloads the results.
+  roofline  the EM kernel against the FP64 FMA-pipe peak measured in this run (MEASURED_PEAKS.json has
+            no FP64 entry) -- algorithmic flops 19*G*L*I + 12*G*L per gene with the
+            iteration counts I the kernel returns -- plus the same step against the measured HBM peak.
+  cpu_baseline  the numpy restatement of the reference (oracle/jacks_oracle.py, bit-exact against the
+            reference, with the reference's eager debug arithmetic mirrored) on all host cores, on a bounded
+            sample of the same genes.
+
+Under torchrun (N > 1) one rank drives one GPU.  Default scaling is weak: every rank runs its own
+Avana-shaped screen (genes are independent, no data-path collective).  --scaling strong shards ONE
+screen's genes over the ranks and all-gathers w1 over NCCL inside the timed region.
+
+--impl reference times the CPU restatement of the reference on the host cores (rank 0 only).
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, REPO)
+
+N_GENES, GUIDES, N_LINES, N_PSEUDO, N_CTRL = 18000, 4, 400, 100000, 1000
+METRIC = 'gene-inferences/sec, Avana shape (18k genes x 4 gRNA x 400 lines + 1e5 pseudo-genes)'
+UNIT = 'gene-inferences/s'
+
+
+def build_workload(seed_offset=0, n_genes=N_GENES, n_pseudo=N_PSEUDO):
+    from jacks_b200 import synth
+    from jacks_b200._native import as_csr
+    gi, test, ctrl, ctrl_genes = synth.make_condensed_screen(n_genes=n_genes, guides_per_gene=GUIDES, n_lines=N_LINES,
+                                                             seed=synth.AVANA_SEED + seed_offset, n_ctrl_genes=N_CTRL)
+    names, offs, rows = as_csr(gi)
+    pos = {g: i for i, g in enumerate(names)}
+    ctrl_ids = [pos[g] for g in ctrl_genes]
+    poffs, prows = synth.make_pseudo_index_csr(offs, ctrl_ids, n_pseudo, seed=synth.AVANA_SEED + 1 + seed_offset)
+    return dict(test=test, ctrl=ctrl, offs=offs, rows=rows.astype(np.int32), poffs=poffs, prows=prows,
+                all_offs=np.concatenate([offs, offs[-1] + poffs[1:]]),
+                all_rows=np.concatenate([rows.astype(np.int32), prows]))
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU baseline (oracle port of the reference) -- runs BEFORE any CUDA initialisation (it forks)
+# ------------------------------------------------------------------------------------------------
+_CPU = {}
+
+
+def _cpu_worker(job):
+    from oracle import jacks_oracle as O
+    lo, hi = job
+    w = _CPU['w']
+    sel = _CPU['sel']
+    offs, rows = w['all_offs'], w['all_rows']
+    gi = {int(g): rows[offs[g]:offs[g + 1]].tolist() for g in sel[lo:hi]}
+    iters = {}
+    O.em_genes(gi, w['test'], w['ctrl'], iters_out=iters, mirror_debug_cost=True)
+    return sum(iters.values())
+
+
+def cpu_reference_rate(w, cores, genes_per_core):
+    """Gene-inferences/s of the numpy restatement of the reference on `cores` processes."""
+    import multiprocessing as mp
+    n_all = len(w['all_offs']) - 1
+    n_sample = int(min(n_all, cores * genes_per_core))
+    sel = np.linspace(0, n_all - 1, n_sample).astype(np.int64)      # evenly over real and pseudo genes
+    _CPU['w'], _CPU['sel'] = w, sel
+    bounds = np.linspace(0, n_sample, cores + 1).astype(int)
+    jobs = [(int(bounds[i]), int(bounds[i + 1])) for i in range(cores) if bounds[i + 1] > bounds[i]]
+    ctx = mp.get_context('fork')
+    with ctx.Pool(len(jobs)) as pool:
+        pool.map(_cpu_worker, [(0, 1)] * len(jobs))                 # warm the workers (imports, page-in)
+        t0 = time.perf_counter()
+        tot_iters = sum(pool.map(_cpu_worker, jobs))
+        dt = time.perf_counter() - t0
+    return n_sample / dt, n_sample, dt, tot_iters / float(n_sample)
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks
+# ------------------------------------------------------------------------------------------------
+class ClockSampler(object):
+    Q = 'index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,' \
+        'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap'
+
+    def __init__(self, gpu_index):
+        self.gpu, self.proc, self.lines = gpu_index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.gpu), '--query-gpu=' + self.Q,
+                                          '--format=csv,noheader,nounits', '-lms', '100'], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(',')]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), f[5:9]):
+                if val.lower().startswith('active'):
+                    reasons.add(name)
+        return {'sm_mhz': statistics.median(sm) if sm else None, 'sm_max_mhz': max(mx) if mx else None,
+                'reasons': sorted(reasons), 'samples': len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+def run_reference_arm(args, rank):
+    """--impl reference: the CPU restatement of the reference's EM on the host cores (rank 0 only)."""
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    w = build_workload(n_pseudo=N_PSEUDO)
+    rates = []
+    gpc = max(40, int(args.ref_genes_per_core))
+    for _ in range(args.warmup):
+        cpu_reference_rate(w, cores, max(8, gpc // 8))
+    for _ in range(args.steps):
+        rate, n_sample, dt, mean_it = cpu_reference_rate(w, cores, gpc)
+        rates.append((rate, dt))
+    value = float(np.mean([r for r, _ in rates]))
+    sample = '%d genes (evenly spaced over the 118,000 real+pseudo genes of the workload) per step, %d processes' % (n_sample, cores)
+    out = {'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': args.steps,
+           'warmup': args.warmup, 'ms_per_step': 1e3 * float(np.mean([d for _, d in rates])), 'higher_is_better': True,
+           'scaling': args.scaling, 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+           'config': workload_config(args, 1),
+           'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': cores, 'kind': 'port', 'sample': sample,
+                            'mean_iters': mean_it,
+                            'note': 'oracle/jacks_oracle.py: numpy restatement of jacks/jacks/infer.py, bit-exact against '
+                                    'the unmodified reference (tests/test_oracle_golden.py); the reference is pure Python '
+                                    'and /root/reference does not travel to the GPU box'},
+           'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
+    print(json.dumps(out), flush=True)
+
+
+def workload_config(args, world):
+    per = 'per rank' if args.scaling == 'weak' else 'sharded over ranks'
+    return {'workload': 'synthetic Avana-shape joint EM: %d genes x %d gRNAs x %d lines + %d pseudo-genes (%s), matched '
+                        'control cube' % (N_GENES, GUIDES, N_LINES, N_PSEUDO, per),
+            'genes_per_step_per_rank': N_GENES + N_PSEUDO if args.scaling == 'weak' else None,
+            'n_iter': 50, 'tol': 0.1, 'l2_policy': 'inputs (0.92 GB of data cubes per rank) exceed the 126 MB L2',
+            'parallelism': 'gene-sharded data parallel, %d rank(s)' % world}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=10)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--scaling', default='weak', choices=['weak', 'strong'])
+    ap.add_argument('--ref-genes-per-core', dest='ref_genes_per_core', type=int, default=1200)
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == 'ours' else args.warmup
+
+    rank = int(os.environ.get('RANK', 0))
+    local_rank = int(os.environ.get('LOCAL_RANK', 0))
+    world = int(os.environ.get('WORLD_SIZE', 1))
+    if args.impl == 'reference':
+        run_reference_arm(args, rank)
+        return
+
+    # ---- workload (host) and the CPU baseline, before CUDA is touched ---------------------------------
+    if args.scaling == 'weak':
+        w = build_workload(seed_offset=rank)
+    else:
+        w = build_workload(seed_offset=0)
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        rate, n_sample, dt, mean_it = cpu_reference_rate(w, cores, max(40, args.ref_genes_per_core))
+        cpu = {'value': rate, 'unit': UNIT, 'cores': cores, 'kind': 'port', 'seconds': dt, 'mean_iters': mean_it,
+               'sample': '%d genes evenly spaced over the 118,000 real+pseudo genes of the workload, one process per core'
+                         % n_sample}
+
+    import torch
+    import torch.distributed as dist
+    from jacks_b200 import _native
+    torch.cuda.set_device(local_rank)
+    dev = torch.device('cuda', local_rank)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+    ctx = _native.context(local_rank)
+
+    offs, rows = w['all_offs'], w['all_rows']
+    n_all = len(offs) - 1
+    if args.scaling == 'strong' and world > 1:
+        # contiguous gene shards of ONE screen; every rank holds the full cubes (pseudo-genes gather anywhere)
+        b = np.linspace(0, n_all, world + 1).astype(np.int64)
+        lo, hi = int(b[rank]), int(b[rank + 1])
+        rows = rows[offs[lo]:offs[hi]]
+        offs = offs[lo:hi + 1] - offs[lo]
+        n_mine = hi - lo
+    else:
+        n_mine = n_all
+    N, L = w['test'].shape[0], w['test'].shape[1]
+    T = int(offs[-1])
+
+    # ---- device-resident run -----------------------------------------------------------------------
+    d_test = torch.from_numpy(w['test']).to(dev)
+    d_ctrl = torch.from_numpy(w['ctrl']).to(dev)
+    o_w1 = torch.empty((n_mine, L), dtype=torch.float64, device=dev)
+    o_w2 = torch.empty((n_mine, L), dtype=torch.float64, device=dev)
+    o_x1 = torch.empty(T, dtype=torch.float64, device=dev)
+    o_x2 = torch.empty(T, dtype=torch.float64, device=dev)
+    o_it = torch.empty(n_mine, dtype=torch.int32, device=dev)
+    gathered = None
+    if args.scaling == 'strong' and world > 1:
+        gathered = torch.empty((world, int(np.max(np.diff(np.linspace(0, n_all, world + 1).astype(np.int64)))), L),
+                               dtype=torch.float64, device=dev)
+    params = _native.default_params()
+    plan = _native.EmPlan(ctx, offs, rows, N, L)
+    io = _native.EmDeviceIO()
+    io.test, io.ctrl, io.ctrl_lines = d_test.data_ptr(), d_ctrl.data_ptr(), L
+    io.w1, io.w2, io.x1, io.x2, io.n_iters = o_w1.data_ptr(), o_w2.data_ptr(), o_x1.data_ptr(), o_x2.data_ptr(), o_it.data_ptr()
+    stream = torch.cuda.current_stream().cuda_stream
+    fp64_peak = ctx.fp64_peak_flops()
+
+    def step():
+        plan.run_device(params, io, stream)
+        if gathered is not None:
+            pad = gathered.shape[1]
+            dist.all_gather_into_tensor(gathered.view(-1), torch.nn.functional.pad(o_w1, (0, 0, 0, pad - n_mine)).view(-1))
+
+    def fence():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    fence()
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()
+    launches0 = ctx.launch_count
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    fence()
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    fence()
+    ms = e0.elapsed_time(e1)
+    launches = ctx.launch_count - launches0
+    clk = clocks.stop() if rank == 0 else None
+    iters = o_it.cpu().numpy().astype(np.float64)
+    G_of = np.diff(offs).astype(np.float64)
+    flops_step = float(((19.0 * iters + 12.0) * G_of * L).sum())
+    real_mask = (np.arange(n_mine) < N_GENES) if args.scaling == 'weak' or world == 1 else np.zeros(n_mine, bool)
+    # algorithmic HBM bytes: 32*G*L read per gene; written: x1,x2 (16*G), w1,w2 (16*L)
+    bytes_step = float((32.0 * G_of * L + 16.0 * G_of + 16.0 * L).sum())
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    f = torch.tensor([flops_step, float(n_mine), bytes_step], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(f, op=dist.ReduceOp.SUM)
+    ms_max = float(t.item())
+    flops_all, genes_all, bytes_all = (float(x) for x in f.tolist())
+    ms_per_step = ms_max / args.steps
+    value = genes_all / (ms_per_step * 1e-3)
+
+    # ---- end to end through the C-ABI host entry point, pinned host buffers ---------------------------
+    pin_test = _native.PinnedArray(w['test'].shape); pin_test.array[...] = w['test']
+    pin_ctrl = _native.PinnedArray(w['ctrl'].shape); pin_ctrl.array[...] = w['ctrl']
+    n_real = min(N_GENES, n_mine) if (args.scaling == 'weak' or world == 1) else 0
+    if args.scaling == 'weak' or world == 1:
+        r_offs, r_rows = w['offs'], w['rows']
+        p_offs, p_rows = w['poffs'], w['prows']
+    else:   # strong scaling: this rank's shard as one index, w1/w2 only
+        r_offs, r_rows = offs, rows
+        p_offs, p_rows = None, None
+    Tr = int(r_offs[-1])
+    nr = len(r_offs) - 1
+    out_r = {k: _native.PinnedArray(s, dt) for k, (s, dt) in dict(
+        x1=((Tr,), np.float64), x2=((Tr,), np.float64), w1=((nr, L), np.float64), w2=((nr, L), np.float64),
+        y=((Tr, L), np.float64), tau=((Tr, L), np.float64), n_iters=((nr,), np.int32)).items()}
+    out_p = None
+    if p_offs is not None:
+        npz = len(p_offs) - 1
+        out_p = {k: _native.PinnedArray((npz, L), np.float64) for k in ('w1', 'w2')}
+    h2d = pin_test.array.nbytes + pin_ctrl.array.nbytes + r_offs.nbytes + r_rows.nbytes + \
+        (0 if p_offs is None else p_offs.nbytes + p_rows.nbytes)
+    d2h = sum(v.array.nbytes for v in out_r.values()) + (0 if out_p is None else sum(v.array.nbytes for v in out_p.values()))
+
+    def e2e_step():
+        _native.em_batched_host(ctx, r_offs, r_rows, pin_test.array, pin_ctrl.array, params=params,
+                                want=tuple(out_r), out={k: v.array for k, v in out_r.items()}, keep_resident=True)
+        if out_p is not None:
+            _native.em_batched_host(ctx, p_offs, p_rows, None, None, params=params, n_rows=N, n_lines=L, ctrl_lines=L,
+                                    want=('w1', 'w2'), out={k: v.array for k, v in out_p.items()})
+
+    e2e_steps = max(2, min(args.steps, 5))
+    e2e_step()
+    fence()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        e2e_step()
+    torch.cuda.synchronize()
+    e2e_s = (time.perf_counter() - t0) / e2e_steps
+    te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_value = genes_all / float(te.item())
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(REPO, 'MEASURED_PEAKS.json')))
+        except Exception:
+            pass
+        hbm_peak = float(peaks.get('hbm_gbs', 6650.0))
+        hbm_src = 'measured (MEASURED_PEAKS.json)' if 'hbm_gbs' in peaks else 'fallback (B200_PROFILING.md)'
+        tf = flops_all / (ms_per_step * 1e-3) / 1e12 / world
+        out = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
+               'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': args.scaling, 'vs_baseline': None,
+               'dtype': 'f64', 'data': 'synthetic', 'config': workload_config(args, world),
+               'clocks': clk, 'gpu_launches': int(launches),
+               'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': int(d2h),
+                       'ms_per_step': 1e3 * float(te.item()), 'api': 'jacks_em_batched_host (C-ABI), pinned host buffers'},
+               'roofline': {'bound': 'fp64', 'achieved': tf, 'peak': fp64_peak / 1e12, 'unit': 'TFLOP/s',
+                            'frac': tf / (fp64_peak / 1e12), 'traffic': None,
+                            'peak_source': 'FP64 FMA-pipe peak measured in this run (jacks_fp64_peak_flops); '
+                                           'MEASURED_PEAKS.json carries no FP64 figure',
+                            'kernel': 'em_fast_kernel<G=4,W>', 'mean_iters': float(iters.mean()),
+                            'flops_per_launch': flops_all / world},
+               'roofline_hbm': {'bound': 'hbm', 'achieved': bytes_all / world / (ms_per_step * 1e-3) / 1e9, 'peak': hbm_peak,
+                                'unit': 'GB/s', 'frac': bytes_all / world / (ms_per_step * 1e-3) / 1e9 / hbm_peak,
+                                'peak_source': hbm_src},
+               'cpu_baseline': cpu}
+        print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()
