@@ -85,8 +85,11 @@ int choose_team(int G, int L) {
     int W = 0;
     if (env) W = atoi(env);
     if (!(W == 1 || W == 2 || W == 4)) {
+        // One warp per gene is the most efficient split (no barriers, one reduction per pass) and, at
+        // the shared-memory-bound occupancy of a few genes per SM, also the fastest measured at L = 400
+        // (W=1 9.2 ms, W=2 10.1 ms, W=4 15.3 ms per Avana pass).  Very long line axes get more warps.
         const int strips = (L + 31) / 32;
-        W = strips >= 12 ? 4 : (strips >= 6 ? 2 : 1);
+        W = strips > 64 ? 4 : (strips > 32 ? 2 : 1);
     }
     if (!em_fast_available(G, W) || em_fast_smem_bytes(G, W, L) > kMaxDynSmem) return 0;
     return W;
