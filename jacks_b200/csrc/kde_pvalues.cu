@@ -1,0 +1,187 @@
+// KDE p-values of gene effects against the pseudo-gene null.
+//
+// Reference: computeW1PvalsAndFDRs with pseudo=True (jacks/jacks/jacks_io.py:69-89) -- per cell line a
+// scipy.stats.gaussian_kde over the non-NaN pseudo-gene w1 values and, per gene,
+// kernel.integrate_box_1d(-100, w1) (negative selection) or integrate_box_1d(w1, 100) (positive).
+// scipy 1.18.1 (stats/_kde.py) evaluates that as
+//     h   = sqrt( cov(s, ddof=1, aweights=1/n) * neff^(-2/5) ),  neff = 1/sum(w^2) = n      (Scott's rule)
+//     p   = sum_i (1/n) * [ ndtr((hi - s_i)/h) - ndtr((lo - s_i)/h) ]
+// so the work is n_genes * L * n_pseudo normal-CDF evaluations (7.2e11 at the Avana shape with 1e5
+// pseudo-genes): FP64-pipe bound.  The term that does not depend on the gene (lo = -100 or hi = +100) is
+// evaluated once per line.
+//
+// Kernels:
+//   kde_line_stats   one CTA per line: compacts the non-NaN pseudo values into a transposed, +inf-padded
+//                    row sT[l][.], two-pass mean / variance, bandwidth, the gene-independent term.
+//   kde_pvalues      grid (gene tiles, lines): a CTA stages chunks of sT[l] in shared memory; each thread
+//                    owns GT genes of the line and streams the chunk through registers (one broadcast
+//                    LDS feeds GT independent normcdf chains).
+#include <cuda_runtime.h>
+#include <math.h>
+
+#include "../../include/jacks_b200.h"
+#include "capi_internal.h"
+
+namespace jacks {
+
+namespace {
+
+constexpr int kStatsThreads = 256;
+constexpr int kPvThreads = 128;
+constexpr int kGT = 4;              // genes per thread
+constexpr int kChunk = 1024;        // pseudo values staged per iteration (8 KB)
+
+__device__ __forceinline__ double block_sum(double v, double* sh) {
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    __syncthreads();
+    if (lane == 0) sh[warp] = v;
+    __syncthreads();
+    double s = 0.0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) s += sh[w];
+    return s;
+}
+
+// stats[l*4 + 0] = h, +1 = n (as double), +2 = gene-independent term, +3 = 1/n
+__global__ void __launch_bounds__(kStatsThreads) kde_line_stats(const double* __restrict__ w1_pseudo, long long n_pseudo,
+                                                                int L, long long ld, int positive,
+                                                                double* __restrict__ sT, double* __restrict__ stats) {
+    __shared__ double sh[kStatsThreads / 32];
+    __shared__ int s_base;
+    const int l = blockIdx.x;
+    double* row = sT + (long long)l * ld;
+    // compaction, order preserving within a block pass (order does not matter for the sum)
+    if (threadIdx.x == 0) s_base = 0;
+    __syncthreads();
+    double sum = 0.0;
+    for (long long i0 = 0; i0 < n_pseudo; i0 += kStatsThreads) {
+        const long long i = i0 + threadIdx.x;
+        double v = 0.0;
+        bool ok = false;
+        if (i < n_pseudo) { v = w1_pseudo[i * L + l]; ok = (v == v); }      // jacks_io.py:78 drops NaN
+        const unsigned m = __ballot_sync(0xffffffffu, ok);
+        const int lane = threadIdx.x & 31;
+        int wbase = 0;
+        if (lane == 0) wbase = atomicAdd(&s_base, __popc(m));
+        wbase = __shfl_sync(0xffffffffu, wbase, 0);
+        if (ok) { row[wbase + __popc(m & ((1u << lane) - 1))] = v; sum += v; }
+    }
+    __syncthreads();
+    const int n = s_base;
+    for (long long i = n + threadIdx.x; i < ld; i += kStatsThreads) row[i] = __longlong_as_double(0x7ff0000000000000LL);
+    const double mean = block_sum(sum, sh) / (double)n;
+    double ss = 0.0;
+    for (int i = threadIdx.x; i < n; i += kStatsThreads) { const double d = row[i] - mean; ss += d * d; }
+    ss = block_sum(ss, sh);
+    // cov with aweights = 1/n: sum(w d^2) / (1 - sum(w^2)) = (ss/n) / (1 - 1/n); neff = n
+    const double wgt = 1.0 / (double)n;
+    const double cov = (ss * wgt) / (1.0 - wgt);
+    const double factor = pow((double)n, -0.2);
+    const double h = sqrt(cov * factor * factor);
+    const double edge = positive ? 100.0 : -100.0;
+    double c = 0.0;
+    // positive selection is evaluated as the upper tail Phi(-z) (no 1 - Phi cancellation)
+    const double sgn = positive ? -1.0 : 1.0;
+    for (int i = threadIdx.x; i < n; i += kStatsThreads) c += normcdf(sgn * (edge - row[i]) / h);
+    c = block_sum(c, sh);
+    if (threadIdx.x == 0) {
+        stats[l * 4 + 0] = h;
+        stats[l * 4 + 1] = (double)n;
+        stats[l * 4 + 2] = c;
+        stats[l * 4 + 3] = wgt;
+    }
+}
+
+__global__ void __launch_bounds__(kPvThreads) kde_pvalues(const double* __restrict__ w1_genes, long long n_genes, int L,
+                                                          const double* __restrict__ sT, long long ld,
+                                                          const double* __restrict__ stats, int positive,
+                                                          double* __restrict__ pvals) {
+    __shared__ double chunk[kChunk];
+    const int l = blockIdx.y;
+    const double h = stats[l * 4 + 0];
+    const int n = (int)stats[l * 4 + 1];
+    const double cterm = stats[l * 4 + 2];
+    const double wgt = stats[l * 4 + 3];
+    const double rh = (positive ? -1.0 : 1.0) / h;     // signed: positive selection sums Phi(-(w-s)/h)
+    const long long g0 = ((long long)blockIdx.x * kPvThreads + threadIdx.x) * kGT;
+    double w[kGT], acc[kGT];
+#pragma unroll
+    for (int k = 0; k < kGT; ++k) {
+        const long long g = g0 + k;
+        w[k] = (g < n_genes) ? w1_genes[g * L + l] : 0.0;
+        acc[k] = 0.0;
+    }
+    const double* row = sT + (long long)l * ld;
+    for (int base = 0; base < n; base += kChunk) {
+        __syncthreads();
+        for (int i = threadIdx.x; i < kChunk; i += kPvThreads) chunk[i] = row[base + i];   // row is padded to a multiple of kChunk with +inf
+        __syncthreads();
+        const int m = min(kChunk, n - base);
+        for (int i = 0; i < m; ++i) {
+            const double s = chunk[i];
+#pragma unroll
+            for (int k = 0; k < kGT; ++k) acc[k] += normcdf((w[k] - s) * rh);
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < kGT; ++k) {
+        const long long g = g0 + k;
+        if (g < n_genes) {
+            // negative: mean_i[Phi((w-s)/h) - Phi((-100-s)/h)]
+            // positive: mean_i[Phi((100-s)/h) - Phi((w-s)/h)] = mean_i[Phi(-(w-s)/h) - Phi(-(100-s)/h)]
+            pvals[g * L + l] = (acc[k] - cterm) * wgt;
+        }
+    }
+}
+
+}  // namespace
+}  // namespace jacks
+
+using namespace jacks;
+
+extern "C" int jacks_kde_pvalues_device(JacksCtx* ctx, const double* w1_genes, int64_t n_genes, const double* w1_pseudo,
+                                        int64_t n_pseudo, int32_t n_lines, int32_t positive, double* pvals, void* stream) {
+    if (!ctx || !pvals || (n_genes > 0 && !w1_genes) || !w1_pseudo) return fail(JACKS_E_INVALID, "jacks_kde_pvalues_device: NULL argument");
+    if (n_genes < 0 || n_pseudo < 2 || n_lines < 1) return fail(JACKS_E_INVALID, "need n_pseudo >= 2 and n_lines >= 1 (got %lld, %d)", (long long)n_pseudo, n_lines);
+    if (n_genes == 0) return JACKS_OK;
+    cudaError_t e = cudaSetDevice(ctx->device);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaSetDevice");
+    cudaStream_t st = (cudaStream_t)stream;
+    const long long ld = ((long long)n_pseudo + kChunk - 1) / kChunk * kChunk;
+    const size_t bytes = (size_t)ld * n_lines * sizeof(double) + (size_t)n_lines * 4 * sizeof(double);
+    int rc = ctx->tmp.reserve(bytes);
+    if (rc != JACKS_OK) return rc;
+    double* sT = (double*)ctx->tmp.p;
+    double* stats = sT + ld * n_lines;
+    kde_line_stats<<<n_lines, kStatsThreads, 0, st>>>(w1_pseudo, n_pseudo, n_lines, ld, positive ? 1 : 0, sT, stats);
+    if ((e = cudaGetLastError()) != cudaSuccess) return cuda_fail(e, "kde_line_stats launch");
+    const long long per_cta = (long long)kPvThreads * kGT;
+    dim3 grid((unsigned)((n_genes + per_cta - 1) / per_cta), (unsigned)n_lines);
+    kde_pvalues<<<grid, kPvThreads, 0, st>>>(w1_genes, n_genes, n_lines, sT, ld, stats, positive ? 1 : 0, pvals);
+    if ((e = cudaGetLastError()) != cudaSuccess) return cuda_fail(e, "kde_pvalues launch");
+    ctx->launches += 2;
+    return JACKS_OK;
+}
+
+extern "C" int jacks_kde_pvalues_host(JacksCtx* ctx, const double* w1_genes, int64_t n_genes, const double* w1_pseudo,
+                                      int64_t n_pseudo, int32_t n_lines, int32_t positive, double* pvals) {
+    if (!ctx || !pvals || (n_genes > 0 && !w1_genes) || !w1_pseudo) return fail(JACKS_E_INVALID, "jacks_kde_pvalues_host: NULL argument");
+    if (n_genes < 0 || n_pseudo < 2 || n_lines < 1) return fail(JACKS_E_INVALID, "need n_pseudo >= 2 and n_lines >= 1 (got %lld, %d)", (long long)n_pseudo, n_lines);
+    if (n_genes == 0) return JACKS_OK;
+    cudaError_t e = cudaSetDevice(ctx->device);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaSetDevice");
+    const size_t gb = (size_t)n_genes * n_lines * sizeof(double), pb = (size_t)n_pseudo * n_lines * sizeof(double);
+    int rc;
+    if ((rc = ctx->out[0].reserve(gb)) != JACKS_OK) return rc;
+    if ((rc = ctx->out[1].reserve(pb)) != JACKS_OK) return rc;
+    if ((rc = ctx->out[2].reserve(gb)) != JACKS_OK) return rc;
+    cudaStream_t st = ctx->stream;
+    if ((e = cudaMemcpyAsync(ctx->out[0].p, w1_genes, gb, cudaMemcpyHostToDevice, st)) != cudaSuccess) return cuda_fail(e, "H2D w1_genes");
+    if ((e = cudaMemcpyAsync(ctx->out[1].p, w1_pseudo, pb, cudaMemcpyHostToDevice, st)) != cudaSuccess) return cuda_fail(e, "H2D w1_pseudo");
+    rc = jacks_kde_pvalues_device(ctx, (const double*)ctx->out[0].p, n_genes, (const double*)ctx->out[1].p, n_pseudo,
+                                  n_lines, positive, (double*)ctx->out[2].p, st);
+    if (rc != JACKS_OK) return rc;
+    if ((e = cudaMemcpyAsync(pvals, ctx->out[2].p, gb, cudaMemcpyDeviceToHost, st)) != cudaSuccess) return cuda_fail(e, "D2H pvals");
+    if ((e = cudaStreamSynchronize(st)) != cudaSuccess) return cuda_fail(e, "kde kernels");
+    return JACKS_OK;
+}

@@ -1,0 +1,73 @@
+"""GPU parity of the KDE p-value kernel (C-ABI jacks_kde_pvalues_host) against the reference's own numbers
+(tests/golden/pvals.npz, produced by jacks_io.computeW1PvalsAndFDRs + scipy 1.18.1) and against the oracle
+on seeded inputs.  Tolerance 1e-10 relative (summation order and a <=5 ulp normal CDF; far tails amplify
+1 ulp of the bandwidth by z^2), NaN patterns identical."""
+import numpy as np
+import pytest
+
+from conftest import load_golden
+
+pytestmark = pytest.mark.gpu
+
+
+def rel_close(a, b, rtol, atol=0.0):
+    """Worst relative error over entries that differ by more than atol.  scipy forms positive-selection
+    p-values as sum(1 - Phi(z)), accurate to ~1e-17 ABSOLUTE only, so that case is compared with atol=1e-15."""
+    nan = np.isnan(a)
+    assert (nan == np.isnan(b)).all()
+    m = ~nan & (np.abs(a - b) > atol)
+    err = np.abs(a[m] - b[m]) / np.maximum(np.abs(b[m]), 1e-300)
+    return float(err.max()) if m.any() else 0.0
+
+
+@pytest.fixture(scope='module')
+def nat():
+    from jacks_b200 import _native
+    return _native
+
+
+def test_pvalues_vs_reference_golden(nat):
+    z = load_golden('pvals.npz')
+    all_w1 = np.concatenate([z['pseudo_w1'], z['gene_w1']])
+    ctx = nat.context(0)
+    for key, positive in (('pv_neg', False), ('pv_pos', True)):
+        pv = nat.kde_pvalues_host(ctx, all_w1, z['pseudo_w1'], positive=positive)
+        assert rel_close(pv, z[key], 1e-10, atol=1e-15 if positive else 0.0) < 1e-10, key
+    # far tails keep full relative accuracy: p ~ 1e-176 in the fixture
+    assert np.nanmin(z['pv_neg']) < 1e-150
+
+
+@pytest.mark.parametrize('n_pseudo,L,n_genes', [(2, 1, 3), (37, 5, 50), (2000, 7, 300), (5000, 3, 1025)])
+def test_pvalues_vs_oracle(nat, n_pseudo, L, n_genes):
+    from oracle import jacks_oracle as O
+    rng = np.random.default_rng(n_pseudo + L)
+    pseudo = rng.normal(0.02, 0.25, size=(n_pseudo, L)) * rng.uniform(0.5, 2.0, size=(1, L))
+    genes = np.concatenate([rng.normal(-0.5, 0.9, size=(n_genes - 2, L)), np.full((1, L), -40.0), np.full((1, L), 12.0)])
+    if n_pseudo > 10:
+        pseudo[rng.integers(0, n_pseudo, size=3), rng.integers(0, L, size=3)] = np.nan
+        genes[1, 0] = np.nan
+    ctx = nat.context(0)
+    for positive in (False, True):
+        pv = nat.kde_pvalues_host(ctx, genes, pseudo, positive=positive)
+        ref = O.kde_pvalues(genes, pseudo, positive=positive)
+        assert rel_close(pv, ref, 1e-10, atol=1e-15 if positive else 0.0) < 1e-10
+
+
+def test_pvalue_properties_full_size(nat):
+    """BASELINE size for one line block: 18,000 genes against 100,000 pseudo-genes -- monotone in w, in [0,1],
+    negative + positive selection sum to the mass between -100 and 100 (= 1)."""
+    rng = np.random.default_rng(9)
+    L = 4
+    pseudo = rng.normal(0.0, 0.2, size=(100000, L))
+    genes = np.sort(rng.normal(-0.3, 0.7, size=(18000, L)), axis=0)
+    ctx = nat.context(0)
+    neg = nat.kde_pvalues_host(ctx, genes, pseudo, positive=False)
+    pos = nat.kde_pvalues_host(ctx, genes, pseudo, positive=True)
+    assert (neg >= 0).all() and (neg <= 1).all()
+    assert (np.diff(neg, axis=0) >= -1e-15).all()
+    assert np.abs(neg + pos - 1.0).max() < 1e-12
+    # spot check 8 entries against scipy
+    from oracle import jacks_oracle as O
+    pick = np.array([0, 17, 4000, 9000, 12000, 15000, 17990, 17999])
+    ref = O.kde_pvalues(genes[pick], pseudo, positive=False)
+    assert rel_close(neg[pick], ref, 1e-10) < 1e-10
