@@ -187,9 +187,13 @@ JACKS_API int jacks_condense_host(JacksCtx* ctx, const double* logcounts, int64_
  * Counts -> normalised log counts (preprocess.py:147 and normalizeLogCounts with normtype 'median',
  * preprocess.py:77-81): out[i,c] = log2(counts[i,c] + prior) - nanmedian_i(log2(counts[.,c] + prior)).
  *   counts [n_guides, n_cols] float64 (the reference eval()s each cell, so non-integers are legal)
+ *   log2_table (optional, may be NULL): table_len host-computed values log2(k + prior), k = 0..table_len-1.
+ *       Integer counts below table_len take their logarithm from the table, i.e. from the caller's own
+ *       libm/numpy, which makes the result bit-identical to the reference run on that host; other counts
+ *       use the device log2 (<= 1 ulp).
  */
 JACKS_API int jacks_lognorm_median_host(JacksCtx* ctx, const double* counts, int64_t n_guides, int32_t n_cols,
-                              double prior, double* logcounts);
+                              double prior, const double* log2_table, int64_t table_len, double* logcounts);
 
 /* FP64 FMA-pipe peak of the current device in FLOP/s (dependent-chain-free DFMA microbenchmark);
  * bench.py uses it as the roofline denominator because MEASURED_PEAKS.json has no FP64 entry. */

@@ -86,7 +86,7 @@ def lib():
             L.jacks_kde_pvalues_host.argtypes = [vp, vp, i64, vp, i64, i32, i32, vp]
         if hasattr(L, 'jacks_condense_host'):
             L.jacks_condense_host.argtypes = [vp, vp, i64, i32, vp, vp, i32, vp]
-            L.jacks_lognorm_median_host.argtypes = [vp, vp, i64, i32, dbl, vp]
+            L.jacks_lognorm_median_host.argtypes = [vp, vp, i64, i32, dbl, vp, i64, vp]
         _lib = L
     return _lib
 
@@ -283,10 +283,22 @@ def kde_pvalues_host(ctx, w1_genes, w1_pseudo, positive=False):
     return out
 
 
-def lognorm_median_host(ctx, counts, prior):
+LOG2_TABLE_MAX = 1 << 24
+
+
+def lognorm_median_host(ctx, counts, prior, use_table=True):
+    """log2(counts + prior) minus the per-column nanmedian, on the GPU.  Integer counts take their logarithm
+    from a table this host computes with numpy (bit-identical to the reference's np.log2 on the same machine)."""
     counts = np.ascontiguousarray(counts, dtype=np.float64)
     out = np.empty(counts.shape, dtype=np.float64)
-    check(lib().jacks_lognorm_median_host(ctx.h, _ptr(counts), counts.shape[0], counts.shape[1], float(prior), _ptr(out)))
+    table = None
+    if use_table and counts.size:
+        finite = counts[np.isfinite(counts)]
+        top = int(min(finite.max(), LOG2_TABLE_MAX - 1)) if finite.size and finite.max() >= 0 else -1
+        if top >= 0:
+            table = np.log2(np.arange(top + 1, dtype=np.float64) + prior)
+    check(lib().jacks_lognorm_median_host(ctx.h, _ptr(counts), counts.shape[0], counts.shape[1], float(prior),
+                                          _ptr(table), 0 if table is None else table.size, _ptr(out)))
     return out
 
 

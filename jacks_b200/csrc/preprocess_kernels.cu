@@ -1,0 +1,498 @@
+// Preprocessing error model on the GPU (reference jacks/jacks/preprocess.py).
+//
+//   jacks_lognorm_median_host   log2(count + prior) (preprocess.py:147) and per-column centring,
+//                               normalizeLogCounts 'median' (preprocess.py:80-81): transpose to
+//                               column-major, radix-select the nanmedian of each column, transpose back.
+//   jacks_condense_host         condense_normalised_counts (preprocess.py:61-67): per sample the mean over
+//                               its replicate columns and calc_posterior_sd (preprocess.py:25-58):
+//                                 means, vars = data.mean(axis=1), nanstd(data, axis=1)**2
+//                                 sort guides by (mean, var, index)                       (:39-40)
+//                                 window = min(max(int(N/100), 30), 800)                  (:35)
+//                                 sliding mean of the sorted vars, the reference's shifted recurrence (:16-22)
+//                                 reverse running maximum (monotonize, :8-13; NaN restarts the run)
+//                                 sd = sqrt(m) scattered back to guide order              (:55-56)
+//
+// Everything is HBM/L2-bound integer-and-double streaming work: coalesced tiles, shared-memory staging,
+// no tensor cores.  The sort is a bitonic network on the full (mean, var, index) key -- the order is
+// total, so no stability is needed -- with all compare-exchange distances below 2048 done in shared
+// memory.  The sliding mean uses prefix sums: for w+1 <= k <= N-w-2 the reference's recurrence
+// m[k] = m[k-1] + (x[k+w+1] - x[k-w])/(2w+1) telescopes to
+// m[w] + (P[k+w+2] - P[2w+2] - P[k-w+1] + P[1])/(2w+1) with P[i] = sum_{t<i} x[t] (agreement ~1e-14).
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+
+#include "../../include/jacks_b200.h"
+#include "capi_internal.h"
+
+namespace jacks {
+namespace {
+
+__device__ __forceinline__ double d_nan() { return __longlong_as_double(0x7ff8000000000000LL); }
+__device__ __forceinline__ double d_inf() { return __longlong_as_double(0x7ff0000000000000LL); }
+
+// order-preserving map double -> uint64 (all NaNs are excluded by the callers)
+__device__ __forceinline__ unsigned long long sortable(double v) {
+    const unsigned long long b = (unsigned long long)__double_as_longlong(v);
+    return (b & 0x8000000000000000ULL) ? ~b : (b | 0x8000000000000000ULL);
+}
+__device__ __forceinline__ double unsortable(unsigned long long k) {
+    const unsigned long long b = (k & 0x8000000000000000ULL) ? (k & 0x7fffffffffffffffULL) : ~k;
+    return __longlong_as_double((long long)b);
+}
+
+// ---- log2 + transpose ----------------------------------------------------------------------------
+// T[c][i] = log2(counts[i][c] + prior); 32x32 tiles through shared memory, coalesced on both sides.
+//
+// log2_table (optional): host-computed log2(k + prior) for k = 0..table_len-1.  Integer counts take their
+// logarithm from it, which makes them bit-identical to the numpy log2 of the calling host; device log2 is
+// <= 1 ulp too, but not the same ulp, and a last-bit difference can swap two guides whose means tie to
+// within an ulp in the (mean, var, index) sort downstream -- a visible change of their smoothed sd.
+__global__ void __launch_bounds__(256) log_transpose_kernel(const double* __restrict__ counts, long long N, int C,
+                                                            double prior, const double* __restrict__ log2_table,
+                                                            long long table_len, double* __restrict__ T, long long ldT) {
+    __shared__ double tile[32][33];
+    const long long i0 = (long long)blockIdx.x * 32;
+    const int c0 = blockIdx.y * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    for (int r = ty; r < 32; r += 8) {
+        const long long i = i0 + r;
+        const int c = c0 + tx;
+        double v = 0.0;
+        if (i < N && c < C) {
+            const double cnt = counts[i * C + c];
+            if (log2_table && cnt >= 0.0 && cnt < (double)table_len && cnt == floor(cnt)) v = log2_table[(long long)cnt];
+            else v = log2(cnt + prior);
+        }
+        tile[r][tx] = v;
+    }
+    __syncthreads();
+    for (int r = ty; r < 32; r += 8) {
+        const int c = c0 + r;
+        const long long i = i0 + tx;
+        if (c < C && i < N) T[(long long)c * ldT + i] = tile[tx][r];
+    }
+}
+
+// out[i][c] = (T[c][i] - shift[c]) * scale[c]
+__global__ void __launch_bounds__(256) untranspose_shift_kernel(const double* __restrict__ T, long long ldT, long long N, int C,
+                                                                const double* __restrict__ shift,
+                                                                const double* __restrict__ scale, double* __restrict__ out) {
+    __shared__ double tile[32][33];
+    const long long i0 = (long long)blockIdx.x * 32;
+    const int c0 = blockIdx.y * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    for (int r = ty; r < 32; r += 8) {
+        const int c = c0 + r;
+        const long long i = i0 + tx;
+        double v = 0.0;
+        if (c < C && i < N) {
+            v = T[(long long)c * ldT + i] - shift[c];
+            if (scale) v = v / scale[c];
+        }
+        tile[r][tx] = v;
+    }
+    __syncthreads();
+    for (int r = ty; r < 32; r += 8) {
+        const long long i = i0 + r;
+        const int c = c0 + tx;
+        if (i < N && c < C) out[i * C + c] = tile[tx][r];
+    }
+}
+
+// ---- per-column nanmedian by radix select --------------------------------------------------------
+// One CTA per column of the column-major T.  mode 0: median of T[c][.]; mode 1: median of |T[c][.] - shift[c]|.
+// Rows can be restricted to a subset (row_mask != nullptr: use rows with mask != 0).
+__global__ void __launch_bounds__(1024) column_median_kernel(const double* __restrict__ T, long long ldT, long long N,
+                                                             const unsigned char* __restrict__ row_mask,
+                                                             const double* __restrict__ shift, int mode,
+                                                             double* __restrict__ med) {
+    __shared__ unsigned int hist[256];
+    __shared__ unsigned long long s_prefix;
+    __shared__ long long s_k;
+    __shared__ long long s_cnt;
+    const int c = blockIdx.x;
+    const double* col = T + (long long)c * ldT;
+    const double sh = (mode == 1) ? shift[c] : 0.0;
+    // count the valid (non-NaN, selected) entries
+    long long cnt = 0;
+    for (long long i = threadIdx.x; i < N; i += blockDim.x) {
+        double v = col[i];
+        if (mode == 1) v = fabs(v - sh);
+        if (v == v && (!row_mask || row_mask[i])) ++cnt;
+    }
+    if (threadIdx.x == 0) s_cnt = 0;
+    __syncthreads();
+    atomicAdd((unsigned long long*)&s_cnt, (unsigned long long)cnt);
+    __syncthreads();
+    const long long n = s_cnt;
+    if (n == 0) { if (threadIdx.x == 0) med[c] = d_nan(); return; }
+    double result[2];
+    for (int which = 0; which < 2; ++which) {
+        long long k = which == 0 ? (n - 1) / 2 : n / 2;       // 0-based order statistic
+        unsigned long long prefix = 0;
+        for (int shift_bits = 56; shift_bits >= 0; shift_bits -= 8) {
+            for (int b = threadIdx.x; b < 256; b += blockDim.x) hist[b] = 0;
+            __syncthreads();
+            const unsigned long long himask = (shift_bits == 56) ? 0ULL : (~0ULL << (shift_bits + 8));
+            for (long long i = threadIdx.x; i < N; i += blockDim.x) {
+                double v = col[i];
+                if (mode == 1) v = fabs(v - sh);
+                if (!(v == v) || (row_mask && !row_mask[i])) continue;
+                const unsigned long long key = sortable(v);
+                if ((key & himask) == prefix) atomicAdd(&hist[(unsigned)((key >> shift_bits) & 0xff)], 1u);
+            }
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                long long acc = 0;
+                int b = 0;
+                for (; b < 256; ++b) {
+                    if (acc + (long long)hist[b] > k) break;
+                    acc += hist[b];
+                }
+                s_prefix = prefix | ((unsigned long long)b << shift_bits);
+                s_k = k - acc;
+            }
+            __syncthreads();
+            prefix = s_prefix;
+            k = s_k;
+            __syncthreads();
+        }
+        result[which] = unsortable(prefix);
+    }
+    if (threadIdx.x == 0) med[c] = (n & 1) ? result[0] : 0.5 * (result[0] + result[1]);
+}
+
+__global__ void scale_mad_kernel(double* mad, int C) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c < C) mad[c] = 1.4826 * mad[c];          // preprocess.py:84
+}
+
+// ---- per-sample mean / variance and sort keys ----------------------------------------------------
+// numpy semantics, no FMA contraction: mean = (x0 + x1 + ...)/R in column order; nanstd uses the NaN-aware
+// mean, population variance, and the reference squares the sqrt (nanstd(...)**2, preprocess.py:38).
+__global__ void __launch_bounds__(256) sample_stats_kernel(const double* __restrict__ lc, long long N, int C,
+                                                           const int* __restrict__ col_off, const int* __restrict__ cols,
+                                                           int S, long long Np, double* __restrict__ data,
+                                                           double* __restrict__ kmean, double* __restrict__ kvar,
+                                                           int* __restrict__ kidx) {
+    const int s = blockIdx.y;
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= Np) return;
+    const int c0 = col_off[s], R = col_off[s + 1] - c0;
+    const long long o = (long long)s * Np + i;
+    if (i >= N) { kmean[o] = d_inf(); kvar[o] = d_inf(); kidx[o] = 0x7fffffff; return; }
+    double sum = 0.0, nsum = 0.0;
+    int cnt = 0;
+    for (int r = 0; r < R; ++r) {
+        const double v = lc[i * C + cols[c0 + r]];
+        sum = __dadd_rn(sum, v);
+        if (v == v) { nsum = __dadd_rn(nsum, v); ++cnt; }
+    }
+    const double mean = sum / (double)R;
+    double var = d_nan();
+    if (cnt > 0) {
+        const double nmean = nsum / (double)cnt;
+        double ss = 0.0;
+        for (int r = 0; r < R; ++r) {
+            const double v = lc[i * C + cols[c0 + r]];
+            if (v == v) { const double d = __dadd_rn(v, -nmean); ss = __dadd_rn(ss, __dmul_rn(d, d)); }
+        }
+        const double sd = sqrt(ss / (double)cnt);
+        var = __dmul_rn(sd, sd);
+    }
+    data[(i * S + s) * 2 + 0] = mean;
+    if (R < 2) data[(i * S + s) * 2 + 1] = d_nan();          // single replicate: undefined sd, preprocess.py:32
+    // NaN keys sort last (Python tuple comparison with NaN is not a total order; such inputs are out of contract)
+    kmean[o] = (mean == mean) ? mean : d_inf();
+    kvar[o] = (var == var) ? var : d_inf();
+    kidx[o] = (int)i;
+}
+
+struct Key { double m, v; int i; };
+__device__ __forceinline__ bool key_less(const Key& a, const Key& b) {
+    if (a.m != b.m) return a.m < b.m;
+    if (a.v != b.v) return a.v < b.v;
+    return a.i < b.i;
+}
+
+constexpr int kSortTile = 2048;      // elements per CTA in the shared-memory phases (2048*20 B = 40 KB)
+
+// all compare-exchange steps with distance j < kSortTile for merge sizes kk = k_lo .. k_hi (powers of two)
+__global__ void __launch_bounds__(1024) bitonic_local_kernel(double* __restrict__ km, double* __restrict__ kv, int* __restrict__ ki,
+                                                             long long Np, int k_lo, int k_hi) {
+    __shared__ double sm[kSortTile];
+    __shared__ double sv[kSortTile];
+    __shared__ int si[kSortTile];
+    const long long base = (long long)blockIdx.y * Np + (long long)blockIdx.x * kSortTile;
+    for (int t = threadIdx.x; t < kSortTile; t += blockDim.x) { sm[t] = km[base + t]; sv[t] = kv[base + t]; si[t] = ki[base + t]; }
+    __syncthreads();
+    const long long tile0 = (long long)blockIdx.x * kSortTile;
+    for (long long kk = k_lo; kk <= k_hi; kk <<= 1) {
+        for (int j = (int)((kk >> 1) < kSortTile ? (kk >> 1) : (kSortTile >> 1)); j > 0; j >>= 1) {
+            for (int t = threadIdx.x; t < kSortTile / 2; t += blockDim.x) {
+                const int a = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+                const int b = a | j;
+                const bool up = (((tile0 + a) & kk) == 0);
+                Key ka{sm[a], sv[a], si[a]}, kb{sm[b], sv[b], si[b]};
+                if (key_less(kb, ka) == up) {
+                    sm[a] = kb.m; sv[a] = kb.v; si[a] = kb.i;
+                    sm[b] = ka.m; sv[b] = ka.v; si[b] = ka.i;
+                }
+            }
+            __syncthreads();
+        }
+    }
+    for (int t = threadIdx.x; t < kSortTile; t += blockDim.x) { km[base + t] = sm[t]; kv[base + t] = sv[t]; ki[base + t] = si[t]; }
+}
+
+// one compare-exchange step with distance j >= kSortTile
+__global__ void __launch_bounds__(256) bitonic_global_kernel(double* __restrict__ km, double* __restrict__ kv, int* __restrict__ ki,
+                                                             long long Np, long long kk, long long j) {
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= Np / 2) return;
+    const long long base = (long long)blockIdx.y * Np;
+    const long long a = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+    const long long b = a | j;
+    const bool up = ((a & kk) == 0);
+    Key ka{km[base + a], kv[base + a], ki[base + a]}, kb{km[base + b], kv[base + b], ki[base + b]};
+    if (key_less(kb, ka) == up) {
+        km[base + a] = kb.m; kv[base + a] = kb.v; ki[base + a] = kb.i;
+        km[base + b] = ka.m; kv[base + b] = ka.v; ki[base + b] = ka.i;
+    }
+}
+
+// ---- sliding mean (shifted, as the reference), reverse running max, sqrt, scatter ----------------
+// One CTA per sample.  P = exclusive prefix sums of the sorted variances (global scratch, chunked scan).
+constexpr int kScanThreads = 1024;
+
+__device__ double block_exclusive_scan(double v, double* sh, double* total) {
+    // inclusive warp scan
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double x = v;
+    for (int o = 1; o < 32; o <<= 1) { const double y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
+    __syncthreads();
+    if (lane == 31) sh[warp] = x;
+    __syncthreads();
+    if (warp == 0) {
+        double w = (lane < (int)(blockDim.x >> 5)) ? sh[lane] : 0.0;
+        for (int o = 1; o < 32; o <<= 1) { const double y = __shfl_up_sync(0xffffffffu, w, o); if (lane >= o) w += y; }
+        sh[lane] = w;
+    }
+    __syncthreads();
+    const double before = (warp == 0) ? 0.0 : sh[warp - 1];
+    *total = sh[(blockDim.x >> 5) - 1];
+    return before + x - v;
+}
+
+__global__ void __launch_bounds__(kScanThreads) smooth_monotone_scatter_kernel(const double* __restrict__ kv, const int* __restrict__ ki,
+                                                                               long long Np, long long N, int S, int window,
+                                                                               const int* __restrict__ col_off,
+                                                                               double* __restrict__ P, double* __restrict__ M,
+                                                                               double* __restrict__ data) {
+    __shared__ double sh[32];
+    __shared__ double s_carry;
+    const int s = blockIdx.x;
+    if (col_off[s + 1] - col_off[s] < 2) return;             // single replicate: sd stays NaN
+    const double* x = kv + (long long)s * Np;
+    const int* idx = ki + (long long)s * Np;
+    double* p = P + (long long)s * (Np + 1);
+    double* m = M + (long long)s * Np;
+    // exclusive prefix sums p[i] = sum_{t<i} x[t], i = 0..N
+    double carry = 0.0;
+    for (long long c0 = 0; c0 < N; c0 += kScanThreads) {
+        const long long i = c0 + threadIdx.x;
+        const double v = (i < N) ? x[i] : 0.0;
+        double total;
+        const double ex = block_exclusive_scan(v, sh, &total);
+        if (i < N) p[i] = carry + ex;
+        carry += total;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) p[N] = carry;
+    __syncthreads();
+    // window_smooth (preprocess.py:16-22), including its behaviour for short inputs: numpy slices clip, so
+    // the head is the mean of x[0:min(2w+1,N)] and the tail slice x[N-2w-1:] wraps when N < 2w+1; the tail
+    // assignment comes last and wins where the ranges overlap.
+    const long long w = window;
+    const double span = (double)(2 * w + 1);
+    const long long head_hi = (2 * w + 1 < N) ? 2 * w + 1 : N;
+    long long tail_lo = N - 2 * w - 1;
+    if (tail_lo < 0) { tail_lo += N; if (tail_lo < 0) tail_lo = 0; }
+    const double head = (p[head_hi] - p[0]) / (double)head_hi;              // np.mean(x[0:2w+1])
+    const double tail = (p[N] - p[tail_lo]) / (double)(N - tail_lo);        // np.mean(x[N-2w-1:])
+    for (long long k = threadIdx.x; k < N; k += kScanThreads) {
+        double v;
+        if (k >= N - w - 1) v = tail;
+        else if (k <= w) v = head;
+        else v = head + ((p[k + w + 2] - p[2 * w + 2]) - (p[k - w + 1] - p[1])) / span;
+        m[k] = v;
+    }
+    __syncthreads();
+    // reverse running maximum with NaN restart, chunked from the end; then sd = sqrt(m) to guide order
+    if (threadIdx.x == 0) s_carry = d_nan();         // "no carry" marker: the last element has no successor
+    __syncthreads();
+    for (long long hi = N; hi > 0; hi -= kScanThreads) {
+        const long long k = hi - 1 - threadIdx.x;                           // thread 0 takes the last element of the chunk
+        const bool live = (k >= 0);
+        double v = live ? m[k] : d_nan();
+        // segmented inclusive max-scan in reverse order == forward scan over threadIdx (thread t covers k = hi-1-t)
+        // flag = value is NaN (segment boundary: a NaN neither receives nor passes on a maximum)
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+        double cur = v;
+        bool open = (v == v);                      // can still take a maximum from earlier threads (later k)
+        bool blocked = !(v == v);                  // a NaN was seen in the span covered so far
+        for (int o = 1; o < 32; o <<= 1) {
+            const double pv = __shfl_up_sync(0xffffffffu, cur, o);
+            const int pb = __shfl_up_sync(0xffffffffu, (int)blocked, o);
+            if (lane >= o) {
+                if (!blocked && pv == pv && pv > cur && open) cur = pv;
+                blocked = blocked || (pb != 0);
+            }
+        }
+        // cross-warp: serial over warps through shared memory (32 warps)
+        __shared__ double w_last[32];
+        __shared__ int w_blocked[32];
+        __shared__ double w_in[32];
+        __syncthreads();
+        if (lane == 31) { w_last[warp] = cur; w_blocked[warp] = (int)blocked; }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double run = s_carry;                     // running max entering the chunk (NaN = none)
+            for (int q = 0; q < (int)(blockDim.x >> 5); ++q) {
+                w_in[q] = run;
+                // what leaves warp q: if the warp saw a NaN the incoming run is cut, the outgoing run is the warp's last value
+                const double last = w_last[q];
+                if (w_blocked[q]) run = last;          // last is the running max since the last NaN (or NaN itself)
+                else run = (run == run && (!(last == last) || run > last)) ? run : last;
+            }
+            s_carry = run;
+        }
+        __syncthreads();
+        const double incoming = w_in[warp];
+        // apply the incoming run to the lanes of this warp that are not behind a NaN of the same warp
+        // (blocked at lane t means a NaN at some lane <= t within the warp)
+        if (live && (v == v) && !blocked && incoming == incoming && incoming > cur) cur = incoming;
+        if (live && (v == v)) {
+            m[k] = cur;
+            data[((long long)idx[k] * S + s) * 2 + 1] = sqrt(cur);
+        } else if (live) {
+            data[((long long)idx[k] * S + s) * 2 + 1] = d_nan();
+        }
+        __syncthreads();
+    }
+}
+
+}  // namespace
+}  // namespace jacks
+
+using namespace jacks;
+
+static int lognorm_impl(JacksCtx* ctx, const double* d_counts, long long N, int C, double prior, const double* d_table,
+                        long long table_len, double* d_out, cudaStream_t st, double* T, double* med) {
+    dim3 tg((unsigned)((N + 31) / 32), (unsigned)((C + 31) / 32));
+    log_transpose_kernel<<<tg, 256, 0, st>>>(d_counts, N, C, prior, d_table, table_len, T, N);
+    column_median_kernel<<<C, 1024, 0, st>>>(T, N, N, nullptr, nullptr, 0, med);
+    untranspose_shift_kernel<<<tg, 256, 0, st>>>(T, N, N, C, med, nullptr, d_out);
+    ctx->launches += 3;
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_fail(e, "lognorm kernels");
+    return JACKS_OK;
+}
+
+extern "C" int jacks_lognorm_median_host(JacksCtx* ctx, const double* counts, int64_t n_guides, int32_t n_cols, double prior,
+                                         const double* log2_table, int64_t table_len, double* logcounts) {
+    if (!ctx || !counts || !logcounts) return fail(JACKS_E_INVALID, "jacks_lognorm_median_host: NULL argument");
+    if (n_guides < 1 || n_cols < 1) return fail(JACKS_E_INVALID, "empty count matrix");
+    cudaError_t e = cudaSetDevice(ctx->device);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaSetDevice");
+    const size_t mb = (size_t)n_guides * n_cols * sizeof(double);
+    int rc;
+    if ((rc = ctx->out[0].reserve(mb)) != JACKS_OK) return rc;
+    if ((rc = ctx->out[1].reserve(mb)) != JACKS_OK) return rc;
+    if ((rc = ctx->tmp.reserve(mb + (size_t)n_cols * sizeof(double))) != JACKS_OK) return rc;
+    if (!log2_table) table_len = 0;
+    if (table_len < 0) return fail(JACKS_E_INVALID, "table_len < 0");
+    if ((rc = ctx->out[2].reserve((size_t)table_len * sizeof(double) + 8)) != JACKS_OK) return rc;
+    cudaStream_t st = ctx->stream;
+    if ((e = cudaMemcpyAsync(ctx->out[0].p, counts, mb, cudaMemcpyHostToDevice, st)) != cudaSuccess) return cuda_fail(e, "H2D counts");
+    if (table_len && (e = cudaMemcpyAsync(ctx->out[2].p, log2_table, (size_t)table_len * sizeof(double), cudaMemcpyHostToDevice, st)) != cudaSuccess) return cuda_fail(e, "H2D log2 table");
+    double* T = (double*)ctx->tmp.p;
+    double* med = T + (size_t)n_guides * n_cols;
+    rc = lognorm_impl(ctx, (const double*)ctx->out[0].p, n_guides, n_cols, prior, table_len ? (const double*)ctx->out[2].p : nullptr,
+                      table_len, (double*)ctx->out[1].p, st, T, med);
+    if (rc != JACKS_OK) return rc;
+    if ((e = cudaMemcpyAsync(logcounts, ctx->out[1].p, mb, cudaMemcpyDeviceToHost, st)) != cudaSuccess) return cuda_fail(e, "D2H logcounts");
+    if ((e = cudaStreamSynchronize(st)) != cudaSuccess) return cuda_fail(e, "lognorm kernels");
+    return JACKS_OK;
+}
+
+extern "C" int jacks_condense_host(JacksCtx* ctx, const double* logcounts, int64_t n_guides, int32_t n_cols,
+                                   const int32_t* sample_col_offsets, const int32_t* sample_cols, int32_t n_samples,
+                                   double* data) {
+    if (!ctx || !logcounts || !sample_col_offsets || !sample_cols || !data) return fail(JACKS_E_INVALID, "jacks_condense_host: NULL argument");
+    if (n_guides < 1 || n_cols < 1 || n_samples < 1) return fail(JACKS_E_INVALID, "empty input");
+    const long long N = n_guides;
+    const int S = n_samples;
+    int max_rep = 0;
+    for (int s = 0; s < S; ++s) {
+        const int R = sample_col_offsets[s + 1] - sample_col_offsets[s];
+        if (R < 1) return fail(JACKS_E_INVALID, "sample %d has no replicate columns", s);
+        for (int r = sample_col_offsets[s]; r < sample_col_offsets[s + 1]; ++r)
+            if (sample_cols[r] < 0 || sample_cols[r] >= n_cols) return fail(JACKS_E_INVALID, "column index out of range");
+        max_rep = R > max_rep ? R : max_rep;
+    }
+    // window = min(max(int(N/100), 30), 800), preprocess.py:35
+    long long window = N / 100;
+    if (window < 30) window = 30;
+    if (window > 800) window = 800;
+    if (max_rep >= 2 && N < window + 1)      // the reference's window_smooth indexes m[0..window]: IndexError below that
+        return fail(JACKS_E_INVALID, "calc_posterior_sd needs at least %lld guides for its smoothing window (got %lld)", window + 1, N);
+    cudaError_t e = cudaSetDevice(ctx->device);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaSetDevice");
+    long long Np = kSortTile;
+    while (Np < N) Np <<= 1;
+    const size_t lb = (size_t)N * n_cols * sizeof(double), db = (size_t)N * S * 2 * sizeof(double);
+    const size_t nidx = (size_t)sample_col_offsets[S];
+    int rc;
+    if ((rc = ctx->out[0].reserve(lb)) != JACKS_OK) return rc;
+    if ((rc = ctx->out[1].reserve(db)) != JACKS_OK) return rc;
+    if ((rc = ctx->out[2].reserve((size_t)S * Np * sizeof(double))) != JACKS_OK) return rc;       // key: mean
+    if ((rc = ctx->out[3].reserve((size_t)S * Np * sizeof(double))) != JACKS_OK) return rc;       // key: var -> sorted var
+    if ((rc = ctx->out[4].reserve((size_t)S * Np * sizeof(int))) != JACKS_OK) return rc;          // key: index
+    if ((rc = ctx->out[5].reserve((size_t)S * (Np + 1) * sizeof(double))) != JACKS_OK) return rc; // prefix sums
+    if ((rc = ctx->out[6].reserve((size_t)S * Np * sizeof(double))) != JACKS_OK) return rc;       // smoothed
+    if ((rc = ctx->out[7].reserve((S + 1 + nidx) * sizeof(int))) != JACKS_OK) return rc;
+    cudaStream_t st = ctx->stream;
+    int* d_off = (int*)ctx->out[7].p;
+    int* d_cols = d_off + S + 1;
+    if ((e = cudaMemcpyAsync(ctx->out[0].p, logcounts, lb, cudaMemcpyHostToDevice, st)) != cudaSuccess) return cuda_fail(e, "H2D logcounts");
+    if ((e = cudaMemcpyAsync(d_off, sample_col_offsets, (S + 1) * sizeof(int), cudaMemcpyHostToDevice, st)) != cudaSuccess) return cuda_fail(e, "H2D offsets");
+    if ((e = cudaMemcpyAsync(d_cols, sample_cols, nidx * sizeof(int), cudaMemcpyHostToDevice, st)) != cudaSuccess) return cuda_fail(e, "H2D cols");
+    double* km = (double*)ctx->out[2].p; double* kv = (double*)ctx->out[3].p; int* ki = (int*)ctx->out[4].p;
+    dim3 sg((unsigned)((Np + 255) / 256), (unsigned)S);
+    sample_stats_kernel<<<sg, 256, 0, st>>>((const double*)ctx->out[0].p, N, n_cols, d_off, d_cols, S, Np, (double*)ctx->out[1].p, km, kv, ki);
+    ctx->launches++;
+    if (max_rep >= 2) {
+        // bitonic sort of every sample's Np keys: shared-memory phases for distances < kSortTile
+        dim3 lg((unsigned)(Np / kSortTile), (unsigned)S);
+        bitonic_local_kernel<<<lg, 1024, 0, st>>>(km, kv, ki, Np, 2, kSortTile);
+        ctx->launches++;
+        for (long long kk = 2LL * kSortTile; kk <= Np; kk <<= 1) {
+            for (long long j = kk >> 1; j >= kSortTile; j >>= 1) {
+                dim3 gg((unsigned)((Np / 2 + 255) / 256), (unsigned)S);
+                bitonic_global_kernel<<<gg, 256, 0, st>>>(km, kv, ki, Np, kk, j);
+                ctx->launches++;
+            }
+            bitonic_local_kernel<<<lg, 1024, 0, st>>>(km, kv, ki, Np, (int)kk, (int)kk);
+            ctx->launches++;
+        }
+        smooth_monotone_scatter_kernel<<<S, kScanThreads, 0, st>>>(kv, ki, Np, N, S, (int)window, d_off, (double*)ctx->out[5].p,
+                                                                   (double*)ctx->out[6].p, (double*)ctx->out[1].p);
+        ctx->launches++;
+    }
+    if ((e = cudaGetLastError()) != cudaSuccess) return cuda_fail(e, "condense kernels");
+    if ((e = cudaMemcpyAsync(data, ctx->out[1].p, db, cudaMemcpyDeviceToHost, st)) != cudaSuccess) return cuda_fail(e, "D2H data");
+    if ((e = cudaStreamSynchronize(st)) != cudaSuccess) return cuda_fail(e, "condense kernels");
+    return JACKS_OK;
+}
