@@ -14,9 +14,9 @@
  *   jacks/jacks/infer.py:55   inferJACKSGene (per-gene EM)     jacks_em_batched_host
  *   jacks/jacks/jacks_io.py:416  pseudo-gene EM                same, with a row-gather CSR index
  *   jacks/jacks/jacks_io.py:69   computeW1PvalsAndFDRs         jacks_kde_pvalues_device / _host
- *   jacks/jacks/preprocess.py:77 normalizeLogCounts (median)   jacks_preprocess_host (step 1-2)
- *   jacks/jacks/preprocess.py:61 condense_normalised_counts    jacks_preprocess_host (step 3)
- *   jacks/jacks/preprocess.py:25 calc_posterior_sd             jacks_posterior_sd_host / jacks_preprocess_host
+ *   jacks/jacks/preprocess.py:77 normalizeLogCounts            jacks_normalize_host
+ *   jacks/jacks/preprocess.py:61 condense_normalised_counts    jacks_condense_host
+ *   jacks/jacks/preprocess.py:25 calc_posterior_sd             jacks_condense_host (one sample)
  *
  * All floating point data is IEEE float64.  All arrays are dense, C order.  "device"
  * entry points take pointers into the current CUDA device's memory and enqueue work on
@@ -172,28 +172,39 @@ JACKS_API int jacks_kde_pvalues_host(JacksCtx* ctx, const double* w1_genes, int6
                            int32_t positive, double* pvals);
 
 /*
- * Mean-variance error model for one or more samples (calc_posterior_sd with the default arguments,
- * preprocess.py:25-58, as called from condense_normalised_counts, preprocess.py:61-67).
+ * Mean-variance error model for one or more samples (calc_posterior_sd, preprocess.py:25-58, as called from
+ * condense_normalised_counts, preprocess.py:61-67).
  *   logcounts [n_guides, n_cols]   normalised log2 counts
  *   sample_col_offsets[n_samples+1], sample_cols[...]   CSR list of the replicate columns of each sample
+ *   window_override   <= 0: window = min(max(int(n_guides/100), 30), 800) (preprocess.py:35); > 0: use this
+ *                     half-width (calc_posterior_sd's windowfracN argument resolved by the caller)
+ *   monotonize        non-zero: enforce the reverse running maximum (do_monotonize=True, the default)
  *   data [n_guides, n_samples, 2]  out: (mean over replicates, posterior sd); sd is NaN for a
  *                                  single-replicate sample (preprocess.py:32)
+ * Fails with JACKS_E_INVALID when n_guides <= window (the reference raises IndexError there).
  */
 JACKS_API int jacks_condense_host(JacksCtx* ctx, const double* logcounts, int64_t n_guides, int32_t n_cols,
                         const int32_t* sample_col_offsets, const int32_t* sample_cols, int32_t n_samples,
-                        double* data);
+                        int32_t window_override, int32_t monotonize, double* data);
 
 /*
- * Counts -> normalised log counts (preprocess.py:147 and normalizeLogCounts with normtype 'median',
- * preprocess.py:77-81): out[i,c] = log2(counts[i,c] + prior) - nanmedian_i(log2(counts[.,c] + prior)).
- *   counts [n_guides, n_cols] float64 (the reference eval()s each cell, so non-integers are legal)
+ * Per-column normalisation of log counts, normalizeLogCounts (preprocess.py:77-96), optionally fused with the
+ * count -> log2(count + prior) map of the loader (preprocess.py:147).
+ *   values [n_guides, n_cols]  counts (take_log != 0; the reference eval()s each cell, so non-integers are
+ *                              legal) or log counts (take_log == 0)
  *   log2_table (optional, may be NULL): table_len host-computed values log2(k + prior), k = 0..table_len-1.
  *       Integer counts below table_len take their logarithm from the table, i.e. from the caller's own
  *       libm/numpy, which makes the result bit-identical to the reference run on that host; other counts
  *       use the device log2 (<= 1 ulp).
+ *   normtype  JACKS_NORM_MEDIAN       x - nanmedian(x)                                    (:80-81)
+ *             JACKS_NORM_ZMAD         (x - nanmedian(x)) / (1.4826 * nanmedian|x - med|)    (:82-84)
+ *             JACKS_NORM_CTRL_GUIDES  x - nanmedian(x[row_mask != 0])                      (:92-94)
+ *   row_mask [n_guides] bytes, required for JACKS_NORM_CTRL_GUIDES only.
  */
-JACKS_API int jacks_lognorm_median_host(JacksCtx* ctx, const double* counts, int64_t n_guides, int32_t n_cols,
-                              double prior, const double* log2_table, int64_t table_len, double* logcounts);
+enum { JACKS_NORM_MEDIAN = 0, JACKS_NORM_ZMAD = 1, JACKS_NORM_CTRL_GUIDES = 2 };
+JACKS_API int jacks_normalize_host(JacksCtx* ctx, const double* values, int64_t n_guides, int32_t n_cols, int32_t take_log,
+                         double prior, const double* log2_table, int64_t table_len, int32_t normtype,
+                         const uint8_t* row_mask, double* out);
 
 /* FP64 FMA-pipe peak of the current device in FLOP/s (dependent-chain-free DFMA microbenchmark);
  * bench.py uses it as the roofline denominator because MEASURED_PEAKS.json has no FP64 entry. */

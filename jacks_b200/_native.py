@@ -85,8 +85,8 @@ def lib():
             L.jacks_kde_pvalues_device.argtypes = [vp, vp, i64, vp, i64, i32, i32, vp, vp]
             L.jacks_kde_pvalues_host.argtypes = [vp, vp, i64, vp, i64, i32, i32, vp]
         if hasattr(L, 'jacks_condense_host'):
-            L.jacks_condense_host.argtypes = [vp, vp, i64, i32, vp, vp, i32, vp]
-            L.jacks_lognorm_median_host.argtypes = [vp, vp, i64, i32, dbl, vp, i64, vp]
+            L.jacks_condense_host.argtypes = [vp, vp, i64, i32, vp, vp, i32, i32, i32, vp]
+            L.jacks_normalize_host.argtypes = [vp, vp, i64, i32, i32, dbl, vp, i64, i32, vp, vp]
         _lib = L
     return _lib
 
@@ -286,28 +286,37 @@ def kde_pvalues_host(ctx, w1_genes, w1_pseudo, positive=False):
 LOG2_TABLE_MAX = 1 << 24
 
 
-def lognorm_median_host(ctx, counts, prior, use_table=True):
-    """log2(counts + prior) minus the per-column nanmedian, on the GPU.  Integer counts take their logarithm
-    from a table this host computes with numpy (bit-identical to the reference's np.log2 on the same machine)."""
-    counts = np.ascontiguousarray(counts, dtype=np.float64)
-    out = np.empty(counts.shape, dtype=np.float64)
+NORM_TYPES = {'median': 0, 'zmad': 1, 'ctrl_guides': 2}
+
+
+def normalize_host(ctx, values, normtype='median', take_log=False, prior=32.0, row_mask=None, use_table=True):
+    """normalizeLogCounts on the GPU, optionally fused with log2(count + prior).  Integer counts take their
+    logarithm from a table this host computes with numpy (bit-identical to the reference's np.log2 here)."""
+    values = np.ascontiguousarray(values, dtype=np.float64)
+    out = np.empty(values.shape, dtype=np.float64)
     table = None
-    if use_table and counts.size:
-        finite = counts[np.isfinite(counts)]
+    if take_log and use_table and values.size:
+        finite = values[np.isfinite(values)]
         top = int(min(finite.max(), LOG2_TABLE_MAX - 1)) if finite.size and finite.max() >= 0 else -1
         if top >= 0:
             table = np.log2(np.arange(top + 1, dtype=np.float64) + prior)
-    check(lib().jacks_lognorm_median_host(ctx.h, _ptr(counts), counts.shape[0], counts.shape[1], float(prior),
-                                          _ptr(table), 0 if table is None else table.size, _ptr(out)))
+    mask = None if row_mask is None else np.ascontiguousarray(row_mask, dtype=np.uint8)
+    check(lib().jacks_normalize_host(ctx.h, _ptr(values), values.shape[0], values.shape[1], int(bool(take_log)), float(prior),
+                                     _ptr(table), 0 if table is None else table.size, NORM_TYPES[normtype], _ptr(mask),
+                                     _ptr(out)))
     return out
 
 
-def condense_host(ctx, logcounts, Iscreens):
+def lognorm_median_host(ctx, counts, prior, use_table=True):
+    return normalize_host(ctx, counts, 'median', take_log=True, prior=prior, use_table=use_table)
+
+
+def condense_host(ctx, logcounts, Iscreens, window=0, monotonize=True):
     logcounts = np.ascontiguousarray(logcounts, dtype=np.float64)
     offs = np.zeros(len(Iscreens) + 1, dtype=np.int32)
     offs[1:] = np.cumsum([len(c) for c in Iscreens])
     cols = np.ascontiguousarray(np.concatenate([np.asarray(c, dtype=np.int32) for c in Iscreens]) if len(Iscreens) else np.zeros(0, np.int32), dtype=np.int32)
     data = np.empty((logcounts.shape[0], len(Iscreens), 2), dtype=np.float64)
     check(lib().jacks_condense_host(ctx.h, _ptr(logcounts), logcounts.shape[0], logcounts.shape[1], _ptr(offs),
-                                    _ptr(cols), len(Iscreens), _ptr(data)))
+                                    _ptr(cols), len(Iscreens), int(window), int(bool(monotonize)), _ptr(data)))
     return data

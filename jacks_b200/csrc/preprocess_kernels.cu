@@ -49,7 +49,7 @@ __device__ __forceinline__ double unsortable(unsigned long long k) {
 // <= 1 ulp too, but not the same ulp, and a last-bit difference can swap two guides whose means tie to
 // within an ulp in the (mean, var, index) sort downstream -- a visible change of their smoothed sd.
 __global__ void __launch_bounds__(256) log_transpose_kernel(const double* __restrict__ counts, long long N, int C,
-                                                            double prior, const double* __restrict__ log2_table,
+                                                            double prior, int take_log, const double* __restrict__ log2_table,
                                                             long long table_len, double* __restrict__ T, long long ldT) {
     __shared__ double tile[32][33];
     const long long i0 = (long long)blockIdx.x * 32;
@@ -61,7 +61,8 @@ __global__ void __launch_bounds__(256) log_transpose_kernel(const double* __rest
         double v = 0.0;
         if (i < N && c < C) {
             const double cnt = counts[i * C + c];
-            if (log2_table && cnt >= 0.0 && cnt < (double)table_len && cnt == floor(cnt)) v = log2_table[(long long)cnt];
+            if (!take_log) v = cnt;
+            else if (log2_table && cnt >= 0.0 && cnt < (double)table_len && cnt == floor(cnt)) v = log2_table[(long long)cnt];
             else v = log2(cnt + prior);
         }
         tile[r][tx] = v;
@@ -287,7 +288,7 @@ __device__ double block_exclusive_scan(double v, double* sh, double* total) {
 
 __global__ void __launch_bounds__(kScanThreads) smooth_monotone_scatter_kernel(const double* __restrict__ kv, const int* __restrict__ ki,
                                                                                long long Np, long long N, int S, int window,
-                                                                               const int* __restrict__ col_off,
+                                                                               int monotonize, const int* __restrict__ col_off,
                                                                                double* __restrict__ P, double* __restrict__ M,
                                                                                double* __restrict__ data) {
     __shared__ double sh[32];
@@ -373,6 +374,7 @@ __global__ void __launch_bounds__(kScanThreads) smooth_monotone_scatter_kernel(c
         // apply the incoming run to the lanes of this warp that are not behind a NaN of the same warp
         // (blocked at lane t means a NaN at some lane <= t within the warp)
         if (live && (v == v) && !blocked && incoming == incoming && incoming > cur) cur = incoming;
+        if (!monotonize) cur = v;                  // calc_posterior_sd(do_monotonize=False)
         if (live && (v == v)) {
             m[k] = cur;
             data[((long long)idx[k] * S + s) * 2 + 1] = sqrt(cur);
@@ -388,48 +390,60 @@ __global__ void __launch_bounds__(kScanThreads) smooth_monotone_scatter_kernel(c
 
 using namespace jacks;
 
-static int lognorm_impl(JacksCtx* ctx, const double* d_counts, long long N, int C, double prior, const double* d_table,
-                        long long table_len, double* d_out, cudaStream_t st, double* T, double* med) {
-    dim3 tg((unsigned)((N + 31) / 32), (unsigned)((C + 31) / 32));
-    log_transpose_kernel<<<tg, 256, 0, st>>>(d_counts, N, C, prior, d_table, table_len, T, N);
-    column_median_kernel<<<C, 1024, 0, st>>>(T, N, N, nullptr, nullptr, 0, med);
-    untranspose_shift_kernel<<<tg, 256, 0, st>>>(T, N, N, C, med, nullptr, d_out);
-    ctx->launches += 3;
-    cudaError_t e = cudaGetLastError();
-    if (e != cudaSuccess) return cuda_fail(e, "lognorm kernels");
-    return JACKS_OK;
-}
-
-extern "C" int jacks_lognorm_median_host(JacksCtx* ctx, const double* counts, int64_t n_guides, int32_t n_cols, double prior,
-                                         const double* log2_table, int64_t table_len, double* logcounts) {
-    if (!ctx || !counts || !logcounts) return fail(JACKS_E_INVALID, "jacks_lognorm_median_host: NULL argument");
-    if (n_guides < 1 || n_cols < 1) return fail(JACKS_E_INVALID, "empty count matrix");
+extern "C" int jacks_normalize_host(JacksCtx* ctx, const double* values, int64_t n_guides, int32_t n_cols, int32_t take_log,
+                                    double prior, const double* log2_table, int64_t table_len, int32_t normtype,
+                                    const uint8_t* row_mask, double* out) {
+    if (!ctx || !values || !out) return fail(JACKS_E_INVALID, "jacks_normalize_host: NULL argument");
+    if (n_guides < 1 || n_cols < 1) return fail(JACKS_E_INVALID, "empty matrix");
+    if (normtype < JACKS_NORM_MEDIAN || normtype > JACKS_NORM_CTRL_GUIDES) return fail(JACKS_E_INVALID, "Unrecognised normalisation type %d", normtype);
+    if (normtype == JACKS_NORM_CTRL_GUIDES && !row_mask) return fail(JACKS_E_INVALID, "No guides specified for ctrl guide normalization");
     cudaError_t e = cudaSetDevice(ctx->device);
     if (e != cudaSuccess) return cuda_fail(e, "cudaSetDevice");
-    const size_t mb = (size_t)n_guides * n_cols * sizeof(double);
+    const long long N = n_guides;
+    const int C = n_cols;
+    const size_t mb = (size_t)N * C * sizeof(double);
+    if (!log2_table || !take_log) table_len = 0;
+    if (table_len < 0) return fail(JACKS_E_INVALID, "table_len < 0");
     int rc;
     if ((rc = ctx->out[0].reserve(mb)) != JACKS_OK) return rc;
     if ((rc = ctx->out[1].reserve(mb)) != JACKS_OK) return rc;
-    if ((rc = ctx->tmp.reserve(mb + (size_t)n_cols * sizeof(double))) != JACKS_OK) return rc;
-    if (!log2_table) table_len = 0;
-    if (table_len < 0) return fail(JACKS_E_INVALID, "table_len < 0");
     if ((rc = ctx->out[2].reserve((size_t)table_len * sizeof(double) + 8)) != JACKS_OK) return rc;
+    if ((rc = ctx->out[3].reserve((size_t)N + 8)) != JACKS_OK) return rc;
+    if ((rc = ctx->tmp.reserve(mb + 2 * (size_t)C * sizeof(double))) != JACKS_OK) return rc;
     cudaStream_t st = ctx->stream;
-    if ((e = cudaMemcpyAsync(ctx->out[0].p, counts, mb, cudaMemcpyHostToDevice, st)) != cudaSuccess) return cuda_fail(e, "H2D counts");
+    if ((e = cudaMemcpyAsync(ctx->out[0].p, values, mb, cudaMemcpyHostToDevice, st)) != cudaSuccess) return cuda_fail(e, "H2D values");
     if (table_len && (e = cudaMemcpyAsync(ctx->out[2].p, log2_table, (size_t)table_len * sizeof(double), cudaMemcpyHostToDevice, st)) != cudaSuccess) return cuda_fail(e, "H2D log2 table");
+    const unsigned char* d_mask = nullptr;
+    if (normtype == JACKS_NORM_CTRL_GUIDES) {
+        if ((e = cudaMemcpyAsync(ctx->out[3].p, row_mask, (size_t)N, cudaMemcpyHostToDevice, st)) != cudaSuccess) return cuda_fail(e, "H2D row mask");
+        d_mask = (const unsigned char*)ctx->out[3].p;
+    }
     double* T = (double*)ctx->tmp.p;
-    double* med = T + (size_t)n_guides * n_cols;
-    rc = lognorm_impl(ctx, (const double*)ctx->out[0].p, n_guides, n_cols, prior, table_len ? (const double*)ctx->out[2].p : nullptr,
-                      table_len, (double*)ctx->out[1].p, st, T, med);
-    if (rc != JACKS_OK) return rc;
-    if ((e = cudaMemcpyAsync(logcounts, ctx->out[1].p, mb, cudaMemcpyDeviceToHost, st)) != cudaSuccess) return cuda_fail(e, "D2H logcounts");
-    if ((e = cudaStreamSynchronize(st)) != cudaSuccess) return cuda_fail(e, "lognorm kernels");
+    double* med = T + (size_t)N * C;
+    double* mad = med + C;
+    dim3 tg((unsigned)((N + 31) / 32), (unsigned)((C + 31) / 32));
+    log_transpose_kernel<<<tg, 256, 0, st>>>((const double*)ctx->out[0].p, N, C, prior, take_log ? 1 : 0,
+                                             table_len ? (const double*)ctx->out[2].p : nullptr, table_len, T, N);
+    column_median_kernel<<<C, 1024, 0, st>>>(T, N, N, d_mask, nullptr, 0, med);                 // preprocess.py:81 / :93
+    ctx->launches += 2;
+    const double* scale = nullptr;
+    if (normtype == JACKS_NORM_ZMAD) {                                                            // preprocess.py:82-84
+        column_median_kernel<<<C, 1024, 0, st>>>(T, N, N, nullptr, med, 1, mad);
+        scale_mad_kernel<<<(C + 255) / 256, 256, 0, st>>>(mad, C);
+        scale = mad;
+        ctx->launches += 2;
+    }
+    untranspose_shift_kernel<<<tg, 256, 0, st>>>(T, N, N, C, med, scale, (double*)ctx->out[1].p);
+    ctx->launches++;
+    if ((e = cudaGetLastError()) != cudaSuccess) return cuda_fail(e, "normalize kernels");
+    if ((e = cudaMemcpyAsync(out, ctx->out[1].p, mb, cudaMemcpyDeviceToHost, st)) != cudaSuccess) return cuda_fail(e, "D2H normalised");
+    if ((e = cudaStreamSynchronize(st)) != cudaSuccess) return cuda_fail(e, "normalize kernels");
     return JACKS_OK;
 }
 
 extern "C" int jacks_condense_host(JacksCtx* ctx, const double* logcounts, int64_t n_guides, int32_t n_cols,
                                    const int32_t* sample_col_offsets, const int32_t* sample_cols, int32_t n_samples,
-                                   double* data) {
+                                   int32_t window_override, int32_t monotonize, double* data) {
     if (!ctx || !logcounts || !sample_col_offsets || !sample_cols || !data) return fail(JACKS_E_INVALID, "jacks_condense_host: NULL argument");
     if (n_guides < 1 || n_cols < 1 || n_samples < 1) return fail(JACKS_E_INVALID, "empty input");
     const long long N = n_guides;
@@ -446,6 +460,7 @@ extern "C" int jacks_condense_host(JacksCtx* ctx, const double* logcounts, int64
     long long window = N / 100;
     if (window < 30) window = 30;
     if (window > 800) window = 800;
+    if (window_override > 0) window = window_override;
     if (max_rep >= 2 && N < window + 1)      // the reference's window_smooth indexes m[0..window]: IndexError below that
         return fail(JACKS_E_INVALID, "calc_posterior_sd needs at least %lld guides for its smoothing window (got %lld)", window + 1, N);
     cudaError_t e = cudaSetDevice(ctx->device);
@@ -487,7 +502,7 @@ extern "C" int jacks_condense_host(JacksCtx* ctx, const double* logcounts, int64
             bitonic_local_kernel<<<lg, 1024, 0, st>>>(km, kv, ki, Np, (int)kk, (int)kk);
             ctx->launches++;
         }
-        smooth_monotone_scatter_kernel<<<S, kScanThreads, 0, st>>>(kv, ki, Np, N, S, (int)window, d_off, (double*)ctx->out[5].p,
+        smooth_monotone_scatter_kernel<<<S, kScanThreads, 0, st>>>(kv, ki, Np, N, S, (int)window, monotonize ? 1 : 0, d_off, (double*)ctx->out[5].p,
                                                                    (double*)ctx->out[6].p, (double*)ctx->out[1].p);
         ctx->launches++;
     }

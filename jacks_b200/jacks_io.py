@@ -1,0 +1,420 @@
+"""Drop-in for the reference module ``jacks.jacks_io`` (jacks/jacks/jacks_io.py): specification readers,
+pseudo-gene construction, p-values, result writers, orchestration and the command-line parser, with
+the same names, arguments, defaults, file formats and error messages.
+
+Host side by design (as in the reference): file parsing, the ``random`` draws of the pseudo-genes,
+gene ranking, Benjamini-Hochberg sets and text formatting -- so that indexing and ranking are
+bit-exact.  GPU side: the EM (``inferJACKS``), the preprocessing error model and the KDE p-values
+(``computeW1PvalsAndFDRs`` with pseudo=True, the only branch the command line reaches).
+"""
+import argparse
+import csv
+import io
+import os
+import random
+
+import numpy as np
+
+from . import _native
+from .infer import LOG, inferJACKS
+from .preprocess import loadDataAndPreprocess, collateTestControlSamples
+
+REP_HDR_DEFAULT = "Replicate"
+SAMPLE_HDR_DEFAULT = "Sample"
+COMMON_CTRL_SAMPLE_DEFAULT = "CONTROL"
+SGRNA_HDR_DEFAULT = "sgRNA"
+GENE_HDR_DEFAULT = "Gene"
+OUTPREFIX_DEFAULT = ""
+APPLY_W_HP_DEFAULT = False
+PICKLE_FILENAME = '_JACKS_results_full.pickle'
+NORM_TYPE_DEFAULT = 'median'
+GENE_FILENAME = '_gene_JACKS_results.txt'
+GRNA_FILENAME = '_grna_JACKS_results.txt'
+
+
+def getGeneWs(jacks_results, gene):
+    return jacks_results[gene][4]
+
+
+def getSortedGenes(jacks_results, positive):
+    """[(mean w1 over lines, gene)] ranked by effect, strongest depletion first (enrichment first if
+    ``positive``); ties break on the gene name (jacks_io.py:26-31)."""
+    ordered_genes = [(np.nanmean(jacks_results[gene][4]), gene) for gene in jacks_results]
+    ordered_genes.sort(reverse=bool(positive))
+    return ordered_genes
+
+
+def getFDRGeneSets(jacks_w1_pvals, fdr):
+    """Per cell line the set of genes passing Benjamini-Hochberg at ``fdr`` (jacks_io.py:52-61)."""
+    fdr_gene_sets = []
+    a_gene = [x for x in jacks_w1_pvals][0]
+    n = len(jacks_w1_pvals)
+    for sample_idx in range(len(jacks_w1_pvals[a_gene])):
+        pval_genes = sorted((jacks_w1_pvals[gene][sample_idx], gene) for gene in jacks_w1_pvals)
+        below_idxs = [i for i, (pval, gene) in enumerate(pval_genes) if pval < fdr * (i + 1) / n]
+        k = max(below_idxs) if len(below_idxs) > 0 else -1
+        fdr_gene_sets.append(set(gene for (pval, gene) in pval_genes[:k + 1]))
+    return fdr_gene_sets
+
+
+def getLocalFDRGeneSets(jacks_w1_fdrs, test_sample_ids, fdr):
+    """Genes whose local fdr is below the threshold, per line.  (The reference's version of this function,
+    jacks_io.py:63-67, cannot run: it is called with two arguments and refers to an undefined name.)"""
+    return [set(gene for gene in jacks_w1_fdrs if jacks_w1_fdrs[gene][sample_idx] < fdr)
+            for sample_idx, _ in enumerate(test_sample_ids)]
+
+
+def computeW1PvalsAndFDRs(jacks_results, test_sample_ids, noness_genes=set(), pseudo=False, compute_fdr=False,
+                          positive=False):
+    """P-value of every gene's w1, per cell line, under the Gaussian-KDE null built from the w1 of the
+    ``noness_genes`` (jacks_io.py:69-89).  Returns ({gene: pvals[L]}, {gene: fdrs[L]}).
+
+    The KDE sums run on the GPU (jacks_kde_pvalues_host).  Only the pseudo=True, compute_fdr=False branch --
+    the one ``writeJacksWResults`` reaches from the command line -- is available."""
+    if not pseudo or compute_fdr:
+        raise NotImplementedError('computeW1PvalsAndFDRs: only pseudo=True, compute_fdr=False runs on the GPU path '
+                                  '(leave-one-out control kernels and the local fdr are not implemented)')
+    genes = [g for g in jacks_results]
+    L = len(test_sample_ids)
+    w1_fdrs = {gene: np.zeros(L) for gene in genes}
+    if len(genes) == 0:
+        return {}, w1_fdrs
+    w1_all = np.stack([np.asarray(jacks_results[g][4], dtype=np.float64) for g in genes])
+    null_rows = [i for i, g in enumerate(genes) if g in noness_genes]
+    pv = _native.kde_pvalues_host(_native.context(0), w1_all, w1_all[null_rows], positive=positive)
+    w1_pvals = {gene: pv[i] for i, gene in enumerate(genes)}
+    return w1_pvals, w1_fdrs
+
+
+def writeJacksWResults(outprefix, jacks_results, cell_lines, write_types=[''], ctrl_geneset=set(), fdr=None,
+                       fdr_thresh_type='REGULAR', pseudo=False, positive=False):
+    """Gene-level result tables, one file per write type ('' = E[w], '_std', '_pval', '_fdr'), genes ranked by
+    mean w1, values formatted '%5e' (jacks_io.py:91-133)."""
+    ordered_genes = getSortedGenes(jacks_results, positive)
+    fouts = [io.open(outprefix + '_gene%s_JACKS_results.txt' % write_type, 'w') for write_type in write_types]
+    for fout in fouts:
+        fout.write(u'Gene\t%s\n' % ('\t'.join(cell_lines)))
+    if '_fdr' in write_types or '_pval' in write_types:
+        LOG.info('Computing P-values for %s selection' % ('positive' if positive else 'negative'))
+        jacks_w1_pvals, jacks_w1_fdrs = computeW1PvalsAndFDRs(jacks_results, cell_lines, noness_genes=ctrl_geneset,
+                                                              pseudo=pseudo, compute_fdr=('_fdr' in write_types),
+                                                              positive=positive)
+    if fdr is not None:
+        if fdr_thresh_type == 'REGULAR':
+            fdr_sets = getFDRGeneSets(jacks_w1_pvals, fdr)
+        elif fdr_thresh_type == 'LOCAL_FDR':
+            fdr_sets = getLocalFDRGeneSets(jacks_w1_fdrs, cell_lines, fdr)
+        else:
+            raise Exception('Unrecognised FDR threshold type (expecting REGULAR or LOCAL_FDR): ', fdr_thresh_type)
+
+    for w1_mean, gene in ordered_genes:
+        w1, w2 = jacks_results[gene][4], jacks_results[gene][5]
+        if fdr is not None:
+            sig_gene_flags = [(gene in x) for x in fdr_sets]
+        else:
+            sig_gene_flags = [True for x in w1]
+        if sum(sig_gene_flags) == 0:
+            continue
+        if 'JACKS_PSEUDO_GENE' in gene:
+            continue                                  # pseudo-genes are never written (jacks_io.py:131)
+        for write_type, fout in zip(write_types, fouts):
+            if write_type == '_pval':
+                vals = ['%5e' % x for x in jacks_w1_pvals[gene]]
+            elif write_type == '_fdr':
+                vals = ['%5e' % x for x in jacks_w1_fdrs[gene]]
+            elif write_type == '_std':
+                vals = ['%5e' % np.sqrt(b - a ** 2.0) for (a, b) in zip(w1, w2)]
+            elif write_type == '':
+                vals = [('%5e' % a) if flag else '' for (a, flag) in zip(w1, sig_gene_flags)]
+            else:
+                raise Exception('Unrecognised write type: %s' % write_type)
+            fout.write(u'%s\t%s\n' % (gene, '\t'.join(vals)))
+    for fout in fouts:
+        fout.close()
+
+
+def writeJacksXResults(filename, jacks_results, gene_grnas):
+    """Guide efficacies sgrna / X1 / X2, guides grouped by gene, genes ranked by mean w1 (jacks_io.py:135-146)."""
+    ordered_genes = sorted((np.nanmean(jacks_results[gene][4]), gene) for gene in jacks_results)
+    fout = io.open(filename, 'w')
+    fout.write(u'sgrna\tX1\tX2\n')
+    for w1_mean, gene in ordered_genes:
+        y, tau, x1, x2, w1, w2 = jacks_results[gene]
+        for i, grna in enumerate(gene_grnas[gene]):
+            fout.write(u'%s\t%5e\t%5e\n' % (grna, x1[i], x2[i]))
+    fout.close()
+
+
+def writeFoldChanges(filename, testdata, ctrldata, meta, sample_ids, write_std=False, write_raw=False):
+    """Per-guide log fold changes (or their standard deviations) against the control (jacks_io.py:148-156)."""
+    fout = io.open(filename, 'w')
+    fout.write(u'gRNA\tgene\t%s\n' % '\t'.join(sample_ids))
+    for i in range(len(meta[:, 0])):
+        if write_std:
+            vals = [np.sqrt(x ** 2.0 + y ** 2.0) for (x, y) in zip(testdata[i, :, 1], ctrldata[i, :, 1])]
+        elif write_raw:
+            vals = [np.sqrt(x ** 2.0 + y ** 2.0) for (x, y) in zip(testdata[i, :, 2], ctrldata[i, :, 2])]
+        else:
+            vals = testdata[i, :, 0] - ctrldata[i, :, 0]
+        fout.write(u'%s\t%s\t%s\n' % (meta[i, 0], meta[i, 1], '\t'.join(['%6e' % x for x in vals])))
+    fout.close()
+
+
+def writeLogData(filename, data, meta, sample_ids, write_std=False, write_raw=False):
+    """Per-guide condensed log counts (mean, sd or raw plane) of every sample (jacks_io.py:158-166)."""
+    fout = io.open(filename, 'w')
+    fout.write(u'gRNA\tgene\t%s\n' % '\t'.join(sample_ids))
+    plane = 1 if write_std else (2 if write_raw else 0)
+    for i in range(len(meta[:, 0])):
+        fout.write(u'%s\t%s\t%s\n' % (meta[i, 0], meta[i, 1], '\t'.join(['%6e' % x for x in data[i, :, plane]])))
+    fout.close()
+
+
+def pickleJacksFullResults(filename, jacks_results, cell_lines, gene_grnas):
+    """[jacks_results, cell_lines, gene_grnas] -- the layout plot_heatmap.py and the web server load (jacks_io.py:168-173)."""
+    import pickle
+    with io.open(filename, 'wb') as f:
+        pickle.dump([jacks_results, cell_lines, gene_grnas], f)
+
+
+def loadJacksFullResultsFromPickle(filename):
+    import pickle
+    with io.open(filename, 'rb') as f:
+        jacks_results, cell_lines, gene_grnas = pickle.load(f)
+    return jacks_results, cell_lines, gene_grnas
+
+
+def prepareFile(filename, hdr):
+    """Open ``filename`` positioned at the header line containing ``hdr`` (at most 100 lines are skipped) and
+    guess the delimiter from the extension (jacks_io.py:182-197)."""
+    f = io.open(filename)
+    skip_lines, line = 0, f.readline()
+    while hdr not in line and skip_lines < 100:
+        skip_lines += 1
+        line = f.readline()
+    f.close()
+    if skip_lines >= 100:
+        raise Exception('Could not find line with header ' + hdr + ' in ' + filename)
+    delim = ',' if (filename.split('.')[-1] == 'csv') else '\t'
+    f = io.open(filename)
+    for i in range(skip_lines):
+        f.readline()
+    return f, delim
+
+
+def createSampleSpec(infile, repfile, rep_hdr, sample_hdr, common_ctrl_sample, ctrl_sample_hdr=None):
+    """Replicate map -> ({infile: [(sample_id, replicate column)]}, {sample: control sample}, {sample: n replicates})
+    (jacks_io.py:200-226)."""
+    f, delim = prepareFile(repfile, rep_hdr)
+    rdr = csv.DictReader(f, delimiter=delim)
+    sample_spec, sample_num_reps = {infile: []}, {}
+    ctrl_per_sample = ctrl_sample_hdr is not None
+    if ctrl_per_sample and ctrl_sample_hdr not in rdr.fieldnames:
+        raise Exception('Could not find column %s specifying controls in %s' % (ctrl_sample_hdr, repfile))
+    ctrl_spec = {}
+    for row in rdr:
+        sample_id, rep_id = row[sample_hdr], row[rep_hdr]
+        sample_num_reps[sample_id] = sample_num_reps.get(sample_id, 0) + 1
+        sample_spec[infile].append((sample_id, rep_id))
+        if ctrl_per_sample:
+            if sample_id in ctrl_spec:
+                if ctrl_spec[sample_id] != row[ctrl_sample_hdr]:
+                    err_msg = '%s vs %s for %s\n' % (ctrl_spec[sample_id], row[ctrl_sample_hdr], sample_id)
+                    raise Exception(err_msg + 'Different controls for replicates of the sample not supported.')
+            else:
+                ctrl_spec[sample_id] = row[ctrl_sample_hdr]
+        else:
+            ctrl_spec[sample_id] = common_ctrl_sample
+    f.close()
+    if not ctrl_per_sample and common_ctrl_sample not in ctrl_spec:
+        raise Exception('Could not find control sample %s in %s' % (common_ctrl_sample, repfile))
+    return sample_spec, ctrl_spec, sample_num_reps
+
+
+def createGeneSpec(guidemappingfile, sgrna_hdr, gene_hdr, ignore_blank_genes=True):
+    """Guide map -> {guide: gene} (jacks_io.py:229-234)."""
+    f, delim = prepareFile(guidemappingfile, sgrna_hdr)
+    rdr = csv.DictReader(f, delimiter=delim)
+    gene_spec = {row[sgrna_hdr]: row[gene_hdr] for row in rdr if (not ignore_blank_genes or row[gene_hdr] != '')}
+    f.close()
+    return gene_spec
+
+
+def readControlGeneset(ctrl_genes, gene_spec):
+    """A gene name, or a file with one gene identifier per line; unknown genes are dropped (jacks_io.py:237-248)."""
+    known_genes = set(gene_spec[x] for x in gene_spec)
+    if os.path.isfile(ctrl_genes):
+        with io.open(ctrl_genes) as f:
+            geneset = set(line.split()[0] for line in f if line.split()[0] in known_genes)
+        LOG.info('Read %d recognised control genes from %s' % (len(geneset), ctrl_genes))
+    else:
+        if ctrl_genes not in known_genes:
+            raise Exception('Not a file or unrecognised control gene: %s' % ctrl_genes)
+        geneset = set([ctrl_genes])
+        LOG.info('Using %s as control gene' % (ctrl_genes))
+    return geneset
+
+
+def loadSgrnaReference(filename):
+    """Reference efficacies {sgrna: {'sgrna', 'X1', 'X2'}} (strings, as read) (jacks_io.py:250-254)."""
+    with io.open(filename) as f:
+        x_ref = {row['sgrna']: row for row in csv.DictReader(f, delimiter='\t')}
+    return x_ref
+
+
+def createPseudoNonessGenes(gene_index, ctrl_geneset, num_psuedo_noness_genes):
+    """Pseudo-genes: the guide count of a random gene, then that many guides, each the random guide of a random
+    control gene, with replacement (jacks_io.py:256-264).  Consumes the global ``random`` stream draw for draw
+    like the reference, so the same seed and the same iteration order of ``ctrl_geneset`` give the same sets."""
+    pseudo_gene_index = {}
+    ctrl_geneset_lst = [x for x in ctrl_geneset if x in gene_index]
+    all_geneset_lst = [x for x in gene_index]
+    for i in range(num_psuedo_noness_genes):
+        num_guides = len(gene_index[random.choice(all_geneset_lst)])
+        pseudo_gene_index['JACKS_PSEUDO_GENE_%d' % i] = [random.choice(gene_index[random.choice(ctrl_geneset_lst)])
+                                                         for j in range(num_guides)]
+    return pseudo_gene_index
+
+
+def getJacksParser():
+    """Command-line parser of run_JACKS.py: same positionals, flags, defaults and help (jacks_io.py:266-350)."""
+    ap = argparse.ArgumentParser(formatter_class=argparse.ArgumentDefaultsHelpFormatter, description="")
+    ap.add_argument("countfile", help="Countfile: assumes sgrna label is always in the first column!")
+    rg = ap.add_argument_group("Replicate file arguments")
+    rg.add_argument("replicatefile", help="A CSV or tab delimited file mapping replicates to samples")
+    rg.add_argument("--rep_hdr", type=str, default=REP_HDR_DEFAULT,
+                    help="Column header for column containing the replicate labels")
+    rg.add_argument("--sample_hdr", type=str, default=SAMPLE_HDR_DEFAULT,
+                    help="Column header for column containing the sample labels")
+    rg.add_argument("--common_ctrl_sample", type=str, default=COMMON_CTRL_SAMPLE_DEFAULT,
+                    help="Name of the sample to be used as a control for all other samples")
+    rg.add_argument("--ctrl_sample_hdr", type=str, default=None,
+                    help="Column header for column containing the sample label for the control to be used for each sample")
+    gg = ap.add_argument_group("Guidemapping file arguments")
+    gg.add_argument("guidemappingfile", help="A CSV or tab delimited file mapping guides to genes")
+    gg.add_argument("--sgrna_hdr", type=str, default=SGRNA_HDR_DEFAULT,
+                    help="Column header for the column containing the guide labels")
+    gg.add_argument("--gene_hdr", type=str, default=GENE_HDR_DEFAULT,
+                    help="Column header for the column containing the gene labels")
+    gg.add_argument("--ignore_blank_genes", action='store_true', default=False,
+                    help="Ignore guides for which the assigned gene is blank")
+    ap.add_argument("--outprefix", type=str, default="", help="Output prefix")
+    ap.add_argument("--reffile", type=str, default=None, help="Reference file containing pre-trained sgRNA efficacy scores")
+    ap.add_argument("--fdr", type=float, default=None,
+                    help="False discovery rate threshold at which to accept significant genes (if None output all in order)")
+    ap.add_argument("--fdr_thresh_type", type=str, default='REGULAR',
+                    help="Method to use to threshold significant genes (REGULAR, LOCAL_FDR)")
+    ap.add_argument("--positive", action='store_true', default=False,
+                    help="Apply positive selection (default is negative selection)")
+    ap.add_argument("--apply_w_hp", action='store_true', default=False,
+                    help="Apply hierarchical prior on gene effects (not recommended, use with caution)")
+    ap.add_argument("--norm_type", type=str, default=NORM_TYPE_DEFAULT,
+                    help="Type of normalisation to use on log count data (median, mode, ctrl_guides - if using ctrl_guides, "
+                         "must provide --ctrl_gene_file)")
+    ap.add_argument("--ctrl_genes", type=str, default=None,
+                    help="(Required if p-value output is wanted) Either, the name of a gene (as used in sgrnamappingfile) "
+                         "specifying a set of negative control guides (e.g. these could be intergenic, non-targeting etc) OR "
+                         "a text file containing a list (one per line) of genes to use as negative controls. Also used to "
+                         "infer variances in case of single replicate data.")
+    ap.add_argument("--n_pseudo", type=int, default=2000,
+                    help="Number of pseudo genes to create and infer JACKS results for by randomly sampling guides from the "
+                         "control genes (specified in --ctrl_genes)")
+    ap.add_argument("--count_prior", type=int, default=32,
+                    help="Prior count to be added to all read counts prior to log operation")
+    return ap
+
+
+def preprocess(countfile, replicatefile, guidemappingfile, rep_hdr=REP_HDR_DEFAULT, sample_hdr=SAMPLE_HDR_DEFAULT,
+               common_ctrl_sample=COMMON_CTRL_SAMPLE_DEFAULT, ctrl_sample_hdr=None, sgrna_hdr=SGRNA_HDR_DEFAULT,
+               gene_hdr=GENE_HDR_DEFAULT, ignore_blank_genes=False, outprefix=OUTPREFIX_DEFAULT, reffile=None):
+    """Read the sample, gene and (optional) reference-efficacy specifications (jacks_io.py:352-377)."""
+    LOG.info('Loading sample specification')
+    sample_spec, ctrl_spec, sample_num_reps = createSampleSpec(countfile, replicatefile, rep_hdr, sample_hdr,
+                                                               common_ctrl_sample, ctrl_sample_hdr)
+    LOG.info('Loading gene mappings')
+    gene_spec = createGeneSpec(guidemappingfile, sgrna_hdr, gene_hdr, ignore_blank_genes=ignore_blank_genes)
+    x_ref = None
+    if reffile:
+        LOG.info('Loading sgrna reference values')
+        x_ref = loadSgrnaReference(reffile)
+        LOG.info('Checking sgrna reference identifiers against gene mappings')
+        for guide in gene_spec:
+            if guide not in x_ref:
+                raise Exception('%s has no sgrna reference in %s' % (guide, reffile))
+    return sample_spec, ctrl_spec, gene_spec, x_ref
+
+
+def load_data_and_run(sample_spec, gene_spec, ctrl_spec, sgrna_reference_file, x_ref, outprefix,
+                      apply_w_hp=APPLY_W_HP_DEFAULT, norm_type=NORM_TYPE_DEFAULT, ctrl_genes=None, fdr=None,
+                      fdr_thresh_type='REGULAR', n_pseudo=0, count_prior=32, positive=False):
+    """Preprocess, infer, (optionally) build the pseudo-gene null and write every output file (jacks_io.py:379-428)."""
+    ctrl_geneset = readControlGeneset(ctrl_genes, gene_spec) if ctrl_genes is not None else set()
+    if '/' in outprefix and not os.path.exists(os.path.dirname(outprefix)):
+        os.makedirs(os.path.dirname(outprefix))
+    outfile_x = outprefix + '_grna_JACKS_results.txt'
+    outfile_lfc = outprefix + '_logfoldchange_means.txt'
+    outfile_lfc_std = outprefix + '_logfoldchange_std.txt'
+    outfile_pickle = outprefix + PICKLE_FILENAME
+
+    LOG.info('Loading data and pre-processing')
+    data, meta, sample_ids, genes, gene_index = loadDataAndPreprocess(sample_spec, gene_spec, ctrl_spec=ctrl_spec,
+                                                                      normtype=norm_type, ctrl_geneset=ctrl_geneset,
+                                                                      prior=count_prior)
+    gene_grnas = {gene: [x for x in meta[gene_index[gene], 0]] for gene in gene_index}
+    testdata, ctrldata, test_sample_idxs = collateTestControlSamples(data, sample_ids, ctrl_spec)
+    sample_ids_without_ctrl = [sample_ids[idx] for idx in test_sample_idxs]
+
+    x_reference = None
+    if sgrna_reference_file:
+        x_reference = {'X1': np.array([eval(x_ref[x]['X1']) for x in meta[:, 0]]),
+                       'X2': np.array([eval(x_ref[x]['X2']) for x in meta[:, 0]])}
+    else:
+        writeFoldChanges(outfile_lfc, testdata, ctrldata, meta, sample_ids_without_ctrl)
+        writeFoldChanges(outfile_lfc_std, testdata, ctrldata, meta, sample_ids_without_ctrl, write_std=True)
+
+    LOG.info('Running JACKS inference')
+    jacks_results = inferJACKS(gene_index, testdata, ctrldata, apply_w_hp=apply_w_hp, fixed_x=x_reference)
+
+    if n_pseudo > 0 and len(ctrl_geneset) > 0:
+        LOG.info('Running JACKS inference on %d pseudogenes' % n_pseudo)
+        pseudo_gene_index = createPseudoNonessGenes(gene_index, ctrl_geneset, n_pseudo)
+        jacks_pseudo_results = inferJACKS(pseudo_gene_index, testdata, ctrldata, apply_w_hp=apply_w_hp)
+        writeJacksWResults(outprefix + '_pseudo_noness', jacks_pseudo_results, sample_ids_without_ctrl,
+                           write_types=['', '_std'], positive=positive)
+        for gene in jacks_results:
+            jacks_pseudo_results[gene] = jacks_results[gene]
+
+    LOG.info('Writing JACKS results')
+    if len(ctrl_geneset) > 0 and n_pseudo > 0:
+        writeJacksWResults(outprefix, jacks_pseudo_results, sample_ids_without_ctrl,
+                           ctrl_geneset=set(x for x in jacks_pseudo_results if 'JACKS_PSEUDO_GENE' in x),
+                           write_types=['', '_std', '_pval'], fdr=fdr, pseudo=True, fdr_thresh_type=fdr_thresh_type,
+                           positive=positive)
+    else:
+        writeJacksWResults(outprefix, jacks_results, sample_ids_without_ctrl, ctrl_geneset=ctrl_geneset,
+                           write_types=['', '_std'], positive=positive)
+    writeJacksXResults(outfile_x, jacks_results, gene_grnas)
+    pickleJacksFullResults(outfile_pickle, jacks_results, sample_ids_without_ctrl, gene_grnas)
+
+
+def runJACKS(countfile, replicatefile, guidemappingfile, rep_hdr=REP_HDR_DEFAULT, sample_hdr=SAMPLE_HDR_DEFAULT,
+             common_ctrl_sample=COMMON_CTRL_SAMPLE_DEFAULT, ctrl_sample_hdr=None, sgrna_hdr=SGRNA_HDR_DEFAULT,
+             gene_hdr=GENE_HDR_DEFAULT, apply_w_hp=APPLY_W_HP_DEFAULT, norm_type=NORM_TYPE_DEFAULT, ignore_blank_genes=False,
+             ctrl_genes=None, fdr=None, fdr_thresh_type='REGULAR', outprefix=OUTPREFIX_DEFAULT, reffile=None, n_pseudo=0,
+             count_prior=32, positive=False):
+    """The whole pipeline from three file names (jacks_io.py:430-442)."""
+    sample_spec, ctrl_spec, gene_spec, x_ref = preprocess(countfile, replicatefile, guidemappingfile, rep_hdr, sample_hdr,
+                                                          common_ctrl_sample, ctrl_sample_hdr, sgrna_hdr, gene_hdr,
+                                                          ignore_blank_genes, outprefix, reffile)
+    load_data_and_run(sample_spec, gene_spec, ctrl_spec, reffile, x_ref, outprefix, apply_w_hp=apply_w_hp,
+                      norm_type=norm_type, ctrl_genes=ctrl_genes, fdr=fdr, fdr_thresh_type=fdr_thresh_type,
+                      n_pseudo=n_pseudo, count_prior=count_prior, positive=positive)
+
+
+def runJACKSFromArgs():
+    """Entry point of run_JACKS.py (jacks_io.py:444-453)."""
+    args = getJacksParser().parse_args()
+    runJACKS(args.countfile, args.replicatefile, args.guidemappingfile, args.rep_hdr, args.sample_hdr,
+             args.common_ctrl_sample, args.ctrl_sample_hdr, args.sgrna_hdr, args.gene_hdr, args.apply_w_hp, args.norm_type,
+             args.ignore_blank_genes, args.ctrl_genes, args.fdr, args.fdr_thresh_type, args.outprefix, args.reffile,
+             args.n_pseudo, args.count_prior, args.positive)

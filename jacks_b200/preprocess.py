@@ -1,0 +1,200 @@
+"""Drop-in for the reference module ``jacks.preprocess`` (jacks/jacks/preprocess.py).
+
+Same public names, arguments, defaults and return layout.  The numerical work -- log2(count + prior),
+per-column centring and the mean-variance error model -- runs on the GPU through the C-ABI
+(jacks_normalize_host, jacks_condense_host); the host keeps what the reference does with Python
+objects: reading the count table, filtering guides, the string sort of guide ids, the gene index.
+
+Not on the GPU (yet) and therefore raising instead of silently computing on the host:
+``normtype='mode'`` and ``calc_posterior_sd(guideset_indexs=...)`` (the control-guide subset fit that
+``inferMissingVariances`` uses for single-replicate samples when control genes are given).
+"""
+import csv
+import io
+import random
+
+import numpy as np
+
+from . import _native
+from .infer import LOG
+
+
+def _window(n, windowfracN=100.0):
+    """Half-width of the smoothing window, preprocess.py:29,35."""
+    return min(max(int(n / windowfracN), 30), 800)
+
+
+def calc_posterior_sd(data, windowfracN=100.0, do_monotonize=True, guideset_indexs=set()):
+    """Posterior standard deviation per guide from the mean-variance relationship (preprocess.py:24-58):
+    the variance of each guide is replaced by the average variance of the ~2*window guides with the
+    nearest means, made non-increasing in the mean.  data: [N, R] normalised log counts of one sample."""
+    data = np.asarray(data, dtype=np.float64)
+    N = data.shape[0]
+    if data.ndim == 1 or data.shape[1] == 1:                     # preprocess.py:32
+        return np.zeros(N) * np.nan
+    if len(guideset_indexs) not in (0, N):
+        raise NotImplementedError('calc_posterior_sd with a guide subset (guideset_indexs) is not available on the '
+                                  'GPU path yet')
+    out = _native.condense_host(_native.context(0), data, [list(range(data.shape[1]))],
+                                window=_window(N, windowfracN), monotonize=do_monotonize)
+    return np.ascontiguousarray(out[:, 0, 1])
+
+
+def condense_normalised_counts(counts, Iscreens, sample_ids):
+    """Per-sample mean and posterior sd over the replicate columns (preprocess.py:60-67) -> [N, S, 2]."""
+    return _native.condense_host(_native.context(0), counts, [list(c) for c in Iscreens])
+
+
+def compute_extras(meta, sample_ids):
+    """Sorted unique gene names and {gene: [row indexes]} in row order (preprocess.py:69-74)."""
+    genes = np.unique(sorted(meta[:, 1]))
+    gene_guides = {g: [] for g in genes}
+    for i, g in enumerate(meta[:, 1]):
+        gene_guides[g].append(i)
+    return genes, gene_guides
+
+
+def normalizeLogCounts(logcounts, normtype='median', ctrl_guide_indexes=[]):
+    """Per-column normalisation of log counts (preprocess.py:76-96).  Returns the normalised array."""
+    LOG.info('Applying %s normalisation' % normtype)
+    logcounts = np.asarray(logcounts, dtype=np.float64)
+    ctx = _native.context(0)
+    if normtype in ('median', 'zmad'):
+        return _native.normalize_host(ctx, logcounts, normtype)
+    if normtype == 'ctrl_guides':
+        if len(ctrl_guide_indexes) == 0:
+            raise Exception('No guides specified for ctrl guide normalization')
+        mask = np.zeros(logcounts.shape[0], dtype=np.uint8)
+        mask[list(ctrl_guide_indexes)] = 1
+        return _native.normalize_host(ctx, logcounts, 'ctrl_guides', row_mask=mask)
+    if normtype == 'mode':
+        raise NotImplementedError("normalisation type 'mode' is not available on the GPU path yet")
+    raise Exception('Unrecognised normalisation type %s' % normtype)
+
+
+def inferMissingVariances(data, meta, sample_ids, ctrl_spec, ctrl_geneset):
+    """Fill undefined variances of single-replicate test samples from the sample-vs-control spread of the
+    control-gene guides (preprocess.py:98-119)."""
+    for s, sample_id in enumerate(sample_ids):
+        if sum(np.isnan(data[:, s, 1]) == 0):
+            continue
+        if sample_id in ctrl_spec and ctrl_spec[sample_id] == sample_id:
+            continue                 # a control: JACKS uses the data variance for it at model time
+        if sample_id in ctrl_spec and len(ctrl_geneset) > 0:
+            nan_flags = np.isnan(data[:, s, 1])
+            guideset_indexs = [i for i, x in enumerate(meta[:, 1]) if x in ctrl_geneset]
+            ctrl_data = data[:, [sample_ids.index(ctrl_spec[sample_id])], 0]
+            concat_data = np.concatenate((ctrl_data, data[:, [s], 0]), axis=1)
+            data[nan_flags, s, 1] = 2 * calc_posterior_sd(concat_data, guideset_indexs=guideset_indexs)[nan_flags]
+        else:
+            LOG.warning('Undefined variances in sample %s, set --ctrl_genes input to JACKS to infer variances from '
+                        'control genes' % sample_id)
+    return data
+
+
+def collateTestControlSamples(data, sample_ids, ctrl_spec):
+    """Split the [N, S, 2] cube into test samples and, per test sample, its control (preprocess.py:121-126)."""
+    test_sample_idxs = [i for i, x in enumerate(sample_ids) if ctrl_spec[x] != x]
+    LOG.info('Collating %d samples' % len(test_sample_idxs))
+    testdata = data[:, test_sample_idxs, :]
+    ctrldata = data[:, [sample_ids.index(ctrl_spec[sample_ids[idx]]) for idx in test_sample_idxs], :]
+    return testdata, ctrldata, test_sample_idxs
+
+
+def _parse_cell(text):
+    """The reference eval()s every cell (preprocess.py:147); plain numbers take the fast path."""
+    try:
+        return float(int(text))
+    except ValueError:
+        try:
+            return float(text)
+        except ValueError:
+            return float(eval(text))
+
+
+def loadDataAndPreprocess(sample_spec, gene_spec, ctrl_spec={}, ctrl_geneset=set(), normtype='median', prior=32):
+    """Load counts from one or more files with the same guides in the same order and condense them
+    (preprocess.py:128-173).  sample_spec {filename: [(sample_id, colname)]}.
+    Returns data [N, S, 2], meta [N, 2] (guide, gene), sample_ids, genes, gene_guides."""
+    ctx = _native.context(0)
+    samples, sample_counts, metas = [], [], []
+    for filename in sample_spec:
+        raw, meta = [], []
+        f = io.open(filename)
+        delim = ',' if (filename.split('.')[-1] == 'csv') else '\t'
+        rdr = csv.DictReader(f, delimiter=delim)
+        sgrna_col = rdr.fieldnames[0]                 # the guide label is the first column
+        samples.extend([sample_id for sample_id, colname in sample_spec[filename]])
+        colnames = [colname for sample_id, colname in sample_spec[filename]]
+        for row in rdr:
+            guide = row[sgrna_col]
+            if guide not in gene_spec:
+                continue                              # no gene mapping: ignored
+            raw.append([_parse_cell(row[c]) for c in colnames])
+            meta.append([guide, gene_spec[guide]])
+        f.close()
+        raw = np.array(raw, dtype=np.float64).reshape(len(meta), len(colnames))
+        mask = None
+        if normtype == 'ctrl_guides':
+            idx = [i for i, m in enumerate(meta) if m[1] in ctrl_geneset]
+            if len(idx) == 0:
+                raise Exception('No guides specified for ctrl guide normalization')
+            mask = np.zeros(len(meta), dtype=np.uint8)
+            mask[idx] = 1
+        LOG.info('Applying %s normalisation' % normtype)
+        if normtype in ('median', 'zmad', 'ctrl_guides'):
+            counts = _native.normalize_host(ctx, raw, normtype, take_log=True, prior=prior, row_mask=mask)
+        elif normtype == 'mode':
+            raise NotImplementedError("normalisation type 'mode' is not available on the GPU path yet")
+        else:
+            raise Exception('Unrecognised normalisation type %s' % normtype)
+        meta = np.array(meta)
+        order = np.argsort(meta[:, 0])
+        meta, counts = meta[order, :], counts[order, :]
+        metas.append(meta)
+        sample_counts.append(counts + 0.0)
+        if len(metas) > 1 and not (metas[0] == meta).all():
+            raise Exception('Incompatible gRNAs in file %s e.g gRNA naming or order does not match other files' % filename)
+    counts = np.concatenate(sample_counts, axis=1)
+
+    sample_ids = sorted(set(samples))
+    Iscreens = [[col_idx for col_idx, x in enumerate(samples) if x == sample_id] for sample_id in sample_ids]
+    data = condense_normalised_counts(counts, Iscreens, sample_ids)
+    genes, gene_guides = compute_extras(meta, sample_ids)
+    data = inferMissingVariances(data, meta, sample_ids, ctrl_spec, ctrl_geneset)
+    return data, meta, sample_ids, genes, gene_guides
+
+
+def subsample_and_preprocess(selected_screens, sample_spec, gene_spec, ctrl_spec={}, ctrl_geneset=set(), normtype='median',
+                             norepl=True):
+    """Pick a number of replicates for each selected screen and preprocess those (preprocess.py:175-227).
+    selected_screens: [(sample_id, n_replicates or -1 for all)]; norepl: sample without replacement."""
+    found = {}
+    wanted = {sample_id: num_rep for (sample_id, num_rep) in selected_screens}
+    for filename in sample_spec:
+        for sample_id, colname in sample_spec[filename]:
+            if sample_id in wanted:
+                found.setdefault(sample_id, []).append((filename, colname))
+
+    chosen_spec, seen = {}, {}
+    for sample_id, num_rep in selected_screens:
+        if sample_id not in found:
+            raise Exception('Could not find data for selected sample %s' % sample_id)
+        if num_rep < 0:
+            picked = found[sample_id]
+        elif norepl:
+            picked = random.sample(found[sample_id], num_rep) if num_rep <= len(found[sample_id]) else found[sample_id]
+        else:
+            picked = [random.choice(found[sample_id]) for i in range(num_rep)]
+
+        ctrl_sample_id = ctrl_spec[sample_id]
+        if sample_id in seen:
+            seen[sample_id] += 1                      # the same sample again: give the extra copy its own id
+            sample_id += ('_%d' % seen[sample_id])
+            ctrl_spec[sample_id] = ctrl_sample_id
+        elif ctrl_sample_id != sample_id:
+            seen[sample_id] = 0
+        for filename, colname in picked:
+            chosen_spec.setdefault(filename, []).append((sample_id, colname))
+
+    return loadDataAndPreprocess(chosen_spec, gene_spec, ctrl_spec=ctrl_spec, ctrl_geneset=ctrl_geneset, normtype=normtype)
