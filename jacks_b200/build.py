@@ -1,4 +1,4 @@
-"""Build recipe for libjacks_b200.so (nvcc, sm_100a only) and the C oracle (gcc).
+"""Build recipe for libjacks_b200.so (nvcc, sm_100a only).
 
     python -m jacks_b200.build          # build if stale
     python -m jacks_b200.build --force
@@ -70,16 +70,5 @@ def build_library(force=False, verbose=False):
     return LIB
 
 
-def build_oracle(force=False):
-    """gcc build of the C restatement of the EM (oracle/em_oracle.c) -- test infrastructure."""
-    src = os.path.join(REPO, 'oracle', 'em_oracle.c')
-    out = os.path.join(REPO, 'oracle', 'libem_oracle.so')
-    if os.path.exists(src) and (force or _stale(out, [src])):
-        _run(['gcc', '-O2', '-fPIC', '-shared', '-fopenmp', '-ffp-contract=off', '-o', out, src, '-lm'])
-    return out
-
-
 if __name__ == '__main__':
-    force = '--force' in sys.argv
-    print(build_library(force=force, verbose='-v' in sys.argv))
-    print(build_oracle(force=force))
+    print(build_library(force='--force' in sys.argv, verbose='-v' in sys.argv))

@@ -58,15 +58,14 @@ def normalizeLogCounts(logcounts, normtype='median', ctrl_guide_indexes=[]):
     """Per-column normalisation of log counts (preprocess.py:76-96).  Returns the normalised array."""
     LOG.info('Applying %s normalisation' % normtype)
     logcounts = np.asarray(logcounts, dtype=np.float64)
-    ctx = _native.context(0)
     if normtype in ('median', 'zmad'):
-        return _native.normalize_host(ctx, logcounts, normtype)
+        return _native.normalize_host(_native.context(0), logcounts, normtype)
     if normtype == 'ctrl_guides':
         if len(ctrl_guide_indexes) == 0:
             raise Exception('No guides specified for ctrl guide normalization')
         mask = np.zeros(logcounts.shape[0], dtype=np.uint8)
         mask[list(ctrl_guide_indexes)] = 1
-        return _native.normalize_host(ctx, logcounts, 'ctrl_guides', row_mask=mask)
+        return _native.normalize_host(_native.context(0), logcounts, 'ctrl_guides', row_mask=mask)
     if normtype == 'mode':
         raise NotImplementedError("normalisation type 'mode' is not available on the GPU path yet")
     raise Exception('Unrecognised normalisation type %s' % normtype)
@@ -116,6 +115,10 @@ def loadDataAndPreprocess(sample_spec, gene_spec, ctrl_spec={}, ctrl_geneset=set
     """Load counts from one or more files with the same guides in the same order and condense them
     (preprocess.py:128-173).  sample_spec {filename: [(sample_id, colname)]}.
     Returns data [N, S, 2], meta [N, 2] (guide, gene), sample_ids, genes, gene_guides."""
+    if normtype == 'mode':
+        raise NotImplementedError("normalisation type 'mode' is not available on the GPU path yet")
+    if normtype not in ('median', 'zmad', 'ctrl_guides'):
+        raise Exception('Unrecognised normalisation type %s' % normtype)
     ctx = _native.context(0)
     samples, sample_counts, metas = [], [], []
     for filename in sample_spec:
@@ -142,12 +145,7 @@ def loadDataAndPreprocess(sample_spec, gene_spec, ctrl_spec={}, ctrl_geneset=set
             mask = np.zeros(len(meta), dtype=np.uint8)
             mask[idx] = 1
         LOG.info('Applying %s normalisation' % normtype)
-        if normtype in ('median', 'zmad', 'ctrl_guides'):
-            counts = _native.normalize_host(ctx, raw, normtype, take_log=True, prior=prior, row_mask=mask)
-        elif normtype == 'mode':
-            raise NotImplementedError("normalisation type 'mode' is not available on the GPU path yet")
-        else:
-            raise Exception('Unrecognised normalisation type %s' % normtype)
+        counts = _native.normalize_host(ctx, raw, normtype, take_log=True, prior=prior, row_mask=mask)
         meta = np.array(meta)
         order = np.argsort(meta[:, 0])
         meta, counts = meta[order, :], counts[order, :]

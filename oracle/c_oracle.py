@@ -1,7 +1,7 @@
 """ctypes wrapper of oracle/libem_oracle.so (C restatement of the EM) -- TEST INFRASTRUCTURE ONLY.
 
 Same contract as the product's batched EM (CSR gene index in, flat arrays out) so that tests can diff
-the two at full size.  Build with ``python -m jacks_b200.build`` (gcc).  Never imported by jacks_b200.
+the two at full size.  Build with ``python oracle/build_oracle.py`` (gcc).  Never imported by jacks_b200.
 """
 import ctypes as C
 import os
@@ -24,9 +24,8 @@ def _load():
     global _lib
     if _lib is None:
         if not os.path.exists(_PATH):
-            import subprocess
-            subprocess.check_call(['gcc', '-O2', '-fPIC', '-shared', '-fopenmp', '-ffp-contract=off', '-o', _PATH,
-                                   os.path.join(_HERE, 'em_oracle.c'), '-lm'])
+            from . import build_oracle
+            build_oracle.build()
         _lib = C.CDLL(_PATH)
         vp = C.c_void_p
         _lib.oracle_em_batched.argtypes = [vp, vp, C.c_int64, C.c_int32, C.c_int32, C.c_int32, vp, vp, C.c_int64, vp, vp,

@@ -7,7 +7,7 @@
  * results agree with numpy to rounding (~1e-15 relative), not bit for bit; the numpy restatement
  * oracle/jacks_oracle.py is the bit-exact one and tests/test_oracle_golden.py pins this file to it
  * and to the reference's golden outputs.  Used only by tests/, smoke() and bench.py's CPU baseline
- * (full-size checks where the numpy oracle would take minutes).  Built by jacks_b200/build.py:
+ * (full-size checks where the numpy oracle would take minutes).  Built by oracle/build_oracle.py:
  *     gcc -O2 -fPIC -shared -fopenmp -ffp-contract=off -o oracle/libem_oracle.so oracle/em_oracle.c -lm
  */
 #include <math.h>
