@@ -83,6 +83,49 @@ __global__ void latency_kernel(double* out, long long* cyc, double a, double b) 
 }
 }  // namespace
 
+// throughput of DFMA with three DISTINCT register-pair operands per instruction (register-file bandwidth)
+__global__ void __launch_bounds__(256) dfma_3op_kernel(double* out, int iters, const double* in) {
+    double acc[8], b[8], c[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { acc[i] = in[threadIdx.x + i]; b[i] = in[threadIdx.x + 8 + i]; c[i] = in[threadIdx.x + 16 + i]; }
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[i] = fma(acc[i], b[i], c[i]);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) b[i] = fma(b[i], c[i], acc[i]);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) c[i] = fma(c[i], acc[i], b[i]);
+    }
+    double s = 0.0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s += acc[i] + b[i] + c[i];
+    if (s == 123.456) out[0] = s;
+}
+
+extern "C" __attribute__((visibility("default"))) int jacks_debug_3op_probe(JacksCtx* ctx, double* flops_out) {
+    using namespace jacks;
+    cudaSetDevice(ctx->device);
+    int rc = ctx->tmp.reserve(8192);
+    if (rc != JACKS_OK) return rc;
+    cudaMemsetAsync(ctx->tmp.p, 0, 8192, ctx->stream);
+    const int iters = 4096, threads = 256, ctas = ctx->n_sm * 8;
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    double best = 1e30;
+    for (int rep = 0; rep < 4; ++rep) {
+        cudaEventRecord(e0, ctx->stream);
+        dfma_3op_kernel<<<ctas, threads, 0, ctx->stream>>>((double*)ctx->tmp.p, iters, (const double*)ctx->tmp.p);
+        cudaEventRecord(e1, ctx->stream);
+        cudaEventSynchronize(e1);
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, e0, e1);
+        if (rep > 0 && ms * 1e-3 < best) best = ms * 1e-3;
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    *flops_out = 2.0 * 24.0 * (double)iters * (double)threads * (double)ctas / best;
+    return JACKS_OK;
+}
+
 extern "C" __attribute__((visibility("default"))) int jacks_debug_latency_probe(JacksCtx* ctx, double* dfma_cycles,
                                                                                double* rcp_cycles, double* dfma4_cycles) {
     using namespace jacks;

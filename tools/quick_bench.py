@@ -18,7 +18,8 @@ def main():
     dev = torch.device('cuda:0')
     ctx = _native.context(0)
     print('fp64 peak TFLOP/s', ctx.fp64_peak_flops() / 1e12, flush=True)
-    gi, test, ctrl, ctrl_genes = synth.make_condensed_screen(n_genes=n_genes)
+    n_lines = int(os.environ.get('QB_LINES', 400))
+    gi, test, ctrl, ctrl_genes = synth.make_condensed_screen(n_genes=n_genes, n_lines=n_lines)
     names, offs, rows = _native.as_csr(gi)
     ctrl_ids = [names.index(g) for g in ctrl_genes]
     poffs, prows = synth.make_pseudo_index_csr(offs, ctrl_ids, n_pseudo)
