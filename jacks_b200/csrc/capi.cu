@@ -67,7 +67,7 @@ struct JacksEmPlan {
     JacksCtx* ctx;
     int64_t n_genes, n_rows, total_guides;
     int L;
-    DevBuf d_offsets, d_rows, d_ids, d_slot_off, d_slot_rows, d_deferred, d_counters, d_scratch;
+    DevBuf d_offsets, d_rows, d_ids, d_slot_off, d_slot_rows, d_deferred, d_counters, d_scratch, d_tpd;
     std::vector<EmBucket> fast;
     EmBucket generic;          // n == 0 if empty
     int generic_maxG;
@@ -240,6 +240,8 @@ int jacks_em_plan_create(JacksCtx* ctx, const int64_t* gene_offsets, const int32
     up(p->d_slot_rows, slot_rows.data(), slot_rows.size() * sizeof(int));
     if (rc == JACKS_OK) rc = p->d_deferred.reserve((size_t)std::max<int64_t>(n_genes, 1) * sizeof(int));
     if (rc == JACKS_OK) rc = p->d_counters.reserve(64 * sizeof(int));
+    if (rc == JACKS_OK && p->fast_maxG > 0)
+        rc = p->d_tpd.reserve((size_t)ctx->n_sm * kMaxFastCtasPerSm * p->fast_maxG * n_lines * sizeof(double));
     // generic kernel configurations (and global scratch if a gene's working set exceeds shared memory)
     memset(&p->cfg_generic, 0, sizeof p->cfg_generic);
     memset(&p->cfg_deferred, 0, sizeof p->cfg_deferred);
@@ -268,7 +270,7 @@ void jacks_em_plan_destroy(JacksEmPlan* p) {
     if (!p) return;
     cudaSetDevice(p->ctx->device);
     p->d_offsets.release(); p->d_rows.release(); p->d_ids.release(); p->d_slot_off.release();
-    p->d_slot_rows.release(); p->d_deferred.release();
+    p->d_slot_rows.release(); p->d_deferred.release(); p->d_tpd.release();
     p->d_counters.release(); p->d_scratch.release();
     delete p;
 }
@@ -302,6 +304,7 @@ int jacks_em_run_device(JacksCtx* ctx, const JacksEmPlan* plan, const JacksEmPar
     a.mu0_x = params->mu0_x; a.var0_x = params->var0_x; a.mu0_w = params->mu0_w; a.var0_w = params->var0_w;
     a.tps = params->tau_prior_strength;
     a.scratch = (double*)plan->d_scratch.p;
+    a.tpd_scratch = (double*)plan->d_tpd.p;
 
     int slot = 1;
     for (const EmBucket& b : plan->fast) {

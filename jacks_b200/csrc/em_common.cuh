@@ -37,6 +37,8 @@ struct EmLaunch {
     // hyper-parameters (infer.py:55 defaults)
     int n_iter; int apply_w_hp;
     double tol, mu0_x, var0_x, mu0_w, var0_w, tps;
+    // fast kernels: per-CTA slab [G][L] for tau_pr_den (global memory, stays L2 resident)
+    double* tpd_scratch;
     // generic kernel only: global scratch when a gene's working set exceeds shared memory
     double* scratch; long long scratch_stride;   // doubles per warp
 };
@@ -51,6 +53,8 @@ bool em_fast_available(int G, int W);
 size_t em_fast_smem_bytes(int G, int W, int L);
 // Largest dynamic shared memory a CTA may request on sm_100a (227 KB minus the static words we use).
 constexpr size_t kMaxDynSmem = 227 * 1024 - 64;
+// Upper bound on resident fast-kernel CTAs per SM the plan provisions tau_pr_den slabs for.
+constexpr int kMaxFastCtasPerSm = 12;
 
 // Generic path: any G and L, NaN-safe, one warp per gene, working set in shared memory when it
 // fits and in `scratch` (EmLaunch::scratch, one slab per warp of the grid) otherwise.

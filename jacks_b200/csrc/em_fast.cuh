@@ -136,25 +136,24 @@ __device__ __forceinline__ void team_allsum(double (&v)[NV], double* scr, double
 // lanes still execute the arithmetic on whatever the shared-memory words past the line hold (the
 // allocation carries one step of slack, see em_fast_smem_doubles), but neither store nor
 // accumulate it: the stores and the three accumulating FMAs of that line are predicated.
-template <int G, int U, bool UNIT_C, bool MASKED>
-__device__ __forceinline__ void em_sweep(const double* __restrict__ ys, const double* __restrict__ tpds,
-                                         double* __restrict__ taus, double* __restrict__ w1s,
+template <int G, int U, int UP, bool UNIT_C, bool MASKED>
+__device__ __forceinline__ void em_sweep(const double* __restrict__ ys, const double (&pd)[UP][G],
+                                         double* __restrict__ taus, double* __restrict__ w1p,
                                          double* __restrict__ w2g, const int L, const int l, const int step,
                                          const double (&x1r)[G], const double (&x2r)[G], const double ivw,
                                          const double mw, const double c_tau, double (&a1)[G], double (&a2)[G],
                                          double (&ab)[G], const bool valid) {
-    double yv[U][G], tv[U][G], pd[U][G];
+    double yv[U][G], tv[U][G];
 #pragma unroll
-    for (int u = 0; u < U; ++u)
+    for (int u = 0; u < U; ++u) {
+        // the masked line of a lane that has run out of lines reads line 0 instead (any valid word)
+        const int lu = (MASKED && u == U - 1 && !valid) ? 0 : l + u * step;
 #pragma unroll
         for (int g = 0; g < G; ++g) {
-            yv[u][g] = ys[g * L + l + u * step];
-            tv[u][g] = taus[g * L + l + u * step];
+            yv[u][g] = ys[g * L + lu];
+            tv[u][g] = taus[g * L + lu];
         }
-#pragma unroll
-    for (int u = 0; u < U; ++u)
-#pragma unroll
-        for (int g = 0; g < G; ++g) pd[u][g] = tpds[g * L + l + u * step];
+    }
     // W step, infer.py:112-116 (old tau, new x): den = 1/var0_w + sum_g x2*tau, num = mu0_w/var0_w + sum_g x1*y*tau
     double yt[U][G];
 #pragma unroll
@@ -243,8 +242,8 @@ __device__ __forceinline__ void em_sweep(const double* __restrict__ ys, const do
 #pragma unroll
     for (int u = 0; u < U; ++u)
         if (!MASKED || u < U - 1 || valid) {
-            w1s[l + u * step] = w1[u];
-            if (w2g) w2g[l + u * step] = w2[u];      // E[w^2] is write-only state: straight to the output row
+            w1p[l + u * step] = w1[u];                // E[w], E[w^2]: write-only state within a pass, kept in the
+            if (w2g) w2g[l + u * step] = w2[u];      // gene's output rows (L2 resident), not in shared memory
         }
 }
 
@@ -259,7 +258,7 @@ template <int G> struct EmSums { double a1[G], a2[G], ab; };
 // U at a time while more than U remain, then one final MASKED step of 1..U lines whose last line
 // is live only in the lanes with l < L.
 template <int G, int STEP, bool UNIT_C>
-__device__ __noinline__ EmSums<G> em_sweep_all(const double* ys, const double* tpds, double* taus, double* w1s,
+__device__ __noinline__ EmSums<G> em_sweep_all(const double* ys, const double* tpdg, double* taus, double* w1p,
                                                double* w2g, const int L, const int l0, const int n_warp,
                                                const EmX<G> x, const double ivw, const double mw,
                                                const double c_tau) {
@@ -269,13 +268,30 @@ __device__ __noinline__ EmSums<G> em_sweep_all(const double* ys, const double* t
     constexpr int U = (G >= 7) ? 2 : 4;       // lines per step: U*G >= 8 independent elements
     int l = l0;
     int n = n_warp;
-    for (; n > U; n -= U, l += U * STEP)
-        em_sweep<G, U, UNIT_C, false>(ys, tpds, taus, w1s, w2g, L, l, STEP, x.x1, x.x2, ivw, mw, c_tau, a1, a2, ab, true);
+    // tau_pr_den lives in an L2-resident global slab (it is read once per pass and never written after
+    // staging, so it does not have to occupy shared memory): software-pipelined one step ahead.
+    double pdn[U][G];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+        const int lu = (l + u * STEP < L) ? l + u * STEP : 0;
+#pragma unroll
+        for (int g = 0; g < G; ++g) pdn[u][g] = __ldg(tpdg + g * L + lu);
+    }
+    for (; n > U; n -= U, l += U * STEP) {
+        double pdc[U][G];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int lu = (l + (U + u) * STEP < L) ? l + (U + u) * STEP : 0;
+#pragma unroll
+            for (int g = 0; g < G; ++g) { pdc[u][g] = pdn[u][g]; pdn[u][g] = __ldg(tpdg + g * L + lu); }
+        }
+        em_sweep<G, U, U, UNIT_C, false>(ys, pdc, taus, w1p, w2g, L, l, STEP, x.x1, x.x2, ivw, mw, c_tau, a1, a2, ab, true);
+    }
     const bool valid = (l + (n - 1) * STEP) < L;
-    if (n == 1) em_sweep<G, 1, UNIT_C, true>(ys, tpds, taus, w1s, w2g, L, l, STEP, x.x1, x.x2, ivw, mw, c_tau, a1, a2, ab, valid);
-    else if (n == 2) em_sweep<G, 2, UNIT_C, true>(ys, tpds, taus, w1s, w2g, L, l, STEP, x.x1, x.x2, ivw, mw, c_tau, a1, a2, ab, valid);
-    else if (U == 4 && n == 3) em_sweep<G, (U == 4 ? 3 : 1), UNIT_C, true>(ys, tpds, taus, w1s, w2g, L, l, STEP, x.x1, x.x2, ivw, mw, c_tau, a1, a2, ab, valid);
-    else if (U == 4 && n == 4) em_sweep<G, (U == 4 ? 4 : 1), UNIT_C, true>(ys, tpds, taus, w1s, w2g, L, l, STEP, x.x1, x.x2, ivw, mw, c_tau, a1, a2, ab, valid);
+    if (n == 1) em_sweep<G, 1, U, UNIT_C, true>(ys, pdn, taus, w1p, w2g, L, l, STEP, x.x1, x.x2, ivw, mw, c_tau, a1, a2, ab, valid);
+    else if (n == 2) em_sweep<G, 2, U, UNIT_C, true>(ys, pdn, taus, w1p, w2g, L, l, STEP, x.x1, x.x2, ivw, mw, c_tau, a1, a2, ab, valid);
+    else if (U == 4 && n == 3) em_sweep<G, (U == 4 ? 3 : 1), U, UNIT_C, true>(ys, pdn, taus, w1p, w2g, L, l, STEP, x.x1, x.x2, ivw, mw, c_tau, a1, a2, ab, valid);
+    else if (U == 4 && n == 4) em_sweep<G, (U == 4 ? 4 : 1), U, UNIT_C, true>(ys, pdn, taus, w1p, w2g, L, l, STEP, x.x1, x.x2, ivw, mw, c_tau, a1, a2, ab, valid);
     EmSums<G> r;
     r.ab = ab[0];
 #pragma unroll
@@ -285,40 +301,65 @@ __device__ __noinline__ EmSums<G> em_sweep_all(const double* ys, const double* t
     return r;
 }
 
-// Stage one guide row: y = test - ctrl and tau_pr_den (infer.py:58-70) for the lane's lines.
-// Not inlined (one copy serves the G rows; it runs once per gene).  Returns true if a staged value
-// is not finite.
-template <int STEP>
-__device__ __noinline__ bool em_stage_row(const double2* __restrict__ tr, const double2* __restrict__ cr,
-                                          double* __restrict__ ys_g, double* __restrict__ tpds_g, const int L,
-                                          const int l0, const int ctrl_lines, const int rowmean_fill,
-                                          const double fill, const double tps) {
+// Stage a gene: y = test - ctrl (shared) and tau_pr_den (global slab) for the lane's lines, infer.py:58-70.
+// All G rows of a line batch are loaded before any is consumed (G*4 independent 16-byte loads in flight per
+// lane): staging is pure memory latency for a team that has only its own warps to hide it behind.
+// Not inlined (runs once per gene).  Returns true if a staged value is not finite.
+template <int G, int STEP>
+__device__ __noinline__ bool em_stage_gene(const double2* __restrict__ test, const double2* __restrict__ ctrl,
+                                           const int* rows, double* __restrict__ ys, double* __restrict__ tpdg,
+                                           const int L, const int l0, const int ctrl_lines, const int rowmean_fill,
+                                           const double* fill, const double tps) {
     bool bad = false;
-    double2 c0 = make_double2(0.0, 0.0);
-    if (ctrl_lines == 1) c0 = cr[0];
-#pragma unroll 4
-    for (int l = l0; l < L; l += STEP) {
-        const double2 t = tr[l];
-        const double2 c = (ctrl_lines == 1) ? c0 : cr[l];
-        const double te = (t.y != t.y) ? 2.0 : t.y;                     // infer.py:58
-        double ce = c.y;
-        if (ce != ce) ce = (ctrl_lines == 1 && rowmean_fill) ? fill : te;   // :63 / :68
-        const double yv = t.x - c.x;
-        const double pd = tps * (te * te + ce * ce + 1e-2);
-        bad |= !(fabs(yv) <= 1.79769313486231570e308) || !(pd <= 1.79769313486231570e308);
-        ys_g[l] = yv;
-        tpds_g[l] = pd;
+    const double2* tr[G];
+    const double2* cr[G];
+    double2 c0[G];
+#pragma unroll
+    for (int g = 0; g < G; ++g) {
+        tr[g] = test + (long long)rows[g] * L;
+        cr[g] = ctrl + (long long)rows[g] * ctrl_lines;
+        c0[g] = make_double2(0.0, 0.0);
+    }
+    if (ctrl_lines == 1) {
+#pragma unroll
+        for (int g = 0; g < G; ++g) c0[g] = cr[g][0];
+    }
+    constexpr int B = 2;                      // lines per batch
+    for (int l = l0; l < L; l += B * STEP) {
+        double2 t[B][G], c[B][G];
+#pragma unroll
+        for (int b = 0; b < B; ++b) {
+            const int lb = (l + b * STEP < L) ? l + b * STEP : l;
+#pragma unroll
+            for (int g = 0; g < G; ++g) {
+                t[b][g] = tr[g][lb];
+                c[b][g] = (ctrl_lines == 1) ? c0[g] : cr[g][lb];
+            }
+        }
+#pragma unroll
+        for (int b = 0; b < B; ++b) {
+            if (l + b * STEP < L) {
+#pragma unroll
+                for (int g = 0; g < G; ++g) {
+                    const double te = (t[b][g].y != t[b][g].y) ? 2.0 : t[b][g].y;               // infer.py:58
+                    double ce = c[b][g].y;
+                    if (ce != ce) ce = (ctrl_lines == 1 && rowmean_fill) ? fill[g] : te;         // :63 / :68
+                    const double yv = t[b][g].x - c[b][g].x;
+                    const double pd = tps * (te * te + ce * ce + 1e-2);
+                    bad |= !(fabs(yv) <= 1.79769313486231570e308) || !(pd <= 1.79769313486231570e308);
+                    ys[g * L + l + b * STEP] = yv;
+                    tpdg[g * L + l + b * STEP] = pd;
+                }
+            }
+        }
     }
     return bad;
 }
 
-// Shared-memory doubles of one team: y, tau_pr_den, tau [G][L]; w1, w2 [L]; reduction buffer.
-// One step of slack (32*W doubles) follows w2 so that the masked last line of a sweep may READ past
-// L without leaving the allocation (it never writes there).
+// Shared memory of one team: y and tau [G][L], the reduction tiles and totals.  tau_pr_den, E[w] and E[w^2]
+// live in global memory (L2): 27.5 KB per gene at G = 4, L = 400 -> 8 genes (two warps per scheduler) per SM.
 __host__ __device__ constexpr long long em_fast_smem_doubles(int G, int W, int L) {
-    return (3LL * G + 1) * L + 32LL * W        /* y, tau_pr_den, tau, w1 + read slack */
-           + (long long)W * (2 * G + 1) * 33   /* reduction tiles */
-           + 2LL * W * (2 * G + 1);            /* reduction totals, double buffered */
+    return 2LL * G * L + (long long)W * (2 * G + 1) * 33 + 2LL * W * (2 * G + 1);
 }
 
 // L2 prefetch of one guide row pair (test + control) of the gene a team will run next.
@@ -340,11 +381,10 @@ __global__ void __launch_bounds__(W * 32) em_fast_kernel(const EmLaunch a) {
     extern __shared__ double smem[];
     const int L = a.L;
     double* ys = smem;                       // [G][L]
-    double* tpds = ys + (size_t)G * L;       // [G][L]
-    double* taus = tpds + (size_t)G * L;     // [G][L]
-    double* w1s = taus + (size_t)G * L;      // [L]
-    double* scr = w1s + L + 32 * W + (threadIdx.x >> 5) * (NV * 33);   // this warp's reduction tile, after the read slack
-    double* red = w1s + L + 32 * W + W * (NV * 33);                    // [2][W][NV] totals
+    double* taus = ys + (size_t)G * L;       // [G][L]
+    double* scr = taus + (size_t)G * L + (threadIdx.x >> 5) * (NV * 33);   // this warp's reduction tile
+    double* red = taus + (size_t)G * L + W * (NV * 33);                    // [2][W][NV] totals
+    double* tpdg = a.tpd_scratch + (size_t)blockIdx.x * G * L;             // this team's tau_pr_den slab [G][L] (global, L2)
     __shared__ int s_slot[2];
 
     const int lane = threadIdx.x & 31;
@@ -391,20 +431,18 @@ __global__ void __launch_bounds__(W * 32) em_fast_kernel(const EmLaunch a) {
         const int n_warp = (L - wv * 32 + STEP - 1) / STEP;     // lines of this warp's fullest lane (lane 0)
 
         // ---- stage y and tau_pr_den (infer.py:58-70) ---------------------------------------
-        bool bad = false;
-        double x1r[G], x2r[G];
+        double x1r[G], x2r[G], fill[G];
 #pragma unroll
         for (int g = 0; g < G; ++g) {
             const int row = rows[g];
-            const double2* tr = a.test + (long long)row * L;
-            const double2* cr = a.ctrl + (long long)row * a.ctrl_lines;
             if (fixed) { x1r[g] = a.fixed_x1[row]; x2r[g] = a.fixed_x2[row]; }
             else { x1r[g] = a.mu0_x; x2r[g] = a.mu0_x * a.mu0_x; }
-            double fill = 0.0;
+            fill[g] = 0.0;
             if (a.ctrl_lines == 1 && a.ctrl_rowmean_fill) {
-                const double cs = cr[0].y;
+                const double cs = a.ctrl[(long long)row].y;
                 if (cs != cs) {
                     // 1-D control with an undefined sd: row mean of the (NaN -> 2.0) test sds, infer.py:63
+                    const double2* tr = a.test + (long long)row * L;
                     double one[1] = {0.0};
 #pragma unroll 1
                     for (int l = l0; l < L; l += STEP) {
@@ -412,11 +450,11 @@ __global__ void __launch_bounds__(W * 32) em_fast_kernel(const EmLaunch a) {
                         one[0] += (e != e) ? 2.0 : e;
                     }
                     team_allsum<1, NV, W>(one, scr, red, parity, warp, lane);
-                    fill = one[0] / (double)L;
+                    fill[g] = one[0] / (double)L;
                 }
             }
-            bad |= em_stage_row<STEP>(tr, cr, ys + g * L, tpds + g * L, L, l0, a.ctrl_lines, a.ctrl_rowmean_fill, fill, tps);
         }
+        const bool bad = em_stage_gene<G, STEP>(a.test, a.ctrl, rows, ys, tpdg, L, l0, a.ctrl_lines, a.ctrl_rowmean_fill, fill, tps);
         const int any_bad = (W == 1) ? __any_sync(JACKS_FULL_MASK, bad) : __syncthreads_or(bad);
         // the look-ahead atomic has landed by now: share it and start loading the next gene's index
         int nslot;
@@ -444,10 +482,11 @@ __global__ void __launch_bounds__(W * 32) em_fast_kernel(const EmLaunch a) {
                 a.deferred_ids[p] = gid;
             }
         } else {
-            // every lane reads back only the shared-memory words it wrote itself: no barrier needed
+            // every lane reads back only the words (shared and global) it wrote itself: no barrier needed
 
             // ---- initial w, tau, bound and the first X-step sums (infer.py:81-86) --------------
             double* const w2g = a.w2 ? a.w2 + (long long)gid * L : nullptr;
+            double* const w1g = a.w1 + (long long)gid * L;
             double acc[NV];
 #pragma unroll
             for (int i = 0; i < NV; ++i) acc[i] = 0.0;
@@ -460,14 +499,14 @@ __global__ void __launch_bounds__(W * 32) em_fast_kernel(const EmLaunch a) {
                 const double w2 = w1 * w1;
 #pragma unroll
                 for (int g = 0; g < G; ++g) {
-                    const double t = tps * fast_rcp(tpds[g * L + l]);
+                    const double t = tps * fast_rcp(tpdg[g * L + l]);
                     taus[g * L + l] = t;
                     const double xw = x1r[g] * w1;
                     acc[2 * G] += t * (yv[g] * yv[g] + x2r[g] * w2 - 2.0 * xw * yv[g]);
                     acc[g] += yv[g] * t * w1;
                     acc[G + g] += t * w2;
                 }
-                w1s[l] = w1;
+                w1g[l] = w1;
                 if (w2g) w2g[l] = w2;
             }
             team_allsum<NV, NV, W>(acc, scr, red, parity, warp, lane);
@@ -510,11 +549,11 @@ __global__ void __launch_bounds__(W * 32) em_fast_kernel(const EmLaunch a) {
                 if (a.apply_w_hp && L > 1) {
                     // hierarchical prior from the current w1, infer.py:92 (population variance)
                     double m[1] = {0.0};
-                    for (int l = l0; l < L; l += STEP) m[0] += w1s[l];
+                    for (int l = l0; l < L; l += STEP) m[0] += w1g[l];
                     team_allsum<1, NV, W>(m, scr, red, parity, warp, lane);
                     const double mean = m[0] / (double)L;
                     double v[1] = {0.0};
-                    for (int l = l0; l < L; l += STEP) { const double d = w1s[l] - mean; v[0] += d * d; }
+                    for (int l = l0; l < L; l += STEP) { const double d = w1g[l] - mean; v[0] += d * d; }
                     team_allsum<1, NV, W>(v, scr, red, parity, warp, lane);
                     mu0_w = mean;
                     var0_w = (v[0] / (double)L) * 3 + 1e-4;
@@ -525,7 +564,7 @@ __global__ void __launch_bounds__(W * 32) em_fast_kernel(const EmLaunch a) {
                     EmX<G> xv;
 #pragma unroll
                     for (int g = 0; g < G; ++g) { xv.x1[g] = x1r[g]; xv.x2[g] = x2r[g]; }
-                    const EmSums<G> r = em_sweep_all<G, STEP, UNIT_C>(ys, tpds, taus, w1s, w2g, L, l0, n_warp, xv, ivw, mw, c_tau);
+                    const EmSums<G> r = em_sweep_all<G, STEP, UNIT_C>(ys, tpdg, taus, w1g, w2g, L, l0, n_warp, xv, ivw, mw, c_tau);
 #pragma unroll
                     for (int g = 0; g < G; ++g) { acc[g] = r.a1[g]; acc[G + g] = r.a2[g]; }
                     acc[2 * G] = r.ab;
@@ -538,7 +577,6 @@ __global__ void __launch_bounds__(W * 32) em_fast_kernel(const EmLaunch a) {
 
             // ---- write results ------------------------------------------------------------------
             for (int l = l0; l < L; l += STEP) {
-                a.w1[(long long)gid * L + l] = w1s[l];
                 if (a.tau) {
 #pragma unroll
                     for (int g = 0; g < G; ++g) a.tau[(off + g) * L + l] = taus[g * L + l];

@@ -21,6 +21,7 @@ cudaError_t launch_inst(const EmLaunch& a, int n_sm, int grid_limit, cudaStream_
     e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k, W * 32, smem);
     if (e != cudaSuccess) return e;
     if (occ < 1) return cudaErrorLaunchOutOfResources;
+    if (occ > kMaxFastCtasPerSm) occ = kMaxFastCtasPerSm;     // tau_pr_den slabs are provisioned for this many
     long long grid = (long long)occ * n_sm;
     if (grid > a.n_work) grid = a.n_work;
     if (grid_limit > 0 && grid > grid_limit) grid = grid_limit;

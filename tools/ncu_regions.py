@@ -25,7 +25,7 @@ def main(path, min_share=0.01):
     # loop boundaries
     cuts = set()
     for i, (a, src, s, n, r) in enumerate(data):
-        m = re.search(r'BRA\s+(?:U?P\d+,\s*)?0x([0-9a-f]+)', src)
+        m = re.search(r'BRA(?:\.\w+)*\s+(?:!?U?P\d+,\s*)?0x([0-9a-f]+)', src)
         if m:
             tgt = int(m.group(1), 16)
             if tgt >= base:
