@@ -324,11 +324,15 @@ def main():
     d2h = sum(v.array.nbytes for v in out_r.values()) + (0 if out_p is None else sum(v.array.nbytes for v in out_p.values()))
 
     def e2e_step():
-        _native.em_batched_host(ctx, r_offs, r_rows, pin_test.array, pin_ctrl.array, params=params,
-                                want=tuple(out_r), out={k: v.array for k, v in out_r.items()}, keep_resident=True)
+        # real genes, then the pseudo-genes on the resident cubes; both calls only enqueue (JACKS_ASYNC), so the
+        # pseudo-gene kernels and downloads overlap the tail of the real-gene transfers; one synchronise per step
+        keep = [_native.em_batched_host(ctx, r_offs, r_rows, pin_test.array, pin_ctrl.array, params=params, want=tuple(out_r),
+                                        out={k: v.array for k, v in out_r.items()}, keep_resident=True, sync=False)]
         if out_p is not None:
-            _native.em_batched_host(ctx, p_offs, p_rows, None, None, params=params, n_rows=N, n_lines=L, ctrl_lines=L,
-                                    want=('w1', 'w2'), out={k: v.array for k, v in out_p.items()})
+            keep.append(_native.em_batched_host(ctx, p_offs, p_rows, None, None, params=params, n_rows=N, n_lines=L,
+                                                ctrl_lines=L, want=('w1', 'w2'), out={k: v.array for k, v in out_p.items()},
+                                                sync=False))
+        ctx.synchronize()
 
     e2e_steps = max(2, min(args.steps, 5))
     e2e_step()

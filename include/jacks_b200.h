@@ -81,6 +81,10 @@ JACKS_API void jacks_ctx_destroy(JacksCtx* ctx);
 /* Kernel launches enqueued through this context since creation (bench.py's gpu_launches). */
 JACKS_API int64_t jacks_ctx_launch_count(const JacksCtx* ctx);
 
+/* Wait for every asynchronous host call issued on this context (JACKS_ASYNC) and release their plans.
+ * Returns the first error of the pipeline, if any. */
+JACKS_API int jacks_ctx_synchronize(JacksCtx* ctx);
+
 JACKS_API void jacks_em_default_params(JacksEmParams* p);
 
 /* Pinned host memory for callers that want direct DMA on the host entry points. */
@@ -148,13 +152,18 @@ typedef struct JacksEmHostIO {
 
 /*
  * inferJACKS in one call on host buffers (infer.py:18-30): uploads the data cubes, runs the EM for
- * every gene of the CSR index, downloads the requested outputs.  If `keep_resident` is non-zero the
- * uploaded cubes stay on the device inside ctx and a following call with test == NULL reuses them
- * (the pseudo-gene pass of jacks_io.py:416 reads the same cubes through another index).
+ * every gene of the CSR index, downloads the requested outputs.  Gene ranges are pipelined over three
+ * streams (upload / kernels / download), so with pinned buffers the call costs about max(upload, download).
+ * `flags`: JACKS_KEEP_RESIDENT -- the uploaded cubes stay on the device inside ctx and a following call with
+ *          test == NULL reuses them (the pseudo-gene pass of jacks_io.py:416 reads the same cubes through another
+ *          index); JACKS_ASYNC -- return as soon as the work is enqueued; outputs are complete, and the host
+ *          buffers may be reused, after jacks_ctx_synchronize().  A following call on the same context queues
+ *          behind it, so the real-gene and pseudo-gene passes of one screen overlap their transfers.
  */
+enum { JACKS_KEEP_RESIDENT = 1, JACKS_ASYNC = 2 };
 JACKS_API int jacks_em_batched_host(JacksCtx* ctx, const JacksEmParams* params,
                           const int64_t* gene_offsets, const int32_t* guide_rows, int64_t n_genes,
-                          const JacksEmHostIO* io, int32_t keep_resident);
+                          const JacksEmHostIO* io, int32_t flags);
 
 /*
  * KDE p-values of gene effects against the pseudo-gene null (computeW1PvalsAndFDRs with pseudo=True,

@@ -70,6 +70,7 @@ def lib():
         L.jacks_ctx_destroy.restype = None
         L.jacks_ctx_launch_count.argtypes = [vp]
         L.jacks_ctx_launch_count.restype = i64
+        L.jacks_ctx_synchronize.argtypes = [vp]
         L.jacks_em_default_params.argtypes = [C.POINTER(EmParams)]
         L.jacks_em_default_params.restype = None
         L.jacks_host_alloc.argtypes = [C.POINTER(vp), C.c_uint64]
@@ -161,6 +162,10 @@ class Context(object):
     def launch_count(self):
         return int(lib().jacks_ctx_launch_count(self.h))
 
+    def synchronize(self):
+        """Wait for asynchronous host calls (em_batched_host(..., sync=False)) on this context."""
+        check(lib().jacks_ctx_synchronize(self.h))
+
     def fp64_peak_flops(self):
         f, s = C.c_double(), C.c_double()
         check(lib().jacks_fp64_peak_flops(self.h, C.byref(f), C.byref(s)))
@@ -227,7 +232,7 @@ class EmPlan(object):
 
 def em_batched_host(ctx, offsets, rows, test, ctrl, params=None, fixed_x1=None, fixed_x2=None,
                     want=('x1', 'x2', 'w1', 'w2', 'y', 'tau', 'n_iters', 'bound'), ctrl_rowmean_fill=False,
-                    keep_resident=False, n_rows=None, n_lines=None, ctrl_lines=None, out=None):
+                    keep_resident=False, n_rows=None, n_lines=None, ctrl_lines=None, out=None, sync=True):
     """jacks_em_batched_host on numpy arrays.  test [N,L,2], ctrl [N,L,2] or [N,1,2] float64 C-contiguous
     (or test=None to reuse the cubes a previous keep_resident call left on the device, with
     n_rows/n_lines/ctrl_lines given).  Returns a dict of the requested outputs."""
@@ -267,8 +272,11 @@ def em_batched_host(ctx, offsets, rows, test, ctrl, params=None, fixed_x1=None, 
         io.fixed_x1, io.fixed_x2 = _ptr(fixed_x1), _ptr(fixed_x2)
     for k in res:
         setattr(io, k, _ptr(res[k]))
-    check(lib().jacks_em_batched_host(ctx.h, C.byref(params), _ptr(offsets), _ptr(rows), n_genes, C.byref(io),
-                                      int(bool(keep_resident))))
+    flags = (1 if keep_resident else 0) | (0 if sync else 2)
+    check(lib().jacks_em_batched_host(ctx.h, C.byref(params), _ptr(offsets), _ptr(rows), n_genes, C.byref(io), flags))
+    if not sync:
+        # the C side reads these host arrays until ctx.synchronize(): keep them alive with the result
+        res['_keepalive'] = (offsets, rows, test, ctrl, fixed_x1, fixed_x2, params)
     return res
 
 

@@ -67,8 +67,9 @@ struct JacksEmPlan {
     JacksCtx* ctx;
     int64_t n_genes, n_rows, total_guides;
     int L;
-    DevBuf d_offsets, d_rows, d_ids, d_slot_off, d_slot_rows, d_deferred, d_counters, d_scratch, d_tpd;
+    PlanBufs* b;               // device buffers (from the context's pool)
     std::vector<EmBucket> fast;
+    std::vector<int> h_ids;    // host copy of d_ids (ascending gene ids inside each bucket)
     EmBucket generic;          // n == 0 if empty
     int generic_maxG;
     int fast_maxG;
@@ -77,6 +78,10 @@ struct JacksEmPlan {
 };
 
 namespace {
+
+constexpr int kCountersPerRange = 16;      // [0] deferred count, [1..] one work counter per launch of a gene range
+constexpr int kMaxRanges = 64;
+constexpr int kCounterInts = kCountersPerRange * kMaxRanges;
 
 // Warps per gene of the fast kernel for (G, L); 0 = use the generic kernel.
 int choose_team(int G, int L) {
@@ -131,6 +136,7 @@ int jacks_ctx_create(int device, JacksCtx** out) {
     c->launches = 0;
     if ((e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)) != cudaSuccess) { delete c; return cuda_fail(e, "cudaStreamCreate"); }
     if ((e = cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking)) != cudaSuccess) { delete c; return cuda_fail(e, "cudaStreamCreate"); }
+    if ((e = cudaStreamCreateWithFlags(&c->out_stream, cudaStreamNonBlocking)) != cudaSuccess) { delete c; return cuda_fail(e, "cudaStreamCreate"); }
     *out = c;
     return JACKS_OK;
 }
@@ -139,15 +145,33 @@ void jacks_ctx_destroy(JacksCtx* c) {
     if (!c) return;
     cudaSetDevice(c->device);
     cudaDeviceSynchronize();
+    for (JacksEmPlan* pl : c->pending_plans) jacks_em_plan_destroy(pl);
+    for (cudaEvent_t ev : c->pending_events) cudaEventDestroy(ev);
+    for (PlanBufs* pb : c->plan_pool) { pb->release(); delete pb; }
     c->res_test.release(); c->res_ctrl.release(); c->res_fx.release();
     for (auto& b : c->out) b.release();
     c->tmp.release();
     if (c->stream) cudaStreamDestroy(c->stream);
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+    if (c->out_stream) cudaStreamDestroy(c->out_stream);
     delete c;
 }
 
 int64_t jacks_ctx_launch_count(const JacksCtx* c) { return c ? c->launches : 0; }
+
+int jacks_ctx_synchronize(JacksCtx* c) {
+    if (!c) return fail(JACKS_E_INVALID, "jacks_ctx_synchronize: NULL ctx");
+    cudaSetDevice(c->device);
+    const cudaError_t e1 = cudaStreamSynchronize(c->copy_stream), e2 = cudaStreamSynchronize(c->stream),
+                      e3 = cudaStreamSynchronize(c->out_stream);
+    for (JacksEmPlan* pl : c->pending_plans) jacks_em_plan_destroy(pl);
+    c->pending_plans.clear();
+    for (cudaEvent_t ev : c->pending_events) cudaEventDestroy(ev);
+    c->pending_events.clear();
+    if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess)
+        return cuda_fail(e2 != cudaSuccess ? e2 : (e1 != cudaSuccess ? e1 : e3), "EM pipeline");
+    return JACKS_OK;
+}
 
 void jacks_em_default_params(JacksEmParams* p) {
     if (!p) return;
@@ -186,6 +210,14 @@ int jacks_em_plan_create(JacksCtx* ctx, const int64_t* gene_offsets, const int32
     if (e != cudaSuccess) return cuda_fail(e, "cudaSetDevice");
 
     JacksEmPlan* p = new JacksEmPlan();
+    if (!ctx->plan_pool.empty()) {
+        size_t pick = ctx->plan_pool.size() - 1;          // prefer buffers that served the same shape: no regrowth
+        for (size_t i = 0; i < ctx->plan_pool.size(); ++i)
+            if (ctx->plan_pool[i]->sig_genes == n_genes && ctx->plan_pool[i]->sig_guides == total) { pick = i; break; }
+        p->b = ctx->plan_pool[pick];
+        ctx->plan_pool.erase(ctx->plan_pool.begin() + pick);
+    } else p->b = new PlanBufs();
+    p->b->sig_genes = n_genes; p->b->sig_guides = total;
     p->ctx = ctx; p->n_genes = n_genes; p->n_rows = n_rows; p->total_guides = total; p->L = n_lines;
     p->generic = EmBucket{0, 0, 0, 0, 0};
     p->generic_maxG = 0; p->fast_maxG = 0; p->n_fast_genes = 0;
@@ -233,15 +265,16 @@ int jacks_em_plan_create(JacksCtx* ctx, const int64_t* gene_offsets, const int32
             if (ee != cudaSuccess) rc = cuda_fail(ee, "cudaMemcpyAsync(plan)");
         }
     };
-    up(p->d_offsets, gene_offsets, (size_t)(n_genes + 1) * sizeof(int64_t));
-    up(p->d_rows, guide_rows, (size_t)total * sizeof(int32_t));
-    up(p->d_ids, ids.data(), ids.size() * sizeof(int));
-    up(p->d_slot_off, slot_off.data(), slot_off.size() * sizeof(long long));
-    up(p->d_slot_rows, slot_rows.data(), slot_rows.size() * sizeof(int));
-    if (rc == JACKS_OK) rc = p->d_deferred.reserve((size_t)std::max<int64_t>(n_genes, 1) * sizeof(int));
-    if (rc == JACKS_OK) rc = p->d_counters.reserve(64 * sizeof(int));
+    up(p->b->d_offsets, gene_offsets, (size_t)(n_genes + 1) * sizeof(int64_t));
+    up(p->b->d_rows, guide_rows, (size_t)total * sizeof(int32_t));
+    up(p->b->d_ids, ids.data(), ids.size() * sizeof(int));
+    p->h_ids = ids;
+    up(p->b->d_slot_off, slot_off.data(), slot_off.size() * sizeof(long long));
+    up(p->b->d_slot_rows, slot_rows.data(), slot_rows.size() * sizeof(int));
+    if (rc == JACKS_OK) rc = p->b->d_deferred.reserve((size_t)std::max<int64_t>(n_genes, 1) * sizeof(int));
+    if (rc == JACKS_OK) rc = p->b->d_counters.reserve(kCounterInts * sizeof(int));
     if (rc == JACKS_OK && p->fast_maxG > 0)
-        rc = p->d_tpd.reserve((size_t)ctx->n_sm * kMaxFastCtasPerSm * p->fast_maxG * n_lines * sizeof(double));
+        rc = p->b->d_tpd.reserve((size_t)ctx->n_sm * kMaxFastCtasPerSm * p->fast_maxG * n_lines * sizeof(double));
     // generic kernel configurations (and global scratch if a gene's working set exceeds shared memory)
     memset(&p->cfg_generic, 0, sizeof p->cfg_generic);
     memset(&p->cfg_deferred, 0, sizeof p->cfg_deferred);
@@ -256,7 +289,7 @@ int jacks_em_plan_create(JacksCtx* ctx, const int64_t* gene_offsets, const int32
         if (e != cudaSuccess) rc = cuda_fail(e, "em_generic_configure");
         else scratch_doubles = std::max(scratch_doubles, p->cfg_deferred.scratch_doubles_per_warp * p->cfg_deferred.grid * p->cfg_deferred.warps_per_cta);
     }
-    if (rc == JACKS_OK && scratch_doubles > 0) rc = p->d_scratch.reserve((size_t)scratch_doubles * sizeof(double));
+    if (rc == JACKS_OK && scratch_doubles > 0) rc = p->b->d_scratch.reserve((size_t)scratch_doubles * sizeof(double));
     if (rc == JACKS_OK) {
         e = cudaStreamSynchronize(ctx->stream);      // host vectors go out of scope
         if (e != cudaSuccess) rc = cuda_fail(e, "cudaStreamSynchronize(plan)");
@@ -268,69 +301,69 @@ int jacks_em_plan_create(JacksCtx* ctx, const int64_t* gene_offsets, const int32
 
 void jacks_em_plan_destroy(JacksEmPlan* p) {
     if (!p) return;
-    cudaSetDevice(p->ctx->device);
-    p->d_offsets.release(); p->d_rows.release(); p->d_ids.release(); p->d_slot_off.release();
-    p->d_slot_rows.release(); p->d_deferred.release(); p->d_tpd.release();
-    p->d_counters.release(); p->d_scratch.release();
+    if (p->b) p->ctx->plan_pool.push_back(p->b);      // buffers are recycled, freed with the context
     delete p;
 }
 
-int jacks_em_run_device(JacksCtx* ctx, const JacksEmPlan* plan, const JacksEmParams* params,
-                        const JacksEmDeviceIO* io, void* stream) {
-    if (!ctx || !plan || !params || !io) return fail(JACKS_E_INVALID, "jacks_em_run_device: NULL argument");
-    if (plan->n_genes == 0) return JACKS_OK;
-    if (!io->test || !io->ctrl || !io->w1) return fail(JACKS_E_INVALID, "test, ctrl and w1 are required");
-    if (io->ctrl_lines != plan->L && io->ctrl_lines != 1)
-        return fail(JACKS_E_SHAPE, "Expecting matched size between control and test data");   // infer.py:26
-    if ((io->fixed_x1 == nullptr) != (io->fixed_x2 == nullptr)) return fail(JACKS_E_INVALID, "fixed_x1 and fixed_x2 go together");
-    if (params->n_iter < 0) return fail(JACKS_E_INVALID, "n_iter < 0");
-    cudaStream_t st = (cudaStream_t)stream;
-    cudaError_t e = cudaSetDevice(ctx->device);
-    if (e != cudaSuccess) return cuda_fail(e, "cudaSetDevice");
-
-    int* counters = (int*)plan->d_counters.p;     // [0] deferred count, [1..] one work counter per launch
-    if ((e = cudaMemsetAsync(counters, 0, 64 * sizeof(int), st)) != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync");
-
+// Enqueue the EM of the genes with id in [g0, g1) (caller order) on `st`.  `range` selects the counter block;
+// the caller zeroes d_counters before the first range of a run.
+static int em_run_range(JacksCtx* ctx, const JacksEmPlan* plan, const JacksEmParams* params, const JacksEmDeviceIO* io,
+                        cudaStream_t st, int64_t g0, int64_t g1, int range) {
+    cudaError_t e;
+    int* counters = (int*)plan->b->d_counters.p + range * kCountersPerRange;
     EmLaunch a;
     memset(&a, 0, sizeof a);
     a.test = (const double2*)io->test; a.ctrl = (const double2*)io->ctrl;
     a.L = plan->L; a.ctrl_lines = io->ctrl_lines; a.ctrl_rowmean_fill = io->ctrl_rowmean_fill;
-    a.gene_offsets = (const long long*)plan->d_offsets.p; a.guide_rows = (const int*)plan->d_rows.p;
+    a.gene_offsets = (const long long*)plan->b->d_offsets.p; a.guide_rows = (const int*)plan->b->d_rows.p;
     a.fixed_x1 = io->fixed_x1; a.fixed_x2 = io->fixed_x2;
     a.x1 = io->x1; a.x2 = io->x2; a.w1 = io->w1; a.w2 = io->w2; a.y = io->y; a.tau = io->tau;
     a.n_iters = io->n_iters; a.bound = io->bound;
-    a.deferred_ids = (int*)plan->d_deferred.p; a.deferred_count = counters;
+    a.deferred_ids = (int*)plan->b->d_deferred.p + g0; a.deferred_count = counters;     // a range defers at most its own genes
     a.n_iter = params->n_iter; a.apply_w_hp = params->apply_w_hp; a.tol = params->tol;
     a.mu0_x = params->mu0_x; a.var0_x = params->var0_x; a.mu0_w = params->mu0_w; a.var0_w = params->var0_w;
     a.tps = params->tau_prior_strength;
-    a.scratch = (double*)plan->d_scratch.p;
-    a.tpd_scratch = (double*)plan->d_tpd.p;
+    a.scratch = (double*)plan->b->d_scratch.p;
+    a.tpd_scratch = (double*)plan->b->d_tpd.p;
 
-    int slot = 1;
+    auto slots_of = [&](const EmBucket& b, int* s0, int* s1) {     // ids ascend inside a bucket
+        const int* first = plan->h_ids.data() + b.ids_off;
+        *s0 = (int)(std::lower_bound(first, first + b.n, (int)g0) - first);
+        *s1 = (int)(std::lower_bound(first, first + b.n, (int)g1) - first);
+    };
+    int slot = 1, n_fast = 0;
     for (const EmBucket& b : plan->fast) {
-        a.gene_ids = (const int*)plan->d_ids.p + b.ids_off;
-        a.slot_off = (const long long*)plan->d_slot_off.p + b.ids_off;
-        a.slot_rows = (const int*)plan->d_slot_rows.p + b.rows_off;
-        a.n_work = b.n; a.n_work_dev = nullptr;
+        int s0, s1;
+        slots_of(b, &s0, &s1);
+        if (s1 <= s0) continue;
+        a.gene_ids = (const int*)plan->b->d_ids.p + b.ids_off + s0;
+        a.slot_off = (const long long*)plan->b->d_slot_off.p + b.ids_off + s0;
+        a.slot_rows = (const int*)plan->b->d_slot_rows.p + b.rows_off + (long long)s0 * b.G;
+        a.n_work = s1 - s0; a.n_work_dev = nullptr;
         a.work_counter = counters + slot++;
         int grid = 0;
         e = launch_em_fast(b.G, b.W, a, ctx->n_sm, 0, st, &grid);
         if (e != cudaSuccess) return cuda_fail(e, "em_fast_kernel launch");
         ctx->launches++;
+        n_fast += s1 - s0;
     }
     if (plan->generic.n > 0) {
-        a.gene_ids = (const int*)plan->d_ids.p + plan->generic.ids_off;
-        a.n_work = plan->generic.n; a.n_work_dev = nullptr;
-        a.work_counter = counters + slot++;
-        a.scratch_stride = plan->cfg_generic.scratch_doubles_per_warp;
-        e = launch_em_generic(plan->cfg_generic, a, st);
-        if (e != cudaSuccess) return cuda_fail(e, "em_generic_kernel launch");
-        ctx->launches++;
+        int s0, s1;
+        slots_of(plan->generic, &s0, &s1);
+        if (s1 > s0) {
+            a.gene_ids = (const int*)plan->b->d_ids.p + plan->generic.ids_off + s0;
+            a.n_work = s1 - s0; a.n_work_dev = nullptr;
+            a.work_counter = counters + slot++;
+            a.scratch_stride = plan->cfg_generic.scratch_doubles_per_warp;
+            e = launch_em_generic(plan->cfg_generic, a, st);
+            if (e != cudaSuccess) return cuda_fail(e, "em_generic_kernel launch");
+            ctx->launches++;
+        }
     }
-    if (plan->n_fast_genes > 0) {
+    if (n_fast > 0) {
         // genes the fast kernels handed back because their data holds NaN/inf
-        a.gene_ids = (const int*)plan->d_deferred.p;
-        a.n_work = plan->n_fast_genes; a.n_work_dev = counters;
+        a.gene_ids = (const int*)plan->b->d_deferred.p + g0;
+        a.n_work = n_fast; a.n_work_dev = counters;
         a.work_counter = counters + slot++;
         a.scratch_stride = plan->cfg_deferred.scratch_doubles_per_warp;
         e = launch_em_generic(plan->cfg_deferred, a, st);
@@ -338,6 +371,28 @@ int jacks_em_run_device(JacksCtx* ctx, const JacksEmPlan* plan, const JacksEmPar
         ctx->launches++;
     }
     return JACKS_OK;
+}
+
+static int em_check_io(const JacksEmPlan* plan, const JacksEmParams* params, const JacksEmDeviceIO* io) {
+    if (!io->test || !io->ctrl || !io->w1) return fail(JACKS_E_INVALID, "test, ctrl and w1 are required");
+    if (io->ctrl_lines != plan->L && io->ctrl_lines != 1)
+        return fail(JACKS_E_SHAPE, "Expecting matched size between control and test data");   // infer.py:26
+    if ((io->fixed_x1 == nullptr) != (io->fixed_x2 == nullptr)) return fail(JACKS_E_INVALID, "fixed_x1 and fixed_x2 go together");
+    if (params->n_iter < 0) return fail(JACKS_E_INVALID, "n_iter < 0");
+    return JACKS_OK;
+}
+
+int jacks_em_run_device(JacksCtx* ctx, const JacksEmPlan* plan, const JacksEmParams* params,
+                        const JacksEmDeviceIO* io, void* stream) {
+    if (!ctx || !plan || !params || !io) return fail(JACKS_E_INVALID, "jacks_em_run_device: NULL argument");
+    if (plan->n_genes == 0) return JACKS_OK;
+    int rc = em_check_io(plan, params, io);
+    if (rc != JACKS_OK) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaError_t e = cudaSetDevice(ctx->device);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaSetDevice");
+    if ((e = cudaMemsetAsync(plan->b->d_counters.p, 0, kCountersPerRange * sizeof(int), st)) != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync");
+    return em_run_range(ctx, plan, params, io, st, 0, plan->n_genes, 0);
 }
 
 int jacks_em_batched_host(JacksCtx* ctx, const JacksEmParams* params, const int64_t* gene_offsets,
@@ -350,18 +405,16 @@ int jacks_em_batched_host(JacksCtx* ctx, const JacksEmParams* params, const int6
         return fail(JACKS_E_SHAPE, "Expecting matched size between control and test data");
     cudaError_t e = cudaSetDevice(ctx->device);
     if (e != cudaSuccess) return cuda_fail(e, "cudaSetDevice");
-    cudaStream_t st = ctx->stream;
+    cudaStream_t s_k = ctx->stream, s_in = ctx->copy_stream, s_out = ctx->out_stream;
     int rc;
 
     // ---- inputs: upload, or reuse the cubes a previous call left resident -------------------------
-    const size_t test_bytes = (size_t)N * L * 2 * sizeof(double);
-    const size_t ctrl_bytes = (size_t)N * io->ctrl_lines * 2 * sizeof(double);
-    if (io->test) {
+    const size_t row_t = (size_t)L * 2 * sizeof(double), row_c = (size_t)io->ctrl_lines * 2 * sizeof(double);
+    const bool upload = (io->test != nullptr);
+    if (upload) {
         if (!io->ctrl) return fail(JACKS_E_INVALID, "ctrl is NULL");
-        if ((rc = ctx->res_test.reserve(test_bytes ? test_bytes : 8)) != JACKS_OK) return rc;
-        if ((rc = ctx->res_ctrl.reserve(ctrl_bytes ? ctrl_bytes : 8)) != JACKS_OK) return rc;
-        if (test_bytes && (e = cudaMemcpyAsync(ctx->res_test.p, io->test, test_bytes, cudaMemcpyHostToDevice, st)) != cudaSuccess) return cuda_fail(e, "H2D test");
-        if (ctrl_bytes && (e = cudaMemcpyAsync(ctx->res_ctrl.p, io->ctrl, ctrl_bytes, cudaMemcpyHostToDevice, st)) != cudaSuccess) return cuda_fail(e, "H2D ctrl");
+        if ((rc = ctx->res_test.reserve(N ? N * row_t : 8)) != JACKS_OK) return rc;
+        if ((rc = ctx->res_ctrl.reserve(N ? N * row_c : 8)) != JACKS_OK) return rc;
         ctx->res_N = N; ctx->res_L = L; ctx->res_ctrl_lines = io->ctrl_lines; ctx->res_valid = true;
     } else {
         if (!ctx->res_valid || ctx->res_N != N || ctx->res_L != L || ctx->res_ctrl_lines != io->ctrl_lines)
@@ -372,8 +425,8 @@ int jacks_em_batched_host(JacksCtx* ctx, const JacksEmParams* params, const int6
         if (!io->fixed_x1 || !io->fixed_x2) return fail(JACKS_E_INVALID, "fixed_x1 and fixed_x2 go together");
         if ((rc = ctx->res_fx.reserve((size_t)N * 2 * sizeof(double) + 8)) != JACKS_OK) return rc;
         if (N) {
-            if ((e = cudaMemcpyAsync(ctx->res_fx.p, io->fixed_x1, (size_t)N * sizeof(double), cudaMemcpyHostToDevice, st)) != cudaSuccess) return cuda_fail(e, "H2D fixed_x1");
-            if ((e = cudaMemcpyAsync((double*)ctx->res_fx.p + N, io->fixed_x2, (size_t)N * sizeof(double), cudaMemcpyHostToDevice, st)) != cudaSuccess) return cuda_fail(e, "H2D fixed_x2");
+            if ((e = cudaMemcpyAsync(ctx->res_fx.p, io->fixed_x1, (size_t)N * sizeof(double), cudaMemcpyHostToDevice, s_k)) != cudaSuccess) return cuda_fail(e, "H2D fixed_x1");
+            if ((e = cudaMemcpyAsync((double*)ctx->res_fx.p + N, io->fixed_x2, (size_t)N * sizeof(double), cudaMemcpyHostToDevice, s_k)) != cudaSuccess) return cuda_fail(e, "H2D fixed_x2");
         }
         d_fx1 = (const double*)ctx->res_fx.p; d_fx2 = d_fx1 + N;
     }
@@ -383,17 +436,19 @@ int jacks_em_batched_host(JacksCtx* ctx, const JacksEmParams* params, const int6
     const int64_t T = plan->total_guides;
 
     // ---- outputs ------------------------------------------------------------------------------------
-    struct Out { void* host; size_t bytes; } outs[8] = {
-        {io->x1, (size_t)T * sizeof(double)},        {io->x2, (size_t)T * sizeof(double)},
-        {io->w1, (size_t)n_genes * L * sizeof(double)}, {io->w2, (size_t)n_genes * L * sizeof(double)},
-        {io->y, (size_t)T * L * sizeof(double)},     {io->tau, (size_t)T * L * sizeof(double)},
-        {io->n_iters, (size_t)n_genes * sizeof(int32_t)}, {io->bound, (size_t)n_genes * sizeof(double)}};
+    // per-unit sizes: [0,1] per guide, [2,3] per gene row, [4,5] per guide row, [6,7] per gene
+    struct Out { char* host; size_t unit; bool per_guide; } outs[8] = {
+        {(char*)io->x1, sizeof(double), true},         {(char*)io->x2, sizeof(double), true},
+        {(char*)io->w1, (size_t)L * sizeof(double), false}, {(char*)io->w2, (size_t)L * sizeof(double), false},
+        {(char*)io->y, (size_t)L * sizeof(double), true},   {(char*)io->tau, (size_t)L * sizeof(double), true},
+        {(char*)io->n_iters, sizeof(int32_t), false},  {(char*)io->bound, sizeof(double), false}};
     if (!io->w1 && n_genes) { jacks_em_plan_destroy(plan); return fail(JACKS_E_INVALID, "w1 is required"); }
-    void* dptr[8] = {nullptr};
+    char* dptr[8] = {nullptr};
     for (int i = 0; i < 8; ++i) {
-        if (!outs[i].host || !outs[i].bytes) continue;
-        if ((rc = ctx->out[i].reserve(outs[i].bytes)) != JACKS_OK) { jacks_em_plan_destroy(plan); return rc; }
-        dptr[i] = ctx->out[i].p;
+        const size_t bytes = outs[i].unit * (size_t)(outs[i].per_guide ? T : n_genes);
+        if (!outs[i].host || !bytes) continue;
+        if ((rc = plan->b->out[i].reserve(bytes)) != JACKS_OK) { jacks_em_plan_destroy(plan); return rc; }
+        dptr[i] = (char*)plan->b->out[i].p;
     }
     JacksEmDeviceIO dio;
     memset(&dio, 0, sizeof dio);
@@ -402,17 +457,67 @@ int jacks_em_batched_host(JacksCtx* ctx, const JacksEmParams* params, const int6
     dio.fixed_x1 = d_fx1; dio.fixed_x2 = d_fx2;
     dio.x1 = (double*)dptr[0]; dio.x2 = (double*)dptr[1]; dio.w1 = (double*)dptr[2]; dio.w2 = (double*)dptr[3];
     dio.y = (double*)dptr[4]; dio.tau = (double*)dptr[5]; dio.n_iters = (int32_t*)dptr[6]; dio.bound = (double*)dptr[7];
-    rc = jacks_em_run_device(ctx, plan, params, &dio, st);
+    rc = (n_genes > 0) ? em_check_io(plan, params, &dio) : JACKS_OK;
+
+    // ---- pipeline: gene ranges flow through upload -> kernels -> download on three streams ------------
+    // Ranges are contiguous gene blocks.  When the guide rows ascend along the index (a real screen: genes own
+    // consecutive rows) each range uploads just the rows up to its last one, so the first kernels start after
+    // 1/R of the upload; otherwise (pseudo-genes, arbitrary gathers) everything is uploaded before the kernels.
+    int R = 1;
+    if (n_genes >= 4096) R = (int)std::min<int64_t>(16, n_genes / 2048);
+    if (R > kMaxRanges) R = kMaxRanges;
+    bool ascending = upload;
+    if (upload && R > 1) {
+        for (int64_t i = 1; i < T && ascending; ++i) ascending = guide_rows[i] >= guide_rows[i - 1];
+    }
+    std::vector<cudaEvent_t> ev_in(R, nullptr), ev_k(R, nullptr);
+    for (int r = 0; r < R && rc == JACKS_OK; ++r) {
+        if ((e = cudaEventCreateWithFlags(&ev_in[r], cudaEventDisableTiming)) != cudaSuccess) rc = cuda_fail(e, "cudaEventCreate");
+        else if ((e = cudaEventCreateWithFlags(&ev_k[r], cudaEventDisableTiming)) != cudaSuccess) rc = cuda_fail(e, "cudaEventCreate");
+    }
+    if (rc == JACKS_OK && (e = cudaMemsetAsync(plan->b->d_counters.p, 0, kCounterInts * sizeof(int), s_k)) != cudaSuccess) rc = cuda_fail(e, "cudaMemsetAsync");
+    cudaEvent_t ev_start = nullptr;
     if (rc == JACKS_OK) {
+        // the copy streams must not run ahead of earlier work on the compute stream (previous call's kernels, memset)
+        if ((e = cudaEventCreateWithFlags(&ev_start, cudaEventDisableTiming)) != cudaSuccess) rc = cuda_fail(e, "cudaEventCreate");
+        else { cudaEventRecord(ev_start, s_k); cudaStreamWaitEvent(s_in, ev_start, 0); cudaStreamWaitEvent(s_out, ev_start, 0); }
+    }
+    int64_t row_done = 0;        // rows [0, row_done) are already enqueued for upload
+    for (int r = 0; r < R && rc == JACKS_OK; ++r) {
+        const int64_t g0 = n_genes * r / R, g1 = n_genes * (r + 1) / R;
+        if (upload) {
+            int64_t row_hi = N;
+            if (ascending && r + 1 < R && g1 > g0) row_hi = std::min<int64_t>(N, (int64_t)guide_rows[gene_offsets[g1] - 1] + 1);
+            else if (!ascending && r > 0) row_hi = row_done;
+            if (row_hi > row_done) {
+                if ((e = cudaMemcpyAsync((char*)ctx->res_test.p + row_done * row_t, (const char*)io->test + row_done * row_t,
+                                         (row_hi - row_done) * row_t, cudaMemcpyHostToDevice, s_in)) != cudaSuccess) { rc = cuda_fail(e, "H2D test"); break; }
+                if ((e = cudaMemcpyAsync((char*)ctx->res_ctrl.p + row_done * row_c, (const char*)io->ctrl + row_done * row_c,
+                                         (row_hi - row_done) * row_c, cudaMemcpyHostToDevice, s_in)) != cudaSuccess) { rc = cuda_fail(e, "H2D ctrl"); break; }
+                row_done = row_hi;
+            }
+            cudaEventRecord(ev_in[r], s_in);
+            cudaStreamWaitEvent(s_k, ev_in[r], 0);
+        }
+        if (g1 > g0) rc = em_run_range(ctx, plan, params, &dio, s_k, g0, g1, r);
+        if (rc != JACKS_OK) break;
+        cudaEventRecord(ev_k[r], s_k);
+        cudaStreamWaitEvent(s_out, ev_k[r], 0);
+        const int64_t t0 = gene_offsets[g0], t1 = gene_offsets[g1];
         for (int i = 0; i < 8 && rc == JACKS_OK; ++i) {
             if (!dptr[i]) continue;
-            if ((e = cudaMemcpyAsync(outs[i].host, dptr[i], outs[i].bytes, cudaMemcpyDeviceToHost, st)) != cudaSuccess) rc = cuda_fail(e, "D2H result");
+            const size_t lo = outs[i].unit * (size_t)(outs[i].per_guide ? t0 : g0), hi = outs[i].unit * (size_t)(outs[i].per_guide ? t1 : g1);
+            if (hi > lo && (e = cudaMemcpyAsync(outs[i].host + lo, dptr[i] + lo, hi - lo, cudaMemcpyDeviceToHost, s_out)) != cudaSuccess) rc = cuda_fail(e, "D2H result");
         }
     }
-    e = cudaStreamSynchronize(st);
-    if (rc == JACKS_OK && e != cudaSuccess) rc = cuda_fail(e, "EM kernels");
-    jacks_em_plan_destroy(plan);
-    if (!keep_resident) ctx->res_valid = false;
+    for (int r = 0; r < R; ++r) { if (ev_in[r]) ctx->pending_events.push_back(ev_in[r]); if (ev_k[r]) ctx->pending_events.push_back(ev_k[r]); }
+    if (ev_start) ctx->pending_events.push_back(ev_start);
+    ctx->pending_plans.push_back(plan);
+    if (!(keep_resident & JACKS_KEEP_RESIDENT)) ctx->res_valid = false;
+    if (rc != JACKS_OK || !(keep_resident & JACKS_ASYNC)) {
+        const int rs = jacks_ctx_synchronize(ctx);
+        if (rc == JACKS_OK) rc = rs;
+    }
     return rc;
 }
 

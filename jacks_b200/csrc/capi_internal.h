@@ -21,12 +21,30 @@ struct DevBuf {
 
 }  // namespace jacks
 
+#include <vector>
+
+// Device buffers of one batched-EM plan.  Plans come and go with every host call; their buffers are recycled
+// through JacksCtx::plan_pool instead of cudaMalloc/cudaFree (both synchronise the device).
+struct PlanBufs {
+    jacks::DevBuf d_offsets, d_rows, d_ids, d_slot_off, d_slot_rows, d_deferred, d_counters, d_scratch, d_tpd;
+    jacks::DevBuf out[8];                   // device-side outputs of a host call that used this plan
+    long long sig_genes = -1, sig_guides = -1;   // shape of the last plan served (pool lookups prefer a match)
+    void release() {
+        for (auto& o : out) o.release();
+        d_offsets.release(); d_rows.release(); d_ids.release(); d_slot_off.release(); d_slot_rows.release();
+        d_deferred.release(); d_counters.release(); d_scratch.release(); d_tpd.release();
+    }
+};
+
+struct JacksEmPlan;
+
 struct JacksCtx {
     int device;
     int n_sm;
     int64_t launches;
     cudaStream_t stream;        // compute + default copies of the host entry points
-    cudaStream_t copy_stream;   // overlapped copies
+    cudaStream_t copy_stream;   // host -> device copies of the pipelined host entry points
+    cudaStream_t out_stream;    // device -> host copies of the pipelined host entry points
     // data cubes kept resident between host calls (jacks_em_batched_host keep_resident)
     jacks::DevBuf res_test, res_ctrl, res_fx;
     int64_t res_N = 0;
@@ -34,4 +52,7 @@ struct JacksCtx {
     bool res_valid = false;
     jacks::DevBuf out[8];       // device-side outputs of the host entry points
     jacks::DevBuf tmp;          // scratch of the p-value / preprocessing entry points
+    std::vector<PlanBufs*> plan_pool;          // recycled plan buffers
+    std::vector<JacksEmPlan*> pending_plans;   // plans of asynchronous host calls, destroyed at the next synchronise
+    std::vector<cudaEvent_t> pending_events;
 };
