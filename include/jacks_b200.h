@@ -208,12 +208,23 @@ JACKS_API int jacks_condense_host(JacksCtx* ctx, const double* logcounts, int64_
  *   normtype  JACKS_NORM_MEDIAN       x - nanmedian(x)                                    (:80-81)
  *             JACKS_NORM_ZMAD         (x - nanmedian(x)) / (1.4826 * nanmedian|x - med|)    (:82-84)
  *             JACKS_NORM_CTRL_GUIDES  x - nanmedian(x[row_mask != 0])                      (:92-94)
+ *             JACKS_NORM_MODE         x - centre of the fullest bin of the 5-tap smoothed 100-bin histogram (:85-91)
  *   row_mask [n_guides] bytes, required for JACKS_NORM_CTRL_GUIDES only.
  */
-enum { JACKS_NORM_MEDIAN = 0, JACKS_NORM_ZMAD = 1, JACKS_NORM_CTRL_GUIDES = 2 };
+enum { JACKS_NORM_MEDIAN = 0, JACKS_NORM_ZMAD = 1, JACKS_NORM_CTRL_GUIDES = 2, JACKS_NORM_MODE = 3 };
 JACKS_API int jacks_normalize_host(JacksCtx* ctx, const double* values, int64_t n_guides, int32_t n_cols, int32_t take_log,
                          double prior, const double* log2_table, int64_t table_len, int32_t normtype,
                          const uint8_t* row_mask, double* out);
+
+/*
+ * calc_posterior_sd with a guide subset (preprocess.py:25-58 with guideset_indexs; used by inferMissingVariances,
+ * preprocess.py:98-119, for single-replicate samples): the mean-variance curve is fitted on the guides with
+ * in_set != 0 (window resolved by the caller from the subset size, preprocess.py:35) and interpolated
+ * (np.interp, preprocess.py:50-52) at every guide's mean.
+ *   data [n_guides, n_rep] (n_rep >= 2), in_set [n_guides] bytes, sd [n_guides] out.
+ */
+JACKS_API int jacks_posterior_sd_subset_host(JacksCtx* ctx, const double* data, int64_t n_guides, int32_t n_rep,
+                                   const uint8_t* in_set, int32_t window, int32_t monotonize, double* sd);
 
 /* FP64 FMA-pipe peak of the current device in FLOP/s (dependent-chain-free DFMA microbenchmark);
  * bench.py uses it as the roofline denominator because MEASURED_PEAKS.json has no FP64 entry. */

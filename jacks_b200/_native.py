@@ -88,6 +88,7 @@ def lib():
         if hasattr(L, 'jacks_condense_host'):
             L.jacks_condense_host.argtypes = [vp, vp, i64, i32, vp, vp, i32, i32, i32, vp]
             L.jacks_normalize_host.argtypes = [vp, vp, i64, i32, i32, dbl, vp, i64, i32, vp, vp]
+            L.jacks_posterior_sd_subset_host.argtypes = [vp, vp, i64, i32, vp, i32, i32, vp]
         _lib = L
     return _lib
 
@@ -294,7 +295,7 @@ def kde_pvalues_host(ctx, w1_genes, w1_pseudo, positive=False):
 LOG2_TABLE_MAX = 1 << 24
 
 
-NORM_TYPES = {'median': 0, 'zmad': 1, 'ctrl_guides': 2}
+NORM_TYPES = {'median': 0, 'zmad': 1, 'ctrl_guides': 2, 'mode': 3}
 
 
 def normalize_host(ctx, values, normtype='median', take_log=False, prior=32.0, row_mask=None, use_table=True):
@@ -328,3 +329,13 @@ def condense_host(ctx, logcounts, Iscreens, window=0, monotonize=True):
     check(lib().jacks_condense_host(ctx.h, _ptr(logcounts), logcounts.shape[0], logcounts.shape[1], _ptr(offs),
                                     _ptr(cols), len(Iscreens), int(window), int(bool(monotonize)), _ptr(data)))
     return data
+
+
+def posterior_sd_subset_host(ctx, data, in_set, window, monotonize=True):
+    """calc_posterior_sd fitted on the guides flagged in `in_set` and interpolated to all guides (GPU)."""
+    data = np.ascontiguousarray(data, dtype=np.float64)
+    mask = np.ascontiguousarray(in_set, dtype=np.uint8)
+    out = np.empty(data.shape[0], dtype=np.float64)
+    check(lib().jacks_posterior_sd_subset_host(ctx.h, _ptr(data), data.shape[0], data.shape[1], _ptr(mask), int(window),
+                                               int(bool(monotonize)), _ptr(out)))
+    return out

@@ -22,6 +22,8 @@
 #include <math.h>
 #include <stdint.h>
 
+#include <vector>
+
 #include "../../include/jacks_b200.h"
 #include "capi_internal.h"
 
@@ -169,6 +171,57 @@ __global__ void scale_mad_kernel(double* mad, int C) {
     if (c < C) mad[c] = 1.4826 * mad[c];          // preprocess.py:84
 }
 
+// normtype 'mode' (preprocess.py:85-91): np.histogram(x, bins=100) of the column, a 5-tap smoothing of the counts,
+// and the centre of the fullest smoothed bin as the shift.  numpy's uniform-bin path is restated step for step
+// (numpy/lib/_histograms_impl.py): edges = linspace(min, max, 101) as i*step + min with the last edge forced to
+// max, a first guess trunc((x-min)/(max-min)*100), then the one-step corrections against the edges -- so every value
+// lands in the bin numpy puts it in.  No FMA contraction.  One CTA per column of the column-major T.
+__global__ void __launch_bounds__(1024) column_mode_kernel(const double* __restrict__ T, long long ldT, long long N,
+                                                           double* __restrict__ shift) {
+    __shared__ double s_edges[101];
+    __shared__ unsigned int s_hist[100];
+    __shared__ double s_red[64];
+    const int c = blockIdx.x;
+    const double* col = T + (long long)c * ldT;
+    double lo = d_inf(), hi = -d_inf();
+    for (long long i = threadIdx.x; i < N; i += blockDim.x) { const double v = col[i]; lo = fmin(lo, v); hi = fmax(hi, v); }
+    for (int o = 16; o > 0; o >>= 1) { lo = fmin(lo, __shfl_xor_sync(0xffffffffu, lo, o)); hi = fmax(hi, __shfl_xor_sync(0xffffffffu, hi, o)); }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) { s_red[warp] = lo; s_red[32 + warp] = hi; }
+    for (int b = threadIdx.x; b < 100; b += blockDim.x) s_hist[b] = 0;
+    __syncthreads();
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) { lo = fmin(lo, s_red[w]); hi = fmax(hi, s_red[32 + w]); }
+    if (lo == hi) { lo = lo - 0.5; hi = hi + 0.5; }                          // numpy widens a zero-width range
+    const double delta = __dadd_rn(hi, -lo);
+    const double step = delta / 100.0;
+    for (int b = threadIdx.x; b <= 100; b += blockDim.x)
+        s_edges[b] = (b == 100) ? hi : __dadd_rn(__dmul_rn((double)b, step), lo);
+    __syncthreads();
+    for (long long i = threadIdx.x; i < N; i += blockDim.x) {
+        const double v = col[i];
+        if (!(v >= lo && v <= hi)) continue;
+        int idx = (int)__dmul_rn(__dadd_rn(v, -lo) / delta, 100.0);
+        if (idx == 100) idx = 99;
+        if (v < s_edges[idx]) idx -= 1;
+        if (v >= s_edges[idx + 1] && idx != 99) idx += 1;
+        atomicAdd(&s_hist[idx], 1u);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double best = -1.0;
+        int arg = 0;
+        for (int i = 0; i < 96; ++i) {
+            double v = __dmul_rn(0.1, (double)s_hist[i]);
+            v = __dadd_rn(v, __dmul_rn(0.2, (double)s_hist[i + 1]));
+            v = __dadd_rn(v, __dmul_rn(0.4, (double)s_hist[i + 2]));
+            v = __dadd_rn(v, __dmul_rn(0.2, (double)s_hist[i + 3]));
+            v = __dadd_rn(v, __dmul_rn(0.1, (double)s_hist[i + 4]));
+            if (v > best) { best = v; arg = i; }                              // np.argmax: first maximum
+        }
+        shift[c] = __dadd_rn(__dmul_rn(0.5, s_edges[arg + 3]), __dmul_rn(0.5, s_edges[arg + 2]));
+    }
+}
+
 // ---- per-sample mean / variance and sort keys ----------------------------------------------------
 // numpy semantics, no FMA contraction: mean = (x0 + x1 + ...)/R in column order; nanstd uses the NaN-aware
 // mean, population variance, and the reference squares the sqrt (nanstd(...)**2, preprocess.py:38).
@@ -286,19 +339,10 @@ __device__ double block_exclusive_scan(double v, double* sh, double* total) {
     return before + x - v;
 }
 
-__global__ void __launch_bounds__(kScanThreads) smooth_monotone_scatter_kernel(const double* __restrict__ kv, const int* __restrict__ ki,
-                                                                               long long Np, long long N, int S, int window,
-                                                                               int monotonize, const int* __restrict__ col_off,
-                                                                               double* __restrict__ P, double* __restrict__ M,
-                                                                               double* __restrict__ data) {
-    __shared__ double sh[32];
-    __shared__ double s_carry;
-    const int s = blockIdx.x;
-    if (col_off[s + 1] - col_off[s] < 2) return;             // single replicate: sd stays NaN
-    const double* x = kv + (long long)s * Np;
-    const int* idx = ki + (long long)s * Np;
-    double* p = P + (long long)s * (Np + 1);
-    double* m = M + (long long)s * Np;
+// m[k] = the reference's shifted sliding mean of x[0..N) with half-width `window` (preprocess.py:16-22); p is
+// scratch for N+1 prefix sums.  Whole CTA (kScanThreads threads) cooperates.
+__device__ void dev_window_smooth(const double* __restrict__ x, long long N, long long window, double* __restrict__ p,
+                                  double* __restrict__ m, double* sh) {
     // exclusive prefix sums p[i] = sum_{t<i} x[t], i = 0..N
     double carry = 0.0;
     for (long long c0 = 0; c0 < N; c0 += kScanThreads) {
@@ -312,9 +356,8 @@ __global__ void __launch_bounds__(kScanThreads) smooth_monotone_scatter_kernel(c
     }
     if (threadIdx.x == 0) p[N] = carry;
     __syncthreads();
-    // window_smooth (preprocess.py:16-22), including its behaviour for short inputs: numpy slices clip, so
-    // the head is the mean of x[0:min(2w+1,N)] and the tail slice x[N-2w-1:] wraps when N < 2w+1; the tail
-    // assignment comes last and wins where the ranges overlap.
+    // numpy slices clip, so the head is the mean of x[0:min(2w+1,N)] and the tail slice x[N-2w-1:] wraps when
+    // N < 2w+1; the tail assignment comes last and wins where the ranges overlap.
     const long long w = window;
     const double span = (double)(2 * w + 1);
     const long long head_hi = (2 * w + 1 < N) ? 2 * w + 1 : N;
@@ -330,18 +373,26 @@ __global__ void __launch_bounds__(kScanThreads) smooth_monotone_scatter_kernel(c
         m[k] = v;
     }
     __syncthreads();
-    // reverse running maximum with NaN restart, chunked from the end; then sd = sqrt(m) to guide order
+}
+
+// In-place reverse running maximum (monotonize, preprocess.py:8-13): a NaN entry stays NaN and restarts the run.
+// Chunked from the end; inside a chunk a segmented max-scan (warp shuffles, then a serial pass over the 32 warp
+// summaries).  Whole CTA cooperates.
+__device__ void dev_reverse_running_max(double* __restrict__ m, long long N) {
+    __shared__ double s_carry;
+    __shared__ double w_last[32];
+    __shared__ int w_blocked[32];
+    __shared__ double w_in[32];
     if (threadIdx.x == 0) s_carry = d_nan();         // "no carry" marker: the last element has no successor
     __syncthreads();
     for (long long hi = N; hi > 0; hi -= kScanThreads) {
         const long long k = hi - 1 - threadIdx.x;                           // thread 0 takes the last element of the chunk
         const bool live = (k >= 0);
-        double v = live ? m[k] : d_nan();
-        // segmented inclusive max-scan in reverse order == forward scan over threadIdx (thread t covers k = hi-1-t)
-        // flag = value is NaN (segment boundary: a NaN neither receives nor passes on a maximum)
+        const double v = live ? m[k] : d_nan();
+        // forward scan over threadIdx == reverse order in k; a NaN neither receives nor passes on a maximum
         const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
         double cur = v;
-        bool open = (v == v);                      // can still take a maximum from earlier threads (later k)
+        const bool open = (v == v);
         bool blocked = !(v == v);                  // a NaN was seen in the span covered so far
         for (int o = 1; o < 32; o <<= 1) {
             const double pv = __shfl_up_sync(0xffffffffu, cur, o);
@@ -351,10 +402,6 @@ __global__ void __launch_bounds__(kScanThreads) smooth_monotone_scatter_kernel(c
                 blocked = blocked || (pb != 0);
             }
         }
-        // cross-warp: serial over warps through shared memory (32 warps)
-        __shared__ double w_last[32];
-        __shared__ int w_blocked[32];
-        __shared__ double w_in[32];
         __syncthreads();
         if (lane == 31) { w_last[warp] = cur; w_blocked[warp] = (int)blocked; }
         __syncthreads();
@@ -362,26 +409,93 @@ __global__ void __launch_bounds__(kScanThreads) smooth_monotone_scatter_kernel(c
             double run = s_carry;                     // running max entering the chunk (NaN = none)
             for (int q = 0; q < (int)(blockDim.x >> 5); ++q) {
                 w_in[q] = run;
-                // what leaves warp q: if the warp saw a NaN the incoming run is cut, the outgoing run is the warp's last value
                 const double last = w_last[q];
-                if (w_blocked[q]) run = last;          // last is the running max since the last NaN (or NaN itself)
+                if (w_blocked[q]) run = last;          // the warp saw a NaN: the incoming run is cut there
                 else run = (run == run && (!(last == last) || run > last)) ? run : last;
             }
             s_carry = run;
         }
         __syncthreads();
         const double incoming = w_in[warp];
-        // apply the incoming run to the lanes of this warp that are not behind a NaN of the same warp
-        // (blocked at lane t means a NaN at some lane <= t within the warp)
         if (live && (v == v) && !blocked && incoming == incoming && incoming > cur) cur = incoming;
-        if (!monotonize) cur = v;                  // calc_posterior_sd(do_monotonize=False)
-        if (live && (v == v)) {
-            m[k] = cur;
-            data[((long long)idx[k] * S + s) * 2 + 1] = sqrt(cur);
-        } else if (live) {
-            data[((long long)idx[k] * S + s) * 2 + 1] = d_nan();
-        }
+        if (live && (v == v)) m[k] = cur;
         __syncthreads();
+    }
+}
+
+// One CTA per sample: smooth the sorted variances, monotonize, sd = sqrt(m) scattered back to guide order.
+__global__ void __launch_bounds__(kScanThreads) smooth_monotone_scatter_kernel(const double* __restrict__ kv, const int* __restrict__ ki,
+                                                                               long long Np, long long N, int S, int window,
+                                                                               int monotonize, const int* __restrict__ col_off,
+                                                                               double* __restrict__ P, double* __restrict__ M,
+                                                                               double* __restrict__ data) {
+    __shared__ double sh[32];
+    const int s = blockIdx.x;
+    if (col_off[s + 1] - col_off[s] < 2) return;             // single replicate: sd stays NaN
+    const int* idx = ki + (long long)s * Np;
+    double* m = M + (long long)s * Np;
+    dev_window_smooth(kv + (long long)s * Np, N, window, P + (long long)s * (Np + 1), m, sh);
+    if (monotonize) dev_reverse_running_max(m, N);
+    for (long long k = threadIdx.x; k < N; k += kScanThreads)
+        data[((long long)idx[k] * S + s) * 2 + 1] = sqrt(m[k]);       // sqrt(NaN) = NaN
+}
+
+// calc_posterior_sd with a guide subset (preprocess.py:44-52): the mean-variance curve is fitted on the subset
+// members (in sorted order), then linearly interpolated (np.interp) at every guide's mean.  One CTA.
+//   km, kv, ki: keys sorted by (mean, var, index), N real entries; in_set[guide] != 0 marks subset members.
+//   sub_mean, sub_var, P, M: scratch of at least N+1 doubles each.
+__global__ void __launch_bounds__(kScanThreads) subset_sd_kernel(const double* __restrict__ km, const double* __restrict__ kv,
+                                                                 const int* __restrict__ ki, long long N,
+                                                                 const unsigned char* __restrict__ in_set, int window,
+                                                                 int monotonize, double* __restrict__ sub_mean,
+                                                                 double* __restrict__ sub_var, double* __restrict__ P,
+                                                                 double* __restrict__ M, double* __restrict__ sd_out) {
+    __shared__ double sh[32];
+    __shared__ long long s_M;
+    // order-preserving compaction of the subset members
+    double carry = 0.0;
+    for (long long c0 = 0; c0 < N; c0 += kScanThreads) {
+        const long long k = c0 + threadIdx.x;
+        const bool member = (k < N) && in_set[ki[k]];
+        double total;
+        const double ex = block_exclusive_scan(member ? 1.0 : 0.0, sh, &total);
+        if (member) {
+            const long long pos = (long long)(carry + ex);
+            sub_mean[pos] = km[k];
+            sub_var[pos] = kv[k];
+        }
+        carry += total;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) s_M = (long long)carry;
+    __syncthreads();
+    const long long Ms = s_M;
+    dev_window_smooth(sub_var, Ms, window, P, M, sh);
+    if (monotonize) dev_reverse_running_max(M, Ms);
+    // np.interp(x = all sorted means, xp = subset means, fp = M)  (numpy/_core/src/multiarray/compiled_base.c)
+    for (long long k = threadIdx.x; k < N; k += kScanThreads) {
+        const double x = km[k];
+        double r;
+        if (x != x) r = x;
+        else if (x < sub_mean[0]) r = M[0];                       // left = fp[0]
+        else if (x >= sub_mean[Ms - 1]) r = M[Ms - 1];            // x == xp[-1] -> fp[-1]; beyond: right = fp[-1]
+        else {
+            long long lo = 0, hi = Ms - 1;                // invariant: sub_mean[lo] <= x < sub_mean[hi]
+            while (hi - lo > 1) {
+                const long long mid = (lo + hi) >> 1;
+                if (sub_mean[mid] <= x) lo = mid; else hi = mid;
+            }
+            if (sub_mean[lo] == x) r = M[lo];
+            else {
+                const double slope = (M[lo + 1] - M[lo]) / (sub_mean[lo + 1] - sub_mean[lo]);
+                r = __dadd_rn(__dmul_rn(slope, x - sub_mean[lo]), M[lo]);
+                if (r != r) {
+                    r = __dadd_rn(__dmul_rn(slope, x - sub_mean[lo + 1]), M[lo + 1]);
+                    if (r != r && M[lo] == M[lo + 1]) r = M[lo];
+                }
+            }
+        }
+        sd_out[ki[k]] = sqrt(r);
     }
 }
 
@@ -395,7 +509,7 @@ extern "C" int jacks_normalize_host(JacksCtx* ctx, const double* values, int64_t
                                     const uint8_t* row_mask, double* out) {
     if (!ctx || !values || !out) return fail(JACKS_E_INVALID, "jacks_normalize_host: NULL argument");
     if (n_guides < 1 || n_cols < 1) return fail(JACKS_E_INVALID, "empty matrix");
-    if (normtype < JACKS_NORM_MEDIAN || normtype > JACKS_NORM_CTRL_GUIDES) return fail(JACKS_E_INVALID, "Unrecognised normalisation type %d", normtype);
+    if (normtype < JACKS_NORM_MEDIAN || normtype > JACKS_NORM_MODE) return fail(JACKS_E_INVALID, "Unrecognised normalisation type %d", normtype);
     if (normtype == JACKS_NORM_CTRL_GUIDES && !row_mask) return fail(JACKS_E_INVALID, "No guides specified for ctrl guide normalization");
     cudaError_t e = cudaSetDevice(ctx->device);
     if (e != cudaSuccess) return cuda_fail(e, "cudaSetDevice");
@@ -424,7 +538,8 @@ extern "C" int jacks_normalize_host(JacksCtx* ctx, const double* values, int64_t
     dim3 tg((unsigned)((N + 31) / 32), (unsigned)((C + 31) / 32));
     log_transpose_kernel<<<tg, 256, 0, st>>>((const double*)ctx->out[0].p, N, C, prior, take_log ? 1 : 0,
                                              table_len ? (const double*)ctx->out[2].p : nullptr, table_len, T, N);
-    column_median_kernel<<<C, 1024, 0, st>>>(T, N, N, d_mask, nullptr, 0, med);                 // preprocess.py:81 / :93
+    if (normtype == JACKS_NORM_MODE) column_mode_kernel<<<C, 1024, 0, st>>>(T, N, N, med);          // preprocess.py:85-91
+    else column_median_kernel<<<C, 1024, 0, st>>>(T, N, N, d_mask, nullptr, 0, med);             // preprocess.py:81 / :93
     ctx->launches += 2;
     const double* scale = nullptr;
     if (normtype == JACKS_NORM_ZMAD) {                                                            // preprocess.py:82-84
@@ -509,5 +624,64 @@ extern "C" int jacks_condense_host(JacksCtx* ctx, const double* logcounts, int64
     if ((e = cudaGetLastError()) != cudaSuccess) return cuda_fail(e, "condense kernels");
     if ((e = cudaMemcpyAsync(data, ctx->out[1].p, db, cudaMemcpyDeviceToHost, st)) != cudaSuccess) return cuda_fail(e, "D2H data");
     if ((e = cudaStreamSynchronize(st)) != cudaSuccess) return cuda_fail(e, "condense kernels");
+    return JACKS_OK;
+}
+
+extern "C" int jacks_posterior_sd_subset_host(JacksCtx* ctx, const double* data, int64_t n_guides, int32_t n_rep,
+                                              const uint8_t* in_set, int32_t window, int32_t monotonize, double* sd) {
+    if (!ctx || !data || !in_set || !sd) return fail(JACKS_E_INVALID, "jacks_posterior_sd_subset_host: NULL argument");
+    if (n_guides < 1 || n_rep < 2) return fail(JACKS_E_INVALID, "need at least one guide and two columns");
+    const long long N = n_guides;
+    long long members = 0;
+    for (long long i = 0; i < N; ++i) members += in_set[i] ? 1 : 0;
+    if (window < 1) return fail(JACKS_E_INVALID, "window < 1");
+    if (members < (long long)window + 1)
+        return fail(JACKS_E_INVALID, "calc_posterior_sd needs at least %d subset guides for its smoothing window (got %lld)", window + 1, members);
+    cudaError_t e = cudaSetDevice(ctx->device);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaSetDevice");
+    long long Np = kSortTile;
+    while (Np < N) Np <<= 1;
+    int rc;
+    const size_t lb = (size_t)N * n_rep * sizeof(double);
+    if ((rc = ctx->out[0].reserve(lb)) != JACKS_OK) return rc;
+    if ((rc = ctx->out[1].reserve((size_t)N * 2 * sizeof(double))) != JACKS_OK) return rc;       // data plane of sample_stats
+    if ((rc = ctx->out[2].reserve((size_t)Np * sizeof(double))) != JACKS_OK) return rc;
+    if ((rc = ctx->out[3].reserve((size_t)Np * sizeof(double))) != JACKS_OK) return rc;
+    if ((rc = ctx->out[4].reserve((size_t)Np * sizeof(int))) != JACKS_OK) return rc;
+    if ((rc = ctx->out[5].reserve((size_t)(N + 1) * 4 * sizeof(double))) != JACKS_OK) return rc;  // sub_mean, sub_var, P, M
+    if ((rc = ctx->out[6].reserve((size_t)N * sizeof(double))) != JACKS_OK) return rc;            // sd
+    if ((rc = ctx->out[7].reserve((size_t)(2 + n_rep) * sizeof(int) + (size_t)N + 16)) != JACKS_OK) return rc;
+    cudaStream_t st = ctx->stream;
+    std::vector<int> h(2 + n_rep);
+    h[0] = 0; h[1] = n_rep;
+    for (int r = 0; r < n_rep; ++r) h[2 + r] = r;
+    int* d_off = (int*)ctx->out[7].p;
+    int* d_cols = d_off + 2;
+    unsigned char* d_set = (unsigned char*)(d_cols + n_rep);
+    if ((e = cudaMemcpyAsync(ctx->out[0].p, data, lb, cudaMemcpyHostToDevice, st)) != cudaSuccess) return cuda_fail(e, "H2D data");
+    if ((e = cudaMemcpyAsync(d_off, h.data(), h.size() * sizeof(int), cudaMemcpyHostToDevice, st)) != cudaSuccess) return cuda_fail(e, "H2D index");
+    if ((e = cudaMemcpyAsync(d_set, in_set, (size_t)N, cudaMemcpyHostToDevice, st)) != cudaSuccess) return cuda_fail(e, "H2D subset");
+    double* km = (double*)ctx->out[2].p; double* kv = (double*)ctx->out[3].p; int* ki = (int*)ctx->out[4].p;
+    dim3 sg((unsigned)((Np + 255) / 256), 1);
+    sample_stats_kernel<<<sg, 256, 0, st>>>((const double*)ctx->out[0].p, N, n_rep, d_off, d_cols, 1, Np, (double*)ctx->out[1].p, km, kv, ki);
+    dim3 lg((unsigned)(Np / kSortTile), 1);
+    bitonic_local_kernel<<<lg, 1024, 0, st>>>(km, kv, ki, Np, 2, kSortTile);
+    ctx->launches += 2;
+    for (long long kk = 2LL * kSortTile; kk <= Np; kk <<= 1) {
+        for (long long j = kk >> 1; j >= kSortTile; j >>= 1) {
+            dim3 gg((unsigned)((Np / 2 + 255) / 256), 1);
+            bitonic_global_kernel<<<gg, 256, 0, st>>>(km, kv, ki, Np, kk, j);
+            ctx->launches++;
+        }
+        bitonic_local_kernel<<<lg, 1024, 0, st>>>(km, kv, ki, Np, (int)kk, (int)kk);
+        ctx->launches++;
+    }
+    double* scratch = (double*)ctx->out[5].p;
+    subset_sd_kernel<<<1, kScanThreads, 0, st>>>(km, kv, ki, N, d_set, window, monotonize ? 1 : 0, scratch, scratch + (N + 1),
+                                                  scratch + 2 * (N + 1), scratch + 3 * (N + 1), (double*)ctx->out[6].p);
+    ctx->launches++;
+    if ((e = cudaGetLastError()) != cudaSuccess) return cuda_fail(e, "subset sd kernels");
+    if ((e = cudaMemcpyAsync(sd, ctx->out[6].p, (size_t)N * sizeof(double), cudaMemcpyDeviceToHost, st)) != cudaSuccess) return cuda_fail(e, "D2H sd");
+    if ((e = cudaStreamSynchronize(st)) != cudaSuccess) return cuda_fail(e, "subset sd kernels");
     return JACKS_OK;
 }

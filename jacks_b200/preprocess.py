@@ -5,9 +5,6 @@ per-column centring and the mean-variance error model -- runs on the GPU through
 (jacks_normalize_host, jacks_condense_host); the host keeps what the reference does with Python
 objects: reading the count table, filtering guides, the string sort of guide ids, the gene index.
 
-Not on the GPU (yet) and therefore raising instead of silently computing on the host:
-``normtype='mode'`` and ``calc_posterior_sd(guideset_indexs=...)`` (the control-guide subset fit that
-``inferMissingVariances`` uses for single-replicate samples when control genes are given).
 """
 import csv
 import io
@@ -32,9 +29,14 @@ def calc_posterior_sd(data, windowfracN=100.0, do_monotonize=True, guideset_inde
     N = data.shape[0]
     if data.ndim == 1 or data.shape[1] == 1:                     # preprocess.py:32
         return np.zeros(N) * np.nan
+    if type(guideset_indexs) == list:
+        guideset_indexs = set(guideset_indexs)
     if len(guideset_indexs) not in (0, N):
-        raise NotImplementedError('calc_posterior_sd with a guide subset (guideset_indexs) is not available on the '
-                                  'GPU path yet')
+        # fit on the subset, interpolate to every guide (preprocess.py:44-52)
+        mask = np.zeros(N, dtype=np.uint8)
+        mask[list(guideset_indexs)] = 1
+        return _native.posterior_sd_subset_host(_native.context(0), data, mask, _window(len(guideset_indexs), windowfracN),
+                                                monotonize=do_monotonize)
     out = _native.condense_host(_native.context(0), data, [list(range(data.shape[1]))],
                                 window=_window(N, windowfracN), monotonize=do_monotonize)
     return np.ascontiguousarray(out[:, 0, 1])
@@ -58,7 +60,7 @@ def normalizeLogCounts(logcounts, normtype='median', ctrl_guide_indexes=[]):
     """Per-column normalisation of log counts (preprocess.py:76-96).  Returns the normalised array."""
     LOG.info('Applying %s normalisation' % normtype)
     logcounts = np.asarray(logcounts, dtype=np.float64)
-    if normtype in ('median', 'zmad'):
+    if normtype in ('median', 'zmad', 'mode'):
         return _native.normalize_host(_native.context(0), logcounts, normtype)
     if normtype == 'ctrl_guides':
         if len(ctrl_guide_indexes) == 0:
@@ -66,8 +68,6 @@ def normalizeLogCounts(logcounts, normtype='median', ctrl_guide_indexes=[]):
         mask = np.zeros(logcounts.shape[0], dtype=np.uint8)
         mask[list(ctrl_guide_indexes)] = 1
         return _native.normalize_host(_native.context(0), logcounts, 'ctrl_guides', row_mask=mask)
-    if normtype == 'mode':
-        raise NotImplementedError("normalisation type 'mode' is not available on the GPU path yet")
     raise Exception('Unrecognised normalisation type %s' % normtype)
 
 
@@ -115,9 +115,7 @@ def loadDataAndPreprocess(sample_spec, gene_spec, ctrl_spec={}, ctrl_geneset=set
     """Load counts from one or more files with the same guides in the same order and condense them
     (preprocess.py:128-173).  sample_spec {filename: [(sample_id, colname)]}.
     Returns data [N, S, 2], meta [N, 2] (guide, gene), sample_ids, genes, gene_guides."""
-    if normtype == 'mode':
-        raise NotImplementedError("normalisation type 'mode' is not available on the GPU path yet")
-    if normtype not in ('median', 'zmad', 'ctrl_guides'):
+    if normtype not in ('median', 'zmad', 'ctrl_guides', 'mode'):
         raise Exception('Unrecognised normalisation type %s' % normtype)
     ctx = _native.context(0)
     samples, sample_counts, metas = [], [], []

@@ -120,8 +120,6 @@ def test_unavailable_branches_raise_instead_of_computing_on_the_host():
     with pytest.raises(NotImplementedError):
         jacks_io.computeW1PvalsAndFDRs({'g': (None,) * 4 + (np.zeros(2), None)}, ['a', 'b'], pseudo=False)
     from jacks_b200 import preprocess
-    with pytest.raises(NotImplementedError):
-        preprocess.normalizeLogCounts(np.zeros((40, 2)), normtype='mode')
     with pytest.raises(Exception, match='Unrecognised normalisation type'):
         preprocess.normalizeLogCounts(np.zeros((40, 2)), normtype='bogus')
     assert np.isnan(preprocess.calc_posterior_sd(np.ones((5, 1)))).all()

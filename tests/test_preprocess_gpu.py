@@ -90,3 +90,58 @@ def test_too_few_guides_is_an_error(nat):
     ctx = nat.context(0)
     with pytest.raises(Exception, match='smoothing window'):
         nat.condense_host(ctx, np.zeros((25, 2)), [[0, 1]])
+
+
+def test_normalisation_types_vs_reference(nat):
+    """zmad and mode against the reference's own outputs; ctrl_guides against the oracle (bit-exact inputs:
+    the fixtures' counts are integers, so log2 comes from the host table)."""
+    from oracle import jacks_oracle as O
+    z = load_golden('sd_model.npz')
+    ctx = nat.context(0)
+    for tag in ['n300r2', 'n4000r3', 'n9000r2', 'n100r4']:
+        counts = z[tag + '.counts'].astype(np.float64)
+        for nt in ('zmad', 'mode'):
+            got = nat.normalize_host(ctx, counts, nt, take_log=True, prior=32.0)
+            assert np.abs(got - z[tag + '.norm_' + nt]).max() < 1e-12, (tag, nt)
+        lc = np.log2(counts + 32.0)
+        got = nat.normalize_host(ctx, lc, 'mode')                       # already-logged input, no table
+        assert np.abs(got - z[tag + '.norm_mode']).max() < 1e-12, tag
+        rows = list(range(0, counts.shape[0], 7))
+        mask = np.zeros(counts.shape[0], dtype=np.uint8); mask[rows] = 1
+        got = nat.normalize_host(ctx, counts, 'ctrl_guides', take_log=True, prior=32.0, row_mask=mask)
+        assert np.abs(got - O.normalize_log_counts(lc, 'ctrl_guides', rows)).max() < 1e-13, tag
+
+
+def test_posterior_sd_subset_vs_reference(nat):
+    """calc_posterior_sd(guideset_indexs=...) -- the fit inferMissingVariances uses for single-replicate samples."""
+    from jacks_b200 import preprocess
+    z = load_golden('sd_model.npz')
+    for tag in ['n300r2', 'n4000r3', 'n9000r2', 'n100r4']:
+        norm = z[tag + '.norm_median']
+        got = preprocess.calc_posterior_sd(norm.copy(), guideset_indexs=z[tag + '.subset'].tolist())
+        ref = z[tag + '.sd_subset']
+        err = np.abs(got - ref) / np.maximum(np.abs(ref), 1e-300)
+        assert err.max() < 1e-9, (tag, err.max())
+        got = preprocess.calc_posterior_sd(norm.copy())
+        err = np.abs(got - z[tag + '.sd']) / np.abs(z[tag + '.sd'])
+        assert err.max() < 1e-9, tag
+
+
+def test_infer_missing_variances_single_replicate(nat):
+    """A single-replicate test sample with control genes: sd = 2 * posterior sd of (control mean, sample mean)
+    fitted on the control-gene guides (preprocess.py:98-119)."""
+    from jacks_b200 import preprocess
+    from oracle import jacks_oracle as O
+    rng = np.random.default_rng(21)
+    N = 1200
+    lc = rng.normal(0, 1.2, size=(N, 3))
+    data = nat.condense_host(nat.context(0), lc, [[0, 1], [2]])
+    assert np.isnan(data[:, 1, 1]).all()
+    meta = np.array([['g%04d' % i, 'GENE%03d' % (i // 4)] for i in range(N)])
+    ctrl_geneset = set('GENE%03d' % k for k in range(0, 300, 3))
+    out = preprocess.inferMissingVariances(data.copy(), meta, ['CTRL', 'S1'], {'CTRL': 'CTRL', 'S1': 'CTRL'}, ctrl_geneset)
+    sub = [i for i in range(N) if meta[i, 1] in ctrl_geneset]
+    ref = 2 * O.posterior_sd(np.stack([data[:, 0, 0], data[:, 1, 0]], axis=1), guideset_indexs=sub)
+    err = np.abs(out[:, 1, 1] - ref) / np.abs(ref)
+    assert err.max() < 1e-9, err.max()
+    assert np.array_equal(out[:, 0, :], data[:, 0, :])
