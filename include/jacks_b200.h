@@ -181,6 +181,19 @@ JACKS_API int jacks_kde_pvalues_host(JacksCtx* ctx, const double* w1_genes, int6
                            int32_t positive, double* pvals);
 
 /*
+ * General KDE evaluation for the branches of computeW1PvalsAndFDRs the command line does not reach
+ * (jacks_io.py:76-88, used by 2018_paper_materials/scripts/jacks/run_JACKS_single.py):
+ *   kind 0 / 1  cdf as jacks_kde_pvalues_* (negative / positive selection)
+ *   kind 2      density, scipy gaussian_kde.evaluate: sum_i exp(-z_i^2/2) / (n h sqrt(2 pi))  -- the two factors
+ *               of the local fdr kernel.evaluate(w)/k_all.evaluate(w) (jacks_io.py:88)
+ *   leave_one_out != 0: every w_eval[i, l] is itself a member of the null sample and is left out of the kernel
+ *               it is evaluated under (jacks_io.py:81-82): n-1 points, bandwidth recomputed without it.
+ * NaN null values are dropped (the reference does so for the shared kernels, jacks_io.py:76-78).
+ */
+JACKS_API int jacks_kde_eval_host(JacksCtx* ctx, const double* w_eval, int64_t n_eval, const double* w_null, int64_t n_null,
+                        int32_t n_lines, int32_t kind, int32_t leave_one_out, double* out);
+
+/*
  * Mean-variance error model for one or more samples (calc_posterior_sd, preprocess.py:25-58, as called from
  * condense_normalised_counts, preprocess.py:61-67).
  *   logcounts [n_guides, n_cols]   normalised log2 counts

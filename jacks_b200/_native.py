@@ -85,6 +85,7 @@ def lib():
         if hasattr(L, 'jacks_kde_pvalues_device'):
             L.jacks_kde_pvalues_device.argtypes = [vp, vp, i64, vp, i64, i32, i32, vp, vp]
             L.jacks_kde_pvalues_host.argtypes = [vp, vp, i64, vp, i64, i32, i32, vp]
+            L.jacks_kde_eval_host.argtypes = [vp, vp, i64, vp, i64, i32, i32, i32, vp]
         if hasattr(L, 'jacks_condense_host'):
             L.jacks_condense_host.argtypes = [vp, vp, i64, i32, vp, vp, i32, i32, i32, vp]
             L.jacks_normalize_host.argtypes = [vp, vp, i64, i32, i32, dbl, vp, i64, i32, vp, vp]
@@ -338,4 +339,14 @@ def posterior_sd_subset_host(ctx, data, in_set, window, monotonize=True):
     out = np.empty(data.shape[0], dtype=np.float64)
     check(lib().jacks_posterior_sd_subset_host(ctx.h, _ptr(data), data.shape[0], data.shape[1], _ptr(mask), int(window),
                                                int(bool(monotonize)), _ptr(out)))
+    return out
+
+
+def kde_eval_host(ctx, w_eval, w_null, kind='cdf_neg', leave_one_out=False):
+    """jacks_kde_eval_host: kind in {'cdf_neg', 'cdf_pos', 'pdf'}; w_eval [m, L], w_null [n, L] -> [m, L]."""
+    w_eval = np.ascontiguousarray(w_eval, dtype=np.float64)
+    w_null = np.ascontiguousarray(w_null, dtype=np.float64)
+    out = np.empty(w_eval.shape, dtype=np.float64)
+    check(lib().jacks_kde_eval_host(ctx.h, _ptr(w_eval), w_eval.shape[0], _ptr(w_null), w_null.shape[0], w_eval.shape[1],
+                                    {'cdf_neg': 0, 'cdf_pos': 1, 'pdf': 2}[kind], int(bool(leave_one_out)), _ptr(out)))
     return out

@@ -42,7 +42,7 @@ __device__ __forceinline__ double block_sum(double v, double* sh) {
     return s;
 }
 
-// stats[l*4 + 0] = h, +1 = n (as double), +2 = gene-independent term, +3 = 1/n
+// stats[l*8 + 0] = h, +1 = n (as double), +2 = gene-independent term, +3 = 1/n, +4 = mean, +5 = sum of squared deviations
 __global__ void __launch_bounds__(kStatsThreads) kde_line_stats(const double* __restrict__ w1_pseudo, long long n_pseudo,
                                                                 int L, long long ld, int positive,
                                                                 double* __restrict__ sT, double* __restrict__ stats) {
@@ -85,10 +85,12 @@ __global__ void __launch_bounds__(kStatsThreads) kde_line_stats(const double* __
     for (int i = threadIdx.x; i < n; i += kStatsThreads) c += normcdf(sgn * (edge - row[i]) / h);
     c = block_sum(c, sh);
     if (threadIdx.x == 0) {
-        stats[l * 4 + 0] = h;
-        stats[l * 4 + 1] = (double)n;
-        stats[l * 4 + 2] = c;
-        stats[l * 4 + 3] = wgt;
+        stats[l * 8 + 0] = h;
+        stats[l * 8 + 1] = (double)n;
+        stats[l * 8 + 2] = c;
+        stats[l * 8 + 3] = wgt;
+        stats[l * 8 + 4] = mean;
+        stats[l * 8 + 5] = ss;
     }
 }
 
@@ -98,10 +100,10 @@ __global__ void __launch_bounds__(kPvThreads) kde_pvalues(const double* __restri
                                                           double* __restrict__ pvals) {
     __shared__ double chunk[kChunk];
     const int l = blockIdx.y;
-    const double h = stats[l * 4 + 0];
-    const int n = (int)stats[l * 4 + 1];
-    const double cterm = stats[l * 4 + 2];
-    const double wgt = stats[l * 4 + 3];
+    const double h = stats[l * 8 + 0];
+    const int n = (int)stats[l * 8 + 1];
+    const double cterm = stats[l * 8 + 2];
+    const double wgt = stats[l * 8 + 3];
     const double rh = (positive ? -1.0 : 1.0) / h;     // signed: positive selection sums Phi(-(w-s)/h)
     const long long g0 = ((long long)blockIdx.x * kPvThreads + threadIdx.x) * kGT;
     double w[kGT], acc[kGT];
@@ -134,6 +136,65 @@ __global__ void __launch_bounds__(kPvThreads) kde_pvalues(const double* __restri
     }
 }
 
+// General KDE evaluation for the branches the command line does not reach (jacks_io.py:76-88):
+//   kind 0/1: cdf as in kde_pvalues;  kind 2: density  sum_i exp(-z^2/2) / (n h sqrt(2 pi))  (kernel.evaluate)
+//   loo != 0: every evaluated value is itself one of the null points and is left out of its own kernel
+//   (jacks_io.py:81-82): n' = n-1, the bandwidth comes from the downdated mean / variance, the point's own term
+//   (Phi(0) = 1/2, or exp(0) = 1) is subtracted, and the gene-independent cdf term is re-evaluated per gene.
+__global__ void __launch_bounds__(kPvThreads) kde_eval_kernel(const double* __restrict__ w_eval, long long m, int L,
+                                                              const double* __restrict__ sT, long long ld,
+                                                              const double* __restrict__ stats, int kind, int loo,
+                                                              double* __restrict__ out) {
+    __shared__ double chunk[kChunk];
+    const int l = blockIdx.y;
+    const int n = (int)stats[l * 8 + 1];
+    const double mean = stats[l * 8 + 4], ss = stats[l * 8 + 5];
+    const long long g = (long long)blockIdx.x * kPvThreads + threadIdx.x;
+    const double w = (g < m) ? w_eval[g * L + l] : 0.0;
+    double h = stats[l * 8 + 0];
+    double cnt = (double)n;
+    if (loo) {
+        // remove the point w from (n, mean, ss): ss' = ss - (w-mean)^2 * n/(n-1)
+        cnt = (double)(n - 1);
+        const double d = w - mean;
+        const double ss1 = ss - d * d * (double)n / cnt;
+        const double wg = 1.0 / cnt;
+        const double cov = (ss1 * wg) / (1.0 - wg);
+        const double f = pow(cnt, -0.2);
+        h = sqrt(cov * f * f);
+    }
+    const double sgn = (kind == 1) ? -1.0 : 1.0;
+    const double rh = sgn / h;
+    const double edge = (kind == 1) ? 100.0 : -100.0;
+    double acc = 0.0, cacc = 0.0;
+    const double* row = sT + (long long)l * ld;
+    for (int base = 0; base < n; base += kChunk) {
+        __syncthreads();
+        for (int i = threadIdx.x; i < kChunk; i += kPvThreads) chunk[i] = row[base + i];
+        __syncthreads();
+        const int mm = min(kChunk, n - base);
+        if (kind == 2) {
+            for (int i = 0; i < mm; ++i) { const double z = (w - chunk[i]) * rh; acc += exp(-0.5 * z * z); }
+        } else {
+            for (int i = 0; i < mm; ++i) {
+                acc += normcdf((w - chunk[i]) * rh);
+                cacc += normcdf((edge - chunk[i]) * rh);
+            }
+        }
+    }
+    if (g < m) {
+        double v;
+        if (kind == 2) {
+            if (loo) acc -= 1.0;
+            v = acc / (cnt * h * 2.5066282746310002);          // sqrt(2 pi)
+        } else {
+            if (loo) { acc -= 0.5; cacc -= normcdf((edge - w) * rh); }
+            v = (acc - cacc) / cnt;
+        }
+        out[g * L + l] = v;
+    }
+}
+
 }  // namespace
 }  // namespace jacks
 
@@ -148,7 +209,7 @@ extern "C" int jacks_kde_pvalues_device(JacksCtx* ctx, const double* w1_genes, i
     if (e != cudaSuccess) return cuda_fail(e, "cudaSetDevice");
     cudaStream_t st = (cudaStream_t)stream;
     const long long ld = ((long long)n_pseudo + kChunk - 1) / kChunk * kChunk;
-    const size_t bytes = (size_t)ld * n_lines * sizeof(double) + (size_t)n_lines * 4 * sizeof(double);
+    const size_t bytes = (size_t)ld * n_lines * sizeof(double) + (size_t)n_lines * 8 * sizeof(double);
     int rc = ctx->tmp.reserve(bytes);
     if (rc != JACKS_OK) return rc;
     double* sT = (double*)ctx->tmp.p;
@@ -182,6 +243,37 @@ extern "C" int jacks_kde_pvalues_host(JacksCtx* ctx, const double* w1_genes, int
                                   n_lines, positive, (double*)ctx->out[2].p, st);
     if (rc != JACKS_OK) return rc;
     if ((e = cudaMemcpyAsync(pvals, ctx->out[2].p, gb, cudaMemcpyDeviceToHost, st)) != cudaSuccess) return cuda_fail(e, "D2H pvals");
+    if ((e = cudaStreamSynchronize(st)) != cudaSuccess) return cuda_fail(e, "kde kernels");
+    return JACKS_OK;
+}
+
+extern "C" int jacks_kde_eval_host(JacksCtx* ctx, const double* w_eval, int64_t n_eval, const double* w_null, int64_t n_null,
+                                   int32_t n_lines, int32_t kind, int32_t leave_one_out, double* out) {
+    if (!ctx || !out || (n_eval > 0 && !w_eval) || !w_null) return fail(JACKS_E_INVALID, "jacks_kde_eval_host: NULL argument");
+    if (n_eval < 0 || n_null < (leave_one_out ? 3 : 2) || n_lines < 1) return fail(JACKS_E_INVALID, "too few null points (%lld)", (long long)n_null);
+    if (kind < 0 || kind > 2) return fail(JACKS_E_INVALID, "kind must be 0 (cdf, negative), 1 (cdf, positive) or 2 (density)");
+    if (n_eval == 0) return JACKS_OK;
+    cudaError_t e = cudaSetDevice(ctx->device);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaSetDevice");
+    const size_t gb = (size_t)n_eval * n_lines * sizeof(double), pb = (size_t)n_null * n_lines * sizeof(double);
+    int rc;
+    if ((rc = ctx->out[0].reserve(gb)) != JACKS_OK) return rc;
+    if ((rc = ctx->out[1].reserve(pb)) != JACKS_OK) return rc;
+    if ((rc = ctx->out[2].reserve(gb)) != JACKS_OK) return rc;
+    const long long ld = ((long long)n_null + kChunk - 1) / kChunk * kChunk;
+    if ((rc = ctx->tmp.reserve((size_t)ld * n_lines * sizeof(double) + (size_t)n_lines * 8 * sizeof(double))) != JACKS_OK) return rc;
+    cudaStream_t st = ctx->stream;
+    if ((e = cudaMemcpyAsync(ctx->out[0].p, w_eval, gb, cudaMemcpyHostToDevice, st)) != cudaSuccess) return cuda_fail(e, "H2D w_eval");
+    if ((e = cudaMemcpyAsync(ctx->out[1].p, w_null, pb, cudaMemcpyHostToDevice, st)) != cudaSuccess) return cuda_fail(e, "H2D w_null");
+    double* sT = (double*)ctx->tmp.p;
+    double* stats = sT + ld * n_lines;
+    kde_line_stats<<<n_lines, kStatsThreads, 0, st>>>((const double*)ctx->out[1].p, n_null, n_lines, ld, kind == 1 ? 1 : 0, sT, stats);
+    dim3 grid((unsigned)((n_eval + kPvThreads - 1) / kPvThreads), (unsigned)n_lines);
+    kde_eval_kernel<<<grid, kPvThreads, 0, st>>>((const double*)ctx->out[0].p, n_eval, n_lines, sT, ld, stats, kind,
+                                                 leave_one_out ? 1 : 0, (double*)ctx->out[2].p);
+    ctx->launches += 2;
+    if ((e = cudaGetLastError()) != cudaSuccess) return cuda_fail(e, "kde_eval launch");
+    if ((e = cudaMemcpyAsync(out, ctx->out[2].p, gb, cudaMemcpyDeviceToHost, st)) != cudaSuccess) return cuda_fail(e, "D2H kde");
     if ((e = cudaStreamSynchronize(st)) != cudaSuccess) return cuda_fail(e, "kde kernels");
     return JACKS_OK;
 }

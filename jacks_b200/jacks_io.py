@@ -69,20 +69,30 @@ def computeW1PvalsAndFDRs(jacks_results, test_sample_ids, noness_genes=set(), ps
     """P-value of every gene's w1, per cell line, under the Gaussian-KDE null built from the w1 of the
     ``noness_genes`` (jacks_io.py:69-89).  Returns ({gene: pvals[L]}, {gene: fdrs[L]}).
 
-    The KDE sums run on the GPU (jacks_kde_pvalues_host).  Only the pseudo=True, compute_fdr=False branch --
-    the one ``writeJacksWResults`` reaches from the command line -- is available."""
-    if not pseudo or compute_fdr:
-        raise NotImplementedError('computeW1PvalsAndFDRs: only pseudo=True, compute_fdr=False runs on the GPU path '
-                                  '(leave-one-out control kernels and the local fdr are not implemented)')
+    All KDE sums run on the GPU.  pseudo=True (the command-line path): one shared kernel per line
+    (jacks_kde_pvalues_host).  pseudo=False: the control genes themselves are scored under a kernel that leaves
+    them out (jacks_kde_eval_host, leave_one_out).  compute_fdr: local fdr = density under the null kernel /
+    density under the kernel of all genes (jacks_io.py:76-77,88)."""
     genes = [g for g in jacks_results]
     L = len(test_sample_ids)
     w1_fdrs = {gene: np.zeros(L) for gene in genes}
     if len(genes) == 0:
         return {}, w1_fdrs
+    ctx = _native.context(0)
     w1_all = np.stack([np.asarray(jacks_results[g][4], dtype=np.float64) for g in genes])
     null_rows = [i for i, g in enumerate(genes) if g in noness_genes]
-    pv = _native.kde_pvalues_host(_native.context(0), w1_all, w1_all[null_rows], positive=positive)
+    w1_null = w1_all[null_rows]
+    pv = _native.kde_pvalues_host(ctx, w1_all, w1_null, positive=positive)
+    if not pseudo and null_rows:
+        pv[null_rows] = _native.kde_eval_host(ctx, w1_null, w1_null, 'cdf_pos' if positive else 'cdf_neg', leave_one_out=True)
     w1_pvals = {gene: pv[i] for i, gene in enumerate(genes)}
+    if compute_fdr:
+        dens_null = _native.kde_eval_host(ctx, w1_all, w1_null, 'pdf')
+        if not pseudo and null_rows:
+            dens_null[null_rows] = _native.kde_eval_host(ctx, w1_null, w1_null, 'pdf', leave_one_out=True)
+        dens_all = _native.kde_eval_host(ctx, w1_all, w1_all, 'pdf')
+        fdr = dens_null / dens_all
+        w1_fdrs = {gene: fdr[i] for i, gene in enumerate(genes)}
     return w1_pvals, w1_fdrs
 
 

@@ -291,11 +291,20 @@ def pvals(gene_index, res):
     pv_neg, _ = RIO.computeW1PvalsAndFDRs(results, lines, noness_genes=pset, pseudo=True, positive=False)
     pv_pos, _ = RIO.computeW1PvalsAndFDRs(results, lines, noness_genes=pset, pseudo=True, positive=True)
     order = list(results)
+    # branches the CLI does not reach: leave-one-out kernels for the control genes (pseudo=False) and the local fdr
+    noness = set('GENE%03d' % i for i in range(0, 40, 2))
+    real = {g: results[g] for g in results if g.startswith('GENE')}
+    pv_loo, fdr_loo = RIO.computeW1PvalsAndFDRs(real, lines, noness_genes=noness, pseudo=False, compute_fdr=True)
+    pv_loo_pos, _ = RIO.computeW1PvalsAndFDRs(real, lines, noness_genes=noness, pseudo=False, positive=True)
+    finite = {g: results[g] for g in results if not np.isnan(results[g][4]).any()}     # scipy's evaluate() rejects NaN points
+    _, fdr_pseudo = RIO.computeW1PvalsAndFDRs(finite, lines, noness_genes=pset, pseudo=True, compute_fdr=True)
     fdr_sets = RIO.getFDRGeneSets(pv_neg, 0.2)
     save('pvals.npz', seed=np.int64(1234), ctrl_sorted=np.array(neg), pseudo_offsets=offs, pseudo_rows=prow,
          pseudo_w1=pseudo_w1, gene_w1=gene_w1,
          pv_neg=np.stack([pv_neg[g] for g in order]), pv_pos=np.stack([pv_pos[g] for g in order]),
-         order=np.array(order),
+         order=np.array(order), real_order=np.array(list(real)), loo_noness=np.array(sorted(noness)),
+         pv_loo=np.stack([pv_loo[g] for g in real]), pv_loo_pos=np.stack([pv_loo_pos[g] for g in real]),
+         fdr_loo=np.stack([fdr_loo[g] for g in real]), fdr_pseudo=np.stack([fdr_pseudo[g] for g in finite]), finite_order=np.array(list(finite)),
          fdr_sets=np.array(['|'.join(sorted(s)) for s in fdr_sets]))
 
 

@@ -116,9 +116,7 @@ def test_writers_format_and_filtering(tmp_path):
     assert open(prefix + '_lfcs.txt').read() == 'gRNA\tgene\tS\na\tG1\t5.000000e+00\nb\tG1\t1.000000e+00\n'
 
 
-def test_unavailable_branches_raise_instead_of_computing_on_the_host():
-    with pytest.raises(NotImplementedError):
-        jacks_io.computeW1PvalsAndFDRs({'g': (None,) * 4 + (np.zeros(2), None)}, ['a', 'b'], pseudo=False)
+def test_bad_arguments_raise_before_touching_the_gpu():
     from jacks_b200 import preprocess
     with pytest.raises(Exception, match='Unrecognised normalisation type'):
         preprocess.normalizeLogCounts(np.zeros((40, 2)), normtype='bogus')

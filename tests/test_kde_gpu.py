@@ -71,3 +71,33 @@ def test_pvalue_properties_full_size(nat):
     pick = np.array([0, 17, 4000, 9000, 12000, 15000, 17990, 17999])
     ref = O.kde_pvalues(genes[pick], pseudo, positive=False)
     assert rel_close(neg[pick], ref, 1e-10) < 1e-10
+
+
+def test_leave_one_out_and_local_fdr_vs_reference(nat):
+    """computeW1PvalsAndFDRs with pseudo=False (control genes scored under a kernel that leaves them out) and
+    compute_fdr=True (density ratio), against the reference's own numbers."""
+    from jacks_b200 import jacks_io
+    z = load_golden('pvals.npz')
+    lines = ['L0', 'L1', 'L2']
+    names = [str(g) for g in z['real_order']]
+    gene_w1 = z['gene_w1']
+    real = {g: (None, None, None, None, gene_w1[i], gene_w1[i] ** 2) for i, g in enumerate(names)}
+    noness = set(str(g) for g in z['loo_noness'])
+    pv, fdr = jacks_io.computeW1PvalsAndFDRs(real, lines, noness_genes=noness, pseudo=False, compute_fdr=True)
+    got_pv = np.stack([pv[g] for g in names]); got_fdr = np.stack([fdr[g] for g in names])
+    assert rel_close(got_pv, z['pv_loo'], 1e-9) < 1e-9
+    ok = np.isclose(got_fdr, z['fdr_loo'], rtol=1e-9, atol=0) | (np.isnan(got_fdr) & np.isnan(z['fdr_loo']))
+    assert ok.all(), np.argwhere(~ok)[:5]
+    pv_pos, _ = jacks_io.computeW1PvalsAndFDRs(real, lines, noness_genes=noness, pseudo=False, positive=True)
+    assert rel_close(np.stack([pv_pos[g] for g in names]), z['pv_loo_pos'], 1e-9, atol=1e-15) < 1e-9
+    # pseudo=True with the local fdr
+    order = [str(g) for g in z['finite_order']]
+    all_names = [str(g) for g in z['order']]
+    all_w1 = np.concatenate([z['pseudo_w1'], gene_w1])
+    results = {g: (None, None, None, None, all_w1[all_names.index(g)], None) for g in order}
+    pset = set(g for g in order if 'JACKS_PSEUDO_GENE' in g)
+    _, fdr = jacks_io.computeW1PvalsAndFDRs(results, lines, noness_genes=pset, pseudo=True, compute_fdr=True)
+    got = np.stack([fdr[g] for g in order])
+    ok = np.isclose(got, z['fdr_pseudo'], rtol=1e-9, atol=0) | (np.isnan(got) & np.isnan(z['fdr_pseudo'])) | \
+        ((got == 0) & (z['fdr_pseudo'] == 0))
+    assert ok.all(), np.argwhere(~ok)[:5]
