@@ -18,6 +18,7 @@
 //                    LDS feeds GT independent normcdf chains).
 #include <cuda_runtime.h>
 #include <math.h>
+#include <stdlib.h>
 
 #include "../../include/jacks_b200.h"
 #include "capi_internal.h"
@@ -48,6 +49,9 @@ __global__ void __launch_bounds__(kStatsThreads) kde_line_stats(const double* __
                                                                 double* __restrict__ sT, double* __restrict__ stats) {
     __shared__ double sh[kStatsThreads / 32];
     __shared__ int s_base;
+    // Positive selection is computed as negative selection of the mirrored problem (s -> -s, w -> -w):
+    // Phi((100-s)/h) - Phi((w-s)/h) = Phi((-w+s)/h) - Phi((-100+s)/h), which also avoids the 1 - Phi cancellation.
+    const double sgn = positive ? -1.0 : 1.0;
     const int l = blockIdx.x;
     double* row = sT + (long long)l * ld;
     // compaction, order preserving within a block pass (order does not matter for the sum)
@@ -64,7 +68,7 @@ __global__ void __launch_bounds__(kStatsThreads) kde_line_stats(const double* __
         int wbase = 0;
         if (lane == 0) wbase = atomicAdd(&s_base, __popc(m));
         wbase = __shfl_sync(0xffffffffu, wbase, 0);
-        if (ok) { row[wbase + __popc(m & ((1u << lane) - 1))] = v; sum += v; }
+        if (ok) { v *= sgn; row[wbase + __popc(m & ((1u << lane) - 1))] = v; sum += v; }
     }
     __syncthreads();
     const int n = s_base;
@@ -78,11 +82,8 @@ __global__ void __launch_bounds__(kStatsThreads) kde_line_stats(const double* __
     const double cov = (ss * wgt) / (1.0 - wgt);
     const double factor = pow((double)n, -0.2);
     const double h = sqrt(cov * factor * factor);
-    const double edge = positive ? 100.0 : -100.0;
     double c = 0.0;
-    // positive selection is evaluated as the upper tail Phi(-z) (no 1 - Phi cancellation)
-    const double sgn = positive ? -1.0 : 1.0;
-    for (int i = threadIdx.x; i < n; i += kStatsThreads) c += normcdf(sgn * (edge - row[i]) / h);
+    for (int i = threadIdx.x; i < n; i += kStatsThreads) c += normcdf((-100.0 - row[i]) / h);
     c = block_sum(c, sh);
     if (threadIdx.x == 0) {
         stats[l * 8 + 0] = h;
@@ -97,20 +98,22 @@ __global__ void __launch_bounds__(kStatsThreads) kde_line_stats(const double* __
 __global__ void __launch_bounds__(kPvThreads) kde_pvalues(const double* __restrict__ w1_genes, long long n_genes, int L,
                                                           const double* __restrict__ sT, long long ld,
                                                           const double* __restrict__ stats, int positive,
-                                                          double* __restrict__ pvals) {
+                                                          const long long* __restrict__ cell_off, double* __restrict__ pvals) {
     __shared__ double chunk[kChunk];
     const int l = blockIdx.y;
+    if (cell_off && cell_off[l + 1] > cell_off[l]) return;        // this line was done by the fast path
     const double h = stats[l * 8 + 0];
     const int n = (int)stats[l * 8 + 1];
     const double cterm = stats[l * 8 + 2];
     const double wgt = stats[l * 8 + 3];
-    const double rh = (positive ? -1.0 : 1.0) / h;     // signed: positive selection sums Phi(-(w-s)/h)
+    const double rh = 1.0 / h;
+    const double sgn = positive ? -1.0 : 1.0;          // mirrored problem for positive selection (see kde_line_stats)
     const long long g0 = ((long long)blockIdx.x * kPvThreads + threadIdx.x) * kGT;
     double w[kGT], acc[kGT];
 #pragma unroll
     for (int k = 0; k < kGT; ++k) {
         const long long g = g0 + k;
-        w[k] = (g < n_genes) ? w1_genes[g * L + l] : 0.0;
+        w[k] = (g < n_genes) ? sgn * w1_genes[g * L + l] : 0.0;
         acc[k] = 0.0;
     }
     const double* row = sT + (long long)l * ld;
@@ -136,6 +139,177 @@ __global__ void __launch_bounds__(kPvThreads) kde_pvalues(const double* __restri
     }
 }
 
+// ---- fast path: sorted null values, cells of width h/4, truncated Taylor (Hermite) expansion per cell -------
+// F(w) = sum_i Phi((w - s_i)/h).  Sort the null values of a line; cut the axis into cells of width delta = h/4
+// with centres c_j; a point of cell j is s_i = c_j + h*u_i, |u_i| <= 1/8.  With z = (w - c_j)/h
+//     sum_{i in j} Phi(z - u_i) = m_0 Phi(z) - phi(z) * sum_{k=1..K} He_{k-1}(z) M_k,    M_k = sum_i u_i^k / k!
+// (Taylor in u; Phi^(k) = (-1)^(k-1) He_{k-1} phi).  Cells whose points all have z >= 8.3 contribute their count
+// (Phi = 1 in double), cells below z_lo = -sqrt(min(z_max,0)^2 + 2 ln(1e16 n)) cannot change the sum at 1e-16
+// relative, and when even the nearest point has z_max < -7.5 the few contributing points are summed directly.
+// K = 16 keeps the truncation below 1e-14 relative for every |z| in the window (numpy prototype: 5e-15 worst case
+// over bulk, tails and edges at n = 2e3 and 1e5).  Work per p-value drops from n normal CDFs to ~45 cells.
+constexpr int kK = 16;                  // expansion order
+constexpr int kCellRec = kK + 2;        // doubles per cell: M_0..M_K, index of the cell's first point
+constexpr double kCellWidth = 0.25;     // in units of h
+constexpr int kSortTileD = 4096;
+
+__global__ void __launch_bounds__(1024) sort_rows_local(double* __restrict__ rows, long long ld, int k_lo, int k_hi) {
+    __shared__ double sm[kSortTileD];
+    const long long base = (long long)blockIdx.y * ld + (long long)blockIdx.x * kSortTileD;
+    for (int t = threadIdx.x; t < kSortTileD; t += blockDim.x) sm[t] = rows[base + t];
+    __syncthreads();
+    const long long tile0 = (long long)blockIdx.x * kSortTileD;
+    for (long long kk = k_lo; kk <= k_hi; kk <<= 1) {
+        for (int j = (int)((kk >> 1) < kSortTileD ? (kk >> 1) : (kSortTileD >> 1)); j > 0; j >>= 1) {
+            for (int t = threadIdx.x; t < kSortTileD / 2; t += blockDim.x) {
+                const int a = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+                const int b = a | j;
+                const bool up = (((tile0 + a) & kk) == 0);
+                const double va = sm[a], vb = sm[b];
+                if ((vb < va) == up) { sm[a] = vb; sm[b] = va; }
+            }
+            __syncthreads();
+        }
+    }
+    for (int t = threadIdx.x; t < kSortTileD; t += blockDim.x) rows[base + t] = sm[t];
+}
+
+__global__ void __launch_bounds__(256) sort_rows_global(double* __restrict__ rows, long long ld, long long kk, long long j) {
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= ld / 2) return;
+    double* r = rows + (long long)blockIdx.y * ld;
+    const long long a = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+    const long long b = a | j;
+    const bool up = ((a & kk) == 0);
+    const double va = r[a], vb = r[b];
+    if ((vb < va) == up) { r[a] = vb; r[b] = va; }
+}
+
+// cell_off[l] .. cell_off[l+1]: cells of line l in the cell table; a line whose cells do not fit is marked
+// (cell_off[l+1] == cell_off[l]) and evaluated by the brute-force kernel.  One thread, L is small.
+__global__ void kde_cell_layout(const double* __restrict__ sT, long long ld, const double* __restrict__ stats, int L,
+                                long long cell_cap, long long* __restrict__ cell_off) {
+    if (blockIdx.x != 0 || threadIdx.x != 0) return;
+    long long off = 0;
+    cell_off[0] = 0;
+    for (int l = 0; l < L; ++l) {
+        const double h = stats[l * 8 + 0];
+        const int n = (int)stats[l * 8 + 1];
+        long long nc = 0;
+        if (n >= 2 && h > 0.0 && h == h) {
+            const double* row = sT + (long long)l * ld;
+            const double span = (row[n - 1] - row[0]) / (h * kCellWidth);
+            if (span == span && span < 1.0e7) nc = (long long)floor(span) + 1;
+        }
+        if (nc > 0 && off + nc <= cell_cap) off += nc;        // else: no cells -> brute force for this line
+        cell_off[l + 1] = off;
+    }
+}
+
+__device__ __forceinline__ long long kde_cell_of(double s, double smin, double inv_delta, long long nc) {
+    long long j = (long long)floor((s - smin) * inv_delta);
+    return j < 0 ? 0 : (j >= nc ? nc - 1 : j);
+}
+
+// One thread per cell: moments of the cell's points (sorted row => the points are a contiguous run).
+__global__ void __launch_bounds__(128) kde_cell_moments(const double* __restrict__ sT, long long ld,
+                                                        const double* __restrict__ stats, int L,
+                                                        const long long* __restrict__ cell_off, double* __restrict__ cells) {
+    const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= cell_off[L]) return;
+    int lo_l = 0, hi_l = L;                       // line of this cell: cell_off[l] <= c < cell_off[l+1]
+    while (hi_l - lo_l > 1) { const int mid = (lo_l + hi_l) >> 1; if (cell_off[mid] <= c) lo_l = mid; else hi_l = mid; }
+    const int l = lo_l;
+    const long long j = c - cell_off[l], nc = cell_off[l + 1] - cell_off[l];
+    const double h = stats[l * 8 + 0];
+    const int n = (int)stats[l * 8 + 1];
+    const double* row = sT + (long long)l * ld;
+    const double smin = row[0];
+    const double inv_delta = 1.0 / (h * kCellWidth);
+    // first point with cell index >= j, first point with cell index > j (cell index is monotone along the row)
+    int a = 0, b = n;
+    while (a < b) { const int mid = (a + b) >> 1; if (kde_cell_of(row[mid], smin, inv_delta, nc) < j) a = mid + 1; else b = mid; }
+    const int first = a;
+    b = n;
+    while (a < b) { const int mid = (a + b) >> 1; if (kde_cell_of(row[mid], smin, inv_delta, nc) <= j) a = mid + 1; else b = mid; }
+    const int last = a;
+    const double centre = smin + ((double)j + 0.5) * (h * kCellWidth);
+    const double rh = 1.0 / h;
+    double M[kK + 1];
+#pragma unroll
+    for (int k = 0; k <= kK; ++k) M[k] = 0.0;
+    for (int i = first; i < last; ++i) {
+        const double u = (row[i] - centre) * rh;
+        double t = 1.0;
+        M[0] += 1.0;
+#pragma unroll
+        for (int k = 1; k <= kK; ++k) { t *= u * (1.0 / k); M[k] += t; }       // u^k / k!
+    }
+    double* rec = cells + c * kCellRec;
+#pragma unroll
+    for (int k = 0; k <= kK; ++k) rec[k] = M[k];
+    rec[kK + 1] = (double)first;
+}
+
+__global__ void __launch_bounds__(128) kde_pvalues_fast(const double* __restrict__ w1_genes, long long n_genes, int L,
+                                                        const double* __restrict__ sT, long long ld,
+                                                        const double* __restrict__ stats, const long long* __restrict__ cell_off,
+                                                        const double* __restrict__ cells, int positive,
+                                                        double* __restrict__ pvals) {
+    const int l = blockIdx.y;
+    const long long nc = cell_off[l + 1] - cell_off[l];
+    if (nc == 0) return;                                   // this line is left to the brute-force kernel
+    const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= n_genes) return;
+    const double h = stats[l * 8 + 0];
+    const int n = (int)stats[l * 8 + 1];
+    const double cterm = stats[l * 8 + 2], wgt = stats[l * 8 + 3];
+    const double* row = sT + (long long)l * ld;
+    const double* ctab = cells + cell_off[l] * kCellRec;
+    const double w = positive ? -w1_genes[g * L + l] : w1_genes[g * L + l];
+    if (!(w == w)) { pvals[g * L + l] = w; return; }
+    const double rh = 1.0 / h;
+    const double smin = row[0];
+    const double zmax = (w - smin) * rh;
+    double tot = 0.0;
+    if (zmax < -7.5) {
+        // far below every null value: only the nearest few points contribute
+        for (int i = 0; i < n; ++i) {
+            const double term = normcdf((w - row[i]) * rh);
+            tot += term;
+            if (term <= 1e-18 * tot) break;          // also stops at the first exact zero (z < -38.5): later points are farther
+        }
+    } else {
+        const double zneg = fmin(zmax, 0.0);
+        const double zlo = -sqrt(zneg * zneg + 2.0 * log(1e16 * (double)n));
+        const double delta = h * kCellWidth;
+        // z_j = (w - centre_j)/h = zmax - (j + 0.5)*kCellWidth decreases with j
+        // saturated: z_j - kCellWidth/2 >= 8.3  <=>  j <= (zmax - 8.3)/kCellWidth - 1
+        long long jsat = (long long)floor((zmax - 8.3) / kCellWidth) - 1;
+        if (jsat >= nc) jsat = nc - 1;
+        if (jsat >= 0) tot = (jsat + 1 < nc) ? ctab[(jsat + 1) * kCellRec + kK + 1] : (double)n;    // points before cell jsat+1
+        long long jend = (long long)ceil((zmax - zlo) / kCellWidth);                                 // z_j + w/2 >= zlo
+        if (jend >= nc) jend = nc - 1;
+        (void)delta;
+        for (long long j = (jsat < 0 ? 0 : jsat + 1); j <= jend; ++j) {
+            const double* rec = ctab + j * kCellRec;
+            const double m0 = rec[0];
+            if (m0 == 0.0) continue;
+            const double z = zmax - ((double)j + 0.5) * kCellWidth;
+            double he_prev = 0.0, he = 1.0, S = 0.0;
+#pragma unroll
+            for (int k = 1; k <= kK; ++k) {
+                S = fma(he, rec[k], S);
+                const double nxt = fma(z, he, -(double)(k - 1) * he_prev);
+                he_prev = he; he = nxt;
+            }
+            const double phi = exp(-0.5 * z * z) * 0.3989422804014327;
+            tot += m0 * normcdf(z) - phi * S;
+        }
+    }
+    pvals[g * L + l] = (tot - cterm) * wgt;
+}
+
 // General KDE evaluation for the branches the command line does not reach (jacks_io.py:76-88):
 //   kind 0/1: cdf as in kde_pvalues;  kind 2: density  sum_i exp(-z^2/2) / (n h sqrt(2 pi))  (kernel.evaluate)
 //   loo != 0: every evaluated value is itself one of the null points and is left out of its own kernel
@@ -150,7 +324,7 @@ __global__ void __launch_bounds__(kPvThreads) kde_eval_kernel(const double* __re
     const int n = (int)stats[l * 8 + 1];
     const double mean = stats[l * 8 + 4], ss = stats[l * 8 + 5];
     const long long g = (long long)blockIdx.x * kPvThreads + threadIdx.x;
-    const double w = (g < m) ? w_eval[g * L + l] : 0.0;
+    const double w = (g < m) ? ((kind == 1) ? -w_eval[g * L + l] : w_eval[g * L + l]) : 0.0;
     double h = stats[l * 8 + 0];
     double cnt = (double)n;
     if (loo) {
@@ -163,9 +337,8 @@ __global__ void __launch_bounds__(kPvThreads) kde_eval_kernel(const double* __re
         const double f = pow(cnt, -0.2);
         h = sqrt(cov * f * f);
     }
-    const double sgn = (kind == 1) ? -1.0 : 1.0;
-    const double rh = sgn / h;
-    const double edge = (kind == 1) ? 100.0 : -100.0;
+    const double rh = 1.0 / h;
+    const double edge = -100.0;
     double acc = 0.0, cacc = 0.0;
     const double* row = sT + (long long)l * ld;
     for (int base = 0; base < n; base += kChunk) {
@@ -208,19 +381,47 @@ extern "C" int jacks_kde_pvalues_device(JacksCtx* ctx, const double* w1_genes, i
     cudaError_t e = cudaSetDevice(ctx->device);
     if (e != cudaSuccess) return cuda_fail(e, "cudaSetDevice");
     cudaStream_t st = (cudaStream_t)stream;
-    const long long ld = ((long long)n_pseudo + kChunk - 1) / kChunk * kChunk;
-    const size_t bytes = (size_t)ld * n_lines * sizeof(double) + (size_t)n_lines * 8 * sizeof(double);
+    // rows padded to a power of two (>= one sort tile) so the bitonic network needs no bounds checks
+    long long ld = kSortTileD;
+    while (ld < n_pseudo) ld <<= 1;
+    const long long cell_cap = (long long)n_lines * 2048;
+    const size_t bytes = (size_t)ld * n_lines * sizeof(double) + (size_t)n_lines * 8 * sizeof(double) +
+                         (size_t)(n_lines + 1) * sizeof(long long) + (size_t)cell_cap * kCellRec * sizeof(double);
     int rc = ctx->tmp.reserve(bytes);
     if (rc != JACKS_OK) return rc;
     double* sT = (double*)ctx->tmp.p;
     double* stats = sT + ld * n_lines;
+    long long* cell_off = (long long*)(stats + (size_t)n_lines * 8);
+    double* cells = (double*)(cell_off + n_lines + 1);
+    const bool brute = getenv("JACKS_KDE_BRUTE") != nullptr;          // validation: force the O(n) sums
     kde_line_stats<<<n_lines, kStatsThreads, 0, st>>>(w1_pseudo, n_pseudo, n_lines, ld, positive ? 1 : 0, sT, stats);
-    if ((e = cudaGetLastError()) != cudaSuccess) return cuda_fail(e, "kde_line_stats launch");
+    ctx->launches++;
     const long long per_cta = (long long)kPvThreads * kGT;
     dim3 grid((unsigned)((n_genes + per_cta - 1) / per_cta), (unsigned)n_lines);
-    kde_pvalues<<<grid, kPvThreads, 0, st>>>(w1_genes, n_genes, n_lines, sT, ld, stats, positive ? 1 : 0, pvals);
-    if ((e = cudaGetLastError()) != cudaSuccess) return cuda_fail(e, "kde_pvalues launch");
-    ctx->launches += 2;
+    if (!brute) {
+        dim3 lg((unsigned)(ld / kSortTileD), (unsigned)n_lines);
+        sort_rows_local<<<lg, 1024, 0, st>>>(sT, ld, 2, kSortTileD);
+        ctx->launches++;
+        for (long long kk = 2LL * kSortTileD; kk <= ld; kk <<= 1) {
+            for (long long j = kk >> 1; j >= kSortTileD; j >>= 1) {
+                dim3 gg((unsigned)((ld / 2 + 255) / 256), (unsigned)n_lines);
+                sort_rows_global<<<gg, 256, 0, st>>>(sT, ld, kk, j);
+                ctx->launches++;
+            }
+            sort_rows_local<<<lg, 1024, 0, st>>>(sT, ld, (int)kk, (int)kk);
+            ctx->launches++;
+        }
+        kde_cell_layout<<<1, 1, 0, st>>>(sT, ld, stats, n_lines, cell_cap, cell_off);
+        kde_cell_moments<<<(unsigned)((cell_cap + 127) / 128), 128, 0, st>>>(sT, ld, stats, n_lines, cell_off, cells);
+        dim3 fg((unsigned)((n_genes + 127) / 128), (unsigned)n_lines);
+        kde_pvalues_fast<<<fg, 128, 0, st>>>(w1_genes, n_genes, n_lines, sT, ld, stats, cell_off, cells, positive ? 1 : 0, pvals);
+        ctx->launches += 3;
+    }
+    // lines the cell table could not hold (pathological ranges), or everything when forced
+    kde_pvalues<<<grid, kPvThreads, 0, st>>>(w1_genes, n_genes, n_lines, sT, ld, stats, positive ? 1 : 0,
+                                             brute ? nullptr : cell_off, pvals);
+    if ((e = cudaGetLastError()) != cudaSuccess) return cuda_fail(e, "kde kernels launch");
+    ctx->launches++;
     return JACKS_OK;
 }
 

@@ -101,3 +101,22 @@ def test_leave_one_out_and_local_fdr_vs_reference(nat):
     ok = np.isclose(got, z['fdr_pseudo'], rtol=1e-9, atol=0) | (np.isnan(got) & np.isnan(z['fdr_pseudo'])) | \
         ((got == 0) & (z['fdr_pseudo'] == 0))
     assert ok.all(), np.argwhere(~ok)[:5]
+
+
+def test_fast_path_matches_brute_force(nat, monkeypatch):
+    """The binned Hermite expansion against the O(n) normal-CDF sums of the same library (JACKS_KDE_BRUTE=1),
+    including far tails on both sides, outliers in the null sample and both selection directions."""
+    rng = np.random.default_rng(31)
+    L = 3
+    pseudo = rng.normal(0.0, 0.2, size=(30000, L))
+    pseudo[:4, 0] = [-3.0, 2.5, 9.0, -9.0]                       # outliers stretch the cell table
+    genes = np.concatenate([rng.normal(-0.3, 0.8, size=(4000, L)), np.linspace(-12, 12, 400)[:, None] * np.ones((1, L)),
+                            pseudo[:50] + 1e-9])
+    ctx = nat.context(0)
+    for positive in (False, True):
+        monkeypatch.delenv('JACKS_KDE_BRUTE', raising=False)
+        fast = nat.kde_pvalues_host(ctx, genes, pseudo, positive=positive)
+        monkeypatch.setenv('JACKS_KDE_BRUTE', '1')
+        brute = nat.kde_pvalues_host(ctx, genes, pseudo, positive=positive)
+        monkeypatch.delenv('JACKS_KDE_BRUTE', raising=False)
+        assert rel_close(fast, brute, 1e-11, atol=1e-300) < 1e-11
