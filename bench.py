@@ -180,6 +180,58 @@ def workload_config(args, world):
             'parallelism': 'gene-sharded data parallel, %d rank(s)' % world}
 
 
+def ncu_traffic():
+    """dram bytes (read + write) per launch of the EM kernel from the committed ncu capture, or None."""
+    try:
+        return json.load(open(os.path.join(REPO, 'profiles', 'ncu_traffic_r01.json')))['em_fast_kernel_118k_genes_bytes']
+    except Exception:
+        return None
+
+
+def aux_measurements(ctx, torch, dev, stream, L):
+    """The other two subsystems of the hot path at the BASELINE shape, device resident where the C-ABI has a device
+    entry point: KDE p-values (18,000 genes x L lines against 1e5 pseudo-genes) and the preprocessing error model
+    (72,000 guides x 802 replicate columns -> 401 samples; host entry points, copies included)."""
+    import ctypes as C
+    from jacks_b200 import _native
+    out = {}
+    g = torch.randn((N_GENES, L), dtype=torch.float64, device=dev) * 0.7 - 0.3
+    pz = torch.randn((N_PSEUDO, L), dtype=torch.float64, device=dev) * 0.2
+    pv = torch.empty_like(g)
+    lib = _native.lib()
+
+    def kde():
+        _native.check(lib.jacks_kde_pvalues_device(ctx.h, g.data_ptr(), N_GENES, pz.data_ptr(), N_PSEUDO, L, 0, pv.data_ptr(),
+                                                   C.c_void_p(stream or None)))
+    kde()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(3):
+        kde()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 3
+    out['kde_pvalues'] = {'value': N_GENES * L / (ms * 1e-3), 'unit': 'p-values/s', 'ms': ms,
+                          'shape': '%d genes x %d lines vs %d pseudo-genes, device resident' % (N_GENES, L, N_PSEUDO),
+                          'pairs_per_s': N_GENES * L * float(N_PSEUDO) / (ms * 1e-3)}
+    del g, pz, pv
+    rng = np.random.default_rng(2)
+    N, Cc = N_GENES * GUIDES, 2 * (L + 1)
+    counts = rng.poisson(300.0, size=(N, Cc)).astype(np.float64)
+    _native.normalize_host(ctx, counts[:4096], 'median', take_log=True, prior=32.0)
+    t0 = time.perf_counter()
+    lc = _native.normalize_host(ctx, counts, 'median', take_log=True, prior=32.0)
+    t1 = time.perf_counter()
+    data = _native.condense_host(ctx, lc, [[2 * s_, 2 * s_ + 1] for s_ in range(Cc // 2)])
+    t2 = time.perf_counter()
+    out['preprocess'] = {'normalize_s': t1 - t0, 'condense_s': t2 - t1, 'unit': 's (host entry points, pageable buffers)',
+                         'shape': '%d guides x %d replicate columns -> %d samples' % (N, Cc, Cc // 2),
+                         'guide_samples_per_s': N * (Cc // 2) / (t2 - t0)}
+    assert np.isfinite(data).all()
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
@@ -283,7 +335,6 @@ def main():
     fence()
     ms = e0.elapsed_time(e1)
     launches = ctx.launch_count - launches0
-    clk = clocks.stop() if rank == 0 else None
     iters = o_it.cpu().numpy().astype(np.float64)
     G_of = np.diff(offs).astype(np.float64)
     flops_step = float(((19.0 * iters + 12.0) * G_of * L).sum())
@@ -346,7 +397,11 @@ def main():
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_value = genes_all / float(te.item())
+    clk = clocks.stop() if rank == 0 else None      # sampled over both timed regions (device-resident and e2e)
 
+    aux = None
+    if rank == 0 and world == 1:
+        aux = aux_measurements(ctx, torch, dev, stream, L)
     if rank == 0:
         peaks = {}
         try:
@@ -363,7 +418,7 @@ def main():
                'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': int(d2h),
                        'ms_per_step': 1e3 * float(te.item()), 'api': 'jacks_em_batched_host (C-ABI), pinned host buffers'},
                'roofline': {'bound': 'fp64', 'achieved': tf, 'peak': fp64_peak / 1e12, 'unit': 'TFLOP/s',
-                            'frac': tf / (fp64_peak / 1e12), 'traffic': None,
+                            'frac': tf / (fp64_peak / 1e12), 'traffic': ncu_traffic(),
                             'peak_source': 'FP64 FMA-pipe peak measured in this run (jacks_fp64_peak_flops); '
                                            'MEASURED_PEAKS.json carries no FP64 figure',
                             'kernel': 'em_fast_kernel<G=4,W>', 'mean_iters': float(iters.mean()),
@@ -371,7 +426,7 @@ def main():
                'roofline_hbm': {'bound': 'hbm', 'achieved': bytes_all / world / (ms_per_step * 1e-3) / 1e9, 'peak': hbm_peak,
                                 'unit': 'GB/s', 'frac': bytes_all / world / (ms_per_step * 1e-3) / 1e9 / hbm_peak,
                                 'peak_source': hbm_src},
-               'cpu_baseline': cpu}
+               'cpu_baseline': cpu, 'aux': aux}
         print(json.dumps(out), flush=True)
     if world > 1:
         dist.destroy_process_group()
