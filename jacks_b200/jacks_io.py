@@ -4,8 +4,8 @@ the same names, arguments, defaults, file formats and error messages.
 
 Host side by design (as in the reference): file parsing, the ``random`` draws of the pseudo-genes,
 gene ranking, Benjamini-Hochberg sets and text formatting -- so that indexing and ranking are
-bit-exact.  GPU side: the EM (``inferJACKS``), the preprocessing error model and the KDE p-values
-(``computeW1PvalsAndFDRs`` with pseudo=True, the only branch the command line reaches).
+bit-exact.  GPU side: the EM (``inferJACKS``), the preprocessing error model and the KDE p-values / local
+fdr (``computeW1PvalsAndFDRs``, every branch).
 """
 import argparse
 import csv
