@@ -239,6 +239,27 @@ JACKS_API int jacks_normalize_host(JacksCtx* ctx, const double* values, int64_t 
 JACKS_API int jacks_posterior_sd_subset_host(JacksCtx* ctx, const double* data, int64_t n_guides, int32_t n_rep,
                                    const uint8_t* in_set, int32_t window, int32_t monotonize, double* sd);
 
+/*
+ * Host-side ingest and formatting (no GPU work).
+ *
+ * jacks_table_scan: count the non-empty records of a delimiter-separated text file after `skip_lines` lines (the
+ *   header and anything above it) and return the byte offset where the data starts.
+ * jacks_table_read: parse n_records records starting at data_offset: values[r, i] = numeric value of column
+ *   sel_cols[i] (NaN and not_numeric[r, i] = 1 when the cell is not a plain decimal literal -- the reference eval()s
+ *   cells, preprocess.py:147, so the caller evaluates just those in Python), label_off/label_len = byte range of the
+ *   record's first field (the guide id) inside the file.  Double-quoted fields follow Python's csv 'excel' dialect.
+ * jacks_table_write: header, then per row its label (bytes labels[label_off[r] .. label_off[r+1]), which may itself
+ *   contain tabs for multi-column labels) followed by n_cols tab-separated values printed like Python's
+ *   '%<width>e' % v ('%5e' in writeJacksWResults / writeJacksXResults, '%6e' in writeFoldChanges,
+ *   jacks_io.py:91-156); blank[r, c] != 0 leaves the field empty (non-significant entries under --fdr).
+ */
+JACKS_API int jacks_table_scan(const char* path, int64_t skip_lines, int64_t* n_records, int64_t* data_offset);
+JACKS_API int jacks_table_read(const char* path, int64_t data_offset, char delim, int64_t n_records, int32_t n_sel,
+                     const int32_t* sel_cols, double* values, uint8_t* not_numeric, int64_t* label_off,
+                     int32_t* label_len);
+JACKS_API int jacks_table_write(const char* path, const char* header, int64_t n_rows, int32_t n_cols, const char* labels,
+                      const int64_t* label_off, const double* values, const uint8_t* blank, int32_t width);
+
 /* FP64 FMA-pipe peak of the current device in FLOP/s (dependent-chain-free DFMA microbenchmark);
  * bench.py uses it as the roofline denominator because MEASURED_PEAKS.json has no FP64 entry. */
 JACKS_API int jacks_fp64_peak_flops(JacksCtx* ctx, double* flops_out, double* seconds_out);

@@ -90,6 +90,9 @@ def lib():
             L.jacks_condense_host.argtypes = [vp, vp, i64, i32, vp, vp, i32, i32, i32, vp]
             L.jacks_normalize_host.argtypes = [vp, vp, i64, i32, i32, dbl, vp, i64, i32, vp, vp]
             L.jacks_posterior_sd_subset_host.argtypes = [vp, vp, i64, i32, vp, i32, i32, vp]
+        L.jacks_table_scan.argtypes = [C.c_char_p, i64, C.POINTER(i64), C.POINTER(i64)]
+        L.jacks_table_read.argtypes = [C.c_char_p, i64, C.c_char, i64, i32, vp, vp, vp, vp, vp]
+        L.jacks_table_write.argtypes = [C.c_char_p, C.c_char_p, i64, i32, vp, vp, vp, vp, i32]
         _lib = L
     return _lib
 
@@ -350,3 +353,46 @@ def kde_eval_host(ctx, w_eval, w_null, kind='cdf_neg', leave_one_out=False):
     check(lib().jacks_kde_eval_host(ctx.h, _ptr(w_eval), w_eval.shape[0], _ptr(w_null), w_null.shape[0], w_eval.shape[1],
                                     {'cdf_neg': 0, 'cdf_pos': 1, 'pdf': 2}[kind], int(bool(leave_one_out)), _ptr(out)))
     return out
+
+
+def table_read(path, delim, sel_cols, skip_lines=1):
+    """Native parse of a delimiter-separated table (jacks_table_read): returns (labels, values, not_numeric) --
+    first field of every record, float64 [n_records, len(sel_cols)] of the selected columns, and a mask of cells
+    that are not plain decimal literals (NaN in `values`)."""
+    import mmap
+    n, off = C.c_int64(), C.c_int64()
+    bpath = os.fsencode(path)
+    check(lib().jacks_table_scan(bpath, int(skip_lines), C.byref(n), C.byref(off)))
+    n = n.value
+    sel = np.ascontiguousarray(sel_cols, dtype=np.int32)
+    values = np.empty((n, len(sel)), dtype=np.float64)
+    bad = np.empty((n, len(sel)), dtype=np.uint8)
+    loff = np.empty(n, dtype=np.int64)
+    llen = np.empty(n, dtype=np.int32)
+    check(lib().jacks_table_read(bpath, off.value, delim.encode()[:1], n, len(sel), _ptr(sel), _ptr(values), _ptr(bad),
+                                 _ptr(loff), _ptr(llen)))
+    labels = []
+    if n:
+        with open(path, 'rb') as f:
+            mm = mmap.mmap(f.fileno(), 0, access=mmap.ACCESS_READ)
+            try:
+                for o, ln in zip(loff.tolist(), llen.tolist()):
+                    labels.append(mm[o:o + ln].decode())
+            finally:
+                mm.close()
+    return labels, values, bad.astype(bool)
+
+
+def table_write(path, header, labels, values, width, blank=None):
+    """Native formatter (jacks_table_write): one line per row, `label` then tab-separated '%<width>e' values."""
+    values = np.ascontiguousarray(values, dtype=np.float64)
+    if values.ndim == 1:
+        values = values.reshape(len(labels), -1)
+    enc = [l.encode() for l in labels]
+    offs = np.zeros(len(enc) + 1, dtype=np.int64)
+    if enc:
+        np.cumsum([len(b) for b in enc], out=offs[1:])
+    blob = b''.join(enc)
+    mask = None if blank is None else np.ascontiguousarray(blank, dtype=np.uint8)
+    check(lib().jacks_table_write(os.fsencode(path), header.encode(), len(enc), values.shape[1] if values.size or len(enc) else 0,
+                                  blob, _ptr(offs), _ptr(values), _ptr(mask), int(width)))

@@ -23,14 +23,14 @@ FAST_G = list(range(1, 9))
 
 UNITS = [('capi.cu', 'capi.o', []), ('em_dispatch.cu', 'em_dispatch.o', []), ('em_generic.cu', 'em_generic.o', []),
          ('fp64_probe.cu', 'fp64_probe.o', []), ('kde_pvalues.cu', 'kde_pvalues.o', []),
-         ('preprocess_kernels.cu', 'preprocess_kernels.o', [])] + \
+         ('preprocess_kernels.cu', 'preprocess_kernels.o', []), ('host_io.cpp', 'host_io.o', ['-x', 'cu'])] + \
         [('em_fast_inst.cu', 'em_fast_g%d.o' % g, ['-DJACKS_G=%d' % g]) for g in FAST_G]
 
 
 def _sources():
     out = [os.path.join(REPO, 'include', 'jacks_b200.h')]
     for f in sorted(os.listdir(CSRC)):
-        if f.endswith(('.cu', '.cuh', '.h')):
+        if f.endswith(('.cu', '.cuh', '.h', '.cpp')):
             out.append(os.path.join(CSRC, f))
     return out
 
@@ -55,7 +55,7 @@ def build_library(force=False, verbose=False):
     if not force and not _stale(LIB, deps):
         return LIB
     os.makedirs(OBJ, exist_ok=True)
-    hdrs = [d for d in deps if not d.endswith('.cu')]
+    hdrs = [d for d in deps if not d.endswith(('.cu', '.cpp'))]
 
     def compile_one(u):
         src, obj, extra = os.path.join(CSRC, u[0]), os.path.join(OBJ, u[1]), u[2]

@@ -1,0 +1,181 @@
+// Host-side ingest and result formatting (no GPU work): the two places where the Python reference spends
+// minutes at the Avana shape once the numerics are on the GPU.
+//
+//   jacks_table_scan / jacks_table_read   delimiter-separated count table -> float64 matrix of selected columns
+//                                         + (offset, length) of every row's first field.  Replaces the per-cell
+//                                         eval() of preprocess.py:136-149; cells that are not plain numbers come
+//                                         back as NaN with a flag so the caller can eval() just those.
+//   jacks_table_write                     rows of '%5e' / '%6e' formatted values with a label prefix, as
+//                                         writeJacksWResults / writeFoldChanges produce them (jacks_io.py:91-156).
+//
+// Quoting follows Python's csv 'excel' dialect as far as count tables need it: a field may be wrapped in double
+// quotes, inside which delimiters are literal and "" is an escaped quote.
+#include <errno.h>
+#include <fcntl.h>
+#include <math.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/jacks_b200.h"
+#include "capi_internal.h"
+
+using namespace jacks;
+
+namespace {
+
+struct Mapped {
+    const char* p = nullptr;
+    size_t n = 0;
+    int fd = -1;
+    int open(const char* path) {
+        fd = ::open(path, O_RDONLY);
+        if (fd < 0) return fail(JACKS_E_INVALID, "cannot open %s: %s", path, strerror(errno));
+        struct stat st;
+        if (fstat(fd, &st) != 0) return fail(JACKS_E_INVALID, "cannot stat %s", path);
+        n = (size_t)st.st_size;
+        if (n == 0) { p = ""; return JACKS_OK; }
+        void* m = mmap(nullptr, n, PROT_READ, MAP_PRIVATE, fd, 0);
+        if (m == MAP_FAILED) return fail(JACKS_E_NOMEM, "cannot map %s", path);
+        p = (const char*)m;
+        return JACKS_OK;
+    }
+    ~Mapped() {
+        if (p && n) munmap((void*)p, n);
+        if (fd >= 0) close(fd);
+    }
+};
+
+// end of the record starting at `b` (exclusive of the line terminator); *next = start of the next record
+inline const char* record_end(const char* b, const char* end, const char** next) {
+    bool quoted = false;
+    const char* q = b;
+    for (; q < end; ++q) {
+        if (*q == '"') quoted = !quoted;
+        else if (!quoted && (*q == '\n' || *q == '\r')) break;
+    }
+    const char* e = q;
+    if (q < end && *q == '\r') ++q;
+    if (q < end && *q == '\n') ++q;
+    *next = q;
+    return e;
+}
+
+}  // namespace
+
+extern "C" int jacks_table_scan(const char* path, int64_t skip_lines, int64_t* n_records, int64_t* data_offset) {
+    if (!path || !n_records || !data_offset) return fail(JACKS_E_INVALID, "jacks_table_scan: NULL argument");
+    Mapped m;
+    int rc = m.open(path);
+    if (rc != JACKS_OK) return rc;
+    const char* b = m.p;
+    const char* end = m.p + m.n;
+    const char* next = b;
+    for (int64_t i = 0; i < skip_lines && b < end; ++i) { record_end(b, end, &next); b = next; }
+    *data_offset = (int64_t)(b - m.p);
+    int64_t cnt = 0;
+    while (b < end) {
+        const char* e = record_end(b, end, &next);
+        if (e > b) ++cnt;                       // csv skips completely empty lines
+        b = next;
+    }
+    *n_records = cnt;
+    return JACKS_OK;
+}
+
+extern "C" int jacks_table_read(const char* path, int64_t data_offset, char delim, int64_t n_records, int32_t n_sel,
+                                const int32_t* sel_cols, double* values, uint8_t* not_numeric, int64_t* label_off,
+                                int32_t* label_len) {
+    if (!path || (n_sel > 0 && (!sel_cols || !values)) || !label_off || !label_len)
+        return fail(JACKS_E_INVALID, "jacks_table_read: NULL argument");
+    Mapped m;
+    int rc = m.open(path);
+    if (rc != JACKS_OK) return rc;
+    int max_col = 0;
+    for (int i = 0; i < n_sel; ++i) { if (sel_cols[i] < 0) return fail(JACKS_E_INVALID, "negative column index"); if (sel_cols[i] > max_col) max_col = sel_cols[i]; }
+    std::vector<std::vector<int>> want(max_col + 1);          // column -> output slots (a column may be selected twice)
+    for (int i = 0; i < n_sel; ++i) want[sel_cols[i]].push_back(i);
+    const char* b = m.p + data_offset;
+    const char* end = m.p + m.n;
+    const char* next = b;
+    int64_t r = 0;
+    std::string tmp;
+    while (b < end && r < n_records) {
+        const char* e = record_end(b, end, &next);
+        if (e == b) { b = next; continue; }
+        for (int i = 0; i < n_sel; ++i) { values[r * n_sel + i] = NAN; if (not_numeric) not_numeric[r * n_sel + i] = 1; }
+        const char* f = b;
+        int col = 0;
+        while (f <= e) {
+            const char* fe;
+            const char* vb; const char* ve;
+            if (f < e && *f == '"') {                         // quoted field
+                const char* q = f + 1;
+                while (q < e) { if (*q == '"') { if (q + 1 < e && q[1] == '"') { q += 2; continue; } break; } ++q; }
+                vb = f + 1; ve = q;
+                fe = (q < e) ? q + 1 : e;
+                while (fe < e && *fe != delim) ++fe;
+            } else {
+                fe = f;
+                while (fe < e && *fe != delim) ++fe;
+                vb = f; ve = fe;
+            }
+            if (col == 0) { label_off[r] = (int64_t)(vb - m.p); label_len[r] = (int32_t)(ve - vb); }
+            if (col <= max_col && !want[col].empty()) {
+                while (vb < ve && (*vb == ' ' || *vb == '\t')) ++vb;
+                while (ve > vb && (ve[-1] == ' ' || ve[-1] == '\t')) --ve;
+                if (ve > vb) {
+                    tmp.assign(vb, ve);
+                    char* stop = nullptr;
+                    errno = 0;
+                    const double v = strtod(tmp.c_str(), &stop);
+                    // plain decimal literals only: Python's eval() reads "0x10", "1_000", "nan" differently from strtod
+                    bool plain = (stop == tmp.c_str() + tmp.size());
+                    for (char ch : tmp) if (!((ch >= '0' && ch <= '9') || ch == '.' || ch == '-' || ch == '+' || ch == 'e' || ch == 'E')) { plain = false; break; }
+                    if (plain) for (int slot : want[col]) { values[r * n_sel + slot] = v; if (not_numeric) not_numeric[r * n_sel + slot] = 0; }
+                }
+            }
+            ++col;
+            if (fe >= e) break;
+            f = fe + 1;
+        }
+        ++r;
+        b = next;
+    }
+    if (r != n_records) return fail(JACKS_E_INVALID, "%s: expected %lld records, found %lld", path, (long long)n_records, (long long)r);
+    return JACKS_OK;
+}
+
+extern "C" int jacks_table_write(const char* path, const char* header, int64_t n_rows, int32_t n_cols, const char* labels,
+                                 const int64_t* label_off, const double* values, const uint8_t* blank, int32_t width) {
+    if (!path || !header || (n_rows > 0 && (!labels || !label_off || (n_cols > 0 && !values))))
+        return fail(JACKS_E_INVALID, "jacks_table_write: NULL argument");
+    FILE* f = fopen(path, "wb");
+    if (!f) return fail(JACKS_E_INVALID, "cannot write %s: %s", path, strerror(errno));
+    std::vector<char> buf(1 << 20);
+    setvbuf(f, buf.data(), _IOFBF, buf.size());
+    fputs(header, f);
+    char num[64];
+    for (int64_t r = 0; r < n_rows; ++r) {
+        fwrite(labels + label_off[r], 1, (size_t)(label_off[r + 1] - label_off[r]), f);
+        for (int c = 0; c < n_cols; ++c) {
+            fputc('\t', f);
+            if (blank && blank[r * n_cols + c]) continue;
+            const double v = values[r * n_cols + c];
+            int len;
+            if (v != v) len = snprintf(num, sizeof num, "%*s", width, "nan");            // Python prints nan without a sign
+            else len = snprintf(num, sizeof num, "%*e", width, v);
+            fwrite(num, 1, (size_t)len, f);
+        }
+        fputc('\n', f);
+    }
+    if (fclose(f) != 0) return fail(JACKS_E_INVALID, "error closing %s", path);
+    return JACKS_OK;
+}

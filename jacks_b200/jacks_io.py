@@ -101,9 +101,8 @@ def writeJacksWResults(outprefix, jacks_results, cell_lines, write_types=[''], c
     """Gene-level result tables, one file per write type ('' = E[w], '_std', '_pval', '_fdr'), genes ranked by
     mean w1, values formatted '%5e' (jacks_io.py:91-133)."""
     ordered_genes = getSortedGenes(jacks_results, positive)
+    # the files are opened first, as in the reference, so that a failing p-value step leaves the same (empty) files
     fouts = [io.open(outprefix + '_gene%s_JACKS_results.txt' % write_type, 'w') for write_type in write_types]
-    for fout in fouts:
-        fout.write(u'Gene\t%s\n' % ('\t'.join(cell_lines)))
     if '_fdr' in write_types or '_pval' in write_types:
         LOG.info('Computing P-values for %s selection' % ('positive' if positive else 'negative'))
         jacks_w1_pvals, jacks_w1_fdrs = computeW1PvalsAndFDRs(jacks_results, cell_lines, noness_genes=ctrl_geneset,
@@ -117,57 +116,65 @@ def writeJacksWResults(outprefix, jacks_results, cell_lines, write_types=[''], c
         else:
             raise Exception('Unrecognised FDR threshold type (expecting REGULAR or LOCAL_FDR): ', fdr_thresh_type)
 
+    for fout in fouts:
+        fout.close()
+    kept, flags = [], []
     for w1_mean, gene in ordered_genes:
-        w1, w2 = jacks_results[gene][4], jacks_results[gene][5]
         if fdr is not None:
             sig_gene_flags = [(gene in x) for x in fdr_sets]
         else:
-            sig_gene_flags = [True for x in w1]
+            sig_gene_flags = [True for x in jacks_results[gene][4]]
         if sum(sig_gene_flags) == 0:
             continue
         if 'JACKS_PSEUDO_GENE' in gene:
             continue                                  # pseudo-genes are never written (jacks_io.py:131)
-        for write_type, fout in zip(write_types, fouts):
-            if write_type == '_pval':
-                vals = ['%5e' % x for x in jacks_w1_pvals[gene]]
-            elif write_type == '_fdr':
-                vals = ['%5e' % x for x in jacks_w1_fdrs[gene]]
-            elif write_type == '_std':
-                vals = ['%5e' % np.sqrt(b - a ** 2.0) for (a, b) in zip(w1, w2)]
-            elif write_type == '':
-                vals = [('%5e' % a) if flag else '' for (a, flag) in zip(w1, sig_gene_flags)]
-            else:
-                raise Exception('Unrecognised write type: %s' % write_type)
-            fout.write(u'%s\t%s\n' % (gene, '\t'.join(vals)))
-    for fout in fouts:
-        fout.close()
+        kept.append(gene)
+        flags.append(sig_gene_flags)
+    L = len(cell_lines)
+    W1 = np.array([jacks_results[g][4] for g in kept], dtype=np.float64).reshape(len(kept), L)
+    header = u'Gene\t%s\n' % ('\t'.join(cell_lines))
+    for write_type in write_types:
+        blank = None
+        if write_type == '_pval':
+            vals = np.array([jacks_w1_pvals[g] for g in kept], dtype=np.float64).reshape(len(kept), L)
+        elif write_type == '_fdr':
+            vals = np.array([jacks_w1_fdrs[g] for g in kept], dtype=np.float64).reshape(len(kept), L)
+        elif write_type == '_std':
+            W2 = np.array([jacks_results[g][5] for g in kept], dtype=np.float64).reshape(len(kept), L)
+            with np.errstate(invalid='ignore'):
+                vals = np.sqrt(W2 - W1 ** 2.0)
+        elif write_type == '':
+            vals = W1
+            blank = ~np.array(flags, dtype=bool).reshape(len(kept), L)
+        else:
+            raise Exception('Unrecognised write type: %s' % write_type)
+        _native.table_write(outprefix + '_gene%s_JACKS_results.txt' % write_type, header, kept, vals, 5, blank=blank)
 
 
 def writeJacksXResults(filename, jacks_results, gene_grnas):
     """Guide efficacies sgrna / X1 / X2, guides grouped by gene, genes ranked by mean w1 (jacks_io.py:135-146)."""
     ordered_genes = sorted((np.nanmean(jacks_results[gene][4]), gene) for gene in jacks_results)
-    fout = io.open(filename, 'w')
-    fout.write(u'sgrna\tX1\tX2\n')
+    labels, x1s, x2s = [], [], []
     for w1_mean, gene in ordered_genes:
         y, tau, x1, x2, w1, w2 = jacks_results[gene]
-        for i, grna in enumerate(gene_grnas[gene]):
-            fout.write(u'%s\t%5e\t%5e\n' % (grna, x1[i], x2[i]))
-    fout.close()
+        grnas = gene_grnas[gene]
+        labels.extend(grnas)
+        x1s.append(np.asarray(x1, dtype=np.float64)[:len(grnas)])
+        x2s.append(np.asarray(x2, dtype=np.float64)[:len(grnas)])
+    vals = np.stack([np.concatenate(x1s), np.concatenate(x2s)], axis=1) if labels else np.zeros((0, 2))
+    _native.table_write(filename, u'sgrna\tX1\tX2\n', [str(g) for g in labels], vals, 5)
 
 
 def writeFoldChanges(filename, testdata, ctrldata, meta, sample_ids, write_std=False, write_raw=False):
     """Per-guide log fold changes (or their standard deviations) against the control (jacks_io.py:148-156)."""
-    fout = io.open(filename, 'w')
-    fout.write(u'gRNA\tgene\t%s\n' % '\t'.join(sample_ids))
-    for i in range(len(meta[:, 0])):
-        if write_std:
-            vals = [np.sqrt(x ** 2.0 + y ** 2.0) for (x, y) in zip(testdata[i, :, 1], ctrldata[i, :, 1])]
-        elif write_raw:
-            vals = [np.sqrt(x ** 2.0 + y ** 2.0) for (x, y) in zip(testdata[i, :, 2], ctrldata[i, :, 2])]
-        else:
-            vals = testdata[i, :, 0] - ctrldata[i, :, 0]
-        fout.write(u'%s\t%s\t%s\n' % (meta[i, 0], meta[i, 1], '\t'.join(['%6e' % x for x in vals])))
-    fout.close()
+    if write_std:
+        vals = np.sqrt(testdata[:, :, 1] ** 2.0 + ctrldata[:, :, 1] ** 2.0)
+    elif write_raw:
+        vals = np.sqrt(testdata[:, :, 2] ** 2.0 + ctrldata[:, :, 2] ** 2.0)
+    else:
+        vals = testdata[:, :, 0] - ctrldata[:, :, 0]
+    labels = ['%s\t%s' % (meta[i, 0], meta[i, 1]) for i in range(len(meta[:, 0]))]
+    _native.table_write(filename, u'gRNA\tgene\t%s\n' % '\t'.join(sample_ids), labels, vals, 6)
 
 
 def writeLogData(filename, data, meta, sample_ids, write_std=False, write_raw=False):

@@ -111,6 +111,41 @@ def _parse_cell(text):
             return float(eval(text))
 
 
+def _read_counts_python(filename, delim, colnames, gene_spec):
+    """The reference's reader (preprocess.py:139-149): csv.DictReader, every cell eval()ed."""
+    raw, meta = [], []
+    with io.open(filename) as f:
+        rdr = csv.DictReader(f, delimiter=delim)
+        sgrna_col = rdr.fieldnames[0]                 # the guide label is the first column
+        for row in rdr:
+            guide = row[sgrna_col]
+            if guide not in gene_spec:
+                continue                              # no gene mapping: ignored
+            raw.append([_parse_cell(row[c]) for c in colnames])
+            meta.append([guide, gene_spec[guide]])
+    return raw, meta
+
+
+def _read_counts_native(filename, delim, colnames, gene_spec):
+    """Same result through the native table parser (jacks_table_read); returns (None, None) when the file needs the
+    csv module after all (a multi-line header, cells that are not plain numbers, duplicate column names)."""
+    with io.open(filename) as f:
+        header_line = f.readline()
+        fieldnames = next(csv.reader([header_line], delimiter=delim), None)
+    if not fieldnames or header_line.count('"') % 2 or len(set(fieldnames)) != len(fieldnames):
+        return None, None
+    try:
+        sel = [fieldnames.index(c) for c in colnames]
+    except ValueError:
+        return None, None                             # let DictReader raise the reference's KeyError
+    labels, values, not_numeric = _native.table_read(filename, delim, sel, skip_lines=1)
+    keep = np.fromiter((g in gene_spec for g in labels), dtype=bool, count=len(labels))
+    if not_numeric[keep].any():
+        return None, None
+    meta = [[g, gene_spec[g]] for g, k in zip(labels, keep) if k]
+    return values[keep], meta
+
+
 def loadDataAndPreprocess(sample_spec, gene_spec, ctrl_spec={}, ctrl_geneset=set(), normtype='median', prior=32):
     """Load counts from one or more files with the same guides in the same order and condense them
     (preprocess.py:128-173).  sample_spec {filename: [(sample_id, colname)]}.
@@ -120,20 +155,12 @@ def loadDataAndPreprocess(sample_spec, gene_spec, ctrl_spec={}, ctrl_geneset=set
     ctx = _native.context(0)
     samples, sample_counts, metas = [], [], []
     for filename in sample_spec:
-        raw, meta = [], []
-        f = io.open(filename)
         delim = ',' if (filename.split('.')[-1] == 'csv') else '\t'
-        rdr = csv.DictReader(f, delimiter=delim)
-        sgrna_col = rdr.fieldnames[0]                 # the guide label is the first column
         samples.extend([sample_id for sample_id, colname in sample_spec[filename]])
         colnames = [colname for sample_id, colname in sample_spec[filename]]
-        for row in rdr:
-            guide = row[sgrna_col]
-            if guide not in gene_spec:
-                continue                              # no gene mapping: ignored
-            raw.append([_parse_cell(row[c]) for c in colnames])
-            meta.append([guide, gene_spec[guide]])
-        f.close()
+        raw, meta = _read_counts_native(filename, delim, colnames, gene_spec)
+        if raw is None:
+            raw, meta = _read_counts_python(filename, delim, colnames, gene_spec)
         raw = np.array(raw, dtype=np.float64).reshape(len(meta), len(colnames))
         mask = None
         if normtype == 'ctrl_guides':

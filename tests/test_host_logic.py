@@ -144,3 +144,61 @@ def test_dropin_shim_exposes_reference_names():
         sys.path.pop(0)
         for m in [k for k in sys.modules if k == 'jacks' or k.startswith('jacks.')]:
             del sys.modules[m]
+
+
+def test_native_table_writer_formats_like_python(tmp_path):
+    rng = np.random.default_rng(4)
+    vals = np.concatenate([rng.normal(size=200) * 10.0 ** rng.integers(-300, 300, size=200),
+                           [0.0, -0.0, np.nan, np.inf, -np.inf, 5e-324, 1.7976931348623157e308, 9.9999995e-5, 1e-259, 0.5]])
+    vals = vals.reshape(-1, 5)
+    labels = ['row%d\tg' % i for i in range(vals.shape[0])]
+    blank = np.zeros(vals.shape, dtype=bool); blank[3, 2] = True
+    path = str(tmp_path / 't.txt')
+    for width, fmt in ((5, '%5e'), (6, '%6e')):
+        _native.table_write(path, 'h1\th2\n', labels, vals, width, blank=blank)
+        want = 'h1\th2\n' + ''.join('%s\t%s\n' % (labels[i], '\t'.join('' if blank[i, j] else fmt % vals[i, j]
+                                                                      for j in range(vals.shape[1]))) for i in range(len(labels)))
+        assert open(path).read() == want
+    _native.table_write(path, 'only header\n', [], np.zeros((0, 3)), 5)
+    assert open(path).read() == 'only header\n'
+
+
+def test_native_table_reader_matches_csv_module(tmp_path):
+    import csv
+    text = ('sgRNA\tGene\ta\tb\tc\r\n'
+            'g1\tX\t10\t2.5\t3\r\n'
+            '\r\n'
+            '"g 2"\tY\t 7 \t1e3\t-4\r\n'
+            '"g""q"\tZ\t0\t12/4\t5\r\n'
+            'g4\tX\t1\t2\t3')
+    p = tmp_path / 'c.tab'
+    p.write_bytes(text.encode())
+    labels, values, bad = _native.table_read(str(p), '\t', [2, 4, 3])
+    rows = list(csv.DictReader(io.open(str(p)), delimiter='\t'))
+    assert [r['sgRNA'] for r in rows][:2] == labels[:2] == ['g1', 'g 2']
+    assert labels[2] == 'g""q' and labels[3] == 'g4'            # raw bytes of a field with an escaped quote
+    assert values.shape == (4, 3)
+    assert values[0].tolist() == [10.0, 3.0, 2.5] and values[1].tolist() == [7.0, -4.0, 1000.0]
+    assert bad[2].tolist() == [False, False, True] and np.isnan(values[2, 2])       # "12/4" is left to eval()
+    assert values[3].tolist() == [1.0, 3.0, 2.0] and not bad[[0, 1, 3]].any()
+    pc = tmp_path / 'c.csv'
+    pc.write_text(u'id,v\nq1,5\n"a,b",6\n')
+    labels, values, bad = _native.table_read(str(pc), ',', [1])
+    assert labels == ['q1', 'a,b'] and values[:, 0].tolist() == [5.0, 6.0]
+
+
+def test_count_reader_native_equals_python_reader(tmp_path):
+    from jacks_b200 import preprocess
+    inp = load_golden('small_inputs.npz')
+    counts = inp['counts'][:400]
+    p = tmp_path / 'counts.tab'
+    with io.open(str(p), 'w', newline='') as f:
+        f.write(u'sgRNA\tGene\t%s\r\n' % '\t'.join(str(c) for c in inp['columns']))
+        for i in range(counts.shape[0]):
+            f.write(u'%s\t%s\t%s\r\n' % (inp['guides'][i], inp['genes'][i], '\t'.join(str(int(v)) for v in counts[i])))
+    gene_spec = {str(g): str(n) for g, n in zip(inp['guides'][:400:2], inp['genes'][:400:2])}      # every other guide mapped
+    cols = [str(c) for c in inp['columns'][[3, 0, 7]]]
+    a_raw, a_meta = preprocess._read_counts_native(str(p), '\t', cols, gene_spec)
+    b_raw, b_meta = preprocess._read_counts_python(str(p), '\t', cols, gene_spec)
+    assert a_meta == b_meta and len(a_meta) == 200
+    assert np.array_equal(np.asarray(a_raw), np.asarray(b_raw, dtype=np.float64))
