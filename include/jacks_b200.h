@@ -246,8 +246,9 @@ JACKS_API int jacks_posterior_sd_subset_host(JacksCtx* ctx, const double* data, 
  *   header and anything above it) and return the byte offset where the data starts.
  * jacks_table_read: parse n_records records starting at data_offset: values[r, i] = numeric value of column
  *   sel_cols[i] (NaN and not_numeric[r, i] = 1 when the cell is not a plain decimal literal -- the reference eval()s
- *   cells, preprocess.py:147, so the caller evaluates just those in Python), label_off/label_len = byte range of the
- *   record's first field (the guide id) inside the file.  Double-quoted fields follow Python's csv 'excel' dialect.
+ *   cells, preprocess.py:147, so the caller evaluates just those in Python); label_off/label_len [n_records, n_str] =
+ *   byte range inside the file of the text columns str_cols[0..n_str) (guide id, gene name; length -1 when the
+ *   record has no such field).  Double-quoted fields follow Python's csv 'excel' dialect.
  * jacks_table_write: header, then per row its label (bytes labels[label_off[r] .. label_off[r+1]), which may itself
  *   contain tabs for multi-column labels) followed by n_cols tab-separated values printed like Python's
  *   '%<width>e' % v ('%5e' in writeJacksWResults / writeJacksXResults, '%6e' in writeFoldChanges,
@@ -255,8 +256,8 @@ JACKS_API int jacks_posterior_sd_subset_host(JacksCtx* ctx, const double* data, 
  */
 JACKS_API int jacks_table_scan(const char* path, int64_t skip_lines, int64_t* n_records, int64_t* data_offset);
 JACKS_API int jacks_table_read(const char* path, int64_t data_offset, char delim, int64_t n_records, int32_t n_sel,
-                     const int32_t* sel_cols, double* values, uint8_t* not_numeric, int64_t* label_off,
-                     int32_t* label_len);
+                     const int32_t* sel_cols, double* values, uint8_t* not_numeric, int32_t n_str,
+                     const int32_t* str_cols, int64_t* label_off, int32_t* label_len);
 JACKS_API int jacks_table_write(const char* path, const char* header, int64_t n_rows, int32_t n_cols, const char* labels,
                       const int64_t* label_off, const double* values, const uint8_t* blank, int32_t width);
 

@@ -91,7 +91,7 @@ def lib():
             L.jacks_normalize_host.argtypes = [vp, vp, i64, i32, i32, dbl, vp, i64, i32, vp, vp]
             L.jacks_posterior_sd_subset_host.argtypes = [vp, vp, i64, i32, vp, i32, i32, vp]
         L.jacks_table_scan.argtypes = [C.c_char_p, i64, C.POINTER(i64), C.POINTER(i64)]
-        L.jacks_table_read.argtypes = [C.c_char_p, i64, C.c_char, i64, i32, vp, vp, vp, vp, vp]
+        L.jacks_table_read.argtypes = [C.c_char_p, i64, C.c_char, i64, i32, vp, vp, vp, i32, vp, vp, vp]
         L.jacks_table_write.argtypes = [C.c_char_p, C.c_char_p, i64, i32, vp, vp, vp, vp, i32]
         _lib = L
     return _lib
@@ -355,31 +355,36 @@ def kde_eval_host(ctx, w_eval, w_null, kind='cdf_neg', leave_one_out=False):
     return out
 
 
-def table_read(path, delim, sel_cols, skip_lines=1):
+def table_read(path, delim, sel_cols, skip_lines=1, str_cols=(0,)):
     """Native parse of a delimiter-separated table (jacks_table_read): returns (labels, values, not_numeric) --
-    first field of every record, float64 [n_records, len(sel_cols)] of the selected columns, and a mask of cells
-    that are not plain decimal literals (NaN in `values`)."""
+    the text of column str_cols[0] of every record (a list of tuples when several text columns are asked for; None
+    for a missing field), float64 [n_records, len(sel_cols)] of the selected columns, and a mask of cells that are
+    not plain decimal literals (NaN in `values`)."""
     import mmap
     n, off = C.c_int64(), C.c_int64()
     bpath = os.fsencode(path)
     check(lib().jacks_table_scan(bpath, int(skip_lines), C.byref(n), C.byref(off)))
     n = n.value
     sel = np.ascontiguousarray(sel_cols, dtype=np.int32)
+    sc = np.ascontiguousarray(str_cols, dtype=np.int32)
     values = np.empty((n, len(sel)), dtype=np.float64)
     bad = np.empty((n, len(sel)), dtype=np.uint8)
-    loff = np.empty(n, dtype=np.int64)
-    llen = np.empty(n, dtype=np.int32)
+    loff = np.empty((n, len(sc)), dtype=np.int64)
+    llen = np.empty((n, len(sc)), dtype=np.int32)
     check(lib().jacks_table_read(bpath, off.value, delim.encode()[:1], n, len(sel), _ptr(sel), _ptr(values), _ptr(bad),
-                                 _ptr(loff), _ptr(llen)))
-    labels = []
+                                 len(sc), _ptr(sc), _ptr(loff), _ptr(llen)))
+    cols = [[] for _ in range(len(sc))]
     if n:
         with open(path, 'rb') as f:
             mm = mmap.mmap(f.fileno(), 0, access=mmap.ACCESS_READ)
             try:
-                for o, ln in zip(loff.tolist(), llen.tolist()):
-                    labels.append(mm[o:o + ln].decode())
+                for k in range(len(sc)):
+                    col = cols[k]
+                    for o, ln in zip(loff[:, k].tolist(), llen[:, k].tolist()):
+                        col.append(None if ln < 0 else mm[o:o + ln].decode())
             finally:
                 mm.close()
+    labels = cols[0] if len(sc) == 1 else list(zip(*cols))
     return labels, values, bad.astype(bool)
 
 

@@ -36,10 +36,23 @@ def getGeneWs(jacks_results, gene):
     return jacks_results[gene][4]
 
 
+def _mean_w1(jacks_results):
+    """np.nanmean(w1) per gene.  Rows of equal length are averaged in one vectorised call (identical bits: numpy
+    reduces each contiguous row with the same pairwise sum as the 1-D call)."""
+    genes = [g for g in jacks_results]
+    if genes:
+        rows = [np.asarray(jacks_results[g][4], dtype=np.float64) for g in genes]
+        if all(r.ndim == 1 and r.shape == rows[0].shape for r in rows) and rows[0].size > 0:
+            W = np.stack(rows)
+            if not np.isnan(W).all(axis=1).any():
+                return list(zip(np.nanmean(W, axis=1), genes))
+    return [(np.nanmean(jacks_results[gene][4]), gene) for gene in genes]
+
+
 def getSortedGenes(jacks_results, positive):
     """[(mean w1 over lines, gene)] ranked by effect, strongest depletion first (enrichment first if
     ``positive``); ties break on the gene name (jacks_io.py:26-31)."""
-    ordered_genes = [(np.nanmean(jacks_results[gene][4]), gene) for gene in jacks_results]
+    ordered_genes = _mean_w1(jacks_results)
     ordered_genes.sort(reverse=bool(positive))
     return ordered_genes
 
@@ -153,7 +166,7 @@ def writeJacksWResults(outprefix, jacks_results, cell_lines, write_types=[''], c
 
 def writeJacksXResults(filename, jacks_results, gene_grnas):
     """Guide efficacies sgrna / X1 / X2, guides grouped by gene, genes ranked by mean w1 (jacks_io.py:135-146)."""
-    ordered_genes = sorted((np.nanmean(jacks_results[gene][4]), gene) for gene in jacks_results)
+    ordered_genes = sorted(_mean_w1(jacks_results))
     labels, x1s, x2s = [], [], []
     for w1_mean, gene in ordered_genes:
         y, tau, x1, x2, w1, w2 = jacks_results[gene]
@@ -250,6 +263,24 @@ def createSampleSpec(infile, repfile, rep_hdr, sample_hdr, common_ctrl_sample, c
 
 def createGeneSpec(guidemappingfile, sgrna_hdr, gene_hdr, ignore_blank_genes=True):
     """Guide map -> {guide: gene} (jacks_io.py:229-234)."""
+    f, delim = prepareFile(guidemappingfile, sgrna_hdr)
+    header_line = f.readline()
+    fieldnames = next(csv.reader([header_line], delimiter=delim), None)
+    f.close()
+    simple = (fieldnames and header_line.count('"') % 2 == 0 and len(set(fieldnames)) == len(fieldnames)
+              and sgrna_hdr in fieldnames and gene_hdr in fieldnames)
+    if simple:
+        # native two-column read (the guide map is usually the count table itself: hundreds of unused columns)
+        skip = 0
+        with io.open(guidemappingfile) as g:
+            line = g.readline()
+            while sgrna_hdr not in line and skip < 100:
+                skip += 1
+                line = g.readline()
+        pairs, _, _ = _native.table_read(guidemappingfile, delim, [], skip_lines=skip + 1,
+                                         str_cols=(fieldnames.index(sgrna_hdr), fieldnames.index(gene_hdr)))
+        if all(a is not None and b is not None and '"' not in a and '"' not in b for a, b in pairs[:1000]):
+            return {a: b for a, b in pairs if (not ignore_blank_genes or b != '')}
     f, delim = prepareFile(guidemappingfile, sgrna_hdr)
     rdr = csv.DictReader(f, delimiter=delim)
     gene_spec = {row[sgrna_hdr]: row[gene_hdr] for row in rdr if (not ignore_blank_genes or row[gene_hdr] != '')}

@@ -75,8 +75,8 @@ def inferMissingVariances(data, meta, sample_ids, ctrl_spec, ctrl_geneset):
     """Fill undefined variances of single-replicate test samples from the sample-vs-control spread of the
     control-gene guides (preprocess.py:98-119)."""
     for s, sample_id in enumerate(sample_ids):
-        if sum(np.isnan(data[:, s, 1]) == 0):
-            continue
+        if np.count_nonzero(~np.isnan(data[:, s, 1])):
+            continue                 # the sample has defined variances
         if sample_id in ctrl_spec and ctrl_spec[sample_id] == sample_id:
             continue                 # a control: JACKS uses the data variance for it at model time
         if sample_id in ctrl_spec and len(ctrl_geneset) > 0:

@@ -185,6 +185,8 @@ def test_native_table_reader_matches_csv_module(tmp_path):
     pc.write_text(u'id,v\nq1,5\n"a,b",6\n')
     labels, values, bad = _native.table_read(str(pc), ',', [1])
     assert labels == ['q1', 'a,b'] and values[:, 0].tolist() == [5.0, 6.0]
+    pairs, _, _ = _native.table_read(str(p), '\t', [], str_cols=(0, 1))
+    assert pairs[0] == ('g1', 'X') and pairs[3] == ('g4', 'X')
 
 
 def test_count_reader_native_equals_python_reader(tmp_path):
@@ -202,3 +204,15 @@ def test_count_reader_native_equals_python_reader(tmp_path):
     b_raw, b_meta = preprocess._read_counts_python(str(p), '\t', cols, gene_spec)
     assert a_meta == b_meta and len(a_meta) == 200
     assert np.array_equal(np.asarray(a_raw), np.asarray(b_raw, dtype=np.float64))
+
+
+def test_vectorised_gene_ranking_is_bit_identical():
+    rng = np.random.default_rng(8)
+    W = rng.normal(size=(500, 37))
+    W[5, 3] = np.nan
+    W[9] = W[8]                                    # exact tie: falls back to the name
+    res = {'g%03d' % i: (None, None, None, None, W[i], None) for i in range(500)}
+    fast = jacks_io.getSortedGenes(res, False)
+    slow = sorted((np.nanmean(res[g][4]), g) for g in res)
+    assert [g for _, g in fast] == [g for _, g in slow]
+    assert all(a == b for (a, _), (b, _) in zip(fast, slow))
