@@ -375,7 +375,10 @@ __device__ __forceinline__ void prefetch_row_l2(const double2* tr, const double2
     }
 }
 
-template <int G, int W, bool UNIT_C>
+// PLAIN: the launch uses neither the w hyper-prior (infer.py:92) nor the 1-D-control sd fill (infer.py:63); both
+// are uniform per launch, and compiling them out keeps the common kernel's code (and its instruction-cache
+// footprint) small.
+template <int G, int W, bool UNIT_C, bool PLAIN>
 __global__ void __launch_bounds__(W * 32) em_fast_kernel(const EmLaunch a) {
     constexpr int NV = 2 * G + 1;
     constexpr int STEP = 32 * W;
@@ -439,7 +442,7 @@ __global__ void __launch_bounds__(W * 32) em_fast_kernel(const EmLaunch a) {
             if (fixed) { x1r[g] = a.fixed_x1[row]; x2r[g] = a.fixed_x2[row]; }
             else { x1r[g] = a.mu0_x; x2r[g] = a.mu0_x * a.mu0_x; }
             fill[g] = 0.0;
-            if (a.ctrl_lines == 1 && a.ctrl_rowmean_fill) {
+            if (!PLAIN && a.ctrl_lines == 1 && a.ctrl_rowmean_fill) {
                 const double cs = a.ctrl[(long long)row].y;
                 if (cs != cs) {
                     // 1-D control with an undefined sd: row mean of the (NaN -> 2.0) test sds, infer.py:63
@@ -547,7 +550,7 @@ __global__ void __launch_bounds__(W * 32) em_fast_kernel(const EmLaunch a) {
 #pragma unroll
                     for (int g = 0; g < G; ++g) { x1r[g] = xu[g] * rm; x2r[g] = x2u[g] * rm2; }
                 }
-                if (a.apply_w_hp && L > 1) {
+                if (!PLAIN && a.apply_w_hp && L > 1) {
                     // hierarchical prior from the current w1, infer.py:92 (population variance)
                     double m[1] = {0.0};
                     for (int l = l0; l < L; l += STEP) m[0] += w1g[l];

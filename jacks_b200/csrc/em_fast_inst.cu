@@ -10,9 +10,9 @@ namespace jacks {
 
 namespace {
 
-template <int G, int W, bool UNIT_C>
+template <int G, int W, bool UNIT_C, bool PLAIN>
 cudaError_t launch_inst(const EmLaunch& a, int n_sm, int grid_limit, cudaStream_t st, int* grid_out) {
-    auto k = em_fast_kernel<G, W, UNIT_C>;
+    auto k = em_fast_kernel<G, W, UNIT_C, PLAIN>;
     const size_t smem = (size_t)em_fast_smem_doubles(G, W, a.L) * sizeof(double);
     if (smem > kMaxDynSmem) return cudaErrorInvalidValue;
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -34,8 +34,12 @@ cudaError_t launch_inst(const EmLaunch& a, int n_sm, int grid_limit, cudaStream_
 template <int G, int W>
 cudaError_t launch_w(const EmLaunch& a, int n_sm, int grid_limit, cudaStream_t st, int* grid_out) {
     // tau = (tps + 0.5) / (...): with the default tps = 0.5 the numerator is exactly 1
-    if (a.tps + 0.5 == 1.0) return launch_inst<G, W, true>(a, n_sm, grid_limit, st, grid_out);
-    return launch_inst<G, W, false>(a, n_sm, grid_limit, st, grid_out);
+    const bool plain = !a.apply_w_hp && !(a.ctrl_lines == 1 && a.ctrl_rowmean_fill);
+    if (a.tps + 0.5 == 1.0) {
+        if (plain) return launch_inst<G, W, true, true>(a, n_sm, grid_limit, st, grid_out);
+        return launch_inst<G, W, true, false>(a, n_sm, grid_limit, st, grid_out);
+    }
+    return launch_inst<G, W, false, false>(a, n_sm, grid_limit, st, grid_out);
 }
 
 }  // namespace
