@@ -274,7 +274,7 @@ int jacks_em_plan_create(JacksCtx* ctx, const int64_t* gene_offsets, const int32
     if (rc == JACKS_OK) rc = p->b->d_deferred.reserve((size_t)std::max<int64_t>(n_genes, 1) * sizeof(int));
     if (rc == JACKS_OK) rc = p->b->d_counters.reserve(kCounterInts * sizeof(int));
     if (rc == JACKS_OK && p->fast_maxG > 0)
-        rc = p->b->d_tpd.reserve((size_t)ctx->n_sm * kMaxFastCtasPerSm * p->fast_maxG * n_lines * sizeof(double));
+        rc = p->b->d_tpd.reserve((size_t)ctx->n_sm * kMaxFastCtasPerSm * p->fast_maxG * em_fast_tpd_stride(n_lines) * sizeof(double));
     // generic kernel configurations (and global scratch if a gene's working set exceeds shared memory)
     memset(&p->cfg_generic, 0, sizeof p->cfg_generic);
     memset(&p->cfg_deferred, 0, sizeof p->cfg_deferred);
@@ -325,6 +325,7 @@ static int em_run_range(JacksCtx* ctx, const JacksEmPlan* plan, const JacksEmPar
     a.tps = params->tau_prior_strength;
     a.scratch = (double*)plan->b->d_scratch.p;
     a.tpd_scratch = (double*)plan->b->d_tpd.p;
+    a.tpd_stride = em_fast_tpd_stride(plan->L);
 
     auto slots_of = [&](const EmBucket& b, int* s0, int* s1) {     // ids ascend inside a bucket
         const int* first = plan->h_ids.data() + b.ids_off;

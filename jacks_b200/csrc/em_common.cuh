@@ -37,8 +37,9 @@ struct EmLaunch {
     // hyper-parameters (infer.py:55 defaults)
     int n_iter; int apply_w_hp;
     double tol, mu0_x, var0_x, mu0_w, var0_w, tps;
-    // fast kernels: per-CTA slab [G][L] for tau_pr_den (global memory, stays L2 resident)
-    double* tpd_scratch;
+    // fast kernels: per-CTA slab [G][tpd_stride] for 2*tau_pr_den (global memory, stays L2 resident);
+    // tpd_stride = em_fast_tpd_stride(L): rows padded so that look-ahead loads need no bounds logic
+    double* tpd_scratch; int tpd_stride;
     // generic kernel only: global scratch when a gene's working set exceeds shared memory
     double* scratch; long long scratch_stride;   // doubles per warp
 };
@@ -53,6 +54,8 @@ bool em_fast_available(int G, int W);
 size_t em_fast_smem_bytes(int G, int W, int L);
 // Largest dynamic shared memory a CTA may request on sm_100a (227 KB minus the static words we use).
 constexpr size_t kMaxDynSmem = 227 * 1024 - 64;
+// Row stride (doubles) of the fast kernels' tau_pr_den slab: L plus one full look-ahead step (4 lines x 128 lanes).
+inline int em_fast_tpd_stride(int L) { return ((L + 15) / 16) * 16 + 512; }
 // Upper bound on resident fast-kernel CTAs per SM the plan provisions tau_pr_den slabs for.
 constexpr int kMaxFastCtasPerSm = 12;
 

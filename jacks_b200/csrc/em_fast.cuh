@@ -133,17 +133,30 @@ __device__ __forceinline__ void team_allsum(double (&v)[NV], double* scr, double
 // independent (a dependent DFMA issues every ~9 cycles on sm_100a, an independent one every 2):
 // with U*G >= 8 each stage is long enough to cover the latency of the previous one.
 //
+// Scaled state (all scalings are exact powers of two): shared memory holds th = tau/2 and the slab
+// holds pd2 = 2*tau_pr_den, so that the tau step (infer.py:118-121) is
+//     den2 = 2*(tau_pr_den + b*/2) = y*(y - 2*x1*w1) + (x2*w2 + pd2),      th = c/den2,
+// three FMAs per element, and the bound needs no b* at all: tau*b* = 2c - 2*tau_pr_den*tau, i.e.
+//     sum tau*b* = 2*c*G*L - 2*sum pd2*th                                   (infer.py:123-125).
+// The W step and the X sums use the doubled guide efficacies (tx = 2*x) / are doubled by the caller.
+// 13 FP64 instructions per element and pass, 6 more per line.
+//
 // MASKED: the step's last line (u = U-1) may lie beyond L for some lanes (`valid` false).  Those
 // lanes still execute the arithmetic on whatever the shared-memory words past the line hold (the
 // allocation carries one step of slack, see em_fast_smem_doubles), but neither store nor
 // accumulate it: the stores and the three accumulating FMAs of that line are predicated.
-template <int G, int U, int UP, bool UNIT_C, bool MASKED>
-__device__ __forceinline__ void em_sweep(const double* __restrict__ ys, const double (&pd)[UP][G],
-                                         double* __restrict__ taus, double* __restrict__ w1p,
+// RELOAD: each pd2 register is refilled with the next step's value (`pd_next`, L2) as soon as its
+// only use (t1 = x2*w2 + pd2) has issued -- the load has the rest of this step and the W step of
+// the next to land.  The bound therefore accumulates t1*th and the caller removes x2*sum th*w2.
+template <int G> struct EmX { double x1[G], x2[G], tx1[G], tx2[G]; };
+
+template <int G, int U, int UP, bool UNIT_C, bool MASKED, bool RELOAD>
+__device__ __forceinline__ void em_sweep(const double* __restrict__ ys, double (&pd)[UP][G],
+                                         const double* __restrict__ pd_next, const int Lp,
+                                         double* __restrict__ ths, double* __restrict__ w1p,
                                          double* __restrict__ w2g, const int L, const int l, const int step,
-                                         const double (&x1r)[G], const double (&x2r)[G], const double ivw,
-                                         const double mw, const double c_tau, double (&a1)[G], double (&a2)[G],
-                                         double (&ab)[G], const bool valid) {
+                                         const EmX<G>& x, const double ivw, const double mw, const double c_tau,
+                                         double (&a1)[G], double (&a2)[G], double (&ab)[G], const bool valid) {
     double yv[U][G], tv[U][G];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
@@ -152,7 +165,7 @@ __device__ __forceinline__ void em_sweep(const double* __restrict__ ys, const do
 #pragma unroll
         for (int g = 0; g < G; ++g) {
             yv[u][g] = ys[g * L + lu];
-            tv[u][g] = taus[g * L + lu];
+            tv[u][g] = ths[g * L + lu];
         }
     }
     // W step, infer.py:112-116 (old tau, new x): den = 1/var0_w + sum_g x2*tau, num = mu0_w/var0_w + sum_g x1*y*tau
@@ -168,8 +181,8 @@ __device__ __forceinline__ void em_sweep(const double* __restrict__ ys, const do
     for (int g = 0; g < G; ++g)
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-            sa[u] = fma(x2r[g], tv[u][g], sa[u]);
-            sb[u] = fma(x1r[g], yt[u][g], sb[u]);
+            sa[u] = fma(x.tx2[g], tv[u][g], sa[u]);
+            sb[u] = fma(x.tx1[g], yt[u][g], sb[u]);
         }
     double r[U], e[U];
 #pragma unroll
@@ -185,20 +198,20 @@ __device__ __forceinline__ void em_sweep(const double* __restrict__ ys, const do
     for (int u = 0; u < U; ++u) w1[u] = sb[u] * r[u];
 #pragma unroll
     for (int u = 0; u < U; ++u) { w2[u] = fma(w1[u], w1[u], r[u]); m2w1[u] = -2.0 * w1[u]; }
-    // tau step, infer.py:118-121: b* = y^2 - 2*y*x1*w1 + x2*w2 ; tau = c / (tau_pr_den + b*/2)
-    double bs[U][G], d[U][G], rd[U][G], ee[U][G];
+    // tau step, infer.py:118-121
+    double d[U][G], t1[U][G], rd[U][G], ee[U][G];
 #pragma unroll
     for (int u = 0; u < U; ++u)
 #pragma unroll
-        for (int g = 0; g < G; ++g) { d[u][g] = fma(x1r[g], m2w1[u], yv[u][g]); bs[u][g] = x2r[g] * w2[u]; }
+        for (int g = 0; g < G; ++g) {
+            d[u][g] = fma(x.x1[g], m2w1[u], yv[u][g]);
+            t1[u][g] = fma(x.x2[g], w2[u], pd[u][g]);
+            if (RELOAD) pd[u][g] = __ldg(pd_next + g * Lp + u * step);
+        }
 #pragma unroll
     for (int u = 0; u < U; ++u)
 #pragma unroll
-        for (int g = 0; g < G; ++g) bs[u][g] = fma(yv[u][g], d[u][g], bs[u][g]);
-#pragma unroll
-    for (int u = 0; u < U; ++u)
-#pragma unroll
-        for (int g = 0; g < G; ++g) d[u][g] = fma(0.5, bs[u][g], pd[u][g]);
+        for (int g = 0; g < G; ++g) d[u][g] = fma(yv[u][g], d[u][g], t1[u][g]);
 #pragma unroll
     for (int u = 0; u < U; ++u)
 #pragma unroll
@@ -222,13 +235,13 @@ __device__ __forceinline__ void em_sweep(const double* __restrict__ ys, const do
     for (int u = 0; u < U; ++u)
 #pragma unroll
         for (int g = 0; g < G; ++g)
-            if (!MASKED || u < U - 1 || valid) taus[g * L + l + u * step] = rd[u][g];
-    // bound (infer.py:123-125: tau*(y^2 + x2*w2 - 2*x1*w1*y) = tau*b*) and the next X step's row sums
+            if (!MASKED || u < U - 1 || valid) ths[g * L + l + u * step] = rd[u][g];
+    // bound (sum pd2*th = sum t1*th - x2*sum th*w2, the caller subtracts) and the next X step's row sums
 #pragma unroll
     for (int u = 0; u < U; ++u)
 #pragma unroll
         for (int g = 0; g < G; ++g) {
-            if (!MASKED || u < U - 1 || valid) ab[g] = fma(rd[u][g], bs[u][g], ab[g]);
+            if (!MASKED || u < U - 1 || valid) ab[g] = fma(t1[u][g], rd[u][g], ab[g]);
             yt[u][g] = yv[u][g] * rd[u][g];
         }
 #pragma unroll
@@ -248,8 +261,8 @@ __device__ __forceinline__ void em_sweep(const double* __restrict__ ys, const do
         }
 }
 
-// Guide efficacies as the sweep consumes them, and the sums it returns (register-passed structs).
-template <int G> struct EmX { double x1[G], x2[G]; };
+// The sums a pass returns (register-passed struct): a1 = sum_l y*th*w1, a2 = sum_l th*w2 per guide
+// (HALF the X-step sums) and ab = sum pd2*th.
 template <int G> struct EmSums { double a1[G], a2[G], ab; };
 
 // One EM pass over all lines of a warp.  Deliberately NOT inlined: compiled on its own, ptxas
@@ -258,10 +271,13 @@ template <int G> struct EmSums { double a1[G], a2[G], ab; };
 // The step plan is warp-uniform (no divergence): `n` = lines of the warp's fullest lane, taken
 // U at a time while more than U remain, then one final MASKED step of 1..U lines whose last line
 // is live only in the lanes with l < L.
+// pd2 lives in an L2-resident global slab [G][Lp] (read once per pass, never written after staging, so
+// it does not have to occupy shared memory); rows are padded (Lp >= L + U*STEP) so that the look-ahead
+// loads need no bounds logic.
 template <int G, int STEP, bool UNIT_C>
-__device__ __noinline__ EmSums<G> em_sweep_all(const double* ys, const double* tpdg, double* taus, double* w1p,
-                                               double* w2g, const int L, const int l0, const int n_warp,
-                                               const EmX<G> x, const double ivw, const double mw,
+__device__ __noinline__ EmSums<G> em_sweep_all(const double* ys, const double* tpdg, const int Lp, double* ths,
+                                               double* w1p, double* w2g, const int L, const int l0,
+                                               const int n_warp, const EmX<G> x, const double ivw, const double mw,
                                                const double c_tau) {
     double a1[G], a2[G], ab[G];
 #pragma unroll
@@ -269,48 +285,37 @@ __device__ __noinline__ EmSums<G> em_sweep_all(const double* ys, const double* t
     constexpr int U = (G >= 7) ? 2 : 4;       // lines per step: U*G >= 8 independent elements
     int l = l0;
     int n = n_warp;
-    // tau_pr_den lives in an L2-resident global slab (it is read once per pass and never written after
-    // staging, so it does not have to occupy shared memory): software-pipelined one step ahead.
-    double pdn[U][G];
+    double pd[U][G];
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-        const int lu = (l + u * STEP < L) ? l + u * STEP : 0;
+    for (int u = 0; u < U; ++u)
 #pragma unroll
-        for (int g = 0; g < G; ++g) pdn[u][g] = __ldg(tpdg + g * L + lu);
-    }
-    for (; n > U; n -= U, l += U * STEP) {
-        double pdc[U][G];
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const int lu = (l + (U + u) * STEP < L) ? l + (U + u) * STEP : 0;
-#pragma unroll
-            for (int g = 0; g < G; ++g) { pdc[u][g] = pdn[u][g]; pdn[u][g] = __ldg(tpdg + g * L + lu); }
-        }
-        em_sweep<G, U, U, UNIT_C, false>(ys, pdc, taus, w1p, w2g, L, l, STEP, x.x1, x.x2, ivw, mw, c_tau, a1, a2, ab, true);
-    }
+        for (int g = 0; g < G; ++g) pd[u][g] = __ldg(tpdg + g * Lp + l + u * STEP);
+    for (; n > U; n -= U, l += U * STEP)
+        em_sweep<G, U, U, UNIT_C, false, true>(ys, pd, tpdg + l + U * STEP, Lp, ths, w1p, w2g, L, l, STEP, x, ivw, mw, c_tau, a1, a2, ab, true);
     const bool valid = (l + (n - 1) * STEP) < L;
-    if (n == 1) em_sweep<G, 1, U, UNIT_C, true>(ys, pdn, taus, w1p, w2g, L, l, STEP, x.x1, x.x2, ivw, mw, c_tau, a1, a2, ab, valid);
-    else if (n == 2) em_sweep<G, 2, U, UNIT_C, true>(ys, pdn, taus, w1p, w2g, L, l, STEP, x.x1, x.x2, ivw, mw, c_tau, a1, a2, ab, valid);
-    else if (U == 4 && n == 3) em_sweep<G, (U == 4 ? 3 : 1), U, UNIT_C, true>(ys, pdn, taus, w1p, w2g, L, l, STEP, x.x1, x.x2, ivw, mw, c_tau, a1, a2, ab, valid);
-    else if (U == 4 && n == 4) em_sweep<G, (U == 4 ? 4 : 1), U, UNIT_C, true>(ys, pdn, taus, w1p, w2g, L, l, STEP, x.x1, x.x2, ivw, mw, c_tau, a1, a2, ab, valid);
+    if (n == 1) em_sweep<G, 1, U, UNIT_C, true, false>(ys, pd, nullptr, Lp, ths, w1p, w2g, L, l, STEP, x, ivw, mw, c_tau, a1, a2, ab, valid);
+    else if (n == 2) em_sweep<G, 2, U, UNIT_C, true, false>(ys, pd, nullptr, Lp, ths, w1p, w2g, L, l, STEP, x, ivw, mw, c_tau, a1, a2, ab, valid);
+    else if (U == 4 && n == 3) em_sweep<G, (U == 4 ? 3 : 1), U, UNIT_C, true, false>(ys, pd, nullptr, Lp, ths, w1p, w2g, L, l, STEP, x, ivw, mw, c_tau, a1, a2, ab, valid);
+    else if (U == 4 && n == 4) em_sweep<G, (U == 4 ? 4 : 1), U, UNIT_C, true, false>(ys, pd, nullptr, Lp, ths, w1p, w2g, L, l, STEP, x, ivw, mw, c_tau, a1, a2, ab, valid);
     EmSums<G> r;
-    r.ab = ab[0];
+    // sum pd2*th = sum (t1 - x2*w2)*th: the accumulators hold sum t1*th
+    r.ab = fma(-x.x2[0], a2[0], ab[0]);
 #pragma unroll
-    for (int g = 1; g < G; ++g) r.ab += ab[g];
+    for (int g = 1; g < G; ++g) r.ab += fma(-x.x2[g], a2[g], ab[g]);
 #pragma unroll
     for (int g = 0; g < G; ++g) { r.a1[g] = a1[g]; r.a2[g] = a2[g]; }
     return r;
 }
 
-// Stage a gene: y = test - ctrl (shared) and tau_pr_den (global slab) for the lane's lines, infer.py:58-70.
+// Stage a gene: y = test - ctrl (shared) and pd2 = 2*tau_pr_den (global slab) for the lane's lines, infer.py:58-70.
 // All G rows of a line batch are loaded before any is consumed (G*4 independent 16-byte loads in flight per
 // lane): staging is pure memory latency for a team that has only its own warps to hide it behind.
 // Not inlined (runs once per gene).  Returns true if a staged value is not finite.
 template <int G, int STEP>
 __device__ __noinline__ bool em_stage_gene(const double2* __restrict__ test, const double2* __restrict__ ctrl,
                                            const int* rows, double* __restrict__ ys, double* __restrict__ tpdg,
-                                           const int L, const int l0, const int ctrl_lines, const int rowmean_fill,
-                                           const double* fill, const double tps) {
+                                           const int L, const int Lp, const int l0, const int ctrl_lines,
+                                           const int rowmean_fill, const double* fill, const double tps) {
     bool bad = false;
     const double2* tr[G];
     const double2* cr[G];
@@ -346,10 +351,10 @@ __device__ __noinline__ bool em_stage_gene(const double2* __restrict__ test, con
                     double ce = c[b][g].y;
                     if (ce != ce) ce = (ctrl_lines == 1 && rowmean_fill) ? fill[g] : te;         // :63 / :68
                     const double yv = t[b][g].x - c[b][g].x;
-                    const double pd = tps * (te * te + ce * ce + 1e-2);
+                    const double pd = 2.0 * (tps * (te * te + ce * ce + 1e-2));   // pd2 = 2*tau_pr_den (exact)
                     bad |= !(fabs(yv) <= 1.79769313486231570e308) || !(pd <= 1.79769313486231570e308);
                     ys[g * L + l + b * STEP] = yv;
-                    tpdg[g * L + l + b * STEP] = pd;
+                    tpdg[g * Lp + l + b * STEP] = pd;
                 }
             }
         }
@@ -363,15 +368,19 @@ __host__ __device__ constexpr long long em_fast_smem_doubles(int G, int W, int L
     return 2LL * G * L + (long long)W * (2 * G + 1) * 33 + 2LL * W * (2 * G + 1);
 }
 
-// L2 prefetch of one guide row pair (test + control) of the gene a team will run next.
-__device__ __forceinline__ void prefetch_row_l2(const double2* tr, const double2* cr, int L, int ctrl_lines,
-                                                int tid, int nthreads) {
-    const char* pt = reinterpret_cast<const char*>(tr);
-    const int nbytes = L * 16;
-    for (int b = tid * 128; b < nbytes; b += nthreads * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(pt + b));
-    if (ctrl_lines > 1) {
-        const char* pc = reinterpret_cast<const char*>(cr);
-        for (int b = tid * 128; b < nbytes; b += nthreads * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(pc + b));
+// L2 prefetch of the G guide rows (test + control) of the gene a team will run next.  One rolled loop over
+// all (row, 128-byte chunk) pairs: this runs once per gene and must stay small in code.
+template <int G>
+__device__ __forceinline__ void prefetch_gene_l2(const double2* test, const double2* ctrl, const int* slot_rows, int L,
+                                                 int ctrl_lines, int tid, int nthreads) {
+    const int nchunk = (L * 16 + 127) >> 7;
+#pragma unroll 1
+    for (int i = tid; i < G * nchunk; i += nthreads) {
+        const int g = i / nchunk;
+        const long long row = slot_rows[g];
+        const int b = (i - g * nchunk) << 7;
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(test + row * L) + b));
+        if (ctrl_lines > 1) asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(ctrl + row * ctrl_lines) + b));
     }
 }
 
@@ -385,10 +394,11 @@ __global__ void __launch_bounds__(W * 32) em_fast_kernel(const EmLaunch a) {
     extern __shared__ double smem[];
     const int L = a.L;
     double* ys = smem;                       // [G][L]
-    double* taus = ys + (size_t)G * L;       // [G][L]
+    double* taus = ys + (size_t)G * L;       // [G][L]  th = tau/2 (see em_sweep)
     double* scr = taus + (size_t)G * L + (threadIdx.x >> 5) * (NV * 33);   // this warp's reduction tile
     double* red = taus + (size_t)G * L + W * (NV * 33);                    // [2][W][NV] totals
-    double* tpdg = a.tpd_scratch + (size_t)blockIdx.x * G * L;             // this team's tau_pr_den slab [G][L] (global, L2)
+    const int Lp = a.tpd_stride;
+    double* tpdg = a.tpd_scratch + (size_t)blockIdx.x * G * Lp;            // this team's pd2 slab [G][Lp] (global, L2)
     __shared__ int s_slot[2];
 
     const int lane = threadIdx.x & 31;
@@ -458,7 +468,7 @@ __global__ void __launch_bounds__(W * 32) em_fast_kernel(const EmLaunch a) {
                 }
             }
         }
-        const bool bad = em_stage_gene<G, STEP>(a.test, a.ctrl, rows, ys, tpdg, L, l0, a.ctrl_lines, a.ctrl_rowmean_fill, fill, tps);
+        const bool bad = em_stage_gene<G, STEP>(a.test, a.ctrl, rows, ys, tpdg, L, Lp, l0, a.ctrl_lines, a.ctrl_rowmean_fill, fill, tps);
         const int any_bad = (W == 1) ? __any_sync(JACKS_FULL_MASK, bad) : __syncthreads_or(bad);
         // the look-ahead atomic has landed by now: share it and start loading the next gene's index
         int nslot;
@@ -503,7 +513,7 @@ __global__ void __launch_bounds__(W * 32) em_fast_kernel(const EmLaunch a) {
                 const double w2 = w1 * w1;
 #pragma unroll
                 for (int g = 0; g < G; ++g) {
-                    const double t = tps * fast_rcp(tpdg[g * L + l]);
+                    const double t = tps * fast_rcp(tpdg[g * Lp + l]);      // th = tau/2 = tps/pd2, infer.py:83
                     taus[g * L + l] = t;
                     const double xw = x1r[g] * w1;
                     acc[2 * G] += t * (yv[g] * yv[g] + x2r[g] * w2 - 2.0 * xw * yv[g]);
@@ -514,19 +524,18 @@ __global__ void __launch_bounds__(W * 32) em_fast_kernel(const EmLaunch a) {
                 if (w2g) w2g[l] = w2;
             }
             team_allsum<NV, NV, W>(acc, scr, red, parity, warp, lane);
-            double bound = acc[2 * G];
+            // every sum was formed with th = tau/2: acc[0..2G) stay HALF sums (the X step doubles them in its
+            // first FMA), the bound is doubled here (exact)
+            double bound = 2.0 * acc[2 * G];
+            const double bound_k = 2.0 * c_tau * (double)(G * L);   // sum tau*b* = 2c*G*L - 2*sum pd2*th
             double mu0_w = a.mu0_w, var0_w = a.var0_w;
             double ivw = 1.0 / var0_w;              // infer.py:113
             double mw = mu0_w / var0_w;
             int iters = 0;
 
             // next gene: its index entries have arrived during the init sweep; pull its rows towards L2
-            if (nslot < a.n_work) {
-#pragma unroll
-                for (int g = 0; g < G; ++g)
-                    prefetch_row_l2(a.test + (long long)nrows[g] * L, a.ctrl + (long long)nrows[g] * a.ctrl_lines, L,
-                                    a.ctrl_lines, threadIdx.x, STEP);
-            }
+            if (nslot < a.n_work)
+                prefetch_gene_l2<G>(a.test, a.ctrl, a.slot_rows + (long long)nslot * G, L, a.ctrl_lines, threadIdx.x, STEP);
 
             // ---- EM passes (infer.py:89-98) ------------------------------------------------------
             for (int it = 0; it < a.n_iter; ++it) {
@@ -536,8 +545,8 @@ __global__ void __launch_bounds__(W * 32) em_fast_kernel(const EmLaunch a) {
                     double xu[G], x2u[G];
 #pragma unroll
                     for (int g = 0; g < G; ++g) {
-                        const double rden = fast_rcp(acc[G + g] + ivx);
-                        xu[g] = (mx + acc[g]) * rden;
+                        const double rden = fast_rcp(fma(2.0, acc[G + g], ivx));
+                        xu[g] = fma(2.0, acc[g], mx) * rden;
                         x2u[g] = fma(xu[g], xu[g], rden);
                     }
                     double sum = xu[0], hi = xu[0], lo = xu[0];
@@ -567,14 +576,17 @@ __global__ void __launch_bounds__(W * 32) em_fast_kernel(const EmLaunch a) {
                 {
                     EmX<G> xv;
 #pragma unroll
-                    for (int g = 0; g < G; ++g) { xv.x1[g] = x1r[g]; xv.x2[g] = x2r[g]; }
-                    const EmSums<G> r = em_sweep_all<G, STEP, UNIT_C>(ys, tpdg, taus, w1g, w2g, L, l0, n_warp, xv, ivw, mw, c_tau);
+                    for (int g = 0; g < G; ++g) {
+                        xv.x1[g] = x1r[g]; xv.x2[g] = x2r[g];
+                        xv.tx1[g] = 2.0 * x1r[g]; xv.tx2[g] = 2.0 * x2r[g];
+                    }
+                    const EmSums<G> r = em_sweep_all<G, STEP, UNIT_C>(ys, tpdg, Lp, taus, w1g, w2g, L, l0, n_warp, xv, ivw, mw, c_tau);
 #pragma unroll
                     for (int g = 0; g < G; ++g) { acc[g] = r.a1[g]; acc[G + g] = r.a2[g]; }
                     acc[2 * G] = r.ab;
                 }
                 team_allsum<NV, NV, W>(acc, scr, red, parity, warp, lane);
-                bound = acc[2 * G];
+                bound = fma(-2.0, acc[2 * G], bound_k);
                 ++iters;
                 if (fabs(last - bound) < a.tol) break;
             }
@@ -583,7 +595,7 @@ __global__ void __launch_bounds__(W * 32) em_fast_kernel(const EmLaunch a) {
             for (int l = l0; l < L; l += STEP) {
                 if (a.tau) {
 #pragma unroll
-                    for (int g = 0; g < G; ++g) a.tau[(off + g) * L + l] = taus[g * L + l];
+                    for (int g = 0; g < G; ++g) a.tau[(off + g) * L + l] = 2.0 * taus[g * L + l];
                 }
                 if (a.y) {
 #pragma unroll
