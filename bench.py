@@ -188,6 +188,39 @@ def ncu_traffic():
         return None
 
 
+def lines_measurement(ctx, torch, dev, stream, w, params):
+    """Per-line ("single JACKS") mode on the real genes of the workload, device resident: 18,000 genes x 400 lines =
+    7.2 M independent one-line EMs per launch set (run_JACKS_single.py:83-85 makes 400 inferJACKS calls for this)."""
+    from jacks_b200 import _native
+    offs, rows = w['offs'], w['rows']
+    N, L = w['test'].shape[0], w['test'].shape[1]
+    n = len(offs) - 1
+    d_test = torch.from_numpy(w['test']).to(dev)
+    d_ctrl = torch.from_numpy(w['ctrl']).to(dev)
+    o_w1 = torch.empty((n, L), dtype=torch.float64, device=dev)
+    o_w2 = torch.empty((n, L), dtype=torch.float64, device=dev)
+    o_it = torch.empty((n, L), dtype=torch.int32, device=dev)
+    plan = _native.EmPlan(ctx, offs, rows, N, L)
+    io = _native.EmDeviceIO()
+    io.test, io.ctrl, io.ctrl_lines = d_test.data_ptr(), d_ctrl.data_ptr(), L
+    io.w1, io.w2, io.n_iters = o_w1.data_ptr(), o_w2.data_ptr(), o_it.data_ptr()
+    for _ in range(2):
+        plan.run_lines_device(params, io, stream)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(5):
+        plan.run_lines_device(params, io, stream)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 5
+    it = o_it.cpu().numpy()
+    plan.close()
+    return {'ms': ms, 'value': n * L / (ms * 1e-3), 'unit': 'one-line gene-inferences/s', 'mean_iters': float(it.mean()),
+            'shape': '%d genes x %d lines, device resident' % (n, L),
+            'hbm_gbs': 2.0 * N * L * 16 / (ms * 1e-3) / 1e9}
+
+
 def aux_measurements(ctx, torch, dev, stream, L):
     """The other two subsystems of the hot path at the BASELINE shape, device resident where the C-ABI has a device
     entry point: KDE p-values (18,000 genes x L lines against 1e5 pseudo-genes) and the preprocessing error model
@@ -402,6 +435,8 @@ def main():
     aux = None
     if rank == 0 and world == 1:
         aux = aux_measurements(ctx, torch, dev, stream, L)
+        del d_test, d_ctrl, o_w1, o_w2
+        aux['em_lines'] = lines_measurement(ctx, torch, dev, stream, w, params)
     if rank == 0:
         peaks = {}
         try:

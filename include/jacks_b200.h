@@ -13,6 +13,8 @@
  *   jacks/jacks/infer.py:18   inferJACKS (gene loop)           jacks_em_plan_create + jacks_em_run_device,
  *   jacks/jacks/infer.py:55   inferJACKSGene (per-gene EM)     jacks_em_batched_host
  *   jacks/jacks/jacks_io.py:416  pseudo-gene EM                same, with a row-gather CSR index
+ *   2018_paper_materials/scripts/jacks/run_JACKS_single.py:83-85
+ *                             per-line inferJACKS loop        jacks_em_lines_device / jacks_em_lines_host
  *   jacks/jacks/jacks_io.py:69   computeW1PvalsAndFDRs         jacks_kde_pvalues_device / _host
  *   jacks/jacks/preprocess.py:77 normalizeLogCounts            jacks_normalize_host
  *   jacks/jacks/preprocess.py:61 condense_normalised_counts    jacks_condense_host
@@ -164,6 +166,23 @@ enum { JACKS_KEEP_RESIDENT = 1, JACKS_ASYNC = 2 };
 JACKS_API int jacks_em_batched_host(JacksCtx* ctx, const JacksEmParams* params,
                           const int64_t* gene_offsets, const int32_t* guide_rows, int64_t n_genes,
                           const JacksEmHostIO* io, int32_t flags);
+
+/*
+ * Per-line ("single JACKS") inference: the reference's
+ *     for ts in range(L): inferJACKS(gene_index, testdata[:,[ts],:], ctrldata[:,[ts],:], ...)
+ * (2018_paper_materials/scripts/jacks/run_JACKS_single.py:83-85, :92-94) in one launch set -- every (gene, line)
+ * pair is an independent EM over that line alone (L = 1: infer.py:55-125; the hierarchical prior of infer.py:92
+ * never applies).  Same structs as the joint run; the control must be matched (ctrl_lines == L) and the outputs
+ * gain a line axis:
+ *     w1, w2, bound [n_genes, L] (double), n_iters [n_genes, L] (int32), x1, x2, y, tau [sum G, L].
+ * Column ts of every output equals what the reference's ts-th inferJACKS call returns.
+ * The host variant honours JACKS_KEEP_RESIDENT and reuses resident cubes when test == NULL; it is synchronous.
+ */
+JACKS_API int jacks_em_lines_device(JacksCtx* ctx, const JacksEmPlan* plan, const JacksEmParams* params,
+                          const JacksEmDeviceIO* io, void* stream);
+JACKS_API int jacks_em_lines_host(JacksCtx* ctx, const JacksEmParams* params,
+                        const int64_t* gene_offsets, const int32_t* guide_rows, int64_t n_genes,
+                        const JacksEmHostIO* io, int32_t flags);
 
 /*
  * KDE p-values of gene effects against the pseudo-gene null (computeW1PvalsAndFDRs with pseudo=True,

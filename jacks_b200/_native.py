@@ -81,6 +81,8 @@ def lib():
         L.jacks_em_plan_destroy.restype = None
         L.jacks_em_run_device.argtypes = [vp, vp, C.POINTER(EmParams), C.POINTER(EmDeviceIO), vp]
         L.jacks_em_batched_host.argtypes = [vp, C.POINTER(EmParams), vp, vp, i64, C.POINTER(EmHostIO), i32]
+        L.jacks_em_lines_device.argtypes = [vp, vp, C.POINTER(EmParams), C.POINTER(EmDeviceIO), vp]
+        L.jacks_em_lines_host.argtypes = [vp, C.POINTER(EmParams), vp, vp, i64, C.POINTER(EmHostIO), i32]
         L.jacks_fp64_peak_flops.argtypes = [vp, C.POINTER(dbl), C.POINTER(dbl)]
         if hasattr(L, 'jacks_kde_pvalues_device'):
             L.jacks_kde_pvalues_device.argtypes = [vp, vp, i64, vp, i64, i32, i32, vp, vp]
@@ -234,6 +236,10 @@ class EmPlan(object):
         """Enqueue the batched EM on `stream` (an int cudaStream_t handle); io is an EmDeviceIO of device pointers."""
         check(lib().jacks_em_run_device(self.ctx.h, self.h, C.byref(params), C.byref(io), C.c_void_p(stream or None)))
 
+    def run_lines_device(self, params, io, stream=0):
+        """Enqueue the per-line EM (jacks_em_lines_device): outputs carry a line axis, see em_lines_host."""
+        check(lib().jacks_em_lines_device(self.ctx.h, self.h, C.byref(params), C.byref(io), C.c_void_p(stream or None)))
+
 
 def em_batched_host(ctx, offsets, rows, test, ctrl, params=None, fixed_x1=None, fixed_x2=None,
                     want=('x1', 'x2', 'w1', 'w2', 'y', 'tau', 'n_iters', 'bound'), ctrl_rowmean_fill=False,
@@ -282,6 +288,44 @@ def em_batched_host(ctx, offsets, rows, test, ctrl, params=None, fixed_x1=None, 
     if not sync:
         # the C side reads these host arrays until ctx.synchronize(): keep them alive with the result
         res['_keepalive'] = (offsets, rows, test, ctrl, fixed_x1, fixed_x2, params)
+    return res
+
+
+def em_lines_host(ctx, offsets, rows, test, ctrl, params=None, fixed_x1=None, fixed_x2=None,
+                  want=('x1', 'x2', 'w1', 'w2', 'y', 'tau', 'n_iters', 'bound'), keep_resident=False,
+                  n_rows=None, n_lines=None):
+    """jacks_em_lines_host: every (gene, line) pair as an independent one-line EM (run_JACKS_single.py:83-85).
+    test, ctrl [N,L,2] (matched), or test=None to reuse resident cubes.  Outputs carry a line axis:
+    w1, w2, bound, n_iters [n_genes, L]; x1, x2, y, tau [sum G, L]."""
+    params = params or default_params()
+    offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+    rows = np.asarray(rows)
+    if test is not None:
+        test = np.ascontiguousarray(test, dtype=np.float64)
+        ctrl = np.ascontiguousarray(ctrl, dtype=np.float64)
+        if test.ndim != 3 or test.shape[2] != 2 or ctrl.shape != test.shape:
+            raise JacksError(JACKS_E_SHAPE, 'Expecting matched size between control and test data')
+        n_rows, n_lines = test.shape[0], test.shape[1]
+    if rows.size and (rows.min() < 0 or rows.max() >= n_rows):
+        raise IndexError('guide row index out of bounds for %d rows' % n_rows)
+    rows = np.ascontiguousarray(rows, dtype=np.int32)
+    n_genes = len(offsets) - 1
+    T = int(offsets[-1]) if n_genes > 0 else 0
+    per = dict(x1=T, x2=T, w1=n_genes, w2=n_genes, y=T, tau=T, n_iters=n_genes, bound=n_genes)
+    res = {k: np.empty((per[k], n_lines), dtype=np.int32 if k == 'n_iters' else np.float64) for k in set(want) | {'w1'}}
+    io = EmHostIO()
+    io.test, io.ctrl = _ptr(test), _ptr(ctrl)
+    io.n_rows, io.n_lines, io.ctrl_lines = int(n_rows), int(n_lines), int(n_lines)
+    if fixed_x1 is not None:
+        fixed_x1 = np.ascontiguousarray(fixed_x1, dtype=np.float64)
+        fixed_x2 = np.ascontiguousarray(fixed_x2, dtype=np.float64)
+        if fixed_x1.shape != (n_rows,) or fixed_x2.shape != (n_rows,):
+            raise JacksError(JACKS_E_INVALID, 'fixed_x arrays must have one entry per data row')
+        io.fixed_x1, io.fixed_x2 = _ptr(fixed_x1), _ptr(fixed_x2)
+    for k in res:
+        setattr(io, k, _ptr(res[k]))
+    check(lib().jacks_em_lines_host(ctx.h, C.byref(params), _ptr(offsets), _ptr(rows), n_genes, C.byref(io),
+                                    1 if keep_resident else 0))
     return res
 
 

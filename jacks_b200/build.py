@@ -21,7 +21,7 @@ ARCH = ['-gencode', 'arch=compute_100a,code=sm_100a']
 FLAGS = ['-O3', '-std=c++17', '-lineinfo', '-Xcompiler', '-fPIC,-fvisibility=hidden']
 FAST_G = list(range(1, 9))
 
-UNITS = [('capi.cu', 'capi.o', []), ('em_dispatch.cu', 'em_dispatch.o', []), ('em_generic.cu', 'em_generic.o', []),
+UNITS = [('capi.cu', 'capi.o', []), ('em_dispatch.cu', 'em_dispatch.o', []), ('em_generic.cu', 'em_generic.o', []), ('em_lines.cu', 'em_lines.o', []),
          ('fp64_probe.cu', 'fp64_probe.o', []), ('kde_pvalues.cu', 'kde_pvalues.o', []),
          ('preprocess_kernels.cu', 'preprocess_kernels.o', []), ('host_io.cpp', 'host_io.o', ['-x', 'cu'])] + \
         [('em_fast_inst.cu', 'em_fast_g%d.o' % g, ['-DJACKS_G=%d' % g]) for g in FAST_G]

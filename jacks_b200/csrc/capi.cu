@@ -522,4 +522,154 @@ int jacks_em_batched_host(JacksCtx* ctx, const JacksEmParams* params, const int6
     return rc;
 }
 
+// ---- per-line ("single JACKS") inference ----------------------------------------------------------------------------
+
+// Enqueue the per-line EM of every (gene, line) pair of the plan on `st`.
+static int em_lines_run(JacksCtx* ctx, const JacksEmPlan* plan, const JacksEmParams* params, const JacksEmDeviceIO* io,
+                        cudaStream_t st) {
+    const int L = plan->L;
+    if ((long long)plan->n_genes * L >= (1LL << 31)) return fail(JACKS_E_INVALID, "per-line run: n_genes * L must stay below 2^31");
+    cudaError_t e;
+    int rc;
+    // the deferred queue holds (gene, line) pairs here: one slot per problem of the fast buckets
+    if ((rc = plan->b->d_deferred.reserve((size_t)std::max<int64_t>(plan->n_genes * L, 1) * sizeof(int))) != JACKS_OK) return rc;
+    if ((e = cudaMemsetAsync(plan->b->d_counters.p, 0, kCountersPerRange * sizeof(int), st)) != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync");
+    int* counters = (int*)plan->b->d_counters.p;
+    EmLaunch a;
+    memset(&a, 0, sizeof a);
+    a.test = (const double2*)io->test; a.ctrl = (const double2*)io->ctrl;
+    a.L = L; a.ctrl_lines = io->ctrl_lines; a.ctrl_rowmean_fill = 0;
+    a.gene_offsets = (const long long*)plan->b->d_offsets.p; a.guide_rows = (const int*)plan->b->d_rows.p;
+    a.fixed_x1 = io->fixed_x1; a.fixed_x2 = io->fixed_x2;
+    a.x1 = io->x1; a.x2 = io->x2; a.w1 = io->w1; a.w2 = io->w2; a.y = io->y; a.tau = io->tau;
+    a.n_iters = io->n_iters; a.bound = io->bound;
+    a.deferred_ids = (int*)plan->b->d_deferred.p; a.deferred_count = counters;
+    a.n_iter = params->n_iter; a.apply_w_hp = 0; a.tol = params->tol;      // infer.py:92 needs L > 1
+    a.mu0_x = params->mu0_x; a.var0_x = params->var0_x; a.mu0_w = params->mu0_w; a.var0_w = params->var0_w;
+    a.tps = params->tau_prior_strength;
+    a.L_full = L;
+    int slot = 1;
+    int64_t n_fast = 0;
+    for (const EmBucket& b : plan->fast) {
+        a.gene_ids = (const int*)plan->b->d_ids.p + b.ids_off;
+        a.slot_off = (const long long*)plan->b->d_slot_off.p + b.ids_off;
+        a.slot_rows = (const int*)plan->b->d_slot_rows.p + b.rows_off;
+        a.n_work = b.n; a.n_work_dev = nullptr;
+        e = launch_em_lines(b.G, a, ctx->n_sm, st);
+        if (e != cudaSuccess) return cuda_fail(e, "em_lines_kernel launch");
+        ctx->launches++;
+        n_fast += b.n;
+    }
+    // NaN-safe warp-per-problem kernel on one-line views: genes with G > 8, then the problems handed back
+    a.L = 1;
+    a.scratch = (double*)plan->b->d_scratch.p;
+    EmGenericConfig cfg;
+    if (plan->generic.n > 0) {
+        if ((e = em_generic_configure(plan->generic_maxG, 1, (long long)plan->generic.n * L, ctx->n_sm, &cfg)) != cudaSuccess) return cuda_fail(e, "em_generic_configure");
+        if (cfg.scratch_doubles_per_warp > 0 &&
+            (rc = plan->b->d_scratch.reserve((size_t)cfg.scratch_doubles_per_warp * cfg.grid * cfg.warps_per_cta * sizeof(double))) != JACKS_OK) return rc;
+        a.scratch = (double*)plan->b->d_scratch.p;
+        a.lines_mode = 1;
+        a.gene_ids = (const int*)plan->b->d_ids.p + plan->generic.ids_off;
+        a.n_work = plan->generic.n; a.n_work_dev = nullptr;
+        a.work_counter = counters + slot++;
+        a.scratch_stride = cfg.scratch_doubles_per_warp;
+        if ((e = launch_em_generic(cfg, a, st)) != cudaSuccess) return cuda_fail(e, "em_generic_kernel (lines) launch");
+        ctx->launches++;
+    }
+    if (n_fast > 0) {
+        if ((e = em_generic_configure(plan->fast_maxG, 1, n_fast * L, ctx->n_sm, &cfg)) != cudaSuccess) return cuda_fail(e, "em_generic_configure");
+        a.lines_mode = 2;
+        a.gene_ids = (const int*)plan->b->d_deferred.p;
+        a.n_work = (int)(n_fast * L); a.n_work_dev = counters;
+        a.work_counter = counters + slot++;
+        a.scratch_stride = cfg.scratch_doubles_per_warp;      // 0: G <= 8 with one line always fits shared memory
+        if ((e = launch_em_generic(cfg, a, st)) != cudaSuccess) return cuda_fail(e, "em_generic_kernel (lines, deferred) launch");
+        ctx->launches++;
+    }
+    return JACKS_OK;
+}
+
+int jacks_em_lines_device(JacksCtx* ctx, const JacksEmPlan* plan, const JacksEmParams* params,
+                          const JacksEmDeviceIO* io, void* stream) {
+    if (!ctx || !plan || !params || !io) return fail(JACKS_E_INVALID, "jacks_em_lines_device: NULL argument");
+    if (plan->n_genes == 0) return JACKS_OK;
+    int rc = em_check_io(plan, params, io);
+    if (rc != JACKS_OK) return rc;
+    if (io->ctrl_lines != plan->L) return fail(JACKS_E_SHAPE, "Expecting matched size between control and test data");   // infer.py:26
+    cudaError_t e = cudaSetDevice(ctx->device);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaSetDevice");
+    return em_lines_run(ctx, plan, params, io, (cudaStream_t)stream);
+}
+
+int jacks_em_lines_host(JacksCtx* ctx, const JacksEmParams* params, const int64_t* gene_offsets,
+                        const int32_t* guide_rows, int64_t n_genes, const JacksEmHostIO* io, int32_t flags) {
+    if (!ctx || !params || !io) return fail(JACKS_E_INVALID, "jacks_em_lines_host: NULL argument");
+    const int64_t N = io->n_rows;
+    const int L = io->n_lines;
+    if (N < 0 || L < 1) return fail(JACKS_E_INVALID, "bad data shape N=%lld L=%d", (long long)N, L);
+    if (io->ctrl_lines != L) return fail(JACKS_E_SHAPE, "Expecting matched size between control and test data");
+    cudaError_t e = cudaSetDevice(ctx->device);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaSetDevice");
+    int rc = jacks_ctx_synchronize(ctx);          // this entry point is synchronous: drain earlier async calls first
+    if (rc != JACKS_OK) return rc;
+    cudaStream_t st = ctx->stream;
+    const size_t cube = (size_t)N * L * 2 * sizeof(double);
+    if (io->test) {
+        if (!io->ctrl) return fail(JACKS_E_INVALID, "ctrl is NULL");
+        if ((rc = ctx->res_test.reserve(cube ? cube : 8)) != JACKS_OK) return rc;
+        if ((rc = ctx->res_ctrl.reserve(cube ? cube : 8)) != JACKS_OK) return rc;
+        ctx->res_N = N; ctx->res_L = L; ctx->res_ctrl_lines = L; ctx->res_valid = true;
+        if (cube) {
+            if ((e = cudaMemcpyAsync(ctx->res_test.p, io->test, cube, cudaMemcpyHostToDevice, st)) != cudaSuccess) return cuda_fail(e, "H2D test");
+            if ((e = cudaMemcpyAsync(ctx->res_ctrl.p, io->ctrl, cube, cudaMemcpyHostToDevice, st)) != cudaSuccess) return cuda_fail(e, "H2D ctrl");
+        }
+    } else if (!ctx->res_valid || ctx->res_N != N || ctx->res_L != L || ctx->res_ctrl_lines != L) {
+        return fail(JACKS_E_INVALID, "test is NULL but no matching resident data cube (call with keep_resident first)");
+    }
+    const double* d_fx1 = nullptr; const double* d_fx2 = nullptr;
+    if (io->fixed_x1 || io->fixed_x2) {
+        if (!io->fixed_x1 || !io->fixed_x2) return fail(JACKS_E_INVALID, "fixed_x1 and fixed_x2 go together");
+        if ((rc = ctx->res_fx.reserve((size_t)N * 2 * sizeof(double) + 8)) != JACKS_OK) return rc;
+        if (N) {
+            if ((e = cudaMemcpyAsync(ctx->res_fx.p, io->fixed_x1, (size_t)N * sizeof(double), cudaMemcpyHostToDevice, st)) != cudaSuccess) return cuda_fail(e, "H2D fixed_x1");
+            if ((e = cudaMemcpyAsync((double*)ctx->res_fx.p + N, io->fixed_x2, (size_t)N * sizeof(double), cudaMemcpyHostToDevice, st)) != cudaSuccess) return cuda_fail(e, "H2D fixed_x2");
+        }
+        d_fx1 = (const double*)ctx->res_fx.p; d_fx2 = d_fx1 + N;
+    }
+    if (!io->w1 && n_genes) return fail(JACKS_E_INVALID, "w1 is required");
+    JacksEmPlan* plan = nullptr;
+    if ((rc = jacks_em_plan_create(ctx, gene_offsets, guide_rows, n_genes, N, L, &plan)) != JACKS_OK) return rc;
+    const int64_t T = plan->total_guides;
+    // every output has L entries per gene or per guide
+    struct Out { char* host; size_t unit; bool per_guide; } outs[8] = {
+        {(char*)io->x1, sizeof(double), true},  {(char*)io->x2, sizeof(double), true},
+        {(char*)io->w1, sizeof(double), false}, {(char*)io->w2, sizeof(double), false},
+        {(char*)io->y, sizeof(double), true},   {(char*)io->tau, sizeof(double), true},
+        {(char*)io->n_iters, sizeof(int32_t), false}, {(char*)io->bound, sizeof(double), false}};
+    char* dptr[8] = {nullptr};
+    size_t nbytes[8] = {0};
+    for (int i = 0; i < 8 && rc == JACKS_OK; ++i) {
+        nbytes[i] = outs[i].unit * (size_t)L * (size_t)(outs[i].per_guide ? T : n_genes);
+        if (!outs[i].host || !nbytes[i]) continue;
+        if ((rc = plan->b->out[i].reserve(nbytes[i])) == JACKS_OK) dptr[i] = (char*)plan->b->out[i].p;
+    }
+    if (rc == JACKS_OK && n_genes > 0) {
+        JacksEmDeviceIO dio;
+        memset(&dio, 0, sizeof dio);
+        dio.test = (const double*)ctx->res_test.p; dio.ctrl = (const double*)ctx->res_ctrl.p;
+        dio.ctrl_lines = L;
+        dio.fixed_x1 = d_fx1; dio.fixed_x2 = d_fx2;
+        dio.x1 = (double*)dptr[0]; dio.x2 = (double*)dptr[1]; dio.w1 = (double*)dptr[2]; dio.w2 = (double*)dptr[3];
+        dio.y = (double*)dptr[4]; dio.tau = (double*)dptr[5]; dio.n_iters = (int32_t*)dptr[6]; dio.bound = (double*)dptr[7];
+        if ((rc = em_check_io(plan, params, &dio)) == JACKS_OK) rc = em_lines_run(ctx, plan, params, &dio, st);
+        for (int i = 0; i < 8 && rc == JACKS_OK; ++i)
+            if (dptr[i] && (e = cudaMemcpyAsync(outs[i].host, dptr[i], nbytes[i], cudaMemcpyDeviceToHost, st)) != cudaSuccess) rc = cuda_fail(e, "D2H result");
+    }
+    ctx->pending_plans.push_back(plan);
+    if (!(flags & JACKS_KEEP_RESIDENT)) ctx->res_valid = false;
+    const int rs = jacks_ctx_synchronize(ctx);
+    return rc != JACKS_OK ? rc : rs;
+}
+
 }  // extern "C"

@@ -42,6 +42,12 @@ struct EmLaunch {
     double* tpd_scratch; int tpd_stride;
     // generic kernel only: global scratch when a gene's working set exceeds shared memory
     double* scratch; long long scratch_stride;   // doubles per warp
+    // Per-line mode (every (gene, line) pair an independent EM with one line; run_JACKS_single.py:83-85).
+    // The cubes keep their L_full lines per row; outputs gain a line axis: w1, w2, n_iters, bound
+    // [n_genes][L_full]; x1, x2, y, tau [sum G][L_full].  lines_mode 0: off (joint run over all lines);
+    // 1: work item w is (bucket slot w / L_full, line w % L_full); 2: gene_ids[] holds gene*L_full + line
+    // (the deferred queue of the per-line kernels).  In the generic kernel L is 1 in modes 1 and 2.
+    int lines_mode; int L_full;
 };
 
 // Fast path: compile-time guide count G (1..8), W (1, 2 or 4) warps per gene, finite data only.
@@ -58,6 +64,10 @@ constexpr size_t kMaxDynSmem = 227 * 1024 - 64;
 inline int em_fast_tpd_stride(int L) { return ((L + 15) / 16) * 16 + 512; }
 // Upper bound on resident fast-kernel CTAs per SM the plan provisions tau_pr_den slabs for.
 constexpr int kMaxFastCtasPerSm = 12;
+
+// Per-line fast path: one LANE per (gene, line) problem of a G-guide bucket (G 1..8), finite data only;
+// problems holding NaN/inf go to the deferred queue as gene*L + line.  `a.L` is the cubes' line count.
+cudaError_t launch_em_lines(int G, const EmLaunch& a, int n_sm, cudaStream_t st);
 
 // Generic path: any G and L, NaN-safe, one warp per gene, working set in shared memory when it
 // fits and in `scratch` (EmLaunch::scratch, one slab per warp of the grid) otherwise.

@@ -56,14 +56,17 @@ __global__ void __launch_bounds__(256) em_generic_kernel(const EmLaunch a, const
     extern __shared__ double smem[];
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
-    const int L = a.L;
+    // per-line mode (em_common.cuh): one line of the cubes per work item, outputs carry a line axis
+    const int L = a.lines_mode ? 1 : a.L;
+    const long long row_stride = a.lines_mode ? a.L_full : a.L;      // lines per cube / output row
     const long long Lp = ((long long)L + 31) / 32 * 32;
     const double tps = a.tps;
     const double c_tau = a.tps + 0.5;
     const double ivx = 1.0 / a.var0_x;
     const double mx = a.mu0_x / a.var0_x;
     const bool fixed = (a.fixed_x1 != nullptr);
-    const int n_work = a.n_work_dev ? *a.n_work_dev : a.n_work;
+    const long long n_work = (a.n_work_dev ? (long long)*a.n_work_dev : (long long)a.n_work) *
+                             (a.lines_mode == 1 ? a.L_full : 1);
     const long long gwarp = (long long)blockIdx.x * warps_per_cta + warp;
 
     for (;;) {
@@ -71,7 +74,10 @@ __global__ void __launch_bounds__(256) em_generic_kernel(const EmLaunch a, const
         if (lane == 0) slot = atomicAdd(a.work_counter, 1);
         slot = __shfl_sync(JACKS_FULL_MASK, slot, 0);
         if (slot >= n_work) break;
-        const int gid = a.gene_ids[slot];
+        int gid, line = 0;
+        if (a.lines_mode == 1) { const int s = slot / a.L_full; line = slot - s * a.L_full; gid = a.gene_ids[s]; }
+        else if (a.lines_mode == 2) { const int pid = a.gene_ids[slot]; gid = pid / a.L_full; line = pid - gid * a.L_full; }
+        else gid = a.gene_ids[slot];
         const long long off = a.gene_offsets[gid];
         const int G = (int)(a.gene_offsets[gid + 1] - off);
 
@@ -91,8 +97,8 @@ __global__ void __launch_bounds__(256) em_generic_kernel(const EmLaunch a, const
         // ---- set-up, infer.py:58-70 ----------------------------------------------------------
         for (int g = 0; g < G; ++g) {
             const int row = a.guide_rows[off + g];
-            const double2* tr = a.test + (long long)row * L;
-            const double2* cr = a.ctrl + (long long)row * a.ctrl_lines;
+            const double2* tr = a.test + (long long)row * row_stride + line;
+            const double2* cr = a.ctrl + (long long)row * a.ctrl_lines + (a.ctrl_lines == 1 ? 0 : line);
             double2 c0 = make_double2(0.0, 0.0);
             double fill = 0.0;
             if (a.ctrl_lines == 1) {
@@ -256,23 +262,25 @@ __global__ void __launch_bounds__(256) em_generic_kernel(const EmLaunch a, const
 
         // ---- results ---------------------------------------------------------------------------
         for (int l = lane; l < L; l += 32) {
-            a.w1[(long long)gid * L + l] = w1s[l];
-            if (a.w2) a.w2[(long long)gid * L + l] = w2s[l];
+            a.w1[(long long)gid * row_stride + line + l] = w1s[l];
+            if (a.w2) a.w2[(long long)gid * row_stride + line + l] = w2s[l];
         }
         if (a.tau || a.y) {
             for (int g = 0; g < G; ++g)
                 for (int l = lane; l < L; l += 32) {
-                    if (a.tau) a.tau[(off + g) * L + l] = taus[g * Lp + l];
-                    if (a.y) a.y[(off + g) * L + l] = ys[g * Lp + l];
+                    if (a.tau) a.tau[(off + g) * row_stride + line + l] = taus[g * Lp + l];
+                    if (a.y) a.y[(off + g) * row_stride + line + l] = ys[g * Lp + l];
                 }
         }
         for (int g = lane; g < G; g += 32) {
-            if (a.x1) a.x1[off + g] = x1s[g];
-            if (a.x2) a.x2[off + g] = x2s[g];
+            const long long q = a.lines_mode ? (off + g) * row_stride + line : off + g;
+            if (a.x1) a.x1[q] = x1s[g];
+            if (a.x2) a.x2[q] = x2s[g];
         }
         if (lane == 0) {
-            if (a.n_iters) a.n_iters[gid] = iters;
-            if (a.bound) a.bound[gid] = bound;
+            const long long q = a.lines_mode ? (long long)gid * row_stride + line : gid;
+            if (a.n_iters) a.n_iters[q] = iters;
+            if (a.bound) a.bound[q] = bound;
         }
         __syncwarp();
     }

@@ -34,19 +34,24 @@ def _pack(res, n_local, t_local, L):
                            res['n_iters'].astype(np.float64).reshape(-1)]).astype(np.float64), (n_local, t_local, L)
 
 
-def _unpack(buf, n_local, t_local, L):
+def _unpack(buf, n_local, t_local, L, per_line=False):
+    """per_line: the per-line mode's outputs carry a line axis on x1, x2 and n_iters as well."""
     o = 0
     out = {}
-    for key, size, shape in (('w1', n_local * L, (n_local, L)), ('w2', n_local * L, (n_local, L)), ('x1', t_local, (t_local,)),
-                             ('x2', t_local, (t_local,)), ('n_iters', n_local, (n_local,))):
+    K = L if per_line else 1
+    xs, its = ((t_local, L), (n_local, L)) if per_line else ((t_local,), (n_local,))
+    for key, size, shape in (('w1', n_local * L, (n_local, L)), ('w2', n_local * L, (n_local, L)), ('x1', t_local * K, xs),
+                             ('x2', t_local * K, xs), ('n_iters', n_local * K, its)):
         out[key] = buf[o:o + size].reshape(shape)
         o += size
     out['n_iters'] = out['n_iters'].astype(np.int32)
     return out
 
 
-def infer_sharded(offsets, rows, testdata, ctrldata, compute=None, group=None, device=None, **em_kwargs):
+def infer_sharded(offsets, rows, testdata, ctrldata, compute=None, group=None, device=None, per_line=False, **em_kwargs):
     """Batched EM of the whole gene index, sharded by gene over the ranks of ``group`` (default: WORLD).
+    per_line: run the per-line ("single JACKS") mode instead of the joint one -- the batch driver of the paper
+    scripts (jacks_b200/paper_modes.py); x1, x2 and n_iters then carry a line axis.
 
     ``compute(offsets, rows, testdata, ctrldata, **em_kwargs) -> dict(w1, w2, x1, x2, n_iters)`` runs one shard;
     by default the GPU path of this rank (jacks_b200.infer.infer_batched on ``device``).  Returns the gathered
@@ -60,20 +65,24 @@ def infer_sharded(offsets, rows, testdata, ctrldata, compute=None, group=None, d
     lo, hi = int(b[rank]), int(b[rank + 1])
     loffs, lrows = local_index(offsets, rows, lo, hi)
     if compute is None:
-        from . import infer
+        from . import infer, _native
 
         def compute(o, r, t, c, **kw):
+            if per_line:
+                return _native.em_lines_host(_native.context(device or 0), o, r, t, c, want=('x1', 'x2', 'w1', 'w2', 'n_iters'), **kw)
             return infer.infer_batched(o, r, t, c, want=('x1', 'x2', 'w1', 'w2'), device=device or 0, **kw)
     L = int(np.asarray(testdata).shape[1])
+    K = L if per_line else 1
     if hi > lo:
         res = compute(loffs, lrows, testdata, ctrldata, **em_kwargs)
     else:
-        res = dict(w1=np.zeros((0, L)), w2=np.zeros((0, L)), x1=np.zeros(0), x2=np.zeros(0), n_iters=np.zeros(0, np.int32))
+        xs, its = ((0, L), (0, L)) if per_line else ((0,), (0,))
+        res = dict(w1=np.zeros((0, L)), w2=np.zeros((0, L)), x1=np.zeros(xs), x2=np.zeros(xs), n_iters=np.zeros(its, np.int32))
     if world == 1:
         return {k: np.asarray(res[k]) for k in ('w1', 'w2', 'x1', 'x2', 'n_iters')}
     # one collective: every rank contributes its packed block, padded to the largest block
     sizes = [(int(b[r + 1] - b[r]), int(offsets[b[r + 1]] - offsets[b[r]])) for r in range(world)]
-    length = lambda n, t: 2 * n * L + 2 * t + n
+    length = lambda n, t: 2 * n * L + 2 * t * K + n * K
     cap = max(length(n, t) for n, t in sizes)
     flat, _ = _pack(res, hi - lo, int(loffs[-1]), L)
     on_gpu = dist.get_backend(group) == 'nccl'
@@ -83,5 +92,5 @@ def infer_sharded(offsets, rows, testdata, ctrldata, compute=None, group=None, d
     recv = torch.empty(world * cap, dtype=torch.float64, device=dev)
     dist.all_gather_into_tensor(recv, send, group=group)
     recv = recv.cpu().numpy().reshape(world, cap)
-    parts = [_unpack(recv[r], sizes[r][0], sizes[r][1], L) for r in range(world)]
+    parts = [_unpack(recv[r], sizes[r][0], sizes[r][1], L, per_line) for r in range(world)]
     return {k: np.concatenate([p[k] for p in parts]) for k in ('w1', 'w2', 'x1', 'x2', 'n_iters')}

@@ -9,6 +9,10 @@ Same names, arguments, defaults, return layout and error behaviour:
         -> (y, tau, x1, x2, w1, w2)                                           (infer.py:55-99)
     LOG                                                                        (infer.py:6-8)
 
+plus the batch form of the paper scripts' per-line loop (run_JACKS_single.py:83-85):
+
+    inferJACKSLines(gene_index, testdata, ctrldata, fixed_x=None, n_iter=50, w_only=False)
+
 All genes of a call go to the GPU in one batch (one gene per warp team, FP64); the host only packs
 the gene index into CSR form and slices the flat result arrays into the per-gene tuples.
 No numerical work of the EM runs on the host and there is no CPU fallback.
@@ -72,6 +76,40 @@ def inferJACKS(gene_index, testdata, ctrldata, fixed_x=None, n_iter=50, apply_w_
     for i, gene in enumerate(names):
         a, b = lo[i], hi[i]
         results[gene] = (y[a:b], tau[a:b], x1[a:b], x2[a:b], w1[i], w2[i])
+    return results
+
+
+def inferJACKSLines(gene_index, testdata, ctrldata, fixed_x=None, n_iter=50, w_only=False, device=0):
+    """Every cell line on its own ("single JACKS"): the result of
+
+        [inferJACKS(gene_index, testdata[:, [ts], :], ctrldata[:, [ts], :], ...) for ts in range(L)]
+
+    (2018_paper_materials/scripts/jacks/run_JACKS_single.py:83-85, combined as in combineSingleResults :8-15) from one
+    set of kernel launches -- each (gene, line) pair is an independent one-line EM.  Returns
+    {gene: (y [G,L], tau [G,L], x1 [G,L], x2 [G,L], w1 [L], w2 [L])}: column ts is what the ts-th reference call
+    returns; with w_only the first four entries are None, as the script's w_only=True calls leave them.
+    """
+    results = {}
+    if len(gene_index) == 0:
+        return results
+    testdata, ctrldata = np.asarray(testdata), np.asarray(ctrldata)
+    if testdata.shape != ctrldata.shape:                    # infer.py:25-26
+        raise Exception(_SHAPE_MSG)
+    names, offsets, rows = _native.as_csr(gene_index)
+    fx1 = fx2 = None
+    if fixed_x is not None:
+        fx1, fx2 = np.asarray(fixed_x['X1'], dtype=np.float64), np.asarray(fixed_x['X2'], dtype=np.float64)
+    want = ('w1', 'w2', 'n_iters') if w_only else ('x1', 'x2', 'w1', 'w2', 'y', 'tau', 'n_iters')
+    r = _native.em_lines_host(_native.context(device), offsets, rows, testdata, ctrldata,
+                              params=_native.default_params(n_iter=int(n_iter)), fixed_x1=fx1, fixed_x2=fx2, want=want)
+    w1, w2 = r['w1'], r['w2']
+    lo, hi = offsets[:-1].tolist(), offsets[1:].tolist()
+    for i, gene in enumerate(names):
+        if w_only:
+            results[gene] = (None, None, None, None, w1[i], w2[i])
+        else:
+            a, b = lo[i], hi[i]
+            results[gene] = (r['y'][a:b], r['tau'][a:b], r['x1'][a:b], r['x2'][a:b], w1[i], w2[i])
     return results
 
 

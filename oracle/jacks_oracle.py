@@ -157,6 +157,30 @@ def em_genes(gene_index, testdata, ctrldata, fixed_x=None, n_iter=50, apply_w_hp
     return out
 
 
+def em_lines(gene_index, testdata, ctrldata, fixed_x=None, n_iter=50, iters_out=None):
+    """Per-line ("single JACKS") inference: restatement of the loop in
+    2018_paper_materials/scripts/jacks/run_JACKS_single.py:83-85 (one inferJACKS call per line on the
+    [:, [ts], :] slices) followed by combineSingleResults (:8-15), except that every output keeps its
+    line axis: {gene: (y [G,L], tau [G,L], x1 [G,L], x2 [G,L], w1 [L], w2 [L])}.
+    iters_out, if given, receives {gene: int array [L]}."""
+    L = testdata.shape[1]
+    per_line, per_iters = [], []
+    for ts in range(L):
+        it = {}
+        per_line.append(em_genes(gene_index, testdata[:, [ts], :], ctrldata[:, [ts], :], fixed_x=fixed_x,
+                                 n_iter=n_iter, iters_out=it))
+        per_iters.append(it)
+    out = {}
+    for gene in gene_index:
+        cols = [r[gene] for r in per_line]
+        out[gene] = (np.concatenate([c[0] for c in cols], axis=1), np.concatenate([c[1] for c in cols], axis=1),
+                     np.stack([c[2] for c in cols], axis=1), np.stack([c[3] for c in cols], axis=1),
+                     np.array([c[4][0] for c in cols]), np.array([c[5][0] for c in cols]))
+        if iters_out is not None:
+            iters_out[gene] = np.array([it[gene] for it in per_iters], dtype=np.int32)
+    return out
+
+
 # --------------------------------------------------------------------------------------
 # Preprocessing error model  (reference jacks/jacks/preprocess.py)
 # --------------------------------------------------------------------------------------

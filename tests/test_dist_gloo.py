@@ -32,6 +32,17 @@ def _worker(rank, world, port, q):
         got = jd.infer_sharded(offs, rows, test, ctrl, compute=compute)
         ref = compute(offs, rows, test, ctrl)
         ok = all(np.array_equal(got[k], ref[k]) for k in ('w1', 'w2', 'x1', 'x2', 'n_iters'))
+
+        # per-line mode (paper-script batch driver): every output carries a line axis
+        def compute_lines(o, r, t, c, **kw):
+            cols = [c_oracle.em_batched(o, r, np.ascontiguousarray(t[:, [l], :]), np.ascontiguousarray(c[:, [l], :]),
+                                        want_y_tau=False, **kw) for l in range(t.shape[1])]
+            return dict(w1=np.concatenate([k['w1'] for k in cols], axis=1), w2=np.concatenate([k['w2'] for k in cols], axis=1),
+                        x1=np.stack([k['x1'] for k in cols], axis=1), x2=np.stack([k['x2'] for k in cols], axis=1),
+                        n_iters=np.stack([k['n_iters'] for k in cols], axis=1))
+        got = jd.infer_sharded(offs, rows, test, ctrl, compute=compute_lines, per_line=True)
+        ref = compute_lines(offs, rows, test, ctrl)
+        ok = ok and all(got[k].shape == ref[k].shape and np.array_equal(got[k], ref[k]) for k in ('w1', 'w2', 'x1', 'x2', 'n_iters'))
         q.put((rank, bool(ok), jd.shard_bounds(offs, world).tolist()))
     finally:
         dist.destroy_process_group()

@@ -216,3 +216,16 @@ def test_vectorised_gene_ranking_is_bit_identical():
     slow = sorted((np.nanmean(res[g][4]), g) for g in res)
     assert [g for _, g in fast] == [g for _, g in slow]
     assert all(a == b for (a, _), (b, _) in zip(fast, slow))
+
+
+def test_paper_mode_spec_filters_and_combine():
+    """Host helpers of the paper scripts (run_JACKS_single.py:8-31, leaveoneout_reference_test.py:10-18)."""
+    from jacks_b200 import paper_modes as P
+    sample_spec = {'f.tab': [('CTRL', 'c1'), ('CTRL', 'c2'), ('A', 'a1'), ('B', 'b1'), ('A', 'a2')]}
+    ctrl_spec = {'CTRL': 'CTRL', 'A': 'CTRL', 'B': 'CTRL'}
+    assert P.filterSampleSpec(sample_spec, 'A', ctrl_spec) == {'f.tab': [('CTRL', 'c1'), ('CTRL', 'c2'), ('A', 'a1'), ('A', 'a2')]}
+    assert P.filterCtrlSpec(ctrl_spec, 'B') == {'B': 'CTRL', 'CTRL': 'CTRL'}
+    assert P.filterOutSampleSpec(sample_spec, 'A', ctrl_spec) == {'f.tab': [('CTRL', 'c1'), ('CTRL', 'c2'), ('B', 'b1')]}
+    singles = [{'g': (None, None, None, None, np.array([0.1 * ts]), np.array([1.0 + ts]))} for ts in range(3)]
+    y, tau, x1, x2, w1, w2 = P.combineSingleResults(singles)['g']
+    assert y is None and [float(v[0]) for v in w1] == [0.0, 0.1, 0.2] and [float(v[0]) for v in w2] == [1.0, 2.0, 3.0]
