@@ -107,3 +107,45 @@ def test_lines_full_scale_properties(nat):
     r2 = nat.em_lines_host(nat.context(0), offs, rows, np.ascontiguousarray(test[:, perm, :]),
                            np.ascontiguousarray(ctrl[:, perm, :]), want=('w1', 'n_iters'))
     assert np.array_equal(r2['w1'], r['w1'][:, perm]) and np.array_equal(r2['n_iters'], r['n_iters'][:, perm])
+
+
+def test_lines_edge_shapes_vs_oracle(nat):
+    """One line, one guide, nine and 150 guides (generic kernel on one-line views), a zero pass cap, and agreement
+    with this library's JOINT run when the cube has a single line."""
+    from oracle import jacks_oracle as O
+    from jacks_b200 import synth
+    counts = np.array([1, 2, 3, 4, 5, 6, 7, 8, 9, 150, 4, 1], dtype=np.int64)
+    problems = []
+    for L in (1, 3, 37):
+        gi, test, ctrl, _ = synth.make_condensed_screen(n_genes=len(counts), n_lines=L, seed=11 + L, guide_counts=counts, n_ctrl_genes=2)
+        names, offs, rows = nat.as_csr(gi)
+        r = nat.em_lines_host(nat.context(0), offs, rows, test, ctrl)
+        it = {}
+        ref = O.em_lines(gi, test, ctrl, iters_out=it)
+        for i, g in enumerate(names):
+            a, b = int(offs[i]), int(offs[i + 1])
+            for k, val in (('w1', ref[g][4]), ('w2', ref[g][5])):
+                ok, worst = close(r[k][i], val)
+                if not ok:
+                    problems.append((L, g, k, worst))
+            for k, val in (('x1', ref[g][2]), ('x2', ref[g][3]), ('tau', ref[g][1]), ('y', ref[g][0])):
+                ok, worst = close(r[k][a:b], val)
+                if not ok:
+                    problems.append((L, g, k, worst))
+            if not np.array_equal(r['n_iters'][i], it[g]):
+                problems.append((L, g, 'iters', r['n_iters'][i].tolist(), it[g].tolist()))
+        if L == 1:
+            joint = nat.em_batched_host(nat.context(0), offs, rows, test, ctrl)
+            for k in ('w1', 'w2'):
+                ok, worst = close(r[k], joint[k], rtol=1e-9)
+                if not ok:
+                    problems.append(('joint-vs-lines', k, worst))
+            if not np.array_equal(r['n_iters'][:, 0], joint['n_iters']):
+                problems.append('joint-vs-lines iters')
+        r0 = nat.em_lines_host(nat.context(0), offs, rows, test, ctrl, params=nat.default_params(n_iter=0), want=('w1', 'n_iters'))
+        assert (r0['n_iters'] == 0).all()
+        med = np.array([[np.median(test[gi[g], l, 0] - ctrl[gi[g], l, 0]) for l in range(L)] for g in names])
+        ok, worst = close(r0['w1'], med, rtol=1e-12)
+        if not ok:
+            problems.append((L, 'n_iter=0 w1 is the initial median', worst))
+    report(problems)
