@@ -30,10 +30,14 @@
 // appends the gene to the deferred queue and the NaN-safe generic kernel (em_generic.cu) runs it.
 #pragma once
 #include "em_common.cuh"
+#include "tmem.cuh"
 
 namespace jacks {
 
 #define JACKS_FULL_MASK 0xffffffffu
+#ifndef JACKS_TMU
+#define JACKS_TMU 3      // lines per sweep step of the tensor-memory variant (G <= 6)
+#endif
 
 __device__ __forceinline__ double warp_allsum(double v) {
 #pragma unroll
@@ -150,14 +154,19 @@ __device__ __forceinline__ void team_allsum(double (&v)[NV], double* scr, double
 // the next to land.  The bound therefore accumulates t1*th and the caller removes x2*sum th*w2.
 template <int G> struct EmX { double x1[G], x2[G], tx1[G], tx2[G]; };
 
-template <int G, int U, int UP, bool UNIT_C, bool MASKED, bool RELOAD>
-__device__ __forceinline__ void em_sweep(const double* __restrict__ ys, double (&pd)[UP][G],
+// TM: th lives in tensor memory (tmem.cuh) instead of shared memory: the step's U*G values are U*G consecutive
+// column pairs of the thread's own TMEM lane at `tcol`, moved by one tcgen05.ld and one tcgen05.st per step.
+// A lane's dead line (MASKED, !valid) then holds garbage that is loaded, computed on and stored back, never used.
+template <int G, int U, int UP, bool UNIT_C, bool MASKED, bool RELOAD, bool TM>
+__device__ __forceinline__ void em_sweep(const uint32_t tcol, const double* __restrict__ ys, double (&pd)[UP][G],
                                          const double* __restrict__ pd_next, const int Lp,
                                          double* __restrict__ ths, double* __restrict__ w1p,
                                          double* __restrict__ w2g, const int L, const int l, const int step,
                                          const EmX<G>& x, const double ivw, const double mw, const double c_tau,
                                          double (&a1)[G], double (&a2)[G], double (&ab)[G], const bool valid) {
     double yv[U][G], tv[U][G];
+    uint32_t traw[TM ? 2 * U * G : 2];
+    if (TM) tmem_ld_issue<(TM ? U * G : 1)>(tcol, reinterpret_cast<uint32_t(&)[2 * (TM ? U * G : 1)]>(traw));
 #pragma unroll
     for (int u = 0; u < U; ++u) {
         // the masked line of a lane that has run out of lines reads line 0 instead (any valid word)
@@ -165,8 +174,16 @@ __device__ __forceinline__ void em_sweep(const double* __restrict__ ys, double (
 #pragma unroll
         for (int g = 0; g < G; ++g) {
             yv[u][g] = ys[g * L + lu];
-            tv[u][g] = ths[g * L + lu];
+            if (!TM) tv[u][g] = ths[g * L + lu];
         }
+    }
+    if (TM) {
+        tmem_wait_ld();
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+#pragma unroll
+            for (int g = 0; g < G; ++g)
+                tv[u][g] = __hiloint2double((int)traw[2 * (u * G + g) + 1], (int)traw[2 * (u * G + g)]);
     }
     // W step, infer.py:112-116 (old tau, new x): den = 1/var0_w + sum_g x2*tau, num = mu0_w/var0_w + sum_g x1*y*tau
     double yt[U][G];
@@ -231,11 +248,15 @@ __device__ __forceinline__ void em_sweep(const double* __restrict__ ys, double (
             rd[u][g] = fma(rd[u][g], ee[u][g], rd[u][g]);
             if (!UNIT_C) rd[u][g] *= c_tau;
         }
+    if (TM) {
+        tmem_store<U * G>(tcol, &rd[0][0]);
+    } else {
 #pragma unroll
-    for (int u = 0; u < U; ++u)
+        for (int u = 0; u < U; ++u)
 #pragma unroll
-        for (int g = 0; g < G; ++g)
-            if (!MASKED || u < U - 1 || valid) ths[g * L + l + u * step] = rd[u][g];
+            for (int g = 0; g < G; ++g)
+                if (!MASKED || u < U - 1 || valid) ths[g * L + l + u * step] = rd[u][g];
+    }
     // bound (sum pd2*th = sum t1*th - x2*sum th*w2, the caller subtracts) and the next X step's row sums
 #pragma unroll
     for (int u = 0; u < U; ++u)
@@ -274,15 +295,15 @@ template <int G> struct EmSums { double a1[G], a2[G], ab; };
 // pd2 lives in an L2-resident global slab [G][Lp] (read once per pass, never written after staging, so
 // it does not have to occupy shared memory); rows are padded (Lp >= L + U*STEP) so that the look-ahead
 // loads need no bounds logic.
-template <int G, int STEP, bool UNIT_C>
-__device__ __noinline__ EmSums<G> em_sweep_all(const double* ys, const double* tpdg, const int Lp, double* ths,
+template <int G, int STEP, bool UNIT_C, bool TM>
+__device__ __noinline__ EmSums<G> em_sweep_all(const uint32_t tbase, const double* ys, const double* tpdg, const int Lp, double* ths,
                                                double* w1p, double* w2g, const int L, const int l0,
                                                const int n_warp, const EmX<G> x, const double ivw, const double mw,
                                                const double c_tau) {
     double a1[G], a2[G], ab[G];
 #pragma unroll
     for (int g = 0; g < G; ++g) { a1[g] = 0.0; a2[g] = 0.0; ab[g] = 0.0; }
-    constexpr int U = (G >= 7) ? 2 : 4;       // lines per step: U*G >= 8 independent elements
+    constexpr int U = (G >= 7) ? 2 : (TM ? JACKS_TMU : 4);       // lines per step: U*G >= 8 independent elements
     int l = l0;
     int n = n_warp;
     double pd[U][G];
@@ -290,13 +311,15 @@ __device__ __noinline__ EmSums<G> em_sweep_all(const double* ys, const double* t
     for (int u = 0; u < U; ++u)
 #pragma unroll
         for (int g = 0; g < G; ++g) pd[u][g] = __ldg(tpdg + g * Lp + l + u * STEP);
-    for (; n > U; n -= U, l += U * STEP)
-        em_sweep<G, U, U, UNIT_C, false, true>(ys, pd, tpdg + l + U * STEP, Lp, ths, w1p, w2g, L, l, STEP, x, ivw, mw, c_tau, a1, a2, ab, true);
+    uint32_t tcol = tbase;
+    for (; n > U; n -= U, l += U * STEP, tcol += 2 * U * G)
+        em_sweep<G, U, U, UNIT_C, false, true, TM>(tcol, ys, pd, tpdg + l + U * STEP, Lp, ths, w1p, w2g, L, l, STEP, x, ivw, mw, c_tau, a1, a2, ab, true);
     const bool valid = (l + (n - 1) * STEP) < L;
-    if (n == 1) em_sweep<G, 1, U, UNIT_C, true, false>(ys, pd, nullptr, Lp, ths, w1p, w2g, L, l, STEP, x, ivw, mw, c_tau, a1, a2, ab, valid);
-    else if (n == 2) em_sweep<G, 2, U, UNIT_C, true, false>(ys, pd, nullptr, Lp, ths, w1p, w2g, L, l, STEP, x, ivw, mw, c_tau, a1, a2, ab, valid);
-    else if (U == 4 && n == 3) em_sweep<G, (U == 4 ? 3 : 1), U, UNIT_C, true, false>(ys, pd, nullptr, Lp, ths, w1p, w2g, L, l, STEP, x, ivw, mw, c_tau, a1, a2, ab, valid);
-    else if (U == 4 && n == 4) em_sweep<G, (U == 4 ? 4 : 1), U, UNIT_C, true, false>(ys, pd, nullptr, Lp, ths, w1p, w2g, L, l, STEP, x, ivw, mw, c_tau, a1, a2, ab, valid);
+    if (n == 1) em_sweep<G, 1, U, UNIT_C, true, false, TM>(tcol, ys, pd, nullptr, Lp, ths, w1p, w2g, L, l, STEP, x, ivw, mw, c_tau, a1, a2, ab, valid);
+    else if (n == 2) em_sweep<G, 2, U, UNIT_C, true, false, TM>(tcol, ys, pd, nullptr, Lp, ths, w1p, w2g, L, l, STEP, x, ivw, mw, c_tau, a1, a2, ab, valid);
+    else if (U >= 3 && n == 3) em_sweep<G, (U >= 3 ? 3 : 1), U, UNIT_C, true, false, TM>(tcol, ys, pd, nullptr, Lp, ths, w1p, w2g, L, l, STEP, x, ivw, mw, c_tau, a1, a2, ab, valid);
+    else if (U == 4 && n == 4) em_sweep<G, (U == 4 ? 4 : 1), U, UNIT_C, true, false, TM>(tcol, ys, pd, nullptr, Lp, ths, w1p, w2g, L, l, STEP, x, ivw, mw, c_tau, a1, a2, ab, valid);
+    if (TM) tmem_wait_st();          // the next pass reads these columns back
     EmSums<G> r;
     // sum pd2*th = sum (t1 - x2*w2)*th: the accumulators hold sum t1*th
     r.ab = fma(-x.x2[0], a2[0], ab[0]);
@@ -367,6 +390,12 @@ __device__ __noinline__ bool em_stage_gene(const double2* __restrict__ test, con
 __host__ __device__ constexpr long long em_fast_smem_doubles(int G, int W, int L) {
     return 2LL * G * L + (long long)W * (2 * G + 1) * 33 + 2LL * W * (2 * G + 1);
 }
+// TMEM variant: four independent one-warp teams per CTA, tau in tensor memory; per team y [G][L] plus the reduction
+// tile and totals, rounded to 128 bytes: 15.3 KB per gene at G = 4, L = 400 -> 12 genes (three warps per scheduler) per SM.
+constexpr int kTmemTeams = 4;
+__host__ __device__ constexpr long long em_fast_tmem_team_doubles(int G, int L) {
+    return ((long long)G * L + (2 * G + 1) * 33 + 2 * (2 * G + 1) + 15) / 16 * 16;
+}
 
 // L2 prefetch of the G guide rows (test + control) of the gene a team will run next.  One rolled loop over
 // all (row, 128-byte chunk) pairs: this runs once per gene and must stay small in code.
@@ -387,22 +416,39 @@ __device__ __forceinline__ void prefetch_gene_l2(const double2* test, const doub
 // PLAIN: the launch uses neither the w hyper-prior (infer.py:92) nor the 1-D-control sd fill (infer.py:63); both
 // are uniform per launch, and compiling them out keeps the common kernel's code (and its instruction-cache
 // footprint) small.
-template <int G, int W, bool UNIT_C, bool PLAIN>
-__global__ void __launch_bounds__(W * 32) em_fast_kernel(const EmLaunch a) {
+// TM: the tensor-memory variant (W must be 1): a CTA is kTmemTeams independent one-warp teams, each with its own
+// gene, shared-memory block and TMEM lane quarter; th = tau/2 lives in TMEM columns [line][g] of the thread's lane.
+// Nothing synchronises the teams between the TMEM allocation at the start and its release at the end.
+template <int G, int W, bool UNIT_C, bool PLAIN, bool TM>
+__global__ void __launch_bounds__(TM ? kTmemTeams * 32 : W * 32, TM ? 3 : 0) em_fast_kernel(const EmLaunch a) {
+    static_assert(!TM || W == 1, "the TMEM variant runs one-warp teams");
     constexpr int NV = 2 * G + 1;
     constexpr int STEP = 32 * W;
     extern __shared__ double smem[];
     const int L = a.L;
-    double* ys = smem;                       // [G][L]
-    double* taus = ys + (size_t)G * L;       // [G][L]  th = tau/2 (see em_sweep)
-    double* scr = taus + (size_t)G * L + (threadIdx.x >> 5) * (NV * 33);   // this warp's reduction tile
-    double* red = taus + (size_t)G * L + W * (NV * 33);                    // [2][W][NV] totals
-    const int Lp = a.tpd_stride;
-    double* tpdg = a.tpd_scratch + (size_t)blockIdx.x * G * Lp;            // this team's pd2 slab [G][Lp] (global, L2)
-    __shared__ int s_slot[2];
-
     const int lane = threadIdx.x & 31;
-    const int warp = threadIdx.x >> 5;
+    const int cta_warp = threadIdx.x >> 5;
+    const int warp = TM ? 0 : cta_warp;                 // warp index inside the team
+    const int tid = TM ? lane : (int)threadIdx.x;       // thread index inside the team
+    const int team = TM ? blockIdx.x * kTmemTeams + cta_warp : blockIdx.x;
+    double* ys = smem + (TM ? cta_warp * em_fast_tmem_team_doubles(G, L) : 0);   // [G][L]
+    double* taus = TM ? nullptr : ys + (size_t)G * L;   // [G][L]  th = tau/2 (see em_sweep); TMEM columns if TM
+    double* tile = TM ? ys + (size_t)G * L : taus + (size_t)G * L;
+    double* scr = tile + warp * (NV * 33);              // this warp's reduction tile
+    double* red = tile + W * (NV * 33);                 // [2][W][NV] totals
+    const int Lp = a.tpd_stride;
+    double* tpdg = a.tpd_scratch + (size_t)team * G * Lp;                  // this team's pd2 slab [G][Lp] (global, L2)
+    __shared__ int s_slot[2];
+    __shared__ uint32_t s_tmem;
+    uint32_t tbase = 0;
+    if (TM) {
+        if (cta_warp == 0) tmem_alloc(&s_tmem, (uint32_t)a.tmem_cols);
+        tmem_fence_before_sync();
+        __syncthreads();
+        tmem_fence_after_sync();
+        tbase = s_tmem + ((uint32_t)(cta_warp * 32) << 16);      // this warp's lane quarter
+    }
+
     const double tps = a.tps;
     const double c_tau = a.tps + 0.5;            // infer.py:120
     const double ivx = 1.0 / a.var0_x;           // infer.py:104
@@ -422,7 +468,7 @@ __global__ void __launch_bounds__(W * 32) em_fast_kernel(const EmLaunch a) {
             if (lane == 0) first = atomicAdd(a.work_counter, 1);
             first = __shfl_sync(JACKS_FULL_MASK, first, 0);
         } else {
-            if (threadIdx.x == 0) s_slot[0] = atomicAdd(a.work_counter, 1);
+            if (tid == 0) s_slot[0] = atomicAdd(a.work_counter, 1);
             __syncthreads();
             first = s_slot[0];
         }
@@ -438,7 +484,7 @@ __global__ void __launch_bounds__(W * 32) em_fast_kernel(const EmLaunch a) {
 
     while (slot < a.n_work) {
         int pending = 0;                       // raw result of the look-ahead atomic (thread 0 only)
-        if (threadIdx.x == 0) pending = atomicAdd(a.work_counter, 1);
+        if (tid == 0) pending = atomicAdd(a.work_counter, 1);
         // rotate which warp owns the (possibly partial) last strip so the SM sub-partitions stay even
         const int wv = (W == 1) ? 0 : (warp + slot) % W;
         const int l0 = wv * 32 + lane;
@@ -475,7 +521,7 @@ __global__ void __launch_bounds__(W * 32) em_fast_kernel(const EmLaunch a) {
         if (W == 1) {
             nslot = __shfl_sync(JACKS_FULL_MASK, pending, 0);
         } else {
-            if (threadIdx.x == 0) s_slot[pipe] = pending;
+            if (tid == 0) s_slot[pipe] = pending;
             __syncthreads();
             nslot = s_slot[pipe];
             pipe ^= 1;
@@ -491,7 +537,7 @@ __global__ void __launch_bounds__(W * 32) em_fast_kernel(const EmLaunch a) {
             for (int g = 0; g < G; ++g) nrows[g] = a.slot_rows[(long long)nslot * G + g];
         }
         if (any_bad) {
-            if (threadIdx.x == 0) {
+            if (tid == 0) {
                 const int p = atomicAdd(a.deferred_count, 1);
                 a.deferred_ids[p] = gid;
             }
@@ -504,24 +550,56 @@ __global__ void __launch_bounds__(W * 32) em_fast_kernel(const EmLaunch a) {
             double acc[NV];
 #pragma unroll
             for (int i = 0; i < NV; ++i) acc[i] = 0.0;
-#pragma unroll 2
-            for (int l = l0; l < L; l += STEP) {
-                double yv[G];
+            if (TM) {
+                // warp-uniform trip count: the TMEM stores are warp-collective; a lane past its last line
+                // computes on line 0 and stores a value nobody uses
+#pragma unroll 1
+                for (int i = 0; i < n_warp; ++i) {
+                    const int l = l0 + i * STEP;
+                    const bool live = l < L;
+                    const int lu = live ? l : 0;
+                    double yv[G], th[G];
 #pragma unroll
-                for (int g = 0; g < G; ++g) yv[g] = ys[g * L + l];
-                const double w1 = median_small<G>(yv);
-                const double w2 = w1 * w1;
+                    for (int g = 0; g < G; ++g) yv[g] = ys[g * L + lu];
+                    const double w1 = median_small<G>(yv);
+                    const double w2 = w1 * w1;
 #pragma unroll
-                for (int g = 0; g < G; ++g) {
-                    const double t = tps * fast_rcp(tpdg[g * Lp + l]);      // th = tau/2 = tps/pd2, infer.py:83
-                    taus[g * L + l] = t;
-                    const double xw = x1r[g] * w1;
-                    acc[2 * G] += t * (yv[g] * yv[g] + x2r[g] * w2 - 2.0 * xw * yv[g]);
-                    acc[g] += yv[g] * t * w1;
-                    acc[G + g] += t * w2;
+                    for (int g = 0; g < G; ++g) {
+                        th[g] = tps * fast_rcp(tpdg[g * Lp + lu]);         // th = tau/2 = tps/pd2, infer.py:83
+                        if (live) {
+                            const double xw = x1r[g] * w1;
+                            acc[2 * G] += th[g] * (yv[g] * yv[g] + x2r[g] * w2 - 2.0 * xw * yv[g]);
+                            acc[g] += yv[g] * th[g] * w1;
+                            acc[G + g] += th[g] * w2;
+                        }
+                    }
+                    tmem_store<G>(tbase + 2 * G * i, th);
+                    if (live) {
+                        w1g[l] = w1;
+                        if (w2g) w2g[l] = w2;
+                    }
                 }
-                w1g[l] = w1;
-                if (w2g) w2g[l] = w2;
+                tmem_wait_st();
+            } else {
+#pragma unroll 2
+                for (int l = l0; l < L; l += STEP) {
+                    double yv[G];
+#pragma unroll
+                    for (int g = 0; g < G; ++g) yv[g] = ys[g * L + l];
+                    const double w1 = median_small<G>(yv);
+                    const double w2 = w1 * w1;
+#pragma unroll
+                    for (int g = 0; g < G; ++g) {
+                        const double t = tps * fast_rcp(tpdg[g * Lp + l]);      // th = tau/2 = tps/pd2, infer.py:83
+                        taus[g * L + l] = t;
+                        const double xw = x1r[g] * w1;
+                        acc[2 * G] += t * (yv[g] * yv[g] + x2r[g] * w2 - 2.0 * xw * yv[g]);
+                        acc[g] += yv[g] * t * w1;
+                        acc[G + g] += t * w2;
+                    }
+                    w1g[l] = w1;
+                    if (w2g) w2g[l] = w2;
+                }
             }
             team_allsum<NV, NV, W>(acc, scr, red, parity, warp, lane);
             // every sum was formed with th = tau/2: acc[0..2G) stay HALF sums (the X step doubles them in its
@@ -535,7 +613,7 @@ __global__ void __launch_bounds__(W * 32) em_fast_kernel(const EmLaunch a) {
 
             // next gene: its index entries have arrived during the init sweep; pull its rows towards L2
             if (nslot < a.n_work)
-                prefetch_gene_l2<G>(a.test, a.ctrl, a.slot_rows + (long long)nslot * G, L, a.ctrl_lines, threadIdx.x, STEP);
+                prefetch_gene_l2<G>(a.test, a.ctrl, a.slot_rows + (long long)nslot * G, L, a.ctrl_lines, tid, STEP);
 
             // ---- EM passes (infer.py:89-98) ------------------------------------------------------
             for (int it = 0; it < a.n_iter; ++it) {
@@ -580,7 +658,7 @@ __global__ void __launch_bounds__(W * 32) em_fast_kernel(const EmLaunch a) {
                         xv.x1[g] = x1r[g]; xv.x2[g] = x2r[g];
                         xv.tx1[g] = 2.0 * x1r[g]; xv.tx2[g] = 2.0 * x2r[g];
                     }
-                    const EmSums<G> r = em_sweep_all<G, STEP, UNIT_C>(ys, tpdg, Lp, taus, w1g, w2g, L, l0, n_warp, xv, ivw, mw, c_tau);
+                    const EmSums<G> r = em_sweep_all<G, STEP, UNIT_C, TM>(tbase, ys, tpdg, Lp, taus, w1g, w2g, L, l0, n_warp, xv, ivw, mw, c_tau);
 #pragma unroll
                     for (int g = 0; g < G; ++g) { acc[g] = r.a1[g]; acc[G + g] = r.a2[g]; }
                     acc[2 * G] = r.ab;
@@ -592,8 +670,20 @@ __global__ void __launch_bounds__(W * 32) em_fast_kernel(const EmLaunch a) {
             }
 
             // ---- write results ------------------------------------------------------------------
+            if (TM && a.tau) {
+#pragma unroll 1
+                for (int i = 0; i < n_warp; ++i) {
+                    const int l = l0 + i * STEP;
+                    double th[G];
+                    tmem_load<G>(tbase + 2 * G * i, th);
+                    if (l < L) {
+#pragma unroll
+                        for (int g = 0; g < G; ++g) a.tau[(off + g) * L + l] = 2.0 * th[g];
+                    }
+                }
+            }
             for (int l = l0; l < L; l += STEP) {
-                if (a.tau) {
+                if (!TM && a.tau) {
 #pragma unroll
                     for (int g = 0; g < G; ++g) a.tau[(off + g) * L + l] = 2.0 * taus[g * L + l];
                 }
@@ -621,6 +711,11 @@ __global__ void __launch_bounds__(W * 32) em_fast_kernel(const EmLaunch a) {
         slot = nslot; gid = ngid; off = noff;
 #pragma unroll
         for (int g = 0; g < G; ++g) rows[g] = nrows[g];
+    }
+    if (TM) {
+        tmem_fence_before_sync();
+        __syncthreads();
+        if (cta_warp == 0) tmem_dealloc(s_tmem, (uint32_t)a.tmem_cols);
     }
 }
 

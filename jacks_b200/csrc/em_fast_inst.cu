@@ -1,5 +1,9 @@
 // Instantiations of the fast EM kernel for one guide count (compile with -DJACKS_G=<1..8>).
 // One translation unit per G keeps the build parallel; em_dispatch.cu switches over them.
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+
 #include "em_fast.cuh"
 
 #ifndef JACKS_G
@@ -10,9 +14,56 @@ namespace jacks {
 
 namespace {
 
+// Tensor-memory variant: four one-warp teams per CTA, tau in TMEM (em_fast.cuh).  The resident CTAs per SM are the
+// smaller of what shared memory / registers and what the 512 TMEM columns allow.
+template <int G, bool UNIT_C, bool PLAIN>
+cudaError_t launch_tmem(const EmLaunch& a0, int n_sm, int grid_limit, cudaStream_t st, int* grid_out) {
+    auto k = em_fast_kernel<G, 1, UNIT_C, PLAIN, true>;
+    EmLaunch a = a0;
+    a.tmem_cols = tmem_cols_for(G, a.L);
+    const size_t smem = (size_t)em_fast_tmem_team_doubles(G, a.L) * kTmemTeams * sizeof(double);
+    if (a.tmem_cols == 0 || smem > kMaxDynSmem) return cudaErrorInvalidValue;
+    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    // cudaOccupancyMaxActiveBlocksPerMultiprocessor answers 1 for any kernel that allocates tensor memory, although the
+    // hardware co-schedules such CTAs as long as their columns fit (tools/probes/tmem_probe.cu): count the resources here.
+    cudaFuncAttributes fa;
+    if ((e = cudaFuncGetAttributes(&fa, k)) != cudaSuccess) return e;
+    const int regs_per_cta = ((fa.numRegs + 7) / 8 * 8) * kTmemTeams * 32;
+    int occ = std::min<int>(65536 / regs_per_cta, (int)((228 * 1024) / (smem + fa.sharedSizeBytes + 1024)));
+    if (occ < 1) return cudaErrorLaunchOutOfResources;
+    occ = std::min(occ, 512 / a.tmem_cols);
+    occ = std::min(occ, kMaxFastCtasPerSm / kTmemTeams);        // tau_pr_den slabs are provisioned per team
+    long long grid = (long long)occ * n_sm;
+    const long long want = ((long long)a.n_work + kTmemTeams - 1) / kTmemTeams;
+    if (grid > want) grid = want;
+    if (grid_limit > 0 && grid > grid_limit) grid = grid_limit;
+    if (grid < 1) grid = 1;
+    if (grid_out) *grid_out = (int)grid;
+    k<<<(int)grid, kTmemTeams * 32, smem, st>>>(a);
+    return cudaGetLastError();
+}
+
+// Is the TMEM variant usable and worthwhile for this shape?  It needs the gene's tau in <= 512 columns, and pays when it
+// puts more genes on an SM than the shared-memory variant does.
+template <int G>
+bool tmem_preferred(const EmLaunch& a) {
+    static const int mode = []() { const char* e = getenv("JACKS_EM_TMEM"); return e ? atoi(e) : -1; }();   // tuning override
+    if (mode == 0) return false;
+    const int cols = tmem_cols_for(G, a.L);
+    if (cols == 0) return false;
+    const size_t team = (size_t)em_fast_tmem_team_doubles(G, a.L) * sizeof(double);
+    if (team * kTmemTeams > kMaxDynSmem) return false;
+    if (mode == 1) return true;
+    const long long genes_tmem = std::min<long long>(std::min<long long>(kMaxDynSmem / (team * kTmemTeams), 512 / cols) * kTmemTeams, kMaxFastCtasPerSm);
+    const long long genes_smem = std::min<long long>(kMaxDynSmem / ((size_t)em_fast_smem_doubles(G, 1, a.L) * sizeof(double)), kMaxFastCtasPerSm);
+    return genes_tmem > genes_smem;
+}
+
 template <int G, int W, bool UNIT_C, bool PLAIN>
 cudaError_t launch_inst(const EmLaunch& a, int n_sm, int grid_limit, cudaStream_t st, int* grid_out) {
-    auto k = em_fast_kernel<G, W, UNIT_C, PLAIN>;
+    if (W == 1 && tmem_preferred<G>(a)) return launch_tmem<G, UNIT_C, PLAIN>(a, n_sm, grid_limit, st, grid_out);
+    auto k = em_fast_kernel<G, W, UNIT_C, PLAIN, false>;
     const size_t smem = (size_t)em_fast_smem_doubles(G, W, a.L) * sizeof(double);
     if (smem > kMaxDynSmem) return cudaErrorInvalidValue;
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
