@@ -36,7 +36,7 @@ namespace jacks {
 
 #define JACKS_FULL_MASK 0xffffffffu
 #ifndef JACKS_TMU
-#define JACKS_TMU 3      // lines per sweep step of the tensor-memory variant (G <= 6)
+#define JACKS_TMU 4      // lines per sweep step of the tensor-memory variant (G <= 6)
 #endif
 
 __device__ __forceinline__ double warp_allsum(double v) {
@@ -391,7 +391,8 @@ __host__ __device__ constexpr long long em_fast_smem_doubles(int G, int W, int L
     return 2LL * G * L + (long long)W * (2 * G + 1) * 33 + 2LL * W * (2 * G + 1);
 }
 // TMEM variant: four independent one-warp teams per CTA, tau in tensor memory; per team y [G][L] plus the reduction
-// tile and totals, rounded to 128 bytes: 15.3 KB per gene at G = 4, L = 400 -> 12 genes (three warps per scheduler) per SM.
+// tile and totals, rounded to 128 bytes.  Two CTAs (eight genes) per SM: with three, the 168-register budget makes
+// ptxas spill in the sweep, and 12 genes at 3 lines per step measured no faster than 8 at 4 (7.9 ms at L = 400).
 constexpr int kTmemTeams = 4;
 __host__ __device__ constexpr long long em_fast_tmem_team_doubles(int G, int L) {
     return ((long long)G * L + (2 * G + 1) * 33 + 2 * (2 * G + 1) + 15) / 16 * 16;
@@ -420,7 +421,7 @@ __device__ __forceinline__ void prefetch_gene_l2(const double2* test, const doub
 // gene, shared-memory block and TMEM lane quarter; th = tau/2 lives in TMEM columns [line][g] of the thread's lane.
 // Nothing synchronises the teams between the TMEM allocation at the start and its release at the end.
 template <int G, int W, bool UNIT_C, bool PLAIN, bool TM>
-__global__ void __launch_bounds__(TM ? kTmemTeams * 32 : W * 32, TM ? 3 : 0) em_fast_kernel(const EmLaunch a) {
+__global__ void __launch_bounds__(TM ? kTmemTeams * 32 : W * 32, TM ? 2 : 0) em_fast_kernel(const EmLaunch a) {
     static_assert(!TM || W == 1, "the TMEM variant runs one-warp teams");
     constexpr int NV = 2 * G + 1;
     constexpr int STEP = 32 * W;

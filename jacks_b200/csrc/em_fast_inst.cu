@@ -1,7 +1,6 @@
 // Instantiations of the fast EM kernel for one guide count (compile with -DJACKS_G=<1..8>).
 // One translation unit per G keeps the build parallel; em_dispatch.cu switches over them.
 #include <algorithm>
-#include <cstdio>
 #include <cstdlib>
 
 #include "em_fast.cuh"
@@ -45,7 +44,8 @@ cudaError_t launch_tmem(const EmLaunch& a0, int n_sm, int grid_limit, cudaStream
 }
 
 // Is the TMEM variant usable and worthwhile for this shape?  It needs the gene's tau in <= 512 columns, and pays when it
-// puts more genes on an SM than the shared-memory variant does.
+// puts more genes on an SM than the shared-memory variant does (measured at G = 4: L = 400, 8 genes either way, parity;
+// L = 800, 8 against 4 genes: 5.1 ms against 6.9 ms per 39,000 genes).  JACKS_EM_TMEM=0/1 forces the choice (tests, tuning).
 template <int G>
 bool tmem_preferred(const EmLaunch& a) {
     static const int mode = []() { const char* e = getenv("JACKS_EM_TMEM"); return e ? atoi(e) : -1; }();   // tuning override
@@ -55,7 +55,8 @@ bool tmem_preferred(const EmLaunch& a) {
     const size_t team = (size_t)em_fast_tmem_team_doubles(G, a.L) * sizeof(double);
     if (team * kTmemTeams > kMaxDynSmem) return false;
     if (mode == 1) return true;
-    const long long genes_tmem = std::min<long long>(std::min<long long>(kMaxDynSmem / (team * kTmemTeams), 512 / cols) * kTmemTeams, kMaxFastCtasPerSm);
+    const long long ctas = std::min<long long>(std::min<long long>(kMaxDynSmem / (team * kTmemTeams), 512 / cols), 2);   // 2: registers
+    const long long genes_tmem = std::min<long long>(ctas * kTmemTeams, kMaxFastCtasPerSm);
     const long long genes_smem = std::min<long long>(kMaxDynSmem / ((size_t)em_fast_smem_doubles(G, 1, a.L) * sizeof(double)), kMaxFastCtasPerSm);
     return genes_tmem > genes_smem;
 }

@@ -201,7 +201,7 @@ def _random_screen(rng, Gs, L, nan_frac=0.0, sd_nan_frac=0.0):
     return offs, perm, np.ascontiguousarray(test[np.argsort(perm)]), np.ascontiguousarray(ctrl[np.argsort(perm)])
 
 
-@pytest.mark.parametrize('L', [1, 2, 5, 31, 32, 33, 64, 100, 128, 129, 257, 400, 416, 417, 448, 449, 512, 513, 700])
+@pytest.mark.parametrize('L', [1, 2, 5, 31, 32, 33, 64, 100, 128, 129, 257, 400, 416, 417, 448, 449, 512, 513, 700, 800, 1100])
 def test_shape_sweep_vs_oracle(nat, L):
     """Every kernel path (fast shapes, generic, deferred NaN genes, scratch spill) against the C oracle,
     which tests/test_oracle_golden.py pins to the reference."""
@@ -265,3 +265,14 @@ def test_full_avana_shape_vs_c_oracle(nat):
     assert (rp['n_iters'] == refp['n_iters']).all()
     ok, worst = close(rp['w1'], refp['w1'])
     assert ok, worst
+
+
+def test_tensor_memory_variant_forced():
+    """The TMEM variant of the fast kernel (tau in tensor memory) is chosen by shape; force it for every eligible
+    shape (JACKS_EM_TMEM=1, read once per process) and re-run the golden and shape-sweep parity tests in a child."""
+    import subprocess
+    import sys
+    env = dict(os.environ, JACKS_EM_TMEM='1')
+    r = subprocess.run([sys.executable, '-m', 'pytest', os.path.abspath(__file__), '-m', 'gpu', '-q', '-x', '-k',
+                        'golden or shape_sweep or fixed_x'], env=env, capture_output=True, text=True, timeout=1500)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
