@@ -41,7 +41,7 @@ struct EmLaunch {
     // tpd_stride = em_fast_tpd_stride(L): rows padded so that look-ahead loads need no bounds logic
     double* tpd_scratch; int tpd_stride;
     // TMEM variant of the fast kernel: columns each CTA allocates (tmem_cols_for(G, L)); 0 selects the shared-memory variant
-    int tmem_cols;
+    int tmem_cols; int tmem_pd_off;        // tmem_pd_off: first column of tau_pr_den when it lives in TMEM too
     // generic kernel only: global scratch when a gene's working set exceeds shared memory
     double* scratch; long long scratch_stride;   // doubles per warp
     // Per-line mode (every (gene, line) pair an independent EM with one line; run_JACKS_single.py:83-85).

@@ -157,8 +157,10 @@ template <int G> struct EmX { double x1[G], x2[G], tx1[G], tx2[G]; };
 // TM: th lives in tensor memory (tmem.cuh) instead of shared memory: the step's U*G values are U*G consecutive
 // column pairs of the thread's own TMEM lane at `tcol`, moved by one tcgen05.ld and one tcgen05.st per step.
 // A lane's dead line (MASKED, !valid) then holds garbage that is loaded, computed on and stored back, never used.
-template <int G, int U, int UP, bool UNIT_C, bool MASKED, bool RELOAD, bool TM>
-__device__ __forceinline__ void em_sweep(const uint32_t tcol, const double* __restrict__ ys, double (&pd)[UP][G],
+// TM == 2: pd2 lives in TMEM as well (columns `pcol`...), loaded at the top of the step that uses it: no L2 round
+// trip, no look-ahead registers, no global slab.
+template <int G, int U, int UP, bool UNIT_C, bool MASKED, bool RELOAD, int TM>
+__device__ __forceinline__ void em_sweep(const uint32_t tcol, const uint32_t pcol, const double* __restrict__ ys, double (&pd)[UP][G],
                                          const double* __restrict__ pd_next, const int Lp,
                                          double* __restrict__ ths, double* __restrict__ w1p,
                                          double* __restrict__ w2g, const int L, const int l, const int step,
@@ -166,7 +168,9 @@ __device__ __forceinline__ void em_sweep(const uint32_t tcol, const double* __re
                                          double (&a1)[G], double (&a2)[G], double (&ab)[G], const bool valid) {
     double yv[U][G], tv[U][G];
     uint32_t traw[TM ? 2 * U * G : 2];
+    uint32_t praw[TM == 2 ? 2 * U * G : 2];
     if (TM) tmem_ld_issue<(TM ? U * G : 1)>(tcol, reinterpret_cast<uint32_t(&)[2 * (TM ? U * G : 1)]>(traw));
+    if (TM == 2) tmem_ld_issue<(TM == 2 ? U * G : 1)>(pcol, reinterpret_cast<uint32_t(&)[2 * (TM == 2 ? U * G : 1)]>(praw));
 #pragma unroll
     for (int u = 0; u < U; ++u) {
         // the masked line of a lane that has run out of lines reads line 0 instead (any valid word)
@@ -184,6 +188,13 @@ __device__ __forceinline__ void em_sweep(const uint32_t tcol, const double* __re
 #pragma unroll
             for (int g = 0; g < G; ++g)
                 tv[u][g] = __hiloint2double((int)traw[2 * (u * G + g) + 1], (int)traw[2 * (u * G + g)]);
+        if (TM == 2) {
+#pragma unroll
+            for (int u = 0; u < U; ++u)
+#pragma unroll
+                for (int g = 0; g < G; ++g)
+                    pd[u][g] = __hiloint2double((int)praw[2 * (u * G + g) + 1], (int)praw[2 * (u * G + g)]);
+        }
     }
     // W step, infer.py:112-116 (old tau, new x): den = 1/var0_w + sum_g x2*tau, num = mu0_w/var0_w + sum_g x1*y*tau
     double yt[U][G];
@@ -223,7 +234,7 @@ __device__ __forceinline__ void em_sweep(const uint32_t tcol, const double* __re
         for (int g = 0; g < G; ++g) {
             d[u][g] = fma(x.x1[g], m2w1[u], yv[u][g]);
             t1[u][g] = fma(x.x2[g], w2[u], pd[u][g]);
-            if (RELOAD) pd[u][g] = __ldg(pd_next + g * Lp + u * step);
+            if (RELOAD && TM != 2) pd[u][g] = __ldg(pd_next + g * Lp + u * step);
         }
 #pragma unroll
     for (int u = 0; u < U; ++u)
@@ -295,8 +306,8 @@ template <int G> struct EmSums { double a1[G], a2[G], ab; };
 // pd2 lives in an L2-resident global slab [G][Lp] (read once per pass, never written after staging, so
 // it does not have to occupy shared memory); rows are padded (Lp >= L + U*STEP) so that the look-ahead
 // loads need no bounds logic.
-template <int G, int STEP, bool UNIT_C, bool TM>
-__device__ __noinline__ EmSums<G> em_sweep_all(const uint32_t tbase, const double* ys, const double* tpdg, const int Lp, double* ths,
+template <int G, int STEP, bool UNIT_C, int TM>
+__device__ __noinline__ EmSums<G> em_sweep_all(const uint32_t tbase, const uint32_t pdoff, const double* ys, const double* tpdg, const int Lp, double* ths,
                                                double* w1p, double* w2g, const int L, const int l0,
                                                const int n_warp, const EmX<G> x, const double ivw, const double mw,
                                                const double c_tau) {
@@ -307,18 +318,20 @@ __device__ __noinline__ EmSums<G> em_sweep_all(const uint32_t tbase, const doubl
     int l = l0;
     int n = n_warp;
     double pd[U][G];
+    if (TM != 2) {
 #pragma unroll
-    for (int u = 0; u < U; ++u)
+        for (int u = 0; u < U; ++u)
 #pragma unroll
-        for (int g = 0; g < G; ++g) pd[u][g] = __ldg(tpdg + g * Lp + l + u * STEP);
+            for (int g = 0; g < G; ++g) pd[u][g] = __ldg(tpdg + g * Lp + l + u * STEP);
+    }
     uint32_t tcol = tbase;
     for (; n > U; n -= U, l += U * STEP, tcol += 2 * U * G)
-        em_sweep<G, U, U, UNIT_C, false, true, TM>(tcol, ys, pd, tpdg + l + U * STEP, Lp, ths, w1p, w2g, L, l, STEP, x, ivw, mw, c_tau, a1, a2, ab, true);
+        em_sweep<G, U, U, UNIT_C, false, true, TM>(tcol, tcol + pdoff, ys, pd, tpdg + l + U * STEP, Lp, ths, w1p, w2g, L, l, STEP, x, ivw, mw, c_tau, a1, a2, ab, true);
     const bool valid = (l + (n - 1) * STEP) < L;
-    if (n == 1) em_sweep<G, 1, U, UNIT_C, true, false, TM>(tcol, ys, pd, nullptr, Lp, ths, w1p, w2g, L, l, STEP, x, ivw, mw, c_tau, a1, a2, ab, valid);
-    else if (n == 2) em_sweep<G, 2, U, UNIT_C, true, false, TM>(tcol, ys, pd, nullptr, Lp, ths, w1p, w2g, L, l, STEP, x, ivw, mw, c_tau, a1, a2, ab, valid);
-    else if (U >= 3 && n == 3) em_sweep<G, (U >= 3 ? 3 : 1), U, UNIT_C, true, false, TM>(tcol, ys, pd, nullptr, Lp, ths, w1p, w2g, L, l, STEP, x, ivw, mw, c_tau, a1, a2, ab, valid);
-    else if (U == 4 && n == 4) em_sweep<G, (U == 4 ? 4 : 1), U, UNIT_C, true, false, TM>(tcol, ys, pd, nullptr, Lp, ths, w1p, w2g, L, l, STEP, x, ivw, mw, c_tau, a1, a2, ab, valid);
+    if (n == 1) em_sweep<G, 1, U, UNIT_C, true, false, TM>(tcol, tcol + pdoff, ys, pd, nullptr, Lp, ths, w1p, w2g, L, l, STEP, x, ivw, mw, c_tau, a1, a2, ab, valid);
+    else if (n == 2) em_sweep<G, 2, U, UNIT_C, true, false, TM>(tcol, tcol + pdoff, ys, pd, nullptr, Lp, ths, w1p, w2g, L, l, STEP, x, ivw, mw, c_tau, a1, a2, ab, valid);
+    else if (U >= 3 && n == 3) em_sweep<G, (U >= 3 ? 3 : 1), U, UNIT_C, true, false, TM>(tcol, tcol + pdoff, ys, pd, nullptr, Lp, ths, w1p, w2g, L, l, STEP, x, ivw, mw, c_tau, a1, a2, ab, valid);
+    else if (U == 4 && n == 4) em_sweep<G, (U == 4 ? 4 : 1), U, UNIT_C, true, false, TM>(tcol, tcol + pdoff, ys, pd, nullptr, Lp, ths, w1p, w2g, L, l, STEP, x, ivw, mw, c_tau, a1, a2, ab, valid);
     if (TM) tmem_wait_st();          // the next pass reads these columns back
     EmSums<G> r;
     // sum pd2*th = sum (t1 - x2*w2)*th: the accumulators hold sum t1*th
@@ -334,11 +347,14 @@ __device__ __noinline__ EmSums<G> em_sweep_all(const uint32_t tbase, const doubl
 // All G rows of a line batch are loaded before any is consumed (G*4 independent 16-byte loads in flight per
 // lane): staging is pure memory latency for a team that has only its own warps to hide it behind.
 // Not inlined (runs once per gene).  Returns true if a staged value is not finite.
-template <int G, int STEP>
+// TM == 2: pd2 goes to the thread's TMEM lane at `tpd` ([line][g] column pairs) instead of the global slab; the loop
+// then has a warp-uniform trip count (the TMEM stores are warp-collective) and dead lines are predicated.
+template <int G, int STEP, int TM>
 __device__ __noinline__ bool em_stage_gene(const double2* __restrict__ test, const double2* __restrict__ ctrl,
                                            const int* rows, double* __restrict__ ys, double* __restrict__ tpdg,
                                            const int L, const int Lp, const int l0, const int ctrl_lines,
-                                           const int rowmean_fill, const double* fill, const double tps) {
+                                           const int rowmean_fill, const double* fill, const double tps,
+                                           const uint32_t tpd, const int n_warp) {
     bool bad = false;
     const double2* tr[G];
     const double2* cr[G];
@@ -354,6 +370,44 @@ __device__ __noinline__ bool em_stage_gene(const double2* __restrict__ test, con
         for (int g = 0; g < G; ++g) c0[g] = cr[g][0];
     }
     constexpr int B = 2;                      // lines per batch
+    if (TM == 2) {
+#pragma unroll 1
+        for (int i = 0; i < n_warp; i += B) {
+            double2 t[B][G], c[B][G];
+            bool live[B];
+#pragma unroll
+            for (int b = 0; b < B; ++b) {
+                const int l = l0 + (i + b) * STEP;
+                live[b] = l < L;
+                const int lb = live[b] ? l : 0;
+#pragma unroll
+                for (int g = 0; g < G; ++g) {
+                    t[b][g] = tr[g][lb];
+                    c[b][g] = (ctrl_lines == 1) ? c0[g] : cr[g][lb];
+                }
+            }
+            double pdv[B][G];
+#pragma unroll
+            for (int b = 0; b < B; ++b) {
+                const int l = l0 + (i + b) * STEP;
+#pragma unroll
+                for (int g = 0; g < G; ++g) {
+                    const double te = (t[b][g].y != t[b][g].y) ? 2.0 : t[b][g].y;               // infer.py:58
+                    double ce = c[b][g].y;
+                    if (ce != ce) ce = (ctrl_lines == 1 && rowmean_fill) ? fill[g] : te;         // :63 / :68
+                    const double yv = t[b][g].x - c[b][g].x;
+                    pdv[b][g] = 2.0 * (tps * (te * te + ce * ce + 1e-2));                        // pd2 = 2*tau_pr_den (exact)
+                    if (live[b]) {
+                        bad |= !(fabs(yv) <= 1.79769313486231570e308) || !(pdv[b][g] <= 1.79769313486231570e308);
+                        ys[g * L + l] = yv;
+                    }
+                }
+            }
+            tmem_store<B * G>(tpd + 2 * G * i, &pdv[0][0]);
+        }
+        tmem_wait_st();
+        return bad;
+    }
     for (int l = l0; l < L; l += B * STEP) {
         double2 t[B][G], c[B][G];
 #pragma unroll
@@ -420,7 +474,8 @@ __device__ __forceinline__ void prefetch_gene_l2(const double2* test, const doub
 // TM: the tensor-memory variant (W must be 1): a CTA is kTmemTeams independent one-warp teams, each with its own
 // gene, shared-memory block and TMEM lane quarter; th = tau/2 lives in TMEM columns [line][g] of the thread's lane.
 // Nothing synchronises the teams between the TMEM allocation at the start and its release at the end.
-template <int G, int W, bool UNIT_C, bool PLAIN, bool TM>
+// TM: 0 shared-memory variant; 1 tau in TMEM; 2 tau and tau_pr_den in TMEM (no global slab, no L2 traffic in a pass).
+template <int G, int W, bool UNIT_C, bool PLAIN, int TM>
 __global__ void __launch_bounds__(TM ? kTmemTeams * 32 : W * 32, TM ? 2 : 0) em_fast_kernel(const EmLaunch a) {
     static_assert(!TM || W == 1, "the TMEM variant runs one-warp teams");
     constexpr int NV = 2 * G + 1;
@@ -449,6 +504,7 @@ __global__ void __launch_bounds__(TM ? kTmemTeams * 32 : W * 32, TM ? 2 : 0) em_
         tmem_fence_after_sync();
         tbase = s_tmem + ((uint32_t)(cta_warp * 32) << 16);      // this warp's lane quarter
     }
+    const uint32_t pdoff = (uint32_t)a.tmem_pd_off;              // columns of pd2 behind those of tau (TM == 2)
 
     const double tps = a.tps;
     const double c_tau = a.tps + 0.5;            // infer.py:120
@@ -515,7 +571,8 @@ __global__ void __launch_bounds__(TM ? kTmemTeams * 32 : W * 32, TM ? 2 : 0) em_
                 }
             }
         }
-        const bool bad = em_stage_gene<G, STEP>(a.test, a.ctrl, rows, ys, tpdg, L, Lp, l0, a.ctrl_lines, a.ctrl_rowmean_fill, fill, tps);
+        const bool bad = em_stage_gene<G, STEP, TM>(a.test, a.ctrl, rows, ys, tpdg, L, Lp, l0, a.ctrl_lines, a.ctrl_rowmean_fill, fill, tps,
+                                                     tbase + pdoff, n_warp);
         const int any_bad = (W == 1) ? __any_sync(JACKS_FULL_MASK, bad) : __syncthreads_or(bad);
         // the look-ahead atomic has landed by now: share it and start loading the next gene's index
         int nslot;
@@ -559,14 +616,18 @@ __global__ void __launch_bounds__(TM ? kTmemTeams * 32 : W * 32, TM ? 2 : 0) em_
                     const int l = l0 + i * STEP;
                     const bool live = l < L;
                     const int lu = live ? l : 0;
-                    double yv[G], th[G];
+                    double yv[G], th[G], pdv[G];
+                    if (TM == 2) tmem_load<G>(tbase + pdoff + 2 * G * i, pdv);
 #pragma unroll
-                    for (int g = 0; g < G; ++g) yv[g] = ys[g * L + lu];
+                    for (int g = 0; g < G; ++g) {
+                        yv[g] = ys[g * L + lu];
+                        if (TM != 2) pdv[g] = tpdg[g * Lp + lu];
+                    }
                     const double w1 = median_small<G>(yv);
                     const double w2 = w1 * w1;
 #pragma unroll
                     for (int g = 0; g < G; ++g) {
-                        th[g] = tps * fast_rcp(tpdg[g * Lp + lu]);         // th = tau/2 = tps/pd2, infer.py:83
+                        th[g] = tps * fast_rcp(pdv[g]);                    // th = tau/2 = tps/pd2, infer.py:83
                         if (live) {
                             const double xw = x1r[g] * w1;
                             acc[2 * G] += th[g] * (yv[g] * yv[g] + x2r[g] * w2 - 2.0 * xw * yv[g]);
@@ -659,7 +720,7 @@ __global__ void __launch_bounds__(TM ? kTmemTeams * 32 : W * 32, TM ? 2 : 0) em_
                         xv.x1[g] = x1r[g]; xv.x2[g] = x2r[g];
                         xv.tx1[g] = 2.0 * x1r[g]; xv.tx2[g] = 2.0 * x2r[g];
                     }
-                    const EmSums<G> r = em_sweep_all<G, STEP, UNIT_C, TM>(tbase, ys, tpdg, Lp, taus, w1g, w2g, L, l0, n_warp, xv, ivw, mw, c_tau);
+                    const EmSums<G> r = em_sweep_all<G, STEP, UNIT_C, TM>(tbase, pdoff, ys, tpdg, Lp, taus, w1g, w2g, L, l0, n_warp, xv, ivw, mw, c_tau);
 #pragma unroll
                     for (int g = 0; g < G; ++g) { acc[g] = r.a1[g]; acc[G + g] = r.a2[g]; }
                     acc[2 * G] = r.ab;

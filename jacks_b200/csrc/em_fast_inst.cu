@@ -15,11 +15,12 @@ namespace {
 
 // Tensor-memory variant: four one-warp teams per CTA, tau in TMEM (em_fast.cuh).  The resident CTAs per SM are the
 // smaller of what shared memory / registers and what the 512 TMEM columns allow.
-template <int G, bool UNIT_C, bool PLAIN>
+template <int G, bool UNIT_C, bool PLAIN, int TM>
 cudaError_t launch_tmem(const EmLaunch& a0, int n_sm, int grid_limit, cudaStream_t st, int* grid_out) {
-    auto k = em_fast_kernel<G, 1, UNIT_C, PLAIN, true>;
+    auto k = em_fast_kernel<G, 1, UNIT_C, PLAIN, TM>;
     EmLaunch a = a0;
-    a.tmem_cols = tmem_cols_for(G, a.L);
+    a.tmem_cols = tmem_cols_for(G, a.L, TM);
+    a.tmem_pd_off = (TM == 2) ? tmem_array_cols(G, a.L) : 0;
     const size_t smem = (size_t)em_fast_tmem_team_doubles(G, a.L) * kTmemTeams * sizeof(double);
     if (a.tmem_cols == 0 || smem > kMaxDynSmem) return cudaErrorInvalidValue;
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -43,28 +44,37 @@ cudaError_t launch_tmem(const EmLaunch& a0, int n_sm, int grid_limit, cudaStream
     return cudaGetLastError();
 }
 
-// Is the TMEM variant usable and worthwhile for this shape?  It needs the gene's tau in <= 512 columns, and pays when it
-// puts more genes on an SM than the shared-memory variant does (measured at G = 4: L = 400, 8 genes either way, parity;
-// L = 800, 8 against 4 genes: 5.1 ms against 6.9 ms per 39,000 genes).  JACKS_EM_TMEM=0/1 forces the choice (tests, tuning).
+// Which variant for this shape?  0: shared memory; 1: tau in TMEM; 2: tau and tau_pr_den in TMEM.
+// The TMEM variants run at most two CTAs (8 genes) per SM (registers).  Variant 2 needs both arrays of two CTAs in the 512
+// columns (L <= 512 at G = 4) and is then preferred even at equal gene count: a pass makes no L2 round trip at all.
+// Variant 1 pays when it puts more genes on an SM than shared memory does (measured at G = 4, L = 800: 8 against 4 genes,
+// 5.1 ms against 6.9 ms per 39,000 genes).  JACKS_EM_TMEM=0/1/2 forces the choice where eligible (tests, tuning).
 template <int G>
-bool tmem_preferred(const EmLaunch& a) {
-    static const int mode = []() { const char* e = getenv("JACKS_EM_TMEM"); return e ? atoi(e) : -1; }();   // tuning override
-    if (mode == 0) return false;
-    const int cols = tmem_cols_for(G, a.L);
-    if (cols == 0) return false;
+int tmem_mode(const EmLaunch& a) {
+    static const int force = []() { const char* e = getenv("JACKS_EM_TMEM"); return e ? atoi(e) : -1; }();
+    if (force == 0) return 0;
     const size_t team = (size_t)em_fast_tmem_team_doubles(G, a.L) * sizeof(double);
-    if (team * kTmemTeams > kMaxDynSmem) return false;
-    if (mode == 1) return true;
-    const long long ctas = std::min<long long>(std::min<long long>(kMaxDynSmem / (team * kTmemTeams), 512 / cols), 2);   // 2: registers
-    const long long genes_tmem = std::min<long long>(ctas * kTmemTeams, kMaxFastCtasPerSm);
+    const long long by_smem = kMaxDynSmem / (team * kTmemTeams);
+    const int cols1 = tmem_cols_for(G, a.L, 1), cols2 = tmem_cols_for(G, a.L, 2);
+    if (by_smem < 1 || cols1 == 0) return 0;
     const long long genes_smem = std::min<long long>(kMaxDynSmem / ((size_t)em_fast_smem_doubles(G, 1, a.L) * sizeof(double)), kMaxFastCtasPerSm);
-    return genes_tmem > genes_smem;
+    const long long genes1 = std::min<long long>(std::min<long long>(by_smem, 512 / cols1), 2) * kTmemTeams;
+    const long long genes2 = cols2 ? std::min<long long>(std::min<long long>(by_smem, 512 / cols2), 2) * kTmemTeams : 0;
+    if (force == 2) return genes2 ? 2 : 1;
+    if (force == 1) return 1;
+    if (genes2 >= genes_smem && genes2 >= genes1) return 2;
+    if (genes1 > genes_smem) return 1;
+    return 0;
 }
 
 template <int G, int W, bool UNIT_C, bool PLAIN>
 cudaError_t launch_inst(const EmLaunch& a, int n_sm, int grid_limit, cudaStream_t st, int* grid_out) {
-    if (W == 1 && tmem_preferred<G>(a)) return launch_tmem<G, UNIT_C, PLAIN>(a, n_sm, grid_limit, st, grid_out);
-    auto k = em_fast_kernel<G, W, UNIT_C, PLAIN, false>;
+    if (W == 1) {
+        const int tm = tmem_mode<G>(a);
+        if (tm == 2) return launch_tmem<G, UNIT_C, PLAIN, 2>(a, n_sm, grid_limit, st, grid_out);
+        if (tm == 1) return launch_tmem<G, UNIT_C, PLAIN, 1>(a, n_sm, grid_limit, st, grid_out);
+    }
+    auto k = em_fast_kernel<G, W, UNIT_C, PLAIN, 0>;
     const size_t smem = (size_t)em_fast_smem_doubles(G, W, a.L) * sizeof(double);
     if (smem > kMaxDynSmem) return cudaErrorInvalidValue;
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -135,10 +135,11 @@ __device__ __forceinline__ void tmem_store(uint32_t addr, const double* v) {
     tmem_st_issue<ND>(addr, r);
 }
 
-// Columns a gene needs for th [lines per lane, rounded up to 4][G] doubles, rounded to what tcgen05.alloc accepts;
-// 0 if it cannot fit.
-__host__ __device__ constexpr int tmem_cols_for(int G, int L) {
-    const int need = 2 * G * (((L + 31) / 32 + 3) / 4 * 4);
+// Columns of one [lines per lane, rounded up to 4][G] array of doubles in a thread's lane.
+__host__ __device__ constexpr int tmem_array_cols(int G, int L) { return 2 * G * (((L + 31) / 32 + 3) / 4 * 4); }
+// Columns a CTA allocates for `arrays` such arrays, rounded to what tcgen05.alloc accepts; 0 if they cannot fit.
+__host__ __device__ constexpr int tmem_cols_for(int G, int L, int arrays = 1) {
+    const int need = arrays * tmem_array_cols(G, L);
     int c = 32;
     while (c < need) c <<= 1;
     return c <= 512 ? c : 0;
