@@ -349,12 +349,22 @@ __device__ __noinline__ EmSums<G> em_sweep_all(const uint32_t tbase, const uint3
 // Not inlined (runs once per gene).  Returns true if a staged value is not finite.
 // TM == 2: pd2 goes to the thread's TMEM lane at `tpd` ([line][g] column pairs) instead of the global slab; the loop
 // then has a warp-uniform trip count (the TMEM stores are warp-collective) and dead lines are predicated.
+// In that mode the pass also INITIALISES the gene (infer.py:81-86), since every value it needs is in registers:
+// th = tau/2 = tps/pd2 to the TMEM columns at `tth`, the initial E[w] (median over the guides) and E[w^2] to the
+// gene's output rows, and the lane's partial sums for the initial bound and the first X step (formed with th,
+// i.e. HALF sums) in the returned struct.
+template <int G> struct EmStaged { double acc[2 * G + 1]; bool bad; };
+
 template <int G, int STEP, int TM>
-__device__ __noinline__ bool em_stage_gene(const double2* __restrict__ test, const double2* __restrict__ ctrl,
-                                           const int* rows, double* __restrict__ ys, double* __restrict__ tpdg,
-                                           const int L, const int Lp, const int l0, const int ctrl_lines,
-                                           const int rowmean_fill, const double* fill, const double tps,
-                                           const uint32_t tpd, const int n_warp) {
+__device__ __noinline__ EmStaged<G> em_stage_gene(const double2* __restrict__ test, const double2* __restrict__ ctrl,
+                                                  const int* rows, double* __restrict__ ys, double* __restrict__ tpdg,
+                                                  const int L, const int Lp, const int l0, const int ctrl_lines,
+                                                  const int rowmean_fill, const double* fill, const double tps,
+                                                  const uint32_t tpd, const uint32_t tth, const int n_warp,
+                                                  const EmX<G> x, double* __restrict__ w1g, double* __restrict__ w2g) {
+    EmStaged<G> r;
+#pragma unroll
+    for (int i = 0; i < 2 * G + 1; ++i) r.acc[i] = 0.0;
     bool bad = false;
     const double2* tr[G];
     const double2* cr[G];
@@ -386,27 +396,44 @@ __device__ __noinline__ bool em_stage_gene(const double2* __restrict__ test, con
                     c[b][g] = (ctrl_lines == 1) ? c0[g] : cr[g][lb];
                 }
             }
-            double pdv[B][G];
+            double pdv[B][G], th[B][G];
 #pragma unroll
             for (int b = 0; b < B; ++b) {
                 const int l = l0 + (i + b) * STEP;
+                double yv[G];
 #pragma unroll
                 for (int g = 0; g < G; ++g) {
                     const double te = (t[b][g].y != t[b][g].y) ? 2.0 : t[b][g].y;               // infer.py:58
                     double ce = c[b][g].y;
                     if (ce != ce) ce = (ctrl_lines == 1 && rowmean_fill) ? fill[g] : te;         // :63 / :68
-                    const double yv = t[b][g].x - c[b][g].x;
+                    yv[g] = t[b][g].x - c[b][g].x;
                     pdv[b][g] = 2.0 * (tps * (te * te + ce * ce + 1e-2));                        // pd2 = 2*tau_pr_den (exact)
+                    th[b][g] = tps * fast_rcp(pdv[b][g]);                                        // tau/2 = tps/pd2, infer.py:83
                     if (live[b]) {
-                        bad |= !(fabs(yv) <= 1.79769313486231570e308) || !(pdv[b][g] <= 1.79769313486231570e308);
-                        ys[g * L + l] = yv;
+                        bad |= !(fabs(yv[g]) <= 1.79769313486231570e308) || !(pdv[b][g] <= 1.79769313486231570e308);
+                        ys[g * L + l] = yv[g];
                     }
+                }
+                const double w1 = median_small<G>(yv);                                           // infer.py:81
+                const double w2 = w1 * w1;
+                if (live[b]) {
+#pragma unroll
+                    for (int g = 0; g < G; ++g) {
+                        const double xw = x.x1[g] * w1;
+                        r.acc[2 * G] += th[b][g] * (yv[g] * yv[g] + x.x2[g] * w2 - 2.0 * xw * yv[g]);
+                        r.acc[g] += yv[g] * th[b][g] * w1;
+                        r.acc[G + g] += th[b][g] * w2;
+                    }
+                    w1g[l] = w1;
+                    if (w2g) w2g[l] = w2;
                 }
             }
             tmem_store<B * G>(tpd + 2 * G * i, &pdv[0][0]);
+            tmem_store<B * G>(tth + 2 * G * i, &th[0][0]);
         }
         tmem_wait_st();
-        return bad;
+        r.bad = bad;
+        return r;
     }
     for (int l = l0; l < L; l += B * STEP) {
         double2 t[B][G], c[B][G];
@@ -436,7 +463,8 @@ __device__ __noinline__ bool em_stage_gene(const double2* __restrict__ test, con
             }
         }
     }
-    return bad;
+    r.bad = bad;
+    return r;
 }
 
 // Shared memory of one team: y and tau [G][L], the reduction tiles and totals.  tau_pr_den, E[w] and E[w^2]
@@ -571,8 +599,20 @@ __global__ void __launch_bounds__(TM ? kTmemTeams * 32 : W * 32, TM ? 2 : 0) em_
                 }
             }
         }
-        const bool bad = em_stage_gene<G, STEP, TM>(a.test, a.ctrl, rows, ys, tpdg, L, Lp, l0, a.ctrl_lines, a.ctrl_rowmean_fill, fill, tps,
-                                                     tbase + pdoff, n_warp);
+        double* const w2g = a.w2 ? a.w2 + (long long)gid * L : nullptr;
+        double* const w1g = a.w1 + (long long)gid * L;
+        double acc[NV];
+        bool bad;
+        {
+            EmX<G> xv;
+#pragma unroll
+            for (int g = 0; g < G; ++g) { xv.x1[g] = x1r[g]; xv.x2[g] = x2r[g]; xv.tx1[g] = 0.0; xv.tx2[g] = 0.0; }
+            const EmStaged<G> sg = em_stage_gene<G, STEP, TM>(a.test, a.ctrl, rows, ys, tpdg, L, Lp, l0, a.ctrl_lines, a.ctrl_rowmean_fill,
+                                                              fill, tps, tbase + pdoff, tbase, n_warp, xv, w1g, w2g);
+            bad = sg.bad;
+#pragma unroll
+            for (int i = 0; i < NV; ++i) acc[i] = sg.acc[i];       // TM == 2: the initial sums; otherwise zeros
+        }
         const int any_bad = (W == 1) ? __any_sync(JACKS_FULL_MASK, bad) : __syncthreads_or(bad);
         // the look-ahead atomic has landed by now: share it and start loading the next gene's index
         int nslot;
@@ -603,12 +643,9 @@ __global__ void __launch_bounds__(TM ? kTmemTeams * 32 : W * 32, TM ? 2 : 0) em_
             // every lane reads back only the words (shared and global) it wrote itself: no barrier needed
 
             // ---- initial w, tau, bound and the first X-step sums (infer.py:81-86) --------------
-            double* const w2g = a.w2 ? a.w2 + (long long)gid * L : nullptr;
-            double* const w1g = a.w1 + (long long)gid * L;
-            double acc[NV];
-#pragma unroll
-            for (int i = 0; i < NV; ++i) acc[i] = 0.0;
-            if (TM) {
+            if (TM == 2) {
+                // staged and initialised in one pass (em_stage_gene)
+            } else if (TM) {
                 // warp-uniform trip count: the TMEM stores are warp-collective; a lane past its last line
                 // computes on line 0 and stores a value nobody uses
 #pragma unroll 1
