@@ -8,16 +8,22 @@
 //   X step   infer.py:103-110    W step  infer.py:112-116
 //   tau step infer.py:118-121    bound   infer.py:123-125
 //
-// Layout.  Shared memory holds what is read AND written every pass: y and tau as [G][L] (25.6 KB at G=4,
-// L=400) plus the reduction tiles -- 8 genes, i.e. two warps per scheduler, per SM.  tau_pr_den is read once
-// per pass and never written after staging: it lives in a per-CTA global slab that stays L2 resident and is
-// software-pipelined one sweep step ahead.  E[w], E[w^2] are write-only within a pass: straight to the gene's
+// Layout, shared-memory variant (TM = 0).  Shared memory holds what is read AND written every pass: y and tau as
+// [G][L] (25.6 KB at G=4, L=400) plus the reduction tiles -- 8 genes, i.e. two warps per scheduler, per SM.
+// tau_pr_den is read once per pass and never written after staging: it lives in a per-team global slab that stays L2
+// resident and is fetched one sweep step ahead.  E[w], E[w^2] are write-only within a pass: straight to the gene's
 // output rows.  Lane `lane` of warp `wv` owns lines l = wv*32 + lane + k*32*W; every line's W step, tau step and
 // bound contribution are lane-local (G is a compile-time constant, so the G values of a line sit in registers
 // while the line is processed), and per EM pass there is exactly ONE cross-lane operation: an all-reduce of
 // 2G+1 doubles carrying the bound of this pass and the 2G row sums the next X step needs, both formed from the
 // same fresh tau in the same sweep.  The sweep is a rolled loop over line steps (a few hundred instructions), so
-// the hot code stays inside the instruction cache; FP64 issue is the limiter.
+// the hot code stays inside the instruction cache.
+//
+// Tensor-memory variants (TM = 1, 2; one-warp teams, four independent teams per CTA).  Blackwell's TMEM is used as a
+// lane-private FP64 scratchpad (tmem.cuh): tau (TM >= 1) and tau_pr_den (TM = 2) live in column pairs [line][g] of each
+// thread's own TMEM lane and move with one LDTM / STTM per sweep step; only y stays in shared memory.  TM = 2 needs
+// no global slab and makes no L2 round trip inside a pass; staging then also initialises the gene.  The launcher
+// (em_fast_inst.cu) picks the variant by shape; DESIGN.md section 4.1 has the measurements.
 //
 // Arithmetic notes (all FP64).  b* = y^2 - 2*y*x1*w1 + x2*w2 is formed as fma(y, y - 2*x1*w1,
 // x2*w2); the bound term tau*(y^2 + x2*w2 - 2*x1*w1*y) (infer.py:125) is the same quantity, so it
