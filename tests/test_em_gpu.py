@@ -267,12 +267,14 @@ def test_full_avana_shape_vs_c_oracle(nat):
     assert ok, worst
 
 
-def test_tensor_memory_variant_forced():
-    """The TMEM variant of the fast kernel (tau in tensor memory) is chosen by shape; force it for every eligible
-    shape (JACKS_EM_TMEM=1, read once per process) and re-run the golden and shape-sweep parity tests in a child."""
+@pytest.mark.parametrize('mode', ['1', '2'])
+def test_tensor_memory_variant_forced(mode):
+    """The TMEM variants of the fast kernel (1: tau in tensor memory, 2: tau and tau_pr_den) are chosen by shape; force
+    each for every eligible shape (JACKS_EM_TMEM, read once per process) and re-run the golden and shape-sweep parity
+    tests in a child process."""
     import subprocess
     import sys
-    env = dict(os.environ, JACKS_EM_TMEM='1')
+    env = dict(os.environ, JACKS_EM_TMEM=mode)
     r = subprocess.run([sys.executable, '-m', 'pytest', os.path.abspath(__file__), '-m', 'gpu', '-q', '-x', '-k',
                         'golden or shape_sweep or fixed_x'], env=env, capture_output=True, text=True, timeout=1500)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
