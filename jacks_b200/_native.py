@@ -353,8 +353,11 @@ def normalize_host(ctx, values, normtype='median', take_log=False, prior=32.0, r
     out = np.empty(values.shape, dtype=np.float64)
     table = None
     if take_log and use_table and values.size:
-        finite = values[np.isfinite(values)]
-        top = int(min(finite.max(), LOG2_TABLE_MAX - 1)) if finite.size and finite.max() >= 0 else -1
+        vmax = values.max()                      # one pass, no temporary; NaN / inf cells take the slow path
+        if not np.isfinite(vmax):
+            finite = values[np.isfinite(values)]
+            vmax = finite.max() if finite.size else -1.0
+        top = int(min(vmax, LOG2_TABLE_MAX - 1)) if vmax >= 0 else -1
         if top >= 0:
             table = np.log2(np.arange(top + 1, dtype=np.float64) + prior)
     mask = None if row_mask is None else np.ascontiguousarray(row_mask, dtype=np.uint8)

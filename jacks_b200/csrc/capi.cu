@@ -12,6 +12,7 @@
 
 #include <algorithm>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/jacks_b200.h"
@@ -102,6 +103,98 @@ int choose_team(int G, int L) {
 
 }  // namespace
 
+// ---- HostStager -----------------------------------------------------------------------------------------------------
+
+static void parallel_memcpy(void* dst, const void* src, size_t bytes, int threads) {
+    if (threads <= 1 || bytes < (4u << 20)) { memcpy(dst, src, bytes); return; }
+    const size_t per = ((bytes / threads) + 4095) & ~(size_t)4095;
+    std::vector<std::thread> pool;
+    for (int t = 1; t < threads; ++t) {
+        const size_t lo = per * t;
+        if (lo >= bytes) break;
+        const size_t n = std::min(per, bytes - lo);
+        pool.emplace_back([=]() { memcpy((char*)dst + lo, (const char*)src + lo, n); });
+    }
+    memcpy(dst, src, std::min(per, bytes));
+    for (auto& th : pool) th.join();
+}
+
+static bool host_pointer_is_pinned(const void* p) {
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return at.type == cudaMemoryTypeHost || at.type == cudaMemoryTypeManaged;
+}
+
+int HostStager::init() {
+    if (buf[0]) return JACKS_OK;
+    cudaError_t e;
+    for (int i = 0; i < 2; ++i) {
+        if ((e = cudaHostAlloc(&buf[i], kChunk, cudaHostAllocDefault)) != cudaSuccess) { release(); return jacks::cuda_fail(e, "cudaHostAlloc(staging)"); }
+        if ((e = cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming)) != cudaSuccess) { release(); return jacks::cuda_fail(e, "cudaEventCreate"); }
+    }
+    const unsigned hw = std::thread::hardware_concurrency();
+    threads = (int)std::max(1u, std::min(8u, hw ? hw / 2 : 1u));
+    if (const char* env = getenv("JACKS_COPY_THREADS")) threads = std::max(1, atoi(env));
+    return JACKS_OK;
+}
+
+void HostStager::release() {
+    for (int i = 0; i < 2; ++i) {
+        if (buf[i]) cudaFreeHost(buf[i]);
+        if (ev[i]) cudaEventDestroy(ev[i]);
+        buf[i] = nullptr; ev[i] = nullptr;
+    }
+}
+
+int HostStager::h2d(void* dst, const void* src, size_t bytes, cudaStream_t st) {
+    cudaError_t e;
+    if (bytes == 0) return JACKS_OK;
+    if (bytes < (8u << 20) || host_pointer_is_pinned(src)) {
+        if ((e = cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, st)) != cudaSuccess) return jacks::cuda_fail(e, "H2D");
+        return JACKS_OK;
+    }
+    int rc = init();
+    if (rc != JACKS_OK) return rc;
+    int k = 0;
+    for (size_t off = 0; off < bytes; off += kChunk, k ^= 1) {
+        const size_t n = std::min(kChunk, bytes - off);
+        if (off >= 2 * kChunk && (e = cudaEventSynchronize(ev[k])) != cudaSuccess) return jacks::cuda_fail(e, "staging event");   // buffer free again?
+        parallel_memcpy(buf[k], (const char*)src + off, n, threads);
+        if ((e = cudaMemcpyAsync((char*)dst + off, buf[k], n, cudaMemcpyHostToDevice, st)) != cudaSuccess) return jacks::cuda_fail(e, "H2D (staged)");
+        cudaEventRecord(ev[k], st);
+    }
+    // the pinned buffers must not be refilled by a later call before these uploads have read them
+    for (int i = 0; i < 2; ++i)
+        if (bytes > (size_t)i * kChunk && (e = cudaEventSynchronize(ev[i])) != cudaSuccess) return jacks::cuda_fail(e, "staging event");
+    return JACKS_OK;
+}
+
+int HostStager::d2h(void* dst, const void* src, size_t bytes, cudaStream_t st) {
+    cudaError_t e;
+    if (bytes == 0) return JACKS_OK;
+    if (bytes < (8u << 20) || host_pointer_is_pinned(dst)) {
+        // small or pinned: plain asynchronous copy -- the caller synchronises `st` before it reads dst
+        if ((e = cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, st)) != cudaSuccess) return jacks::cuda_fail(e, "D2H");
+        return JACKS_OK;
+    }
+    int rc = init();
+    if (rc != JACKS_OK) return rc;
+    const size_t nchunk = (bytes + kChunk - 1) / kChunk;
+    for (size_t i = 0; i <= nchunk; ++i) {
+        if (i < nchunk) {
+            const size_t off = i * kChunk, n = std::min(kChunk, bytes - off);
+            if ((e = cudaMemcpyAsync(buf[i & 1], (const char*)src + off, n, cudaMemcpyDeviceToHost, st)) != cudaSuccess) return jacks::cuda_fail(e, "D2H (staged)");
+            cudaEventRecord(ev[i & 1], st);
+        }
+        if (i > 0) {          // drain the previous chunk while the one just issued is in flight
+            const size_t j = i - 1, off = j * kChunk, n = std::min(kChunk, bytes - off);
+            if ((e = cudaEventSynchronize(ev[j & 1])) != cudaSuccess) return jacks::cuda_fail(e, "staging event");
+            parallel_memcpy((char*)dst + off, buf[j & 1], n, threads);
+        }
+    }
+    return JACKS_OK;
+}
+
 extern "C" {
 
 const char* jacks_last_error(void) { return g_last_error.c_str(); }
@@ -151,6 +244,7 @@ void jacks_ctx_destroy(JacksCtx* c) {
     c->res_test.release(); c->res_ctrl.release(); c->res_fx.release();
     for (auto& b : c->out) b.release();
     c->tmp.release();
+    c->stager.release();
     if (c->stream) cudaStreamDestroy(c->stream);
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     if (c->out_stream) cudaStreamDestroy(c->out_stream);
@@ -483,6 +577,7 @@ int jacks_em_batched_host(JacksCtx* ctx, const JacksEmParams* params, const int6
         if ((e = cudaEventCreateWithFlags(&ev_start, cudaEventDisableTiming)) != cudaSuccess) rc = cuda_fail(e, "cudaEventCreate");
         else { cudaEventRecord(ev_start, s_k); cudaStreamWaitEvent(s_in, ev_start, 0); cudaStreamWaitEvent(s_out, ev_start, 0); }
     }
+    const bool staged_out = !(keep_resident & JACKS_ASYNC);
     int64_t row_done = 0;        // rows [0, row_done) are already enqueued for upload
     for (int r = 0; r < R && rc == JACKS_OK; ++r) {
         const int64_t g0 = n_genes * r / R, g1 = n_genes * (r + 1) / R;
@@ -491,10 +586,11 @@ int jacks_em_batched_host(JacksCtx* ctx, const JacksEmParams* params, const int6
             if (ascending && r + 1 < R && g1 > g0) row_hi = std::min<int64_t>(N, (int64_t)guide_rows[gene_offsets[g1] - 1] + 1);
             else if (!ascending && r > 0) row_hi = row_done;
             if (row_hi > row_done) {
-                if ((e = cudaMemcpyAsync((char*)ctx->res_test.p + row_done * row_t, (const char*)io->test + row_done * row_t,
-                                         (row_hi - row_done) * row_t, cudaMemcpyHostToDevice, s_in)) != cudaSuccess) { rc = cuda_fail(e, "H2D test"); break; }
-                if ((e = cudaMemcpyAsync((char*)ctx->res_ctrl.p + row_done * row_c, (const char*)io->ctrl + row_done * row_c,
-                                         (row_hi - row_done) * row_c, cudaMemcpyHostToDevice, s_in)) != cudaSuccess) { rc = cuda_fail(e, "H2D ctrl"); break; }
+                // pinned caller memory goes up directly; pageable memory through the pinned ring with threaded host copies
+                if ((rc = ctx->stager.h2d((char*)ctx->res_test.p + row_done * row_t, (const char*)io->test + row_done * row_t,
+                                          (row_hi - row_done) * row_t, s_in)) != JACKS_OK) break;
+                if ((rc = ctx->stager.h2d((char*)ctx->res_ctrl.p + row_done * row_c, (const char*)io->ctrl + row_done * row_c,
+                                          (row_hi - row_done) * row_c, s_in)) != JACKS_OK) break;
                 row_done = row_hi;
             }
             cudaEventRecord(ev_in[r], s_in);
@@ -503,12 +599,27 @@ int jacks_em_batched_host(JacksCtx* ctx, const JacksEmParams* params, const int6
         if (g1 > g0) rc = em_run_range(ctx, plan, params, &dio, s_k, g0, g1, r);
         if (rc != JACKS_OK) break;
         cudaEventRecord(ev_k[r], s_k);
+        if (staged_out) continue;          // downloads follow below, once every range is enqueued
         cudaStreamWaitEvent(s_out, ev_k[r], 0);
         const int64_t t0 = gene_offsets[g0], t1 = gene_offsets[g1];
         for (int i = 0; i < 8 && rc == JACKS_OK; ++i) {
             if (!dptr[i]) continue;
             const size_t lo = outs[i].unit * (size_t)(outs[i].per_guide ? t0 : g0), hi = outs[i].unit * (size_t)(outs[i].per_guide ? t1 : g1);
             if (hi > lo && (e = cudaMemcpyAsync(outs[i].host + lo, dptr[i] + lo, hi - lo, cudaMemcpyDeviceToHost, s_out)) != cudaSuccess) rc = cuda_fail(e, "D2H result");
+        }
+    }
+    if (staged_out) {
+        // Synchronous call: the host thread drains range r (through the pinned ring when the caller's arrays are
+        // pageable) while the kernels of the later ranges run.
+        for (int r = 0; r < R && rc == JACKS_OK; ++r) {
+            const int64_t g0 = n_genes * r / R, g1 = n_genes * (r + 1) / R;
+            const int64_t t0 = gene_offsets[g0], t1 = gene_offsets[g1];
+            cudaStreamWaitEvent(s_out, ev_k[r], 0);
+            for (int i = 0; i < 8 && rc == JACKS_OK; ++i) {
+                if (!dptr[i]) continue;
+                const size_t lo = outs[i].unit * (size_t)(outs[i].per_guide ? t0 : g0), hi = outs[i].unit * (size_t)(outs[i].per_guide ? t1 : g1);
+                if (hi > lo) rc = ctx->stager.d2h(outs[i].host + lo, dptr[i] + lo, hi - lo, s_out);
+            }
         }
     }
     for (int r = 0; r < R; ++r) { if (ev_in[r]) ctx->pending_events.push_back(ev_in[r]); if (ev_k[r]) ctx->pending_events.push_back(ev_k[r]); }
@@ -621,8 +732,8 @@ int jacks_em_lines_host(JacksCtx* ctx, const JacksEmParams* params, const int64_
         if ((rc = ctx->res_ctrl.reserve(cube ? cube : 8)) != JACKS_OK) return rc;
         ctx->res_N = N; ctx->res_L = L; ctx->res_ctrl_lines = L; ctx->res_valid = true;
         if (cube) {
-            if ((e = cudaMemcpyAsync(ctx->res_test.p, io->test, cube, cudaMemcpyHostToDevice, st)) != cudaSuccess) return cuda_fail(e, "H2D test");
-            if ((e = cudaMemcpyAsync(ctx->res_ctrl.p, io->ctrl, cube, cudaMemcpyHostToDevice, st)) != cudaSuccess) return cuda_fail(e, "H2D ctrl");
+            if ((rc = ctx->stager.h2d(ctx->res_test.p, io->test, cube, st)) != JACKS_OK) return rc;
+            if ((rc = ctx->stager.h2d(ctx->res_ctrl.p, io->ctrl, cube, st)) != JACKS_OK) return rc;
         }
     } else if (!ctx->res_valid || ctx->res_N != N || ctx->res_L != L || ctx->res_ctrl_lines != L) {
         return fail(JACKS_E_INVALID, "test is NULL but no matching resident data cube (call with keep_resident first)");
@@ -664,7 +775,7 @@ int jacks_em_lines_host(JacksCtx* ctx, const JacksEmParams* params, const int64_
         dio.y = (double*)dptr[4]; dio.tau = (double*)dptr[5]; dio.n_iters = (int32_t*)dptr[6]; dio.bound = (double*)dptr[7];
         if ((rc = em_check_io(plan, params, &dio)) == JACKS_OK) rc = em_lines_run(ctx, plan, params, &dio, st);
         for (int i = 0; i < 8 && rc == JACKS_OK; ++i)
-            if (dptr[i] && (e = cudaMemcpyAsync(outs[i].host, dptr[i], nbytes[i], cudaMemcpyDeviceToHost, st)) != cudaSuccess) rc = cuda_fail(e, "D2H result");
+            if (dptr[i]) rc = ctx->stager.d2h(outs[i].host, dptr[i], nbytes[i], st);
     }
     ctx->pending_plans.push_back(plan);
     if (!(flags & JACKS_KEEP_RESIDENT)) ctx->res_valid = false;

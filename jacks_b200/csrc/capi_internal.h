@@ -38,6 +38,23 @@ struct PlanBufs {
 
 struct JacksEmPlan;
 
+// Staged copies between PAGEABLE host memory and the device.  cudaMemcpy on pageable memory moves 11 GB/s up and only
+// 2 GB/s down into freshly allocated pages on this box (tools/pcie_probe.py; the page faults of a first touch are
+// taken by one driver thread); here chunks pass through two pinned buffers while several host threads copy the
+// previous chunk to / from the caller's memory (and take the first-touch faults in parallel).  Pinned host memory
+// is recognised and copied directly.  Both calls return when the host side is complete (the device side of an
+// upload may still be in flight on `st`).
+struct HostStager {
+    static constexpr size_t kChunk = 32u << 20;
+    void* buf[2] = {nullptr, nullptr};
+    cudaEvent_t ev[2] = {nullptr, nullptr};
+    int threads = 0;
+    int init();
+    void release();
+    int h2d(void* dst_dev, const void* src_host, size_t bytes, cudaStream_t st);
+    int d2h(void* dst_host, const void* src_dev, size_t bytes, cudaStream_t st);
+};
+
 struct JacksCtx {
     int device;
     int n_sm;
@@ -52,6 +69,7 @@ struct JacksCtx {
     bool res_valid = false;
     jacks::DevBuf out[8];       // device-side outputs of the host entry points
     jacks::DevBuf tmp;          // scratch of the p-value / preprocessing entry points
+    HostStager stager;          // pinned ring of the synchronous host entry points (pageable caller buffers)
     std::vector<PlanBufs*> plan_pool;          // recycled plan buffers
     std::vector<JacksEmPlan*> pending_plans;   // plans of asynchronous host calls, destroyed at the next synchronise
     std::vector<cudaEvent_t> pending_events;

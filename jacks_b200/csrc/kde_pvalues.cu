@@ -438,12 +438,12 @@ extern "C" int jacks_kde_pvalues_host(JacksCtx* ctx, const double* w1_genes, int
     if ((rc = ctx->out[1].reserve(pb)) != JACKS_OK) return rc;
     if ((rc = ctx->out[2].reserve(gb)) != JACKS_OK) return rc;
     cudaStream_t st = ctx->stream;
-    if ((e = cudaMemcpyAsync(ctx->out[0].p, w1_genes, gb, cudaMemcpyHostToDevice, st)) != cudaSuccess) return cuda_fail(e, "H2D w1_genes");
-    if ((e = cudaMemcpyAsync(ctx->out[1].p, w1_pseudo, pb, cudaMemcpyHostToDevice, st)) != cudaSuccess) return cuda_fail(e, "H2D w1_pseudo");
+    if ((rc = ctx->stager.h2d(ctx->out[0].p, w1_genes, gb, st)) != JACKS_OK) return rc;
+    if ((rc = ctx->stager.h2d(ctx->out[1].p, w1_pseudo, pb, st)) != JACKS_OK) return rc;
     rc = jacks_kde_pvalues_device(ctx, (const double*)ctx->out[0].p, n_genes, (const double*)ctx->out[1].p, n_pseudo,
                                   n_lines, positive, (double*)ctx->out[2].p, st);
     if (rc != JACKS_OK) return rc;
-    if ((e = cudaMemcpyAsync(pvals, ctx->out[2].p, gb, cudaMemcpyDeviceToHost, st)) != cudaSuccess) return cuda_fail(e, "D2H pvals");
+    if ((rc = ctx->stager.d2h(pvals, ctx->out[2].p, gb, st)) != JACKS_OK) return rc;
     if ((e = cudaStreamSynchronize(st)) != cudaSuccess) return cuda_fail(e, "kde kernels");
     return JACKS_OK;
 }
@@ -464,8 +464,8 @@ extern "C" int jacks_kde_eval_host(JacksCtx* ctx, const double* w_eval, int64_t 
     const long long ld = ((long long)n_null + kChunk - 1) / kChunk * kChunk;
     if ((rc = ctx->tmp.reserve((size_t)ld * n_lines * sizeof(double) + (size_t)n_lines * 8 * sizeof(double))) != JACKS_OK) return rc;
     cudaStream_t st = ctx->stream;
-    if ((e = cudaMemcpyAsync(ctx->out[0].p, w_eval, gb, cudaMemcpyHostToDevice, st)) != cudaSuccess) return cuda_fail(e, "H2D w_eval");
-    if ((e = cudaMemcpyAsync(ctx->out[1].p, w_null, pb, cudaMemcpyHostToDevice, st)) != cudaSuccess) return cuda_fail(e, "H2D w_null");
+    if ((rc = ctx->stager.h2d(ctx->out[0].p, w_eval, gb, st)) != JACKS_OK) return rc;
+    if ((rc = ctx->stager.h2d(ctx->out[1].p, w_null, pb, st)) != JACKS_OK) return rc;
     double* sT = (double*)ctx->tmp.p;
     double* stats = sT + ld * n_lines;
     kde_line_stats<<<n_lines, kStatsThreads, 0, st>>>((const double*)ctx->out[1].p, n_null, n_lines, ld, kind == 1 ? 1 : 0, sT, stats);
@@ -474,7 +474,7 @@ extern "C" int jacks_kde_eval_host(JacksCtx* ctx, const double* w_eval, int64_t 
                                                  leave_one_out ? 1 : 0, (double*)ctx->out[2].p);
     ctx->launches += 2;
     if ((e = cudaGetLastError()) != cudaSuccess) return cuda_fail(e, "kde_eval launch");
-    if ((e = cudaMemcpyAsync(out, ctx->out[2].p, gb, cudaMemcpyDeviceToHost, st)) != cudaSuccess) return cuda_fail(e, "D2H kde");
+    if ((rc = ctx->stager.d2h(out, ctx->out[2].p, gb, st)) != JACKS_OK) return rc;
     if ((e = cudaStreamSynchronize(st)) != cudaSuccess) return cuda_fail(e, "kde kernels");
     return JACKS_OK;
 }

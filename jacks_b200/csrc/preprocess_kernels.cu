@@ -525,7 +525,7 @@ extern "C" int jacks_normalize_host(JacksCtx* ctx, const double* values, int64_t
     if ((rc = ctx->out[3].reserve((size_t)N + 8)) != JACKS_OK) return rc;
     if ((rc = ctx->tmp.reserve(mb + 2 * (size_t)C * sizeof(double))) != JACKS_OK) return rc;
     cudaStream_t st = ctx->stream;
-    if ((e = cudaMemcpyAsync(ctx->out[0].p, values, mb, cudaMemcpyHostToDevice, st)) != cudaSuccess) return cuda_fail(e, "H2D values");
+    if ((rc = ctx->stager.h2d(ctx->out[0].p, values, mb, st)) != JACKS_OK) return rc;
     if (table_len && (e = cudaMemcpyAsync(ctx->out[2].p, log2_table, (size_t)table_len * sizeof(double), cudaMemcpyHostToDevice, st)) != cudaSuccess) return cuda_fail(e, "H2D log2 table");
     const unsigned char* d_mask = nullptr;
     if (normtype == JACKS_NORM_CTRL_GUIDES) {
@@ -551,7 +551,7 @@ extern "C" int jacks_normalize_host(JacksCtx* ctx, const double* values, int64_t
     untranspose_shift_kernel<<<tg, 256, 0, st>>>(T, N, N, C, med, scale, (double*)ctx->out[1].p);
     ctx->launches++;
     if ((e = cudaGetLastError()) != cudaSuccess) return cuda_fail(e, "normalize kernels");
-    if ((e = cudaMemcpyAsync(out, ctx->out[1].p, mb, cudaMemcpyDeviceToHost, st)) != cudaSuccess) return cuda_fail(e, "D2H normalised");
+    if ((rc = ctx->stager.d2h(out, ctx->out[1].p, mb, st)) != JACKS_OK) return rc;
     if ((e = cudaStreamSynchronize(st)) != cudaSuccess) return cuda_fail(e, "normalize kernels");
     return JACKS_OK;
 }
@@ -596,7 +596,7 @@ extern "C" int jacks_condense_host(JacksCtx* ctx, const double* logcounts, int64
     cudaStream_t st = ctx->stream;
     int* d_off = (int*)ctx->out[7].p;
     int* d_cols = d_off + S + 1;
-    if ((e = cudaMemcpyAsync(ctx->out[0].p, logcounts, lb, cudaMemcpyHostToDevice, st)) != cudaSuccess) return cuda_fail(e, "H2D logcounts");
+    if ((rc = ctx->stager.h2d(ctx->out[0].p, logcounts, lb, st)) != JACKS_OK) return rc;
     if ((e = cudaMemcpyAsync(d_off, sample_col_offsets, (S + 1) * sizeof(int), cudaMemcpyHostToDevice, st)) != cudaSuccess) return cuda_fail(e, "H2D offsets");
     if ((e = cudaMemcpyAsync(d_cols, sample_cols, nidx * sizeof(int), cudaMemcpyHostToDevice, st)) != cudaSuccess) return cuda_fail(e, "H2D cols");
     double* km = (double*)ctx->out[2].p; double* kv = (double*)ctx->out[3].p; int* ki = (int*)ctx->out[4].p;
@@ -622,7 +622,7 @@ extern "C" int jacks_condense_host(JacksCtx* ctx, const double* logcounts, int64
         ctx->launches++;
     }
     if ((e = cudaGetLastError()) != cudaSuccess) return cuda_fail(e, "condense kernels");
-    if ((e = cudaMemcpyAsync(data, ctx->out[1].p, db, cudaMemcpyDeviceToHost, st)) != cudaSuccess) return cuda_fail(e, "D2H data");
+    if ((rc = ctx->stager.d2h(data, ctx->out[1].p, db, st)) != JACKS_OK) return rc;
     if ((e = cudaStreamSynchronize(st)) != cudaSuccess) return cuda_fail(e, "condense kernels");
     return JACKS_OK;
 }
@@ -658,7 +658,7 @@ extern "C" int jacks_posterior_sd_subset_host(JacksCtx* ctx, const double* data,
     int* d_off = (int*)ctx->out[7].p;
     int* d_cols = d_off + 2;
     unsigned char* d_set = (unsigned char*)(d_cols + n_rep);
-    if ((e = cudaMemcpyAsync(ctx->out[0].p, data, lb, cudaMemcpyHostToDevice, st)) != cudaSuccess) return cuda_fail(e, "H2D data");
+    if ((rc = ctx->stager.h2d(ctx->out[0].p, data, lb, st)) != JACKS_OK) return rc;
     if ((e = cudaMemcpyAsync(d_off, h.data(), h.size() * sizeof(int), cudaMemcpyHostToDevice, st)) != cudaSuccess) return cuda_fail(e, "H2D index");
     if ((e = cudaMemcpyAsync(d_set, in_set, (size_t)N, cudaMemcpyHostToDevice, st)) != cudaSuccess) return cuda_fail(e, "H2D subset");
     double* km = (double*)ctx->out[2].p; double* kv = (double*)ctx->out[3].p; int* ki = (int*)ctx->out[4].p;
@@ -681,7 +681,7 @@ extern "C" int jacks_posterior_sd_subset_host(JacksCtx* ctx, const double* data,
                                                   scratch + 2 * (N + 1), scratch + 3 * (N + 1), (double*)ctx->out[6].p);
     ctx->launches++;
     if ((e = cudaGetLastError()) != cudaSuccess) return cuda_fail(e, "subset sd kernels");
-    if ((e = cudaMemcpyAsync(sd, ctx->out[6].p, (size_t)N * sizeof(double), cudaMemcpyDeviceToHost, st)) != cudaSuccess) return cuda_fail(e, "D2H sd");
+    if ((rc = ctx->stager.d2h(sd, ctx->out[6].p, (size_t)N * sizeof(double), st)) != JACKS_OK) return rc;
     if ((e = cudaStreamSynchronize(st)) != cudaSuccess) return cuda_fail(e, "subset sd kernels");
     return JACKS_OK;
 }

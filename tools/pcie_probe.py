@@ -41,3 +41,20 @@ def both():
 for name, fn in (('h2d', h2d), ('d2h', d2h), ('both', both)):
     ms = timed(fn)
     print('%-5s %.2f ms per GiB  -> %.1f GB/s per direction' % (name, ms, n / ms / 1e6))
+
+# pageable host memory (what a numpy caller hands to the host entry points)
+import time
+import numpy as np
+a = np.random.default_rng(0).random(n // 8)
+t = torch.from_numpy(a)
+for _ in range(2):
+    t0 = time.perf_counter(); d = t.cuda(); torch.cuda.synchronize(); t1 = time.perf_counter()
+print('pageable h2d %.1f ms per GiB -> %.1f GB/s' % ((t1 - t0) * 1e3, n / (t1 - t0) / 1e9))
+for _ in range(2):
+    t0 = time.perf_counter(); b = d.cpu(); t1 = time.perf_counter()
+print('pageable d2h %.1f ms per GiB -> %.1f GB/s' % ((t1 - t0) * 1e3, n / (t1 - t0) / 1e9))
+dst = np.empty_like(a)
+t0 = time.perf_counter(); np.copyto(dst, a); t1 = time.perf_counter()
+print('host memcpy (1 thread) %.1f ms per GiB -> %.1f GB/s' % ((t1 - t0) * 1e3, n / (t1 - t0) / 1e9))
+import os
+print('cpus', os.cpu_count())
