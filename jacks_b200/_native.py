@@ -180,14 +180,28 @@ class Context(object):
 
 
 _ctx = {}
+_ctx_lock = threading.Lock()
 
 
 def context(device=0):
     """Process-wide context of a device (created on first use)."""
     device = int(device)
-    if device not in _ctx:
-        _ctx[device] = Context(device)
-    return _ctx[device]
+    with _ctx_lock:
+        if device not in _ctx:
+            _ctx[device] = Context(device)
+        return _ctx[device]
+
+
+def warm_context(device=0):
+    """Start creating the device context (CUDA initialisation, ~1 s) on a background thread, so that it overlaps host
+    work such as parsing the count table; the first context() call waits for it.  Errors surface at that call."""
+    def run():
+        try:
+            context(device)
+        except Exception:
+            pass
+    if int(device) not in _ctx:
+        threading.Thread(target=run, name='jacks-b200-ctx', daemon=True).start()
 
 
 def as_csr(gene_index):

@@ -21,8 +21,10 @@
 #include <sys/stat.h>
 #include <unistd.h>
 
+#include <algorithm>
 #include <string>
 #include <thread>
+#include <utility>
 #include <vector>
 
 #include "../../include/jacks_b200.h"
@@ -106,51 +108,71 @@ extern "C" int jacks_table_read(const char* path, int64_t data_offset, char deli
     const char* b = m.p + data_offset;
     const char* end = m.p + m.n;
     const char* next = b;
-    int64_t r = 0;
-    std::string tmp;
-    while (b < end && r < n_records) {
+    // pass 1 (serial, a byte scan): record boundaries; pass 2 (threads): split and convert the fields of each record
+    std::vector<std::pair<const char*, const char*>> recs;
+    recs.reserve((size_t)n_records);
+    while (b < end && (int64_t)recs.size() < n_records) {
         const char* e = record_end(b, end, &next);
-        if (e == b) { b = next; continue; }
-        for (int i = 0; i < n_sel; ++i) { values[r * n_sel + i] = NAN; if (not_numeric) not_numeric[r * n_sel + i] = 1; }
-        for (int k = 0; k < n_str; ++k) { label_off[r * n_str + k] = 0; label_len[r * n_str + k] = -1; }     // -1: field absent
-        const char* f = b;
-        int col = 0;
-        while (f <= e) {
-            const char* fe;
-            const char* vb; const char* ve;
-            if (f < e && *f == '"') {                         // quoted field
-                const char* q = f + 1;
-                while (q < e) { if (*q == '"') { if (q + 1 < e && q[1] == '"') { q += 2; continue; } break; } ++q; }
-                vb = f + 1; ve = q;
-                fe = (q < e) ? q + 1 : e;
-                while (fe < e && *fe != delim) ++fe;
-            } else {
-                fe = f;
-                while (fe < e && *fe != delim) ++fe;
-                vb = f; ve = fe;
-            }
-            for (int k = 0; k < n_str; ++k)
-                if (col == str_cols[k]) { label_off[r * n_str + k] = (int64_t)(vb - m.p); label_len[r * n_str + k] = (int32_t)(ve - vb); }
-            if (col <= max_col && !want[col].empty()) {
-                while (vb < ve && (*vb == ' ' || *vb == '\t')) ++vb;
-                while (ve > vb && (ve[-1] == ' ' || ve[-1] == '\t')) --ve;
-                if (ve > vb) {
-                    tmp.assign(vb, ve);
-                    char* stop = nullptr;
-                    errno = 0;
-                    const double v = strtod(tmp.c_str(), &stop);
-                    // plain decimal literals only: Python's eval() reads "0x10", "1_000", "nan" differently from strtod
-                    bool plain = (stop == tmp.c_str() + tmp.size());
-                    for (char ch : tmp) if (!((ch >= '0' && ch <= '9') || ch == '.' || ch == '-' || ch == '+' || ch == 'e' || ch == 'E')) { plain = false; break; }
-                    if (plain) for (int slot : want[col]) { values[r * n_sel + slot] = v; if (not_numeric) not_numeric[r * n_sel + slot] = 0; }
-                }
-            }
-            ++col;
-            if (fe >= e) break;
-            f = fe + 1;
-        }
-        ++r;
+        if (e != b) recs.emplace_back(b, e);
         b = next;
+    }
+    int64_t r = (int64_t)recs.size();
+    auto parse_block = [&](int64_t r0, int64_t r1) {
+        std::string tmp;
+        for (int64_t r = r0; r < r1; ++r) {
+            const char* b = recs[(size_t)r].first;
+            const char* e = recs[(size_t)r].second;
+            for (int i = 0; i < n_sel; ++i) { values[r * n_sel + i] = NAN; if (not_numeric) not_numeric[r * n_sel + i] = 1; }
+            for (int k = 0; k < n_str; ++k) { label_off[r * n_str + k] = 0; label_len[r * n_str + k] = -1; }     // -1: field absent
+            const char* f = b;
+            int col = 0;
+            while (f <= e) {
+                const char* fe;
+                const char* vb; const char* ve;
+                if (f < e && *f == '"') {                         // quoted field
+                    const char* q = f + 1;
+                    while (q < e) { if (*q == '"') { if (q + 1 < e && q[1] == '"') { q += 2; continue; } break; } ++q; }
+                    vb = f + 1; ve = q;
+                    fe = (q < e) ? q + 1 : e;
+                    while (fe < e && *fe != delim) ++fe;
+                } else {
+                    fe = f;
+                    while (fe < e && *fe != delim) ++fe;
+                    vb = f; ve = fe;
+                }
+                for (int k = 0; k < n_str; ++k)
+                    if (col == str_cols[k]) { label_off[r * n_str + k] = (int64_t)(vb - m.p); label_len[r * n_str + k] = (int32_t)(ve - vb); }
+                if (col <= max_col && !want[col].empty()) {
+                    while (vb < ve && (*vb == ' ' || *vb == '\t')) ++vb;
+                    while (ve > vb && (ve[-1] == ' ' || ve[-1] == '\t')) --ve;
+                    if (ve > vb) {
+                        tmp.assign(vb, ve);
+                        char* stop = nullptr;
+                        const double v = strtod(tmp.c_str(), &stop);
+                        // plain decimal literals only: Python's eval() reads "0x10", "1_000", "nan" differently from strtod
+                        bool plain = (stop == tmp.c_str() + tmp.size());
+                        for (char ch : tmp) if (!((ch >= '0' && ch <= '9') || ch == '.' || ch == '-' || ch == '+' || ch == 'e' || ch == 'E')) { plain = false; break; }
+                        if (plain) for (int slot : want[col]) { values[r * n_sel + slot] = v; if (not_numeric) not_numeric[r * n_sel + slot] = 0; }
+                    }
+                }
+                ++col;
+                if (fe >= e) break;
+                f = fe + 1;
+            }
+        }
+    };
+    unsigned hw = std::thread::hardware_concurrency();
+    int n_thr = (int)std::max(1u, std::min(16u, hw ? hw : 1u));
+    if (m.n < (4u << 20) || r < 1024) n_thr = 1;
+    if (n_thr == 1) parse_block(0, r);
+    else {
+        std::vector<std::thread> pool;
+        const int64_t per = (r + n_thr - 1) / n_thr;
+        for (int t = 0; t < n_thr; ++t) {
+            const int64_t r0 = per * t, r1 = std::min<int64_t>(r, r0 + per);
+            if (r0 < r1) pool.emplace_back(parse_block, r0, r1);
+        }
+        for (auto& th : pool) th.join();
     }
     if (r != n_records) return fail(JACKS_E_INVALID, "%s: expected %lld records, found %lld", path, (long long)n_records, (long long)r);
     return JACKS_OK;

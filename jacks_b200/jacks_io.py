@@ -396,6 +396,7 @@ def load_data_and_run(sample_spec, gene_spec, ctrl_spec, sgrna_reference_file, x
                       apply_w_hp=APPLY_W_HP_DEFAULT, norm_type=NORM_TYPE_DEFAULT, ctrl_genes=None, fdr=None,
                       fdr_thresh_type='REGULAR', n_pseudo=0, count_prior=32, positive=False):
     """Preprocess, infer, (optionally) build the pseudo-gene null and write every output file (jacks_io.py:379-428)."""
+    _native.warm_context(0)
     ctrl_geneset = readControlGeneset(ctrl_genes, gene_spec) if ctrl_genes is not None else set()
     if '/' in outprefix and not os.path.exists(os.path.dirname(outprefix)):
         os.makedirs(os.path.dirname(outprefix))
@@ -451,6 +452,7 @@ def runJACKS(countfile, replicatefile, guidemappingfile, rep_hdr=REP_HDR_DEFAULT
              ctrl_genes=None, fdr=None, fdr_thresh_type='REGULAR', outprefix=OUTPREFIX_DEFAULT, reffile=None, n_pseudo=0,
              count_prior=32, positive=False):
     """The whole pipeline from three file names (jacks_io.py:430-442)."""
+    _native.warm_context(0)        # CUDA initialisation (~1 s) overlaps the parsing of the input files
     sample_spec, ctrl_spec, gene_spec, x_ref = preprocess(countfile, replicatefile, guidemappingfile, rep_hdr, sample_hdr,
                                                           common_ctrl_sample, ctrl_sample_hdr, sgrna_hdr, gene_hdr,
                                                           ignore_blank_genes, outprefix, reffile)
