@@ -161,8 +161,12 @@ typedef struct JacksEmHostIO {
  *          index); JACKS_ASYNC -- return as soon as the work is enqueued; outputs are complete, and the host
  *          buffers may be reused, after jacks_ctx_synchronize().  A following call on the same context queues
  *          behind it, so the real-gene and pseudo-gene passes of one screen overlap their transfers.
+ *          JACKS_UPLOAD_USED_ROWS -- upload only the rows the index references (gathered on the host into a compact cube;
+ *          any resident screen stays untouched).  For the pseudo-gene index of jacks_io.py:416, which draws from a few
+ *          thousand control guides, that is tens of megabytes instead of the screen: issued on a second context it lets
+ *          the pseudo-gene kernels and downloads run while the real-gene call is still uploading.
  */
-enum { JACKS_KEEP_RESIDENT = 1, JACKS_ASYNC = 2 };
+enum { JACKS_KEEP_RESIDENT = 1, JACKS_ASYNC = 2, JACKS_UPLOAD_USED_ROWS = 4 };
 JACKS_API int jacks_em_batched_host(JacksCtx* ctx, const JacksEmParams* params,
                           const int64_t* gene_offsets, const int32_t* guide_rows, int64_t n_genes,
                           const JacksEmHostIO* io, int32_t flags);

@@ -257,10 +257,13 @@ class EmPlan(object):
 
 def em_batched_host(ctx, offsets, rows, test, ctrl, params=None, fixed_x1=None, fixed_x2=None,
                     want=('x1', 'x2', 'w1', 'w2', 'y', 'tau', 'n_iters', 'bound'), ctrl_rowmean_fill=False,
-                    keep_resident=False, n_rows=None, n_lines=None, ctrl_lines=None, out=None, sync=True):
+                    keep_resident=False, n_rows=None, n_lines=None, ctrl_lines=None, out=None, sync=True,
+                    used_rows_only=False):
     """jacks_em_batched_host on numpy arrays.  test [N,L,2], ctrl [N,L,2] or [N,1,2] float64 C-contiguous
     (or test=None to reuse the cubes a previous keep_resident call left on the device, with
-    n_rows/n_lines/ctrl_lines given).  Returns a dict of the requested outputs."""
+    n_rows/n_lines/ctrl_lines given).  used_rows_only: upload just the rows the index references
+    (JACKS_UPLOAD_USED_ROWS: a pseudo-gene index over a few thousand control guides moves tens of megabytes instead
+    of the screen).  Returns a dict of the requested outputs."""
     params = params or default_params()
     offsets = np.ascontiguousarray(offsets, dtype=np.int64)
     rows = np.asarray(rows)
@@ -297,7 +300,7 @@ def em_batched_host(ctx, offsets, rows, test, ctrl, params=None, fixed_x1=None, 
         io.fixed_x1, io.fixed_x2 = _ptr(fixed_x1), _ptr(fixed_x2)
     for k in res:
         setattr(io, k, _ptr(res[k]))
-    flags = (1 if keep_resident else 0) | (0 if sync else 2)
+    flags = (1 if keep_resident else 0) | (0 if sync else 2) | (4 if used_rows_only else 0)
     check(lib().jacks_em_batched_host(ctx.h, C.byref(params), _ptr(offsets), _ptr(rows), n_genes, C.byref(io), flags))
     if not sync:
         # the C side reads these host arrays until ctx.synchronize(): keep them alive with the result

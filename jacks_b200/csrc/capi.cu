@@ -245,6 +245,9 @@ void jacks_ctx_destroy(JacksCtx* c) {
     for (auto& b : c->out) b.release();
     c->tmp.release();
     c->stager.release();
+    if (c->cmp_stage) cudaFreeHost(c->cmp_stage);
+    if (c->cmp_ready) cudaEventDestroy(c->cmp_ready);
+    c->cmp_dev.release(); c->cmp_rows.release();
     if (c->stream) cudaStreamDestroy(c->stream);
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     if (c->out_stream) cudaStreamDestroy(c->out_stream);
@@ -490,10 +493,154 @@ int jacks_em_run_device(JacksCtx* ctx, const JacksEmPlan* plan, const JacksEmPar
     return em_run_range(ctx, plan, params, io, st, 0, plan->n_genes, 0);
 }
 
-int jacks_em_batched_host(JacksCtx* ctx, const JacksEmParams* params, const int64_t* gene_offsets,
-                          const int32_t* guide_rows, int64_t n_genes, const JacksEmHostIO* io, int32_t keep_resident) {
-    if (!ctx || !params || !io) return fail(JACKS_E_INVALID, "jacks_em_batched_host: NULL argument");
+}  // extern "C"
+
+// Device cubes that hold only the rows an index references (JACKS_UPLOAD_USED_ROWS), already enqueued for upload.
+struct CompactCubes {
+    const double* d_test; const double* d_ctrl;
+    const double* d_fx1; const double* d_fx2;
+    int64_t n_rows;
+    cudaEvent_t ready;
+};
+
+static int em_batched_host_core(JacksCtx* ctx, const JacksEmParams* params, const int64_t* gene_offsets,
+                                const int32_t* guide_rows, int64_t n_genes, const JacksEmHostIO* io, int32_t keep_resident,
+                                const CompactCubes* cc);
+
+// Row gather straight out of PINNED host memory (zero-copy reads over PCIe): one CTA per (row, cube), 16-byte loads.
+// The SMs pull the rows themselves, so neither a host-side gather nor the H2D copy engine's queue (FIFO across
+// streams: a small copy enqueued behind a screen-sized upload waits for all of it) stands in the way.
+__global__ void __launch_bounds__(128) gather_rows_kernel(const double2* __restrict__ src_test, const double2* __restrict__ src_ctrl,
+                                                          const long long* __restrict__ used, long long row_t2, long long row_c2,
+                                                          double2* __restrict__ dst_test, double2* __restrict__ dst_ctrl) {
+    const long long u = blockIdx.x;
+    const long long r = used[u];
+    const bool is_ctrl = blockIdx.y != 0;
+    const long long n = is_ctrl ? row_c2 : row_t2;
+    const double2* s = (is_ctrl ? src_ctrl : src_test) + r * n;
+    double2* d = (is_ctrl ? dst_ctrl : dst_test) + u * n;
+    for (long long i = threadIdx.x; i < n; i += blockDim.x) d[i] = s[i];
+}
+
+// JACKS_UPLOAD_USED_ROWS: gather the rows the index references (ascending) into a compact cube -- by a kernel reading
+// the caller's pinned memory directly, or on the host (all cores, pinned staging) when the memory is pageable --
+// and run the EM on a re-based index.  For a pseudo-gene index over a few thousand control guides
+// this moves tens of megabytes instead of the whole screen, so its kernels and downloads need not wait for it.
+static int em_batched_host_compact(JacksCtx* ctx, const JacksEmParams* params, const int64_t* gene_offsets,
+                                   const int32_t* guide_rows, int64_t n_genes, const JacksEmHostIO* io, int32_t flags) {
     const int64_t N = io->n_rows;
+    const int L = io->n_lines;
+    const int64_t T = n_genes ? gene_offsets[n_genes] : 0;
+    std::vector<int32_t> remap((size_t)N, -1);
+    for (int64_t i = 0; i < T; ++i) {
+        const int32_t r = guide_rows[i];
+        if (r < 0 || r >= N) return fail(JACKS_E_INVALID, "guide row %d at position %lld outside [0, %lld)", r, (long long)i, (long long)N);
+        remap[(size_t)r] = 0;
+    }
+    std::vector<int64_t> used;
+    for (int64_t r = 0; r < N; ++r)
+        if (remap[(size_t)r] == 0) { remap[(size_t)r] = (int32_t)used.size(); used.push_back(r); }
+    const int64_t U = (int64_t)used.size();
+    std::vector<int32_t> rows2((size_t)T);
+    for (int64_t i = 0; i < T; ++i) rows2[(size_t)i] = remap[(size_t)guide_rows[i]];
+    const size_t row_t = (size_t)L * 2 * sizeof(double), row_c = (size_t)io->ctrl_lines * 2 * sizeof(double);
+    const bool fx = io->fixed_x1 && io->fixed_x2;
+    const size_t bytes = (size_t)U * (row_t + row_c + (fx ? 2 * sizeof(double) : 0));
+    cudaError_t e;
+    int rc;
+    // staging is reused from call to call: wait until the previous compact upload has read it
+    if (ctx->cmp_ready && (e = cudaEventSynchronize(ctx->cmp_ready)) != cudaSuccess) return cuda_fail(e, "compact staging event");
+    if (bytes > ctx->cmp_stage_cap) {
+        if (ctx->cmp_stage) cudaFreeHost(ctx->cmp_stage);
+        ctx->cmp_stage = nullptr; ctx->cmp_stage_cap = 0;
+        if ((e = cudaHostAlloc(&ctx->cmp_stage, bytes + (bytes >> 2) + 4096, cudaHostAllocDefault)) != cudaSuccess) return cuda_fail(e, "cudaHostAlloc(compact staging)");
+        ctx->cmp_stage_cap = bytes + (bytes >> 2) + 4096;
+    }
+    if (!ctx->cmp_ready && (e = cudaEventCreateWithFlags(&ctx->cmp_ready, cudaEventDisableTiming)) != cudaSuccess) return cuda_fail(e, "cudaEventCreate");
+    if ((rc = ctx->cmp_dev.reserve(bytes ? bytes : 8)) != JACKS_OK) return rc;
+    char* st_test = (char*)ctx->cmp_stage;
+    char* st_ctrl = st_test + (size_t)U * row_t;
+    double* st_fx = (double*)(st_ctrl + (size_t)U * row_c);
+    cudaStream_t s_in = ctx->copy_stream;
+    const bool zero_copy = U > 0 && host_pointer_is_pinned(io->test) && host_pointer_is_pinned(io->ctrl);
+    if (zero_copy) {
+        // the list of rows and the (small) fixed-x gather go through the staging buffer; the cubes are pulled by the GPU
+        long long* st_used = (long long*)ctx->cmp_stage;            // staging is at least U*(row_t+row_c) >= 32*U bytes
+        for (int64_t u = 0; u < U; ++u) st_used[u] = used[(size_t)u];
+        if ((rc = ctx->cmp_rows.reserve((size_t)U * sizeof(long long))) != JACKS_OK) return rc;
+        if ((e = cudaMemcpyAsync(ctx->cmp_rows.p, st_used, (size_t)U * sizeof(long long), cudaMemcpyHostToDevice, s_in)) != cudaSuccess) return cuda_fail(e, "H2D used rows");
+        void* dt = nullptr; void* dc = nullptr;
+        if ((e = cudaHostGetDevicePointer(&dt, (void*)io->test, 0)) != cudaSuccess) return cuda_fail(e, "cudaHostGetDevicePointer");
+        if ((e = cudaHostGetDevicePointer(&dc, (void*)io->ctrl, 0)) != cudaSuccess) return cuda_fail(e, "cudaHostGetDevicePointer");
+        char* dev = (char*)ctx->cmp_dev.p;
+        gather_rows_kernel<<<dim3((unsigned)U, 2), 128, 0, s_in>>>((const double2*)dt, (const double2*)dc, (const long long*)ctx->cmp_rows.p,
+                                                                   (long long)L, (long long)io->ctrl_lines, (double2*)dev,
+                                                                   (double2*)(dev + (size_t)U * row_t));
+        if ((e = cudaGetLastError()) != cudaSuccess) return cuda_fail(e, "gather_rows_kernel launch");
+        ctx->launches++;
+        if (fx) {
+            std::vector<double> hfx((size_t)(2 * U));
+            for (int64_t u = 0; u < U; ++u) { hfx[(size_t)u] = io->fixed_x1[used[(size_t)u]]; hfx[(size_t)(U + u)] = io->fixed_x2[used[(size_t)u]]; }
+            if ((e = cudaMemcpyAsync(dev + (size_t)U * (row_t + row_c), hfx.data(), hfx.size() * sizeof(double), cudaMemcpyHostToDevice, s_in)) != cudaSuccess) return cuda_fail(e, "H2D fixed_x");
+            if ((e = cudaStreamSynchronize(s_in)) != cudaSuccess) return cuda_fail(e, "H2D fixed_x");      // hfx goes out of scope
+        }
+    } else {
+        const unsigned hw = std::thread::hardware_concurrency();
+        int n_thr = (int)std::max(1u, std::min(8u, hw ? hw / 2 : 1u));
+        if (bytes < (4u << 20)) n_thr = 1;
+        auto gather = [&](int64_t u0, int64_t u1) {
+            for (int64_t u = u0; u < u1; ++u) {
+                const int64_t r = used[(size_t)u];
+                memcpy(st_test + (size_t)u * row_t, (const char*)io->test + (size_t)r * row_t, row_t);
+                memcpy(st_ctrl + (size_t)u * row_c, (const char*)io->ctrl + (size_t)r * row_c, row_c);
+                if (fx) { st_fx[u] = io->fixed_x1[r]; st_fx[U + u] = io->fixed_x2[r]; }
+            }
+        };
+        std::vector<std::thread> pool;
+        const int64_t per = (U + n_thr - 1) / n_thr;
+        for (int t = 1; t < n_thr; ++t) {
+            const int64_t u0 = per * t, u1 = std::min<int64_t>(U, u0 + per);
+            if (u0 < u1) pool.emplace_back(gather, u0, u1);
+        }
+        gather(0, std::min<int64_t>(U, per));
+        for (auto& th : pool) th.join();
+        if (bytes && (e = cudaMemcpyAsync(ctx->cmp_dev.p, ctx->cmp_stage, bytes, cudaMemcpyHostToDevice, s_in)) != cudaSuccess) return cuda_fail(e, "H2D compact cube");
+    }
+    cudaEventRecord(ctx->cmp_ready, s_in);
+    CompactCubes cc;
+    cc.d_test = (const double*)ctx->cmp_dev.p;
+    cc.d_ctrl = (const double*)((const char*)ctx->cmp_dev.p + (size_t)U * row_t);
+    cc.d_fx1 = fx ? (const double*)((const char*)ctx->cmp_dev.p + (size_t)U * (row_t + row_c)) : nullptr;
+    cc.d_fx2 = fx ? cc.d_fx1 + U : nullptr;
+    cc.n_rows = U;
+    cc.ready = ctx->cmp_ready;
+    return em_batched_host_core(ctx, params, gene_offsets, rows2.data(), n_genes, io, flags, &cc);
+}
+
+extern "C" {
+
+int jacks_em_batched_host(JacksCtx* ctx, const JacksEmParams* params, const int64_t* gene_offsets,
+                          const int32_t* guide_rows, int64_t n_genes, const JacksEmHostIO* io, int32_t flags) {
+    if (!ctx || !params || !io) return fail(JACKS_E_INVALID, "jacks_em_batched_host: NULL argument");
+    if ((flags & JACKS_UPLOAD_USED_ROWS) && io->test) {
+        if (!io->ctrl) return fail(JACKS_E_INVALID, "ctrl is NULL");
+        if (io->n_rows < 0 || io->n_lines < 1) return fail(JACKS_E_INVALID, "bad data shape N=%lld L=%d", (long long)io->n_rows, io->n_lines);
+        if (io->ctrl_lines != io->n_lines && io->ctrl_lines != 1)
+            return fail(JACKS_E_SHAPE, "Expecting matched size between control and test data");
+        if ((io->fixed_x1 == nullptr) != (io->fixed_x2 == nullptr)) return fail(JACKS_E_INVALID, "fixed_x1 and fixed_x2 go together");
+        cudaError_t e = cudaSetDevice(ctx->device);
+        if (e != cudaSuccess) return cuda_fail(e, "cudaSetDevice");
+        return em_batched_host_compact(ctx, params, gene_offsets, guide_rows, n_genes, io, flags);
+    }
+    return em_batched_host_core(ctx, params, gene_offsets, guide_rows, n_genes, io, flags, nullptr);
+}
+
+}  // extern "C"
+
+static int em_batched_host_core(JacksCtx* ctx, const JacksEmParams* params, const int64_t* gene_offsets,
+                                const int32_t* guide_rows, int64_t n_genes, const JacksEmHostIO* io, int32_t keep_resident,
+                                const CompactCubes* cc) {
+    const int64_t N = cc ? cc->n_rows : io->n_rows;
     const int L = io->n_lines;
     if (N < 0 || L < 1) return fail(JACKS_E_INVALID, "bad data shape N=%lld L=%d", (long long)N, L);
     if (io->ctrl_lines != L && io->ctrl_lines != 1)
@@ -505,8 +652,10 @@ int jacks_em_batched_host(JacksCtx* ctx, const JacksEmParams* params, const int6
 
     // ---- inputs: upload, or reuse the cubes a previous call left resident -------------------------
     const size_t row_t = (size_t)L * 2 * sizeof(double), row_c = (size_t)io->ctrl_lines * 2 * sizeof(double);
-    const bool upload = (io->test != nullptr);
-    if (upload) {
+    const bool upload = (io->test != nullptr) && !cc;
+    if (cc) {
+        // compact cubes: uploaded by the caller, the resident screen (if any) stays as it is
+    } else if (upload) {
         if (!io->ctrl) return fail(JACKS_E_INVALID, "ctrl is NULL");
         if ((rc = ctx->res_test.reserve(N ? N * row_t : 8)) != JACKS_OK) return rc;
         if ((rc = ctx->res_ctrl.reserve(N ? N * row_c : 8)) != JACKS_OK) return rc;
@@ -515,8 +664,8 @@ int jacks_em_batched_host(JacksCtx* ctx, const JacksEmParams* params, const int6
         if (!ctx->res_valid || ctx->res_N != N || ctx->res_L != L || ctx->res_ctrl_lines != io->ctrl_lines)
             return fail(JACKS_E_INVALID, "test is NULL but no matching resident data cube (call with keep_resident first)");
     }
-    const double* d_fx1 = nullptr; const double* d_fx2 = nullptr;
-    if (io->fixed_x1 || io->fixed_x2) {
+    const double* d_fx1 = cc ? cc->d_fx1 : nullptr; const double* d_fx2 = cc ? cc->d_fx2 : nullptr;
+    if (!cc && (io->fixed_x1 || io->fixed_x2)) {
         if (!io->fixed_x1 || !io->fixed_x2) return fail(JACKS_E_INVALID, "fixed_x1 and fixed_x2 go together");
         if ((rc = ctx->res_fx.reserve((size_t)N * 2 * sizeof(double) + 8)) != JACKS_OK) return rc;
         if (N) {
@@ -547,12 +696,13 @@ int jacks_em_batched_host(JacksCtx* ctx, const JacksEmParams* params, const int6
     }
     JacksEmDeviceIO dio;
     memset(&dio, 0, sizeof dio);
-    dio.test = (const double*)ctx->res_test.p; dio.ctrl = (const double*)ctx->res_ctrl.p;
+    dio.test = cc ? cc->d_test : (const double*)ctx->res_test.p; dio.ctrl = cc ? cc->d_ctrl : (const double*)ctx->res_ctrl.p;
     dio.ctrl_lines = io->ctrl_lines; dio.ctrl_rowmean_fill = io->ctrl_rowmean_fill;
     dio.fixed_x1 = d_fx1; dio.fixed_x2 = d_fx2;
     dio.x1 = (double*)dptr[0]; dio.x2 = (double*)dptr[1]; dio.w1 = (double*)dptr[2]; dio.w2 = (double*)dptr[3];
     dio.y = (double*)dptr[4]; dio.tau = (double*)dptr[5]; dio.n_iters = (int32_t*)dptr[6]; dio.bound = (double*)dptr[7];
     rc = (n_genes > 0) ? em_check_io(plan, params, &dio) : JACKS_OK;
+    if (cc) cudaStreamWaitEvent(s_k, cc->ready, 0);          // the compact cubes are on their way on the copy stream
 
     // ---- pipeline: gene ranges flow through upload -> kernels -> download on three streams ------------
     // Ranges are contiguous gene blocks.  When the guide rows ascend along the index (a real screen: genes own
@@ -625,13 +775,15 @@ int jacks_em_batched_host(JacksCtx* ctx, const JacksEmParams* params, const int6
     for (int r = 0; r < R; ++r) { if (ev_in[r]) ctx->pending_events.push_back(ev_in[r]); if (ev_k[r]) ctx->pending_events.push_back(ev_k[r]); }
     if (ev_start) ctx->pending_events.push_back(ev_start);
     ctx->pending_plans.push_back(plan);
-    if (!(keep_resident & JACKS_KEEP_RESIDENT)) ctx->res_valid = false;
+    if (!cc && !(keep_resident & JACKS_KEEP_RESIDENT)) ctx->res_valid = false;
     if (rc != JACKS_OK || !(keep_resident & JACKS_ASYNC)) {
         const int rs = jacks_ctx_synchronize(ctx);
         if (rc == JACKS_OK) rc = rs;
     }
     return rc;
 }
+
+extern "C" {
 
 // ---- per-line ("single JACKS") inference ----------------------------------------------------------------------------
 

@@ -69,6 +69,10 @@ struct JacksCtx {
     bool res_valid = false;
     jacks::DevBuf out[8];       // device-side outputs of the host entry points
     jacks::DevBuf tmp;          // scratch of the p-value / preprocessing entry points
+    // compact cubes of JACKS_UPLOAD_USED_ROWS calls: pinned staging, device copy, "upload enqueued" event
+    void* cmp_stage = nullptr; size_t cmp_stage_cap = 0;
+    jacks::DevBuf cmp_dev, cmp_rows;
+    cudaEvent_t cmp_ready = nullptr;
     HostStager stager;          // pinned ring of the synchronous host entry points (pageable caller buffers)
     std::vector<PlanBufs*> plan_pool;          // recycled plan buffers
     std::vector<JacksEmPlan*> pending_plans;   // plans of asynchronous host calls, destroyed at the next synchronise

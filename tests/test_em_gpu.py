@@ -278,3 +278,39 @@ def test_tensor_memory_variant_forced(mode):
     r = subprocess.run([sys.executable, '-m', 'pytest', os.path.abspath(__file__), '-m', 'gpu', '-q', '-x', '-k',
                         'golden or shape_sweep or fixed_x'], env=env, capture_output=True, text=True, timeout=1500)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+
+
+def test_used_rows_only_upload_is_identical(nat):
+    """JACKS_UPLOAD_USED_ROWS (compact cube of the rows an index references, re-based index) changes what is uploaded,
+    not what is computed: bit-identical outputs for a pseudo-gene-like index over scattered rows, with and without
+    fixed x, on a second context, synchronously and asynchronously."""
+    rng = np.random.default_rng(5)
+    Gs = [4] * 300 + [3, 5, 9, 1]
+    offs, rows, test, ctrl = _random_screen(rng, Gs, 64, sd_nan_frac=0.01)
+    N = test.shape[0]
+    pool = rng.choice(N, size=90, replace=False)                   # "control guides"
+    p_rows = rng.choice(pool, size=4 * 500).astype(np.int32)       # pseudo-genes draw them with replacement
+    p_offs = (4 * np.arange(501)).astype(np.int64)
+    ctx2 = nat.Context(0)
+    fx1, fx2 = rng.uniform(0.5, 1.5, N), rng.uniform(1.0, 3.0, N)
+    for kw in ({}, dict(fixed_x1=fx1, fixed_x2=fx2)):
+        full = nat.em_batched_host(nat.context(0), p_offs, p_rows, test, ctrl, **kw)
+        part = nat.em_batched_host(ctx2, p_offs, p_rows, test, ctrl, used_rows_only=True, **kw)
+        for k in full:
+            assert np.array_equal(full[k], part[k], equal_nan=True), k
+    # pinned caller memory: the GPU gathers the rows itself (zero-copy reads), no host gather
+    pt, pc = nat.PinnedArray(test.shape), nat.PinnedArray(ctrl.shape)
+    pt.array[...] = test; pc.array[...] = ctrl
+    full = nat.em_batched_host(nat.context(0), p_offs, p_rows, test, ctrl, fixed_x1=fx1, fixed_x2=fx2)
+    part = nat.em_batched_host(ctx2, p_offs, p_rows, pt.array, pc.array, used_rows_only=True, fixed_x1=fx1, fixed_x2=fx2)
+    for k in full:
+        assert np.array_equal(full[k], part[k], equal_nan=True), ('pinned', k)
+    # asynchronous, interleaved with a full call on the first context
+    a = nat.em_batched_host(nat.context(0), offs, rows, test, ctrl, sync=False)
+    b = nat.em_batched_host(ctx2, p_offs, p_rows, test, ctrl, used_rows_only=True, sync=False)
+    ctx2.synchronize(); nat.context(0).synchronize()
+    ref = nat.em_batched_host(nat.context(0), p_offs, p_rows, test, ctrl)
+    for k in ref:
+        assert np.array_equal(ref[k], b[k], equal_nan=True), k
+    assert np.isfinite(a['w1']).all()
+    ctx2.close()
