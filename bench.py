@@ -404,8 +404,12 @@ def main():
         npz = len(p_offs) - 1
         out_p = {k: _native.PinnedArray((npz, L), np.float64) for k in ('w1', 'w2')}
     # the pseudo-gene call runs on a second context and uploads only the control-guide rows its index references
-    ctx2 = _native.Context(local_rank) if p_offs is not None else None
-    n_used = 0 if p_offs is None else int(np.unique(p_rows).size)
+    # (one rank per box only: with several ranks the GPUs of this pool share their PCIe uplink, and the fully
+    # bidirectional pattern then moves FEWER bytes per second in aggregate than the reference's call order does --
+    # measured at 2 ranks: 45.9 ms against 37.4 ms per step)
+    two_ctx = p_offs is not None and world == 1
+    ctx2 = _native.Context(local_rank) if two_ctx else None
+    n_used = int(np.unique(p_rows).size) if two_ctx else 0
     h2d = pin_test.array.nbytes + pin_ctrl.array.nbytes + r_offs.nbytes + r_rows.nbytes + \
         (0 if p_offs is None else p_offs.nbytes + p_rows.nbytes + n_used * 2 * L * 16)
     d2h = sum(v.array.nbytes for v in out_r.values()) + (0 if out_p is None else sum(v.array.nbytes for v in out_p.values()))
@@ -417,13 +421,18 @@ def main():
         # real-gene call streams the whole screen up range by range -- both PCIe directions stay busy.  (Issued second,
         # its small uploads would queue behind the screen in the copy engine's FIFO.)
         keep = []
-        if out_p is not None:
+        if two_ctx:
             keep.append(_native.em_batched_host(ctx2, p_offs, p_rows, pin_test.array, pin_ctrl.array, params=params,
                                                 want=('w1', 'w2'), out={k: v.array for k, v in out_p.items()},
                                                 sync=False, used_rows_only=True))
         keep.append(_native.em_batched_host(ctx, r_offs, r_rows, pin_test.array, pin_ctrl.array, params=params, want=tuple(out_r),
-                                            out={k: v.array for k, v in out_r.items()}, sync=False))
-        if out_p is not None:
+                                            out={k: v.array for k, v in out_r.items()}, keep_resident=not two_ctx, sync=False))
+        if out_p is not None and not two_ctx:
+            # several ranks: the reference's order on one context, the pseudo-genes reading the resident cubes
+            keep.append(_native.em_batched_host(ctx, p_offs, p_rows, None, None, params=params, n_rows=N, n_lines=L,
+                                                ctrl_lines=L, want=('w1', 'w2'), out={k: v.array for k, v in out_p.items()},
+                                                sync=False))
+        if two_ctx:
             ctx2.synchronize()
         ctx.synchronize()
 
@@ -460,7 +469,7 @@ def main():
                'dtype': 'f64', 'data': 'synthetic', 'config': workload_config(args, world),
                'clocks': clk, 'gpu_launches': int(launches),
                'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': int(d2h),
-                       'ms_per_step': 1e3 * float(te.item()), 'api': 'jacks_em_batched_host (C-ABI), pinned host buffers; pseudo-gene call on a second context with JACKS_UPLOAD_USED_ROWS'},
+                       'ms_per_step': 1e3 * float(te.item()), 'api': 'jacks_em_batched_host (C-ABI), pinned host buffers' + ('; pseudo-gene call first, on a second context, with JACKS_UPLOAD_USED_ROWS' if two_ctx else '; real then pseudo on one context, cubes kept resident')},
                'roofline': {'bound': 'fp64', 'achieved': tf, 'peak': fp64_peak / 1e12, 'unit': 'TFLOP/s',
                             'frac': tf / (fp64_peak / 1e12), 'traffic': ncu_traffic(),
                             'peak_source': 'FP64 FMA-pipe peak measured in this run (jacks_fp64_peak_flops); '
