@@ -313,4 +313,8 @@ def test_used_rows_only_upload_is_identical(nat):
     for k in ref:
         assert np.array_equal(ref[k], b[k], equal_nan=True), k
     assert np.isfinite(a['w1']).all()
+    empty = nat.em_batched_host(ctx2, np.zeros(1, np.int64), np.zeros(0, np.int32), test, ctrl, used_rows_only=True)
+    assert empty['w1'].shape == (0, test.shape[1])
+    with pytest.raises(IndexError):
+        nat.em_batched_host(ctx2, np.array([0, 1], np.int64), np.array([N], np.int32), test, ctrl, used_rows_only=True)
     ctx2.close()
