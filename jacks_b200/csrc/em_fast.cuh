@@ -99,6 +99,27 @@ __device__ __forceinline__ double median_small(const double (&v)[G]) {
     return (k_lo == k_hi) ? lo : 0.5 * (lo + hi);
 }
 
+// Maximum, minimum and median of G FINITE values in one go (the X step's normaliser, infer.py:108).  Plain compares
+// and selects: fmax/fmin spend instructions on NaN operands the fast path never sees; for G = 4 one five-comparator
+// network yields all three (the median stays the exact mean of the two middle elements, as numpy forms it).
+__device__ __forceinline__ double sel_max(double a, double b) { return a > b ? a : b; }
+__device__ __forceinline__ double sel_min(double a, double b) { return a < b ? a : b; }
+template <int G>
+__device__ __forceinline__ void max_min_median(const double (&v)[G], double& hi, double& lo, double& med) {
+    if (G == 4) {
+        const double lo1 = sel_min(v[0], v[1]), hi1 = sel_max(v[0], v[1]);
+        const double lo2 = sel_min(v[2], v[3]), hi2 = sel_max(v[2], v[3]);
+        hi = sel_max(hi1, hi2);
+        lo = sel_min(lo1, lo2);
+        med = 0.5 * (sel_max(lo1, lo2) + sel_min(hi1, hi2));
+        return;
+    }
+    hi = v[0]; lo = v[0];
+#pragma unroll
+    for (int g = 1; g < G; ++g) { hi = sel_max(hi, v[g]); lo = sel_min(lo, v[g]); }
+    med = median_small<G>(v);
+}
+
 // All-reduce of NV doubles over the team (W warps); every thread ends up with bit-identical sums
 // (fixed summation order), which keeps the convergence test uniform.
 // A butterfly over 32 lanes costs 5*NV shuffle pairs + 5*NV DADDs plus register moves (~320
@@ -732,11 +753,12 @@ __global__ void __launch_bounds__(TM ? kTmemTeams * 32 : W * 32, TM ? 2 : 0) em_
                         xu[g] = fma(2.0, acc[g], mx) * rden;
                         x2u[g] = fma(xu[g], xu[g], rden);
                     }
-                    double sum = xu[0], hi = xu[0], lo = xu[0];
+                    double sum = xu[0], hi, lo, med;
 #pragma unroll
-                    for (int g = 1; g < G; ++g) { sum += xu[g]; hi = fmax(hi, xu[g]); lo = fmin(lo, xu[g]); }
+                    for (int g = 1; g < G; ++g) sum += xu[g];
+                    max_min_median<G>(xu, hi, lo, med);
                     const double wadj = 0.5 / G;
-                    const double x1m = sum * (1.0 / G) + 2 * wadj * median_small<G>(xu) - wadj * hi - wadj * lo;
+                    const double x1m = sum * (1.0 / G) + 2 * wadj * med - wadj * hi - wadj * lo;
                     const double rm = fast_rcp(x1m);
                     const double rm2 = rm * rm;
 #pragma unroll
