@@ -72,11 +72,12 @@ __global__ void __launch_bounds__(128) em_lines_kernel(const EmLaunch a) {
                     xu[g] = (mx + s1[g]) * rden;
                     x2u[g] = fma(xu[g], xu[g], rden);
                 }
-                double sum = xu[0], hi = xu[0], lo = xu[0];
+                double sum = xu[0], hi, lo, med;
 #pragma unroll
-                for (int g = 1; g < G; ++g) { sum += xu[g]; hi = fmax(hi, xu[g]); lo = fmin(lo, xu[g]); }
+                for (int g = 1; g < G; ++g) sum += xu[g];
+                max_min_median<G>(xu, hi, lo, med);
                 const double wadj = 0.5 / G;
-                const double x1m = sum * (1.0 / G) + 2 * wadj * median_small<G>(xu) - wadj * hi - wadj * lo;
+                const double x1m = sum * (1.0 / G) + 2 * wadj * med - wadj * hi - wadj * lo;
                 const double rm = fast_rcp(x1m);
                 const double rm2 = rm * rm;
 #pragma unroll
