@@ -351,6 +351,9 @@ __device__ __noinline__ EmSums<G> em_sweep_all(const uint32_t tbase, const uint3
 #pragma unroll
             for (int g = 0; g < G; ++g) pd[u][g] = __ldg(tpdg + g * Lp + l + u * STEP);
     }
+    // the previous pass's (or the initialisation's) TMEM stores must have landed before these columns are read
+    // back; waiting here rather than after the last store hides the store latency behind the reduction and X step
+    if (TM) tmem_wait_st();
     uint32_t tcol = tbase;
     for (; n > U; n -= U, l += U * STEP, tcol += 2 * U * G)
         em_sweep<G, U, U, UNIT_C, false, true, TM>(tcol, tcol + pdoff, ys, pd, tpdg + l + U * STEP, Lp, ths, w1p, w2g, L, l, STEP, x, ivw, mw, c_tau, a1, a2, ab, true);
@@ -359,7 +362,6 @@ __device__ __noinline__ EmSums<G> em_sweep_all(const uint32_t tbase, const uint3
     else if (n == 2) em_sweep<G, 2, U, UNIT_C, true, false, TM>(tcol, tcol + pdoff, ys, pd, nullptr, Lp, ths, w1p, w2g, L, l, STEP, x, ivw, mw, c_tau, a1, a2, ab, valid);
     else if (U >= 3 && n == 3) em_sweep<G, (U >= 3 ? 3 : 1), U, UNIT_C, true, false, TM>(tcol, tcol + pdoff, ys, pd, nullptr, Lp, ths, w1p, w2g, L, l, STEP, x, ivw, mw, c_tau, a1, a2, ab, valid);
     else if (U == 4 && n == 4) em_sweep<G, (U == 4 ? 4 : 1), U, UNIT_C, true, false, TM>(tcol, tcol + pdoff, ys, pd, nullptr, Lp, ths, w1p, w2g, L, l, STEP, x, ivw, mw, c_tau, a1, a2, ab, valid);
-    if (TM) tmem_wait_st();          // the next pass reads these columns back
     EmSums<G> r;
     // sum pd2*th = sum (t1 - x2*w2)*th: the accumulators hold sum t1*th
     r.ab = fma(-x.x2[0], a2[0], ab[0]);
@@ -798,6 +800,7 @@ __global__ void __launch_bounds__(TM ? kTmemTeams * 32 : W * 32, TM ? 2 : 0) em_
 
             // ---- write results ------------------------------------------------------------------
             if (TM && a.tau) {
+                tmem_wait_st();
 #pragma unroll 1
                 for (int i = 0; i < n_warp; ++i) {
                     const int l = l0 + i * STEP;
