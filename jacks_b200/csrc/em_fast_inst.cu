@@ -45,10 +45,13 @@ cudaError_t launch_tmem(const EmLaunch& a0, int n_sm, int grid_limit, cudaStream
 }
 
 // Which variant for this shape?  0: shared memory; 1: tau in TMEM; 2: tau and tau_pr_den in TMEM.
-// The TMEM variants run at most two CTAs (8 genes) per SM (registers).  Variant 2 needs both arrays of two CTAs in the 512
-// columns (L <= 512 at G = 4) and is then preferred even at equal gene count: a pass makes no L2 round trip at all.
-// Variant 1 pays when it puts more genes on an SM than shared memory does (measured at G = 4, L = 800: 8 against 4 genes,
-// 5.1 ms against 6.9 ms per 39,000 genes).  JACKS_EM_TMEM=0/1/2 forces the choice where eligible (tests, tuning).
+// The TMEM variants run at most two CTAs (8 genes) per SM (registers).  Measured per pass at 400 lines, 39,000 genes
+// (ms; smem / mode 1 / mode 2): G=3 1.63 / 1.64 / 1.45, G=4 2.6 / 2.7 / 2.3, G=5 5.09 / 3.60 / 4.79, G=6 7.73 / 7.36 / 8.28,
+// G=8 10.2 / 13.2 / 10.6; and mode 2 against shared memory at G=4 with 64 / 128 / 256 / 320 / 800 lines: 0.99 / 1.09,
+// 1.57 / 1.60, 2.76 / 2.99, 3.36 / 3.76, (mode 1) 5.1 / 6.9.  Hence: mode 2 whenever both arrays of two CTAs fit the 512
+// columns (it wins even against 12 shared-memory genes: a pass makes no L2 round trip); otherwise mode 1 when it puts
+// more genes on an SM than shared memory does; otherwise shared memory.  JACKS_EM_TMEM=0/1/2 forces the choice where
+// eligible (tests, tuning).
 template <int G>
 int tmem_mode(const EmLaunch& a) {
     static const int force = []() { const char* e = getenv("JACKS_EM_TMEM"); return e ? atoi(e) : -1; }();
@@ -62,7 +65,7 @@ int tmem_mode(const EmLaunch& a) {
     const long long genes2 = cols2 ? std::min<long long>(std::min<long long>(by_smem, 512 / cols2), 2) * kTmemTeams : 0;
     if (force == 2) return genes2 ? 2 : 1;
     if (force == 1) return 1;
-    if (genes2 >= genes_smem && genes2 >= genes1) return 2;
+    if (genes2 == 2 * kTmemTeams && a.L >= 32) return 2;
     if (genes1 > genes_smem) return 1;
     return 0;
 }

@@ -19,7 +19,8 @@ def main():
     ctx = _native.context(0)
     print('fp64 peak TFLOP/s', ctx.fp64_peak_flops() / 1e12, flush=True)
     n_lines = int(os.environ.get('QB_LINES', 400))
-    gi, test, ctrl, ctrl_genes = synth.make_condensed_screen(n_genes=n_genes, n_lines=n_lines)
+    guides = int(os.environ.get('QB_GUIDES', 4))
+    gi, test, ctrl, ctrl_genes = synth.make_condensed_screen(n_genes=n_genes, n_lines=n_lines, guides_per_gene=guides)
     names, offs, rows = _native.as_csr(gi)
     ctrl_ids = [names.index(g) for g in ctrl_genes]
     poffs, prows = synth.make_pseudo_index_csr(offs, ctrl_ids, n_pseudo)
@@ -59,7 +60,7 @@ def main():
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / reps
         it = iters.cpu().numpy()
-        flops = (19.0 * it.astype(np.float64) + 12.0).sum() * 4 * L
+        flops = (19.0 * it.astype(np.float64) + 12.0).sum() * guides * L
         print('shape %-8s  %8.3f ms  %10.0f genes/s  mean_iters %.2f  algorithmic %.2f TFLOP/s' %
               (shape, ms, n_all / ms * 1e3, it.mean(), flops / ms / 1e9), flush=True)
         plan.close()
