@@ -41,9 +41,6 @@
 namespace jacks {
 
 #define JACKS_FULL_MASK 0xffffffffu
-#ifndef JACKS_TMU
-#define JACKS_TMU 4      // lines per sweep step of the tensor-memory variant (G <= 6)
-#endif
 
 __device__ __forceinline__ double warp_allsum(double v) {
 #pragma unroll
@@ -341,7 +338,9 @@ __device__ __noinline__ EmSums<G> em_sweep_all(const uint32_t tbase, const uint3
     double a1[G], a2[G], ab[G];
 #pragma unroll
     for (int g = 0; g < G; ++g) { a1[g] = 0.0; a2[g] = 0.0; ab[g] = 0.0; }
-    constexpr int U = (G >= 7) ? 2 : (TM ? JACKS_TMU : 4);       // lines per step: U*G >= 8 independent elements
+    // lines per step: U*G >= 8 independent elements, and few enough (<= 20) to stay in registers
+    // (measured at 400 lines: G = 5 wants 3 lines from shared memory, 4 from TMEM; G = 6 wants 3 either way)
+    constexpr int U = (G >= 7) ? 2 : ((G >= (TM ? 6 : 5)) ? 3 : 4);
     int l = l0;
     int n = n_warp;
     double pd[U][G];
