@@ -251,23 +251,39 @@ __global__ void __launch_bounds__(128) kde_cell_moments(const double* __restrict
     rec[kK + 1] = (double)first;
 }
 
-__global__ void __launch_bounds__(128) kde_pvalues_fast(const double* __restrict__ w1_genes, long long n_genes, int L,
-                                                        const double* __restrict__ sT, long long ld,
-                                                        const double* __restrict__ stats, const long long* __restrict__ cell_off,
-                                                        const double* __restrict__ cells, int positive,
-                                                        double* __restrict__ pvals) {
+// One CTA evaluates kFastGenes genes of one line.  The line's cell table (a few hundred 144-byte records that every
+// gene of the line walks a ~45-cell window of) is staged in shared memory first: read from L2 by every thread it was
+// 47 GB per Avana-shaped call, i.e. the kernel ran at L2 bandwidth.  A table too large for the CTA's shared memory
+// is read in place.
+constexpr int kFastThreads = 256;
+constexpr int kFastPerThread = 4;
+constexpr int kFastGenes = kFastThreads * kFastPerThread;
+constexpr int kFastSmemCells = 480;          // 67.5 KB: three CTAs per SM
+
+__global__ void __launch_bounds__(kFastThreads) kde_pvalues_fast(const double* __restrict__ w1_genes, long long n_genes, int L,
+                                                                 const double* __restrict__ sT, long long ld,
+                                                                 const double* __restrict__ stats, const long long* __restrict__ cell_off,
+                                                                 const double* __restrict__ cells, int positive,
+                                                                 double* __restrict__ pvals) {
+    extern __shared__ double s_tab[];
     const int l = blockIdx.y;
     const long long nc = cell_off[l + 1] - cell_off[l];
     if (nc == 0) return;                                   // this line is left to the brute-force kernel
-    const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (g >= n_genes) return;
+    const double* ctab = cells + cell_off[l] * kCellRec;
+    if (nc <= kFastSmemCells) {
+        for (long long i = threadIdx.x; i < nc * kCellRec; i += kFastThreads) s_tab[i] = ctab[i];
+        __syncthreads();
+        ctab = s_tab;
+    }
     const double h = stats[l * 8 + 0];
     const int n = (int)stats[l * 8 + 1];
     const double cterm = stats[l * 8 + 2], wgt = stats[l * 8 + 3];
     const double* row = sT + (long long)l * ld;
-    const double* ctab = cells + cell_off[l] * kCellRec;
+  for (int k = 0; k < kFastPerThread; ++k) {
+    const long long g = ((long long)blockIdx.x * kFastPerThread + k) * kFastThreads + threadIdx.x;
+    if (g >= n_genes) break;
     const double w = positive ? -w1_genes[g * L + l] : w1_genes[g * L + l];
-    if (!(w == w)) { pvals[g * L + l] = w; return; }
+    if (!(w == w)) { pvals[g * L + l] = w; continue; }
     const double rh = 1.0 / h;
     const double smin = row[0];
     const double zmax = (w - smin) * rh;
@@ -308,6 +324,7 @@ __global__ void __launch_bounds__(128) kde_pvalues_fast(const double* __restrict
         }
     }
     pvals[g * L + l] = (tot - cterm) * wgt;
+  }
 }
 
 // General KDE evaluation for the branches the command line does not reach (jacks_io.py:76-88):
@@ -413,8 +430,10 @@ extern "C" int jacks_kde_pvalues_device(JacksCtx* ctx, const double* w1_genes, i
         }
         kde_cell_layout<<<1, 1, 0, st>>>(sT, ld, stats, n_lines, cell_cap, cell_off);
         kde_cell_moments<<<(unsigned)((cell_cap + 127) / 128), 128, 0, st>>>(sT, ld, stats, n_lines, cell_off, cells);
-        dim3 fg((unsigned)((n_genes + 127) / 128), (unsigned)n_lines);
-        kde_pvalues_fast<<<fg, 128, 0, st>>>(w1_genes, n_genes, n_lines, sT, ld, stats, cell_off, cells, positive ? 1 : 0, pvals);
+        dim3 fg((unsigned)((n_genes + kFastGenes - 1) / kFastGenes), (unsigned)n_lines);
+        const size_t fsm = (size_t)kFastSmemCells * kCellRec * sizeof(double);
+        if ((e = cudaFuncSetAttribute(kde_pvalues_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsm)) != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute");
+        kde_pvalues_fast<<<fg, kFastThreads, fsm, st>>>(w1_genes, n_genes, n_lines, sT, ld, stats, cell_off, cells, positive ? 1 : 0, pvals);
         ctx->launches += 3;
     }
     // lines the cell table could not hold (pathological ranges), or everything when forced
