@@ -94,3 +94,39 @@ def infer_sharded(offsets, rows, testdata, ctrldata, compute=None, group=None, d
     recv = recv.cpu().numpy().reshape(world, cap)
     parts = [_unpack(recv[r], sizes[r][0], sizes[r][1], L, per_line) for r in range(world)]
     return {k: np.concatenate([p[k] for p in parts]) for k in ('w1', 'w2', 'x1', 'x2', 'n_iters')}
+
+
+def pvalues_sharded(w1_genes, w1_pseudo, positive=False, compute=None, group=None, device=None):
+    """KDE p-values of every gene against the pseudo-gene null (computeW1PvalsAndFDRs with pseudo=True,
+    jacks_io.py:69-89), sharded by gene over the ranks of ``group``.
+
+    Every rank holds the full ``w1_genes [n, L]`` and ``w1_pseudo [n_pseudo, L]`` (what infer_sharded returns), builds
+    the per-line kernel density of the null itself -- it is a few hundred kilobytes of state, cheaper to rebuild than to
+    ship -- and evaluates a contiguous block of genes; ONE all-gather reassembles ``[n, L]``.  p-values of a gene do not
+    depend on the other genes, so the result is bit-identical to the unsharded call.
+    ``compute(w1_block, w1_pseudo, positive) -> [m, L]`` evaluates one block; by default the GPU path of this rank."""
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    w1_genes = np.ascontiguousarray(w1_genes, dtype=np.float64)
+    n, L = w1_genes.shape
+    if compute is None:
+        from . import _native
+
+        def compute(block, pseudo, pos):
+            return _native.kde_pvalues_host(_native.context(device or 0), block, pseudo, positive=pos)
+    b = np.linspace(0, n, world + 1).astype(np.int64)
+    lo, hi = int(b[rank]), int(b[rank + 1])
+    mine = compute(w1_genes[lo:hi], w1_pseudo, positive) if hi > lo else np.zeros((0, L))
+    if world == 1:
+        return np.asarray(mine)
+    cap = int(np.max(np.diff(b))) * L
+    on_gpu = dist.get_backend(group) == 'nccl'
+    dev = torch.device('cuda', device if device is not None else torch.cuda.current_device()) if on_gpu else torch.device('cpu')
+    send = torch.zeros(cap, dtype=torch.float64, device=dev)
+    send[:mine.size] = torch.from_numpy(np.ascontiguousarray(mine).reshape(-1)).to(dev)
+    recv = torch.empty(world * cap, dtype=torch.float64, device=dev)
+    dist.all_gather_into_tensor(recv, send, group=group)
+    recv = recv.cpu().numpy().reshape(world, cap)
+    return np.concatenate([recv[r, :int(b[r + 1] - b[r]) * L].reshape(-1, L) for r in range(world)])

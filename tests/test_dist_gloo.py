@@ -43,6 +43,13 @@ def _worker(rank, world, port, q):
         got = jd.infer_sharded(offs, rows, test, ctrl, compute=compute_lines, per_line=True)
         ref = compute_lines(offs, rows, test, ctrl)
         ok = ok and all(got[k].shape == ref[k].shape and np.array_equal(got[k], ref[k]) for k in ('w1', 'w2', 'x1', 'x2', 'n_iters'))
+        # p-values of every gene against a pseudo-gene null, gene-sharded (BASELINE config 5)
+        from oracle import jacks_oracle as O
+        rng = np.random.default_rng(9)
+        wg, wp = rng.normal(-0.2, 0.6, size=(23, 3)), rng.normal(0.0, 0.2, size=(57, 3))
+        wg[4, 1] = np.nan
+        pv = jd.pvalues_sharded(wg, wp, positive=False, compute=lambda blk, ps, pos: O.kde_pvalues(blk, ps, positive=pos))
+        ok = ok and np.array_equal(pv, O.kde_pvalues(wg, wp), equal_nan=True)
         q.put((rank, bool(ok), jd.shard_bounds(offs, world).tolist()))
     finally:
         dist.destroy_process_group()
