@@ -49,28 +49,34 @@ __global__ void __launch_bounds__(kStatsThreads) kde_line_stats(const double* __
                                                                 double* __restrict__ sT, double* __restrict__ stats) {
     __shared__ double sh[kStatsThreads / 32];
     __shared__ int s_base;
+    __shared__ int s_cnt[kStatsThreads / 32];
     // Positive selection is computed as negative selection of the mirrored problem (s -> -s, w -> -w):
     // Phi((100-s)/h) - Phi((w-s)/h) = Phi((-w+s)/h) - Phi((-100+s)/h), which also avoids the 1 - Phi cancellation.
     const double sgn = positive ? -1.0 : 1.0;
     const int l = blockIdx.x;
     double* row = sT + (long long)l * ld;
-    // compaction, order preserving within a block pass (order does not matter for the sum)
+    // Order-preserving compaction (a block-wide scan of the per-warp counts, no atomics): the row order fixes the order
+    // of the sums below, so mean, bandwidth and the gene-independent term are bit-reproducible from run to run and do
+    // not depend on which genes are evaluated with them.
     if (threadIdx.x == 0) s_base = 0;
     __syncthreads();
     double sum = 0.0;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (long long i0 = 0; i0 < n_pseudo; i0 += kStatsThreads) {
         const long long i = i0 + threadIdx.x;
         double v = 0.0;
         bool ok = false;
         if (i < n_pseudo) { v = w1_pseudo[i * L + l]; ok = (v == v); }      // jacks_io.py:78 drops NaN
         const unsigned m = __ballot_sync(0xffffffffu, ok);
-        const int lane = threadIdx.x & 31;
-        int wbase = 0;
-        if (lane == 0) wbase = atomicAdd(&s_base, __popc(m));
-        wbase = __shfl_sync(0xffffffffu, wbase, 0);
+        if (lane == 0) s_cnt[warp] = __popc(m);
+        __syncthreads();
+        int wbase = s_base, total = 0;
+        for (int w = 0; w < kStatsThreads / 32; ++w) { const int c = s_cnt[w]; if (w < warp) wbase += c; total += c; }
         if (ok) { v *= sgn; row[wbase + __popc(m & ((1u << lane) - 1))] = v; sum += v; }
+        __syncthreads();
+        if (threadIdx.x == 0) s_base += total;
+        __syncthreads();
     }
-    __syncthreads();
     const int n = s_base;
     for (long long i = n + threadIdx.x; i < ld; i += kStatsThreads) row[i] = __longlong_as_double(0x7ff0000000000000LL);
     const double mean = block_sum(sum, sh) / (double)n;

@@ -120,3 +120,21 @@ def test_fast_path_matches_brute_force(nat, monkeypatch):
         brute = nat.kde_pvalues_host(ctx, genes, pseudo, positive=positive)
         monkeypatch.delenv('JACKS_KDE_BRUTE', raising=False)
         assert rel_close(fast, brute, 1e-11, atol=1e-300) < 1e-11
+
+
+def test_pvalues_reproducible_and_block_independent():
+    """Bit-reproducible from call to call, and a gene's p-value does not depend on which other genes are evaluated in
+    the same call (what lets dist.pvalues_sharded shard by gene with bit-identical results)."""
+    from jacks_b200 import _native as nat
+    rng = np.random.default_rng(12)
+    genes = rng.normal(-0.3, 0.7, size=(700, 7))
+    pseudo = rng.normal(0.0, 0.2, size=(30000, 7))
+    pseudo[rng.integers(0, 30000, 50), rng.integers(0, 7, 50)] = np.nan
+    ctx = nat.context(0)
+    a = nat.kde_pvalues_host(ctx, genes, pseudo)
+    b = nat.kde_pvalues_host(ctx, genes, pseudo)
+    assert np.array_equal(a, b)
+    parts = np.concatenate([nat.kde_pvalues_host(ctx, genes[:211], pseudo), nat.kde_pvalues_host(ctx, genes[211:], pseudo)])
+    assert np.array_equal(a, parts)
+    p = nat.kde_pvalues_host(ctx, genes, pseudo, positive=True)
+    assert np.array_equal(p, nat.kde_pvalues_host(ctx, genes, pseudo, positive=True))
