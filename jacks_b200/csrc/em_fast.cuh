@@ -375,13 +375,16 @@ __device__ __noinline__ EmSums<G> em_sweep_all(const uint32_t tbase, const uint3
 // All G rows of a line batch are loaded before any is consumed (G*4 independent 16-byte loads in flight per
 // lane): staging is pure memory latency for a team that has only its own warps to hide it behind.
 // Not inlined (runs once per gene).  Returns true if a staged value is not finite.
-// TM == 2: pd2 goes to the thread's TMEM lane at `tpd` ([line][g] column pairs) instead of the global slab; the loop
-// then has a warp-uniform trip count (the TMEM stores are warp-collective) and dead lines are predicated.
+// TMEM variants: the loop has a warp-uniform trip count (the TMEM stores are warp-collective) and dead lines are
+// predicated; with TM == 2, pd2 goes to the thread's TMEM lane at `tpd` ([line][g] column pairs) instead of the slab.
 // In that mode the pass also INITIALISES the gene (infer.py:81-86), since every value it needs is in registers:
 // th = tau/2 = tps/pd2 to the TMEM columns at `tth`, the initial E[w] (median over the guides) and E[w^2] to the
 // gene's output rows, and the lane's partial sums for the initial bound and the first X step (formed with th,
 // i.e. HALF sums) in the returned struct.
 template <int G> struct EmStaged { double acc[2 * G + 1]; bool bad; };
+// Staging also initialises the gene in the TMEM variants -- mode 2 always; mode 1 up to four guides (measured at
+// 400..800 lines: G = 4 gains 5 %, G = 5..7 lose 1..4 % to register pressure in the staging loop).
+template <int G, int TM> __host__ __device__ constexpr bool em_stage_initialises() { return TM == 2 || (TM == 1 && G <= 4); }
 
 template <int G, int STEP, int TM>
 __device__ __noinline__ EmStaged<G> em_stage_gene(const double2* __restrict__ test, const double2* __restrict__ ctrl,
@@ -408,7 +411,7 @@ __device__ __noinline__ EmStaged<G> em_stage_gene(const double2* __restrict__ te
         for (int g = 0; g < G; ++g) c0[g] = cr[g][0];
     }
     constexpr int B = 2;                      // lines per batch
-    if (TM == 2) {
+    if (em_stage_initialises<G, TM>()) {
 #pragma unroll 1
         for (int i = 0; i < n_warp; i += B) {
             double2 t[B][G], c[B][G];
@@ -456,7 +459,16 @@ __device__ __noinline__ EmStaged<G> em_stage_gene(const double2* __restrict__ te
                     if (w2g) w2g[l] = w2;
                 }
             }
-            tmem_store<B * G>(tpd + 2 * G * i, &pdv[0][0]);
+            if (TM == 2) {
+                tmem_store<B * G>(tpd + 2 * G * i, &pdv[0][0]);
+            } else {
+#pragma unroll
+                for (int b = 0; b < B; ++b)
+                    if (live[b]) {
+#pragma unroll
+                        for (int g = 0; g < G; ++g) tpdg[g * Lp + l0 + (i + b) * STEP] = pdv[b][g];
+                    }
+            }
             tmem_store<B * G>(tth + 2 * G * i, &th[0][0]);
         }
         tmem_wait_st();
@@ -639,7 +651,7 @@ __global__ void __launch_bounds__(TM ? kTmemTeams * 32 : W * 32, TM ? 2 : 0) em_
                                                               fill, tps, tbase + pdoff, tbase, n_warp, xv, w1g, w2g);
             bad = sg.bad;
 #pragma unroll
-            for (int i = 0; i < NV; ++i) acc[i] = sg.acc[i];       // TM == 2: the initial sums; otherwise zeros
+            for (int i = 0; i < NV; ++i) acc[i] = sg.acc[i];       // the initial sums if staging initialises; otherwise zeros
         }
         const int any_bad = (W == 1) ? __any_sync(JACKS_FULL_MASK, bad) : __syncthreads_or(bad);
         // the look-ahead atomic has landed by now: share it and start loading the next gene's index
@@ -671,7 +683,7 @@ __global__ void __launch_bounds__(TM ? kTmemTeams * 32 : W * 32, TM ? 2 : 0) em_
             // every lane reads back only the words (shared and global) it wrote itself: no barrier needed
 
             // ---- initial w, tau, bound and the first X-step sums (infer.py:81-86) --------------
-            if (TM == 2) {
+            if (em_stage_initialises<G, TM>()) {
                 // staged and initialised in one pass (em_stage_gene)
             } else if (TM) {
                 // warp-uniform trip count: the TMEM stores are warp-collective; a lane past its last line
@@ -682,11 +694,10 @@ __global__ void __launch_bounds__(TM ? kTmemTeams * 32 : W * 32, TM ? 2 : 0) em_
                     const bool live = l < L;
                     const int lu = live ? l : 0;
                     double yv[G], th[G], pdv[G];
-                    if (TM == 2) tmem_load<G>(tbase + pdoff + 2 * G * i, pdv);
 #pragma unroll
                     for (int g = 0; g < G; ++g) {
                         yv[g] = ys[g * L + lu];
-                        if (TM != 2) pdv[g] = tpdg[g * Lp + lu];
+                        pdv[g] = tpdg[g * Lp + lu];
                     }
                     const double w1 = median_small<G>(yv);
                     const double w2 = w1 * w1;
@@ -706,7 +717,6 @@ __global__ void __launch_bounds__(TM ? kTmemTeams * 32 : W * 32, TM ? 2 : 0) em_
                         if (w2g) w2g[l] = w2;
                     }
                 }
-                tmem_wait_st();
             } else {
 #pragma unroll 2
                 for (int l = l0; l < L; l += STEP) {
