@@ -73,6 +73,10 @@ struct JacksEmPlan {
     std::vector<int> h_ids;    // host copy of d_ids (ascending gene ids inside each bucket)
     EmBucket generic;          // n == 0 if empty
     int generic_maxG;
+    EmBucket big;              // genes of the generic kind large enough for a CTA each (em_big_kernel)
+    int big_maxG;
+    int big_grid;
+    long long big_slab;        // doubles of global scratch per CTA
     int fast_maxG;
     int n_fast_genes;
     EmGenericConfig cfg_generic, cfg_deferred;
@@ -317,16 +321,18 @@ int jacks_em_plan_create(JacksCtx* ctx, const int64_t* gene_offsets, const int32
     p->b->sig_genes = n_genes; p->b->sig_guides = total;
     p->ctx = ctx; p->n_genes = n_genes; p->n_rows = n_rows; p->total_guides = total; p->L = n_lines;
     p->generic = EmBucket{0, 0, 0, 0, 0};
-    p->generic_maxG = 0; p->fast_maxG = 0; p->n_fast_genes = 0;
+    p->big = EmBucket{0, 0, 0, 0, 0};
+    p->generic_maxG = 0; p->fast_maxG = 0; p->n_fast_genes = 0; p->big_maxG = 0; p->big_grid = 0; p->big_slab = 0;
 
     // bucket genes by guide count, keeping the caller's order inside each bucket
     std::vector<std::vector<int>> byG(9);
-    std::vector<int> gen;
+    std::vector<int> gen, big;
     int teamW[9] = {0};
     for (int G = 1; G <= 8; ++G) teamW[G] = choose_team(G, n_lines);
     for (int64_t g = 0; g < n_genes; ++g) {
         const int G = (int)(gene_offsets[g + 1] - gene_offsets[g]);
         if (G <= 8 && teamW[G] > 0) byG[G].push_back((int)g);
+        else if ((long long)G * n_lines >= kBigGeneElements) { big.push_back((int)g); p->big_maxG = std::max(p->big_maxG, G); }
         else { gen.push_back((int)g); p->generic_maxG = std::max(p->generic_maxG, G); }
     }
     std::vector<int> ids;
@@ -352,6 +358,12 @@ int jacks_em_plan_create(JacksCtx* ctx, const int64_t* gene_offsets, const int32
         p->generic = EmBucket{0, 0, (int)gen.size(), (int)ids.size(), 0};
         ids.insert(ids.end(), gen.begin(), gen.end());
     }
+    if (!big.empty()) {
+        p->big = EmBucket{0, 0, (int)big.size(), (int)ids.size(), 0};
+        ids.insert(ids.end(), big.begin(), big.end());
+        p->big_grid = (int)std::min<long long>((long long)big.size(), 2LL * ctx->n_sm);
+        p->big_slab = em_generic_work_doubles(p->big_maxG, n_lines);
+    }
 
     int rc = JACKS_OK;
     auto up = [&](DevBuf& b, const void* src, size_t bytes) {
@@ -375,7 +387,7 @@ int jacks_em_plan_create(JacksCtx* ctx, const int64_t* gene_offsets, const int32
     // generic kernel configurations (and global scratch if a gene's working set exceeds shared memory)
     memset(&p->cfg_generic, 0, sizeof p->cfg_generic);
     memset(&p->cfg_deferred, 0, sizeof p->cfg_deferred);
-    long long scratch_doubles = 0;
+    long long scratch_doubles = (long long)p->big_grid * p->big_slab;
     if (rc == JACKS_OK && p->generic.n > 0) {
         e = em_generic_configure(p->generic_maxG, n_lines, p->generic.n, ctx->n_sm, &p->cfg_generic);
         if (e != cudaSuccess) rc = cuda_fail(e, "em_generic_configure");
@@ -455,6 +467,18 @@ static int em_run_range(JacksCtx* ctx, const JacksEmPlan* plan, const JacksEmPar
             a.scratch_stride = plan->cfg_generic.scratch_doubles_per_warp;
             e = launch_em_generic(plan->cfg_generic, a, st);
             if (e != cudaSuccess) return cuda_fail(e, "em_generic_kernel launch");
+            ctx->launches++;
+        }
+    }
+    if (plan->big.n > 0) {
+        int s0, s1;
+        slots_of(plan->big, &s0, &s1);
+        if (s1 > s0) {
+            a.gene_ids = (const int*)plan->b->d_ids.p + plan->big.ids_off + s0;
+            a.n_work = s1 - s0; a.n_work_dev = nullptr;
+            a.work_counter = counters + slot++;
+            e = launch_em_big(a, std::min(plan->big_grid, s1 - s0), plan->big_slab, st);
+            if (e != cudaSuccess) return cuda_fail(e, "em_big_kernel launch");
             ctx->launches++;
         }
     }
@@ -827,14 +851,18 @@ static int em_lines_run(JacksCtx* ctx, const JacksEmPlan* plan, const JacksEmPar
     a.L = 1;
     a.scratch = (double*)plan->b->d_scratch.p;
     EmGenericConfig cfg;
-    if (plan->generic.n > 0) {
-        if ((e = em_generic_configure(plan->generic_maxG, 1, (long long)plan->generic.n * L, ctx->n_sm, &cfg)) != cudaSuccess) return cuda_fail(e, "em_generic_configure");
+    // (with one line a gene's working set is small whatever its guide count: the big-gene bucket runs here too)
+    const EmBucket* rest[2] = {&plan->generic, &plan->big};
+    const int rest_maxG[2] = {plan->generic_maxG, plan->big_maxG};
+    for (int k = 0; k < 2; ++k) {
+        if (rest[k]->n == 0) continue;
+        if ((e = em_generic_configure(rest_maxG[k], 1, (long long)rest[k]->n * L, ctx->n_sm, &cfg)) != cudaSuccess) return cuda_fail(e, "em_generic_configure");
         if (cfg.scratch_doubles_per_warp > 0 &&
             (rc = plan->b->d_scratch.reserve((size_t)cfg.scratch_doubles_per_warp * cfg.grid * cfg.warps_per_cta * sizeof(double))) != JACKS_OK) return rc;
         a.scratch = (double*)plan->b->d_scratch.p;
         a.lines_mode = 1;
-        a.gene_ids = (const int*)plan->b->d_ids.p + plan->generic.ids_off;
-        a.n_work = plan->generic.n; a.n_work_dev = nullptr;
+        a.gene_ids = (const int*)plan->b->d_ids.p + rest[k]->ids_off;
+        a.n_work = rest[k]->n; a.n_work_dev = nullptr;
         a.work_counter = counters + slot++;
         a.scratch_stride = cfg.scratch_doubles_per_warp;
         if ((e = launch_em_generic(cfg, a, st)) != cudaSuccess) return cuda_fail(e, "em_generic_kernel (lines) launch");

@@ -318,3 +318,26 @@ def test_used_rows_only_upload_is_identical(nat):
     with pytest.raises(IndexError):
         nat.em_batched_host(ctx2, np.array([0, 1], np.int64), np.array([N], np.int32), test, ctrl, used_rows_only=True)
     ctx2.close()
+
+
+def test_big_gene_kernel_vs_oracle(nat):
+    """Genes of 16,384 elements and more run one per CTA (em_big_kernel): a 600-guide and a 1,000-guide gene among small
+    ones, with missing means and sds, the hyper-prior, fixed x and an odd and an even number of valid values per line
+    (both nanmedian branches of the bit-wise selection)."""
+    from oracle import c_oracle
+    rng = np.random.default_rng(2024)
+    offs, rows, test, ctrl = _random_screen(rng, [600, 4, 1000, 7, 33], 41, nan_frac=0.002, sd_nan_frac=0.01)
+    N = test.shape[0]
+    problems = []
+    fx1 = rng.uniform(0.5, 1.5, N)
+    fx2 = fx1 ** 2 + rng.uniform(0.01, 0.5, N)             # second moments of a real posterior: E[x^2] >= E[x]^2
+    for label, kw in (('joint', {}), ('hp', dict(apply_w_hp=True)), ('fixed', dict(fixed_x1=fx1, fixed_x2=fx2))):
+        ref = c_oracle.em_batched(offs, rows, test, ctrl, **kw)
+        r = run(nat, offs, rows, test, ctrl, **kw)
+        if r['n_iters'].tolist() != ref['n_iters'].tolist():
+            problems.append((label, 'iters', r['n_iters'].tolist(), ref['n_iters'].tolist()))
+        for k in ('x1', 'x2', 'w1', 'w2', 'tau'):
+            ok, worst = close(r[k], ref[k])
+            if not ok:
+                problems.append((label, k, worst))
+    report(problems)
