@@ -19,7 +19,7 @@ LIB = os.path.join(PKG, 'libjacks_b200.so')
 NVCC = os.environ.get('NVCC', '/usr/local/cuda/bin/nvcc')
 ARCH = ['-gencode', 'arch=compute_100a,code=sm_100a']
 FLAGS = ['-O3', '-std=c++17', '-lineinfo', '-Xcompiler', '-fPIC,-fvisibility=hidden']
-FAST_G = list(range(1, 9))
+FAST_G = list(range(1, 13))      # kMaxFastG in csrc/em_common.cuh
 
 UNITS = [('capi.cu', 'capi.o', []), ('em_dispatch.cu', 'em_dispatch.o', []), ('em_generic.cu', 'em_generic.o', []), ('em_lines.cu', 'em_lines.o', []),
          ('fp64_probe.cu', 'fp64_probe.o', []), ('kde_pvalues.cu', 'kde_pvalues.o', []),

@@ -90,7 +90,7 @@ constexpr int kCounterInts = kCountersPerRange * kMaxRanges;
 
 // Warps per gene of the fast kernel for (G, L); 0 = use the generic kernel.
 int choose_team(int G, int L) {
-    if (G < 1 || G > 8) return 0;
+    if (G < 1 || G > kMaxFastG) return 0;
     const char* env = getenv("JACKS_EM_W");          // tuning override
     int W = 0;
     if (env) W = atoi(env);
@@ -325,13 +325,13 @@ int jacks_em_plan_create(JacksCtx* ctx, const int64_t* gene_offsets, const int32
     p->generic_maxG = 0; p->fast_maxG = 0; p->n_fast_genes = 0; p->big_maxG = 0; p->big_grid = 0; p->big_slab = 0;
 
     // bucket genes by guide count, keeping the caller's order inside each bucket
-    std::vector<std::vector<int>> byG(9);
+    std::vector<std::vector<int>> byG(kMaxFastG + 1);
     std::vector<int> gen, big;
-    int teamW[9] = {0};
-    for (int G = 1; G <= 8; ++G) teamW[G] = choose_team(G, n_lines);
+    int teamW[kMaxFastG + 1] = {0};
+    for (int G = 1; G <= kMaxFastG; ++G) teamW[G] = choose_team(G, n_lines);
     for (int64_t g = 0; g < n_genes; ++g) {
         const int G = (int)(gene_offsets[g + 1] - gene_offsets[g]);
-        if (G <= 8 && teamW[G] > 0) byG[G].push_back((int)g);
+        if (G <= kMaxFastG && teamW[G] > 0) byG[G].push_back((int)g);
         else if ((long long)G * n_lines >= kBigGeneElements) { big.push_back((int)g); p->big_maxG = std::max(p->big_maxG, G); }
         else { gen.push_back((int)g); p->generic_maxG = std::max(p->generic_maxG, G); }
     }
@@ -342,7 +342,7 @@ int jacks_em_plan_create(JacksCtx* ctx, const int64_t* gene_offsets, const int32
     slot_off.reserve((size_t)n_genes);
     slot_rows.reserve((size_t)total);
     // larger G first: the heavier buckets start while the GPU is empty
-    for (int G = 8; G >= 1; --G) {
+    for (int G = kMaxFastG; G >= 1; --G) {
         if (byG[G].empty()) continue;
         EmBucket b{G, teamW[G], (int)byG[G].size(), (int)ids.size(), (long long)slot_rows.size()};
         ids.insert(ids.end(), byG[G].begin(), byG[G].end());
@@ -847,7 +847,7 @@ static int em_lines_run(JacksCtx* ctx, const JacksEmPlan* plan, const JacksEmPar
         ctx->launches++;
         n_fast += b.n;
     }
-    // NaN-safe warp-per-problem kernel on one-line views: genes with G > 8, then the problems handed back
+    // NaN-safe warp-per-problem kernel on one-line views: genes without a fast kernel, then the problems handed back
     a.L = 1;
     a.scratch = (double*)plan->b->d_scratch.p;
     EmGenericConfig cfg;
@@ -874,7 +874,7 @@ static int em_lines_run(JacksCtx* ctx, const JacksEmPlan* plan, const JacksEmPar
         a.gene_ids = (const int*)plan->b->d_deferred.p;
         a.n_work = (int)(n_fast * L); a.n_work_dev = counters;
         a.work_counter = counters + slot++;
-        a.scratch_stride = cfg.scratch_doubles_per_warp;      // 0: G <= 8 with one line always fits shared memory
+        a.scratch_stride = cfg.scratch_doubles_per_warp;      // 0: a fast-kernel gene with one line always fits shared memory
         if ((e = launch_em_generic(cfg, a, st)) != cudaSuccess) return cuda_fail(e, "em_generic_kernel (lines, deferred) launch");
         ctx->launches++;
     }

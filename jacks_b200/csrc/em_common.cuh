@@ -52,7 +52,9 @@ struct EmLaunch {
     int lines_mode; int L_full;
 };
 
-// Fast path: compile-time guide count G (1..8), W (1, 2 or 4) warps per gene, finite data only.
+// Largest guide count with compiled fast kernels (TKOv1-style libraries have 12 guides per gene).
+constexpr int kMaxFastG = 12;
+// Fast path: compile-time guide count G (1..kMaxFastG), W (1, 2 or 4) warps per gene, finite data only.
 // Returns cudaErrorInvalidValue if (G, W) was not instantiated.
 cudaError_t launch_em_fast(int G, int W, const EmLaunch& a, int n_sm, int grid_limit, cudaStream_t st,
                            int* grid_out);

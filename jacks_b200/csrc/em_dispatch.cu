@@ -8,6 +8,7 @@ namespace jacks {
     cudaError_t launch_em_fast_g##g(int W, const EmLaunch& a, int n_sm, int grid_limit, cudaStream_t st,    \
                                     int* grid_out);
 JACKS_DECL(1) JACKS_DECL(2) JACKS_DECL(3) JACKS_DECL(4) JACKS_DECL(5) JACKS_DECL(6) JACKS_DECL(7) JACKS_DECL(8)
+JACKS_DECL(9) JACKS_DECL(10) JACKS_DECL(11) JACKS_DECL(12)
 #undef JACKS_DECL
 
 cudaError_t launch_em_fast(int G, int W, const EmLaunch& a, int n_sm, int grid_limit, cudaStream_t st, int* grid_out) {
@@ -20,11 +21,15 @@ cudaError_t launch_em_fast(int G, int W, const EmLaunch& a, int n_sm, int grid_l
         case 6: return launch_em_fast_g6(W, a, n_sm, grid_limit, st, grid_out);
         case 7: return launch_em_fast_g7(W, a, n_sm, grid_limit, st, grid_out);
         case 8: return launch_em_fast_g8(W, a, n_sm, grid_limit, st, grid_out);
+        case 9: return launch_em_fast_g9(W, a, n_sm, grid_limit, st, grid_out);
+        case 10: return launch_em_fast_g10(W, a, n_sm, grid_limit, st, grid_out);
+        case 11: return launch_em_fast_g11(W, a, n_sm, grid_limit, st, grid_out);
+        case 12: return launch_em_fast_g12(W, a, n_sm, grid_limit, st, grid_out);
         default: return cudaErrorInvalidValue;
     }
 }
 
-bool em_fast_available(int G, int W) { return G >= 1 && G <= 8 && (W == 1 || W == 2 || W == 4); }
+bool em_fast_available(int G, int W) { return G >= 1 && G <= kMaxFastG && (W == 1 || W == 2 || W == 4); }
 
 size_t em_fast_smem_bytes(int G, int W, int L) { return (size_t)em_fast_smem_doubles(G, W, L) * sizeof(double); }
 

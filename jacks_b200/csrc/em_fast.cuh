@@ -340,7 +340,7 @@ __device__ __noinline__ EmSums<G> em_sweep_all(const uint32_t tbase, const uint3
     for (int g = 0; g < G; ++g) { a1[g] = 0.0; a2[g] = 0.0; ab[g] = 0.0; }
     // lines per step: U*G >= 8 independent elements, and few enough (<= 20) to stay in registers
     // (measured at 400 lines: G = 5 wants 3 lines from shared memory, 4 from TMEM; G = 6 wants 3 either way)
-    constexpr int U = (G >= 7) ? 2 : ((G >= (TM ? 6 : 5)) ? 3 : 4);
+    constexpr int U = (G >= 9) ? 1 : (G >= 7) ? 2 : ((G >= (TM ? 6 : 5)) ? 3 : 4);
     int l = l0;
     int n = n_warp;
     double pd[U][G];
@@ -358,7 +358,7 @@ __device__ __noinline__ EmSums<G> em_sweep_all(const uint32_t tbase, const uint3
         em_sweep<G, U, U, UNIT_C, false, true, TM>(tcol, tcol + pdoff, ys, pd, tpdg + l + U * STEP, Lp, ths, w1p, w2g, L, l, STEP, x, ivw, mw, c_tau, a1, a2, ab, true);
     const bool valid = (l + (n - 1) * STEP) < L;
     if (n == 1) em_sweep<G, 1, U, UNIT_C, true, false, TM>(tcol, tcol + pdoff, ys, pd, nullptr, Lp, ths, w1p, w2g, L, l, STEP, x, ivw, mw, c_tau, a1, a2, ab, valid);
-    else if (n == 2) em_sweep<G, 2, U, UNIT_C, true, false, TM>(tcol, tcol + pdoff, ys, pd, nullptr, Lp, ths, w1p, w2g, L, l, STEP, x, ivw, mw, c_tau, a1, a2, ab, valid);
+    else if (U >= 2 && n == 2) em_sweep<G, (U >= 2 ? 2 : 1), U, UNIT_C, true, false, TM>(tcol, tcol + pdoff, ys, pd, nullptr, Lp, ths, w1p, w2g, L, l, STEP, x, ivw, mw, c_tau, a1, a2, ab, valid);
     else if (U >= 3 && n == 3) em_sweep<G, (U >= 3 ? 3 : 1), U, UNIT_C, true, false, TM>(tcol, tcol + pdoff, ys, pd, nullptr, Lp, ths, w1p, w2g, L, l, STEP, x, ivw, mw, c_tau, a1, a2, ab, valid);
     else if (U == 4 && n == 4) em_sweep<G, (U == 4 ? 4 : 1), U, UNIT_C, true, false, TM>(tcol, tcol + pdoff, ys, pd, nullptr, Lp, ths, w1p, w2g, L, l, STEP, x, ivw, mw, c_tau, a1, a2, ab, valid);
     EmSums<G> r;
@@ -410,7 +410,7 @@ __device__ __noinline__ EmStaged<G> em_stage_gene(const double2* __restrict__ te
 #pragma unroll
         for (int g = 0; g < G; ++g) c0[g] = cr[g][0];
     }
-    constexpr int B = 2;                      // lines per batch
+    constexpr int B = (G >= 9) ? 1 : 2;       // lines per batch
     if (em_stage_initialises<G, TM>()) {
 #pragma unroll 1
         for (int i = 0; i < n_warp; i += B) {

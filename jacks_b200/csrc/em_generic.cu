@@ -1,7 +1,7 @@
 // Generic batched EM kernel: any guide count G and line count L, NaN-safe, one warp per gene.
 //
 // This is the catch-all behind the fast kernels (em_fast.cuh): it runs genes whose shape has no
-// fast instantiation (G > 8, L > 512) and genes with missing measurements (NaN in y), following
+// fast instantiation (G > 12, or a line count too large for the fast variants) and genes with missing measurements (NaN in y), following
 // numpy's NaN rules as the reference uses them:
 //   sums are nansum (NaN terms count as 0)                   infer.py:39,42,44,125
 //   w1 init and the x normaliser use nanmedian               infer.py:81,108

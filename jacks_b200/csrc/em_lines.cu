@@ -146,6 +146,10 @@ cudaError_t launch_em_lines(int G, const EmLaunch& a, int n_sm, cudaStream_t st)
         case 6: return launch_lines<6>(a, n_sm, st);
         case 7: return launch_lines<7>(a, n_sm, st);
         case 8: return launch_lines<8>(a, n_sm, st);
+        case 9: return launch_lines<9>(a, n_sm, st);
+        case 10: return launch_lines<10>(a, n_sm, st);
+        case 11: return launch_lines<11>(a, n_sm, st);
+        case 12: return launch_lines<12>(a, n_sm, st);
         default: return cudaErrorInvalidValue;
     }
 }

@@ -33,7 +33,7 @@ def compare(tag, r, z, prefix, keys, problems):
 
 
 def test_example_small_every_line_vs_reference(nat):
-    """All 1,579 genes (G = 1..18: per-lane kernels and, above 8 guides, the generic kernel on one-line views)."""
+    """All 1,579 genes (G = 1..18: per-lane kernels and, above 12 guides, the generic kernel on one-line views)."""
     genes, offs, rows, testdata, ctrldata = small_screen()
     z = load_golden('lines_em.npz')
     r = nat.em_lines_host(nat.context(0), offs, rows, testdata, ctrldata)
