@@ -85,7 +85,7 @@ struct EmGenericConfig {
 // Working-set size (doubles) of one gene in the generic kernel.
 __host__ __device__ long long em_generic_work_doubles(int G, int L);
 // Genes at least this big (guides x lines) run one per CTA (em_big_kernel) instead of one per warp.
-constexpr long long kBigGeneElements = 16384;
+constexpr long long kBigGeneElements = 4096;
 cudaError_t launch_em_big(const EmLaunch& a, int grid, long long slab_doubles, cudaStream_t st);
 cudaError_t em_generic_configure(int maxG, int L, long long n_work_cap, int n_sm, EmGenericConfig* cfg);
 cudaError_t launch_em_generic(const EmGenericConfig& cfg, const EmLaunch& a, cudaStream_t st);

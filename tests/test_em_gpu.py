@@ -321,7 +321,7 @@ def test_used_rows_only_upload_is_identical(nat):
 
 
 def test_big_gene_kernel_vs_oracle(nat):
-    """Genes of 16,384 elements and more run one per CTA (em_big_kernel): a 600-guide and a 1,000-guide gene among small
+    """Genes without a fast kernel of 4,096 elements and more run one per CTA (em_big_kernel): a 600-guide and a 1,000-guide gene among small
     ones, with missing means and sds, the hyper-prior, fixed x and an odd and an even number of valid values per line
     (both nanmedian branches of the bit-wise selection)."""
     from oracle import c_oracle
