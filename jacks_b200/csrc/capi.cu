@@ -95,11 +95,13 @@ int choose_team(int G, int L) {
     int W = 0;
     if (env) W = atoi(env);
     if (!(W == 1 || W == 2 || W == 4)) {
-        // One warp per gene is the most efficient split (no barriers, one reduction per pass) and, at
-        // the shared-memory-bound occupancy of a few genes per SM, also the fastest measured at L = 400
-        // (W=1 9.2 ms, W=2 10.1 ms, W=4 15.3 ms per Avana pass).  Very long line axes get more warps.
-        const int strips = (L + 31) / 32;
-        W = strips > 64 ? 4 : (strips > 32 ? 2 : 1);
+        // One warp per gene is the most efficient split (no barriers, one reduction per pass) as long as a few genes fit
+        // an SM -- in shared memory or, with tau in tensor memory, four per CTA (em_fast_single_warp_genes).  Long line
+        // axes that leave room for one or two genes get 4 or 2 warps each instead (measured at G = 4: 1,100 lines
+        // W = 1 / 2 / 4 -> 3.8 / 4.1 / 4.1 ms per 16,000 genes; 1,800 lines 23.4 / 14.7 / 9.0 ms).
+        const int g1 = em_fast_single_warp_genes(G, L);
+        W = g1 >= 3 ? 1 : (g1 == 2 ? 2 : 4);
+        while (W > 1 && em_fast_smem_bytes(G, W, L) > kMaxDynSmem) W >>= 1;       // (tile per warp: cannot happen before W = 1 fails)
     }
     if (!em_fast_available(G, W) || em_fast_smem_bytes(G, W, L) > kMaxDynSmem) return 0;
     return W;

@@ -58,6 +58,8 @@ constexpr int kMaxFastG = 12;
 // Returns cudaErrorInvalidValue if (G, W) was not instantiated.
 cudaError_t launch_em_fast(int G, int W, const EmLaunch& a, int n_sm, int grid_limit, cudaStream_t st,
                            int* grid_out);
+// Genes one SM can hold with ONE warp per gene: the larger of the shared-memory variant's and the TMEM variants' count.
+int em_fast_single_warp_genes(int G, int L);
 // Is (G, W) compiled in?
 bool em_fast_available(int G, int W);
 // Bytes of dynamic shared memory one gene team needs (y, tau_pr_den, tau, w1, w2 + reduction buffer).

@@ -1,5 +1,7 @@
 // Switch from a runtime guide count to the per-G translation units (em_fast_inst.cu).
 #include "em_common.cuh"
+#include <algorithm>
+
 #include "em_fast.cuh"
 
 namespace jacks {
@@ -30,6 +32,18 @@ cudaError_t launch_em_fast(int G, int W, const EmLaunch& a, int n_sm, int grid_l
 }
 
 bool em_fast_available(int G, int W) { return G >= 1 && G <= kMaxFastG && (W == 1 || W == 2 || W == 4); }
+
+int em_fast_single_warp_genes(int G, int L) {
+    const long long smem1 = em_fast_smem_doubles(G, 1, L) * (long long)sizeof(double);
+    long long genes = std::min<long long>((long long)kMaxDynSmem / smem1, kMaxFastCtasPerSm);
+    const int cols = tmem_cols_for(G, L, 1);
+    const long long team = em_fast_tmem_team_doubles(G, L) * (long long)sizeof(double);
+    if (cols > 0 && team * kTmemTeams <= (long long)kMaxDynSmem) {
+        const long long ctas = std::min<long long>(std::min<long long>((long long)kMaxDynSmem / (team * kTmemTeams), 512 / cols), 2);
+        genes = std::max(genes, ctas * kTmemTeams);
+    }
+    return (int)genes;
+}
 
 size_t em_fast_smem_bytes(int G, int W, int L) { return (size_t)em_fast_smem_doubles(G, W, L) * sizeof(double); }
 
