@@ -16,6 +16,8 @@
  *   2018_paper_materials/scripts/jacks/run_JACKS_single.py:83-85
  *                             per-line inferJACKS loop        jacks_em_lines_device / jacks_em_lines_host
  *   jacks/jacks/jacks_io.py:69   computeW1PvalsAndFDRs         jacks_kde_pvalues_device / _host
+ *   jacks/jacks/jacks_io.py:402-441  load_data_and_run: inferJACKS on the real genes, inferJACKS on the pseudo-genes,
+ *                             computeW1PvalsAndFDRs -- one screen, one call     jacks_run_screen_host / _device
  *   jacks/jacks/preprocess.py:77 normalizeLogCounts            jacks_normalize_host
  *   jacks/jacks/preprocess.py:61 condense_normalised_counts    jacks_condense_host
  *   jacks/jacks/preprocess.py:25 calc_posterior_sd             jacks_condense_host (one sample)
@@ -38,7 +40,7 @@
 extern "C" {
 #endif
 
-#define JACKS_B200_ABI_VERSION 1
+#define JACKS_B200_ABI_VERSION 2
 
 #if defined(__GNUC__)
 #define JACKS_API __attribute__((visibility("default")))
@@ -170,6 +172,58 @@ enum { JACKS_KEEP_RESIDENT = 1, JACKS_ASYNC = 2, JACKS_UPLOAD_USED_ROWS = 4 };
 JACKS_API int jacks_em_batched_host(JacksCtx* ctx, const JacksEmParams* params,
                           const int64_t* gene_offsets, const int32_t* guide_rows, int64_t n_genes,
                           const JacksEmHostIO* io, int32_t flags);
+
+/*
+ * The whole inference job of one screen in ONE call -- what load_data_and_run does between preprocessing and the
+ * writers (jacks_io.py:425-441): inferJACKS on the real genes, inferJACKS on the pseudo-genes drawn from the control
+ * genes (same cubes, another index, never fixed_x, jacks_io.py:430), and the KDE p-values of the real genes against the
+ * pseudo-gene null (computeW1PvalsAndFDRs, pseudo=True).  The pseudo-gene results never leave the device unless asked
+ * for: the reference writes no pseudo-gene to any file (jacks_io.py:131) and needs their p-values only for --fdr.
+ *
+ * Real-gene outputs as in JacksEmDeviceIO / JacksEmHostIO, plus
+ *   pvals         [n_genes, L]   optional (needs n_pseudo >= 2)
+ *   pseudo_w1     [n_pseudo, L]  device call: required work buffer when n_pseudo > 0; host call: optional download
+ *   pseudo_w2, pseudo_n_iters, pseudo_pvals   optional
+ *   positive      selection direction of the p-values (--positive)
+ */
+typedef struct JacksScreenDeviceIO {
+    JacksEmDeviceIO real;      /* cubes, fixed_x (real genes only) and the real-gene outputs */
+    double* pvals;
+    double* pseudo_w1;
+    double* pseudo_w2;
+    int32_t* pseudo_n_iters;
+    double* pseudo_pvals;
+    int32_t positive;
+    int32_t reserved;
+} JacksScreenDeviceIO;
+
+/* Enqueue on `stream`: EM of plan_real, EM of plan_pseudo (may be NULL), null densities, p-values.  No synchronisation. */
+JACKS_API int jacks_run_screen_device(JacksCtx* ctx, const JacksEmPlan* plan_real, const JacksEmPlan* plan_pseudo,
+                            const JacksEmParams* params, const JacksScreenDeviceIO* io, void* stream);
+
+typedef struct JacksScreenHostIO {
+    JacksEmHostIO real;
+    double* pvals;
+    double* pseudo_w1;
+    double* pseudo_w2;
+    int32_t* pseudo_n_iters;
+    double* pseudo_pvals;
+    int32_t positive;
+    int32_t reserved;
+} JacksScreenHostIO;
+
+/*
+ * Host buffers.  Transfers: the rows the pseudo-gene index references (a few thousand control guides) go up first, as a
+ * compact cube, so the pseudo-gene EM -- 85 % of the arithmetic at the Avana shape -- and the null densities run while
+ * the screen itself is still uploading; the real genes follow range by range behind their rows (EM, p-values, download).
+ * The screen is uploaded ONCE; a control shared by all lines is passed as [N, 1, 2] (ctrl_lines = 1).  Downloaded: the
+ * real-gene outputs that are non-NULL and the pseudo-gene outputs that are non-NULL.
+ * flags: JACKS_ASYNC, JACKS_KEEP_RESIDENT as for jacks_em_batched_host.
+ */
+JACKS_API int jacks_run_screen_host(JacksCtx* ctx, const JacksEmParams* params,
+                          const int64_t* gene_offsets, const int32_t* guide_rows, int64_t n_genes,
+                          const int64_t* pseudo_offsets, const int32_t* pseudo_rows, int64_t n_pseudo,
+                          const JacksScreenHostIO* io, int32_t flags);
 
 /*
  * Per-line ("single JACKS") inference: the reference's

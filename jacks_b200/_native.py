@@ -11,7 +11,7 @@ import threading
 import numpy as np
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG, 'libjacks_b200.so')
+LIB_PATH = os.environ.get('JACKS_B200_LIB') or os.path.join(_PKG, 'libjacks_b200.so')   # env: developer A/B builds
 
 JACKS_OK, JACKS_E_INVALID, JACKS_E_CUDA, JACKS_E_NOMEM, JACKS_E_SHAPE = 0, 1, 2, 3, 4
 
@@ -43,6 +43,16 @@ class EmHostIO(C.Structure):
                 ('fixed_x1', C.c_void_p), ('fixed_x2', C.c_void_p), ('x1', C.c_void_p), ('x2', C.c_void_p),
                 ('w1', C.c_void_p), ('w2', C.c_void_p), ('y', C.c_void_p), ('tau', C.c_void_p),
                 ('n_iters', C.c_void_p), ('bound', C.c_void_p)]
+
+
+class ScreenDeviceIO(C.Structure):
+    _fields_ = [('real', EmDeviceIO), ('pvals', C.c_void_p), ('pseudo_w1', C.c_void_p), ('pseudo_w2', C.c_void_p),
+                ('pseudo_n_iters', C.c_void_p), ('pseudo_pvals', C.c_void_p), ('positive', C.c_int32), ('reserved', C.c_int32)]
+
+
+class ScreenHostIO(C.Structure):
+    _fields_ = [('real', EmHostIO), ('pvals', C.c_void_p), ('pseudo_w1', C.c_void_p), ('pseudo_w2', C.c_void_p),
+                ('pseudo_n_iters', C.c_void_p), ('pseudo_pvals', C.c_void_p), ('positive', C.c_int32), ('reserved', C.c_int32)]
 
 
 _lib = None
@@ -83,6 +93,8 @@ def lib():
         L.jacks_em_batched_host.argtypes = [vp, C.POINTER(EmParams), vp, vp, i64, C.POINTER(EmHostIO), i32]
         L.jacks_em_lines_device.argtypes = [vp, vp, C.POINTER(EmParams), C.POINTER(EmDeviceIO), vp]
         L.jacks_em_lines_host.argtypes = [vp, C.POINTER(EmParams), vp, vp, i64, C.POINTER(EmHostIO), i32]
+        L.jacks_run_screen_device.argtypes = [vp, vp, vp, C.POINTER(EmParams), C.POINTER(ScreenDeviceIO), vp]
+        L.jacks_run_screen_host.argtypes = [vp, C.POINTER(EmParams), vp, vp, i64, vp, vp, i64, C.POINTER(ScreenHostIO), i32]
         L.jacks_fp64_peak_flops.argtypes = [vp, C.POINTER(dbl), C.POINTER(dbl)]
         if hasattr(L, 'jacks_kde_pvalues_device'):
             L.jacks_kde_pvalues_device.argtypes = [vp, vp, i64, vp, i64, i32, i32, vp, vp]
@@ -305,6 +317,78 @@ def em_batched_host(ctx, offsets, rows, test, ctrl, params=None, fixed_x1=None, 
     if not sync:
         # the C side reads these host arrays until ctx.synchronize(): keep them alive with the result
         res['_keepalive'] = (offsets, rows, test, ctrl, fixed_x1, fixed_x2, params)
+    return res
+
+
+def run_screen_device(ctx, plan_real, plan_pseudo, params, io, stream=0):
+    """Enqueue the whole inference job of a screen (jacks_run_screen_device): io is a ScreenDeviceIO of device pointers."""
+    check(lib().jacks_run_screen_device(ctx.h, plan_real.h, None if plan_pseudo is None else plan_pseudo.h, C.byref(params),
+                                        C.byref(io), C.c_void_p(stream or None)))
+
+
+def run_screen_host(ctx, offsets, rows, pseudo_offsets, pseudo_rows, test, ctrl, params=None, fixed_x1=None, fixed_x2=None,
+                    want=('x1', 'x2', 'w1', 'w2', 'pvals', 'n_iters'), want_pseudo=(), positive=False,
+                    ctrl_rowmean_fill=False, out=None, sync=True):
+    """jacks_run_screen_host: real-gene EM, pseudo-gene EM and KDE p-values of one screen in one call, the screen
+    uploaded once.  test [N,L,2]; ctrl [N,L,2] or [N,1,2] (one control for all lines).  want: real-gene outputs out of
+    x1, x2, w1, w2, y, tau, n_iters, bound, pvals; want_pseudo: out of w1, w2, n_iters, pvals (returned as 'pseudo_<k>').
+    pseudo_offsets=None runs the real genes alone (no p-values)."""
+    params = params or default_params()
+    offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+    test = np.ascontiguousarray(test, dtype=np.float64)
+    ctrl = np.ascontiguousarray(ctrl, dtype=np.float64)
+    if test.ndim != 3 or test.shape[2] != 2 or ctrl.ndim != 3 or ctrl.shape[2] != 2 or ctrl.shape[0] != test.shape[0]:
+        raise JacksError(JACKS_E_SHAPE, 'Expecting matched size between control and test data')
+    n_rows, n_lines = test.shape[0], test.shape[1]
+
+    def index(rows_):
+        rows_ = np.asarray(rows_)
+        if rows_.size and (rows_.min() < 0 or rows_.max() >= n_rows):
+            raise IndexError('guide row index out of bounds for %d rows' % n_rows)
+        return np.ascontiguousarray(rows_, dtype=np.int32)
+    rows = index(rows)
+    n_genes = len(offsets) - 1
+    T = int(offsets[-1]) if n_genes > 0 else 0
+    n_pseudo = 0
+    if pseudo_offsets is not None:
+        pseudo_offsets = np.ascontiguousarray(pseudo_offsets, dtype=np.int64)
+        pseudo_rows = index(pseudo_rows)
+        n_pseudo = len(pseudo_offsets) - 1
+    want = tuple(k for k in want if k != 'pvals' or n_pseudo > 0)       # no pseudo-genes at all: plain inferJACKS
+    shapes = dict(x1=((T,), np.float64), x2=((T,), np.float64), w1=((n_genes, n_lines), np.float64),
+                  w2=((n_genes, n_lines), np.float64), y=((T, n_lines), np.float64), tau=((T, n_lines), np.float64),
+                  n_iters=((n_genes,), np.int32), bound=((n_genes,), np.float64), pvals=((n_genes, n_lines), np.float64),
+                  pseudo_w1=((n_pseudo, n_lines), np.float64), pseudo_w2=((n_pseudo, n_lines), np.float64),
+                  pseudo_n_iters=((n_pseudo,), np.int32), pseudo_pvals=((n_pseudo, n_lines), np.float64))
+    keys = list(set(want) | {'w1'}) + ['pseudo_' + k for k in want_pseudo]
+    res = {}
+    for k in keys:
+        if out is not None and k in out:
+            assert out[k].shape == shapes[k][0] and out[k].dtype == shapes[k][1] and out[k].flags.c_contiguous
+            res[k] = out[k]
+        else:
+            res[k] = np.empty(shapes[k][0], dtype=shapes[k][1])
+    io = ScreenHostIO()
+    io.real.test, io.real.ctrl = _ptr(test), _ptr(ctrl)
+    io.real.n_rows, io.real.n_lines, io.real.ctrl_lines = int(n_rows), int(n_lines), int(ctrl.shape[1])
+    io.real.ctrl_rowmean_fill = int(bool(ctrl_rowmean_fill))
+    if fixed_x1 is not None:
+        fixed_x1 = np.ascontiguousarray(fixed_x1, dtype=np.float64)
+        fixed_x2 = np.ascontiguousarray(fixed_x2, dtype=np.float64)
+        if fixed_x1.shape != (n_rows,) or fixed_x2.shape != (n_rows,):
+            raise JacksError(JACKS_E_INVALID, 'fixed_x arrays must have one entry per data row')
+        io.real.fixed_x1, io.real.fixed_x2 = _ptr(fixed_x1), _ptr(fixed_x2)
+    for k in res:
+        if k == 'pvals' or k.startswith('pseudo_'):
+            setattr(io, k, _ptr(res[k]))
+        else:
+            setattr(io.real, k, _ptr(res[k]))
+    io.positive = int(bool(positive))
+    check(lib().jacks_run_screen_host(ctx.h, C.byref(params), _ptr(offsets), _ptr(rows), n_genes,
+                                      None if n_pseudo == 0 else _ptr(pseudo_offsets), None if n_pseudo == 0 else _ptr(pseudo_rows),
+                                      n_pseudo, C.byref(io), 0 if sync else 2))
+    if not sync:
+        res['_keepalive'] = (offsets, rows, pseudo_offsets, pseudo_rows, test, ctrl, fixed_x1, fixed_x2, params)
     return res
 
 

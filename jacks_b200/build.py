@@ -49,7 +49,13 @@ def _run(cmd):
     return r.stdout + r.stderr
 
 
-def build_library(force=False, verbose=False):
+def build_library(force=False, verbose=False, variant=None, defines=()):
+    """variant/defines: developer A/B builds -- libjacks_b200_<variant>.so compiled with extra -D flags (objects in
+    csrc/build/<variant>/); load it with JACKS_B200_LIB=<path> (jacks_b200/_native.py)."""
+    global OBJ, LIB
+    if variant:
+        OBJ = os.path.join(PKG, 'csrc', 'build', variant)
+        LIB = os.path.join(PKG, 'libjacks_b200_%s.so' % variant)
     deps = _sources()
     units = [u for u in UNITS if os.path.exists(os.path.join(CSRC, u[0]))]
     if not force and not _stale(LIB, deps):
@@ -60,7 +66,7 @@ def build_library(force=False, verbose=False):
     def compile_one(u):
         src, obj, extra = os.path.join(CSRC, u[0]), os.path.join(OBJ, u[1]), u[2]
         if force or _stale(obj, [src] + hdrs):
-            log = _run([NVCC] + ARCH + FLAGS + (['-Xptxas', '-v'] if verbose else []) + extra + ['-c', src, '-o', obj])
+            log = _run([NVCC] + ARCH + FLAGS + ['-D' + d for d in defines] + (['-Xptxas', '-v'] if verbose else []) + extra + ['-c', src, '-o', obj])
             if verbose:
                 print(log)
         return obj
@@ -71,4 +77,6 @@ def build_library(force=False, verbose=False):
 
 
 if __name__ == '__main__':
-    print(build_library(force='--force' in sys.argv, verbose='-v' in sys.argv))
+    var = [a.split('=', 1)[1] for a in sys.argv if a.startswith('--variant=')]
+    print(build_library(force='--force' in sys.argv, verbose='-v' in sys.argv, variant=var[0] if var else None,
+                        defines=[a[2:] for a in sys.argv if a.startswith('-D')]))

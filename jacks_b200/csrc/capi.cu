@@ -53,40 +53,7 @@ void DevBuf::release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
 
 using namespace jacks;
 
-// ------------------------------------------------------------------------------------------------
-// Plan
-// ------------------------------------------------------------------------------------------------
-struct EmBucket {
-    int G;            // guide count (fast buckets); 0 for the generic bucket
-    int W;            // warps per gene of the fast kernel
-    int n;            // genes in the bucket
-    int ids_off;      // offset into JacksEmPlan::d_ids / d_slot_off
-    long long rows_off;   // offset into JacksEmPlan::d_slot_rows (fast buckets)
-};
-
-struct JacksEmPlan {
-    JacksCtx* ctx;
-    int64_t n_genes, n_rows, total_guides;
-    int L;
-    PlanBufs* b;               // device buffers (from the context's pool)
-    std::vector<EmBucket> fast;
-    std::vector<int> h_ids;    // host copy of d_ids (ascending gene ids inside each bucket)
-    EmBucket generic;          // n == 0 if empty
-    int generic_maxG;
-    EmBucket big;              // genes of the generic kind large enough for a CTA each (em_big_kernel)
-    int big_maxG;
-    int big_grid;
-    long long big_slab;        // doubles of global scratch per CTA
-    int fast_maxG;
-    int n_fast_genes;
-    EmGenericConfig cfg_generic, cfg_deferred;
-};
-
 namespace {
-
-constexpr int kCountersPerRange = 16;      // [0] deferred count, [1..] one work counter per launch of a gene range
-constexpr int kMaxRanges = 64;
-constexpr int kCounterInts = kCountersPerRange * kMaxRanges;
 
 // Warps per gene of the fast kernel for (G, L); 0 = use the generic kernel.
 int choose_team(int G, int L) {
@@ -125,7 +92,7 @@ static void parallel_memcpy(void* dst, const void* src, size_t bytes, int thread
     for (auto& th : pool) th.join();
 }
 
-static bool host_pointer_is_pinned(const void* p) {
+bool host_pointer_is_pinned(const void* p) {
     cudaPointerAttributes at;
     if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
     return at.type == cudaMemoryTypeHost || at.type == cudaMemoryTypeManaged;
@@ -253,6 +220,7 @@ void jacks_ctx_destroy(JacksCtx* c) {
     c->stager.release();
     if (c->cmp_stage) cudaFreeHost(c->cmp_stage);
     if (c->cmp_ready) cudaEventDestroy(c->cmp_ready);
+    if (c->cmp_done) cudaEventDestroy(c->cmp_done);
     c->cmp_dev.release(); c->cmp_rows.release();
     if (c->stream) cudaStreamDestroy(c->stream);
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
@@ -416,9 +384,11 @@ void jacks_em_plan_destroy(JacksEmPlan* p) {
     delete p;
 }
 
+}  // extern "C"
+
 // Enqueue the EM of the genes with id in [g0, g1) (caller order) on `st`.  `range` selects the counter block;
 // the caller zeroes d_counters before the first range of a run.
-static int em_run_range(JacksCtx* ctx, const JacksEmPlan* plan, const JacksEmParams* params, const JacksEmDeviceIO* io,
+int em_run_range(JacksCtx* ctx, const JacksEmPlan* plan, const JacksEmParams* params, const JacksEmDeviceIO* io,
                         cudaStream_t st, int64_t g0, int64_t g1, int range) {
     cudaError_t e;
     int* counters = (int*)plan->b->d_counters.p + range * kCountersPerRange;
@@ -497,7 +467,7 @@ static int em_run_range(JacksCtx* ctx, const JacksEmPlan* plan, const JacksEmPar
     return JACKS_OK;
 }
 
-static int em_check_io(const JacksEmPlan* plan, const JacksEmParams* params, const JacksEmDeviceIO* io) {
+int em_check_io(const JacksEmPlan* plan, const JacksEmParams* params, const JacksEmDeviceIO* io) {
     if (!io->test || !io->ctrl || !io->w1) return fail(JACKS_E_INVALID, "test, ctrl and w1 are required");
     if (io->ctrl_lines != plan->L && io->ctrl_lines != 1)
         return fail(JACKS_E_SHAPE, "Expecting matched size between control and test data");   // infer.py:26
@@ -505,6 +475,8 @@ static int em_check_io(const JacksEmPlan* plan, const JacksEmParams* params, con
     if (params->n_iter < 0) return fail(JACKS_E_INVALID, "n_iter < 0");
     return JACKS_OK;
 }
+
+extern "C" {
 
 int jacks_em_run_device(JacksCtx* ctx, const JacksEmPlan* plan, const JacksEmParams* params,
                         const JacksEmDeviceIO* io, void* stream) {
@@ -529,9 +501,18 @@ struct CompactCubes {
     cudaEvent_t ready;
 };
 
+// What the pipelined host run does besides the plain inferJACKS call.
+struct HostRunOpts {
+    int32_t flags = 0;                    // JACKS_KEEP_RESIDENT | JACKS_ASYNC
+    const CompactCubes* cc = nullptr;     // run on compact cubes (already enqueued for upload) instead of the resident screen
+    bool w1_stays = false;                // E[w] is produced on the device even when io->w1 is NULL (nothing is downloaded for it)
+    const jacks::KdeNull* kde = nullptr;  // p-values of every gene range right after its EM (jacks_run_screen_host) ...
+    double* pvals_host = nullptr;         // ... downloaded here, [n_genes, L]
+    JacksEmPlan** plan_out = nullptr;     // the (pending) plan: its device outputs stay valid until the next synchronise
+};
+
 static int em_batched_host_core(JacksCtx* ctx, const JacksEmParams* params, const int64_t* gene_offsets,
-                                const int32_t* guide_rows, int64_t n_genes, const JacksEmHostIO* io, int32_t keep_resident,
-                                const CompactCubes* cc);
+                                const int32_t* guide_rows, int64_t n_genes, const JacksEmHostIO* io, const HostRunOpts& opt);
 
 // Row gather straight out of PINNED host memory (zero-copy reads over PCIe): one CTA per (row, cube), 16-byte loads.
 // The SMs pull the rows themselves, so neither a host-side gather nor the H2D copy engine's queue (FIFO across
@@ -553,7 +534,7 @@ __global__ void __launch_bounds__(128) gather_rows_kernel(const double2* __restr
 // and run the EM on a re-based index.  For a pseudo-gene index over a few thousand control guides
 // this moves tens of megabytes instead of the whole screen, so its kernels and downloads need not wait for it.
 static int em_batched_host_compact(JacksCtx* ctx, const JacksEmParams* params, const int64_t* gene_offsets,
-                                   const int32_t* guide_rows, int64_t n_genes, const JacksEmHostIO* io, int32_t flags) {
+                                   const int32_t* guide_rows, int64_t n_genes, const JacksEmHostIO* io, HostRunOpts opt) {
     const int64_t N = io->n_rows;
     const int L = io->n_lines;
     const int64_t T = n_genes ? gene_offsets[n_genes] : 0;
@@ -588,6 +569,9 @@ static int em_batched_host_compact(JacksCtx* ctx, const JacksEmParams* params, c
     char* st_ctrl = st_test + (size_t)U * row_t;
     double* st_fx = (double*)(st_ctrl + (size_t)U * row_c);
     cudaStream_t s_in = ctx->copy_stream;
+    // the device cube is reused from call to call too: the kernels of the previous compact run (compute stream) may
+    // still be reading it, so the refill below is ordered behind them
+    if (ctx->cmp_done) cudaStreamWaitEvent(s_in, ctx->cmp_done, 0);
     const bool zero_copy = U > 0 && host_pointer_is_pinned(io->test) && host_pointer_is_pinned(io->ctrl);
     if (zero_copy) {
         // the list of rows and the (small) fixed-x gather go through the staging buffer; the cubes are pulled by the GPU
@@ -640,7 +624,11 @@ static int em_batched_host_compact(JacksCtx* ctx, const JacksEmParams* params, c
     cc.d_fx2 = fx ? cc.d_fx1 + U : nullptr;
     cc.n_rows = U;
     cc.ready = ctx->cmp_ready;
-    return em_batched_host_core(ctx, params, gene_offsets, rows2.data(), n_genes, io, flags, &cc);
+    opt.cc = &cc;
+    const int rc2 = em_batched_host_core(ctx, params, gene_offsets, rows2.data(), n_genes, io, opt);
+    if (!ctx->cmp_done && (e = cudaEventCreateWithFlags(&ctx->cmp_done, cudaEventDisableTiming)) != cudaSuccess) return cuda_fail(e, "cudaEventCreate");
+    cudaEventRecord(ctx->cmp_done, ctx->stream);        // the last kernel that reads the compact cube
+    return rc2;
 }
 
 extern "C" {
@@ -656,16 +644,21 @@ int jacks_em_batched_host(JacksCtx* ctx, const JacksEmParams* params, const int6
         if ((io->fixed_x1 == nullptr) != (io->fixed_x2 == nullptr)) return fail(JACKS_E_INVALID, "fixed_x1 and fixed_x2 go together");
         cudaError_t e = cudaSetDevice(ctx->device);
         if (e != cudaSuccess) return cuda_fail(e, "cudaSetDevice");
-        return em_batched_host_compact(ctx, params, gene_offsets, guide_rows, n_genes, io, flags);
+        HostRunOpts opt;
+        opt.flags = flags;
+        return em_batched_host_compact(ctx, params, gene_offsets, guide_rows, n_genes, io, opt);
     }
-    return em_batched_host_core(ctx, params, gene_offsets, guide_rows, n_genes, io, flags, nullptr);
+    HostRunOpts opt;
+    opt.flags = flags;
+    return em_batched_host_core(ctx, params, gene_offsets, guide_rows, n_genes, io, opt);
 }
 
 }  // extern "C"
 
 static int em_batched_host_core(JacksCtx* ctx, const JacksEmParams* params, const int64_t* gene_offsets,
-                                const int32_t* guide_rows, int64_t n_genes, const JacksEmHostIO* io, int32_t keep_resident,
-                                const CompactCubes* cc) {
+                                const int32_t* guide_rows, int64_t n_genes, const JacksEmHostIO* io, const HostRunOpts& opt) {
+    const CompactCubes* cc = opt.cc;
+    const int32_t keep_resident = opt.flags;
     const int64_t N = cc ? cc->n_rows : io->n_rows;
     const int L = io->n_lines;
     if (N < 0 || L < 1) return fail(JACKS_E_INVALID, "bad data shape N=%lld L=%d", (long long)N, L);
@@ -707,19 +700,22 @@ static int em_batched_host_core(JacksCtx* ctx, const JacksEmParams* params, cons
 
     // ---- outputs ------------------------------------------------------------------------------------
     // per-unit sizes: [0,1] per guide, [2,3] per gene row, [4,5] per guide row, [6,7] per gene
-    struct Out { char* host; size_t unit; bool per_guide; } outs[8] = {
+    constexpr int NO = 9;         // [8]: p-values of the screen job
+    struct Out { char* host; size_t unit; bool per_guide; } outs[NO] = {
         {(char*)io->x1, sizeof(double), true},         {(char*)io->x2, sizeof(double), true},
         {(char*)io->w1, (size_t)L * sizeof(double), false}, {(char*)io->w2, (size_t)L * sizeof(double), false},
         {(char*)io->y, (size_t)L * sizeof(double), true},   {(char*)io->tau, (size_t)L * sizeof(double), true},
-        {(char*)io->n_iters, sizeof(int32_t), false},  {(char*)io->bound, sizeof(double), false}};
-    if (!io->w1 && n_genes) { jacks_em_plan_destroy(plan); return fail(JACKS_E_INVALID, "w1 is required"); }
-    char* dptr[8] = {nullptr};
-    for (int i = 0; i < 8; ++i) {
+        {(char*)io->n_iters, sizeof(int32_t), false},  {(char*)io->bound, sizeof(double), false},
+        {(char*)(opt.kde ? opt.pvals_host : nullptr), (size_t)L * sizeof(double), false}};
+    if (!io->w1 && !opt.w1_stays && n_genes) { jacks_em_plan_destroy(plan); return fail(JACKS_E_INVALID, "w1 is required"); }
+    char* dptr[NO] = {nullptr};
+    for (int i = 0; i < NO; ++i) {
         const size_t bytes = outs[i].unit * (size_t)(outs[i].per_guide ? T : n_genes);
-        if (!outs[i].host || !bytes) continue;
+        if ((!outs[i].host && !(i == 2 && opt.w1_stays)) || !bytes) continue;
         if ((rc = plan->b->out[i].reserve(bytes)) != JACKS_OK) { jacks_em_plan_destroy(plan); return rc; }
         dptr[i] = (char*)plan->b->out[i].p;
     }
+    if (opt.plan_out) *opt.plan_out = plan;
     JacksEmDeviceIO dio;
     memset(&dio, 0, sizeof dio);
     dio.test = cc ? cc->d_test : (const double*)ctx->res_test.p; dio.ctrl = cc ? cc->d_ctrl : (const double*)ctx->res_ctrl.p;
@@ -737,6 +733,14 @@ static int em_batched_host_core(JacksCtx* ctx, const JacksEmParams* params, cons
     int R = 1;
     if (n_genes >= 4096) R = (int)std::min<int64_t>(16, n_genes / 2048);
     if (R > kMaxRanges) R = kMaxRanges;
+    // range r covers genes [gb(r), gb(r+1)); with p-values on, boundaries sit on multiples of 1,024 genes (one CTA of
+    // the evaluation kernel walks a line's cell table for 1,024 genes)
+    auto gb = [&](int r) -> int64_t {
+        if (r >= R) return n_genes;
+        int64_t g = n_genes * r / R;
+        if (opt.kde && R > 1) g = std::min<int64_t>(n_genes, (g + 512) / 1024 * 1024);
+        return g;
+    };
     bool ascending = upload;
     if (upload && R > 1) {
         for (int64_t i = 1; i < T && ascending; ++i) ascending = guide_rows[i] >= guide_rows[i - 1];
@@ -756,7 +760,7 @@ static int em_batched_host_core(JacksCtx* ctx, const JacksEmParams* params, cons
     const bool staged_out = !(keep_resident & JACKS_ASYNC);
     int64_t row_done = 0;        // rows [0, row_done) are already enqueued for upload
     for (int r = 0; r < R && rc == JACKS_OK; ++r) {
-        const int64_t g0 = n_genes * r / R, g1 = n_genes * (r + 1) / R;
+        const int64_t g0 = gb(r), g1 = gb(r + 1);
         if (upload) {
             int64_t row_hi = N;
             if (ascending && r + 1 < R && g1 > g0) row_hi = std::min<int64_t>(N, (int64_t)guide_rows[gene_offsets[g1] - 1] + 1);
@@ -773,12 +777,15 @@ static int em_batched_host_core(JacksCtx* ctx, const JacksEmParams* params, cons
             cudaStreamWaitEvent(s_k, ev_in[r], 0);
         }
         if (g1 > g0) rc = em_run_range(ctx, plan, params, &dio, s_k, g0, g1, r);
+        if (rc == JACKS_OK && opt.kde && g1 > g0 && dptr[8])
+            rc = jacks::kde_eval(ctx, *opt.kde, (const double*)dptr[2] + g0 * L, g1 - g0, (double*)dptr[8] + g0 * L, s_k);
         if (rc != JACKS_OK) break;
         cudaEventRecord(ev_k[r], s_k);
         if (staged_out) continue;          // downloads follow below, once every range is enqueued
         cudaStreamWaitEvent(s_out, ev_k[r], 0);
         const int64_t t0 = gene_offsets[g0], t1 = gene_offsets[g1];
-        for (int i = 0; i < 8 && rc == JACKS_OK; ++i) {
+        for (int i = 0; i < NO && rc == JACKS_OK; ++i) {
+            if (!outs[i].host) continue;
             if (!dptr[i]) continue;
             const size_t lo = outs[i].unit * (size_t)(outs[i].per_guide ? t0 : g0), hi = outs[i].unit * (size_t)(outs[i].per_guide ? t1 : g1);
             if (hi > lo && (e = cudaMemcpyAsync(outs[i].host + lo, dptr[i] + lo, hi - lo, cudaMemcpyDeviceToHost, s_out)) != cudaSuccess) rc = cuda_fail(e, "D2H result");
@@ -788,11 +795,11 @@ static int em_batched_host_core(JacksCtx* ctx, const JacksEmParams* params, cons
         // Synchronous call: the host thread drains range r (through the pinned ring when the caller's arrays are
         // pageable) while the kernels of the later ranges run.
         for (int r = 0; r < R && rc == JACKS_OK; ++r) {
-            const int64_t g0 = n_genes * r / R, g1 = n_genes * (r + 1) / R;
+            const int64_t g0 = gb(r), g1 = gb(r + 1);
             const int64_t t0 = gene_offsets[g0], t1 = gene_offsets[g1];
             cudaStreamWaitEvent(s_out, ev_k[r], 0);
-            for (int i = 0; i < 8 && rc == JACKS_OK; ++i) {
-                if (!dptr[i]) continue;
+            for (int i = 0; i < NO && rc == JACKS_OK; ++i) {
+                if (!dptr[i] || !outs[i].host) continue;
                 const size_t lo = outs[i].unit * (size_t)(outs[i].per_guide ? t0 : g0), hi = outs[i].unit * (size_t)(outs[i].per_guide ? t1 : g1);
                 if (hi > lo) rc = ctx->stager.d2h(outs[i].host + lo, dptr[i] + lo, hi - lo, s_out);
             }
@@ -803,6 +810,104 @@ static int em_batched_host_core(JacksCtx* ctx, const JacksEmParams* params, cons
     ctx->pending_plans.push_back(plan);
     if (!cc && !(keep_resident & JACKS_KEEP_RESIDENT)) ctx->res_valid = false;
     if (rc != JACKS_OK || !(keep_resident & JACKS_ASYNC)) {
+        const int rs = jacks_ctx_synchronize(ctx);
+        if (rc == JACKS_OK) rc = rs;
+    }
+    return rc;
+}
+
+
+// ---- the whole inference job of one screen (jacks_io.py:425-441) ------------------------------------------------------
+
+extern "C" int jacks_run_screen_device(JacksCtx* ctx, const JacksEmPlan* plan_real, const JacksEmPlan* plan_pseudo,
+                                       const JacksEmParams* params, const JacksScreenDeviceIO* io, void* stream) {
+    if (!ctx || !plan_real || !params || !io) return fail(JACKS_E_INVALID, "jacks_run_screen_device: NULL argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaError_t e = cudaSetDevice(ctx->device);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaSetDevice");
+    int rc;
+    const int L = plan_real->L;
+    const int64_t n_pseudo = plan_pseudo ? plan_pseudo->n_genes : 0;
+    if (n_pseudo > 0) {
+        if (plan_pseudo->L != L || plan_pseudo->n_rows != plan_real->n_rows) return fail(JACKS_E_INVALID, "the two plans describe different cubes");
+        if (!io->pseudo_w1) return fail(JACKS_E_INVALID, "pseudo_w1 is required when there are pseudo-genes");
+        // pseudo-genes: same cubes, never fixed_x (jacks_io.py:430); only E[w] (and what the caller asks for) is kept
+        JacksEmDeviceIO pio;
+        memset(&pio, 0, sizeof pio);
+        pio.test = io->real.test; pio.ctrl = io->real.ctrl; pio.ctrl_lines = io->real.ctrl_lines;
+        pio.ctrl_rowmean_fill = io->real.ctrl_rowmean_fill;
+        pio.w1 = io->pseudo_w1; pio.w2 = io->pseudo_w2; pio.n_iters = io->pseudo_n_iters;
+        if ((rc = em_check_io(plan_pseudo, params, &pio)) != JACKS_OK) return rc;
+        if ((e = cudaMemsetAsync(plan_pseudo->b->d_counters.p, 0, kCountersPerRange * sizeof(int), st)) != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync");
+        if ((rc = em_run_range(ctx, plan_pseudo, params, &pio, st, 0, n_pseudo, 0)) != JACKS_OK) return rc;
+    }
+    if (plan_real->n_genes > 0) {
+        if ((rc = em_check_io(plan_real, params, &io->real)) != JACKS_OK) return rc;
+        if ((e = cudaMemsetAsync(plan_real->b->d_counters.p, 0, kCountersPerRange * sizeof(int), st)) != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync");
+        if ((rc = em_run_range(ctx, plan_real, params, &io->real, st, 0, plan_real->n_genes, 0)) != JACKS_OK) return rc;
+    }
+    if (io->pvals || io->pseudo_pvals) {
+        if (n_pseudo < 2) return fail(JACKS_E_INVALID, "p-values need at least two pseudo-genes (got %lld)", (long long)n_pseudo);
+        jacks::KdeNull nl;
+        if ((rc = jacks::kde_null_prepare(ctx, io->pseudo_w1, n_pseudo, L, io->positive, st, &nl)) != JACKS_OK) return rc;
+        if (io->pvals && (rc = jacks::kde_eval(ctx, nl, io->real.w1, plan_real->n_genes, io->pvals, st)) != JACKS_OK) return rc;
+        if (io->pseudo_pvals && (rc = jacks::kde_eval(ctx, nl, io->pseudo_w1, n_pseudo, io->pseudo_pvals, st)) != JACKS_OK) return rc;
+    }
+    return JACKS_OK;
+}
+
+extern "C" int jacks_run_screen_host(JacksCtx* ctx, const JacksEmParams* params, const int64_t* gene_offsets,
+                                     const int32_t* guide_rows, int64_t n_genes, const int64_t* pseudo_offsets,
+                                     const int32_t* pseudo_rows, int64_t n_pseudo, const JacksScreenHostIO* io, int32_t flags) {
+    if (!ctx || !params || !io) return fail(JACKS_E_INVALID, "jacks_run_screen_host: NULL argument");
+    const JacksEmHostIO& rio = io->real;
+    if (!rio.test || !rio.ctrl) return fail(JACKS_E_INVALID, "test and ctrl are required");
+    if (rio.n_rows < 0 || rio.n_lines < 1) return fail(JACKS_E_INVALID, "bad data shape N=%lld L=%d", (long long)rio.n_rows, rio.n_lines);
+    if (rio.ctrl_lines != rio.n_lines && rio.ctrl_lines != 1)
+        return fail(JACKS_E_SHAPE, "Expecting matched size between control and test data");
+    if (n_pseudo < 0 || (n_pseudo > 0 && (!pseudo_offsets || !pseudo_rows))) return fail(JACKS_E_INVALID, "NULL pseudo-gene index");
+    const bool want_p = io->pvals || io->pseudo_pvals;
+    if (want_p && n_pseudo < 2) return fail(JACKS_E_INVALID, "p-values need at least two pseudo-genes (got %lld)", (long long)n_pseudo);
+    cudaError_t e = cudaSetDevice(ctx->device);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaSetDevice");
+    const int L = rio.n_lines;
+    int rc;
+    jacks::KdeNull nl;
+    JacksEmPlan* pplan = nullptr;
+    if (n_pseudo > 0) {
+        // 1. pseudo-genes on a compact cube of the rows they reference, uploaded ahead of the screen
+        JacksEmHostIO pio;
+        memset(&pio, 0, sizeof pio);
+        pio.test = rio.test; pio.ctrl = rio.ctrl; pio.n_rows = rio.n_rows; pio.n_lines = L; pio.ctrl_lines = rio.ctrl_lines;
+        pio.ctrl_rowmean_fill = rio.ctrl_rowmean_fill;
+        pio.w1 = io->pseudo_w1; pio.w2 = io->pseudo_w2; pio.n_iters = io->pseudo_n_iters;
+        HostRunOpts popt;
+        popt.flags = JACKS_ASYNC;
+        popt.w1_stays = true;
+        popt.plan_out = &pplan;
+        if ((rc = em_batched_host_compact(ctx, params, pseudo_offsets, pseudo_rows, n_pseudo, &pio, popt)) != JACKS_OK) { jacks_ctx_synchronize(ctx); return rc; }
+        // 2. null densities from the pseudo-gene E[w], still on the device
+        if (want_p && (rc = jacks::kde_null_prepare(ctx, (const double*)pplan->b->out[2].p, n_pseudo, L, io->positive, ctx->stream, &nl)) != JACKS_OK) { jacks_ctx_synchronize(ctx); return rc; }
+        if (io->pseudo_pvals) {
+            if ((rc = pplan->b->out[8].reserve((size_t)n_pseudo * L * sizeof(double))) == JACKS_OK)
+                rc = jacks::kde_eval(ctx, nl, (const double*)pplan->b->out[2].p, n_pseudo, (double*)pplan->b->out[8].p, ctx->stream);
+            if (rc == JACKS_OK) {
+                cudaEvent_t ev = nullptr;
+                if ((e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming)) != cudaSuccess) rc = cuda_fail(e, "cudaEventCreate");
+                else {
+                    cudaEventRecord(ev, ctx->stream); cudaStreamWaitEvent(ctx->out_stream, ev, 0); ctx->pending_events.push_back(ev);
+                    if ((e = cudaMemcpyAsync(io->pseudo_pvals, pplan->b->out[8].p, (size_t)n_pseudo * L * sizeof(double), cudaMemcpyDeviceToHost, ctx->out_stream)) != cudaSuccess) rc = cuda_fail(e, "D2H pseudo p-values");
+                }
+            }
+            if (rc != JACKS_OK) { jacks_ctx_synchronize(ctx); return rc; }
+        }
+    }
+    // 3. the screen itself: upload once, real genes range by range (EM, p-values, download)
+    HostRunOpts ropt;
+    ropt.flags = flags;
+    if (io->pvals) { ropt.kde = &nl; ropt.pvals_host = io->pvals; }
+    rc = em_batched_host_core(ctx, params, gene_offsets, guide_rows, n_genes, &rio, ropt);
+    if (rc != JACKS_OK || !(flags & JACKS_ASYNC)) {
         const int rs = jacks_ctx_synchronize(ctx);
         if (rc == JACKS_OK) rc = rs;
     }

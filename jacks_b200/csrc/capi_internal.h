@@ -27,7 +27,7 @@ struct DevBuf {
 // through JacksCtx::plan_pool instead of cudaMalloc/cudaFree (both synchronise the device).
 struct PlanBufs {
     jacks::DevBuf d_offsets, d_rows, d_ids, d_slot_off, d_slot_rows, d_deferred, d_counters, d_scratch, d_tpd;
-    jacks::DevBuf out[8];                   // device-side outputs of a host call that used this plan
+    jacks::DevBuf out[9];                   // device-side outputs of a host call that used this plan ([8]: p-values)
     long long sig_genes = -1, sig_guides = -1;   // shape of the last plan served (pool lookups prefer a match)
     void release() {
         for (auto& o : out) o.release();
@@ -72,9 +72,67 @@ struct JacksCtx {
     // compact cubes of JACKS_UPLOAD_USED_ROWS calls: pinned staging, device copy, "upload enqueued" event
     void* cmp_stage = nullptr; size_t cmp_stage_cap = 0;
     jacks::DevBuf cmp_dev, cmp_rows;
-    cudaEvent_t cmp_ready = nullptr;
+    cudaEvent_t cmp_ready = nullptr;     // the compact upload has read its pinned staging
+    cudaEvent_t cmp_done = nullptr;      // the kernels of the last compact run have read the device cube
+    bool kde_attr_set = false;  // kde_pvalues_fast's shared-memory attribute has been set on this device
     HostStager stager;          // pinned ring of the synchronous host entry points (pageable caller buffers)
     std::vector<PlanBufs*> plan_pool;          // recycled plan buffers
     std::vector<JacksEmPlan*> pending_plans;   // plans of asynchronous host calls, destroyed at the next synchronise
     std::vector<cudaEvent_t> pending_events;
 };
+
+// ------------------------------------------------------------------------------------------------
+// Batched-EM plan (built by jacks_em_plan_create, capi.cu)
+// ------------------------------------------------------------------------------------------------
+#include "../../include/jacks_b200.h"
+#include "em_common.cuh"
+
+constexpr int kCountersPerRange = 16;      // [0] deferred count, [1..] one work counter per launch of a gene range
+constexpr int kMaxRanges = 64;
+constexpr int kCounterInts = kCountersPerRange * kMaxRanges;
+
+struct EmBucket {
+    int G;            // guide count (fast buckets); 0 for the generic bucket
+    int W;            // warps per gene of the fast kernel
+    int n;            // genes in the bucket
+    int ids_off;      // offset into JacksEmPlan::d_ids / d_slot_off
+    long long rows_off;   // offset into JacksEmPlan::d_slot_rows (fast buckets)
+};
+
+struct JacksEmPlan {
+    JacksCtx* ctx;
+    int64_t n_genes, n_rows, total_guides;
+    int L;
+    PlanBufs* b;               // device buffers (from the context's pool)
+    std::vector<EmBucket> fast;
+    std::vector<int> h_ids;    // host copy of d_ids (ascending gene ids inside each bucket)
+    EmBucket generic;          // n == 0 if empty
+    int generic_maxG;
+    EmBucket big;              // genes of the generic kind large enough for a CTA each (em_big_kernel)
+    int big_maxG;
+    int big_grid;
+    long long big_slab;        // doubles of global scratch per CTA
+    int fast_maxG;
+    int n_fast_genes;
+    jacks::EmGenericConfig cfg_generic, cfg_deferred;
+};
+
+// Enqueue the EM of the genes with id in [g0, g1) (caller order) on `st`.  `range` selects the counter block
+// (0 .. kMaxRanges-1); the caller zeroes d_counters before the first range of a run.
+int em_run_range(JacksCtx* ctx, const JacksEmPlan* plan, const JacksEmParams* params, const JacksEmDeviceIO* io,
+                 cudaStream_t st, int64_t g0, int64_t g1, int range);
+int em_check_io(const JacksEmPlan* plan, const JacksEmParams* params, const JacksEmDeviceIO* io);
+bool host_pointer_is_pinned(const void* p);
+
+// ------------------------------------------------------------------------------------------------
+// KDE p-values (kde_pvalues.cu): the null density of every line, prepared once, evaluated for any block of genes
+// ------------------------------------------------------------------------------------------------
+namespace jacks {
+struct KdeNull {
+    double* sT; double* stats; long long* cell_off; double* cells;     // views into JacksCtx::tmp
+    long long ld; int n_lines; int positive; int brute;
+};
+int kde_null_prepare(JacksCtx* ctx, const double* w1_pseudo, int64_t n_pseudo, int32_t n_lines, int32_t positive,
+                     cudaStream_t st, KdeNull* out);
+int kde_eval(JacksCtx* ctx, const KdeNull& nl, const double* w1_genes, int64_t n_genes, double* pvals, cudaStream_t st);
+}  // namespace jacks

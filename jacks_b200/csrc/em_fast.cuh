@@ -57,6 +57,21 @@ __device__ __forceinline__ double fast_rcp(double d) {
     return fma(r, t, r);
 }
 
+// Reciprocal seed for a Newton refinement: MUFU.RCP64H delivers the HIGH word of 1/d (>= 20 bits); as PTX defines it the
+// low word is zero, which costs a register move per seed.  The low word only carries mantissa bits 2^-21 and below, so
+// any bit pattern will do for a seed: it is taken from `junk`, a value that is dead at this point, whose register pair
+// the seed can then occupy without a move.
+__device__ __forceinline__ double rcp_seed(double d, double junk) {
+    double t;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(t) : "d"(d));
+#ifdef JACKS_SEED_ZERO_LOW
+    (void)junk;
+    return t;
+#else
+    return __hiloint2double(__double2hiint(t), __double2loint(junk));
+#endif
+}
+
 // Median of G finite values held in registers (numpy semantics: mean of the two middle values for
 // even G).  G <= 5 use min/max networks (the median stays an exact element / exact pair mean);
 // larger G use rank selection with index tie-break, O(G^2) compares, no data movement.
@@ -173,28 +188,33 @@ __device__ __forceinline__ void team_allsum(double (&v)[NV], double* scr, double
 // lanes still execute the arithmetic on whatever the shared-memory words past the line hold (the
 // allocation carries one step of slack, see em_fast_smem_doubles), but neither store nor
 // accumulate it: the stores and the three accumulating FMAs of that line are predicated.
-// RELOAD: each pd2 register is refilled with the next step's value (`pd_next`, L2) as soon as its
+// reload: each pd2 register is refilled with the next step's value (`pd_next`, L2) as soon as its
 // only use (t1 = x2*w2 + pd2) has issued -- the load has the rest of this step and the W step of
 // the next to land.  The bound therefore accumulates t1*th and the caller removes x2*sum th*w2.
 template <int G> struct EmX { double x1[G], x2[G], tx1[G], tx2[G]; };
+// What the sweep needs of x: E[x^2] and the doubled moments (the state is th = tau/2).  E[x] itself enters only as
+// -2*x1*w1, formed from tx1 with a (free) operand negation.
+template <int G> struct EmXs { double x2[G], tx1[G], tx2[G]; };
 
 // TM: th lives in tensor memory (tmem.cuh) instead of shared memory: the step's U*G values are U*G consecutive
 // column pairs of the thread's own TMEM lane at `tcol`, moved by one tcgen05.ld and one tcgen05.st per step.
 // A lane's dead line (MASKED, !valid) then holds garbage that is loaded, computed on and stored back, never used.
 // TM == 2: pd2 lives in TMEM as well (columns `pcol`...), loaded at the top of the step that uses it: no L2 round
 // trip, no look-ahead registers, no global slab.
-template <int G, int U, int UP, bool UNIT_C, bool MASKED, bool RELOAD, int TM>
+template <int G, int U, int UP, bool UNIT_C, bool MASKED, int TM>
 __device__ __forceinline__ void em_sweep(const uint32_t tcol, const uint32_t pcol, const double* __restrict__ ys, double (&pd)[UP][G],
                                          const double* __restrict__ pd_next, const int Lp,
                                          double* __restrict__ ths, double* __restrict__ w1p,
                                          double* __restrict__ w2g, const int L, const int l, const int step,
-                                         const EmX<G>& x, const double ivw, const double mw, const double c_tau,
-                                         double (&a1)[G], double (&a2)[G], double (&ab)[G], const bool valid) {
+                                         const EmXs<G>& x, const double ivw, const double mw, const double c_tau,
+                                         double (&a1)[G], double (&a2)[G], double (&ab)[G], const bool valid, const bool reload) {
     double yv[U][G], tv[U][G];
     uint32_t traw[TM ? 2 * U * G : 2];
     uint32_t praw[TM == 2 ? 2 * U * G : 2];
     if (TM) tmem_ld_issue<(TM ? U * G : 1)>(tcol, reinterpret_cast<uint32_t(&)[2 * (TM ? U * G : 1)]>(traw));
+#ifndef JACKS_PD_LATE
     if (TM == 2) tmem_ld_issue<(TM == 2 ? U * G : 1)>(pcol, reinterpret_cast<uint32_t(&)[2 * (TM == 2 ? U * G : 1)]>(praw));
+#endif
 #pragma unroll
     for (int u = 0; u < U; ++u) {
         // the masked line of a lane that has run out of lines reads line 0 instead (any valid word)
@@ -212,6 +232,7 @@ __device__ __forceinline__ void em_sweep(const uint32_t tcol, const uint32_t pco
 #pragma unroll
             for (int g = 0; g < G; ++g)
                 tv[u][g] = __hiloint2double((int)traw[2 * (u * G + g) + 1], (int)traw[2 * (u * G + g)]);
+#ifndef JACKS_PD_LATE
         if (TM == 2) {
 #pragma unroll
             for (int u = 0; u < U; ++u)
@@ -219,6 +240,7 @@ __device__ __forceinline__ void em_sweep(const uint32_t tcol, const uint32_t pco
                 for (int g = 0; g < G; ++g)
                     pd[u][g] = __hiloint2double((int)praw[2 * (u * G + g) + 1], (int)praw[2 * (u * G + g)]);
         }
+#endif
     }
     // W step, infer.py:112-116 (old tau, new x): den = 1/var0_w + sum_g x2*tau, num = mu0_w/var0_w + sum_g x1*y*tau
     double yt[U][G];
@@ -236,6 +258,19 @@ __device__ __forceinline__ void em_sweep(const uint32_t tcol, const uint32_t pco
             sa[u] = fma(x.tx2[g], tv[u][g], sa[u]);
             sb[u] = fma(x.tx1[g], yt[u][g], sb[u]);
         }
+#ifdef JACKS_PD_LATE
+    // tau_pr_den comes in only now, after the last use of the old tau: both arrays can pass through the SAME block of
+    // 2*U*G consecutive registers (LDTM needs them contiguous) without the first being copied out of the way
+    if (TM == 2) {
+        tmem_ld_issue<(TM == 2 ? U * G : 1)>(pcol, reinterpret_cast<uint32_t(&)[2 * (TM == 2 ? U * G : 1)]>(praw));
+        tmem_wait_ld();
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+#pragma unroll
+            for (int g = 0; g < G; ++g)
+                pd[u][g] = __hiloint2double((int)praw[2 * (u * G + g) + 1], (int)praw[2 * (u * G + g)]);
+    }
+#endif
     double r[U], e[U];
 #pragma unroll
     for (int u = 0; u < U; ++u) asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r[u]) : "d"(sa[u]));
@@ -245,20 +280,20 @@ __device__ __forceinline__ void em_sweep(const uint32_t tcol, const uint32_t pco
     for (int u = 0; u < U; ++u) e[u] = fma(e[u], e[u], e[u]);
 #pragma unroll
     for (int u = 0; u < U; ++u) r[u] = fma(r[u], e[u], r[u]);
-    double w1[U], w2[U], m2w1[U];
+    double w1[U], w2[U];
 #pragma unroll
     for (int u = 0; u < U; ++u) w1[u] = sb[u] * r[u];
 #pragma unroll
-    for (int u = 0; u < U; ++u) { w2[u] = fma(w1[u], w1[u], r[u]); m2w1[u] = -2.0 * w1[u]; }
+    for (int u = 0; u < U; ++u) w2[u] = fma(w1[u], w1[u], r[u]);
     // tau step, infer.py:118-121
     double d[U][G], t1[U][G], rd[U][G], ee[U][G];
 #pragma unroll
     for (int u = 0; u < U; ++u)
 #pragma unroll
         for (int g = 0; g < G; ++g) {
-            d[u][g] = fma(x.x1[g], m2w1[u], yv[u][g]);
+            d[u][g] = fma(-x.tx1[g], w1[u], yv[u][g]);
             t1[u][g] = fma(x.x2[g], w2[u], pd[u][g]);
-            if (RELOAD && TM != 2) pd[u][g] = __ldg(pd_next + g * Lp + u * step);
+            if (TM != 2 && reload) pd[u][g] = __ldg(pd_next + g * Lp + u * step);
         }
 #pragma unroll
     for (int u = 0; u < U; ++u)
@@ -267,7 +302,7 @@ __device__ __forceinline__ void em_sweep(const uint32_t tcol, const uint32_t pco
 #pragma unroll
     for (int u = 0; u < U; ++u)
 #pragma unroll
-        for (int g = 0; g < G; ++g) asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(rd[u][g]) : "d"(d[u][g]));
+        for (int g = 0; g < G; ++g) rd[u][g] = rcp_seed(d[u][g], tv[u][g]);       // the old tau is dead by now
 #pragma unroll
     for (int u = 0; u < U; ++u)
 #pragma unroll
@@ -321,32 +356,41 @@ __device__ __forceinline__ void em_sweep(const uint32_t tcol, const uint32_t pco
 // (HALF the X-step sums) and ab = sum pd2*th.
 template <int G> struct EmSums { double a1[G], a2[G], ab; };
 
+// Lines per sweep step: U*G >= 8 independent elements, and few enough (<= 20) to stay in registers
+// (measured at 400 lines: G = 5 wants 3 lines from shared memory, 4 from TMEM; G = 6 wants 3 either way).
+template <int G, int TM> __host__ __device__ constexpr int em_sweep_lines() {
+    return (G >= 9) ? 1 : (G >= 7) ? 2 : ((G >= (TM ? 6 : 5)) ? 3 : 4);
+}
+
 // One EM pass over all lines of a warp.  Deliberately NOT inlined: compiled on its own, ptxas
 // interleaves the U*G independent element chains of a step (a lone warp then keeps the FP64 pipe
 // ~75 % busy, tools/sass_sim.py); inlined into the kernel it serialises them line by line.
-// The step plan is warp-uniform (no divergence): `n` = lines of the warp's fullest lane, taken
-// U at a time while more than U remain, then one final MASKED step of 1..U lines whose last line
-// is live only in the lanes with l < L.
-// pd2 lives in an L2-resident global slab [G][Lp] (read once per pass, never written after staging, so
+//
+// Step plan (warp-uniform, no divergence).  `n` = lines of the warp's fullest lane: `n_big` steps of UMAX lines, then one
+// final MASKED step of B = 1..UMAX lines whose last line is live only in the lanes with l < L.  B is a template
+// parameter (the kernel switches over it once per pass), so only the two step bodies a launch actually uses occupy the
+// instruction cache.  (Measured at 400 lines, 13 = 4+4+4+1 against the balanced 4+3+3+3: 6.70 against 6.88 ms -- the
+// kernel is bound by instruction dispatch, FP64 instructions weighing ~2.6 slots each, and a 3-line step carries more
+// bookkeeping per line than a 4-line one; the short tail step is cheap in those terms.)
+//
+// pd2 (TM != 2) lives in an L2-resident global slab [G][Lp] (read once per pass, never written after staging, so
 // it does not have to occupy shared memory); rows are padded (Lp >= L + U*STEP) so that the look-ahead
-// loads need no bounds logic.
-template <int G, int STEP, bool UNIT_C, int TM>
+// loads need no bounds logic.  A step refills its pd registers for the NEXT step, which is never taller than itself.
+template <int G, int STEP, bool UNIT_C, int TM, int B>
 __device__ __noinline__ EmSums<G> em_sweep_all(const uint32_t tbase, const uint32_t pdoff, const double* ys, const double* tpdg, const int Lp, double* ths,
                                                double* w1p, double* w2g, const int L, const int l0,
-                                               const int n_warp, const EmX<G> x, const double ivw, const double mw,
+                                               const int n_big, const EmXs<G> x, const double ivw, const double mw,
                                                const double c_tau) {
+    constexpr int UMAX = em_sweep_lines<G, TM>();
+    constexpr int UP = UMAX;
     double a1[G], a2[G], ab[G];
 #pragma unroll
     for (int g = 0; g < G; ++g) { a1[g] = 0.0; a2[g] = 0.0; ab[g] = 0.0; }
-    // lines per step: U*G >= 8 independent elements, and few enough (<= 20) to stay in registers
-    // (measured at 400 lines: G = 5 wants 3 lines from shared memory, 4 from TMEM; G = 6 wants 3 either way)
-    constexpr int U = (G >= 9) ? 1 : (G >= 7) ? 2 : ((G >= (TM ? 6 : 5)) ? 3 : 4);
     int l = l0;
-    int n = n_warp;
-    double pd[U][G];
+    double pd[UP][G];
     if (TM != 2) {
 #pragma unroll
-        for (int u = 0; u < U; ++u)
+        for (int u = 0; u < UP; ++u)
 #pragma unroll
             for (int g = 0; g < G; ++g) pd[u][g] = __ldg(tpdg + g * Lp + l + u * STEP);
     }
@@ -354,13 +398,9 @@ __device__ __noinline__ EmSums<G> em_sweep_all(const uint32_t tbase, const uint3
     // back; waiting here rather than after the last store hides the store latency behind the reduction and X step
     if (TM) tmem_wait_st();
     uint32_t tcol = tbase;
-    for (; n > U; n -= U, l += U * STEP, tcol += 2 * U * G)
-        em_sweep<G, U, U, UNIT_C, false, true, TM>(tcol, tcol + pdoff, ys, pd, tpdg + l + U * STEP, Lp, ths, w1p, w2g, L, l, STEP, x, ivw, mw, c_tau, a1, a2, ab, true);
-    const bool valid = (l + (n - 1) * STEP) < L;
-    if (n == 1) em_sweep<G, 1, U, UNIT_C, true, false, TM>(tcol, tcol + pdoff, ys, pd, nullptr, Lp, ths, w1p, w2g, L, l, STEP, x, ivw, mw, c_tau, a1, a2, ab, valid);
-    else if (U >= 2 && n == 2) em_sweep<G, (U >= 2 ? 2 : 1), U, UNIT_C, true, false, TM>(tcol, tcol + pdoff, ys, pd, nullptr, Lp, ths, w1p, w2g, L, l, STEP, x, ivw, mw, c_tau, a1, a2, ab, valid);
-    else if (U >= 3 && n == 3) em_sweep<G, (U >= 3 ? 3 : 1), U, UNIT_C, true, false, TM>(tcol, tcol + pdoff, ys, pd, nullptr, Lp, ths, w1p, w2g, L, l, STEP, x, ivw, mw, c_tau, a1, a2, ab, valid);
-    else if (U == 4 && n == 4) em_sweep<G, (U == 4 ? 4 : 1), U, UNIT_C, true, false, TM>(tcol, tcol + pdoff, ys, pd, nullptr, Lp, ths, w1p, w2g, L, l, STEP, x, ivw, mw, c_tau, a1, a2, ab, valid);
+    for (int i = 0; i < n_big; ++i, l += UP * STEP, tcol += 2 * UP * G)
+        em_sweep<G, UP, UP, UNIT_C, false, TM>(tcol, tcol + pdoff, ys, pd, tpdg + l + UP * STEP, Lp, ths, w1p, w2g, L, l, STEP, x, ivw, mw, c_tau, a1, a2, ab, true, true);
+    em_sweep<G, B, UP, UNIT_C, true, TM>(tcol, tcol + pdoff, ys, pd, nullptr, Lp, ths, w1p, w2g, L, l, STEP, x, ivw, mw, c_tau, a1, a2, ab, (l + (B - 1) * STEP) < L, false);
     EmSums<G> r;
     // sum pd2*th = sum (t1 - x2*w2)*th: the accumulators hold sum t1*th
     r.ab = fma(-x.x2[0], a2[0], ab[0]);
@@ -369,6 +409,13 @@ __device__ __noinline__ EmSums<G> em_sweep_all(const uint32_t tbase, const uint3
 #pragma unroll
     for (int g = 0; g < G; ++g) { r.a1[g] = a1[g]; r.a2[g] = a2[g]; }
     return r;
+}
+
+// The plan for `n` lines per lane (see em_sweep_all): n = n_big*umax + B, 1 <= B <= umax.
+__device__ __forceinline__ void em_step_plan(int n, int umax, int& B, int& n_big) {
+    if (n < 1) n = 1;          // an empty strip (W > 1, short line axis) runs one fully masked step
+    n_big = (n - 1) / umax;
+    B = n - n_big * umax;
 }
 
 // Stage a gene: y = test - ctrl (shared) and pd2 = 2*tau_pr_den (global slab) for the lane's lines, infer.py:58-70.
@@ -548,6 +595,7 @@ __global__ void __launch_bounds__(TM ? kTmemTeams * 32 : W * 32, TM ? 2 : 0) em_
     static_assert(!TM || W == 1, "the TMEM variant runs one-warp teams");
     constexpr int NV = 2 * G + 1;
     constexpr int STEP = 32 * W;
+    constexpr int UMAX = em_sweep_lines<G, TM>();
     extern __shared__ double smem[];
     const int L = a.L;
     const int lane = threadIdx.x & 31;
@@ -614,6 +662,8 @@ __global__ void __launch_bounds__(TM ? kTmemTeams * 32 : W * 32, TM ? 2 : 0) em_
         const int wv = (W == 1) ? 0 : (warp + slot) % W;
         const int l0 = wv * 32 + lane;
         const int n_warp = (L - wv * 32 + STEP - 1) / STEP;     // lines of this warp's fullest lane (lane 0)
+        int plan_B, plan_big;
+        em_step_plan(n_warp, UMAX, plan_B, plan_big);
 
         // ---- stage y and tau_pr_den (infer.py:58-70) ---------------------------------------
         double x1r[G], x2r[G], fill[G];
@@ -790,13 +840,16 @@ __global__ void __launch_bounds__(TM ? kTmemTeams * 32 : W * 32, TM ? 2 : 0) em_
                     mw = mu0_w / var0_w;
                 }
                 {
-                    EmX<G> xv;
+                    EmXs<G> xv;
 #pragma unroll
-                    for (int g = 0; g < G; ++g) {
-                        xv.x1[g] = x1r[g]; xv.x2[g] = x2r[g];
-                        xv.tx1[g] = 2.0 * x1r[g]; xv.tx2[g] = 2.0 * x2r[g];
-                    }
-                    const EmSums<G> r = em_sweep_all<G, STEP, UNIT_C, TM>(tbase, pdoff, ys, tpdg, Lp, taus, w1g, w2g, L, l0, n_warp, xv, ivw, mw, c_tau);
+                    for (int g = 0; g < G; ++g) { xv.x2[g] = x2r[g]; xv.tx1[g] = 2.0 * x1r[g]; xv.tx2[g] = 2.0 * x2r[g]; }
+                    EmSums<G> r;
+#define JACKS_SWEEP(BB) r = em_sweep_all<G, STEP, UNIT_C, TM, (BB <= UMAX ? BB : 1)>(tbase, pdoff, ys, tpdg, Lp, taus, w1g, w2g, L, l0, plan_big, xv, ivw, mw, c_tau)
+                    if (UMAX >= 4 && plan_B == 4) JACKS_SWEEP(4);
+                    else if (UMAX >= 3 && plan_B == 3) JACKS_SWEEP(3);
+                    else if (UMAX >= 2 && plan_B == 2) JACKS_SWEEP(2);
+                    else JACKS_SWEEP(1);
+#undef JACKS_SWEEP
 #pragma unroll
                     for (int g = 0; g < G; ++g) { acc[g] = r.a1[g]; acc[G + g] = r.a2[g]; }
                     acc[2 * G] = r.ab;

@@ -396,14 +396,10 @@ __global__ void __launch_bounds__(kPvThreads) kde_eval_kernel(const double* __re
 
 using namespace jacks;
 
-extern "C" int jacks_kde_pvalues_device(JacksCtx* ctx, const double* w1_genes, int64_t n_genes, const double* w1_pseudo,
-                                        int64_t n_pseudo, int32_t n_lines, int32_t positive, double* pvals, void* stream) {
-    if (!ctx || !pvals || (n_genes > 0 && !w1_genes) || !w1_pseudo) return fail(JACKS_E_INVALID, "jacks_kde_pvalues_device: NULL argument");
-    if (n_genes < 0 || n_pseudo < 2 || n_lines < 1) return fail(JACKS_E_INVALID, "need n_pseudo >= 2 and n_lines >= 1 (got %lld, %d)", (long long)n_pseudo, n_lines);
-    if (n_genes == 0) return JACKS_OK;
-    cudaError_t e = cudaSetDevice(ctx->device);
-    if (e != cudaSuccess) return cuda_fail(e, "cudaSetDevice");
-    cudaStream_t st = (cudaStream_t)stream;
+// Null density of every line from the pseudo-gene effects (jacks_io.py:76-79): compaction, bandwidth, sorted rows and
+// the cell table, all in ctx->tmp.  `out` stays valid until the next KDE call on this context.
+int jacks::kde_null_prepare(JacksCtx* ctx, const double* w1_pseudo, int64_t n_pseudo, int32_t n_lines, int32_t positive,
+                            cudaStream_t st, KdeNull* out) {
     // rows padded to a power of two (>= one sort tile) so the bitonic network needs no bounds checks
     long long ld = kSortTileD;
     while (ld < n_pseudo) ld <<= 1;
@@ -412,6 +408,7 @@ extern "C" int jacks_kde_pvalues_device(JacksCtx* ctx, const double* w1_genes, i
                          (size_t)(n_lines + 1) * sizeof(long long) + (size_t)cell_cap * kCellRec * sizeof(double);
     int rc = ctx->tmp.reserve(bytes);
     if (rc != JACKS_OK) return rc;
+    cudaError_t e;
     double* sT = (double*)ctx->tmp.p;
     double* stats = sT + ld * n_lines;
     long long* cell_off = (long long*)(stats + (size_t)n_lines * 8);
@@ -419,8 +416,6 @@ extern "C" int jacks_kde_pvalues_device(JacksCtx* ctx, const double* w1_genes, i
     const bool brute = getenv("JACKS_KDE_BRUTE") != nullptr;          // validation: force the O(n) sums
     kde_line_stats<<<n_lines, kStatsThreads, 0, st>>>(w1_pseudo, n_pseudo, n_lines, ld, positive ? 1 : 0, sT, stats);
     ctx->launches++;
-    const long long per_cta = (long long)kPvThreads * kGT;
-    dim3 grid((unsigned)((n_genes + per_cta - 1) / per_cta), (unsigned)n_lines);
     if (!brute) {
         dim3 lg((unsigned)(ld / kSortTileD), (unsigned)n_lines);
         sort_rows_local<<<lg, 1024, 0, st>>>(sT, ld, 2, kSortTileD);
@@ -436,18 +431,50 @@ extern "C" int jacks_kde_pvalues_device(JacksCtx* ctx, const double* w1_genes, i
         }
         kde_cell_layout<<<1, 1, 0, st>>>(sT, ld, stats, n_lines, cell_cap, cell_off);
         kde_cell_moments<<<(unsigned)((cell_cap + 127) / 128), 128, 0, st>>>(sT, ld, stats, n_lines, cell_off, cells);
+        ctx->launches += 2;
+    }
+    if ((e = cudaGetLastError()) != cudaSuccess) return cuda_fail(e, "kde null kernels launch");
+    out->sT = sT; out->stats = stats; out->cell_off = cell_off; out->cells = cells;
+    out->ld = ld; out->n_lines = n_lines; out->positive = positive ? 1 : 0; out->brute = brute ? 1 : 0;
+    return JACKS_OK;
+}
+
+// p-values of `n_genes` rows of w1_genes [n_genes, n_lines] under a prepared null.
+int jacks::kde_eval(JacksCtx* ctx, const KdeNull& nl, const double* w1_genes, int64_t n_genes, double* pvals, cudaStream_t st) {
+    if (n_genes == 0) return JACKS_OK;
+    cudaError_t e;
+    const int n_lines = nl.n_lines;
+    if (!nl.brute) {
         dim3 fg((unsigned)((n_genes + kFastGenes - 1) / kFastGenes), (unsigned)n_lines);
         const size_t fsm = (size_t)kFastSmemCells * kCellRec * sizeof(double);
-        if ((e = cudaFuncSetAttribute(kde_pvalues_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsm)) != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute");
-        kde_pvalues_fast<<<fg, kFastThreads, fsm, st>>>(w1_genes, n_genes, n_lines, sT, ld, stats, cell_off, cells, positive ? 1 : 0, pvals);
-        ctx->launches += 3;
+        if (!ctx->kde_attr_set) {          // per device: one process may hold contexts on several
+            if ((e = cudaFuncSetAttribute(kde_pvalues_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsm)) != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute");
+            ctx->kde_attr_set = true;
+        }
+        kde_pvalues_fast<<<fg, kFastThreads, fsm, st>>>(w1_genes, n_genes, n_lines, nl.sT, nl.ld, nl.stats, nl.cell_off, nl.cells, nl.positive, pvals);
+        ctx->launches++;
     }
     // lines the cell table could not hold (pathological ranges), or everything when forced
-    kde_pvalues<<<grid, kPvThreads, 0, st>>>(w1_genes, n_genes, n_lines, sT, ld, stats, positive ? 1 : 0,
-                                             brute ? nullptr : cell_off, pvals);
+    const long long per_cta = (long long)kPvThreads * kGT;
+    dim3 grid((unsigned)((n_genes + per_cta - 1) / per_cta), (unsigned)n_lines);
+    kde_pvalues<<<grid, kPvThreads, 0, st>>>(w1_genes, n_genes, n_lines, nl.sT, nl.ld, nl.stats, nl.positive,
+                                             nl.brute ? nullptr : nl.cell_off, pvals);
     if ((e = cudaGetLastError()) != cudaSuccess) return cuda_fail(e, "kde kernels launch");
     ctx->launches++;
     return JACKS_OK;
+}
+
+extern "C" int jacks_kde_pvalues_device(JacksCtx* ctx, const double* w1_genes, int64_t n_genes, const double* w1_pseudo,
+                                        int64_t n_pseudo, int32_t n_lines, int32_t positive, double* pvals, void* stream) {
+    if (!ctx || !pvals || (n_genes > 0 && !w1_genes) || !w1_pseudo) return fail(JACKS_E_INVALID, "jacks_kde_pvalues_device: NULL argument");
+    if (n_genes < 0 || n_pseudo < 2 || n_lines < 1) return fail(JACKS_E_INVALID, "need n_pseudo >= 2 and n_lines >= 1 (got %lld, %d)", (long long)n_pseudo, n_lines);
+    if (n_genes == 0) return JACKS_OK;
+    cudaError_t e = cudaSetDevice(ctx->device);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaSetDevice");
+    KdeNull nl;
+    int rc = kde_null_prepare(ctx, w1_pseudo, n_pseudo, n_lines, positive, (cudaStream_t)stream, &nl);
+    if (rc != JACKS_OK) return rc;
+    return kde_eval(ctx, nl, w1_genes, n_genes, pvals, (cudaStream_t)stream);
 }
 
 extern "C" int jacks_kde_pvalues_host(JacksCtx* ctx, const double* w1_genes, int64_t n_genes, const double* w1_pseudo,

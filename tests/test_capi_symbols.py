@@ -27,7 +27,7 @@ def test_library_exports_every_declared_symbol():
 def test_abi_version_and_defaults():
     from jacks_b200 import _native
     lib = _native.lib()
-    assert lib.jacks_abi_version() == 1
+    assert lib.jacks_abi_version() == 2
     p = _native.default_params()
     assert (p.n_iter, p.apply_w_hp, p.tol, p.mu0_x, p.var0_x, p.mu0_w, p.var0_w, p.tau_prior_strength) == \
         (50, 0, 0.1, 1.0, 1.0, 0.0, 1e4, 0.5)                   # infer.py:18, :55
