@@ -1,13 +1,22 @@
 """Gene-sharded data parallelism over the GPUs of one box (one process per GPU, torch.distributed).
 
-Genes are independent (jacks/jacks/infer.py:20-29 carries no state from one gene to the next), so the batched
-EM shards by gene with NO collective inside the iteration: every rank runs the kernels on a contiguous block of
-the gene index, cost-balanced by guide count, and ONE all-gather of the packed per-gene results (w1, w2, x1, x2,
-iteration counts) over NCCL / NVLink hands every rank the full answer.  1-rank and N-rank results are bit-identical
-because nothing is reduced across ranks.
+Genes are independent (jacks/jacks/infer.py:20-29 carries no state from one gene to the next), so the EM shards by gene
+with NO collective inside the iteration.  The job of one screen (jacks/jacks/jacks_io.py:425-441) runs like this:
 
-The data cubes are replicated (each rank uploads what its genes reference; pseudo-genes reference control rows
-anywhere in the cube).  Under the gloo backend (CPU tests) tensors stay on the host.
+  1. every rank takes a contiguous block of the real genes and of the pseudo-genes (balanced by guide count) and uploads
+     ONLY the guide rows those reference -- its slice of the screen plus the few thousand control-guide rows the
+     pseudo-genes draw from -- as a compact cube with a re-based index;
+  2. EM of both blocks on the rank's GPU (the same kernels as the one-GPU call);
+  3. ONE all-to-all over NCCL / NVLink turns "my genes x all lines" into "all genes x my lines" for E[w] of real and
+     pseudo-genes (each rank keeps L/W lines: 1/W of what an all-gather of the pseudo-gene E[w] would move);
+  4. the KDE null of a line needs all pseudo-genes of that line and nothing else, so the p-values are line-sharded:
+     every rank prepares the null densities of its lines and evaluates every real gene on them;
+  5. ONE gather (a one-sided all-to-all) hands rank `dst` the per-gene results: w1, w2, x1, x2, iteration counts and
+     the p-value column blocks.
+
+Nothing is reduced across ranks and every per-line sum runs over the pseudo-genes in their original order, so 1-rank and
+N-rank results are bit-identical.  All buffers between steps 2 and 5 stay on the device; under the gloo backend (CPU
+tests) the same driver runs on host tensors with an injected engine (CPU restatements of the kernels).
 """
 import numpy as np
 
@@ -29,6 +38,310 @@ def local_index(offsets, rows, lo, hi):
     return offsets[lo:hi + 1] - offsets[lo], np.asarray(rows)[offsets[lo]:offsets[hi]]
 
 
+def line_bounds(n_lines, world):
+    """Contiguous line blocks [lb[r], lb[r+1]) of the p-value stage."""
+    return np.linspace(0, n_lines, world + 1).astype(np.int64)
+
+
+def compact_rows(index_rows, n_rows):
+    """Rows an index references (ascending, unique) and the index re-based onto them."""
+    index_rows = np.asarray(index_rows, dtype=np.int64)
+    used = np.unique(index_rows)
+    remap = np.full(n_rows, -1, dtype=np.int64)
+    remap[used] = np.arange(len(used))
+    return used, remap[index_rows].astype(np.int32)
+
+
+def _world(group):
+    import torch.distributed as dist
+    if not dist.is_initialized():
+        return 1, 0
+    return dist.get_world_size(group), dist.get_rank(group)
+
+
+def _resolve_device(device, group):
+    """The CUDA device of this rank: the explicit argument, else torch's current device (what torchrun scripts set from
+    LOCAL_RANK) -- one answer for the kernels AND the collectives.  None under gloo."""
+    import torch
+    import torch.distributed as dist
+    if dist.is_initialized() and dist.get_backend(group) != 'nccl':
+        return None
+    if not torch.cuda.is_available():
+        return None
+    return int(device) if device is not None else torch.cuda.current_device()
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# Engines: what one rank computes.  The product engine drives the C-ABI on device tensors; tests inject a CPU engine.
+# ----------------------------------------------------------------------------------------------------------------------
+class NativeEngine(object):
+    """This rank's GPU through the C-ABI device entry points (jacks_em_run_device, jacks_kde_pvalues_device) on torch
+    CUDA tensors, everything enqueued on torch's current stream."""
+
+    def __init__(self, device):
+        import torch
+        from . import _native
+        self.torch, self.nat = torch, _native
+        self.device = torch.device('cuda', int(device))
+        self.ctx = _native.context(int(device))
+        self._plans = {}
+
+    def upload(self, array):
+        """Host array -> device tensor (through a pinned copy when the source is pageable)."""
+        t = self.torch.from_numpy(np.ascontiguousarray(array))
+        return t.to(self.device, non_blocking=True)
+
+    def plan(self, key, offsets, rows, n_rows, n_lines):
+        """Plans are cached per key: a resident screen is inferred again and again (benchmark, bootstrap draws)."""
+        if key is None or key not in self._plans:
+            p = self.nat.EmPlan(self.ctx, offsets, rows, n_rows, n_lines)
+            if key is None:
+                return p
+            self._plans[key] = p
+        return self._plans[key]
+
+    def em(self, plan, test, ctrl, params, fixed_x1=None, fixed_x2=None, want_x=True, y_tau=False, w1_out=None):
+        """w1_out: an [n, L] device view E[w] is written into (the exchange buffer), instead of a fresh tensor."""
+        torch, nat = self.torch, self.nat
+        n, T, L = plan.n_genes, plan.total_guides, plan.n_lines
+        f64 = dict(dtype=torch.float64, device=self.device)
+        out = dict(w1=w1_out if w1_out is not None else torch.empty((n, L), **f64), w2=torch.empty((n, L), **f64),
+                   n_iters=torch.empty(n, dtype=torch.int32, device=self.device))
+        if want_x:
+            out['x1'], out['x2'] = torch.empty(T, **f64), torch.empty(T, **f64)
+        if y_tau:
+            out['y'], out['tau'] = torch.empty((T, L), **f64), torch.empty((T, L), **f64)
+        if n == 0:
+            return out
+        io = nat.EmDeviceIO()
+        io.test, io.ctrl, io.ctrl_lines = test.data_ptr(), ctrl.data_ptr(), int(ctrl.shape[1])
+        if fixed_x1 is not None:
+            io.fixed_x1, io.fixed_x2 = fixed_x1.data_ptr(), fixed_x2.data_ptr()
+        for k, v in out.items():
+            setattr(io, k, v.data_ptr())
+        plan.run_device(params, io, torch.cuda.current_stream().cuda_stream)
+        out['_keep'] = (test, ctrl, fixed_x1, fixed_x2)
+        return out
+
+    def kde(self, w1_genes, w1_pseudo, positive):
+        import ctypes as C
+        torch, nat = self.torch, self.nat
+        pv = torch.empty_like(w1_genes)
+        if w1_genes.shape[0] and w1_genes.shape[1]:
+            nat.check(nat.lib().jacks_kde_pvalues_device(self.ctx.h, w1_genes.data_ptr(), w1_genes.shape[0], w1_pseudo.data_ptr(),
+                                                         w1_pseudo.shape[0], w1_genes.shape[1], int(bool(positive)), pv.data_ptr(),
+                                                         C.c_void_p(torch.cuda.current_stream().cuda_stream or None)))
+        return pv
+
+
+class HostEngine(object):
+    """CPU stand-in with the engine interface, built from two callables (the gloo tests pass CPU restatements):
+    em_fn(offsets, rows, test, ctrl, fixed_x1, fixed_x2) -> dict(w1, w2, x1, x2, n_iters) of numpy arrays,
+    kde_fn(w1_genes, w1_pseudo, positive) -> [m, L]."""
+
+    def __init__(self, em_fn, kde_fn):
+        import torch
+        self.torch, self.em_fn, self.kde_fn = torch, em_fn, kde_fn
+        self.device = torch.device('cpu')
+
+    def upload(self, array):
+        return self.torch.from_numpy(np.ascontiguousarray(array))
+
+    def plan(self, key, offsets, rows, n_rows, n_lines):
+        class P(object):
+            pass
+        p = P()
+        p.offsets, p.rows = np.asarray(offsets, dtype=np.int64), np.asarray(rows, dtype=np.int32)
+        p.n_genes, p.total_guides, p.n_lines = len(p.offsets) - 1, int(p.offsets[-1]) if len(p.offsets) else 0, n_lines
+        return p
+
+    def em(self, plan, test, ctrl, params, fixed_x1=None, fixed_x2=None, want_x=True, y_tau=False, w1_out=None):
+        t = self.torch
+        L = plan.n_lines
+        if plan.n_genes == 0:
+            return dict(w1=t.zeros((0, L), dtype=t.float64), w2=t.zeros((0, L), dtype=t.float64), x1=t.zeros(0, dtype=t.float64),
+                        x2=t.zeros(0, dtype=t.float64), n_iters=t.zeros(0, dtype=t.int32))
+        r = self.em_fn(plan.offsets, plan.rows, test.numpy(), ctrl.numpy(), None if fixed_x1 is None else fixed_x1.numpy(),
+                       None if fixed_x2 is None else fixed_x2.numpy())
+        out = {k: t.from_numpy(np.ascontiguousarray(r[k])) for k in ('w1', 'w2', 'x1', 'x2', 'n_iters')}
+        if w1_out is not None:
+            w1_out.copy_(out['w1'])
+            out['w1'] = w1_out
+        return out
+
+    def kde(self, w1_genes, w1_pseudo, positive):
+        if w1_genes.shape[0] == 0 or w1_genes.shape[1] == 0:
+            return self.torch.zeros(tuple(w1_genes.shape), dtype=self.torch.float64)
+        return self.torch.from_numpy(np.ascontiguousarray(self.kde_fn(w1_genes.numpy(), w1_pseudo.numpy(), positive)))
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# The sharded screen job
+# ----------------------------------------------------------------------------------------------------------------------
+class ShardedScreen(object):
+    """One screen, sharded over the ranks of ``group``: build once (index split, compact upload, plans), run() many times.
+
+    offsets/rows: CSR index of the real genes; pseudo_offsets/pseudo_rows: of the pseudo-genes (or None: no p-values).
+    testdata [N,L,2]; ctrldata [N,L,2] or [N,1,2].  fixed_x: {'X1','X2'} by row, real genes only (jacks_io.py:425, :430).
+    """
+
+    def __init__(self, offsets, rows, pseudo_offsets, pseudo_rows, testdata, ctrldata, engine=None, group=None, device=None,
+                 fixed_x=None, params=None, positive=False, dst=0, shard=True):
+        import torch
+        self.torch, self.group, self.dst, self.positive = torch, group, dst, bool(positive)
+        self.world, self.rank = _world(group) if shard else (1, 0)      # shard=False: the whole screen on this rank (replicas)
+        if not shard:
+            self.dst = 0
+        dev = _resolve_device(device, group)
+        if engine is None:
+            if dev is None:
+                raise RuntimeError('jacks_b200.dist: no CUDA device for this rank and no engine given (there is no CPU fallback)')
+            engine = NativeEngine(dev)
+        self.engine = engine
+        from . import _native
+        self.params = params if params is not None else (_native.default_params() if isinstance(engine, NativeEngine) else None)
+        offsets = np.asarray(offsets, dtype=np.int64)
+        rows = np.asarray(rows)
+        N, L = int(testdata.shape[0]), int(testdata.shape[1])
+        self.N, self.L = N, L
+        self.n_genes = len(offsets) - 1
+        self.T = int(offsets[-1]) if self.n_genes > 0 else 0
+        self.has_pseudo = pseudo_offsets is not None and len(pseudo_offsets) > 1
+        self.n_pseudo = len(pseudo_offsets) - 1 if self.has_pseudo else 0
+        W, r = self.world, self.rank
+        self.b = shard_bounds(offsets, W)
+        self.bt = offsets[self.b]                                       # guide offsets of the gene blocks
+        lo, hi = int(self.b[r]), int(self.b[r + 1])
+        loffs, lrows = local_index(offsets, rows, lo, hi)
+        if self.has_pseudo:
+            pseudo_offsets = np.asarray(pseudo_offsets, dtype=np.int64)
+            self.bp = shard_bounds(pseudo_offsets, W)
+            plo, phi = int(self.bp[r]), int(self.bp[r + 1])
+            poffs, prows = local_index(pseudo_offsets, pseudo_rows, plo, phi)
+        else:
+            self.bp = np.zeros(W + 1, dtype=np.int64)
+            poffs, prows = np.zeros(1, dtype=np.int64), np.zeros(0, dtype=np.int64)
+        self.lb = line_bounds(L, W)
+        # compact cube: the rows this rank's two blocks reference, nothing else
+        used, both = compact_rows(np.concatenate([np.asarray(lrows, dtype=np.int64), np.asarray(prows, dtype=np.int64)]), N)
+        self.used = used
+        self.h2d_bytes = 0
+        test_c = np.ascontiguousarray(np.asarray(testdata)[used])
+        ctrl_c = np.ascontiguousarray(np.asarray(ctrldata)[used])
+        self.d_test, self.d_ctrl = engine.upload(test_c), engine.upload(ctrl_c)
+        self.h2d_bytes += test_c.nbytes + ctrl_c.nbytes
+        self.d_fx1 = self.d_fx2 = None
+        if fixed_x is not None:
+            fx1 = np.ascontiguousarray(np.asarray(fixed_x['X1'], dtype=np.float64)[used])
+            fx2 = np.ascontiguousarray(np.asarray(fixed_x['X2'], dtype=np.float64)[used])
+            self.d_fx1, self.d_fx2 = engine.upload(fx1), engine.upload(fx2)
+            self.h2d_bytes += fx1.nbytes + fx2.nbytes
+        U = len(used)
+        self.plan_real = engine.plan(None, loffs, both[:len(lrows)], U, L)
+        self.plan_pseudo = engine.plan(None, poffs, both[len(lrows):], U, L) if self.has_pseudo else None
+        self.h2d_bytes += loffs.nbytes + poffs.nbytes + both.nbytes
+
+    # -- collectives -------------------------------------------------------------------------------------------------
+    def _all_to_all(self, send, in_splits, out_splits):
+        import torch.distributed as dist
+        if self.world == 1:
+            return send
+        recv = self.torch.empty(int(sum(out_splits)), dtype=send.dtype, device=send.device)
+        dist.all_to_all_single(recv, send, output_split_sizes=[int(x) for x in out_splits],
+                                   input_split_sizes=[int(x) for x in in_splits], group=self.group)
+        return recv
+
+    def _lines_of_all_genes(self, w1_local, gene_bounds):
+        """[my genes, L] on every rank -> [all genes, my lines] on every rank: ONE all-to-all (step 3)."""
+        t, lb, r = self.torch, self.lb, self.rank
+        n_local = w1_local.shape[0]
+        blocks = [w1_local[:, int(lb[s]):int(lb[s + 1])].reshape(-1) for s in range(self.world)]
+        send = t.cat(blocks) if self.world > 1 else blocks[0].contiguous()
+        in_splits = [n_local * int(lb[s + 1] - lb[s]) for s in range(self.world)]
+        my_l = int(lb[r + 1] - lb[r])
+        out_splits = [int(gene_bounds[s + 1] - gene_bounds[s]) * my_l for s in range(self.world)]
+        recv = self._all_to_all(send, in_splits, out_splits)
+        return recv.view(int(gene_bounds[-1]), my_l)
+
+    def run(self, want_pvals=True):
+        """Steps 2-5.  Returns on rank ``dst`` a dict of device tensors in the caller's gene order -- w1, w2 [n, L];
+        x1, x2 [sum G]; n_iters [n]; pvals [n, L] (if there are pseudo-genes and want_pvals) -- and None elsewhere."""
+        t, eng = self.torch, self.engine
+        W, r, L = self.world, self.rank, self.L
+        do_p = bool(want_pvals and self.has_pseudo and self.n_pseudo >= 2)
+        n_lr, n_lp = int(self.b[r + 1] - self.b[r]), int(self.bp[r + 1] - self.bp[r])
+        pv_block = None
+        if do_p:
+            # one exchange buffer for both: [real | pseudo] E[w] of my genes, written by the kernels themselves
+            both = t.empty((n_lr + n_lp, L), dtype=t.float64, device=eng.device)
+            pseudo = eng.em(self.plan_pseudo, self.d_test, self.d_ctrl, self.params, want_x=False, w1_out=both[n_lr:])
+            real = eng.em(self.plan_real, self.d_test, self.d_ctrl, self.params, self.d_fx1, self.d_fx2, want_x=True, w1_out=both[:n_lr])
+            gb = np.concatenate([[0], np.cumsum([(self.b[s + 1] - self.b[s]) + (self.bp[s + 1] - self.bp[s]) for s in range(W)])])
+            mine = self._lines_of_all_genes(both, gb)                        # [(real_s, pseudo_s) for s in ranks, my lines]
+            parts_r, parts_p, o = [], [], 0
+            for s in range(W):
+                nr, npz = int(self.b[s + 1] - self.b[s]), int(self.bp[s + 1] - self.bp[s])
+                parts_r.append(mine[o:o + nr]); o += nr
+                parts_p.append(mine[o:o + npz]); o += npz
+            g_block = t.cat(parts_r) if W > 1 else parts_r[0]                # [n_genes, my lines], caller order
+            p_block = t.cat(parts_p) if W > 1 else parts_p[0]                # [n_pseudo, my lines], original order
+            pv_block = eng.kde(g_block.contiguous(), p_block.contiguous(), self.positive)
+        else:
+            real = eng.em(self.plan_real, self.d_test, self.d_ctrl, self.params, self.d_fx1, self.d_fx2, want_x=True)
+        if W == 1:
+            res = {k: real[k] for k in ('w1', 'w2', 'x1', 'x2', 'n_iters')}
+            if do_p:
+                res['pvals'] = pv_block
+            self.exchange_bytes = 0
+            return res
+        # gather to dst: per rank [w1 | w2 | x1 | x2 | n_iters as f64 | p-value column block]
+        n_l = int(self.b[r + 1] - self.b[r])
+        t_l = int(self.bt[r + 1] - self.bt[r])
+        pieces = [real['w1'].reshape(-1), real['w2'].reshape(-1), real['x1'], real['x2'], real['n_iters'].to(t.float64)]
+        if do_p:
+            pieces.append(pv_block.reshape(-1))
+        send = t.cat(pieces)
+
+        def length(s):
+            n_s, t_s = int(self.b[s + 1] - self.b[s]), int(self.bt[s + 1] - self.bt[s])
+            return 2 * n_s * L + 2 * t_s + n_s + (self.n_genes * int(self.lb[s + 1] - self.lb[s]) if do_p else 0)
+        in_splits = [send.numel() if s == self.dst else 0 for s in range(W)]
+        out_splits = [length(s) if r == self.dst else 0 for s in range(W)]
+        recv = self._all_to_all(send, in_splits, out_splits)
+        self.exchange_bytes = (both.numel() * 8 * (W - 1) // W if do_p else 0) + (send.numel() * 8 if r != self.dst else 0)
+        if r != self.dst:
+            return None
+        out = {k: [] for k in ('w1', 'w2', 'x1', 'x2', 'n_iters', 'pv')}
+        o = 0
+        for s in range(W):
+            n_s, t_s = int(self.b[s + 1] - self.b[s]), int(self.bt[s + 1] - self.bt[s])
+            l_s = int(self.lb[s + 1] - self.lb[s])
+            for key, size, shape in (('w1', n_s * L, (n_s, L)), ('w2', n_s * L, (n_s, L)), ('x1', t_s, (t_s,)), ('x2', t_s, (t_s,)),
+                                     ('n_iters', n_s, (n_s,))):
+                out[key].append(recv[o:o + size].view(shape)); o += size
+            if do_p:
+                out['pv'].append(recv[o:o + self.n_genes * l_s].view(self.n_genes, l_s)); o += self.n_genes * l_s
+        res = {k: (t.cat(out[k]) if W > 1 else out[k][0]) for k in ('w1', 'w2', 'x1', 'x2')}
+        res['n_iters'] = (t.cat(out['n_iters']) if W > 1 else out['n_iters'][0]).to(t.int32)
+        if do_p:
+            res['pvals'] = t.cat(out['pv'], dim=1) if W > 1 else out['pv'][0]
+        return res
+
+
+def run_screen_sharded(offsets, rows, pseudo_offsets, pseudo_rows, testdata, ctrldata, engine=None, group=None, device=None,
+                       fixed_x=None, params=None, positive=False, dst=0, want_pvals=True):
+    """One-shot form of ShardedScreen: returns numpy arrays on rank ``dst`` (None elsewhere)."""
+    job = ShardedScreen(offsets, rows, pseudo_offsets, pseudo_rows, testdata, ctrldata, engine=engine, group=group, device=device,
+                        fixed_x=fixed_x, params=params, positive=positive, dst=dst)
+    res = job.run(want_pvals=want_pvals)
+    if res is None:
+        return None
+    return {k: v.cpu().numpy() for k, v in res.items()}
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# Earlier, array-level drivers (kept: the paper-script batch modes use infer_sharded with per_line=True)
+# ----------------------------------------------------------------------------------------------------------------------
 def _pack(res, n_local, t_local, L):
     return np.concatenate([res['w1'].reshape(-1), res['w2'].reshape(-1), res['x1'].reshape(-1), res['x2'].reshape(-1),
                            res['n_iters'].astype(np.float64).reshape(-1)]).astype(np.float64), (n_local, t_local, L)
@@ -49,28 +362,37 @@ def _unpack(buf, n_local, t_local, L, per_line=False):
 
 
 def infer_sharded(offsets, rows, testdata, ctrldata, compute=None, group=None, device=None, per_line=False, **em_kwargs):
-    """Batched EM of the whole gene index, sharded by gene over the ranks of ``group`` (default: WORLD).
+    """Batched EM of the whole gene index, sharded by gene over the ranks of ``group`` (default: WORLD), host arrays in,
+    host arrays out on every rank (one all-gather of the packed results).
     per_line: run the per-line ("single JACKS") mode instead of the joint one -- the batch driver of the paper
     scripts (jacks_b200/paper_modes.py); x1, x2 and n_iters then carry a line axis.
 
     ``compute(offsets, rows, testdata, ctrldata, **em_kwargs) -> dict(w1, w2, x1, x2, n_iters)`` runs one shard;
-    by default the GPU path of this rank (jacks_b200.infer.infer_batched on ``device``).  Returns the gathered
-    dict (flat arrays in the caller's gene order) on every rank."""
+    by default the GPU path of this rank.  em_kwargs: n_iter, fixed_x, apply_w_hp and the hyper-parameters of
+    jacks_em_default_params."""
     import torch
     import torch.distributed as dist
-    world = dist.get_world_size(group) if dist.is_initialized() else 1
-    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    world, rank = _world(group)
     offsets = np.asarray(offsets, dtype=np.int64)
     b = shard_bounds(offsets, world)
     lo, hi = int(b[rank]), int(b[rank + 1])
     loffs, lrows = local_index(offsets, rows, lo, hi)
+    dev_index = _resolve_device(device, group)
     if compute is None:
         from . import infer, _native
+        if dev_index is None:
+            raise RuntimeError('jacks_b200.dist: no CUDA device for this rank and no compute given (there is no CPU fallback)')
 
         def compute(o, r, t, c, **kw):
             if per_line:
-                return _native.em_lines_host(_native.context(device or 0), o, r, t, c, want=('x1', 'x2', 'w1', 'w2', 'n_iters'), **kw)
-            return infer.infer_batched(o, r, t, c, want=('x1', 'x2', 'w1', 'w2'), device=device or 0, **kw)
+                fixed = kw.pop('fixed_x', None)
+                kw.pop('apply_w_hp', None)                       # infer.py:92 never applies with one line
+                params = _native.default_params(n_iter=int(kw.pop('n_iter', 50)), **kw)
+                fx1 = None if fixed is None else np.asarray(fixed['X1'], dtype=np.float64)
+                fx2 = None if fixed is None else np.asarray(fixed['X2'], dtype=np.float64)
+                return _native.em_lines_host(_native.context(dev_index), o, r, t, c, params=params, fixed_x1=fx1, fixed_x2=fx2,
+                                             want=('x1', 'x2', 'w1', 'w2', 'n_iters'))
+            return infer.infer_batched(o, r, t, c, want=('x1', 'x2', 'w1', 'w2'), device=dev_index, **kw)
     L = int(np.asarray(testdata).shape[1])
     K = L if per_line else 1
     if hi > lo:
@@ -85,8 +407,7 @@ def infer_sharded(offsets, rows, testdata, ctrldata, compute=None, group=None, d
     length = lambda n, t: 2 * n * L + 2 * t * K + n * K
     cap = max(length(n, t) for n, t in sizes)
     flat, _ = _pack(res, hi - lo, int(loffs[-1]), L)
-    on_gpu = dist.get_backend(group) == 'nccl'
-    dev = torch.device('cuda', device if device is not None else torch.cuda.current_device()) if on_gpu else torch.device('cpu')
+    dev = torch.device('cuda', dev_index) if (dev_index is not None and dist.get_backend(group) == 'nccl') else torch.device('cpu')
     send = torch.zeros(cap, dtype=torch.float64, device=dev)
     send[:flat.size] = torch.from_numpy(flat).to(dev)
     recv = torch.empty(world * cap, dtype=torch.float64, device=dev)
@@ -98,32 +419,29 @@ def infer_sharded(offsets, rows, testdata, ctrldata, compute=None, group=None, d
 
 def pvalues_sharded(w1_genes, w1_pseudo, positive=False, compute=None, group=None, device=None):
     """KDE p-values of every gene against the pseudo-gene null (computeW1PvalsAndFDRs with pseudo=True,
-    jacks_io.py:69-89), sharded by gene over the ranks of ``group``.
-
-    Every rank holds the full ``w1_genes [n, L]`` and ``w1_pseudo [n_pseudo, L]`` (what infer_sharded returns), builds
-    the per-line kernel density of the null itself -- it is a few hundred kilobytes of state, cheaper to rebuild than to
-    ship -- and evaluates a contiguous block of genes; ONE all-gather reassembles ``[n, L]``.  p-values of a gene do not
-    depend on the other genes, so the result is bit-identical to the unsharded call.
+    jacks_io.py:69-89) from HOST arrays every rank already holds, sharded by gene; one all-gather reassembles [n, L].
+    (The screen job above shards this stage by LINE behind an all-to-all instead and never leaves the device.)
     ``compute(w1_block, w1_pseudo, positive) -> [m, L]`` evaluates one block; by default the GPU path of this rank."""
     import torch
     import torch.distributed as dist
-    world = dist.get_world_size(group) if dist.is_initialized() else 1
-    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    world, rank = _world(group)
     w1_genes = np.ascontiguousarray(w1_genes, dtype=np.float64)
     n, L = w1_genes.shape
+    dev_index = _resolve_device(device, group)
     if compute is None:
         from . import _native
+        if dev_index is None:
+            raise RuntimeError('jacks_b200.dist: no CUDA device for this rank and no compute given (there is no CPU fallback)')
 
         def compute(block, pseudo, pos):
-            return _native.kde_pvalues_host(_native.context(device or 0), block, pseudo, positive=pos)
+            return _native.kde_pvalues_host(_native.context(dev_index), block, pseudo, positive=pos)
     b = np.linspace(0, n, world + 1).astype(np.int64)
     lo, hi = int(b[rank]), int(b[rank + 1])
     mine = compute(w1_genes[lo:hi], w1_pseudo, positive) if hi > lo else np.zeros((0, L))
     if world == 1:
         return np.asarray(mine)
     cap = int(np.max(np.diff(b))) * L
-    on_gpu = dist.get_backend(group) == 'nccl'
-    dev = torch.device('cuda', device if device is not None else torch.cuda.current_device()) if on_gpu else torch.device('cpu')
+    dev = torch.device('cuda', dev_index) if (dev_index is not None and dist.get_backend(group) == 'nccl') else torch.device('cpu')
     send = torch.zeros(cap, dtype=torch.float64, device=dev)
     send[:mine.size] = torch.from_numpy(np.ascontiguousarray(mine).reshape(-1)).to(dev)
     recv = torch.empty(world * cap, dtype=torch.float64, device=dev)

@@ -30,6 +30,31 @@ LOG.setLevel(logging.DEBUG)
 _SHAPE_MSG = 'Expecting matched size between control and test data'      # infer.py:26
 
 
+def _planes(a):
+    """The (mean, sd) planes of a data cube: the reference reads planes 0 and 1 only (infer.py:24), so cubes that carry a
+    third, raw plane (writeFoldChanges(write_raw=True), jacks_io.py:153) are accepted."""
+    a = np.asarray(a)
+    if a.ndim == 3 and a.shape[2] > 2:
+        a = a[:, :, :2]
+    return a
+
+
+def _one_control(ctrldata):
+    """A control cube whose columns are ONE column repeated without being materialised -- numpy.broadcast_to of an
+    [N, 1, 2] block, which is what jacks_b200.preprocess.collateTestControlSamples returns when every line has the same
+    control sample -- goes to the GPU as [N, 1, 2]: half the upload, half the reads, identical arithmetic (the matched
+    branch of infer.py:66-70 with equal columns)."""
+    return ctrldata.ndim == 3 and ctrldata.shape[1] > 1 and ctrldata.strides[1] == 0
+
+
+def _rows(rows, n_rows):
+    """numpy's fancy indexing (infer.py:21) wraps negative row numbers; out-of-range ones raise IndexError."""
+    rows = np.asarray(rows, dtype=np.int64)
+    if rows.size and (rows.min() < -n_rows or rows.max() >= n_rows):
+        raise IndexError('index out of bounds for axis 0 with size %d' % n_rows)
+    return np.where(rows < 0, rows + n_rows, rows)
+
+
 def infer_batched(offsets, rows, testdata, ctrldata, fixed_x=None, n_iter=50, apply_w_hp=False,
                   want=('x1', 'x2', 'w1', 'w2', 'y', 'tau'), device=0, params=None, **hyper):
     """Batched EM on flat arrays (the array-level form of inferJACKS).
@@ -44,8 +69,11 @@ def infer_batched(offsets, rows, testdata, ctrldata, fixed_x=None, n_iter=50, ap
     fx1 = fx2 = None
     if fixed_x is not None:
         fx1, fx2 = np.asarray(fixed_x['X1'], dtype=np.float64), np.asarray(fixed_x['X2'], dtype=np.float64)
-    return _native.em_batched_host(ctx, offsets, rows, testdata, ctrldata, params=params, fixed_x1=fx1, fixed_x2=fx2,
-                                   want=tuple(want) + ('n_iters',))
+    testdata, ctrldata = _planes(testdata), _planes(ctrldata)
+    if _one_control(ctrldata):
+        ctrldata = ctrldata[:, :1, :]
+    return _native.em_batched_host(ctx, offsets, _rows(rows, testdata.shape[0]), testdata, ctrldata, params=params, fixed_x1=fx1,
+                                   fixed_x2=fx2, want=tuple(want) + ('n_iters',))
 
 
 def inferJACKS(gene_index, testdata, ctrldata, fixed_x=None, n_iter=50, apply_w_hp=False, w_only=False):
@@ -79,6 +107,46 @@ def inferJACKS(gene_index, testdata, ctrldata, fixed_x=None, n_iter=50, apply_w_
     return results
 
 
+def inferJACKSScreen(gene_index, pseudo_gene_index, testdata, ctrldata, fixed_x=None, n_iter=50, apply_w_hp=False,
+                     positive=False, device=0, full_pseudo=False):
+    """The inference job of load_data_and_run in one GPU call (jacks_run_screen_host): what the reference does with
+
+        jacks_results = inferJACKS(gene_index, testdata, ctrldata, apply_w_hp=..., fixed_x=...)        (jacks_io.py:425)
+        jacks_pseudo_results = inferJACKS(pseudo_gene_index, testdata, ctrldata, apply_w_hp=...)       (jacks_io.py:430)
+        computeW1PvalsAndFDRs(all results, pseudo=True, positive=...)                                  (jacks_io.py:69-89)
+
+    The screen is uploaded once, the pseudo-gene E[w] never leaves the device unless ``full_pseudo`` asks for the
+    pseudo-genes' w1, w2 and p-values (only --fdr needs them: the Benjamini-Hochberg ranks count the pseudo-genes,
+    jacks_io.py:52-61; no pseudo-gene is ever written to a file, jacks_io.py:131).
+    Returns (jacks_results, pvals {gene: [L]}, pseudo) with pseudo = None or (names, w1, w2, pvals)."""
+    testdata, ctrldata = np.asarray(testdata), np.asarray(ctrldata)
+    if testdata.shape != ctrldata.shape:
+        raise Exception(_SHAPE_MSG)
+    names, offsets, rows = _native.as_csr(gene_index)
+    pnames, poffsets, prows = _native.as_csr(pseudo_gene_index)
+    testdata, ctrldata = _planes(testdata), _planes(ctrldata)
+    if _one_control(ctrldata):
+        ctrldata = ctrldata[:, :1, :]
+    N = testdata.shape[0]
+    fx1 = fx2 = None
+    if fixed_x is not None:
+        fx1, fx2 = np.asarray(fixed_x['X1'], dtype=np.float64), np.asarray(fixed_x['X2'], dtype=np.float64)
+    params = _native.default_params(n_iter=int(n_iter), apply_w_hp=int(bool(apply_w_hp)))
+    r = _native.run_screen_host(_native.context(device), offsets, _rows(rows, N), poffsets, _rows(prows, N), testdata, ctrldata,
+                                params=params, fixed_x1=fx1, fixed_x2=fx2, positive=positive,
+                                want=('x1', 'x2', 'w1', 'w2', 'y', 'tau', 'pvals'),
+                                want_pseudo=('w1', 'w2', 'pvals') if full_pseudo else ())
+    results, pvals = {}, {}
+    lo, hi = offsets[:-1].tolist(), offsets[1:].tolist()
+    y, tau, x1, x2, w1, w2, pv = r['y'], r['tau'], r['x1'], r['x2'], r['w1'], r['w2'], r['pvals']
+    for i, gene in enumerate(names):
+        a, b = lo[i], hi[i]
+        results[gene] = (y[a:b], tau[a:b], x1[a:b], x2[a:b], w1[i], w2[i])
+        pvals[gene] = pv[i]
+    pseudo = (pnames, r['pseudo_w1'], r['pseudo_w2'], r['pseudo_pvals']) if full_pseudo else None
+    return results, pvals, pseudo
+
+
 def inferJACKSLines(gene_index, testdata, ctrldata, fixed_x=None, n_iter=50, w_only=False, device=0):
     """Every cell line on its own ("single JACKS"): the result of
 
@@ -100,6 +168,8 @@ def inferJACKSLines(gene_index, testdata, ctrldata, fixed_x=None, n_iter=50, w_o
     if fixed_x is not None:
         fx1, fx2 = np.asarray(fixed_x['X1'], dtype=np.float64), np.asarray(fixed_x['X2'], dtype=np.float64)
     want = ('w1', 'w2', 'n_iters') if w_only else ('x1', 'x2', 'w1', 'w2', 'y', 'tau', 'n_iters')
+    testdata, ctrldata = _planes(testdata), _planes(ctrldata)
+    rows = _rows(rows, testdata.shape[0])
     r = _native.em_lines_host(_native.context(device), offsets, rows, testdata, ctrldata,
                               params=_native.default_params(n_iter=int(n_iter)), fixed_x1=fx1, fixed_x2=fx2, want=want)
     w1, w2 = r['w1'], r['w2']

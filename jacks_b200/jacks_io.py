@@ -16,7 +16,7 @@ import random
 import numpy as np
 
 from . import _native
-from .infer import LOG, inferJACKS
+from .infer import LOG, inferJACKS, inferJACKSScreen
 from .preprocess import loadDataAndPreprocess, collateTestControlSamples
 
 REP_HDR_DEFAULT = "Replicate"
@@ -110,13 +110,16 @@ def computeW1PvalsAndFDRs(jacks_results, test_sample_ids, noness_genes=set(), ps
 
 
 def writeJacksWResults(outprefix, jacks_results, cell_lines, write_types=[''], ctrl_geneset=set(), fdr=None,
-                       fdr_thresh_type='REGULAR', pseudo=False, positive=False):
+                       fdr_thresh_type='REGULAR', pseudo=False, positive=False, w1_pvals=None):
     """Gene-level result tables, one file per write type ('' = E[w], '_std', '_pval', '_fdr'), genes ranked by
-    mean w1, values formatted '%5e' (jacks_io.py:91-133)."""
+    mean w1, values formatted '%5e' (jacks_io.py:91-133).  w1_pvals: p-values already computed on the GPU by the screen
+    job (load_data_and_run); otherwise computeW1PvalsAndFDRs is called here, as in the reference."""
     ordered_genes = getSortedGenes(jacks_results, positive)
     # the files are opened first, as in the reference, so that a failing p-value step leaves the same (empty) files
     fouts = [io.open(outprefix + '_gene%s_JACKS_results.txt' % write_type, 'w') for write_type in write_types]
-    if '_fdr' in write_types or '_pval' in write_types:
+    if w1_pvals is not None and '_fdr' not in write_types:
+        jacks_w1_pvals, jacks_w1_fdrs = w1_pvals, None
+    elif '_fdr' in write_types or '_pval' in write_types:
         LOG.info('Computing P-values for %s selection' % ('positive' if positive else 'negative'))
         jacks_w1_pvals, jacks_w1_fdrs = computeW1PvalsAndFDRs(jacks_results, cell_lines, noness_genes=ctrl_geneset,
                                                               pseudo=pseudo, compute_fdr=('_fdr' in write_types),
@@ -279,7 +282,9 @@ def createGeneSpec(guidemappingfile, sgrna_hdr, gene_hdr, ignore_blank_genes=Tru
                 line = g.readline()
         pairs, _, _ = _native.table_read(guidemappingfile, delim, [], skip_lines=skip + 1,
                                          str_cols=(fieldnames.index(sgrna_hdr), fieldnames.index(gene_hdr)))
-        if all(a is not None and b is not None and '"' not in a and '"' not in b for a, b in pairs[:1000]):
+        # raw field bytes come back: a quoted field anywhere (csv would unescape it) or a short record sends the whole
+        # file through csv.DictReader instead
+        if all(a is not None and b is not None and '"' not in a and '"' not in b for a, b in pairs):
             return {a: b for a, b in pairs if (not ignore_blank_genes or b != '')}
     f, delim = prepareFile(guidemappingfile, sgrna_hdr)
     rdr = csv.DictReader(f, delimiter=delim)
@@ -422,23 +427,41 @@ def load_data_and_run(sample_spec, gene_spec, ctrl_spec, sgrna_reference_file, x
         writeFoldChanges(outfile_lfc_std, testdata, ctrldata, meta, sample_ids_without_ctrl, write_std=True)
 
     LOG.info('Running JACKS inference')
-    jacks_results = inferJACKS(gene_index, testdata, ctrldata, apply_w_hp=apply_w_hp, fixed_x=x_reference)
-
-    if n_pseudo > 0 and len(ctrl_geneset) > 0:
-        LOG.info('Running JACKS inference on %d pseudogenes' % n_pseudo)
+    with_pseudo = n_pseudo > 0 and len(ctrl_geneset) > 0
+    if with_pseudo and n_pseudo >= 2:
+        # The reference's two inferJACKS calls (jacks_io.py:425, :430) and its p-value pass (:69-89) as ONE job on the GPU:
+        # the screen goes up once, the pseudo-gene E[w] feeds the null densities on the device.  The pseudo-genes are
+        # drawn first -- the same draws: inference does not touch the random stream.
         pseudo_gene_index = createPseudoNonessGenes(gene_index, ctrl_geneset, n_pseudo)
-        jacks_pseudo_results = inferJACKS(pseudo_gene_index, testdata, ctrldata, apply_w_hp=apply_w_hp)
-        writeJacksWResults(outprefix + '_pseudo_noness', jacks_pseudo_results, sample_ids_without_ctrl,
-                           write_types=['', '_std'], positive=positive)
-        for gene in jacks_results:
-            jacks_pseudo_results[gene] = jacks_results[gene]
+        LOG.info('Running JACKS inference on %d pseudogenes' % n_pseudo)
+        jacks_results, w1_pvals, pseudo = inferJACKSScreen(gene_index, pseudo_gene_index, testdata, ctrldata, fixed_x=x_reference,
+                                                           apply_w_hp=apply_w_hp, positive=positive, full_pseudo=(fdr is not None))
+        # no pseudo-gene is ever written (jacks_io.py:131): the reference's '_pseudo_noness' files hold the header only
+        writeJacksWResults(outprefix + '_pseudo_noness', {}, sample_ids_without_ctrl, write_types=['', '_std'], positive=positive)
+        jacks_pseudo_results = dict(jacks_results)
+        if pseudo is not None:               # --fdr: the Benjamini-Hochberg ranks count the pseudo-genes (jacks_io.py:52-61)
+            pnames, pw1, pw2, ppv = pseudo
+            for i, gene in enumerate(pnames):
+                jacks_pseudo_results[gene] = (None, None, None, None, pw1[i], pw2[i])
+                w1_pvals[gene] = ppv[i]
+    else:
+        jacks_results = inferJACKS(gene_index, testdata, ctrldata, apply_w_hp=apply_w_hp, fixed_x=x_reference)
+        w1_pvals = None
+        if with_pseudo:
+            LOG.info('Running JACKS inference on %d pseudogenes' % n_pseudo)
+            pseudo_gene_index = createPseudoNonessGenes(gene_index, ctrl_geneset, n_pseudo)
+            jacks_pseudo_results = inferJACKS(pseudo_gene_index, testdata, ctrldata, apply_w_hp=apply_w_hp)
+            writeJacksWResults(outprefix + '_pseudo_noness', jacks_pseudo_results, sample_ids_without_ctrl,
+                               write_types=['', '_std'], positive=positive)
+            for gene in jacks_results:
+                jacks_pseudo_results[gene] = jacks_results[gene]
 
     LOG.info('Writing JACKS results')
-    if len(ctrl_geneset) > 0 and n_pseudo > 0:
+    if with_pseudo:
         writeJacksWResults(outprefix, jacks_pseudo_results, sample_ids_without_ctrl,
                            ctrl_geneset=set(x for x in jacks_pseudo_results if 'JACKS_PSEUDO_GENE' in x),
                            write_types=['', '_std', '_pval'], fdr=fdr, pseudo=True, fdr_thresh_type=fdr_thresh_type,
-                           positive=positive)
+                           positive=positive, w1_pvals=w1_pvals)
     else:
         writeJacksWResults(outprefix, jacks_results, sample_ids_without_ctrl, ctrl_geneset=ctrl_geneset,
                            write_types=['', '_std'], positive=positive)

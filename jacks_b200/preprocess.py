@@ -59,16 +59,24 @@ def compute_extras(meta, sample_ids):
 def normalizeLogCounts(logcounts, normtype='median', ctrl_guide_indexes=[]):
     """Per-column normalisation of log counts (preprocess.py:76-96).  Returns the normalised array."""
     LOG.info('Applying %s normalisation' % normtype)
+    caller = logcounts
     logcounts = np.asarray(logcounts, dtype=np.float64)
     if normtype in ('median', 'zmad', 'mode'):
-        return _native.normalize_host(_native.context(0), logcounts, normtype)
-    if normtype == 'ctrl_guides':
+        out = _native.normalize_host(_native.context(0), logcounts, normtype)
+    elif normtype == 'ctrl_guides':
         if len(ctrl_guide_indexes) == 0:
             raise Exception('No guides specified for ctrl guide normalization')
         mask = np.zeros(logcounts.shape[0], dtype=np.uint8)
         mask[list(ctrl_guide_indexes)] = 1
-        return _native.normalize_host(_native.context(0), logcounts, 'ctrl_guides', row_mask=mask)
-    raise Exception('Unrecognised normalisation type %s' % normtype)
+        out = _native.normalize_host(_native.context(0), logcounts, 'ctrl_guides', row_mask=mask)
+    else:
+        raise Exception('Unrecognised normalisation type %s' % normtype)
+    # the reference normalises IN PLACE for median, mode and ctrl_guides (logcounts -= ..., preprocess.py:81,91,94) and
+    # returns the same object; zmad rebinds a new array (preprocess.py:84).  Keep that observable behaviour.
+    if normtype != 'zmad' and isinstance(caller, np.ndarray) and caller.dtype == np.float64 and caller.flags.writeable:
+        caller[...] = out
+        return caller
+    return out
 
 
 def inferMissingVariances(data, meta, sample_ids, ctrl_spec, ctrl_geneset):
@@ -96,7 +104,13 @@ def collateTestControlSamples(data, sample_ids, ctrl_spec):
     test_sample_idxs = [i for i, x in enumerate(sample_ids) if ctrl_spec[x] != x]
     LOG.info('Collating %d samples' % len(test_sample_idxs))
     testdata = data[:, test_sample_idxs, :]
-    ctrldata = data[:, [sample_ids.index(ctrl_spec[sample_ids[idx]]) for idx in test_sample_idxs], :]
+    ctrl_idxs = [sample_ids.index(ctrl_spec[sample_ids[idx]]) for idx in test_sample_idxs]
+    if len(ctrl_idxs) > 1 and len(set(ctrl_idxs)) == 1:
+        # one control sample for every line (--common_ctrl_sample): the same [N, L, 2] values as the reference's copy,
+        # as a read-only broadcast view of the one column -- inferJACKS sends such a cube to the GPU as [N, 1, 2]
+        ctrldata = np.broadcast_to(data[:, ctrl_idxs[:1], :], testdata.shape)
+    else:
+        ctrldata = data[:, ctrl_idxs, :]
     return testdata, ctrldata, test_sample_idxs
 
 
@@ -139,6 +153,8 @@ def _read_counts_native(filename, delim, colnames, gene_spec):
     except ValueError:
         return None, None                             # let DictReader raise the reference's KeyError
     labels, values, not_numeric = _native.table_read(filename, delim, sel, skip_lines=1)
+    if any(g is None or '"' in g for g in labels):
+        return None, None                             # quoted guide ids: csv unescapes them, the raw field bytes do not
     keep = np.fromiter((g in gene_spec for g in labels), dtype=bool, count=len(labels))
     if not_numeric[keep].any():
         return None, None

@@ -1,5 +1,6 @@
-"""N > 1 path on CPU: two gloo ranks shard the gene index, each computes its block with the C oracle standing in
-for the GPU kernels, one all-gather reassembles -- the result must equal the unsharded run bit for bit."""
+"""N > 1 path on CPU: gloo ranks shard the gene index, each computes its block with the C oracle standing in for the GPU
+kernels -- the result must equal the unsharded run bit for bit.  Covers the screen job (row-slice compact cubes, all-to-all
+to line blocks, line-sharded p-values, gather to one rank: jacks_b200.dist.ShardedScreen) and the array-level drivers."""
 import os
 import socket
 
@@ -13,6 +14,50 @@ def _free_port():
     p = s.getsockname()[1]
     s.close()
     return p
+
+
+def _screen_job(rank, world):
+    """The whole screen job sharded (real + pseudo EM, all-to-all, line-sharded KDE, gather) against the unsharded oracle
+    calls: ragged genes, a NaN measurement, fewer lines than ranks * 2, matched and one-column control, fixed x."""
+    from jacks_b200 import dist as jd, synth, _native
+    from oracle import c_oracle, jacks_oracle as O
+    counts = np.array([4, 1, 7, 4, 4, 2, 9, 4, 3, 4, 4, 5, 4, 4, 4, 6, 4], dtype=np.int64)
+    gi, test, ctrl, ctrl_genes = synth.make_condensed_screen(n_genes=len(counts), n_lines=5, seed=3, guide_counts=counts, n_ctrl_genes=4)
+    test[6, 2, 0] = np.nan
+    names, offs, rows = _native.as_csr(gi)
+    pos = {g: i for i, g in enumerate(names)}
+    poffs, prows = synth.make_pseudo_index_csr(offs, [pos[g] for g in ctrl_genes], 41, seed=11)
+
+    def em_fn(o, r, t, c, fx1, fx2):
+        return c_oracle.em_batched(o, r, t, c, fixed_x1=fx1, fixed_x2=fx2, want_y_tau=False)
+
+    def kde_fn(g, p, positive):
+        return O.kde_pvalues(g, p, positive=positive)
+    ok = True
+    rng = np.random.default_rng(1)
+    fixed = {'X1': rng.normal(1.0, 0.2, size=test.shape[0]), 'X2': rng.normal(1.1, 0.1, size=test.shape[0]) ** 2 + 1.0}
+    for c, fx, positive in ((ctrl, None, False), (np.ascontiguousarray(ctrl[:, :1, :]), None, True), (ctrl, fixed, False)):
+        eng = jd.HostEngine(em_fn, kde_fn)
+        job = jd.ShardedScreen(offs, rows, poffs, prows, test, c, engine=eng, fixed_x=fx, positive=positive)
+        assert len(job.used) <= test.shape[0]
+        res = job.run()
+        # another run on the same resident shard (benchmark / bootstrap pattern) gives the same answer
+        res2 = job.run()
+        if rank == 0:
+            ref = em_fn(offs, rows, test, c, None if fx is None else fx['X1'], None if fx is None else fx['X2'])
+            refp = em_fn(poffs, prows, test, c, None, None)
+            pv = kde_fn(ref['w1'], refp['w1'], positive)
+            for k in ('w1', 'w2', 'x1', 'x2', 'n_iters'):
+                ok = ok and np.array_equal(res[k].numpy(), ref[k], equal_nan=True) and np.array_equal(res2[k].numpy(), ref[k], equal_nan=True)
+            ok = ok and np.array_equal(res['pvals'].numpy(), pv, equal_nan=True)
+        else:
+            ok = ok and res is None
+    # no pseudo-genes: EM + gather only
+    r0 = jd.run_screen_sharded(offs, rows, None, None, test, ctrl, engine=jd.HostEngine(em_fn, kde_fn))
+    if rank == 0:
+        ref = em_fn(offs, rows, test, ctrl, None, None)
+        ok = ok and 'pvals' not in r0 and np.array_equal(r0['w1'], ref['w1'], equal_nan=True) and np.array_equal(r0['x2'], ref['x2'], equal_nan=True)
+    return ok
 
 
 def _worker(rank, world, port, q):
@@ -50,6 +95,7 @@ def _worker(rank, world, port, q):
         wg[4, 1] = np.nan
         pv = jd.pvalues_sharded(wg, wp, positive=False, compute=lambda blk, ps, pos: O.kde_pvalues(blk, ps, positive=pos))
         ok = ok and np.array_equal(pv, O.kde_pvalues(wg, wp), equal_nan=True)
+        ok = ok and _screen_job(rank, world)
         q.put((rank, bool(ok), jd.shard_bounds(offs, world).tolist()))
     finally:
         dist.destroy_process_group()
