@@ -217,6 +217,7 @@ void jacks_ctx_destroy(JacksCtx* c) {
     c->res_test.release(); c->res_ctrl.release(); c->res_fx.release();
     for (auto& b : c->out) b.release();
     c->tmp.release();
+    c->kde_tail.release();
     c->stager.release();
     if (c->cmp_stage) cudaFreeHost(c->cmp_stage);
     if (c->cmp_ready) cudaEventDestroy(c->cmp_ready);

@@ -69,12 +69,13 @@ struct JacksCtx {
     bool res_valid = false;
     jacks::DevBuf out[8];       // device-side outputs of the host entry points
     jacks::DevBuf tmp;          // scratch of the p-value / preprocessing entry points
+    jacks::DevBuf kde_tail;     // queue of far-lower-tail evaluation points of the p-value kernels
     // compact cubes of JACKS_UPLOAD_USED_ROWS calls: pinned staging, device copy, "upload enqueued" event
     void* cmp_stage = nullptr; size_t cmp_stage_cap = 0;
     jacks::DevBuf cmp_dev, cmp_rows;
     cudaEvent_t cmp_ready = nullptr;     // the compact upload has read its pinned staging
     cudaEvent_t cmp_done = nullptr;      // the kernels of the last compact run have read the device cube
-    bool kde_attr_set = false;  // kde_pvalues_fast's shared-memory attribute has been set on this device
+    bool kde_attr_set = false;  // the KDE's derivative table and kernel attributes have been set up on this device
     HostStager stager;          // pinned ring of the synchronous host entry points (pageable caller buffers)
     std::vector<PlanBufs*> plan_pool;          // recycled plan buffers
     std::vector<JacksEmPlan*> pending_plans;   // plans of asynchronous host calls, destroyed at the next synchronise
@@ -129,7 +130,7 @@ bool host_pointer_is_pinned(const void* p);
 // ------------------------------------------------------------------------------------------------
 namespace jacks {
 struct KdeNull {
-    double* sT; double* stats; long long* cell_off; double* cells;     // views into JacksCtx::tmp
+    double* sT; double* srt; double* stats; int* cell_first; double* loc;     // views into JacksCtx::tmp
     long long ld; int n_lines; int positive; int brute;
 };
 int kde_null_prepare(JacksCtx* ctx, const double* w1_pseudo, int64_t n_pseudo, int32_t n_lines, int32_t positive,

@@ -104,10 +104,10 @@ __global__ void __launch_bounds__(kStatsThreads) kde_line_stats(const double* __
 __global__ void __launch_bounds__(kPvThreads) kde_pvalues(const double* __restrict__ w1_genes, long long n_genes, int L,
                                                           const double* __restrict__ sT, long long ld,
                                                           const double* __restrict__ stats, int positive,
-                                                          const long long* __restrict__ cell_off, double* __restrict__ pvals) {
+                                                          int skip_fast, double* __restrict__ pvals) {
     __shared__ double chunk[kChunk];
     const int l = blockIdx.y;
-    if (cell_off && cell_off[l + 1] > cell_off[l]) return;        // this line was done by the fast path
+    if (skip_fast && stats[l * 8 + 7] > 0.0) return;              // this line was done by the fast path
     const double h = stats[l * 8 + 0];
     const int n = (int)stats[l * 8 + 1];
     const double cterm = stats[l * 8 + 2];
@@ -145,192 +145,453 @@ __global__ void __launch_bounds__(kPvThreads) kde_pvalues(const double* __restri
     }
 }
 
-// ---- fast path: sorted null values, cells of width h/4, truncated Taylor (Hermite) expansion per cell -------
-// F(w) = sum_i Phi((w - s_i)/h).  Sort the null values of a line; cut the axis into cells of width delta = h/4
-// with centres c_j; a point of cell j is s_i = c_j + h*u_i, |u_i| <= 1/8.  With z = (w - c_j)/h
-//     sum_{i in j} Phi(z - u_i) = m_0 Phi(z) - phi(z) * sum_{k=1..K} He_{k-1}(z) M_k,    M_k = sum_i u_i^k / k!
-// (Taylor in u; Phi^(k) = (-1)^(k-1) He_{k-1} phi).  Cells whose points all have z >= 8.3 contribute their count
-// (Phi = 1 in double), cells below z_lo = -sqrt(min(z_max,0)^2 + 2 ln(1e16 n)) cannot change the sum at 1e-16
-// relative, and when even the nearest point has z_max < -7.5 the few contributing points are summed directly.
-// K = 16 keeps the truncation below 1e-14 relative for every |z| in the window (numpy prototype: 5e-15 worst case
-// over bulk, tails and edges at n = 2e3 and 1e5).  Work per p-value drops from n normal CDFs to ~45 cells.
-constexpr int kK = 16;                  // expansion order
-constexpr int kCellRec = kK + 2;        // doubles per cell: M_0..M_K, index of the cell's first point
-constexpr double kCellWidth = 0.25;     // in units of h
-constexpr int kSortTileD = 4096;
+// ---- fast path: local expansions (a one-dimensional fast Gauss transform for the normal CDF) ------------------------
+// F(w) = sum_i Phi((w - s_i)/h).  The axis is cut into cells of width h/4 from the smallest null value; cell c has its
+// centre at zc(c) = (c + 1/2)/4 (in units of h from smin), a source point of it is s_i = smin + h (zc(c) + u_i), |u| <= 1/8,
+// and an evaluation point in target cell j (any integer) is w = smin + h (zc(j) + t), |t| <= 1/8.  Then
+//     (w - s_i)/h = (j - c)/4 + (t - u_i)                 and, Taylor in (t - u) around Z = (j - c)/4,
+//     F(w) = sum_m t^m A_m(j),
+//     A_m(j) = [m = 0] #{points in cells c <= j - KSAT - 1}
+//              + (1/m!) sum_{k = -KNEG..KSAT} sum_{q = 0..Q} (-1)^q D_{m+q}(k/4) M_q(j - k),
+//     M_q(c) = sum_{i in c} u_i^q / q!        D_0 = Phi,  D_n(Z) = (-1)^(n-1) He_{n-1}(Z) phi(Z).
+// Source cells further than 8.5 bandwidths below the target contribute their count (every other term of the series is
+// below 1e-16), cells more than 12 bandwidths above it cannot change the sum at 1e-16 relative, and a target more than
+// 5 bandwidths below every null value sums its nearest points directly (F is then tiny and its relative accuracy rests
+// on those few terms).  With P = Q = 12 the truncation is <= 6e-15 relative over bulk, edges and tails
+// (tools/kde_fgt_prototype.py).  Per p-value this is one degree-12 polynomial; per line the table costs a convolution of
+// ~80 source cells per target cell.  Preparing the null needs no sort: ONE stable counting-sort pass by cell index
+// puts each cell's points next to each other in their original order, so every sum below runs in a fixed order and the
+// p-values are bit-reproducible, independent of which genes are evaluated and of how the lines are sharded.
+constexpr int kP = 12;                   // orders of the source moments and of the local series
+constexpr int kNM = kP + 1;              // coefficients per cell
+constexpr double kCellWidth = 0.25;      // in units of h
+constexpr int kKsat = 34;                // (j - c)/4 >= 8.5: the cell counts fully
+constexpr int kKneg = 48;                // (j - c)/4 <= -12: negligible
+constexpr int kJmin = -20;               // targets below smin - 5 h: direct sum
+constexpr int kMaxCells = 2048;          // source cells per line; a line that needs more falls back to the O(n) sums
+constexpr int kMaxTargets = kMaxCells + kKsat - kJmin;
+constexpr int kPartChunk = 4096;         // null values per CTA of the partition pass
+constexpr int kPartThreads = 256;
+constexpr int kNK = kKneg + kKsat + 1;
 
-__global__ void __launch_bounds__(1024) sort_rows_local(double* __restrict__ rows, long long ld, int k_lo, int k_hi) {
-    __shared__ double sm[kSortTileD];
-    const long long base = (long long)blockIdx.y * ld + (long long)blockIdx.x * kSortTileD;
-    for (int t = threadIdx.x; t < kSortTileD; t += blockDim.x) sm[t] = rows[base + t];
+// D_n(k/4), n = 0..2P, k = -KNEG..KSAT: filled once per context by kde_deriv_table (device arithmetic, so every rank
+// of a sharded run holds identical bits).
+__constant__ double c_dtab[kNK * (2 * kP + 1)];
+
+__global__ void kde_deriv_table(double* __restrict__ tab) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= kNK) return;
+    const double Z = (double)(k - kKneg) * kCellWidth;
+    double* row = tab + k * (2 * kP + 1);
+    row[0] = normcdf(Z);
+    const double phi = exp(-0.5 * Z * Z) * 0.3989422804014327;
+    double he_prev = 0.0, he = 1.0;                           // He_{-1}, He_0
+    for (int n = 1; n <= 2 * kP; ++n) {
+        row[n] = ((n & 1) ? 1.0 : -1.0) * he * phi;           // (-1)^(n-1) He_{n-1} phi
+        const double nxt = Z * he - (double)(n - 1) * he_prev;
+        he_prev = he; he = nxt;
+    }
+}
+
+// Transpose [n_pseudo, L] -> rows sT[l][.] (mirrored for positive selection), coalesced both ways; counts the NaNs of
+// every line.  (The first version read the matrix with stride L per thread: 0.9 ms of uncoalesced loads.)
+__global__ void __launch_bounds__(256) kde_transpose(const double* __restrict__ w1_pseudo, long long n_pseudo, int L, long long ld,
+                                                     int positive, double* __restrict__ sT, int* __restrict__ nan_count) {
+    __shared__ double tile[32][33];
+    __shared__ int s_nan[32];
+    const long long i0 = (long long)blockIdx.x * 32;
+    const int l0 = blockIdx.y * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const double sgn = positive ? -1.0 : 1.0;
+    if (threadIdx.x < 32) s_nan[threadIdx.x] = 0;
     __syncthreads();
-    const long long tile0 = (long long)blockIdx.x * kSortTileD;
-    for (long long kk = k_lo; kk <= k_hi; kk <<= 1) {
-        for (int j = (int)((kk >> 1) < kSortTileD ? (kk >> 1) : (kSortTileD >> 1)); j > 0; j >>= 1) {
-            for (int t = threadIdx.x; t < kSortTileD / 2; t += blockDim.x) {
-                const int a = ((t & ~(j - 1)) << 1) | (t & (j - 1));
-                const int b = a | j;
-                const bool up = (((tile0 + a) & kk) == 0);
-                const double va = sm[a], vb = sm[b];
-                if ((vb < va) == up) { sm[a] = vb; sm[b] = va; }
-            }
+    for (int r = ty; r < 32; r += 8) {
+        const long long i = i0 + r;
+        const int l = l0 + tx;
+        double v = __longlong_as_double(0x7ff8000000000000LL);
+        if (i < n_pseudo && l < L) v = sgn * w1_pseudo[i * L + l];
+        tile[r][tx] = v;
+    }
+    __syncthreads();
+    for (int r = ty; r < 32; r += 8) {
+        const int l = l0 + r;
+        const long long i = i0 + tx;
+        if (l < L && i < n_pseudo) {
+            const double v = tile[tx][r];
+            sT[(long long)l * ld + i] = v;
+            if (v != v) atomicAdd(&s_nan[r], 1);
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x < 32 && s_nan[threadIdx.x] && l0 + (int)threadIdx.x < L) atomicAdd(&nan_count[l0 + threadIdx.x], s_nan[threadIdx.x]);
+}
+
+__device__ __forceinline__ double block_min(double v, double* sh) {
+    for (int o = 16; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(0xffffffffu, v, o));
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    __syncthreads();
+    if (lane == 0) sh[warp] = v;
+    __syncthreads();
+    double s = sh[0];
+    for (int w = 1; w < (int)(blockDim.x >> 5); ++w) s = fmin(s, sh[w]);
+    return s;
+}
+
+// One CTA per line on its transposed row: drops NaNs in place (order preserving; rare), then mean, bandwidth, the
+// gene-independent term, range and cell count.  Every sum runs over the row in a fixed order.
+// stats[l*8 + 0] = h, +1 = n, +2 = gene-independent term, +3 = 1/n, +4 = mean, +5 = sum of squared deviations,
+//                +6 = smallest null value, +7 = number of cells (0: the line is evaluated by the O(n) kernel)
+constexpr int kRowThreads = 1024;
+__global__ void __launch_bounds__(kRowThreads) kde_row_stats(double* __restrict__ sT, long long n_pseudo, long long ld,
+                                                             const int* __restrict__ nan_count, double* __restrict__ stats) {
+    constexpr int kStatsThreads = kRowThreads;           // (shadows the width of the older kde_line_stats kernel)
+    __shared__ double sh[kStatsThreads / 32];
+    __shared__ int s_base;
+    __shared__ int s_cnt[kStatsThreads / 32];
+    const int l = blockIdx.x;
+    double* row = sT + (long long)l * ld;
+    int n = (int)n_pseudo;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (nan_count[l] > 0) {
+        if (threadIdx.x == 0) s_base = 0;
+        __syncthreads();
+        for (long long i0 = 0; i0 < n_pseudo; i0 += kStatsThreads) {
+            const long long i = i0 + threadIdx.x;
+            double v = 0.0;
+            bool ok = false;
+            if (i < n_pseudo) { v = row[i]; ok = (v == v); }                 // jacks_io.py:78 drops NaN
+            const unsigned m = __ballot_sync(0xffffffffu, ok);
+            if (lane == 0) s_cnt[warp] = __popc(m);
+            __syncthreads();
+            int wbase = s_base, total = 0;
+            for (int w = 0; w < kStatsThreads / 32; ++w) { const int c = s_cnt[w]; if (w < warp) wbase += c; total += c; }
+            if (ok) row[wbase + __popc(m & ((1u << lane) - 1))] = v;          // destination <= source: in place is safe
+            __syncthreads();
+            if (threadIdx.x == 0) s_base += total;
             __syncthreads();
         }
+        n = s_base;
     }
-    for (int t = threadIdx.x; t < kSortTileD; t += blockDim.x) rows[base + t] = sm[t];
-}
-
-__global__ void __launch_bounds__(256) sort_rows_global(double* __restrict__ rows, long long ld, long long kk, long long j) {
-    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= ld / 2) return;
-    double* r = rows + (long long)blockIdx.y * ld;
-    const long long a = ((t & ~(j - 1)) << 1) | (t & (j - 1));
-    const long long b = a | j;
-    const bool up = ((a & kk) == 0);
-    const double va = r[a], vb = r[b];
-    if ((vb < va) == up) { r[a] = vb; r[b] = va; }
-}
-
-// cell_off[l] .. cell_off[l+1]: cells of line l in the cell table; a line whose cells do not fit is marked
-// (cell_off[l+1] == cell_off[l]) and evaluated by the brute-force kernel.  One thread, L is small.
-__global__ void kde_cell_layout(const double* __restrict__ sT, long long ld, const double* __restrict__ stats, int L,
-                                long long cell_cap, long long* __restrict__ cell_off) {
-    if (blockIdx.x != 0 || threadIdx.x != 0) return;
-    long long off = 0;
-    cell_off[0] = 0;
-    for (int l = 0; l < L; ++l) {
-        const double h = stats[l * 8 + 0];
-        const int n = (int)stats[l * 8 + 1];
-        long long nc = 0;
+    for (long long i = n + threadIdx.x; i < ld; i += kStatsThreads) row[i] = __longlong_as_double(0x7ff0000000000000LL);
+    __syncthreads();
+    double sum = 0.0, lo = __longlong_as_double(0x7ff0000000000000LL), hi = -lo;
+    for (int i = threadIdx.x; i < n; i += kStatsThreads) { const double v = row[i]; sum += v; lo = fmin(lo, v); hi = fmax(hi, v); }
+    const double mean = block_sum(sum, sh) / (double)n;
+    const double smin = block_min(lo, sh);
+    const double smax = -block_min(-hi, sh);
+    double ss = 0.0;
+    for (int i = threadIdx.x; i < n; i += kStatsThreads) { const double d = row[i] - mean; ss += d * d; }
+    ss = block_sum(ss, sh);
+    // cov with aweights = 1/n: sum(w d^2) / (1 - sum(w^2)) = (ss/n) / (1 - 1/n); neff = n
+    const double wgt = 1.0 / (double)n;
+    const double cov = (ss * wgt) / (1.0 - wgt);
+    const double factor = pow((double)n, -0.2);
+    const double h = sqrt(cov * factor * factor);
+    // gene-independent term sum_i Phi((-100 - s_i)/h): every s_i >= smin, so when even the smallest null value puts
+    // -100 more than 38.6 bandwidths away every term is exactly 0 in double (the usual case by a factor of thousands)
+    double c = 0.0;
+    if (!((-100.0 - smin) / h < -38.6)) {
+        for (int i = threadIdx.x; i < n; i += kStatsThreads) c += normcdf((-100.0 - row[i]) / h);
+        c = block_sum(c, sh);
+    }
+    if (threadIdx.x == 0) {
+        double nc = 0.0;
         if (n >= 2 && h > 0.0 && h == h) {
-            const double* row = sT + (long long)l * ld;
-            const double span = (row[n - 1] - row[0]) / (h * kCellWidth);
-            if (span == span && span < 1.0e7) nc = (long long)floor(span) + 1;
+            const double span = (smax - smin) / (h * kCellWidth);
+            if (span == span && span < (double)(kMaxCells - 1)) nc = floor(span) + 1.0;
         }
-        if (nc > 0 && off + nc <= cell_cap) off += nc;        // else: no cells -> brute force for this line
-        cell_off[l + 1] = off;
+        stats[l * 8 + 0] = h;
+        stats[l * 8 + 1] = (double)n;
+        stats[l * 8 + 2] = c;
+        stats[l * 8 + 3] = wgt;
+        stats[l * 8 + 4] = mean;
+        stats[l * 8 + 5] = ss;
+        stats[l * 8 + 6] = smin;
+        stats[l * 8 + 7] = nc;
     }
 }
 
-__device__ __forceinline__ long long kde_cell_of(double s, double smin, double inv_delta, long long nc) {
-    long long j = (long long)floor((s - smin) * inv_delta);
+__device__ __forceinline__ int kde_cell_of(double s, double smin, double inv_delta, int nc) {
+    const int j = (int)floor((s - smin) * inv_delta);
     return j < 0 ? 0 : (j >= nc ? nc - 1 : j);
 }
 
-// One thread per cell: moments of the cell's points (sorted row => the points are a contiguous run).
-__global__ void __launch_bounds__(128) kde_cell_moments(const double* __restrict__ sT, long long ld,
-                                                        const double* __restrict__ stats, int L,
-                                                        const long long* __restrict__ cell_off, double* __restrict__ cells) {
-    const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= cell_off[L]) return;
-    int lo_l = 0, hi_l = L;                       // line of this cell: cell_off[l] <= c < cell_off[l+1]
-    while (hi_l - lo_l > 1) { const int mid = (lo_l + hi_l) >> 1; if (cell_off[mid] <= c) lo_l = mid; else hi_l = mid; }
-    const int l = lo_l;
-    const long long j = c - cell_off[l], nc = cell_off[l + 1] - cell_off[l];
-    const double h = stats[l * 8 + 0];
+// Partition pass 1: per (line, chunk) histogram of the cell indices.
+__global__ void __launch_bounds__(kPartThreads) kde_cell_hist(const double* __restrict__ sT, long long ld, const double* __restrict__ stats,
+                                                              int nchunk, unsigned* __restrict__ hist) {
+    __shared__ unsigned sh[kMaxCells];
+    const int l = blockIdx.y, chunk = blockIdx.x;
+    const int nc = (int)stats[l * 8 + 7];
+    if (nc == 0) return;
     const int n = (int)stats[l * 8 + 1];
+    const double smin = stats[l * 8 + 6];
+    const double inv_delta = 1.0 / (stats[l * 8 + 0] * kCellWidth);
+    for (int c = threadIdx.x; c < nc; c += kPartThreads) sh[c] = 0;
+    __syncthreads();
     const double* row = sT + (long long)l * ld;
-    const double smin = row[0];
-    const double inv_delta = 1.0 / (h * kCellWidth);
-    // first point with cell index >= j, first point with cell index > j (cell index is monotone along the row)
-    int a = 0, b = n;
-    while (a < b) { const int mid = (a + b) >> 1; if (kde_cell_of(row[mid], smin, inv_delta, nc) < j) a = mid + 1; else b = mid; }
-    const int first = a;
-    b = n;
-    while (a < b) { const int mid = (a + b) >> 1; if (kde_cell_of(row[mid], smin, inv_delta, nc) <= j) a = mid + 1; else b = mid; }
-    const int last = a;
-    const double centre = smin + ((double)j + 0.5) * (h * kCellWidth);
-    const double rh = 1.0 / h;
-    double M[kK + 1];
+    const int i1 = min(n, (chunk + 1) * kPartChunk);
+    for (int i = chunk * kPartChunk + threadIdx.x; i < i1; i += kPartThreads) atomicAdd(&sh[kde_cell_of(row[i], smin, inv_delta, nc)], 1u);
+    __syncthreads();
+    unsigned* out = hist + ((long long)l * nchunk + chunk) * kMaxCells;
+    for (int c = threadIdx.x; c < nc; c += kPartThreads) out[c] = sh[c];
+}
+
+// Partition pass 2 (one CTA per line): cell_first[c] = points in cells below c; hist[chunk][c] becomes the position of
+// the first point of (chunk, c) in the partitioned row.
+__global__ void __launch_bounds__(1024) kde_cell_scan(const double* __restrict__ stats, int nchunk, unsigned* __restrict__ hist,
+                                                      int* __restrict__ cell_first) {
+    __shared__ unsigned tot[kMaxCells + 1];
+    __shared__ unsigned wsum[32];
+    const int l = blockIdx.x;
+    const int nc = (int)stats[l * 8 + 7];
+    if (nc == 0) return;
+    unsigned* h = hist + (long long)l * nchunk * kMaxCells;
+    for (int c = threadIdx.x; c < nc; c += 1024) {
+        unsigned run = 0;
+        for (int k = 0; k < nchunk; ++k) { const unsigned t = h[(long long)k * kMaxCells + c]; h[(long long)k * kMaxCells + c] = run; run += t; }
+        tot[c] = run;
+    }
+    __syncthreads();
+    // exclusive scan of tot[0..nc) (nc <= 2048: two elements per thread)
+    const int c0 = 2 * threadIdx.x;
+    const unsigned a = c0 < nc ? tot[c0] : 0u, b = c0 + 1 < nc ? tot[c0 + 1] : 0u;
+    unsigned v = a + b;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int o = 1; o < 32; o <<= 1) { const unsigned t = __shfl_up_sync(0xffffffffu, v, o); if (lane >= o) v += t; }
+    if (lane == 31) wsum[warp] = v;
+    __syncthreads();
+    if (warp == 0) {
+        unsigned w = wsum[lane];
+        for (int o = 1; o < 32; o <<= 1) { const unsigned t = __shfl_up_sync(0xffffffffu, w, o); if (lane >= o) w += t; }
+        wsum[lane] = w;
+    }
+    __syncthreads();
+    const unsigned excl = v - (a + b) + (warp ? wsum[warp - 1] : 0u);
+    __syncthreads();
+    if (c0 < nc) tot[c0] = excl;
+    if (c0 + 1 < nc) tot[c0 + 1] = excl + a;
+    __syncthreads();
+    int* cf = cell_first + (long long)l * (kMaxCells + 1);
+    for (int c = threadIdx.x; c < nc; c += 1024) {
+        const unsigned f = tot[c];
+        cf[c] = (int)f;
+        for (int k = 0; k < nchunk; ++k) h[(long long)k * kMaxCells + c] += f;
+    }
+    if (threadIdx.x == 0) cf[nc] = (int)stats[l * 8 + 1];
+}
+
+// Partition pass 3: STABLE scatter.  Warp w of the CTA owns a contiguous eighth of the chunk and walks it in order, 32
+// consecutive values at a time; the lanes of a group that fall into the same cell take consecutive positions in lane
+// order (match_any), and the warp's running count per cell (shared memory, one row per warp) carries on to the next group.
+__global__ void __launch_bounds__(kPartThreads) kde_cell_scatter(const double* __restrict__ sT, long long ld, const double* __restrict__ stats,
+                                                                 int nchunk, const unsigned* __restrict__ hist, double* __restrict__ srt) {
+    extern __shared__ unsigned cnt[];                    // [8 warps][kMaxCells]
+    const int l = blockIdx.y, chunk = blockIdx.x;
+    const int nc = (int)stats[l * 8 + 7];
+    if (nc == 0) return;
+    const int n = (int)stats[l * 8 + 1];
+    const double smin = stats[l * 8 + 6];
+    const double inv_delta = 1.0 / (stats[l * 8 + 0] * kCellWidth);
+    constexpr int W = kPartThreads / 32, SEG = kPartChunk / W;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int c = threadIdx.x; c < W * kMaxCells; c += kPartThreads) if ((c & (kMaxCells - 1)) < nc) cnt[c] = 0;
+    __syncthreads();
+    const double* row = sT + (long long)l * ld;
+    const int base = chunk * kPartChunk + warp * SEG;
+    unsigned* mine = cnt + warp * kMaxCells;
+    double v[SEG / 32];
+    int cell[SEG / 32];
 #pragma unroll
-    for (int k = 0; k <= kK; ++k) M[k] = 0.0;
-    for (int i = first; i < last; ++i) {
-        const double u = (row[i] - centre) * rh;
+    for (int k = 0; k < SEG / 32; ++k) {
+        const int i = base + k * 32 + lane;
+        cell[k] = -1 - lane;                              // past the end: a key of its own, never written
+        v[k] = 0.0;
+        if (i < n) { v[k] = row[i]; cell[k] = kde_cell_of(v[k], smin, inv_delta, nc); atomicAdd(&mine[cell[k]], 1u); }
+    }
+    __syncthreads();
+    // prefix over the warps of every cell, starting from the chunk's base position
+    const unsigned* hb = hist + ((long long)l * nchunk + chunk) * kMaxCells;
+    for (int c = threadIdx.x; c < nc; c += kPartThreads) {
+        unsigned run = hb[c];
+        for (int w = 0; w < W; ++w) { const unsigned t = cnt[w * kMaxCells + c]; cnt[w * kMaxCells + c] = run; run += t; }
+    }
+    __syncthreads();
+    double* dst = srt + (long long)l * ld;
+#pragma unroll
+    for (int k = 0; k < SEG / 32; ++k) {
+        const unsigned peers = __match_any_sync(0xffffffffu, cell[k]);
+        const int leader = __ffs(peers) - 1;
+        const int rank = __popc(peers & ((1u << lane) - 1));
+        unsigned old = 0;
+        if (lane == leader && cell[k] >= 0) { old = mine[cell[k]]; mine[cell[k]] = old + __popc(peers); }
+        old = __shfl_sync(0xffffffffu, old, leader);
+        if (cell[k] >= 0) dst[old + rank] = v[k];
+        __syncwarp();
+    }
+}
+
+// Moments of every cell: one warp per (line, cell); the lanes stride over the cell's points, a fixed butterfly adds up.
+__global__ void __launch_bounds__(256) kde_cell_moments(const double* __restrict__ srt, long long ld, const double* __restrict__ stats,
+                                                        const int* __restrict__ cell_first, double* __restrict__ mom) {
+    const int l = blockIdx.y;
+    const int c = blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    const int nc = (int)stats[l * 8 + 7];
+    if (c >= nc) return;
+    const int* cf = cell_first + (long long)l * (kMaxCells + 1);
+    const int first = cf[c], last = cf[c + 1];
+    const double smin = stats[l * 8 + 6];
+    const double rh = 1.0 / stats[l * 8 + 0];
+    const double centre = ((double)c + 0.5) * kCellWidth;
+    const double* row = srt + (long long)l * ld;
+    double M[kNM];
+#pragma unroll
+    for (int k = 0; k < kNM; ++k) M[k] = 0.0;
+    for (int i = first + lane; i < last; i += 32) {
+        const double u = (row[i] - smin) * rh - centre;
         double t = 1.0;
         M[0] += 1.0;
 #pragma unroll
-        for (int k = 1; k <= kK; ++k) { t *= u * (1.0 / k); M[k] += t; }       // u^k / k!
+        for (int k = 1; k < kNM; ++k) { t *= u * (1.0 / k); M[k] += t; }       // u^k / k!
     }
-    double* rec = cells + c * kCellRec;
 #pragma unroll
-    for (int k = 0; k <= kK; ++k) rec[k] = M[k];
-    rec[kK + 1] = (double)first;
+    for (int k = 0; k < kNM; ++k) {
+        double s = M[k];
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        M[k] = s;
+    }
+    if (lane == 0) {
+        double* rec = mom + ((long long)l * kMaxCells + c) * kNM;
+#pragma unroll
+        for (int k = 0; k < kNM; ++k) rec[k] = M[k];
+    }
 }
 
-// One CTA evaluates kFastGenes genes of one line.  The line's cell table (a few hundred 144-byte records that every
-// gene of the line walks a ~45-cell window of) is staged in shared memory first: read from L2 by every thread it was
-// 47 GB per Avana-shaped call, i.e. the kernel ran at L2 bandwidth.  A table too large for the CTA's shared memory
-// is read in place.
-constexpr int kFastThreads = 256;
-constexpr int kFastPerThread = 4;
-constexpr int kFastGenes = kFastThreads * kFastPerThread;
-constexpr int kFastSmemCells = 480;          // 67.5 KB: three CTAs per SM
-
-__global__ void __launch_bounds__(kFastThreads) kde_pvalues_fast(const double* __restrict__ w1_genes, long long n_genes, int L,
-                                                                 const double* __restrict__ sT, long long ld,
-                                                                 const double* __restrict__ stats, const long long* __restrict__ cell_off,
-                                                                 const double* __restrict__ cells, int positive,
-                                                                 double* __restrict__ pvals) {
-    extern __shared__ double s_tab[];
+// Local expansions: one thread per (line, target cell) forms its kNM coefficients from the moments of the source cells
+// in its window; the derivative table is the same for every thread at every step (constant-bank operands).
+constexpr int kLocThreads = 128;
+__global__ void __launch_bounds__(kLocThreads) kde_local_expansions(const double* __restrict__ stats, const int* __restrict__ cell_first,
+                                                                    const double* __restrict__ mom, double* __restrict__ loc) {
     const int l = blockIdx.y;
-    const long long nc = cell_off[l + 1] - cell_off[l];
-    if (nc == 0) return;                                   // this line is left to the brute-force kernel
-    const double* ctab = cells + cell_off[l] * kCellRec;
-    if (nc <= kFastSmemCells) {
-        for (long long i = threadIdx.x; i < nc * kCellRec; i += kFastThreads) s_tab[i] = ctab[i];
-        __syncthreads();
-        ctab = s_tab;
-    }
-    const double h = stats[l * 8 + 0];
-    const int n = (int)stats[l * 8 + 1];
-    const double cterm = stats[l * 8 + 2], wgt = stats[l * 8 + 3];
-    const double* row = sT + (long long)l * ld;
-  for (int k = 0; k < kFastPerThread; ++k) {
-    const long long g = ((long long)blockIdx.x * kFastPerThread + k) * kFastThreads + threadIdx.x;
-    if (g >= n_genes) break;
-    const double w = positive ? -w1_genes[g * L + l] : w1_genes[g * L + l];
-    if (!(w == w)) { pvals[g * L + l] = w; continue; }
-    const double rh = 1.0 / h;
-    const double smin = row[0];
-    const double zmax = (w - smin) * rh;
-    double tot = 0.0;
-    if (zmax < -7.5) {
-        // far below every null value: only the nearest few points contribute
-        for (int i = 0; i < n; ++i) {
-            const double term = normcdf((w - row[i]) * rh);
-            tot += term;
-            if (term <= 1e-18 * tot) break;          // also stops at the first exact zero (z < -38.5): later points are farther
-        }
-    } else {
-        const double zneg = fmin(zmax, 0.0);
-        const double zlo = -sqrt(zneg * zneg + 2.0 * log(1e16 * (double)n));
-        const double delta = h * kCellWidth;
-        // z_j = (w - centre_j)/h = zmax - (j + 0.5)*kCellWidth decreases with j
-        // saturated: z_j - kCellWidth/2 >= 8.3  <=>  j <= (zmax - 8.3)/kCellWidth - 1
-        long long jsat = (long long)floor((zmax - 8.3) / kCellWidth) - 1;
-        if (jsat >= nc) jsat = nc - 1;
-        if (jsat >= 0) tot = (jsat + 1 < nc) ? ctab[(jsat + 1) * kCellRec + kK + 1] : (double)n;    // points before cell jsat+1
-        long long jend = (long long)ceil((zmax - zlo) / kCellWidth);                                 // z_j + w/2 >= zlo
-        if (jend >= nc) jend = nc - 1;
-        (void)delta;
-        for (long long j = (jsat < 0 ? 0 : jsat + 1); j <= jend; ++j) {
-            const double* rec = ctab + j * kCellRec;
-            const double m0 = rec[0];
-            if (m0 == 0.0) continue;
-            const double z = zmax - ((double)j + 0.5) * kCellWidth;
-            double he_prev = 0.0, he = 1.0, S = 0.0;
+    const int nc = (int)stats[l * 8 + 7];
+    if (nc == 0) return;
+    const int nt = nc + kKsat - kJmin;
+    const int jj = blockIdx.x * kLocThreads + threadIdx.x;
+    if (jj >= nt) return;
+    const int j = jj + kJmin;
+    double A[kNM];
 #pragma unroll
-            for (int k = 1; k <= kK; ++k) {
-                S = fma(he, rec[k], S);
-                const double nxt = fma(z, he, -(double)(k - 1) * he_prev);
-                he_prev = he; he = nxt;
-            }
-            const double phi = exp(-0.5 * z * z) * 0.3989422804014327;
-            tot += m0 * normcdf(z) - phi * S;
+    for (int m = 0; m < kNM; ++m) A[m] = 0.0;
+    const double* M = mom + (long long)l * kMaxCells * kNM;
+    // source cells c = j - k inside [0, nc), k = KSAT down to -KNEG (ascending c: a fixed order); k is the same for every
+    // thread of the CTA at every step, so the derivative table is read through the constant bank without divergence
+    for (int k = kKsat; k >= -kKneg; --k) {
+        const int c = j - k;
+        if (c < 0 || c >= nc) continue;
+        const double* rec = M + (long long)c * kNM;
+        if (rec[0] == 0.0) continue;
+        const double* D = c_dtab + (k + kKneg) * (2 * kP + 1);
+        double b[kNM];
+#pragma unroll
+        for (int q = 0; q < kNM; ++q) b[q] = (q & 1) ? -rec[q] : rec[q];
+#pragma unroll
+        for (int m = 0; m < kNM; ++m) {
+            double s = 0.0;
+#pragma unroll
+            for (int q = 0; q < kNM; ++q) s = fma(D[m + q], b[q], s);
+            A[m] += s;
         }
     }
-    pvals[g * L + l] = (tot - cterm) * wgt;
-  }
+    double fact = 1.0;
+#pragma unroll
+    for (int m = 1; m < kNM; ++m) { fact *= (double)m; A[m] /= fact; }
+    const int csat = j - kKsat - 1;                                    // cells that count fully
+    if (csat >= 0) A[0] += (double)cell_first[(long long)l * (kMaxCells + 1) + min(csat, nc - 1) + 1];
+    double* out = loc + ((long long)l * kMaxTargets + jj) * kNM;
+#pragma unroll
+    for (int m = 0; m < kNM; ++m) out[m] = A[m];
+}
+
+// Sum over the nearest null values for a point more than 5 bandwidths below all of them (F is tiny there and its relative
+// accuracy rests on those few terms).  The points of cells 0, 1, ... are added in stored order up to the cell from which
+// on nothing can change the sum at 1e-18 relative: Phi(z - a)/Phi(z) <= exp(-((|z| + a)^2 - z^2)/2) for z <= -5, a >= 0,
+// and the smallest null value itself (a = 0) is in the sum, so a >= sqrt(z^2 + 2 ln(1e18 n)) - |z| is negligible.
+__device__ __forceinline__ double kde_tail_sum(double w, double z, double rh, int n, int nc, const int* __restrict__ cf,
+                                               const double* __restrict__ row) {
+    const double reach = sqrt(z * z + 2.0 * log(1e18 * (double)n)) + z;            // z < 0
+    int c_stop = (int)ceil(reach * (1.0 / kCellWidth)) + 1;
+    if (c_stop > nc) c_stop = nc;
+    const int last = cf[c_stop];
+    double tot = 0.0;
+    for (int i = 0; i < last; ++i) tot += normcdf((w - row[i]) * rh);
+    return tot;
+}
+
+// p-values: one thread per (gene, line), consecutive threads on consecutive lines (coalesced loads and stores); a degree-P
+// polynomial from the line's table of local expansions (L2 resident: ~450 cells x 104 bytes per line).  Points in the
+// far lower tail are queued (one aggregated atomic per warp) for kde_pvalues_tail: evaluated here they would hold up
+// the 31 other lanes of their warp for a few thousand instructions each.
+__global__ void __launch_bounds__(256) kde_pvalues_fast(const double* __restrict__ w1_genes, long long n_genes, int L,
+                                                        const double* __restrict__ stats, const double* __restrict__ loc, int positive,
+                                                        double* __restrict__ pvals, unsigned* __restrict__ tail_count,
+                                                        long long* __restrict__ tail_idx) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    bool queue = false;
+    if (idx < n_genes * L) {
+        const int l = (int)(idx % L);
+        const int nc = (int)stats[l * 8 + 7];
+        if (nc > 0) {                                      // (nc == 0: this line is left to the O(n) kernel)
+            const double wv = w1_genes[idx];
+            if (!(wv == wv)) pvals[idx] = wv;
+            else {
+                const double w = positive ? -wv : wv;
+                const int n = (int)stats[l * 8 + 1];
+                const double cterm = stats[l * 8 + 2], wgt = stats[l * 8 + 3], smin = stats[l * 8 + 6];
+                const double z = (w - smin) / stats[l * 8 + 0];
+                const double jf = floor(z * (1.0 / kCellWidth));
+                double tot = 0.0;
+                if (z < -38.6) tot = 0.0;                  // Phi underflows to exactly 0 for every null value
+                else if (jf < (double)kJmin) queue = true;
+                else if (jf >= (double)(nc + kKsat)) tot = (double)n;
+                else {
+                    const int j = (int)jf;
+                    const double t = z - ((double)j + 0.5) * kCellWidth;
+                    const double* a = loc + ((long long)l * kMaxTargets + (j - kJmin)) * kNM;
+                    tot = a[kP];
+#pragma unroll
+                    for (int m = kP - 1; m >= 0; --m) tot = fma(tot, t, a[m]);
+                }
+                if (!queue) pvals[idx] = (tot - cterm) * wgt;
+            }
+        }
+    }
+    const unsigned m = __ballot_sync(0xffffffffu, queue);
+    if (m) {
+        const int lane = threadIdx.x & 31;
+        const int leader = __ffs(m) - 1;
+        unsigned base = 0;
+        if (lane == leader) base = atomicAdd(tail_count, __popc(m));
+        base = __shfl_sync(0xffffffffu, base, leader);
+        if (queue) tail_idx[base + __popc(m & ((1u << lane) - 1))] = idx;
+    }
+}
+
+__global__ void __launch_bounds__(256) kde_pvalues_tail(const double* __restrict__ w1_genes, int L, const double* __restrict__ srt,
+                                                        long long ld, const double* __restrict__ stats, const int* __restrict__ cell_first,
+                                                        int positive, double* __restrict__ pvals, const unsigned* __restrict__ tail_count,
+                                                        const long long* __restrict__ tail_idx) {
+    const unsigned count = *tail_count;
+    for (unsigned q = blockIdx.x * blockDim.x + threadIdx.x; q < count; q += gridDim.x * blockDim.x) {
+        const long long idx = tail_idx[q];
+        const int l = (int)(idx % L);
+        const double wv = w1_genes[idx];
+        const double w = positive ? -wv : wv;
+        const double rh = 1.0 / stats[l * 8 + 0];
+        const double z = (w - stats[l * 8 + 6]) / stats[l * 8 + 0];
+        const double tot = kde_tail_sum(w, z, rh, (int)stats[l * 8 + 1], (int)stats[l * 8 + 7], cell_first + (long long)l * (kMaxCells + 1),
+                                        srt + (long long)l * ld);
+        pvals[idx] = (tot - stats[l * 8 + 2]) * stats[l * 8 + 3];
+    }
 }
 
 // General KDE evaluation for the branches the command line does not reach (jacks_io.py:76-88):
@@ -396,45 +657,57 @@ __global__ void __launch_bounds__(kPvThreads) kde_eval_kernel(const double* __re
 
 using namespace jacks;
 
-// Null density of every line from the pseudo-gene effects (jacks_io.py:76-79): compaction, bandwidth, sorted rows and
-// the cell table, all in ctx->tmp.  `out` stays valid until the next KDE call on this context.
+// Null density of every line from the pseudo-gene effects (jacks_io.py:76-79): transposed rows, bandwidth, the rows
+// partitioned by cell, cell moments and the table of local expansions, all in ctx->tmp.  `out` stays valid until the
+// next KDE call on this context.
 int jacks::kde_null_prepare(JacksCtx* ctx, const double* w1_pseudo, int64_t n_pseudo, int32_t n_lines, int32_t positive,
                             cudaStream_t st, KdeNull* out) {
-    // rows padded to a power of two (>= one sort tile) so the bitonic network needs no bounds checks
-    long long ld = kSortTileD;
-    while (ld < n_pseudo) ld <<= 1;
-    const long long cell_cap = (long long)n_lines * 2048;
-    const size_t bytes = (size_t)ld * n_lines * sizeof(double) + (size_t)n_lines * 8 * sizeof(double) +
-                         (size_t)(n_lines + 1) * sizeof(long long) + (size_t)cell_cap * kCellRec * sizeof(double);
-    int rc = ctx->tmp.reserve(bytes);
+    if (n_pseudo >= (1LL << 31) - kPartChunk) return fail(JACKS_E_INVALID, "too many pseudo-genes (%lld)", (long long)n_pseudo);
+    const long long ld = (n_pseudo + kChunk - 1) / kChunk * kChunk;            // rows padded with +inf for the O(n) kernels
+    const int nchunk = (int)((n_pseudo + kPartChunk - 1) / kPartChunk);
+    const size_t L = (size_t)n_lines;
+    size_t off = 0;
+    auto take = [&](size_t bytes) { const size_t o = off; off += (bytes + 255) & ~(size_t)255; return o; };
+    const size_t o_sT = take((size_t)ld * L * sizeof(double)), o_srt = take((size_t)ld * L * sizeof(double));
+    const size_t o_stats = take(L * 8 * sizeof(double)), o_nan = take(L * sizeof(int));
+    const size_t o_hist = take(L * nchunk * kMaxCells * sizeof(unsigned)), o_first = take(L * (kMaxCells + 1) * sizeof(int));
+    const size_t o_mom = take(L * kMaxCells * kNM * sizeof(double)), o_loc = take(L * kMaxTargets * kNM * sizeof(double));
+    const size_t o_tab = take((size_t)kNK * (2 * kP + 1) * sizeof(double));
+    int rc = ctx->tmp.reserve(off);
     if (rc != JACKS_OK) return rc;
     cudaError_t e;
-    double* sT = (double*)ctx->tmp.p;
-    double* stats = sT + ld * n_lines;
-    long long* cell_off = (long long*)(stats + (size_t)n_lines * 8);
-    double* cells = (double*)(cell_off + n_lines + 1);
+    char* base = (char*)ctx->tmp.p;
+    double* sT = (double*)(base + o_sT);
+    double* srt = (double*)(base + o_srt);
+    double* stats = (double*)(base + o_stats);
+    int* nan_count = (int*)(base + o_nan);
+    unsigned* hist = (unsigned*)(base + o_hist);
+    int* cell_first = (int*)(base + o_first);
+    double* mom = (double*)(base + o_mom);
+    double* loc = (double*)(base + o_loc);
     const bool brute = getenv("JACKS_KDE_BRUTE") != nullptr;          // validation: force the O(n) sums
-    kde_line_stats<<<n_lines, kStatsThreads, 0, st>>>(w1_pseudo, n_pseudo, n_lines, ld, positive ? 1 : 0, sT, stats);
-    ctx->launches++;
-    if (!brute) {
-        dim3 lg((unsigned)(ld / kSortTileD), (unsigned)n_lines);
-        sort_rows_local<<<lg, 1024, 0, st>>>(sT, ld, 2, kSortTileD);
+    if (!ctx->kde_attr_set) {          // once per device: the derivative table and the scatter kernel's shared memory
+        double* tab = (double*)(base + o_tab);
+        kde_deriv_table<<<(kNK + 127) / 128, 128, 0, st>>>(tab);
+        if ((e = cudaMemcpyToSymbolAsync(c_dtab, tab, (size_t)kNK * (2 * kP + 1) * sizeof(double), 0, cudaMemcpyDeviceToDevice, st)) != cudaSuccess) return cuda_fail(e, "cudaMemcpyToSymbolAsync");
+        if ((e = cudaFuncSetAttribute(kde_cell_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kPartThreads / 32 * kMaxCells * sizeof(unsigned)))) != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute");
+        ctx->kde_attr_set = true;
         ctx->launches++;
-        for (long long kk = 2LL * kSortTileD; kk <= ld; kk <<= 1) {
-            for (long long j = kk >> 1; j >= kSortTileD; j >>= 1) {
-                dim3 gg((unsigned)((ld / 2 + 255) / 256), (unsigned)n_lines);
-                sort_rows_global<<<gg, 256, 0, st>>>(sT, ld, kk, j);
-                ctx->launches++;
-            }
-            sort_rows_local<<<lg, 1024, 0, st>>>(sT, ld, (int)kk, (int)kk);
-            ctx->launches++;
-        }
-        kde_cell_layout<<<1, 1, 0, st>>>(sT, ld, stats, n_lines, cell_cap, cell_off);
-        kde_cell_moments<<<(unsigned)((cell_cap + 127) / 128), 128, 0, st>>>(sT, ld, stats, n_lines, cell_off, cells);
-        ctx->launches += 2;
+    }
+    if ((e = cudaMemsetAsync(nan_count, 0, L * sizeof(int), st)) != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync");
+    kde_transpose<<<dim3((unsigned)((n_pseudo + 31) / 32), (unsigned)((n_lines + 31) / 32)), 256, 0, st>>>(w1_pseudo, n_pseudo, n_lines, ld, positive ? 1 : 0, sT, nan_count);
+    kde_row_stats<<<n_lines, kRowThreads, 0, st>>>(sT, n_pseudo, ld, nan_count, stats);
+    ctx->launches += 2;
+    if (!brute) {
+        kde_cell_hist<<<dim3((unsigned)nchunk, (unsigned)n_lines), kPartThreads, 0, st>>>(sT, ld, stats, nchunk, hist);
+        kde_cell_scan<<<n_lines, 1024, 0, st>>>(stats, nchunk, hist, cell_first);
+        kde_cell_scatter<<<dim3((unsigned)nchunk, (unsigned)n_lines), kPartThreads, kPartThreads / 32 * kMaxCells * sizeof(unsigned), st>>>(sT, ld, stats, nchunk, hist, srt);
+        kde_cell_moments<<<dim3(kMaxCells / 8, (unsigned)n_lines), 256, 0, st>>>(srt, ld, stats, cell_first, mom);
+        kde_local_expansions<<<dim3((kMaxTargets + kLocThreads - 1) / kLocThreads, (unsigned)n_lines), kLocThreads, 0, st>>>(stats, cell_first, mom, loc);
+        ctx->launches += 5;
     }
     if ((e = cudaGetLastError()) != cudaSuccess) return cuda_fail(e, "kde null kernels launch");
-    out->sT = sT; out->stats = stats; out->cell_off = cell_off; out->cells = cells;
+    out->sT = sT; out->srt = srt; out->stats = stats; out->cell_first = cell_first; out->loc = loc;
     out->ld = ld; out->n_lines = n_lines; out->positive = positive ? 1 : 0; out->brute = brute ? 1 : 0;
     return JACKS_OK;
 }
@@ -445,20 +718,20 @@ int jacks::kde_eval(JacksCtx* ctx, const KdeNull& nl, const double* w1_genes, in
     cudaError_t e;
     const int n_lines = nl.n_lines;
     if (!nl.brute) {
-        dim3 fg((unsigned)((n_genes + kFastGenes - 1) / kFastGenes), (unsigned)n_lines);
-        const size_t fsm = (size_t)kFastSmemCells * kCellRec * sizeof(double);
-        if (!ctx->kde_attr_set) {          // per device: one process may hold contexts on several
-            if ((e = cudaFuncSetAttribute(kde_pvalues_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsm)) != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute");
-            ctx->kde_attr_set = true;
-        }
-        kde_pvalues_fast<<<fg, kFastThreads, fsm, st>>>(w1_genes, n_genes, n_lines, nl.sT, nl.ld, nl.stats, nl.cell_off, nl.cells, nl.positive, pvals);
-        ctx->launches++;
+        const long long total = (long long)n_genes * n_lines;
+        int rc = ctx->kde_tail.reserve(256 + (size_t)total * sizeof(long long));
+        if (rc != JACKS_OK) return rc;
+        unsigned* tail_count = (unsigned*)ctx->kde_tail.p;
+        long long* tail_idx = (long long*)((char*)ctx->kde_tail.p + 256);
+        if ((e = cudaMemsetAsync(tail_count, 0, sizeof(unsigned), st)) != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync");
+        kde_pvalues_fast<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(w1_genes, n_genes, n_lines, nl.stats, nl.loc, nl.positive, pvals, tail_count, tail_idx);
+        kde_pvalues_tail<<<4 * ctx->n_sm, 256, 0, st>>>(w1_genes, n_lines, nl.srt, nl.ld, nl.stats, nl.cell_first, nl.positive, pvals, tail_count, tail_idx);
+        ctx->launches += 2;
     }
-    // lines the cell table could not hold (pathological ranges), or everything when forced
+    // lines whose range needs more cells than the table holds (far outliers), or everything when forced
     const long long per_cta = (long long)kPvThreads * kGT;
     dim3 grid((unsigned)((n_genes + per_cta - 1) / per_cta), (unsigned)n_lines);
-    kde_pvalues<<<grid, kPvThreads, 0, st>>>(w1_genes, n_genes, n_lines, nl.sT, nl.ld, nl.stats, nl.positive,
-                                             nl.brute ? nullptr : nl.cell_off, pvals);
+    kde_pvalues<<<grid, kPvThreads, 0, st>>>(w1_genes, n_genes, n_lines, nl.sT, nl.ld, nl.stats, nl.positive, nl.brute ? 0 : 1, pvals);
     if ((e = cudaGetLastError()) != cudaSuccess) return cuda_fail(e, "kde kernels launch");
     ctx->launches++;
     return JACKS_OK;

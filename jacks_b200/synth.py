@@ -122,3 +122,59 @@ def make_count_screen(n_genes=2000, guides_per_gene=4, n_lines=20, n_reps=2, see
     guide_ids = [''.join(alphabet[rng.integers(0, 4, size=20)]) + '_%06d' % i for i in range(N)]
     gene_ids = ['G%05d' % g for g in gene_of_row]
     return guide_ids, gene_ids, cols, samples, counts
+
+
+# Sample layout of the reference's full example screen, jacks/example/example_repmap.tab (the count file itself is not in
+# the reference repository): 53 replicate columns -> the control CTRL (2 replicates) and 16 cell lines.
+EXAMPLE_LAYOUT = (('CTRL', 2), ('MOLM', 2), ('MV411', 2), ('HL60', 2), ('OCIAML2', 2), ('OCIAML3', 2), ('A375', 3), ('A2058', 3),
+                  ('CO205', 3), ('HuPT3', 3), ('HuPT4', 3), ('MB415', 3), ('MB436', 3), ('MB453', 3), ('SW1990', 2), ('SW48', 3),
+                  ('HT29', 12))
+
+
+def make_example_count_screen(n_genes=18000, guides_per_gene=5, layout=EXAMPLE_LAYOUT, seed=AVANA_SEED + 7, frac_essential=0.10):
+    """BASELINE config 2 stand-in: a count-level screen with the sample layout of jacks/example (control first) and
+    ``n_genes * guides_per_gene`` guides (90,000 by default).  Same count model as make_count_screen.
+    Returns (guide_ids, gene_ids, colnames, samples, counts[int64 N x C])."""
+    rng = np.random.default_rng(seed)
+    N = n_genes * guides_per_gene
+    lines = [name for name, _ in layout[1:]]
+    essential = rng.random(n_genes) < frac_essential
+    w = np.where(essential[:, None], rng.normal(-1.5, 0.5, size=(n_genes, len(lines))),
+                 rng.normal(0.0, 0.15, size=(n_genes, len(lines))))
+    x = rng.normal(1.0, 0.4, size=N)
+    lam = rng.lognormal(np.log(500.0), 0.6, size=N)
+    gene_of_row = np.repeat(np.arange(n_genes), guides_per_gene)
+    cols, samples, blocks = [], [], []
+    for li, (name, reps) in enumerate(layout):
+        for r in range(reps):
+            depth = rng.uniform(0.7, 1.3)
+            if li == 0:
+                blocks.append(rng.poisson(lam * depth))
+            else:
+                lfc = x * w[gene_of_row, li - 1] + rng.normal(0.0, 0.25, size=N)
+                blocks.append(rng.poisson(lam * depth * np.exp2(lfc)))
+            cols.append('%s_rep_%d' % (name, r + 1)); samples.append(name)
+    counts = np.stack(blocks, axis=1).astype(np.int64)
+    alphabet = np.array(list('ACGT'))
+    order = rng.permutation(N)                   # guide ids do not sort in gene order: the loader's string sort matters
+    guide_ids = [''.join(alphabet[rng.integers(0, 4, size=12)]) + '_%06d' % order[i] for i in range(N)]
+    gene_ids = ['G%05d' % g for g in gene_of_row]
+    return guide_ids, gene_ids, cols, samples, counts
+
+
+def write_count_screen(prefix, guide_ids, gene_ids, cols, samples, counts, ctrl_genes=()):
+    """Write the count table, the replicate map and (optionally) a control-gene list the way run_JACKS.py reads them."""
+    import pandas as pd
+    df = pd.DataFrame(counts, columns=cols)
+    df.insert(0, 'Gene', gene_ids)
+    df.insert(0, 'sgRNA', guide_ids)
+    df.to_csv(prefix + '_counts.tab', sep='\t', index=False)
+    with open(prefix + '_repmap.tab', 'w') as f:
+        f.write('Replicate\tSample\n')
+        for c, sname in zip(cols, samples):
+            f.write('%s\t%s\n' % (c, sname))
+    if len(ctrl_genes):
+        with open(prefix + '_ctrl_genes.txt', 'w') as f:
+            for g in ctrl_genes:
+                f.write('%s\n' % g)
+    return prefix + '_counts.tab', prefix + '_repmap.tab', prefix + '_ctrl_genes.txt'

@@ -16,7 +16,7 @@ import sys
 import numpy as np
 from scipy.special import ndtr
 
-P = Q = 16
+P = Q = int(__import__("os").environ.get("PQ", 16))
 DW = 0.25
 KSAT = 34          # k D' = 8.5
 KNEG = 48          # k D' = -12
