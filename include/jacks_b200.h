@@ -21,6 +21,8 @@
  *   jacks/jacks/preprocess.py:77 normalizeLogCounts            jacks_normalize_host
  *   jacks/jacks/preprocess.py:61 condense_normalised_counts    jacks_condense_host
  *   jacks/jacks/preprocess.py:25 calc_posterior_sd             jacks_condense_host (one sample)
+ *   jacks/jacks/preprocess.py:132 loadDataAndPreprocess        jacks_preprocess_host (one count table, one upload);
+ *                                                             jacks_normalize_device -> jacks_condense_device
  *
  * All floating point data is IEEE float64.  All arrays are dense, C order.  "device"
  * entry points take pointers into the current CUDA device's memory and enqueue work on
@@ -305,6 +307,31 @@ enum { JACKS_NORM_MEDIAN = 0, JACKS_NORM_ZMAD = 1, JACKS_NORM_CTRL_GUIDES = 2, J
 JACKS_API int jacks_normalize_host(JacksCtx* ctx, const double* values, int64_t n_guides, int32_t n_cols, int32_t take_log,
                          double prior, const double* log2_table, int64_t table_len, int32_t normtype,
                          const uint8_t* row_mask, double* out);
+
+/*
+ * The same two steps on DEVICE buffers, enqueued on `stream` without synchronising, so that they chain without leaving the
+ * GPU (normalise -> condense -> jacks_em_run_device).  values / log2_table / row_mask / out / logcounts / data are device
+ * pointers; the (small) sample index arrays of jacks_condense_device are HOST arrays.  Scratch lives in the context.
+ */
+JACKS_API int jacks_normalize_device(JacksCtx* ctx, const double* values, int64_t n_guides, int32_t n_cols, int32_t take_log,
+                           double prior, const double* log2_table, int64_t table_len, int32_t normtype,
+                           const uint8_t* row_mask, double* out, void* stream);
+JACKS_API int jacks_condense_device(JacksCtx* ctx, const double* logcounts, int64_t n_guides, int32_t n_cols,
+                          const int32_t* sample_col_offsets, const int32_t* sample_cols, int32_t n_samples,
+                          int32_t window_override, int32_t monotonize, double* data, void* stream);
+
+/*
+ * loadDataAndPreprocess for one count table in one call (preprocess.py:132-171): log2(count + prior), per-column
+ * normalisation, the loader's row sort (row_order[i] = input row that becomes output row i: numpy.argsort of the guide
+ * ids, preprocess.py:154-157; NULL keeps the input order) and condense_normalised_counts.  The counts go up ONCE, the
+ * [N, S, 2] cube comes down once; the normalised, row-sorted log counts are downloaded only if logcounts_out != NULL.
+ * row_mask refers to INPUT rows.  Host pointers.
+ */
+JACKS_API int jacks_preprocess_host(JacksCtx* ctx, const double* counts, int64_t n_guides, int32_t n_cols, int32_t take_log,
+                          double prior, const double* log2_table, int64_t table_len, int32_t normtype,
+                          const uint8_t* row_mask, const int64_t* row_order, const int32_t* sample_col_offsets,
+                          const int32_t* sample_cols, int32_t n_samples, int32_t window_override, int32_t monotonize,
+                          double* logcounts_out, double* data);
 
 /*
  * calc_posterior_sd with a guide subset (preprocess.py:25-58 with guideset_indexs; used by inferMissingVariances,

@@ -104,6 +104,9 @@ def lib():
             L.jacks_condense_host.argtypes = [vp, vp, i64, i32, vp, vp, i32, i32, i32, vp]
             L.jacks_normalize_host.argtypes = [vp, vp, i64, i32, i32, dbl, vp, i64, i32, vp, vp]
             L.jacks_posterior_sd_subset_host.argtypes = [vp, vp, i64, i32, vp, i32, i32, vp]
+            L.jacks_normalize_device.argtypes = [vp, vp, i64, i32, i32, dbl, vp, i64, i32, vp, vp, vp]
+            L.jacks_condense_device.argtypes = [vp, vp, i64, i32, vp, vp, i32, i32, i32, vp, vp]
+            L.jacks_preprocess_host.argtypes = [vp, vp, i64, i32, i32, dbl, vp, i64, i32, vp, vp, vp, vp, i32, i32, i32, vp, vp]
         L.jacks_table_scan.argtypes = [C.c_char_p, i64, C.POINTER(i64), C.POINTER(i64)]
         L.jacks_table_read.argtypes = [C.c_char_p, i64, C.c_char, i64, i32, vp, vp, vp, i32, vp, vp, vp]
         L.jacks_table_write.argtypes = [C.c_char_p, C.c_char_p, i64, i32, vp, vp, vp, vp, i32]
@@ -452,20 +455,82 @@ def normalize_host(ctx, values, normtype='median', take_log=False, prior=32.0, r
     logarithm from a table this host computes with numpy (bit-identical to the reference's np.log2 here)."""
     values = np.ascontiguousarray(values, dtype=np.float64)
     out = np.empty(values.shape, dtype=np.float64)
-    table = None
-    if take_log and use_table and values.size:
-        vmax = values.max()                      # one pass, no temporary; NaN / inf cells take the slow path
-        if not np.isfinite(vmax):
-            finite = values[np.isfinite(values)]
-            vmax = finite.max() if finite.size else -1.0
-        top = int(min(vmax, LOG2_TABLE_MAX - 1)) if vmax >= 0 else -1
-        if top >= 0:
-            table = np.log2(np.arange(top + 1, dtype=np.float64) + prior)
+    table = _log2_table(values, prior) if (take_log and use_table) else None
     mask = None if row_mask is None else np.ascontiguousarray(row_mask, dtype=np.uint8)
     check(lib().jacks_normalize_host(ctx.h, _ptr(values), values.shape[0], values.shape[1], int(bool(take_log)), float(prior),
                                      _ptr(table), 0 if table is None else table.size, NORM_TYPES[normtype], _ptr(mask),
                                      _ptr(out)))
     return out
+
+
+def _log2_table(values, prior):
+    """log2(k + prior) for every integer count k up to the largest in `values`, computed by THIS host's numpy (integer counts
+    then take exactly the bits the reference's np.log2 produces here); None when there is nothing to tabulate."""
+    if not values.size:
+        return None
+    vmax = values.max()                      # one pass, no temporary; NaN / inf cells take the slow path
+    if not np.isfinite(vmax):
+        finite = values[np.isfinite(values)]
+        vmax = finite.max() if finite.size else -1.0
+    top = int(min(vmax, LOG2_TABLE_MAX - 1)) if vmax >= 0 else -1
+    return np.log2(np.arange(top + 1, dtype=np.float64) + prior) if top >= 0 else None
+
+
+def _sample_csr(Iscreens):
+    offs = np.zeros(len(Iscreens) + 1, dtype=np.int32)
+    offs[1:] = np.cumsum([len(c) for c in Iscreens])
+    cols = np.ascontiguousarray(np.concatenate([np.asarray(c, dtype=np.int32) for c in Iscreens]) if len(Iscreens) else np.zeros(0, np.int32), dtype=np.int32)
+    return offs, cols
+
+
+def preprocess_host(ctx, counts, Iscreens, normtype='median', prior=32.0, take_log=True, row_mask=None, row_order=None, window=0,
+                    monotonize=True, want_logcounts=False):
+    """jacks_preprocess_host: counts [N, C] -> (data [N, S, 2], logcounts or None) with one upload and one download:
+    log2(count + prior), normalizeLogCounts, the row sort by guide id (row_order = argsort of the ids) and
+    condense_normalised_counts, chained on the device."""
+    counts = np.ascontiguousarray(counts, dtype=np.float64)
+    N, Cc = counts.shape
+    table = _log2_table(counts, prior) if take_log else None
+    offs, cols = _sample_csr(Iscreens)
+    mask = None if row_mask is None else np.ascontiguousarray(row_mask, dtype=np.uint8)
+    order = None if row_order is None else np.ascontiguousarray(row_order, dtype=np.int64)
+    data = np.empty((N, len(Iscreens), 2), dtype=np.float64)
+    lc = np.empty((N, Cc), dtype=np.float64) if want_logcounts else None
+    check(lib().jacks_preprocess_host(ctx.h, _ptr(counts), N, Cc, int(bool(take_log)), float(prior), _ptr(table),
+                                      0 if table is None else table.size, NORM_TYPES[normtype], _ptr(mask), _ptr(order), _ptr(offs),
+                                      _ptr(cols), len(Iscreens), int(window), int(bool(monotonize)), _ptr(lc), _ptr(data)))
+    return data, lc
+
+
+def preprocess_device_ms(ctx, counts, Iscreens, prior=32.0, reps=3):
+    """Device time (ms, CUDA events) of the resident chain jacks_normalize_device -> jacks_condense_device on counts
+    already in HBM -- the figure behind bench.py's aux.preprocess.roofline.  Needs torch for the device buffers."""
+    import torch
+    counts = np.ascontiguousarray(counts, dtype=np.float64)
+    N, Cc = counts.shape
+    dev = torch.device('cuda', ctx.device)
+    d_counts = torch.from_numpy(counts).to(dev)
+    table = _log2_table(counts, prior)
+    d_table = torch.from_numpy(table).to(dev)
+    d_lc = torch.empty_like(d_counts)
+    d_data = torch.empty((N, len(Iscreens), 2), dtype=torch.float64, device=dev)
+    offs, cols = _sample_csr(Iscreens)
+    stream = torch.cuda.current_stream().cuda_stream
+
+    def chain():
+        check(lib().jacks_normalize_device(ctx.h, d_counts.data_ptr(), N, Cc, 1, float(prior), d_table.data_ptr(), table.size,
+                                           NORM_TYPES['median'], None, d_lc.data_ptr(), C.c_void_p(stream or None)))
+        check(lib().jacks_condense_device(ctx.h, d_lc.data_ptr(), N, Cc, _ptr(offs), _ptr(cols), len(Iscreens), 0, 1,
+                                          d_data.data_ptr(), C.c_void_p(stream or None)))
+    chain()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        chain()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps
 
 
 def lognorm_median_host(ctx, counts, prior, use_table=True):
@@ -474,9 +539,7 @@ def lognorm_median_host(ctx, counts, prior, use_table=True):
 
 def condense_host(ctx, logcounts, Iscreens, window=0, monotonize=True):
     logcounts = np.ascontiguousarray(logcounts, dtype=np.float64)
-    offs = np.zeros(len(Iscreens) + 1, dtype=np.int32)
-    offs[1:] = np.cumsum([len(c) for c in Iscreens])
-    cols = np.ascontiguousarray(np.concatenate([np.asarray(c, dtype=np.int32) for c in Iscreens]) if len(Iscreens) else np.zeros(0, np.int32), dtype=np.int32)
+    offs, cols = _sample_csr(Iscreens)
     data = np.empty((logcounts.shape[0], len(Iscreens), 2), dtype=np.float64)
     check(lib().jacks_condense_host(ctx.h, _ptr(logcounts), logcounts.shape[0], logcounts.shape[1], _ptr(offs),
                                     _ptr(cols), len(Iscreens), int(window), int(bool(monotonize)), _ptr(data)))

@@ -218,6 +218,7 @@ void jacks_ctx_destroy(JacksCtx* c) {
     for (auto& b : c->out) b.release();
     c->tmp.release();
     c->kde_tail.release();
+    c->pre.release();
     c->stager.release();
     if (c->cmp_stage) cudaFreeHost(c->cmp_stage);
     if (c->cmp_ready) cudaEventDestroy(c->cmp_ready);

@@ -69,12 +69,14 @@ struct JacksCtx {
     bool res_valid = false;
     jacks::DevBuf out[8];       // device-side outputs of the host entry points
     jacks::DevBuf tmp;          // scratch of the p-value / preprocessing entry points
+    jacks::DevBuf pre;          // scratch of the preprocessing cores (sort keys, prefix sums)
     jacks::DevBuf kde_tail;     // queue of far-lower-tail evaluation points of the p-value kernels
     // compact cubes of JACKS_UPLOAD_USED_ROWS calls: pinned staging, device copy, "upload enqueued" event
     void* cmp_stage = nullptr; size_t cmp_stage_cap = 0;
     jacks::DevBuf cmp_dev, cmp_rows;
     cudaEvent_t cmp_ready = nullptr;     // the compact upload has read its pinned staging
     cudaEvent_t cmp_done = nullptr;      // the kernels of the last compact run have read the device cube
+    bool pre_attr_set = false;  // the radix sort's shared-memory attribute has been set on this device
     bool kde_attr_set = false;  // the KDE's derivative table and kernel attributes have been set up on this device
     HostStager stager;          // pinned ring of the synchronous host entry points (pageable caller buffers)
     std::vector<PlanBufs*> plan_pool;          // recycled plan buffers

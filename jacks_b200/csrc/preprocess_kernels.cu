@@ -13,15 +13,17 @@
 //                                 sd = sqrt(m) scattered back to guide order              (:55-56)
 //
 // Everything is HBM/L2-bound integer-and-double streaming work: coalesced tiles, shared-memory staging,
-// no tensor cores.  The sort is a bitonic network on the full (mean, var, index) key -- the order is
-// total, so no stability is needed -- with all compare-exchange distances below 2048 done in shared
-// memory.  The sliding mean uses prefix sums: for w+1 <= k <= N-w-2 the reference's recurrence
+// no tensor cores.  The sort is a segmented stable LSD radix sort (11-bit digits: variance, then mean, from index
+// order).  Device entry points (jacks_normalize_device, jacks_condense_device) chain on one stream without leaving
+// the GPU; jacks_preprocess_host is the whole chain for one count table with ONE upload and ONE download.
+// The sliding mean uses prefix sums: for w+1 <= k <= N-w-2 the reference's recurrence
 // m[k] = m[k-1] + (x[k+w+1] - x[k-w])/(2w+1) telescopes to
 // m[w] + (P[k+w+2] - P[2w+2] - P[k-w+1] + P[1])/(2w+1) with P[i] = sum_{t<i} x[t] (agreement ~1e-14).
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdint.h>
 
+#include <algorithm>
 #include <vector>
 
 #include "../../include/jacks_b200.h"
@@ -263,57 +265,142 @@ __global__ void __launch_bounds__(256) sample_stats_kernel(const double* __restr
     kidx[o] = (int)i;
 }
 
-struct Key { double m, v; int i; };
-__device__ __forceinline__ bool key_less(const Key& a, const Key& b) {
-    if (a.m != b.m) return a.m < b.m;
-    if (a.v != b.v) return a.v < b.v;
-    return a.i < b.i;
+// ---- segmented stable LSD radix sort of (mean, variance, index) keys ---------------------------------------------------
+// Every sample is one segment of N keys.  The order wanted is Python's tuple order (mean, var, index), preprocess.py:39-40:
+// a stable sort by the variance followed by a stable sort by the mean, starting from index order, gives exactly that.
+// Each of the two is 6 passes over 11-bit digits of the order-preserving 64-bit image of the double; a pass is
+// histogram (per segment and chunk) -> scan -> stable scatter of (key, index) pairs, 12 bytes per element each way.
+// The first version ran a bitonic network on padded power-of-two segments: 136 compare-exchange sweeps of 20-byte
+// records over 1.8x the data, 17 ms at the Avana shape.
+constexpr int kRsBits = 11;
+constexpr int kRsBins = 1 << kRsBits;
+constexpr int kRsChunk = 4096;           // keys per CTA
+constexpr int kRsThreads = 256;
+
+__device__ __forceinline__ unsigned long long sortable_key(double v) {
+    if (v == 0.0) v = 0.0;               // -0.0 and +0.0 compare equal in the reference's tuple sort
+    return sortable(v);
 }
 
-constexpr int kSortTile = 2048;      // elements per CTA in the shared-memory phases (2048*20 B = 40 KB)
+// keys[s][i] = image of src[s][i] (or of src[s][idx[s][i]] when idx is given); idx_out[s][i] = i when asked for
+__global__ void __launch_bounds__(256) rs_load_keys(const double* __restrict__ src, const int* __restrict__ idx, long long ld, long long N,
+                                                    unsigned long long* __restrict__ keys, int* __restrict__ idx_out) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    const long long o = (long long)blockIdx.y * ld;
+    const long long from = idx ? idx[o + i] : i;
+    keys[o + i] = sortable_key(src[o + from]);
+    if (idx_out) idx_out[o + i] = (int)i;
+}
 
-// all compare-exchange steps with distance j < kSortTile for merge sizes kk = k_lo .. k_hi (powers of two)
-__global__ void __launch_bounds__(1024) bitonic_local_kernel(double* __restrict__ km, double* __restrict__ kv, int* __restrict__ ki,
-                                                             long long Np, int k_lo, int k_hi) {
-    __shared__ double sm[kSortTile];
-    __shared__ double sv[kSortTile];
-    __shared__ int si[kSortTile];
-    const long long base = (long long)blockIdx.y * Np + (long long)blockIdx.x * kSortTile;
-    for (int t = threadIdx.x; t < kSortTile; t += blockDim.x) { sm[t] = km[base + t]; sv[t] = kv[base + t]; si[t] = ki[base + t]; }
+__global__ void __launch_bounds__(kRsThreads) rs_hist(const unsigned long long* __restrict__ keys, long long ld, long long N, int shift,
+                                                      int nchunk, unsigned* __restrict__ hist) {
+    __shared__ unsigned sh[kRsBins];
+    const int s = blockIdx.y, chunk = blockIdx.x;
+    for (int c = threadIdx.x; c < kRsBins; c += kRsThreads) sh[c] = 0;
     __syncthreads();
-    const long long tile0 = (long long)blockIdx.x * kSortTile;
-    for (long long kk = k_lo; kk <= k_hi; kk <<= 1) {
-        for (int j = (int)((kk >> 1) < kSortTile ? (kk >> 1) : (kSortTile >> 1)); j > 0; j >>= 1) {
-            for (int t = threadIdx.x; t < kSortTile / 2; t += blockDim.x) {
-                const int a = ((t & ~(j - 1)) << 1) | (t & (j - 1));
-                const int b = a | j;
-                const bool up = (((tile0 + a) & kk) == 0);
-                Key ka{sm[a], sv[a], si[a]}, kb{sm[b], sv[b], si[b]};
-                if (key_less(kb, ka) == up) {
-                    sm[a] = kb.m; sv[a] = kb.v; si[a] = kb.i;
-                    sm[b] = ka.m; sv[b] = ka.v; si[b] = ka.i;
-                }
-            }
-            __syncthreads();
+    const unsigned long long* row = keys + (long long)s * ld;
+    const long long i1 = min(N, (long long)(chunk + 1) * kRsChunk);
+    for (long long i = (long long)chunk * kRsChunk + threadIdx.x; i < i1; i += kRsThreads)
+        atomicAdd(&sh[(unsigned)(row[i] >> shift) & (kRsBins - 1)], 1u);
+    __syncthreads();
+    unsigned* out = hist + ((long long)s * nchunk + chunk) * kRsBins;
+    for (int c = threadIdx.x; c < kRsBins; c += kRsThreads) out[c] = sh[c];
+}
+
+// one CTA per segment: hist[chunk][bin] becomes the position of the first key of (chunk, bin) in the sorted segment
+__global__ void __launch_bounds__(1024) rs_scan(int nchunk, unsigned* __restrict__ hist) {
+    __shared__ unsigned tot[kRsBins];
+    __shared__ unsigned wsum[32];
+    unsigned* h = hist + (long long)blockIdx.x * nchunk * kRsBins;
+    for (int c = threadIdx.x; c < kRsBins; c += 1024) {
+        unsigned run = 0;
+        for (int k = 0; k < nchunk; ++k) { const unsigned t = h[(long long)k * kRsBins + c]; h[(long long)k * kRsBins + c] = run; run += t; }
+        tot[c] = run;
+    }
+    __syncthreads();
+    const int c0 = 2 * threadIdx.x;
+    const unsigned a = tot[c0], b = tot[c0 + 1];
+    unsigned v = a + b;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int o = 1; o < 32; o <<= 1) { const unsigned t = __shfl_up_sync(0xffffffffu, v, o); if (lane >= o) v += t; }
+    if (lane == 31) wsum[warp] = v;
+    __syncthreads();
+    if (warp == 0) {
+        unsigned w = wsum[lane];
+        for (int o = 1; o < 32; o <<= 1) { const unsigned t = __shfl_up_sync(0xffffffffu, w, o); if (lane >= o) w += t; }
+        wsum[lane] = w;
+    }
+    __syncthreads();
+    const unsigned excl = v - (a + b) + (warp ? wsum[warp - 1] : 0u);
+    __syncthreads();
+    tot[c0] = excl;
+    tot[c0 + 1] = excl + a;
+    __syncthreads();
+    for (int c = threadIdx.x; c < kRsBins; c += 1024) {
+        const unsigned f = tot[c];
+        if (f) for (int k = 0; k < nchunk; ++k) h[(long long)k * kRsBins + c] += f;
+    }
+}
+
+// Stable scatter: warp w of the CTA owns a contiguous eighth of the chunk and walks it in order, 32 consecutive keys at
+// a time; keys of a group with equal digit take consecutive positions in lane order (match_any); the warp's running
+// count per digit (shared memory, one row per warp) carries on to the next group.
+__global__ void __launch_bounds__(kRsThreads) rs_scatter(const unsigned long long* __restrict__ kin, const int* __restrict__ iin,
+                                                         long long ld, long long N, int shift, int nchunk,
+                                                         const unsigned* __restrict__ hist, unsigned long long* __restrict__ kout,
+                                                         int* __restrict__ iout) {
+    extern __shared__ unsigned cnt[];                    // [8 warps][kRsBins]
+    const int s = blockIdx.y, chunk = blockIdx.x;
+    constexpr int W = kRsThreads / 32, SEG = kRsChunk / W;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int c = threadIdx.x; c < W * kRsBins; c += kRsThreads) cnt[c] = 0;
+    __syncthreads();
+    const long long o = (long long)s * ld;
+    const long long base = (long long)chunk * kRsChunk + warp * SEG;
+    unsigned* mine = cnt + warp * kRsBins;
+    unsigned long long key[SEG / 32];
+    int pay[SEG / 32], dig[SEG / 32];
+#pragma unroll
+    for (int k = 0; k < SEG / 32; ++k) {
+        const long long i = base + k * 32 + lane;
+        dig[k] = -1 - lane;                               // past the end: a digit of its own, never written
+        key[k] = 0; pay[k] = 0;
+        if (i < N) {
+            key[k] = kin[o + i]; pay[k] = iin[o + i];
+            dig[k] = (int)((unsigned)(key[k] >> shift) & (kRsBins - 1));
+            atomicAdd(&mine[dig[k]], 1u);
         }
     }
-    for (int t = threadIdx.x; t < kSortTile; t += blockDim.x) { km[base + t] = sm[t]; kv[base + t] = sv[t]; ki[base + t] = si[t]; }
+    __syncthreads();
+    const unsigned* hb = hist + ((long long)s * nchunk + chunk) * kRsBins;
+    for (int c = threadIdx.x; c < kRsBins; c += kRsThreads) {
+        unsigned run = hb[c];
+        for (int w = 0; w < W; ++w) { const unsigned t = cnt[w * kRsBins + c]; cnt[w * kRsBins + c] = run; run += t; }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < SEG / 32; ++k) {
+        const unsigned peers = __match_any_sync(0xffffffffu, dig[k]);
+        const int leader = __ffs(peers) - 1;
+        const int rank = __popc(peers & ((1u << lane) - 1));
+        unsigned old = 0;
+        if (lane == leader && dig[k] >= 0) { old = mine[dig[k]]; mine[dig[k]] = old + __popc(peers); }
+        old = __shfl_sync(0xffffffffu, old, leader);
+        if (dig[k] >= 0) { kout[o + old + rank] = key[k]; iout[o + old + rank] = pay[k]; }
+        __syncwarp();
+    }
 }
 
-// one compare-exchange step with distance j >= kSortTile
-__global__ void __launch_bounds__(256) bitonic_global_kernel(double* __restrict__ km, double* __restrict__ kv, int* __restrict__ ki,
-                                                             long long Np, long long kk, long long j) {
-    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= Np / 2) return;
-    const long long base = (long long)blockIdx.y * Np;
-    const long long a = ((t & ~(j - 1)) << 1) | (t & (j - 1));
-    const long long b = a | j;
-    const bool up = ((a & kk) == 0);
-    Key ka{km[base + a], kv[base + a], ki[base + a]}, kb{km[base + b], kv[base + b], ki[base + b]};
-    if (key_less(kb, ka) == up) {
-        km[base + a] = kb.m; kv[base + a] = kb.v; ki[base + a] = kb.i;
-        km[base + b] = ka.m; kv[base + b] = ka.v; ki[base + b] = ka.i;
-    }
+// sorted copies: dm[k] = km[idx[k]], dv[k] = kv[idx[k]]
+__global__ void __launch_bounds__(256) rs_gather_sorted(const double* __restrict__ km, const double* __restrict__ kv, const int* __restrict__ idx,
+                                                        long long ld, long long N, double* __restrict__ dm, double* __restrict__ dv) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    const long long o = (long long)blockIdx.y * ld;
+    const int from = idx[o + i];
+    dm[o + i] = km[o + from];
+    dv[o + i] = kv[o + from];
 }
 
 // ---- sliding mean (shifted, as the reference), reverse running max, sqrt, scatter ----------------
@@ -504,6 +591,226 @@ __global__ void __launch_bounds__(kScanThreads) subset_sd_kernel(const double* _
 
 using namespace jacks;
 
+namespace jacks {
+namespace {
+
+// Bump allocator over a grow-only device buffer (256-byte aligned pieces).
+struct Arena {
+    size_t off = 0;
+    size_t take(size_t bytes) { const size_t o = off; off += (bytes + 255) & ~(size_t)255; return o; }
+};
+
+__global__ void __launch_bounds__(256) permute_rows_kernel(const double* __restrict__ in, const long long* __restrict__ order, long long N,
+                                                           int C, double* __restrict__ out) {
+    const long long r = blockIdx.x;
+    const double* src = in + order[r] * C;
+    double* dst = out + r * C;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) dst[c] = src[c];
+}
+
+// normalizeLogCounts on device buffers (preprocess.py:77-96), optionally fused with log2(count + prior) (:147).
+// Scratch: ctx->tmp ([C][N] transposed copy + per-column statistics).
+int normalize_core(JacksCtx* ctx, const double* d_values, long long N, int C, int take_log, double prior, const double* d_table,
+                   long long table_len, int normtype, const unsigned char* d_mask, double* d_out, cudaStream_t st) {
+    int rc;
+    if ((rc = ctx->tmp.reserve((size_t)N * C * sizeof(double) + 2 * (size_t)C * sizeof(double))) != JACKS_OK) return rc;
+    double* T = (double*)ctx->tmp.p;
+    double* med = T + (size_t)N * C;
+    double* mad = med + C;
+    dim3 tg((unsigned)((N + 31) / 32), (unsigned)((C + 31) / 32));
+    log_transpose_kernel<<<tg, 256, 0, st>>>(d_values, N, C, prior, take_log ? 1 : 0, table_len ? d_table : nullptr, table_len, T, N);
+    if (normtype == JACKS_NORM_MODE) column_mode_kernel<<<C, 1024, 0, st>>>(T, N, N, med);          // preprocess.py:85-91
+    else column_median_kernel<<<C, 1024, 0, st>>>(T, N, N, d_mask, nullptr, 0, med);             // preprocess.py:81 / :93
+    ctx->launches += 2;
+    const double* scale = nullptr;
+    if (normtype == JACKS_NORM_ZMAD) {                                                            // preprocess.py:82-84
+        column_median_kernel<<<C, 1024, 0, st>>>(T, N, N, nullptr, med, 1, mad);
+        scale_mad_kernel<<<(C + 255) / 256, 256, 0, st>>>(mad, C);
+        scale = mad;
+        ctx->launches += 2;
+    }
+    untranspose_shift_kernel<<<tg, 256, 0, st>>>(T, N, N, C, med, scale, d_out);
+    ctx->launches++;
+    const cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_fail(e, "normalize kernels");
+    return JACKS_OK;
+}
+
+// Sort every segment's (mean, var, index) keys: on return km_s / kv_s / ki_s hold the sorted keys.  Scratch from `base`.
+struct SortScratch { unsigned long long* kA; unsigned long long* kB; int* iA; int* iB; unsigned* hist; };
+size_t sort_scratch_bytes(int S, long long ld, Arena* a, size_t o[5]) {
+    const int nchunk = (int)((ld + kRsChunk - 1) / kRsChunk);
+    o[0] = a->take((size_t)S * ld * 8); o[1] = a->take((size_t)S * ld * 8);
+    o[2] = a->take((size_t)S * ld * 4); o[3] = a->take((size_t)S * ld * 4);
+    o[4] = a->take((size_t)S * nchunk * kRsBins * 4);
+    return a->off;
+}
+int sort_mean_var(JacksCtx* ctx, cudaStream_t st, const double* km, const double* kv, int S, long long ld, long long N,
+                  const SortScratch& w, double* km_s, double* kv_s, int** ki_sorted) {
+    cudaError_t e;
+    if (!ctx->pre_attr_set) {              // per device
+        if ((e = cudaFuncSetAttribute(rs_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, kRsThreads / 32 * kRsBins * 4)) != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute");
+        ctx->pre_attr_set = true;
+    }
+    const int nchunk = (int)((N + kRsChunk - 1) / kRsChunk);
+    dim3 eg((unsigned)((N + 255) / 256), (unsigned)S), cg((unsigned)nchunk, (unsigned)S);
+    unsigned long long* kin = w.kA; unsigned long long* kout = w.kB;
+    int* iin = w.iA; int* iout = w.iB;
+    for (int which = 0; which < 2; ++which) {              // stable by variance, then stable by mean
+        rs_load_keys<<<eg, 256, 0, st>>>(which == 0 ? kv : km, which == 0 ? nullptr : iin, ld, N, kin, which == 0 ? iin : nullptr);
+        ctx->launches++;
+        for (int shift = 0; shift < 64; shift += kRsBits) {
+            rs_hist<<<cg, kRsThreads, 0, st>>>(kin, ld, N, shift, nchunk, w.hist);
+            rs_scan<<<S, 1024, 0, st>>>(nchunk, w.hist);
+            rs_scatter<<<cg, kRsThreads, kRsThreads / 32 * kRsBins * 4, st>>>(kin, iin, ld, N, shift, nchunk, w.hist, kout, iout);
+            ctx->launches += 3;
+            std::swap(kin, kout); std::swap(iin, iout);
+        }
+    }
+    rs_gather_sorted<<<eg, 256, 0, st>>>(km, kv, iin, ld, N, km_s, kv_s);
+    ctx->launches++;
+    if ((e = cudaGetLastError()) != cudaSuccess) return cuda_fail(e, "sort kernels");
+    *ki_sorted = iin;
+    return JACKS_OK;
+}
+
+// condense_normalised_counts on device buffers (preprocess.py:61-67); h_off / h_cols are host arrays (small).
+int condense_core(JacksCtx* ctx, const double* d_lc, long long N, int C, const int32_t* h_off, const int32_t* h_cols, int S,
+                  long long window, int monotonize, int max_rep, double* d_data, cudaStream_t st) {
+    const long long ld = (N + 31) / 32 * 32;
+    const size_t nidx = (size_t)h_off[S];
+    Arena a;
+    const size_t o_km = a.take((size_t)S * ld * 8), o_kv = a.take((size_t)S * ld * 8), o_ki = a.take((size_t)S * ld * 4);
+    const size_t o_kms = a.take((size_t)S * ld * 8), o_kvs = a.take((size_t)S * ld * 8);
+    const size_t o_P = a.take((size_t)S * (ld + 1) * 8), o_M = a.take((size_t)S * ld * 8);
+    const size_t o_idx = a.take((S + 1 + nidx) * sizeof(int));
+    size_t so[5];
+    sort_scratch_bytes(S, ld, &a, so);
+    int rc;
+    if ((rc = ctx->pre.reserve(a.off)) != JACKS_OK) return rc;
+    char* base = (char*)ctx->pre.p;
+    double* km = (double*)(base + o_km); double* kv = (double*)(base + o_kv); int* ki = (int*)(base + o_ki);
+    double* kms = (double*)(base + o_kms); double* kvs = (double*)(base + o_kvs);
+    int* d_off = (int*)(base + o_idx);
+    int* d_cols = d_off + S + 1;
+    cudaError_t e;
+    if ((e = cudaMemcpyAsync(d_off, h_off, (S + 1) * sizeof(int), cudaMemcpyHostToDevice, st)) != cudaSuccess) return cuda_fail(e, "H2D offsets");
+    if ((e = cudaMemcpyAsync(d_cols, h_cols, nidx * sizeof(int), cudaMemcpyHostToDevice, st)) != cudaSuccess) return cuda_fail(e, "H2D cols");
+    dim3 sg((unsigned)((ld + 255) / 256), (unsigned)S);
+    sample_stats_kernel<<<sg, 256, 0, st>>>(d_lc, N, C, d_off, d_cols, S, ld, d_data, km, kv, ki);
+    ctx->launches++;
+    if (max_rep >= 2) {
+        SortScratch w{(unsigned long long*)(base + so[0]), (unsigned long long*)(base + so[1]), (int*)(base + so[2]), (int*)(base + so[3]),
+                      (unsigned*)(base + so[4])};
+        int* kis = nullptr;
+        if ((rc = sort_mean_var(ctx, st, km, kv, S, ld, N, w, kms, kvs, &kis)) != JACKS_OK) return rc;
+        smooth_monotone_scatter_kernel<<<S, kScanThreads, 0, st>>>(kvs, kis, ld, N, S, (int)window, monotonize ? 1 : 0, d_off,
+                                                                   (double*)(base + o_P), (double*)(base + o_M), d_data);
+        ctx->launches++;
+    }
+    if ((e = cudaGetLastError()) != cudaSuccess) return cuda_fail(e, "condense kernels");
+    return JACKS_OK;
+}
+
+int check_samples(const int32_t* off, const int32_t* cols, int S, int n_cols, long long N, int window_override, long long* window, int* max_rep) {
+    *max_rep = 0;
+    for (int s = 0; s < S; ++s) {
+        const int R = off[s + 1] - off[s];
+        if (R < 1) return fail(JACKS_E_INVALID, "sample %d has no replicate columns", s);
+        for (int r = off[s]; r < off[s + 1]; ++r)
+            if (cols[r] < 0 || cols[r] >= n_cols) return fail(JACKS_E_INVALID, "column index out of range");
+        *max_rep = R > *max_rep ? R : *max_rep;
+    }
+    // window = min(max(int(N/100), 30), 800), preprocess.py:35
+    long long w = N / 100;
+    if (w < 30) w = 30;
+    if (w > 800) w = 800;
+    if (window_override > 0) w = window_override;
+    if (*max_rep >= 2 && N < w + 1)      // the reference's window_smooth indexes m[0..window]: IndexError below that
+        return fail(JACKS_E_INVALID, "calc_posterior_sd needs at least %lld guides for its smoothing window (got %lld)", w + 1, N);
+    *window = w;
+    return JACKS_OK;
+}
+
+}  // namespace
+}  // namespace jacks
+
+extern "C" int jacks_normalize_device(JacksCtx* ctx, const double* values, int64_t n_guides, int32_t n_cols, int32_t take_log,
+                                      double prior, const double* log2_table, int64_t table_len, int32_t normtype,
+                                      const uint8_t* row_mask, double* out, void* stream) {
+    if (!ctx || !values || !out) return fail(JACKS_E_INVALID, "jacks_normalize_device: NULL argument");
+    if (n_guides < 1 || n_cols < 1) return fail(JACKS_E_INVALID, "empty matrix");
+    if (normtype < JACKS_NORM_MEDIAN || normtype > JACKS_NORM_MODE) return fail(JACKS_E_INVALID, "Unrecognised normalisation type %d", normtype);
+    if (normtype == JACKS_NORM_CTRL_GUIDES && !row_mask) return fail(JACKS_E_INVALID, "No guides specified for ctrl guide normalization");
+    if (!log2_table || !take_log) table_len = 0;
+    if (table_len < 0) return fail(JACKS_E_INVALID, "table_len < 0");
+    cudaError_t e = cudaSetDevice(ctx->device);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaSetDevice");
+    return normalize_core(ctx, values, n_guides, n_cols, take_log, prior, log2_table, table_len, normtype,
+                          normtype == JACKS_NORM_CTRL_GUIDES ? row_mask : nullptr, out, (cudaStream_t)stream);
+}
+
+extern "C" int jacks_condense_device(JacksCtx* ctx, const double* logcounts, int64_t n_guides, int32_t n_cols,
+                                     const int32_t* sample_col_offsets, const int32_t* sample_cols, int32_t n_samples,
+                                     int32_t window_override, int32_t monotonize, double* data, void* stream) {
+    if (!ctx || !logcounts || !sample_col_offsets || !sample_cols || !data) return fail(JACKS_E_INVALID, "jacks_condense_device: NULL argument");
+    if (n_guides < 1 || n_cols < 1 || n_samples < 1) return fail(JACKS_E_INVALID, "empty input");
+    long long window; int max_rep;
+    int rc = check_samples(sample_col_offsets, sample_cols, n_samples, n_cols, n_guides, window_override, &window, &max_rep);
+    if (rc != JACKS_OK) return rc;
+    cudaError_t e = cudaSetDevice(ctx->device);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaSetDevice");
+    return condense_core(ctx, logcounts, n_guides, n_cols, sample_col_offsets, sample_cols, n_samples, window, monotonize, max_rep, data,
+                         (cudaStream_t)stream);
+}
+
+extern "C" int jacks_preprocess_host(JacksCtx* ctx, const double* counts, int64_t n_guides, int32_t n_cols, int32_t take_log,
+                                     double prior, const double* log2_table, int64_t table_len, int32_t normtype,
+                                     const uint8_t* row_mask, const int64_t* row_order, const int32_t* sample_col_offsets,
+                                     const int32_t* sample_cols, int32_t n_samples, int32_t window_override, int32_t monotonize,
+                                     double* logcounts_out, double* data) {
+    if (!ctx || !counts || !sample_col_offsets || !sample_cols || !data) return fail(JACKS_E_INVALID, "jacks_preprocess_host: NULL argument");
+    if (n_guides < 1 || n_cols < 1 || n_samples < 1) return fail(JACKS_E_INVALID, "empty input");
+    if (normtype < JACKS_NORM_MEDIAN || normtype > JACKS_NORM_MODE) return fail(JACKS_E_INVALID, "Unrecognised normalisation type %d", normtype);
+    if (normtype == JACKS_NORM_CTRL_GUIDES && !row_mask) return fail(JACKS_E_INVALID, "No guides specified for ctrl guide normalization");
+    if (!log2_table || !take_log) table_len = 0;
+    if (table_len < 0) return fail(JACKS_E_INVALID, "table_len < 0");
+    const long long N = n_guides;
+    const int C = n_cols, S = n_samples;
+    long long window; int max_rep;
+    int rc = check_samples(sample_col_offsets, sample_cols, S, C, N, window_override, &window, &max_rep);
+    if (rc != JACKS_OK) return rc;
+    if (row_order) for (long long i = 0; i < N; ++i) if (row_order[i] < 0 || row_order[i] >= N) return fail(JACKS_E_INVALID, "row_order out of range");
+    cudaError_t e = cudaSetDevice(ctx->device);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaSetDevice");
+    const size_t mb = (size_t)N * C * sizeof(double), db = (size_t)N * S * 2 * sizeof(double);
+    if ((rc = ctx->out[0].reserve(mb)) != JACKS_OK) return rc;                        // counts, later the row-sorted log counts
+    if ((rc = ctx->out[1].reserve(mb)) != JACKS_OK) return rc;                        // normalised log counts
+    if ((rc = ctx->out[2].reserve((size_t)table_len * sizeof(double) + 8)) != JACKS_OK) return rc;
+    if ((rc = ctx->out[3].reserve((size_t)N * 9 + 16)) != JACKS_OK) return rc;        // row order (8 B) + row mask (1 B)
+    if ((rc = ctx->out[4].reserve(db)) != JACKS_OK) return rc;
+    cudaStream_t st = ctx->stream;
+    if ((rc = ctx->stager.h2d(ctx->out[0].p, counts, mb, st)) != JACKS_OK) return rc;          // the ONE upload
+    if (table_len && (e = cudaMemcpyAsync(ctx->out[2].p, log2_table, (size_t)table_len * sizeof(double), cudaMemcpyHostToDevice, st)) != cudaSuccess) return cuda_fail(e, "H2D log2 table");
+    long long* d_order = (long long*)ctx->out[3].p;
+    unsigned char* d_mask = (unsigned char*)(d_order + N);
+    if (normtype == JACKS_NORM_CTRL_GUIDES && (e = cudaMemcpyAsync(d_mask, row_mask, (size_t)N, cudaMemcpyHostToDevice, st)) != cudaSuccess) return cuda_fail(e, "H2D row mask");
+    if ((rc = normalize_core(ctx, (const double*)ctx->out[0].p, N, C, take_log, prior, (const double*)ctx->out[2].p, table_len, normtype,
+                             normtype == JACKS_NORM_CTRL_GUIDES ? d_mask : nullptr, (double*)ctx->out[1].p, st)) != JACKS_OK) return rc;
+    const double* d_lc = (const double*)ctx->out[1].p;
+    if (row_order) {                      // the loader's sort by guide id (preprocess.py:154-157), after the normalisation
+        if ((e = cudaMemcpyAsync(d_order, row_order, (size_t)N * sizeof(long long), cudaMemcpyHostToDevice, st)) != cudaSuccess) return cuda_fail(e, "H2D row order");
+        permute_rows_kernel<<<(unsigned)N, 256, 0, st>>>(d_lc, d_order, N, C, (double*)ctx->out[0].p);
+        ctx->launches++;
+        d_lc = (const double*)ctx->out[0].p;
+    }
+    if ((rc = condense_core(ctx, d_lc, N, C, sample_col_offsets, sample_cols, S, window, monotonize, max_rep, (double*)ctx->out[4].p, st)) != JACKS_OK) return rc;
+    if (logcounts_out && (rc = ctx->stager.d2h(logcounts_out, d_lc, mb, st)) != JACKS_OK) return rc;
+    if ((rc = ctx->stager.d2h(data, ctx->out[4].p, db, st)) != JACKS_OK) return rc;
+    if ((e = cudaStreamSynchronize(st)) != cudaSuccess) return cuda_fail(e, "preprocess kernels");
+    return JACKS_OK;
+}
+
 extern "C" int jacks_normalize_host(JacksCtx* ctx, const double* values, int64_t n_guides, int32_t n_cols, int32_t take_log,
                                     double prior, const double* log2_table, int64_t table_len, int32_t normtype,
                                     const uint8_t* row_mask, double* out) {
@@ -523,7 +830,6 @@ extern "C" int jacks_normalize_host(JacksCtx* ctx, const double* values, int64_t
     if ((rc = ctx->out[1].reserve(mb)) != JACKS_OK) return rc;
     if ((rc = ctx->out[2].reserve((size_t)table_len * sizeof(double) + 8)) != JACKS_OK) return rc;
     if ((rc = ctx->out[3].reserve((size_t)N + 8)) != JACKS_OK) return rc;
-    if ((rc = ctx->tmp.reserve(mb + 2 * (size_t)C * sizeof(double))) != JACKS_OK) return rc;
     cudaStream_t st = ctx->stream;
     if ((rc = ctx->stager.h2d(ctx->out[0].p, values, mb, st)) != JACKS_OK) return rc;
     if (table_len && (e = cudaMemcpyAsync(ctx->out[2].p, log2_table, (size_t)table_len * sizeof(double), cudaMemcpyHostToDevice, st)) != cudaSuccess) return cuda_fail(e, "H2D log2 table");
@@ -532,25 +838,8 @@ extern "C" int jacks_normalize_host(JacksCtx* ctx, const double* values, int64_t
         if ((e = cudaMemcpyAsync(ctx->out[3].p, row_mask, (size_t)N, cudaMemcpyHostToDevice, st)) != cudaSuccess) return cuda_fail(e, "H2D row mask");
         d_mask = (const unsigned char*)ctx->out[3].p;
     }
-    double* T = (double*)ctx->tmp.p;
-    double* med = T + (size_t)N * C;
-    double* mad = med + C;
-    dim3 tg((unsigned)((N + 31) / 32), (unsigned)((C + 31) / 32));
-    log_transpose_kernel<<<tg, 256, 0, st>>>((const double*)ctx->out[0].p, N, C, prior, take_log ? 1 : 0,
-                                             table_len ? (const double*)ctx->out[2].p : nullptr, table_len, T, N);
-    if (normtype == JACKS_NORM_MODE) column_mode_kernel<<<C, 1024, 0, st>>>(T, N, N, med);          // preprocess.py:85-91
-    else column_median_kernel<<<C, 1024, 0, st>>>(T, N, N, d_mask, nullptr, 0, med);             // preprocess.py:81 / :93
-    ctx->launches += 2;
-    const double* scale = nullptr;
-    if (normtype == JACKS_NORM_ZMAD) {                                                            // preprocess.py:82-84
-        column_median_kernel<<<C, 1024, 0, st>>>(T, N, N, nullptr, med, 1, mad);
-        scale_mad_kernel<<<(C + 255) / 256, 256, 0, st>>>(mad, C);
-        scale = mad;
-        ctx->launches += 2;
-    }
-    untranspose_shift_kernel<<<tg, 256, 0, st>>>(T, N, N, C, med, scale, (double*)ctx->out[1].p);
-    ctx->launches++;
-    if ((e = cudaGetLastError()) != cudaSuccess) return cuda_fail(e, "normalize kernels");
+    if ((rc = normalize_core(ctx, (const double*)ctx->out[0].p, N, C, take_log, prior, (const double*)ctx->out[2].p, table_len, normtype, d_mask,
+                             (double*)ctx->out[1].p, st)) != JACKS_OK) return rc;
     if ((rc = ctx->stager.d2h(out, ctx->out[1].p, mb, st)) != JACKS_OK) return rc;
     if ((e = cudaStreamSynchronize(st)) != cudaSuccess) return cuda_fail(e, "normalize kernels");
     return JACKS_OK;
@@ -563,65 +852,18 @@ extern "C" int jacks_condense_host(JacksCtx* ctx, const double* logcounts, int64
     if (n_guides < 1 || n_cols < 1 || n_samples < 1) return fail(JACKS_E_INVALID, "empty input");
     const long long N = n_guides;
     const int S = n_samples;
-    int max_rep = 0;
-    for (int s = 0; s < S; ++s) {
-        const int R = sample_col_offsets[s + 1] - sample_col_offsets[s];
-        if (R < 1) return fail(JACKS_E_INVALID, "sample %d has no replicate columns", s);
-        for (int r = sample_col_offsets[s]; r < sample_col_offsets[s + 1]; ++r)
-            if (sample_cols[r] < 0 || sample_cols[r] >= n_cols) return fail(JACKS_E_INVALID, "column index out of range");
-        max_rep = R > max_rep ? R : max_rep;
-    }
-    // window = min(max(int(N/100), 30), 800), preprocess.py:35
-    long long window = N / 100;
-    if (window < 30) window = 30;
-    if (window > 800) window = 800;
-    if (window_override > 0) window = window_override;
-    if (max_rep >= 2 && N < window + 1)      // the reference's window_smooth indexes m[0..window]: IndexError below that
-        return fail(JACKS_E_INVALID, "calc_posterior_sd needs at least %lld guides for its smoothing window (got %lld)", window + 1, N);
+    long long window; int max_rep;
+    int rc = check_samples(sample_col_offsets, sample_cols, S, n_cols, N, window_override, &window, &max_rep);
+    if (rc != JACKS_OK) return rc;
     cudaError_t e = cudaSetDevice(ctx->device);
     if (e != cudaSuccess) return cuda_fail(e, "cudaSetDevice");
-    long long Np = kSortTile;
-    while (Np < N) Np <<= 1;
     const size_t lb = (size_t)N * n_cols * sizeof(double), db = (size_t)N * S * 2 * sizeof(double);
-    const size_t nidx = (size_t)sample_col_offsets[S];
-    int rc;
     if ((rc = ctx->out[0].reserve(lb)) != JACKS_OK) return rc;
     if ((rc = ctx->out[1].reserve(db)) != JACKS_OK) return rc;
-    if ((rc = ctx->out[2].reserve((size_t)S * Np * sizeof(double))) != JACKS_OK) return rc;       // key: mean
-    if ((rc = ctx->out[3].reserve((size_t)S * Np * sizeof(double))) != JACKS_OK) return rc;       // key: var -> sorted var
-    if ((rc = ctx->out[4].reserve((size_t)S * Np * sizeof(int))) != JACKS_OK) return rc;          // key: index
-    if ((rc = ctx->out[5].reserve((size_t)S * (Np + 1) * sizeof(double))) != JACKS_OK) return rc; // prefix sums
-    if ((rc = ctx->out[6].reserve((size_t)S * Np * sizeof(double))) != JACKS_OK) return rc;       // smoothed
-    if ((rc = ctx->out[7].reserve((S + 1 + nidx) * sizeof(int))) != JACKS_OK) return rc;
     cudaStream_t st = ctx->stream;
-    int* d_off = (int*)ctx->out[7].p;
-    int* d_cols = d_off + S + 1;
     if ((rc = ctx->stager.h2d(ctx->out[0].p, logcounts, lb, st)) != JACKS_OK) return rc;
-    if ((e = cudaMemcpyAsync(d_off, sample_col_offsets, (S + 1) * sizeof(int), cudaMemcpyHostToDevice, st)) != cudaSuccess) return cuda_fail(e, "H2D offsets");
-    if ((e = cudaMemcpyAsync(d_cols, sample_cols, nidx * sizeof(int), cudaMemcpyHostToDevice, st)) != cudaSuccess) return cuda_fail(e, "H2D cols");
-    double* km = (double*)ctx->out[2].p; double* kv = (double*)ctx->out[3].p; int* ki = (int*)ctx->out[4].p;
-    dim3 sg((unsigned)((Np + 255) / 256), (unsigned)S);
-    sample_stats_kernel<<<sg, 256, 0, st>>>((const double*)ctx->out[0].p, N, n_cols, d_off, d_cols, S, Np, (double*)ctx->out[1].p, km, kv, ki);
-    ctx->launches++;
-    if (max_rep >= 2) {
-        // bitonic sort of every sample's Np keys: shared-memory phases for distances < kSortTile
-        dim3 lg((unsigned)(Np / kSortTile), (unsigned)S);
-        bitonic_local_kernel<<<lg, 1024, 0, st>>>(km, kv, ki, Np, 2, kSortTile);
-        ctx->launches++;
-        for (long long kk = 2LL * kSortTile; kk <= Np; kk <<= 1) {
-            for (long long j = kk >> 1; j >= kSortTile; j >>= 1) {
-                dim3 gg((unsigned)((Np / 2 + 255) / 256), (unsigned)S);
-                bitonic_global_kernel<<<gg, 256, 0, st>>>(km, kv, ki, Np, kk, j);
-                ctx->launches++;
-            }
-            bitonic_local_kernel<<<lg, 1024, 0, st>>>(km, kv, ki, Np, (int)kk, (int)kk);
-            ctx->launches++;
-        }
-        smooth_monotone_scatter_kernel<<<S, kScanThreads, 0, st>>>(kv, ki, Np, N, S, (int)window, monotonize ? 1 : 0, d_off, (double*)ctx->out[5].p,
-                                                                   (double*)ctx->out[6].p, (double*)ctx->out[1].p);
-        ctx->launches++;
-    }
-    if ((e = cudaGetLastError()) != cudaSuccess) return cuda_fail(e, "condense kernels");
+    if ((rc = condense_core(ctx, (const double*)ctx->out[0].p, N, n_cols, sample_col_offsets, sample_cols, S, window, monotonize, max_rep,
+                            (double*)ctx->out[1].p, st)) != JACKS_OK) return rc;
     if ((rc = ctx->stager.d2h(data, ctx->out[1].p, db, st)) != JACKS_OK) return rc;
     if ((e = cudaStreamSynchronize(st)) != cudaSuccess) return cuda_fail(e, "condense kernels");
     return JACKS_OK;
@@ -639,18 +881,21 @@ extern "C" int jacks_posterior_sd_subset_host(JacksCtx* ctx, const double* data,
         return fail(JACKS_E_INVALID, "calc_posterior_sd needs at least %d subset guides for its smoothing window (got %lld)", window + 1, members);
     cudaError_t e = cudaSetDevice(ctx->device);
     if (e != cudaSuccess) return cuda_fail(e, "cudaSetDevice");
-    long long Np = kSortTile;
-    while (Np < N) Np <<= 1;
+    const long long Np = (N + 31) / 32 * 32;
     int rc;
     const size_t lb = (size_t)N * n_rep * sizeof(double);
     if ((rc = ctx->out[0].reserve(lb)) != JACKS_OK) return rc;
     if ((rc = ctx->out[1].reserve((size_t)N * 2 * sizeof(double))) != JACKS_OK) return rc;       // data plane of sample_stats
-    if ((rc = ctx->out[2].reserve((size_t)Np * sizeof(double))) != JACKS_OK) return rc;
-    if ((rc = ctx->out[3].reserve((size_t)Np * sizeof(double))) != JACKS_OK) return rc;
+    if ((rc = ctx->out[2].reserve((size_t)Np * 2 * sizeof(double))) != JACKS_OK) return rc;      // means: keys, sorted
+    if ((rc = ctx->out[3].reserve((size_t)Np * 2 * sizeof(double))) != JACKS_OK) return rc;      // variances: keys, sorted
     if ((rc = ctx->out[4].reserve((size_t)Np * sizeof(int))) != JACKS_OK) return rc;
     if ((rc = ctx->out[5].reserve((size_t)(N + 1) * 4 * sizeof(double))) != JACKS_OK) return rc;  // sub_mean, sub_var, P, M
     if ((rc = ctx->out[6].reserve((size_t)N * sizeof(double))) != JACKS_OK) return rc;            // sd
     if ((rc = ctx->out[7].reserve((size_t)(2 + n_rep) * sizeof(int) + (size_t)N + 16)) != JACKS_OK) return rc;
+    Arena ar;
+    size_t so[5];
+    sort_scratch_bytes(1, Np, &ar, so);
+    if ((rc = ctx->pre.reserve(ar.off)) != JACKS_OK) return rc;
     cudaStream_t st = ctx->stream;
     std::vector<int> h(2 + n_rep);
     h[0] = 0; h[1] = n_rep;
@@ -661,20 +906,17 @@ extern "C" int jacks_posterior_sd_subset_host(JacksCtx* ctx, const double* data,
     if ((rc = ctx->stager.h2d(ctx->out[0].p, data, lb, st)) != JACKS_OK) return rc;
     if ((e = cudaMemcpyAsync(d_off, h.data(), h.size() * sizeof(int), cudaMemcpyHostToDevice, st)) != cudaSuccess) return cuda_fail(e, "H2D index");
     if ((e = cudaMemcpyAsync(d_set, in_set, (size_t)N, cudaMemcpyHostToDevice, st)) != cudaSuccess) return cuda_fail(e, "H2D subset");
-    double* km = (double*)ctx->out[2].p; double* kv = (double*)ctx->out[3].p; int* ki = (int*)ctx->out[4].p;
+    double* km0 = (double*)ctx->out[2].p; double* kv0 = (double*)ctx->out[3].p;
+    double* km = km0 + Np; double* kv = kv0 + Np;
+    int* ki = nullptr;
     dim3 sg((unsigned)((Np + 255) / 256), 1);
-    sample_stats_kernel<<<sg, 256, 0, st>>>((const double*)ctx->out[0].p, N, n_rep, d_off, d_cols, 1, Np, (double*)ctx->out[1].p, km, kv, ki);
-    dim3 lg((unsigned)(Np / kSortTile), 1);
-    bitonic_local_kernel<<<lg, 1024, 0, st>>>(km, kv, ki, Np, 2, kSortTile);
-    ctx->launches += 2;
-    for (long long kk = 2LL * kSortTile; kk <= Np; kk <<= 1) {
-        for (long long j = kk >> 1; j >= kSortTile; j >>= 1) {
-            dim3 gg((unsigned)((Np / 2 + 255) / 256), 1);
-            bitonic_global_kernel<<<gg, 256, 0, st>>>(km, kv, ki, Np, kk, j);
-            ctx->launches++;
-        }
-        bitonic_local_kernel<<<lg, 1024, 0, st>>>(km, kv, ki, Np, (int)kk, (int)kk);
-        ctx->launches++;
+    sample_stats_kernel<<<sg, 256, 0, st>>>((const double*)ctx->out[0].p, N, n_rep, d_off, d_cols, 1, Np, (double*)ctx->out[1].p, km0, kv0, (int*)ctx->out[4].p);
+    ctx->launches++;
+    {
+        char* base = (char*)ctx->pre.p;
+        SortScratch w{(unsigned long long*)(base + so[0]), (unsigned long long*)(base + so[1]), (int*)(base + so[2]), (int*)(base + so[3]),
+                      (unsigned*)(base + so[4])};
+        if ((rc = sort_mean_var(ctx, st, km0, kv0, 1, Np, N, w, km, kv, &ki)) != JACKS_OK) return rc;
     }
     double* scratch = (double*)ctx->out[5].p;
     subset_sd_kernel<<<1, kScanThreads, 0, st>>>(km, kv, ki, N, d_set, window, monotonize ? 1 : 0, scratch, scratch + (N + 1),

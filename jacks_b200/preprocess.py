@@ -170,6 +170,8 @@ def loadDataAndPreprocess(sample_spec, gene_spec, ctrl_spec={}, ctrl_geneset=set
         raise Exception('Unrecognised normalisation type %s' % normtype)
     ctx = _native.context(0)
     samples, sample_counts, metas = [], [], []
+    single = (len(sample_spec) == 1)          # one count table (the command line): the whole chain in one GPU call
+    data = None
     for filename in sample_spec:
         delim = ',' if (filename.split('.')[-1] == 'csv') else '\t'
         samples.extend([sample_id for sample_id, colname in sample_spec[filename]])
@@ -186,19 +188,28 @@ def loadDataAndPreprocess(sample_spec, gene_spec, ctrl_spec={}, ctrl_geneset=set
             mask = np.zeros(len(meta), dtype=np.uint8)
             mask[idx] = 1
         LOG.info('Applying %s normalisation' % normtype)
-        counts = _native.normalize_host(ctx, raw, normtype, take_log=True, prior=prior, row_mask=mask)
         meta = np.array(meta)
         order = np.argsort(meta[:, 0])
+        if single and len(meta) > 0:
+            # log2 + normalisation + row sort + condense on the device: the counts go up once, the cube comes down once
+            sample_ids = sorted(set(samples))
+            Iscreens = [[col_idx for col_idx, x in enumerate(samples) if x == sample_id] for sample_id in sample_ids]
+            data, _ = _native.preprocess_host(ctx, raw, Iscreens, normtype=normtype, prior=prior, row_mask=mask, row_order=order)
+            meta = meta[order, :]
+            metas.append(meta)
+            break
+        counts = _native.normalize_host(ctx, raw, normtype, take_log=True, prior=prior, row_mask=mask)
         meta, counts = meta[order, :], counts[order, :]
         metas.append(meta)
         sample_counts.append(counts + 0.0)
         if len(metas) > 1 and not (metas[0] == meta).all():
             raise Exception('Incompatible gRNAs in file %s e.g gRNA naming or order does not match other files' % filename)
-    counts = np.concatenate(sample_counts, axis=1)
 
     sample_ids = sorted(set(samples))
-    Iscreens = [[col_idx for col_idx, x in enumerate(samples) if x == sample_id] for sample_id in sample_ids]
-    data = condense_normalised_counts(counts, Iscreens, sample_ids)
+    if data is None:
+        counts = np.concatenate(sample_counts, axis=1)
+        Iscreens = [[col_idx for col_idx, x in enumerate(samples) if x == sample_id] for sample_id in sample_ids]
+        data = condense_normalised_counts(counts, Iscreens, sample_ids)
     genes, gene_guides = compute_extras(meta, sample_ids)
     data = inferMissingVariances(data, meta, sample_ids, ctrl_spec, ctrl_geneset)
     return data, meta, sample_ids, genes, gene_guides
