@@ -203,6 +203,7 @@ int jacks_ctx_create(int device, JacksCtx** out) {
     if ((e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)) != cudaSuccess) { delete c; return cuda_fail(e, "cudaStreamCreate"); }
     if ((e = cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking)) != cudaSuccess) { delete c; return cuda_fail(e, "cudaStreamCreate"); }
     if ((e = cudaStreamCreateWithFlags(&c->out_stream, cudaStreamNonBlocking)) != cudaSuccess) { delete c; return cuda_fail(e, "cudaStreamCreate"); }
+    if ((e = cudaStreamCreateWithFlags(&c->plan_stream, cudaStreamNonBlocking)) != cudaSuccess) { delete c; return cuda_fail(e, "cudaStreamCreate"); }
     *out = c;
     return JACKS_OK;
 }
@@ -227,6 +228,8 @@ void jacks_ctx_destroy(JacksCtx* c) {
     if (c->stream) cudaStreamDestroy(c->stream);
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     if (c->out_stream) cudaStreamDestroy(c->out_stream);
+    if (c->plan_stream) cudaStreamDestroy(c->plan_stream);
+    if (c->res_busy) cudaEventDestroy(c->res_busy);
     delete c;
 }
 
@@ -342,7 +345,7 @@ int jacks_em_plan_create(JacksCtx* ctx, const int64_t* gene_offsets, const int32
         if (rc != JACKS_OK) return;
         rc = b.reserve(bytes ? bytes : 8);
         if (rc == JACKS_OK && bytes) {
-            cudaError_t ee = cudaMemcpyAsync(b.p, src, bytes, cudaMemcpyHostToDevice, ctx->stream);
+            cudaError_t ee = cudaMemcpyAsync(b.p, src, bytes, cudaMemcpyHostToDevice, ctx->plan_stream);
             if (ee != cudaSuccess) rc = cuda_fail(ee, "cudaMemcpyAsync(plan)");
         }
     };
@@ -372,7 +375,9 @@ int jacks_em_plan_create(JacksCtx* ctx, const int64_t* gene_offsets, const int32
     }
     if (rc == JACKS_OK && scratch_doubles > 0) rc = p->b->d_scratch.reserve((size_t)scratch_doubles * sizeof(double));
     if (rc == JACKS_OK) {
-        e = cudaStreamSynchronize(ctx->stream);      // host vectors go out of scope
+        // host vectors go out of scope.  The index goes up on a stream of its own: waiting for it must not wait for
+        // kernels of an earlier asynchronous call (the pseudo-gene EM of a screen job) on the compute stream.
+        e = cudaStreamSynchronize(ctx->plan_stream);
         if (e != cudaSuccess) rc = cuda_fail(e, "cudaStreamSynchronize(plan)");
     }
     if (rc != JACKS_OK) { jacks_em_plan_destroy(p); return rc; }
@@ -754,10 +759,11 @@ static int em_batched_host_core(JacksCtx* ctx, const JacksEmParams* params, cons
     }
     if (rc == JACKS_OK && (e = cudaMemsetAsync(plan->b->d_counters.p, 0, kCounterInts * sizeof(int), s_k)) != cudaSuccess) rc = cuda_fail(e, "cudaMemsetAsync");
     cudaEvent_t ev_start = nullptr;
-    if (rc == JACKS_OK) {
-        // the copy streams must not run ahead of earlier work on the compute stream (previous call's kernels, memset)
-        if ((e = cudaEventCreateWithFlags(&ev_start, cudaEventDisableTiming)) != cudaSuccess) rc = cuda_fail(e, "cudaEventCreate");
-        else { cudaEventRecord(ev_start, s_k); cudaStreamWaitEvent(s_in, ev_start, 0); cudaStreamWaitEvent(s_out, ev_start, 0); }
+    if (rc == JACKS_OK && upload) {
+        // the upload overwrites the resident cubes: it waits for the kernels of earlier calls that READ them -- and for
+        // nothing else on the compute stream (a screen job's pseudo-gene EM and null densities, which read the compact
+        // cube, run while the screen goes up)
+        if (ctx->res_busy) cudaStreamWaitEvent(s_in, ctx->res_busy, 0);
     }
     const bool staged_out = !(keep_resident & JACKS_ASYNC);
     int64_t row_done = 0;        // rows [0, row_done) are already enqueued for upload
@@ -809,6 +815,10 @@ static int em_batched_host_core(JacksCtx* ctx, const JacksEmParams* params, cons
     }
     for (int r = 0; r < R; ++r) { if (ev_in[r]) ctx->pending_events.push_back(ev_in[r]); if (ev_k[r]) ctx->pending_events.push_back(ev_k[r]); }
     if (ev_start) ctx->pending_events.push_back(ev_start);
+    if (!cc) {                    // the last kernel of this call that reads the resident cubes
+        if (!ctx->res_busy && (e = cudaEventCreateWithFlags(&ctx->res_busy, cudaEventDisableTiming)) != cudaSuccess && rc == JACKS_OK) rc = cuda_fail(e, "cudaEventCreate");
+        if (ctx->res_busy) cudaEventRecord(ctx->res_busy, s_k);
+    }
     ctx->pending_plans.push_back(plan);
     if (!cc && !(keep_resident & JACKS_KEEP_RESIDENT)) ctx->res_valid = false;
     if (rc != JACKS_OK || !(keep_resident & JACKS_ASYNC)) {

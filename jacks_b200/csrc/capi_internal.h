@@ -62,6 +62,8 @@ struct JacksCtx {
     cudaStream_t stream;        // compute + default copies of the host entry points
     cudaStream_t copy_stream;   // host -> device copies of the pipelined host entry points
     cudaStream_t out_stream;    // device -> host copies of the pipelined host entry points
+    cudaStream_t plan_stream = nullptr;   // uploads of gene indexes (jacks_em_plan_create)
+    cudaEvent_t res_busy = nullptr;       // the kernels that read the resident cubes (res_test / res_ctrl) have run
     // data cubes kept resident between host calls (jacks_em_batched_host keep_resident)
     jacks::DevBuf res_test, res_ctrl, res_fx;
     int64_t res_N = 0;

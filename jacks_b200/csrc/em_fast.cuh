@@ -457,6 +457,98 @@ __device__ __noinline__ EmStaged<G> em_stage_gene(const double2* __restrict__ te
 #pragma unroll
         for (int g = 0; g < G; ++g) c0[g] = cr[g][0];
     }
+#ifdef JACKS_STAGE_V2
+    constexpr int B = (G >= 9) ? 1 : 2;       // lines per batch
+    if (em_stage_initialises<G, TM>()) {
+        // Per-guide constants of the initial sums; with one control column its mean, its (NaN-patched) variance term
+        // and the 2*tps factor leave the line loop as well.
+        const bool one_ctrl = (ctrl_lines == 1);
+        const double two_tps = 2.0 * tps;
+        double tx1[G], cm[G], cc[G];
+        bool cnan[G];
+#pragma unroll
+        for (int g = 0; g < G; ++g) {
+            tx1[g] = 2.0 * x.x1[g];
+            cm[g] = c0[g].x;
+            double ce = c0[g].y;
+            cnan[g] = one_ctrl && (ce != ce) && !rowmean_fill;         // matched rule: a NaN control sd takes the test sd (:68)
+            if (one_ctrl && (ce != ce) && rowmean_fill) ce = fill[g];   // 1-D control rule (:63)
+            cc[g] = fma(ce, ce, 1e-2);
+        }
+        double chk = 0.0;                       // finite <=> every staged value is: checked once, after the loop
+#pragma unroll 1
+        for (int i = 0; i < n_warp; i += B) {
+            double2 t[B][G], c[B][G];
+            bool live[B];
+#pragma unroll
+            for (int b = 0; b < B; ++b) {
+                const int l = l0 + (i + b) * STEP;
+                live[b] = l < L;
+                const int lb = live[b] ? l : 0;
+#pragma unroll
+                for (int g = 0; g < G; ++g) {
+                    t[b][g] = tr[g][lb];
+                    if (!one_ctrl) c[b][g] = cr[g][lb];
+                }
+            }
+            double pdv[B][G], th[B][G];
+#pragma unroll
+            for (int b = 0; b < B; ++b) {
+                const int l = l0 + (i + b) * STEP;
+                double yv[G];
+#pragma unroll
+                for (int g = 0; g < G; ++g) {
+                    const double te = (t[b][g].y != t[b][g].y) ? 2.0 : t[b][g].y;               // infer.py:58
+                    double base;
+                    if (one_ctrl) {
+                        yv[g] = t[b][g].x - cm[g];
+                        base = cnan[g] ? fma(te, te, 1e-2) : cc[g];
+                    } else {
+                        double ce = c[b][g].y;
+                        if (ce != ce) ce = te;                                                   // :68
+                        yv[g] = t[b][g].x - c[b][g].x;
+                        base = fma(ce, ce, 1e-2);
+                    }
+                    pdv[b][g] = two_tps * fma(te, te, base);                                     // pd2 = 2*tau_pr_den, infer.py:70
+                    th[b][g] = tps * fast_rcp(pdv[b][g]);                                        // tau/2 = tps/pd2, infer.py:83
+                    if (live[b]) {
+                        chk += fabs(yv[g]) + pdv[b][g];
+                        ys[g * L + l] = yv[g];
+                    }
+                }
+                double w1, hi_, lo_;
+                max_min_median<G>(yv, hi_, lo_, w1);                                             // infer.py:81 (finite genes only:
+                const double w2 = w1 * w1;                                                       //  the others are deferred)
+                if (live[b]) {
+#pragma unroll
+                    for (int g = 0; g < G; ++g) {
+                        // tau*(y^2 + x2*w2 - 2*x1*w1*y) = tau*(y*(y - 2*x1*w1) + x2*w2), infer.py:125
+                        const double bb = fma(yv[g], fma(-tx1[g], w1, yv[g]), x.x2[g] * w2);
+                        r.acc[2 * G] = fma(th[b][g], bb, r.acc[2 * G]);
+                        r.acc[g] = fma(yv[g] * th[b][g], w1, r.acc[g]);
+                        r.acc[G + g] = fma(th[b][g], w2, r.acc[G + g]);
+                    }
+                    w1g[l] = w1;
+                    if (w2g) w2g[l] = w2;
+                }
+            }
+            if (TM == 2) {
+                tmem_store<B * G>(tpd + 2 * G * i, &pdv[0][0]);
+            } else {
+#pragma unroll
+                for (int b = 0; b < B; ++b)
+                    if (live[b]) {
+#pragma unroll
+                        for (int g = 0; g < G; ++g) tpdg[g * Lp + l0 + (i + b) * STEP] = pdv[b][g];
+                    }
+            }
+            tmem_store<B * G>(tth + 2 * G * i, &th[0][0]);
+        }
+        tmem_wait_st();
+        r.bad = !(chk <= 1.79769313486231570e308);
+        return r;
+    }
+#else
     constexpr int B = (G >= 9) ? 1 : 2;       // lines per batch
     if (em_stage_initialises<G, TM>()) {
 #pragma unroll 1
@@ -522,6 +614,7 @@ __device__ __noinline__ EmStaged<G> em_stage_gene(const double2* __restrict__ te
         r.bad = bad;
         return r;
     }
+#endif
     for (int l = l0; l < L; l += B * STEP) {
         double2 t[B][G], c[B][G];
 #pragma unroll

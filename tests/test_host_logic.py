@@ -229,3 +229,71 @@ def test_paper_mode_spec_filters_and_combine():
     singles = [{'g': (None, None, None, None, np.array([0.1 * ts]), np.array([1.0 + ts]))} for ts in range(3)]
     y, tau, x1, x2, w1, w2 = P.combineSingleResults(singles)['g']
     assert y is None and [float(v[0]) for v in w1] == [0.0, 0.1, 0.2] and [float(v[0]) for v in w2] == [1.0, 2.0, 3.0]
+
+
+# ---- round 2: host logic around the fused screen job and the sharded driver -----------------------------------------
+def test_collate_returns_broadcast_control_for_one_control_sample():
+    from jacks_b200 import preprocess as P, infer
+    rng = np.random.default_rng(0)
+    data = rng.normal(size=(7, 4, 2))
+    sample_ids = ['A', 'B', 'CTRL', 'D']
+    ctrl_spec = {'A': 'CTRL', 'B': 'CTRL', 'CTRL': 'CTRL', 'D': 'CTRL'}
+    test, ctrl, idx = P.collateTestControlSamples(data, sample_ids, ctrl_spec)
+    assert idx == [0, 1, 3] and test.shape == ctrl.shape == (7, 3, 2)
+    assert np.array_equal(ctrl, data[:, [2, 2, 2], :])           # the reference's values (preprocess.py:125) ...
+    assert ctrl.strides[1] == 0 and infer._one_control(ctrl)     # ... without the copies: goes to the GPU as [N, 1, 2]
+    # matched controls stay materialised
+    ctrl_spec = {'A': 'CTRL', 'B': 'D', 'CTRL': 'CTRL', 'D': 'D'}
+    test, ctrl, idx = P.collateTestControlSamples(data, sample_ids, ctrl_spec)
+    assert idx == [0, 1] and np.array_equal(ctrl, data[:, [2, 3], :]) and not infer._one_control(ctrl)
+
+
+def test_infer_row_and_plane_conventions():
+    from jacks_b200 import infer
+    assert infer._rows([0, -1, 3, -5], 5).tolist() == [0, 4, 3, 0]      # numpy fancy indexing wraps negatives (infer.py:21)
+    with pytest.raises(IndexError):
+        infer._rows([5], 5)
+    with pytest.raises(IndexError):
+        infer._rows([-6], 5)
+    cube = np.zeros((3, 2, 3))
+    assert infer._planes(cube).shape == (3, 2, 2)                         # a raw third plane is ignored (infer.py:24)
+
+
+def test_sharding_helpers():
+    from jacks_b200 import dist as jd
+    assert jd.line_bounds(400, 8).tolist() == [0, 50, 100, 150, 200, 250, 300, 350, 400]
+    assert jd.line_bounds(5, 3).tolist() == [0, 1, 3, 5]
+    used, rebased = jd.compact_rows([7, 3, 3, 9, 7], 12)
+    assert used.tolist() == [3, 7, 9] and rebased.tolist() == [1, 0, 0, 2, 1]
+    # with one rank the sharded job degenerates to the plain calls (no process group needed)
+    calls = []
+
+    def em_fn(o, r, t, c, fx1, fx2):
+        calls.append((len(o) - 1, t.shape[0]))
+        n, L = len(o) - 1, t.shape[1]
+        return dict(w1=np.arange(n * L, dtype=np.float64).reshape(n, L), w2=np.ones((n, L)), x1=np.ones(int(o[-1])),
+                    x2=np.ones(int(o[-1])), n_iters=np.full(n, 3, dtype=np.int32))
+
+    def kde_fn(g, p, positive):
+        return g * 0.0 + p.shape[0]
+    offs, rows = np.array([0, 2, 3]), np.array([4, 5, 9])
+    poffs, prows = np.array([0, 1, 3]), np.array([9, 9, 4])
+    test = np.zeros((12, 6, 2)); ctrl = np.zeros((12, 1, 2))
+    res = jd.run_screen_sharded(offs, rows, poffs, prows, test, ctrl, engine=jd.HostEngine(em_fn, kde_fn))
+    assert sorted(calls) == [(2, 3), (2, 3)]                # both blocks ran on the 3 rows they reference, not on 12
+    assert res['w1'].shape == (2, 6) and res['pvals'].shape == (2, 6) and (res['pvals'] == 2).all()
+
+
+def test_reference_recipe_imports_the_unmodified_reference():
+    import os
+    from oracle import make_ref
+    if make_ref.make() is None:
+        pytest.skip('no /root/reference and no oracle/_ref copy on this box')
+    RI, RIO = make_ref.import_reference()
+    assert os.path.abspath(RI.__file__).startswith(os.path.join(os.path.abspath(os.path.dirname(make_ref.__file__)), '_ref'))
+    data = np.array([[0.1, -0.4, 0.3], [0.2, -0.5, 0.1]])
+    err = np.full((2, 3), 0.2)
+    y, tau, x1, x2, w1, w2 = RI.inferJACKSGene(data, err.copy(), np.zeros((2, 3)), err.copy(), 5)
+    from oracle import jacks_oracle as O
+    o = O.em_gene(data, err.copy(), np.zeros((2, 3)), err.copy(), n_iter=5)
+    assert np.array_equal(w1, o[4]) and np.array_equal(x1, o[2])          # the restatement is bit-exact against it

@@ -1,4 +1,5 @@
-"""Developer probe: wall-clock profile of the whole CLI path (run_JACKS semantics) on a synthetic count-level screen."""
+"""Developer probe: wall-clock profile of the whole CLI path (run_JACKS semantics) on a synthetic count-level screen.
+CP_GENES / CP_LINES / CP_PSEUDO set the shape: 18000 / 400 / 100000 is the full Avana shape (802 count columns)."""
 import cProfile
 import io
 import os
@@ -19,20 +20,7 @@ n_pseudo = int(os.environ.get('CP_PSEUDO', 2000))
 tmp = tempfile.mkdtemp()
 t0 = time.time()
 guides, genes, cols, samples, counts = synth.make_count_screen(n_genes=n_genes, n_lines=n_lines)
-cfile = os.path.join(tmp, 'counts.tab')
-with io.open(cfile, 'w') as f:
-    f.write(u'sgRNA\tGene\t%s\n' % '\t'.join(cols))
-    for i in range(counts.shape[0]):
-        f.write(u'%s\t%s\t%s\n' % (guides[i], genes[i], '\t'.join(map(str, counts[i].tolist()))))
-rfile = os.path.join(tmp, 'rep.tab')
-with io.open(rfile, 'w') as f:
-    f.write(u'Replicate\tSample\n')
-    for c, s in zip(cols, samples):
-        f.write(u'%s\t%s\n' % (c, s))
-nfile = os.path.join(tmp, 'neg.txt')
-with io.open(nfile, 'w') as f:
-    for g in sorted(set(genes))[5::18]:
-        f.write(u'%s\n' % g)
+cfile, rfile, nfile = synth.write_count_screen(os.path.join(tmp, 'cp'), guides, genes, cols, samples, counts, sorted(set(genes))[5::18])
 print('inputs written in %.1f s: %d guides x %d columns' % (time.time() - t0, counts.shape[0], counts.shape[1]), flush=True)
 pr = cProfile.Profile()
 t0 = time.time()
