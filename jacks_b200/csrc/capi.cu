@@ -11,6 +11,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <chrono>
 #include <string>
 #include <thread>
 #include <vector>
@@ -516,7 +517,64 @@ struct HostRunOpts {
     const jacks::KdeNull* kde = nullptr;  // p-values of every gene range right after its EM (jacks_run_screen_host) ...
     double* pvals_host = nullptr;         // ... downloaded here, [n_genes, L]
     JacksEmPlan** plan_out = nullptr;     // the (pending) plan: its device outputs stay valid until the next synchronise
+    const struct PreUpload* pre = nullptr; // the screen is already on its way up (enqueue_screen_upload): ranges + events
 };
+
+// Gene ranges of the pipelined host run: contiguous blocks; with p-values on, boundaries sit on multiples of 1,024 genes.
+static int host_run_ranges(int64_t n_genes) {
+    int R = 1;
+    if (n_genes >= 4096) R = (int)std::min<int64_t>(16, n_genes / 2048);
+    return std::min(R, kMaxRanges);
+}
+static int64_t host_run_bound(int64_t n_genes, int R, int r, bool kde) {
+    if (r >= R) return n_genes;
+    int64_t g = n_genes * r / R;
+    if (kde && R > 1) g = std::min<int64_t>(n_genes, (g + 512) / 1024 * 1024);
+    return g;
+}
+
+// Upload of a screen enqueued AHEAD of everything else of a screen job (pinned host cubes only: the copies are
+// asynchronous): ev_in[r] fires when the rows of gene range r are on the device.
+struct PreUpload {
+    int R = 0;
+    std::vector<cudaEvent_t> ev_in;
+};
+
+static int enqueue_screen_upload(JacksCtx* ctx, const JacksEmHostIO* io, const int64_t* gene_offsets, const int32_t* guide_rows,
+                                 int64_t n_genes, bool kde, PreUpload* pre) {
+    const int64_t N = io->n_rows;
+    const int L = io->n_lines;
+    const size_t row_t = (size_t)L * 2 * sizeof(double), row_c = (size_t)io->ctrl_lines * 2 * sizeof(double);
+    int rc;
+    cudaError_t e;
+    if ((rc = ctx->res_test.reserve(N ? N * row_t : 8)) != JACKS_OK) return rc;
+    if ((rc = ctx->res_ctrl.reserve(N ? N * row_c : 8)) != JACKS_OK) return rc;
+    ctx->res_N = N; ctx->res_L = L; ctx->res_ctrl_lines = io->ctrl_lines; ctx->res_valid = true;
+    cudaStream_t s_in = ctx->copy_stream;
+    if (ctx->res_busy) cudaStreamWaitEvent(s_in, ctx->res_busy, 0);
+    const int R = host_run_ranges(n_genes);
+    const int64_t T = n_genes ? gene_offsets[n_genes] : 0;
+    bool ascending = true;
+    for (int64_t i = 1; i < T && ascending; ++i) ascending = guide_rows[i] >= guide_rows[i - 1];
+    pre->R = R;
+    pre->ev_in.assign(R, nullptr);
+    int64_t row_done = 0;
+    for (int r = 0; r < R; ++r) {
+        const int64_t g0 = host_run_bound(n_genes, R, r, kde), g1 = host_run_bound(n_genes, R, r + 1, kde);
+        int64_t row_hi = N;
+        if (ascending && r + 1 < R && g1 > g0) row_hi = std::min<int64_t>(N, (int64_t)guide_rows[gene_offsets[g1] - 1] + 1);
+        else if (!ascending && r > 0) row_hi = row_done;
+        if (row_hi > row_done) {
+            if ((e = cudaMemcpyAsync((char*)ctx->res_test.p + row_done * row_t, (const char*)io->test + row_done * row_t, (row_hi - row_done) * row_t, cudaMemcpyHostToDevice, s_in)) != cudaSuccess) return cuda_fail(e, "H2D screen");
+            if ((e = cudaMemcpyAsync((char*)ctx->res_ctrl.p + row_done * row_c, (const char*)io->ctrl + row_done * row_c, (row_hi - row_done) * row_c, cudaMemcpyHostToDevice, s_in)) != cudaSuccess) return cuda_fail(e, "H2D screen");
+            row_done = row_hi;
+        }
+        if ((e = cudaEventCreateWithFlags(&pre->ev_in[r], cudaEventDisableTiming)) != cudaSuccess) return cuda_fail(e, "cudaEventCreate");
+        cudaEventRecord(pre->ev_in[r], s_in);
+        ctx->pending_events.push_back(pre->ev_in[r]);
+    }
+    return JACKS_OK;
+}
 
 static int em_batched_host_core(JacksCtx* ctx, const JacksEmParams* params, const int64_t* gene_offsets,
                                 const int32_t* guide_rows, int64_t n_genes, const JacksEmHostIO* io, const HostRunOpts& opt);
@@ -678,7 +736,7 @@ static int em_batched_host_core(JacksCtx* ctx, const JacksEmParams* params, cons
 
     // ---- inputs: upload, or reuse the cubes a previous call left resident -------------------------
     const size_t row_t = (size_t)L * 2 * sizeof(double), row_c = (size_t)io->ctrl_lines * 2 * sizeof(double);
-    const bool upload = (io->test != nullptr) && !cc;
+    const bool upload = (io->test != nullptr) && !cc && !opt.pre;
     if (cc) {
         // compact cubes: uploaded by the caller, the resident screen (if any) stays as it is
     } else if (upload) {
@@ -737,17 +795,9 @@ static int em_batched_host_core(JacksCtx* ctx, const JacksEmParams* params, cons
     // Ranges are contiguous gene blocks.  When the guide rows ascend along the index (a real screen: genes own
     // consecutive rows) each range uploads just the rows up to its last one, so the first kernels start after
     // 1/R of the upload; otherwise (pseudo-genes, arbitrary gathers) everything is uploaded before the kernels.
-    int R = 1;
-    if (n_genes >= 4096) R = (int)std::min<int64_t>(16, n_genes / 2048);
-    if (R > kMaxRanges) R = kMaxRanges;
-    // range r covers genes [gb(r), gb(r+1)); with p-values on, boundaries sit on multiples of 1,024 genes (one CTA of
-    // the evaluation kernel walks a line's cell table for 1,024 genes)
-    auto gb = [&](int r) -> int64_t {
-        if (r >= R) return n_genes;
-        int64_t g = n_genes * r / R;
-        if (opt.kde && R > 1) g = std::min<int64_t>(n_genes, (g + 512) / 1024 * 1024);
-        return g;
-    };
+    const int R = opt.pre ? opt.pre->R : host_run_ranges(n_genes);
+    // range r covers genes [gb(r), gb(r+1))
+    auto gb = [&](int r) -> int64_t { return host_run_bound(n_genes, R, r, opt.kde != nullptr); };
     bool ascending = upload;
     if (upload && R > 1) {
         for (int64_t i = 1; i < T && ascending; ++i) ascending = guide_rows[i] >= guide_rows[i - 1];
@@ -783,6 +833,8 @@ static int em_batched_host_core(JacksCtx* ctx, const JacksEmParams* params, cons
             }
             cudaEventRecord(ev_in[r], s_in);
             cudaStreamWaitEvent(s_k, ev_in[r], 0);
+        } else if (opt.pre) {
+            cudaStreamWaitEvent(s_k, opt.pre->ev_in[r], 0);
         }
         if (g1 > g0) rc = em_run_range(ctx, plan, params, &dio, s_k, g0, g1, r);
         if (rc == JACKS_OK && opt.kde && g1 > g0 && dptr[8])
@@ -886,6 +938,20 @@ extern "C" int jacks_run_screen_host(JacksCtx* ctx, const JacksEmParams* params,
     int rc;
     jacks::KdeNull nl;
     JacksEmPlan* pplan = nullptr;
+    PreUpload pre;
+    static const int upload_first_env = []() { const char* v = getenv("JACKS_SCREEN_UPLOAD_FIRST"); return v ? atoi(v) : 0; }();
+    static const bool trace = getenv("JACKS_TRACE") != nullptr;
+    const auto t_start = std::chrono::steady_clock::now();
+    auto stamp = [&](const char* what) {
+        if (trace) fprintf(stderr, "[jacks trace] %-28s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_start).count());
+    };
+    const bool upload_first = upload_first_env && n_pseudo > 0 && host_pointer_is_pinned(rio.test) && host_pointer_is_pinned(rio.ctrl);
+    if (upload_first) {
+        // 0. pinned cubes: the screen starts going up (copy stream, range by range) before any host-side preparation of
+        //    the pseudo-gene run; the control rows the pseudo-genes need are pulled by a kernel, not by the copy engine
+        if ((rc = enqueue_screen_upload(ctx, &rio, gene_offsets, guide_rows, n_genes, io->pvals != nullptr, &pre)) != JACKS_OK) { jacks_ctx_synchronize(ctx); return rc; }
+        stamp("screen upload enqueued");
+    }
     if (n_pseudo > 0) {
         // 1. pseudo-genes on a compact cube of the rows they reference, uploaded ahead of the screen
         JacksEmHostIO pio;
@@ -898,6 +964,7 @@ extern "C" int jacks_run_screen_host(JacksCtx* ctx, const JacksEmParams* params,
         popt.w1_stays = true;
         popt.plan_out = &pplan;
         if ((rc = em_batched_host_compact(ctx, params, pseudo_offsets, pseudo_rows, n_pseudo, &pio, popt)) != JACKS_OK) { jacks_ctx_synchronize(ctx); return rc; }
+        stamp("pseudo-gene EM enqueued");
         // 2. null densities from the pseudo-gene E[w], still on the device
         if (want_p && (rc = jacks::kde_null_prepare(ctx, (const double*)pplan->b->out[2].p, n_pseudo, L, io->positive, ctx->stream, &nl)) != JACKS_OK) { jacks_ctx_synchronize(ctx); return rc; }
         if (io->pseudo_pvals) {
@@ -917,12 +984,16 @@ extern "C" int jacks_run_screen_host(JacksCtx* ctx, const JacksEmParams* params,
     // 3. the screen itself: upload once, real genes range by range (EM, p-values, download)
     HostRunOpts ropt;
     ropt.flags = flags;
+    if (upload_first) ropt.pre = &pre;
     if (io->pvals) { ropt.kde = &nl; ropt.pvals_host = io->pvals; }
+    stamp("null densities enqueued");
     rc = em_batched_host_core(ctx, params, gene_offsets, guide_rows, n_genes, &rio, ropt);
+    stamp("real genes done / enqueued");
     if (rc != JACKS_OK || !(flags & JACKS_ASYNC)) {
         const int rs = jacks_ctx_synchronize(ctx);
         if (rc == JACKS_OK) rc = rs;
     }
+    stamp("synchronised");
     return rc;
 }
 
