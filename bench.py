@@ -463,22 +463,24 @@ def main():
     ev_k0, ev_k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 
     def gather_results():
-        """The north star's one collective: rank 0 receives the real genes' w1, w2, x1, x2 (and iteration counts)."""
+        """The north star's one collective: rank 0 receives the real genes' w1, w2, x1, x2 (and iteration counts).
+        Asynchronous: NCCL waits for the real-gene EM just enqueued and moves the bytes while the pseudo-gene EM runs."""
         send = torch.cat([o['w1'].reshape(-1), o['w2'].reshape(-1), o['x1'], o['x2'], o['it'].to(torch.float64)])
         sizes = [2 * int(job.b[s + 1] - job.b[s]) * L + 2 * int(job.bt[s + 1] - job.bt[s]) + int(job.b[s + 1] - job.b[s]) for s in range(world)]
         recv = torch.empty(sum(sizes) if rank == 0 else 0, **f64)
-        dist.all_to_all_single(recv, send, output_split_sizes=sizes if rank == 0 else [0] * world,
-                               input_split_sizes=[send.numel()] + [0] * (world - 1))
-        return recv
+        work = dist.all_to_all_single(recv, send, output_split_sizes=sizes if rank == 0 else [0] * world,
+                                      input_split_sizes=[send.numel()] + [0] * (world - 1), async_op=True)
+        return work, recv, send
 
     def step():
         ev_k0.record()
+        plan_r.run_device(params, io_r, stream)              # the real genes first: their results travel ...
+        pending = gather_results() if gather_w > 1 else None
         if n_p:
-            plan_p.run_device(params, io_p, stream)
-        plan_r.run_device(params, io_r, stream)
+            plan_p.run_device(params, io_p, stream)          # ... while the pseudo-genes (85 % of the arithmetic) run
         ev_k1.record()
-        if gather_w > 1:
-            gather_results()
+        if pending is not None:
+            pending[0].wait()                                # the step ends when rank 0 holds the gathered results
 
     for _ in range(args.warmup):
         step()

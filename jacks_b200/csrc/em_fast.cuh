@@ -201,7 +201,7 @@ template <int G> struct EmXs { double x2[G], tx1[G], tx2[G]; };
 // A lane's dead line (MASKED, !valid) then holds garbage that is loaded, computed on and stored back, never used.
 // TM == 2: pd2 lives in TMEM as well (columns `pcol`...), loaded at the top of the step that uses it: no L2 round
 // trip, no look-ahead registers, no global slab.
-template <int G, int U, int UP, bool UNIT_C, bool MASKED, int TM>
+template <int G, int U, int UP, bool UNIT_C, bool MASKED, int TM, bool WS>
 __device__ __forceinline__ void em_sweep(const uint32_t tcol, const uint32_t pcol, const double* __restrict__ ys, double (&pd)[UP][G],
                                          const double* __restrict__ pd_next, const int Lp,
                                          double* __restrict__ ths, double* __restrict__ w1p,
@@ -347,8 +347,15 @@ __device__ __forceinline__ void em_sweep(const uint32_t tcol, const uint32_t pco
 #pragma unroll
     for (int u = 0; u < U; ++u)
         if (!MASKED || u < U - 1 || valid) {
-            w1p[l + u * step] = w1[u];                // E[w], E[w^2]: write-only state within a pass, kept in the
-            if (w2g) w2g[l + u * step] = w2[u];      // gene's output rows (L2 resident), not in shared memory
+            if (WS) {
+                // E[w], E[w^2] of the pass as one 16-byte shared-memory store per line; they reach the gene's output rows
+                // once, after the last pass (every pass used to write them to global memory: two STG and their
+                // descriptor moves per line, and 0.8 GB of DRAM writes per Avana pass for values that are overwritten)
+                reinterpret_cast<double2*>(w1p)[l + u * step] = make_double2(w1[u], w2[u]);
+            } else {
+                w1p[l + u * step] = w1[u];                // E[w], E[w^2]: write-only state within a pass, kept in the
+                if (w2g) w2g[l + u * step] = w2[u];      // gene's output rows (L2 resident), not in shared memory
+            }
         }
 }
 
@@ -376,7 +383,7 @@ template <int G, int TM> __host__ __device__ constexpr int em_sweep_lines() {
 // pd2 (TM != 2) lives in an L2-resident global slab [G][Lp] (read once per pass, never written after staging, so
 // it does not have to occupy shared memory); rows are padded (Lp >= L + U*STEP) so that the look-ahead
 // loads need no bounds logic.  A step refills its pd registers for the NEXT step, which is never taller than itself.
-template <int G, int STEP, bool UNIT_C, int TM, int B>
+template <int G, int STEP, bool UNIT_C, int TM, int B, bool WS>
 __device__ __noinline__ EmSums<G> em_sweep_all(const uint32_t tbase, const uint32_t pdoff, const double* ys, const double* tpdg, const int Lp, double* ths,
                                                double* w1p, double* w2g, const int L, const int l0,
                                                const int n_big, const EmXs<G> x, const double ivw, const double mw,
@@ -399,8 +406,8 @@ __device__ __noinline__ EmSums<G> em_sweep_all(const uint32_t tbase, const uint3
     if (TM) tmem_wait_st();
     uint32_t tcol = tbase;
     for (int i = 0; i < n_big; ++i, l += UP * STEP, tcol += 2 * UP * G)
-        em_sweep<G, UP, UP, UNIT_C, false, TM>(tcol, tcol + pdoff, ys, pd, tpdg + l + UP * STEP, Lp, ths, w1p, w2g, L, l, STEP, x, ivw, mw, c_tau, a1, a2, ab, true, true);
-    em_sweep<G, B, UP, UNIT_C, true, TM>(tcol, tcol + pdoff, ys, pd, nullptr, Lp, ths, w1p, w2g, L, l, STEP, x, ivw, mw, c_tau, a1, a2, ab, (l + (B - 1) * STEP) < L, false);
+        em_sweep<G, UP, UP, UNIT_C, false, TM, WS>(tcol, tcol + pdoff, ys, pd, tpdg + l + UP * STEP, Lp, ths, w1p, w2g, L, l, STEP, x, ivw, mw, c_tau, a1, a2, ab, true, true);
+    em_sweep<G, B, UP, UNIT_C, true, TM, WS>(tcol, tcol + pdoff, ys, pd, nullptr, Lp, ths, w1p, w2g, L, l, STEP, x, ivw, mw, c_tau, a1, a2, ab, (l + (B - 1) * STEP) < L, false);
     EmSums<G> r;
     // sum pd2*th = sum (t1 - x2*w2)*th: the accumulators hold sum t1*th
     r.ab = fma(-x.x2[0], a2[0], ab[0]);
@@ -433,7 +440,7 @@ template <int G> struct EmStaged { double acc[2 * G + 1]; bool bad; };
 // 400..800 lines: G = 4 gains 5 %, G = 5..7 lose 1..4 % to register pressure in the staging loop).
 template <int G, int TM> __host__ __device__ constexpr bool em_stage_initialises() { return TM == 2 || (TM == 1 && G <= 4); }
 
-template <int G, int STEP, int TM>
+template <int G, int STEP, int TM, bool WS>
 __device__ __noinline__ EmStaged<G> em_stage_gene(const double2* __restrict__ test, const double2* __restrict__ ctrl,
                                                   const int* rows, double* __restrict__ ys, double* __restrict__ tpdg,
                                                   const int L, const int Lp, const int l0, const int ctrl_lines,
@@ -528,8 +535,11 @@ __device__ __noinline__ EmStaged<G> em_stage_gene(const double2* __restrict__ te
                         r.acc[g] = fma(yv[g] * th[b][g], w1, r.acc[g]);
                         r.acc[G + g] = fma(th[b][g], w2, r.acc[G + g]);
                     }
-                    w1g[l] = w1;
-                    if (w2g) w2g[l] = w2;
+                    if (WS) reinterpret_cast<double2*>(w1g)[l] = make_double2(w1, w2);
+                    else {
+                        w1g[l] = w1;
+                        if (w2g) w2g[l] = w2;
+                    }
                 }
             }
             if (TM == 2) {
@@ -594,8 +604,11 @@ __device__ __noinline__ EmStaged<G> em_stage_gene(const double2* __restrict__ te
                         r.acc[g] += yv[g] * th[b][g] * w1;
                         r.acc[G + g] += th[b][g] * w2;
                     }
-                    w1g[l] = w1;
-                    if (w2g) w2g[l] = w2;
+                    if (WS) reinterpret_cast<double2*>(w1g)[l] = make_double2(w1, w2);
+                    else {
+                        w1g[l] = w1;
+                        if (w2g) w2g[l] = w2;
+                    }
                 }
             }
             if (TM == 2) {
@@ -656,8 +669,9 @@ __host__ __device__ constexpr long long em_fast_smem_doubles(int G, int W, int L
 // tile and totals, rounded to 128 bytes.  Two CTAs (eight genes) per SM: with three, the 168-register budget makes
 // ptxas spill in the sweep, and 12 genes at 3 lines per step measured no faster than 8 at 4 (7.9 ms at L = 400).
 constexpr int kTmemTeams = 4;
-__host__ __device__ constexpr long long em_fast_tmem_team_doubles(int G, int L) {
-    return ((long long)G * L + (2 * G + 1) * 33 + 2 * (2 * G + 1) + 15) / 16 * 16;
+__host__ __device__ constexpr long long em_fast_tmem_team_doubles(int G, int L, bool ws = false) {
+    // ws: plus (E[w], E[w^2]) pairs of the running pass, [L][2]
+    return ((long long)G * L + (2 * G + 1) * 33 + 2 * (2 * G + 1) + (ws ? 2LL * L : 0) + 15) / 16 * 16;
 }
 
 // L2 prefetch of the G guide rows (test + control) of the gene a team will run next.  One rolled loop over
@@ -683,9 +697,10 @@ __device__ __forceinline__ void prefetch_gene_l2(const double2* test, const doub
 // gene, shared-memory block and TMEM lane quarter; th = tau/2 lives in TMEM columns [line][g] of the thread's lane.
 // Nothing synchronises the teams between the TMEM allocation at the start and its release at the end.
 // TM: 0 shared-memory variant; 1 tau in TMEM; 2 tau and tau_pr_den in TMEM (no global slab, no L2 traffic in a pass).
-template <int G, int W, bool UNIT_C, bool PLAIN, int TM>
+template <int G, int W, bool UNIT_C, bool PLAIN, int TM, bool WS = false>
 __global__ void __launch_bounds__(TM ? kTmemTeams * 32 : W * 32, TM ? 2 : 0) em_fast_kernel(const EmLaunch a) {
     static_assert(!TM || W == 1, "the TMEM variant runs one-warp teams");
+    static_assert(!WS || TM == 2, "E[w] is kept in shared memory by the tensor-memory mode 2 kernel only");
     constexpr int NV = 2 * G + 1;
     constexpr int STEP = 32 * W;
     constexpr int UMAX = em_sweep_lines<G, TM>();
@@ -696,11 +711,13 @@ __global__ void __launch_bounds__(TM ? kTmemTeams * 32 : W * 32, TM ? 2 : 0) em_
     const int warp = TM ? 0 : cta_warp;                 // warp index inside the team
     const int tid = TM ? lane : (int)threadIdx.x;       // thread index inside the team
     const int team = TM ? blockIdx.x * kTmemTeams + cta_warp : blockIdx.x;
-    double* ys = smem + (TM ? cta_warp * em_fast_tmem_team_doubles(G, L) : 0);   // [G][L]
+    double* ys = smem + (TM ? cta_warp * em_fast_tmem_team_doubles(G, L, WS) : 0);   // [G][L]
     double* taus = TM ? nullptr : ys + (size_t)G * L;   // [G][L]  th = tau/2 (see em_sweep); TMEM columns if TM
     double* tile = TM ? ys + (size_t)G * L : taus + (size_t)G * L;
     double* scr = tile + warp * (NV * 33);              // this warp's reduction tile
     double* red = tile + W * (NV * 33);                 // [2][W][NV] totals
+    double* wb = red + 2 * W * NV;                      // WS: (E[w], E[w^2]) of the running pass, [L][2]
+    wb += (reinterpret_cast<unsigned long long>(wb) & 8) ? 1 : 0;       // 16-byte aligned pairs
     const int Lp = a.tpd_stride;
     double* tpdg = a.tpd_scratch + (size_t)team * G * Lp;                  // this team's pd2 slab [G][Lp] (global, L2)
     __shared__ int s_slot[2];
@@ -782,15 +799,17 @@ __global__ void __launch_bounds__(TM ? kTmemTeams * 32 : W * 32, TM ? 2 : 0) em_
                 }
             }
         }
-        double* const w2g = a.w2 ? a.w2 + (long long)gid * L : nullptr;
-        double* const w1g = a.w1 + (long long)gid * L;
+        double* const w2o = a.w2 ? a.w2 + (long long)gid * L : nullptr;       // the gene's output rows
+        double* const w1o = a.w1 + (long long)gid * L;
+        double* const w2g = WS ? wb + 1 : w2o;                                  // where the passes keep E[w^2], E[w]
+        double* const w1g = WS ? wb : w1o;
         double acc[NV];
         bool bad;
         {
             EmX<G> xv;
 #pragma unroll
             for (int g = 0; g < G; ++g) { xv.x1[g] = x1r[g]; xv.x2[g] = x2r[g]; xv.tx1[g] = 0.0; xv.tx2[g] = 0.0; }
-            const EmStaged<G> sg = em_stage_gene<G, STEP, TM>(a.test, a.ctrl, rows, ys, tpdg, L, Lp, l0, a.ctrl_lines, a.ctrl_rowmean_fill,
+            const EmStaged<G> sg = em_stage_gene<G, STEP, TM, WS>(a.test, a.ctrl, rows, ys, tpdg, L, Lp, l0, a.ctrl_lines, a.ctrl_rowmean_fill,
                                                               fill, tps, tbase + pdoff, tbase, n_warp, xv, w1g, w2g);
             bad = sg.bad;
 #pragma unroll
@@ -877,8 +896,11 @@ __global__ void __launch_bounds__(TM ? kTmemTeams * 32 : W * 32, TM ? 2 : 0) em_
                         acc[g] += yv[g] * t * w1;
                         acc[G + g] += t * w2;
                     }
-                    w1g[l] = w1;
-                    if (w2g) w2g[l] = w2;
+                    if (WS) reinterpret_cast<double2*>(w1g)[l] = make_double2(w1, w2);
+                    else {
+                        w1g[l] = w1;
+                        if (w2g) w2g[l] = w2;
+                    }
                 }
             }
             team_allsum<NV, NV, W>(acc, scr, red, parity, warp, lane);
@@ -921,11 +943,11 @@ __global__ void __launch_bounds__(TM ? kTmemTeams * 32 : W * 32, TM ? 2 : 0) em_
                 if (!PLAIN && a.apply_w_hp && L > 1) {
                     // hierarchical prior from the current w1, infer.py:92 (population variance)
                     double m[1] = {0.0};
-                    for (int l = l0; l < L; l += STEP) m[0] += w1g[l];
+                    for (int l = l0; l < L; l += STEP) m[0] += w1g[WS ? 2 * l : l];
                     team_allsum<1, NV, W>(m, scr, red, parity, warp, lane);
                     const double mean = m[0] / (double)L;
                     double v[1] = {0.0};
-                    for (int l = l0; l < L; l += STEP) { const double d = w1g[l] - mean; v[0] += d * d; }
+                    for (int l = l0; l < L; l += STEP) { const double d = w1g[WS ? 2 * l : l] - mean; v[0] += d * d; }
                     team_allsum<1, NV, W>(v, scr, red, parity, warp, lane);
                     mu0_w = mean;
                     var0_w = (v[0] / (double)L) * 3 + 1e-4;
@@ -937,7 +959,7 @@ __global__ void __launch_bounds__(TM ? kTmemTeams * 32 : W * 32, TM ? 2 : 0) em_
 #pragma unroll
                     for (int g = 0; g < G; ++g) { xv.x2[g] = x2r[g]; xv.tx1[g] = 2.0 * x1r[g]; xv.tx2[g] = 2.0 * x2r[g]; }
                     EmSums<G> r;
-#define JACKS_SWEEP(BB) r = em_sweep_all<G, STEP, UNIT_C, TM, (BB <= UMAX ? BB : 1)>(tbase, pdoff, ys, tpdg, Lp, taus, w1g, w2g, L, l0, plan_big, xv, ivw, mw, c_tau)
+#define JACKS_SWEEP(BB) r = em_sweep_all<G, STEP, UNIT_C, TM, (BB <= UMAX ? BB : 1), WS>(tbase, pdoff, ys, tpdg, Lp, taus, w1g, w2g, L, l0, plan_big, xv, ivw, mw, c_tau)
                     if (UMAX >= 4 && plan_B == 4) JACKS_SWEEP(4);
                     else if (UMAX >= 3 && plan_B == 3) JACKS_SWEEP(3);
                     else if (UMAX >= 2 && plan_B == 2) JACKS_SWEEP(2);
@@ -954,6 +976,13 @@ __global__ void __launch_bounds__(TM ? kTmemTeams * 32 : W * 32, TM ? 2 : 0) em_
             }
 
             // ---- write results ------------------------------------------------------------------
+            if (WS) {
+                for (int l = l0; l < L; l += STEP) {
+                    const double2 ww = reinterpret_cast<const double2*>(wb)[l];
+                    w1o[l] = ww.x;
+                    if (w2o) w2o[l] = ww.y;
+                }
+            }
             if (TM && a.tau) {
                 tmem_wait_st();
 #pragma unroll 1

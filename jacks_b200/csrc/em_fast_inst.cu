@@ -15,13 +15,13 @@ namespace {
 
 // Tensor-memory variant: four one-warp teams per CTA, tau in TMEM (em_fast.cuh).  The resident CTAs per SM are the
 // smaller of what shared memory / registers and what the 512 TMEM columns allow.
-template <int G, bool UNIT_C, bool PLAIN, int TM>
+template <int G, bool UNIT_C, bool PLAIN, int TM, bool WS = false>
 cudaError_t launch_tmem(const EmLaunch& a0, int n_sm, int grid_limit, cudaStream_t st, int* grid_out) {
-    auto k = em_fast_kernel<G, 1, UNIT_C, PLAIN, TM>;
+    auto k = em_fast_kernel<G, 1, UNIT_C, PLAIN, TM, WS>;
     EmLaunch a = a0;
     a.tmem_cols = tmem_cols_for(G, a.L, TM);
     a.tmem_pd_off = (TM == 2) ? tmem_array_cols(G, a.L) : 0;
-    const size_t smem = (size_t)em_fast_tmem_team_doubles(G, a.L) * kTmemTeams * sizeof(double);
+    const size_t smem = (size_t)em_fast_tmem_team_doubles(G, a.L, WS) * kTmemTeams * sizeof(double);
     if (a.tmem_cols == 0 || smem > kMaxDynSmem) return cudaErrorInvalidValue;
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
@@ -74,7 +74,15 @@ template <int G, int W, bool UNIT_C, bool PLAIN>
 cudaError_t launch_inst(const EmLaunch& a, int n_sm, int grid_limit, cudaStream_t st, int* grid_out) {
     if (W == 1) {
         const int tm = tmem_mode<G>(a);
-        if (tm == 2) return launch_tmem<G, UNIT_C, PLAIN, 2>(a, n_sm, grid_limit, st, grid_out);
+        if (tm == 2) {
+            // E[w], E[w^2] of the running pass in shared memory whenever two CTAs still fit an SM with it (L <= ~600 at
+            // G = 4); JACKS_EM_WSMEM=0/1 forces the choice where it fits (tests, tuning)
+            static const int force_ws = []() { const char* e = getenv("JACKS_EM_WSMEM"); return e ? atoi(e) : -1; }();
+            const size_t smem_ws = (size_t)em_fast_tmem_team_doubles(G, a.L, true) * kTmemTeams * sizeof(double);
+            const bool fits = 2 * (smem_ws + 2048) <= 228 * 1024;
+            if (fits && force_ws != 0) return launch_tmem<G, UNIT_C, PLAIN, 2, true>(a, n_sm, grid_limit, st, grid_out);
+            return launch_tmem<G, UNIT_C, PLAIN, 2>(a, n_sm, grid_limit, st, grid_out);
+        }
         if (tm == 1) return launch_tmem<G, UNIT_C, PLAIN, 1>(a, n_sm, grid_limit, st, grid_out);
     }
     auto k = em_fast_kernel<G, W, UNIT_C, PLAIN, 0>;

@@ -242,14 +242,16 @@ class ShardedScreen(object):
         self.h2d_bytes += loffs.nbytes + poffs.nbytes + both.nbytes
 
     # -- collectives -------------------------------------------------------------------------------------------------
-    def _all_to_all(self, send, in_splits, out_splits):
+    def _all_to_all(self, send, in_splits, out_splits, async_op=False):
+        """all_to_all_single with uneven splits.  async_op: returns (work, recv) and does not make the current stream
+        wait for the transfer."""
         import torch.distributed as dist
         if self.world == 1:
-            return send
+            return (None, send) if async_op else send
         recv = self.torch.empty(int(sum(out_splits)), dtype=send.dtype, device=send.device)
-        dist.all_to_all_single(recv, send, output_split_sizes=[int(x) for x in out_splits],
-                                   input_split_sizes=[int(x) for x in in_splits], group=self.group)
-        return recv
+        work = dist.all_to_all_single(recv, send, output_split_sizes=[int(x) for x in out_splits],
+                                      input_split_sizes=[int(x) for x in in_splits], group=self.group, async_op=async_op)
+        return (work, recv) if async_op else recv
 
     def _lines_of_all_genes(self, w1_local, gene_bounds):
         """[my genes, L] on every rank -> [all genes, my lines] on every rank: ONE all-to-all (step 3)."""
@@ -270,12 +272,25 @@ class ShardedScreen(object):
         W, r, L = self.world, self.rank, self.L
         do_p = bool(want_pvals and self.has_pseudo and self.n_pseudo >= 2)
         n_lr, n_lp = int(self.b[r + 1] - self.b[r]), int(self.bp[r + 1] - self.bp[r])
+        t_l = int(self.bt[r + 1] - self.bt[r])
         pv_block = None
+        early = None
+
+        def gather_em(real):
+            """Gather of the real genes' EM results (w1 | w2 | x1 | x2 | n_iters as f64) on dst, ASYNCHRONOUS: it travels
+            while the pseudo-gene EM and the p-value stage run."""
+            send = t.cat([real['w1'].reshape(-1), real['w2'].reshape(-1), real['x1'], real['x2'], real['n_iters'].to(t.float64)])
+            sizes = [2 * int(self.b[s + 1] - self.b[s]) * L + 2 * int(self.bt[s + 1] - self.bt[s]) + int(self.b[s + 1] - self.b[s])
+                     for s in range(W)]
+            return self._all_to_all(send, [send.numel() if s == self.dst else 0 for s in range(W)],
+                                    [sizes[s] if r == self.dst else 0 for s in range(W)], async_op=True) + (sizes, send)
         if do_p:
             # one exchange buffer for both: [real | pseudo] E[w] of my genes, written by the kernels themselves
             both = t.empty((n_lr + n_lp, L), dtype=t.float64, device=eng.device)
-            pseudo = eng.em(self.plan_pseudo, self.d_test, self.d_ctrl, self.params, want_x=False, w1_out=both[n_lr:])
             real = eng.em(self.plan_real, self.d_test, self.d_ctrl, self.params, self.d_fx1, self.d_fx2, want_x=True, w1_out=both[:n_lr])
+            if W > 1:
+                early = gather_em(real)
+            pseudo = eng.em(self.plan_pseudo, self.d_test, self.d_ctrl, self.params, want_x=False, w1_out=both[n_lr:])
             gb = np.concatenate([[0], np.cumsum([(self.b[s + 1] - self.b[s]) + (self.bp[s + 1] - self.bp[s]) for s in range(W)])])
             mine = self._lines_of_all_genes(both, gb)                        # [(real_s, pseudo_s) for s in ranks, my lines]
             parts_r, parts_p, o = [], [], 0
@@ -288,43 +303,43 @@ class ShardedScreen(object):
             pv_block = eng.kde(g_block.contiguous(), p_block.contiguous(), self.positive)
         else:
             real = eng.em(self.plan_real, self.d_test, self.d_ctrl, self.params, self.d_fx1, self.d_fx2, want_x=True)
+            if W > 1:
+                early = gather_em(real)
         if W == 1:
             res = {k: real[k] for k in ('w1', 'w2', 'x1', 'x2', 'n_iters')}
             if do_p:
                 res['pvals'] = pv_block
             self.exchange_bytes = 0
             return res
-        # gather to dst: per rank [w1 | w2 | x1 | x2 | n_iters as f64 | p-value column block]
-        n_l = int(self.b[r + 1] - self.b[r])
-        t_l = int(self.bt[r + 1] - self.bt[r])
-        pieces = [real['w1'].reshape(-1), real['w2'].reshape(-1), real['x1'], real['x2'], real['n_iters'].to(t.float64)]
+        # late gather: the p-value column blocks (all genes x my lines)
+        work, recv_em, em_sizes, em_send = early
+        recv_pv = None
         if do_p:
-            pieces.append(pv_block.reshape(-1))
-        send = t.cat(pieces)
-
-        def length(s):
-            n_s, t_s = int(self.b[s + 1] - self.b[s]), int(self.bt[s + 1] - self.bt[s])
-            return 2 * n_s * L + 2 * t_s + n_s + (self.n_genes * int(self.lb[s + 1] - self.lb[s]) if do_p else 0)
-        in_splits = [send.numel() if s == self.dst else 0 for s in range(W)]
-        out_splits = [length(s) if r == self.dst else 0 for s in range(W)]
-        recv = self._all_to_all(send, in_splits, out_splits)
-        self.exchange_bytes = (both.numel() * 8 * (W - 1) // W if do_p else 0) + (send.numel() * 8 if r != self.dst else 0)
+            send = pv_block.reshape(-1)
+            pv_sizes = [self.n_genes * int(self.lb[s + 1] - self.lb[s]) for s in range(W)]
+            recv_pv = self._all_to_all(send, [send.numel() if s == self.dst else 0 for s in range(W)],
+                                       [pv_sizes[s] if r == self.dst else 0 for s in range(W)])
+        if work is not None:
+            work.wait()
+        self.exchange_bytes = (both.numel() * 8 * (W - 1) // W if do_p else 0) + \
+            ((em_send.numel() + (pv_block.numel() if do_p else 0)) * 8 if r != self.dst else 0)
         if r != self.dst:
             return None
-        out = {k: [] for k in ('w1', 'w2', 'x1', 'x2', 'n_iters', 'pv')}
+        out = {k: [] for k in ('w1', 'w2', 'x1', 'x2', 'n_iters')}
         o = 0
         for s in range(W):
             n_s, t_s = int(self.b[s + 1] - self.b[s]), int(self.bt[s + 1] - self.bt[s])
-            l_s = int(self.lb[s + 1] - self.lb[s])
             for key, size, shape in (('w1', n_s * L, (n_s, L)), ('w2', n_s * L, (n_s, L)), ('x1', t_s, (t_s,)), ('x2', t_s, (t_s,)),
                                      ('n_iters', n_s, (n_s,))):
-                out[key].append(recv[o:o + size].view(shape)); o += size
-            if do_p:
-                out['pv'].append(recv[o:o + self.n_genes * l_s].view(self.n_genes, l_s)); o += self.n_genes * l_s
-        res = {k: (t.cat(out[k]) if W > 1 else out[k][0]) for k in ('w1', 'w2', 'x1', 'x2')}
-        res['n_iters'] = (t.cat(out['n_iters']) if W > 1 else out['n_iters'][0]).to(t.int32)
+                out[key].append(recv_em[o:o + size].view(shape)); o += size
+        res = {k: t.cat(out[k]) for k in ('w1', 'w2', 'x1', 'x2')}
+        res['n_iters'] = t.cat(out['n_iters']).to(t.int32)
         if do_p:
-            res['pvals'] = t.cat(out['pv'], dim=1) if W > 1 else out['pv'][0]
+            blocks, o = [], 0
+            for s in range(W):
+                l_s = int(self.lb[s + 1] - self.lb[s])
+                blocks.append(recv_pv[o:o + self.n_genes * l_s].view(self.n_genes, l_s)); o += self.n_genes * l_s
+            res['pvals'] = t.cat(blocks, dim=1)
         return res
 
 
