@@ -472,12 +472,19 @@ def main():
                                       input_split_sizes=[send.numel()] + [0] * (world - 1), async_op=True)
         return work, recv, send
 
+    side = torch.cuda.Stream(device=dev)
+    cur = torch.cuda.current_stream()
+
     def step():
         ev_k0.record()
+        side.wait_stream(cur)
         plan_r.run_device(params, io_r, stream)              # the real genes first: their results travel ...
         pending = gather_results() if gather_w > 1 else None
         if n_p:
-            plan_p.run_device(params, io_p, stream)          # ... while the pseudo-genes (85 % of the arithmetic) run
+            # ... while the pseudo-genes (85 % of the arithmetic) run -- on a second stream, so that their CTAs move in
+            # as the real-gene kernel's drain (both kernels are persistent: no tail between the two launches)
+            plan_p.run_device(params, io_p, side.cuda_stream)
+        cur.wait_stream(side)
         ev_k1.record()
         if pending is not None:
             pending[0].wait()                                # the step ends when rank 0 holds the gathered results

@@ -54,7 +54,7 @@ def build_library(force=False, verbose=False, variant=None, defines=()):
     csrc/build/<variant>/); load it with JACKS_B200_LIB=<path> (jacks_b200/_native.py)."""
     global OBJ, LIB
     if variant:
-        OBJ = os.path.join(PKG, 'csrc', 'build', variant)
+        OBJ = os.path.join(os.environ.get('JACKS_VARIANT_OBJ', '/tmp/jacks_b200_build'), variant)      # out of the tree: the GPU snapshot is size-capped
         LIB = os.path.join(PKG, 'libjacks_b200_%s.so' % variant)
     deps = _sources()
     units = [u for u in UNITS if os.path.exists(os.path.join(CSRC, u[0]))]

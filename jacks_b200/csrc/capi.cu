@@ -205,6 +205,9 @@ int jacks_ctx_create(int device, JacksCtx** out) {
     if ((e = cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking)) != cudaSuccess) { delete c; return cuda_fail(e, "cudaStreamCreate"); }
     if ((e = cudaStreamCreateWithFlags(&c->out_stream, cudaStreamNonBlocking)) != cudaSuccess) { delete c; return cuda_fail(e, "cudaStreamCreate"); }
     if ((e = cudaStreamCreateWithFlags(&c->plan_stream, cudaStreamNonBlocking)) != cudaSuccess) { delete c; return cuda_fail(e, "cudaStreamCreate"); }
+    if ((e = cudaStreamCreateWithFlags(&c->side_stream, cudaStreamNonBlocking)) != cudaSuccess) { delete c; return cuda_fail(e, "cudaStreamCreate"); }
+    if ((e = cudaEventCreateWithFlags(&c->side_fork, cudaEventDisableTiming)) != cudaSuccess) { delete c; return cuda_fail(e, "cudaEventCreate"); }
+    if ((e = cudaEventCreateWithFlags(&c->side_join, cudaEventDisableTiming)) != cudaSuccess) { delete c; return cuda_fail(e, "cudaEventCreate"); }
     *out = c;
     return JACKS_OK;
 }
@@ -230,6 +233,9 @@ void jacks_ctx_destroy(JacksCtx* c) {
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     if (c->out_stream) cudaStreamDestroy(c->out_stream);
     if (c->plan_stream) cudaStreamDestroy(c->plan_stream);
+    if (c->side_stream) cudaStreamDestroy(c->side_stream);
+    if (c->side_fork) cudaEventDestroy(c->side_fork);
+    if (c->side_join) cudaEventDestroy(c->side_join);
     if (c->res_busy) cudaEventDestroy(c->res_busy);
     delete c;
 }
@@ -892,6 +898,20 @@ extern "C" int jacks_run_screen_device(JacksCtx* ctx, const JacksEmPlan* plan_re
     int rc;
     const int L = plan_real->L;
     const int64_t n_pseudo = plan_pseudo ? plan_pseudo->n_genes : 0;
+    // The two EM launches are independent.  The real genes go first on the caller's stream; the pseudo-genes run beside
+    // them on the context's side stream: both kernels are persistent (every SM full), so the pseudo-gene CTAs move in as
+    // the real-gene kernel's CTAs drain and its tail costs nothing.  The caller's stream joins before the p-values.
+    const bool both = n_pseudo > 0 && plan_real->n_genes > 0;
+    cudaStream_t pst = both ? ctx->side_stream : st;
+    if (both) {
+        if ((e = cudaEventRecord(ctx->side_fork, st)) != cudaSuccess) return cuda_fail(e, "cudaEventRecord");
+        if ((e = cudaStreamWaitEvent(ctx->side_stream, ctx->side_fork, 0)) != cudaSuccess) return cuda_fail(e, "cudaStreamWaitEvent");
+    }
+    if (plan_real->n_genes > 0) {
+        if ((rc = em_check_io(plan_real, params, &io->real)) != JACKS_OK) return rc;
+        if ((e = cudaMemsetAsync(plan_real->b->d_counters.p, 0, kCountersPerRange * sizeof(int), st)) != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync");
+        if ((rc = em_run_range(ctx, plan_real, params, &io->real, st, 0, plan_real->n_genes, 0)) != JACKS_OK) return rc;
+    }
     if (n_pseudo > 0) {
         if (plan_pseudo->L != L || plan_pseudo->n_rows != plan_real->n_rows) return fail(JACKS_E_INVALID, "the two plans describe different cubes");
         if (!io->pseudo_w1) return fail(JACKS_E_INVALID, "pseudo_w1 is required when there are pseudo-genes");
@@ -902,13 +922,13 @@ extern "C" int jacks_run_screen_device(JacksCtx* ctx, const JacksEmPlan* plan_re
         pio.ctrl_rowmean_fill = io->real.ctrl_rowmean_fill;
         pio.w1 = io->pseudo_w1; pio.w2 = io->pseudo_w2; pio.n_iters = io->pseudo_n_iters;
         if ((rc = em_check_io(plan_pseudo, params, &pio)) != JACKS_OK) return rc;
-        if ((e = cudaMemsetAsync(plan_pseudo->b->d_counters.p, 0, kCountersPerRange * sizeof(int), st)) != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync");
-        if ((rc = em_run_range(ctx, plan_pseudo, params, &pio, st, 0, n_pseudo, 0)) != JACKS_OK) return rc;
-    }
-    if (plan_real->n_genes > 0) {
-        if ((rc = em_check_io(plan_real, params, &io->real)) != JACKS_OK) return rc;
-        if ((e = cudaMemsetAsync(plan_real->b->d_counters.p, 0, kCountersPerRange * sizeof(int), st)) != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync");
-        if ((rc = em_run_range(ctx, plan_real, params, &io->real, st, 0, plan_real->n_genes, 0)) != JACKS_OK) return rc;
+        if ((e = cudaMemsetAsync(plan_pseudo->b->d_counters.p, 0, kCountersPerRange * sizeof(int), pst)) != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync");
+        rc = em_run_range(ctx, plan_pseudo, params, &pio, pst, 0, n_pseudo, 0);
+        if (both) {        // join even after a failed launch: the side stream must not be left dangling behind the caller's
+            cudaEventRecord(ctx->side_join, ctx->side_stream);
+            cudaStreamWaitEvent(st, ctx->side_join, 0);
+        }
+        if (rc != JACKS_OK) return rc;
     }
     if (io->pvals || io->pseudo_pvals) {
         if (n_pseudo < 2) return fail(JACKS_E_INVALID, "p-values need at least two pseudo-genes (got %lld)", (long long)n_pseudo);

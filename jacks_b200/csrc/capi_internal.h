@@ -63,6 +63,9 @@ struct JacksCtx {
     cudaStream_t copy_stream;   // host -> device copies of the pipelined host entry points
     cudaStream_t out_stream;    // device -> host copies of the pipelined host entry points
     cudaStream_t plan_stream = nullptr;   // uploads of gene indexes (jacks_em_plan_create)
+    cudaStream_t side_stream = nullptr;   // second kernel stream of jacks_run_screen_device: the pseudo-gene EM runs beside the
+    cudaEvent_t side_fork = nullptr;      // real-gene EM, so that its CTAs fill the SMs the other kernel's tail leaves idle
+    cudaEvent_t side_join = nullptr;
     cudaEvent_t res_busy = nullptr;       // the kernels that read the resident cubes (res_test / res_ctrl) have run
     // data cubes kept resident between host calls (jacks_em_batched_host keep_resident)
     jacks::DevBuf res_test, res_ctrl, res_fx;

@@ -39,7 +39,7 @@ int em_fast_single_warp_genes(int G, int L) {
     const int cols = tmem_cols_for(G, L, 1);
     const long long team = em_fast_tmem_team_doubles(G, L) * (long long)sizeof(double);
     if (cols > 0 && team * kTmemTeams <= (long long)kMaxDynSmem) {
-        const long long ctas = std::min<long long>(std::min<long long>((long long)kMaxDynSmem / (team * kTmemTeams), 512 / cols), 2);
+        const long long ctas = std::min<long long>(std::min<long long>((long long)kMaxDynSmem / (team * kTmemTeams), 512 / cols), JACKS_TM_CTAS);
         genes = std::max(genes, ctas * kTmemTeams);
     }
     return (int)genes;

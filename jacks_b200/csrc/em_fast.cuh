@@ -271,13 +271,19 @@ __device__ __forceinline__ void em_sweep(const uint32_t tcol, const uint32_t pco
                 pd[u][g] = __hiloint2double((int)praw[2 * (u * G + g) + 1], (int)praw[2 * (u * G + g)]);
     }
 #endif
+    // JACKS_RCP2 (developer A/B, off): one quadratic Newton step instead of the cubic one, 12 instead of 13 FP64
+    // instructions per element: 6.46 -> 6.16 ms per Avana pass with identical pass counts, but the seed carries only
+    // 20 bits, tau comes out 1e-12 off and gene scores that cancel to |w1| ~ 1e-6 miss the 1e-6 RELATIVE bar
+    // (the full-size Avana parity test: worst 3.3e-6; 1.2e-6 with a zeroed low seed word).  Rejected.
     double r[U], e[U];
 #pragma unroll
     for (int u = 0; u < U; ++u) asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r[u]) : "d"(sa[u]));
 #pragma unroll
     for (int u = 0; u < U; ++u) e[u] = fma(-sa[u], r[u], 1.0);
+#ifndef JACKS_RCP2
 #pragma unroll
     for (int u = 0; u < U; ++u) e[u] = fma(e[u], e[u], e[u]);
+#endif
 #pragma unroll
     for (int u = 0; u < U; ++u) r[u] = fma(r[u], e[u], r[u]);
     double w1[U], w2[U];
@@ -307,10 +313,12 @@ __device__ __forceinline__ void em_sweep(const uint32_t tcol, const uint32_t pco
     for (int u = 0; u < U; ++u)
 #pragma unroll
         for (int g = 0; g < G; ++g) ee[u][g] = fma(-d[u][g], rd[u][g], 1.0);
+#ifndef JACKS_RCP2
 #pragma unroll
     for (int u = 0; u < U; ++u)
 #pragma unroll
         for (int g = 0; g < G; ++g) ee[u][g] = fma(ee[u][g], ee[u][g], ee[u][g]);
+#endif
 #pragma unroll
     for (int u = 0; u < U; ++u)
 #pragma unroll
@@ -366,6 +374,9 @@ template <int G> struct EmSums { double a1[G], a2[G], ab; };
 // Lines per sweep step: U*G >= 8 independent elements, and few enough (<= 20) to stay in registers
 // (measured at 400 lines: G = 5 wants 3 lines from shared memory, 4 from TMEM; G = 6 wants 3 either way).
 template <int G, int TM> __host__ __device__ constexpr int em_sweep_lines() {
+#ifdef JACKS_UMAX_TM
+    if (TM && G <= 4) return JACKS_UMAX_TM;
+#endif
     return (G >= 9) ? 1 : (G >= 7) ? 2 : ((G >= (TM ? 6 : 5)) ? 3 : 4);
 }
 
@@ -386,10 +397,11 @@ template <int G, int TM> __host__ __device__ constexpr int em_sweep_lines() {
 template <int G, int STEP, bool UNIT_C, int TM, int B, bool WS>
 __device__ __noinline__ EmSums<G> em_sweep_all(const uint32_t tbase, const uint32_t pdoff, const double* ys, const double* tpdg, const int Lp, double* ths,
                                                double* w1p, double* w2g, const int L, const int l0,
-                                               const int n_big, const EmXs<G> x, const double ivw, const double mw,
+                                               const int n_big, const EmXs<G> x_in, const double ivw, const double mw,
                                                const double c_tau) {
     constexpr int UMAX = em_sweep_lines<G, TM>();
     constexpr int UP = UMAX;
+    const EmXs<G>& x = x_in;
     double a1[G], a2[G], ab[G];
 #pragma unroll
     for (int g = 0; g < G; ++g) { a1[g] = 0.0; a2[g] = 0.0; ab[g] = 0.0; }
@@ -669,6 +681,9 @@ __host__ __device__ constexpr long long em_fast_smem_doubles(int G, int W, int L
 // tile and totals, rounded to 128 bytes.  Two CTAs (eight genes) per SM: with three, the 168-register budget makes
 // ptxas spill in the sweep, and 12 genes at 3 lines per step measured no faster than 8 at 4 (7.9 ms at L = 400).
 constexpr int kTmemTeams = 4;
+#ifndef JACKS_TM_CTAS
+#define JACKS_TM_CTAS 2
+#endif
 __host__ __device__ constexpr long long em_fast_tmem_team_doubles(int G, int L, bool ws = false) {
     // ws: plus (E[w], E[w^2]) pairs of the running pass, [L][2]
     return ((long long)G * L + (2 * G + 1) * 33 + 2 * (2 * G + 1) + (ws ? 2LL * L : 0) + 15) / 16 * 16;
@@ -698,7 +713,7 @@ __device__ __forceinline__ void prefetch_gene_l2(const double2* test, const doub
 // Nothing synchronises the teams between the TMEM allocation at the start and its release at the end.
 // TM: 0 shared-memory variant; 1 tau in TMEM; 2 tau and tau_pr_den in TMEM (no global slab, no L2 traffic in a pass).
 template <int G, int W, bool UNIT_C, bool PLAIN, int TM, bool WS = false>
-__global__ void __launch_bounds__(TM ? kTmemTeams * 32 : W * 32, TM ? 2 : 0) em_fast_kernel(const EmLaunch a) {
+__global__ void __launch_bounds__(TM ? kTmemTeams * 32 : W * 32, TM ? JACKS_TM_CTAS : 0) em_fast_kernel(const EmLaunch a) {
     static_assert(!TM || W == 1, "the TMEM variant runs one-warp teams");
     static_assert(!WS || TM == 2, "E[w] is kept in shared memory by the tensor-memory mode 2 kernel only");
     constexpr int NV = 2 * G + 1;

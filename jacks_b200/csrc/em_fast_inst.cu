@@ -61,11 +61,11 @@ int tmem_mode(const EmLaunch& a) {
     const int cols1 = tmem_cols_for(G, a.L, 1), cols2 = tmem_cols_for(G, a.L, 2);
     if (by_smem < 1 || cols1 == 0) return 0;
     const long long genes_smem = std::min<long long>(kMaxDynSmem / ((size_t)em_fast_smem_doubles(G, 1, a.L) * sizeof(double)), kMaxFastCtasPerSm);
-    const long long genes1 = std::min<long long>(std::min<long long>(by_smem, 512 / cols1), 2) * kTmemTeams;
-    const long long genes2 = cols2 ? std::min<long long>(std::min<long long>(by_smem, 512 / cols2), 2) * kTmemTeams : 0;
+    const long long genes1 = std::min<long long>(std::min<long long>(by_smem, 512 / cols1), JACKS_TM_CTAS) * kTmemTeams;
+    const long long genes2 = cols2 ? std::min<long long>(std::min<long long>(by_smem, 512 / cols2), JACKS_TM_CTAS) * kTmemTeams : 0;
     if (force == 2) return genes2 ? 2 : 1;
     if (force == 1) return 1;
-    if (genes2 == 2 * kTmemTeams && a.L >= 32) return 2;
+    if (genes2 >= 2 * kTmemTeams && a.L >= 32) return 2;
     if (genes1 > genes_smem) return 1;
     return 0;
 }
@@ -79,7 +79,7 @@ cudaError_t launch_inst(const EmLaunch& a, int n_sm, int grid_limit, cudaStream_
             // G = 4); JACKS_EM_WSMEM=0/1 forces the choice where it fits (tests, tuning)
             static const int force_ws = []() { const char* e = getenv("JACKS_EM_WSMEM"); return e ? atoi(e) : -1; }();
             const size_t smem_ws = (size_t)em_fast_tmem_team_doubles(G, a.L, true) * kTmemTeams * sizeof(double);
-            const bool fits = 2 * (smem_ws + 2048) <= 228 * 1024;
+            const bool fits = JACKS_TM_CTAS * (smem_ws + 2048) <= 228 * 1024;
             if (fits && force_ws != 0) return launch_tmem<G, UNIT_C, PLAIN, 2, true>(a, n_sm, grid_limit, st, grid_out);
             return launch_tmem<G, UNIT_C, PLAIN, 2>(a, n_sm, grid_limit, st, grid_out);
         }

@@ -85,6 +85,7 @@ class NativeEngine(object):
         self.device = torch.device('cuda', int(device))
         self.ctx = _native.context(int(device))
         self._plans = {}
+        self._side = None
 
     def upload(self, array):
         """Host array -> device tensor (through a pinned copy when the source is pageable)."""
@@ -100,8 +101,23 @@ class NativeEngine(object):
             self._plans[key] = p
         return self._plans[key]
 
-    def em(self, plan, test, ctrl, params, fixed_x1=None, fixed_x2=None, want_x=True, y_tau=False, w1_out=None):
-        """w1_out: an [n, L] device view E[w] is written into (the exchange buffer), instead of a fresh tensor."""
+    def fork(self):
+        """Open a side stream behind everything enqueued so far: a second EM launched with side=True runs BESIDE the
+        kernels enqueued on the current stream afterwards (both are persistent kernels, so its CTAs move in as the first
+        kernel's drain -- the first kernel's tail costs nothing).  join() makes the current stream wait for it."""
+        torch = self.torch
+        if self._side is None:
+            self._side = torch.cuda.Stream(device=self.device)
+        self._side.wait_stream(torch.cuda.current_stream(self.device))
+
+    def join(self):
+        if self._side is not None:
+            self.torch.cuda.current_stream(self.device).wait_stream(self._side)
+
+    def em(self, plan, test, ctrl, params, fixed_x1=None, fixed_x2=None, want_x=True, y_tau=False, w1_out=None, side=False):
+        """w1_out: an [n, L] device view E[w] is written into (the exchange buffer), instead of a fresh tensor.
+        side: launch on the side stream opened by fork() (the outputs are allocated on the current stream; the caller
+        join()s before it reads or drops them)."""
         torch, nat = self.torch, self.nat
         n, T, L = plan.n_genes, plan.total_guides, plan.n_lines
         f64 = dict(dtype=torch.float64, device=self.device)
@@ -119,7 +135,7 @@ class NativeEngine(object):
             io.fixed_x1, io.fixed_x2 = fixed_x1.data_ptr(), fixed_x2.data_ptr()
         for k, v in out.items():
             setattr(io, k, v.data_ptr())
-        plan.run_device(params, io, torch.cuda.current_stream().cuda_stream)
+        plan.run_device(params, io, (self._side if side else torch.cuda.current_stream()).cuda_stream)
         out['_keep'] = (test, ctrl, fixed_x1, fixed_x2)
         return out
 
@@ -155,7 +171,13 @@ class HostEngine(object):
         p.n_genes, p.total_guides, p.n_lines = len(p.offsets) - 1, int(p.offsets[-1]) if len(p.offsets) else 0, n_lines
         return p
 
-    def em(self, plan, test, ctrl, params, fixed_x1=None, fixed_x2=None, want_x=True, y_tau=False, w1_out=None):
+    def fork(self):
+        pass
+
+    def join(self):
+        pass
+
+    def em(self, plan, test, ctrl, params, fixed_x1=None, fixed_x2=None, want_x=True, y_tau=False, w1_out=None, side=False):
         t = self.torch
         L = plan.n_lines
         if plan.n_genes == 0:
@@ -287,10 +309,13 @@ class ShardedScreen(object):
         if do_p:
             # one exchange buffer for both: [real | pseudo] E[w] of my genes, written by the kernels themselves
             both = t.empty((n_lr + n_lp, L), dtype=t.float64, device=eng.device)
+            eng.fork()
             real = eng.em(self.plan_real, self.d_test, self.d_ctrl, self.params, self.d_fx1, self.d_fx2, want_x=True, w1_out=both[:n_lr])
             if W > 1:
                 early = gather_em(real)
-            pseudo = eng.em(self.plan_pseudo, self.d_test, self.d_ctrl, self.params, want_x=False, w1_out=both[n_lr:])
+            # beside the real genes, on the side stream: no kernel tail between the two launches
+            pseudo = eng.em(self.plan_pseudo, self.d_test, self.d_ctrl, self.params, want_x=False, w1_out=both[n_lr:], side=True)
+            eng.join()
             gb = np.concatenate([[0], np.cumsum([(self.b[s + 1] - self.b[s]) + (self.bp[s + 1] - self.bp[s]) for s in range(W)])])
             mine = self._lines_of_all_genes(both, gb)                        # [(real_s, pseudo_s) for s in ranks, my lines]
             parts_r, parts_p, o = [], [], 0
