@@ -375,7 +375,24 @@ def sharded_parity(torch, dist, jd, _native, local_rank, rank, world):
             ref = _native.run_screen_host(_native.context(local_rank), w['offs'], w['rows'], w['poffs'], w['prows'], w['test'], ctrl,
                                           want=('x1', 'x2', 'w1', 'w2', 'n_iters', 'pvals'))
             for k in ('x1', 'x2', 'w1', 'w2', 'n_iters', 'pvals'):
-                ok = ok and bool(np.array_equal(res[k].cpu().numpy(), ref[k], equal_nan=True))
+                same = bool(np.array_equal(res[k].cpu().numpy(), ref[k], equal_nan=True))
+                if not same:
+                    sys.stderr.write('sharded_parity: gathered %s differs from the unsharded call\n' % k)
+                ok = ok and same
+        # ... and the gather-free delivery into shared host memory (the e2e path)
+        host = jd.SharedHostResults(job.n_genes, job.T, job.L)
+        arr = job.run_to_host(host)
+        if rank == 0:
+            for k in ('x1', 'x2', 'w1', 'w2', 'n_iters', 'pvals'):
+                same = bool(np.array_equal(arr[k], ref[k], equal_nan=True))
+                if not same:
+                    bad = np.argwhere(~((arr[k] == ref[k]) | (np.isnan(arr[k]) & np.isnan(ref[k]))))
+                    sys.stderr.write('sharded_parity: shared-host %s differs from the unsharded call at %d places, first %s\n'
+                                     % (k, len(bad), bad[:3].tolist()))
+                ok = ok and same
+        del arr
+        dist.barrier()
+        host.close()
     flag = torch.tensor([1 if ok else 0], dtype=torch.int32, device=torch.device('cuda', local_rank))
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     dist.broadcast(flag, src=0)
@@ -392,6 +409,7 @@ def main():
     ap.add_argument('--ref-genes-per-core', dest='ref_genes_per_core', type=int, default=1200)
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-aux', action='store_true')
+    ap.add_argument('--parity-only', action='store_true')
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == 'ours' else args.warmup
 
@@ -441,6 +459,11 @@ def main():
     parity = None
     if world > 1 and strong:
         parity = sharded_parity(torch, dist, jd, _native, local_rank, rank, world)
+        if args.parity_only:
+            if rank == 0:
+                print(json.dumps({'sharded_parity': parity}), flush=True)
+            dist.destroy_process_group()
+            sys.exit(0 if parity else 3)
 
     # ---- this rank's share of the screen, resident on the device -------------------------------------------------------
     # strong: gene blocks of ONE screen, each rank holding only the rows its genes reference (dist.ShardedScreen);
@@ -574,28 +597,23 @@ def main():
         api = 'jacks_run_screen_host (C-ABI): pinned host cubes, control as [N,1,2]; real + pseudo EM + 7.2 M p-values; ' \
               'x1, x2, w1, w2, n_iters, pvals downloaded'
     else:
-        # N ranks: each uploads the rows of its shard (pinned), rank 0 downloads the gathered results
+        # N ranks: each uploads the rows of its shard (pinned) and delivers the rows of its own genes into ONE shared,
+        # page-locked host segment that rank 0 reads in place (dist.SharedHostResults): no gather, eight PCIe links
         pins = [torch.from_numpy(np.ascontiguousarray(np.asarray(w['test'])[job.used])).pin_memory(),
                 torch.from_numpy(np.ascontiguousarray(np.asarray(w['ctrl1'])[job.used])).pin_memory()]
-        host_out = {}
+        host = jd.SharedHostResults(job.n_genes, job.T, L)
         h2d = sum(p.numel() * 8 for p in pins)
-        d2h = 0
+        n_mine, t_mine = int(job.b[rank + 1] - job.b[rank]), int(job.bt[rank + 1] - job.bt[rank])
+        d2h = 8 * (3 * n_mine * L + 2 * t_mine) + 4 * n_mine
 
         def e2e_step():
             job.d_test.copy_(pins[0], non_blocking=True)
             job.d_ctrl.copy_(pins[1], non_blocking=True)
-            res = job.run()
-            if res is not None:
-                for k, v in res.items():
-                    if k not in host_out:
-                        host_out[k] = torch.empty(v.shape, dtype=v.dtype).pin_memory()
-                    host_out[k].copy_(v, non_blocking=True)
-            torch.cuda.synchronize()
-        api = 'jacks_b200.dist.ShardedScreen: every rank uploads the rows of its gene blocks from pinned memory, EM -> all-to-all -> ' \
-              'p-values -> gather; rank 0 downloads w1, w2, x1, x2, n_iters, pvals'
+            job.run_to_host(host)
+        api = 'jacks_b200.dist.ShardedScreen.run_to_host: every rank uploads the rows of its gene blocks from pinned memory, EM -> ' \
+              'all-to-all -> p-values -> all-to-all back, and copies w1, w2, x1, x2, n_iters, pvals of ITS genes into one shared ' \
+              'page-locked host segment (no gather; rank 0 reads the assembled arrays in place)'
     e2e_step()
-    if world > 1:
-        d2h = sum(v.numel() * v.element_size() for v in host_out.values())
     fence()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):

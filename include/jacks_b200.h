@@ -96,6 +96,12 @@ JACKS_API void jacks_em_default_params(JacksEmParams* p);
 /* Pinned host memory for callers that want direct DMA on the host entry points. */
 JACKS_API int jacks_host_alloc(void** out, uint64_t bytes);
 JACKS_API void jacks_host_free(void* p);
+/* Page-lock host memory the CALLER owns -- e.g. a shared-memory segment that the rank processes of one node all map, so
+ * that every rank delivers its slice of the per-gene results (the dict inferJACKS returns, infer.py:28) over its own
+ * PCIe link -- and undo it.  jacks_copy_to_host_async enqueues a device -> host copy on `stream` (a cudaStream_t). */
+JACKS_API int jacks_host_register(void* p, uint64_t bytes);
+JACKS_API int jacks_host_unregister(void* p);
+JACKS_API int jacks_copy_to_host_async(void* dst_host, const void* src_device, uint64_t bytes, void* stream);
 
 /*
  * Build a plan for a gene index (the gene_index dict of inferJACKS, infer.py:18-21, in CSR form).

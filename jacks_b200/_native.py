@@ -86,6 +86,9 @@ def lib():
         L.jacks_host_alloc.argtypes = [C.POINTER(vp), C.c_uint64]
         L.jacks_host_free.argtypes = [vp]
         L.jacks_host_free.restype = None
+        L.jacks_host_register.argtypes = [vp, C.c_uint64]
+        L.jacks_host_unregister.argtypes = [vp]
+        L.jacks_copy_to_host_async.argtypes = [vp, vp, C.c_uint64, vp]
         L.jacks_em_plan_create.argtypes = [vp, vp, vp, i64, i64, i32, C.POINTER(vp)]
         L.jacks_em_plan_destroy.argtypes = [vp]
         L.jacks_em_plan_destroy.restype = None

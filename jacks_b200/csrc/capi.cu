@@ -270,6 +270,25 @@ int jacks_host_alloc(void** out, uint64_t bytes) {
 }
 void jacks_host_free(void* p) { if (p) cudaFreeHost(p); }
 
+int jacks_host_register(void* p, uint64_t bytes) {
+    if (!p || bytes == 0) return fail(JACKS_E_INVALID, "jacks_host_register: empty range");
+    const cudaError_t e = cudaHostRegister(p, (size_t)bytes, cudaHostRegisterPortable);
+    return e == cudaSuccess ? JACKS_OK : cuda_fail(e, "cudaHostRegister");
+}
+
+int jacks_host_unregister(void* p) {
+    if (!p) return JACKS_OK;
+    const cudaError_t e = cudaHostUnregister(p);
+    return e == cudaSuccess ? JACKS_OK : cuda_fail(e, "cudaHostUnregister");
+}
+
+int jacks_copy_to_host_async(void* dst_host, const void* src_device, uint64_t bytes, void* stream) {
+    if (bytes == 0) return JACKS_OK;
+    if (!dst_host || !src_device) return fail(JACKS_E_INVALID, "jacks_copy_to_host_async: NULL pointer");
+    const cudaError_t e = cudaMemcpyAsync(dst_host, src_device, (size_t)bytes, cudaMemcpyDeviceToHost, (cudaStream_t)stream);
+    return e == cudaSuccess ? JACKS_OK : cuda_fail(e, "cudaMemcpyAsync (device -> host)");
+}
+
 int jacks_em_plan_create(JacksCtx* ctx, const int64_t* gene_offsets, const int32_t* guide_rows, int64_t n_genes,
                          int64_t n_rows, int32_t n_lines, JacksEmPlan** out) {
     if (!ctx || !out) return fail(JACKS_E_INVALID, "jacks_em_plan_create: NULL ctx/out");

@@ -18,6 +18,8 @@ Nothing is reduced across ranks and every per-line sum runs over the pseudo-gene
 N-rank results are bit-identical.  All buffers between steps 2 and 5 stay on the device; under the gloo backend (CPU
 tests) the same driver runs on host tensors with an injected engine (CPU restatements of the kernels).
 """
+import os
+
 import numpy as np
 
 
@@ -86,6 +88,7 @@ class NativeEngine(object):
         self.ctx = _native.context(int(device))
         self._plans = {}
         self._side = None
+        self._down, self._down_keep = None, []
 
     def upload(self, array):
         """Host array -> device tensor (through a pinned copy when the source is pageable)."""
@@ -116,28 +119,51 @@ class NativeEngine(object):
 
     def em(self, plan, test, ctrl, params, fixed_x1=None, fixed_x2=None, want_x=True, y_tau=False, w1_out=None, side=False):
         """w1_out: an [n, L] device view E[w] is written into (the exchange buffer), instead of a fresh tensor.
-        side: launch on the side stream opened by fork() (the outputs are allocated on the current stream; the caller
-        join()s before it reads or drops them)."""
+        side: launch on the side stream opened by fork(); the caller join()s before the current stream reads the results."""
         torch, nat = self.torch, self.nat
         n, T, L = plan.n_genes, plan.total_guides, plan.n_lines
         f64 = dict(dtype=torch.float64, device=self.device)
-        out = dict(w1=w1_out if w1_out is not None else torch.empty((n, L), **f64), w2=torch.empty((n, L), **f64),
-                   n_iters=torch.empty(n, dtype=torch.int32, device=self.device))
-        if want_x:
-            out['x1'], out['x2'] = torch.empty(T, **f64), torch.empty(T, **f64)
-        if y_tau:
-            out['y'], out['tau'] = torch.empty((T, L), **f64), torch.empty((T, L), **f64)
-        if n == 0:
-            return out
-        io = nat.EmDeviceIO()
-        io.test, io.ctrl, io.ctrl_lines = test.data_ptr(), ctrl.data_ptr(), int(ctrl.shape[1])
-        if fixed_x1 is not None:
-            io.fixed_x1, io.fixed_x2 = fixed_x1.data_ptr(), fixed_x2.data_ptr()
-        for k, v in out.items():
-            setattr(io, k, v.data_ptr())
-        plan.run_device(params, io, (self._side if side else torch.cuda.current_stream()).cuda_stream)
+        # side: the outputs come from the SIDE stream's pool -- a block the current stream has just freed (a temporary of
+        # the gather, say) may still be read by kernels the side stream does not wait for
+        with torch.cuda.stream(self._side if side else torch.cuda.current_stream(self.device)):
+            out = dict(w1=w1_out if w1_out is not None else torch.empty((n, L), **f64), w2=torch.empty((n, L), **f64),
+                       n_iters=torch.empty(n, dtype=torch.int32, device=self.device))
+            if want_x:
+                out['x1'], out['x2'] = torch.empty(T, **f64), torch.empty(T, **f64)
+            if y_tau:
+                out['y'], out['tau'] = torch.empty((T, L), **f64), torch.empty((T, L), **f64)
+            if n == 0:
+                return out
+            io = nat.EmDeviceIO()
+            io.test, io.ctrl, io.ctrl_lines = test.data_ptr(), ctrl.data_ptr(), int(ctrl.shape[1])
+            if fixed_x1 is not None:
+                io.fixed_x1, io.fixed_x2 = fixed_x1.data_ptr(), fixed_x2.data_ptr()
+            for k, v in out.items():
+                setattr(io, k, v.data_ptr())
+            plan.run_device(params, io, torch.cuda.current_stream(self.device).cuda_stream)
         out['_keep'] = (test, ctrl, fixed_x1, fixed_x2)
         return out
+
+    def to_host(self, dst, src):
+        """Enqueue the copy of device tensor ``src`` into the numpy view ``dst`` (contiguous, page-locked: SharedHostResults)
+        on this engine's download stream, behind everything enqueued on the current stream so far."""
+        import ctypes as C
+        torch = self.torch
+        if src.numel() == 0:
+            return
+        assert dst.flags['C_CONTIGUOUS'] and src.is_contiguous() and dst.nbytes == src.numel() * src.element_size()
+        if self._down is None:
+            self._down = torch.cuda.Stream(device=self.device)
+        self._down.wait_stream(torch.cuda.current_stream(self.device))
+        self.nat.check(self.nat.lib().jacks_copy_to_host_async(C.c_void_p(dst.ctypes.data), C.c_void_p(src.data_ptr()),
+                                                               dst.nbytes, C.c_void_p(self._down.cuda_stream)))
+        self._down_keep.append(src)
+
+    def host_done(self):
+        """Wait for the copies enqueued by to_host()."""
+        if self._down is not None:
+            self._down.synchronize()
+        del self._down_keep[:]
 
     def kde(self, w1_genes, w1_pseudo, positive):
         import ctypes as C
@@ -191,6 +217,12 @@ class HostEngine(object):
             out['w1'] = w1_out
         return out
 
+    def to_host(self, dst, src):
+        dst[...] = src.numpy().reshape(dst.shape)
+
+    def host_done(self):
+        pass
+
     def kde(self, w1_genes, w1_pseudo, positive):
         if w1_genes.shape[0] == 0 or w1_genes.shape[1] == 0:
             return self.torch.zeros(tuple(w1_genes.shape), dtype=self.torch.float64)
@@ -200,6 +232,70 @@ class HostEngine(object):
 # ----------------------------------------------------------------------------------------------------------------------
 # The sharded screen job
 # ----------------------------------------------------------------------------------------------------------------------
+class SharedHostResults(object):
+    """The result arrays of one screen -- w1, w2, pvals [n, L]; x1, x2 [sum G]; n_iters [n] -- in ONE shared-memory segment
+    that every rank process of the node maps and page-locks.  With it ShardedScreen.run_to_host() needs no gather at all:
+    each rank copies the rows of its own genes down over its own PCIe link and rank ``owner`` reads the assembled arrays
+    in place (the 174 MB of an Avana-shaped screen leave the node's eight GPUs in parallel instead of queueing on one
+    link behind an NVLink gather).  Collective over ``group``: construct and close() on every rank."""
+
+    FIELDS = (('w1', 'nL', np.float64), ('w2', 'nL', np.float64), ('pvals', 'nL', np.float64), ('x1', 'T', np.float64),
+              ('x2', 'T', np.float64), ('n_iters', 'n', np.int32))
+
+    def __init__(self, n_genes, total_guides, n_lines, group=None, owner=0, register=True):
+        import mmap
+        import torch.distributed as dist
+        world, rank = _world(group)
+        self.group, self.owner, self.rank = group, owner, rank
+        n, T, L = int(n_genes), int(total_guides), int(n_lines)
+        shapes = {'nL': (n, L), 'T': (T,), 'n': (n,)}
+        offs, o = {}, 0
+        for name, kind, dt in self.FIELDS:
+            offs[name] = o
+            o += (int(np.prod(shapes[kind], dtype=np.int64)) * np.dtype(dt).itemsize + 255) // 256 * 256
+        self.nbytes = max(o, 256)
+        path = [None]
+        if rank == owner:
+            path[0] = '/dev/shm/jacks_b200_%d_%s' % (os.getpid(), os.urandom(6).hex())
+            fd = os.open(path[0], os.O_CREAT | os.O_EXCL | os.O_RDWR, 0o600)
+            os.ftruncate(fd, self.nbytes)
+        if world > 1:
+            dist.broadcast_object_list(path, src=owner, group=group)
+        if rank != owner:
+            fd = os.open(path[0], os.O_RDWR)
+        self._map = mmap.mmap(fd, self.nbytes)
+        os.close(fd)
+        if world > 1:
+            dist.barrier(group=group)
+        if rank == owner:
+            os.unlink(path[0])                   # every rank holds its mapping: nothing is left behind if a rank dies
+        base = np.frombuffer(self._map, dtype=np.uint8)
+        self.arrays = {}
+        for name, kind, dt in self.FIELDS:
+            size = int(np.prod(shapes[kind], dtype=np.int64))
+            self.arrays[name] = base[offs[name]:offs[name] + size * np.dtype(dt).itemsize].view(dt).reshape(shapes[kind])
+        self._registered = None
+        if register:
+            from . import _native
+            import ctypes as C
+            self._registered = C.c_void_p(base.ctypes.data)
+            _native.check(_native.lib().jacks_host_register(self._registered, self.nbytes))
+
+    def __getitem__(self, key):
+        return self.arrays[key]
+
+    def close(self):
+        if self._registered is not None:
+            from . import _native
+            _native.lib().jacks_host_unregister(self._registered)
+            self._registered = None
+        self.arrays = {}
+        try:
+            self._map.close()
+        except BufferError:
+            pass                                 # a caller still holds a view: the mapping goes with it
+
+
 class ShardedScreen(object):
     """One screen, sharded over the ranks of ``group``: build once (index split, compact upload, plans), run() many times.
 
@@ -366,6 +462,66 @@ class ShardedScreen(object):
                 blocks.append(recv_pv[o:o + self.n_genes * l_s].view(self.n_genes, l_s)); o += self.n_genes * l_s
             res['pvals'] = t.cat(blocks, dim=1)
         return res
+
+    def run_to_host(self, host, want_pvals=True):
+        """Steps 2-5 with the results delivered to ``host`` (SharedHostResults) and NO gather: every rank copies the rows
+        of its own genes -- E[w], E[w^2], x, pass counts right behind the real-gene EM, travelling under the pseudo-gene
+        EM; p-values after a second all-to-all has turned [all genes, my lines] back into [my genes, all lines] -- and a
+        barrier tells rank ``owner`` the arrays are complete.  Returns the arrays (numpy views) on every rank."""
+        import torch.distributed as dist
+        t, eng = self.torch, self.engine
+        W, r, L = self.world, self.rank, self.L
+        do_p = bool(want_pvals and self.has_pseudo and self.n_pseudo >= 2)
+        lo, hi = int(self.b[r]), int(self.b[r + 1])
+        tlo, thi = int(self.bt[r]), int(self.bt[r + 1])
+        n_lr, n_lp = hi - lo, int(self.bp[r + 1] - self.bp[r])
+
+        def deliver(real):
+            eng.to_host(host['w1'][lo:hi], real['w1'])
+            eng.to_host(host['w2'][lo:hi], real['w2'])
+            eng.to_host(host['x1'][tlo:thi], real['x1'])
+            eng.to_host(host['x2'][tlo:thi], real['x2'])
+            eng.to_host(host['n_iters'][lo:hi], real['n_iters'])
+        if do_p:
+            both = t.empty((n_lr + n_lp, L), dtype=t.float64, device=eng.device)
+            eng.fork()
+            real = eng.em(self.plan_real, self.d_test, self.d_ctrl, self.params, self.d_fx1, self.d_fx2, want_x=True, w1_out=both[:n_lr])
+            deliver(real)
+            pseudo = eng.em(self.plan_pseudo, self.d_test, self.d_ctrl, self.params, want_x=False, w1_out=both[n_lr:], side=True)
+            eng.join()
+            gb = np.concatenate([[0], np.cumsum([(self.b[s + 1] - self.b[s]) + (self.bp[s + 1] - self.bp[s]) for s in range(W)])])
+            mine = self._lines_of_all_genes(both, gb)
+            parts_r, parts_p, o = [], [], 0
+            for s in range(W):
+                nr, npz = int(self.b[s + 1] - self.b[s]), int(self.bp[s + 1] - self.bp[s])
+                parts_r.append(mine[o:o + nr]); o += nr
+                parts_p.append(mine[o:o + npz]); o += npz
+            g_block = t.cat(parts_r) if W > 1 else parts_r[0]
+            p_block = t.cat(parts_p) if W > 1 else parts_p[0]
+            pv_block = eng.kde(g_block.contiguous(), p_block.contiguous(), self.positive)        # [n_genes, my lines]
+            # back: rank s receives the rows of ITS genes from every line block
+            my_l = int(self.lb[r + 1] - self.lb[r])
+            recv = self._all_to_all(pv_block.reshape(-1), [int(self.b[s + 1] - self.b[s]) * my_l for s in range(W)],
+                                    [n_lr * int(self.lb[s + 1] - self.lb[s]) for s in range(W)])
+            if W > 1:
+                cols, o = [], 0
+                for s in range(W):
+                    l_s = int(self.lb[s + 1] - self.lb[s])
+                    cols.append(recv[o:o + n_lr * l_s].view(n_lr, l_s)); o += n_lr * l_s
+                pv_mine = t.cat(cols, dim=1)
+            else:
+                pv_mine = recv.view(n_lr, L)
+            eng.to_host(host['pvals'][lo:hi], pv_mine.contiguous())
+            self.exchange_bytes = (both.numel() + pv_block.numel()) * 8 * (W - 1) // W
+            del pseudo
+        else:
+            real = eng.em(self.plan_real, self.d_test, self.d_ctrl, self.params, self.d_fx1, self.d_fx2, want_x=True)
+            deliver(real)
+            self.exchange_bytes = 0
+        eng.host_done()
+        if W > 1:
+            dist.barrier(group=self.group)
+        return host.arrays
 
 
 def run_screen_sharded(offsets, rows, pseudo_offsets, pseudo_rows, testdata, ctrldata, engine=None, group=None, device=None,

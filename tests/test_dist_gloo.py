@@ -52,6 +52,17 @@ def _screen_job(rank, world):
             ok = ok and np.array_equal(res['pvals'].numpy(), pv, equal_nan=True)
         else:
             ok = ok and res is None
+        # the gather-free delivery: every rank writes the rows of its own genes into one shared host segment
+        host = jd.SharedHostResults(job.n_genes, job.T, job.L, register=False)
+        arr = job.run_to_host(host)
+        if rank == 0:
+            for k in ('w1', 'w2', 'x1', 'x2', 'n_iters'):
+                ok = ok and np.array_equal(arr[k], ref[k], equal_nan=True)
+            ok = ok and np.array_equal(arr['pvals'], pv, equal_nan=True)
+        import torch.distributed as dist
+        if dist.is_initialized():
+            dist.barrier()
+        host.close()
     # no pseudo-genes: EM + gather only
     r0 = jd.run_screen_sharded(offs, rows, None, None, test, ctrl, engine=jd.HostEngine(em_fn, kde_fn))
     if rank == 0:
