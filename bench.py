@@ -330,7 +330,7 @@ def aux_measurements(ctx, torch, dev, stream, w, params, hbm_peak, cpu_pv):
     return out
 
 
-def fixed_x_measurement(ctx, torch, dev, stream, w, params, d_test, d_ctrl):
+def fixed_x_measurement(ctx, torch, dev, stream, w, params):
     """BASELINE config 3: reference-efficacy mode (--reffile / fixed_x, infer.py:22-24,77-79,91: the X step is skipped) on
     the real genes of the Avana-shaped screen, device resident.  The published Avana efficacies do not travel to the GPU
     box; x is drawn from their distribution (mean 1, sd 0.4) -- the arithmetic does not depend on the values."""
@@ -346,6 +346,7 @@ def fixed_x_measurement(ctx, torch, dev, stream, w, params, d_test, d_ctrl):
     o_it = torch.empty(n, dtype=torch.int32, device=dev)
     plan = _native.EmPlan(ctx, offs, rows, N, L)
     io = _native.EmDeviceIO()
+    d_test, d_ctrl = torch.from_numpy(w['test']).to(dev), torch.from_numpy(w['ctrl1']).to(dev)      # caller row order
     io.test, io.ctrl, io.ctrl_lines = d_test.data_ptr(), d_ctrl.data_ptr(), int(d_ctrl.shape[1])
     io.fixed_x1, io.fixed_x2 = d_x1.data_ptr(), d_x2.data_ptr()
     io.w1, io.w2, io.n_iters = o_w1.data_ptr(), o_w2.data_ptr(), o_it.data_ptr()
@@ -599,16 +600,16 @@ def main():
     else:
         # N ranks: each uploads the rows of its shard (pinned) and delivers the rows of its own genes into ONE shared,
         # page-locked host segment that rank 0 reads in place (dist.SharedHostResults): no gather, eight PCIe links
-        pins = [torch.from_numpy(np.ascontiguousarray(np.asarray(w['test'])[job.used])).pin_memory(),
-                torch.from_numpy(np.ascontiguousarray(np.asarray(w['ctrl1'])[job.used])).pin_memory()]
+        # (control-guide rows: 1/N of them per rank, completed by an all-gather over NVLink, so that the pseudo-gene EM runs
+        # while the real-gene rows are still arriving)
+        pins = {k: torch.from_numpy(v).pin_memory() for k, v in job.host_parts(w['test'], w['ctrl1']).items()}
         host = jd.SharedHostResults(job.n_genes, job.T, L)
-        h2d = sum(p.numel() * 8 for p in pins)
+        h2d = sum(p.numel() * 8 for p in pins.values())
         n_mine, t_mine = int(job.b[rank + 1] - job.b[rank]), int(job.bt[rank + 1] - job.bt[rank])
         d2h = 8 * (3 * n_mine * L + 2 * t_mine) + 4 * n_mine
 
         def e2e_step():
-            job.d_test.copy_(pins[0], non_blocking=True)
-            job.d_ctrl.copy_(pins[1], non_blocking=True)
+            job.upload(pins)
             job.run_to_host(host)
         api = 'jacks_b200.dist.ShardedScreen.run_to_host: every rank uploads the rows of its gene blocks from pinned memory, EM -> ' \
               'all-to-all -> p-values -> all-to-all back, and copies w1, w2, x1, x2, n_iters, pvals of ITS genes into one shared ' \
@@ -650,7 +651,7 @@ def main():
         except Exception:
             pass
         aux = aux_measurements(ctx, torch, dev, stream, w, params, float(peaks.get('hbm_gbs', 6650.0)), cpu_pv)
-        aux['fixed_x'] = fixed_x_measurement(ctx, torch, dev, stream, w, params, d_test, d_ctrl)
+        aux['fixed_x'] = fixed_x_measurement(ctx, torch, dev, stream, w, params)
         del o
         aux['em_lines'] = lines_measurement(ctx, torch, dev, stream, w, params)
     if rank == 0:

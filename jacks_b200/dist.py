@@ -54,6 +54,21 @@ def compact_rows(index_rows, n_rows):
     return used, remap[index_rows].astype(np.int32)
 
 
+def two_part_layout(real_rows, pseudo_rows_mine, pseudo_rows_all, n_rows, world):
+    """Row layout of a rank's compact cube: [P | R].  P = every row ANY pseudo-gene references (the control guides; the same
+    set on every rank), padded to world * k rows so that each rank uploads only its k-row slice of it and one all-gather
+    over NVLink completes the block; R = the rows of this rank's real genes that are not in P.  Returns (P, R, k) and the
+    two indexes re-based onto the layout."""
+    P = np.unique(np.asarray(pseudo_rows_all, dtype=np.int64))
+    k = (len(P) + world - 1) // world
+    R = np.setdiff1d(np.unique(np.asarray(real_rows, dtype=np.int64)), P, assume_unique=True)
+    pos = np.full(n_rows, -1, dtype=np.int64)
+    pos[P] = np.arange(len(P))
+    pos[R] = world * k + np.arange(len(R))
+    return P, R, k, pos[np.asarray(real_rows, dtype=np.int64)].astype(np.int32), \
+        pos[np.asarray(pseudo_rows_mine, dtype=np.int64)].astype(np.int32)
+
+
 def _world(group):
     import torch.distributed as dist
     if not dist.is_initialized():
@@ -88,12 +103,50 @@ class NativeEngine(object):
         self.ctx = _native.context(int(device))
         self._plans = {}
         self._side = None
+        self._up = None
         self._down, self._down_keep = None, []
 
     def upload(self, array):
         """Host array -> device tensor (through a pinned copy when the source is pageable)."""
         t = self.torch.from_numpy(np.ascontiguousarray(array))
         return t.to(self.device, non_blocking=True)
+
+    def alloc(self, shape):
+        return self.torch.empty(tuple(int(x) for x in shape), dtype=self.torch.float64, device=self.device)
+
+    # -- staged upload: copies and the control-row all-gather run on an upload stream; marks are events the EM launches wait
+    #    for (the pseudo-gene EM only for the control block, so that it runs while the screen rows are still arriving)
+    def begin_upload(self):
+        torch = self.torch
+        if self._up is None:
+            self._up = torch.cuda.Stream(device=self.device)
+        self._up.wait_stream(torch.cuda.current_stream(self.device))     # earlier kernels may still read the cubes
+        if self._side is not None:
+            self._up.wait_stream(self._side)
+
+    def h2d(self, dst, src):
+        """dst: contiguous device view; src: host array (numpy, or a torch CPU tensor -- pinned for a truly asynchronous copy)."""
+        torch = self.torch
+        if dst.numel() == 0:
+            return
+        t = src if torch.is_tensor(src) else torch.from_numpy(np.ascontiguousarray(src))
+        with torch.cuda.stream(self._up):
+            dst.copy_(t.view(dst.shape), non_blocking=True)
+
+    def allgather_rows(self, cube, k, world, rank, group):
+        """cube[:world*k] <- the k-row slices every rank has uploaded at its own position (in place, NCCL over NVLink)."""
+        import torch.distributed as dist
+        with self.torch.cuda.stream(self._up):
+            dist.all_gather_into_tensor(cube[:world * k], cube[rank * k:(rank + 1) * k], group=group)
+
+    def mark(self):
+        ev = self.torch.cuda.Event()
+        ev.record(self._up)
+        return ev
+
+    def wait(self, ev, side=False):
+        if ev is not None:
+            (self._side if side else self.torch.cuda.current_stream(self.device)).wait_event(ev)
 
     def plan(self, key, offsets, rows, n_rows, n_lines):
         """Plans are cached per key: a resident screen is inferred again and again (benchmark, bootstrap draws)."""
@@ -201,6 +254,30 @@ class HostEngine(object):
         pass
 
     def join(self):
+        pass
+
+    def alloc(self, shape):
+        return self.torch.zeros(tuple(int(x) for x in shape), dtype=self.torch.float64)
+
+    def begin_upload(self):
+        pass
+
+    def h2d(self, dst, src):
+        if dst.numel():
+            t = src if self.torch.is_tensor(src) else self.torch.from_numpy(np.ascontiguousarray(src))
+            dst.copy_(t.view(dst.shape))
+
+    def allgather_rows(self, cube, k, world, rank, group):
+        import torch.distributed as dist
+        parts = [self.torch.empty_like(cube[:k]) for _ in range(world)]
+        dist.all_gather(parts, cube[rank * k:(rank + 1) * k].contiguous(), group=group)
+        for s_, part in enumerate(parts):
+            cube[s_ * k:(s_ + 1) * k] = part
+
+    def mark(self):
+        return None
+
+    def wait(self, ev, side=False):
         pass
 
     def em(self, plan, test, ctrl, params, fixed_x1=None, fixed_x2=None, want_x=True, y_tau=False, w1_out=None, side=False):
@@ -340,24 +417,55 @@ class ShardedScreen(object):
             self.bp = np.zeros(W + 1, dtype=np.int64)
             poffs, prows = np.zeros(1, dtype=np.int64), np.zeros(0, dtype=np.int64)
         self.lb = line_bounds(L, W)
-        # compact cube: the rows this rank's two blocks reference, nothing else
-        used, both = compact_rows(np.concatenate([np.asarray(lrows, dtype=np.int64), np.asarray(prows, dtype=np.int64)]), N)
-        self.used = used
+        # compact cube [P | R]: the control-guide rows of ALL pseudo-genes (each rank uploads 1/W of them, one all-gather
+        # over NVLink completes the block) followed by the rows of this rank's real genes -- nothing else goes up
+        P, R, k, real_idx, pseudo_idx = two_part_layout(lrows, prows, pseudo_rows if self.has_pseudo else np.zeros(0, np.int64), N, W)
+        self.P, self.R, self.k = P, R, k
+        self.used = np.concatenate([P, R])                              # rows resident on this rank (cube order, unpadded)
+        U = W * k + len(R)
+        self.d_test, self.d_ctrl = engine.alloc((U, L, 2)), engine.alloc((U, int(ctrldata.shape[1]), 2))
+        self._ev_ctrl = self._ev_all = None
         self.h2d_bytes = 0
-        test_c = np.ascontiguousarray(np.asarray(testdata)[used])
-        ctrl_c = np.ascontiguousarray(np.asarray(ctrldata)[used])
-        self.d_test, self.d_ctrl = engine.upload(test_c), engine.upload(ctrl_c)
-        self.h2d_bytes += test_c.nbytes + ctrl_c.nbytes
+        self.upload(self.host_parts(testdata, ctrldata))
         self.d_fx1 = self.d_fx2 = None
         if fixed_x is not None:
-            fx1 = np.ascontiguousarray(np.asarray(fixed_x['X1'], dtype=np.float64)[used])
-            fx2 = np.ascontiguousarray(np.asarray(fixed_x['X2'], dtype=np.float64)[used])
+            cube_rows = np.concatenate([P, np.zeros(W * k - len(P), dtype=np.int64), R])
+            fx1 = np.ascontiguousarray(np.asarray(fixed_x['X1'], dtype=np.float64)[cube_rows])
+            fx2 = np.ascontiguousarray(np.asarray(fixed_x['X2'], dtype=np.float64)[cube_rows])
             self.d_fx1, self.d_fx2 = engine.upload(fx1), engine.upload(fx2)
             self.h2d_bytes += fx1.nbytes + fx2.nbytes
-        U = len(used)
-        self.plan_real = engine.plan(None, loffs, both[:len(lrows)], U, L)
-        self.plan_pseudo = engine.plan(None, poffs, both[len(lrows):], U, L) if self.has_pseudo else None
-        self.h2d_bytes += loffs.nbytes + poffs.nbytes + both.nbytes
+        self.plan_real = engine.plan(None, loffs, real_idx, U, L)
+        self.plan_pseudo = engine.plan(None, poffs, pseudo_idx, U, L) if self.has_pseudo else None
+        self.h2d_bytes += loffs.nbytes + poffs.nbytes + real_idx.nbytes + pseudo_idx.nbytes
+
+    # -- upload ------------------------------------------------------------------------------------------------------
+    def host_parts(self, testdata, ctrldata):
+        """The four contiguous host blocks this rank uploads: its slice of the control block and its real-gene rows, of
+        the test and of the control cube (callers that re-upload per step keep them in pinned memory)."""
+        r, k = self.rank, self.k
+        mine = self.P[r * k:(r + 1) * k]
+        td, cd = np.asarray(testdata), np.asarray(ctrldata)
+        return dict(test_p=np.ascontiguousarray(td[mine]), ctrl_p=np.ascontiguousarray(cd[mine]),
+                    test_r=np.ascontiguousarray(td[self.R]), ctrl_r=np.ascontiguousarray(cd[self.R]))
+
+    def upload(self, parts):
+        """Enqueue the upload of this rank's share of the screen (host_parts) on the engine's upload stream: control block
+        first -- my slice, then the all-gather -- so that the pseudo-gene EM of the next run() starts while the real-gene
+        rows are still on their way up."""
+        eng, W, r, k = self.engine, self.world, self.rank, self.k
+        n_mine = len(self.P[r * k:(r + 1) * k])
+        eng.begin_upload()
+        if k:
+            eng.h2d(self.d_test[r * k:r * k + n_mine], parts['test_p'])
+            eng.h2d(self.d_ctrl[r * k:r * k + n_mine], parts['ctrl_p'])
+            if W > 1:
+                eng.allgather_rows(self.d_test, k, W, r, self.group)
+                eng.allgather_rows(self.d_ctrl, k, W, r, self.group)
+        self._ev_ctrl = eng.mark()
+        eng.h2d(self.d_test[W * k:], parts['test_r'])
+        eng.h2d(self.d_ctrl[W * k:], parts['ctrl_r'])
+        self._ev_all = eng.mark()
+        self.h2d_bytes = sum(int(v.numel() * v.element_size()) if self.torch.is_tensor(v) else int(v.nbytes) for v in parts.values())
 
     # -- collectives -------------------------------------------------------------------------------------------------
     def _all_to_all(self, send, in_splits, out_splits, async_op=False):
@@ -406,6 +514,8 @@ class ShardedScreen(object):
             # one exchange buffer for both: [real | pseudo] E[w] of my genes, written by the kernels themselves
             both = t.empty((n_lr + n_lp, L), dtype=t.float64, device=eng.device)
             eng.fork()
+            eng.wait(self._ev_ctrl, side=True)
+            eng.wait(self._ev_all)
             real = eng.em(self.plan_real, self.d_test, self.d_ctrl, self.params, self.d_fx1, self.d_fx2, want_x=True, w1_out=both[:n_lr])
             if W > 1:
                 early = gather_em(real)
@@ -423,6 +533,7 @@ class ShardedScreen(object):
             p_block = t.cat(parts_p) if W > 1 else parts_p[0]                # [n_pseudo, my lines], original order
             pv_block = eng.kde(g_block.contiguous(), p_block.contiguous(), self.positive)
         else:
+            eng.wait(self._ev_all)
             real = eng.em(self.plan_real, self.d_test, self.d_ctrl, self.params, self.d_fx1, self.d_fx2, want_x=True)
             if W > 1:
                 early = gather_em(real)
@@ -485,6 +596,8 @@ class ShardedScreen(object):
         if do_p:
             both = t.empty((n_lr + n_lp, L), dtype=t.float64, device=eng.device)
             eng.fork()
+            eng.wait(self._ev_ctrl, side=True)
+            eng.wait(self._ev_all)
             real = eng.em(self.plan_real, self.d_test, self.d_ctrl, self.params, self.d_fx1, self.d_fx2, want_x=True, w1_out=both[:n_lr])
             deliver(real)
             pseudo = eng.em(self.plan_pseudo, self.d_test, self.d_ctrl, self.params, want_x=False, w1_out=both[n_lr:], side=True)
@@ -515,6 +628,7 @@ class ShardedScreen(object):
             self.exchange_bytes = (both.numel() + pv_block.numel()) * 8 * (W - 1) // W
             del pseudo
         else:
+            eng.wait(self._ev_all)
             real = eng.em(self.plan_real, self.d_test, self.d_ctrl, self.params, self.d_fx1, self.d_fx2, want_x=True)
             deliver(real)
             self.exchange_bytes = 0
