@@ -235,16 +235,34 @@ def as_csr(gene_index):
     return names, offsets, rows
 
 
+def _cube(a):
+    """float64 C-contiguous [N, L, 2] form of a data cube.  Planes beyond the first two are ignored, as the reference
+    reads only [..., 0] and [..., 1] (infer.py:57-58; writeFoldChanges(write_raw=True) implies [N, L, 3] cubes)."""
+    a = np.asarray(a, dtype=np.float64)
+    if a.ndim == 3 and a.shape[2] > 2:
+        a = a[:, :, :2]
+    return np.ascontiguousarray(a)
+
+
+def _rows(rows, n_rows):
+    """Guide rows as int32 with numpy's index semantics: negative rows count from the end, anything else out of range
+    raises IndexError (the reference indexes its cubes with these, infer.py:43-44)."""
+    rows = np.asarray(rows)
+    if rows.size:
+        if rows.min() < -n_rows or rows.max() >= n_rows:
+            raise IndexError('guide row index out of bounds for %d rows' % n_rows)
+        if rows.min() < 0:
+            rows = np.where(rows < 0, rows + n_rows, rows)
+    return np.ascontiguousarray(rows, dtype=np.int32)
+
+
 class EmPlan(object):
     """Device-resident gene index (JacksEmPlan)."""
 
     def __init__(self, ctx, offsets, rows, n_rows, n_lines):
         self.ctx = ctx
         self.offsets = np.ascontiguousarray(offsets, dtype=np.int64)
-        rows = np.asarray(rows)
-        if rows.size and (rows.min() < 0 or rows.max() >= n_rows):
-            raise IndexError('guide row index out of bounds for %d rows' % n_rows)
-        self.rows = np.ascontiguousarray(rows, dtype=np.int32)
+        self.rows = _rows(rows, n_rows)
         self.n_genes = len(self.offsets) - 1
         self.total_guides = int(self.offsets[-1]) if self.n_genes >= 0 and len(self.offsets) else 0
         self.n_lines = int(n_lines)
@@ -286,14 +304,11 @@ def em_batched_host(ctx, offsets, rows, test, ctrl, params=None, fixed_x1=None, 
     offsets = np.ascontiguousarray(offsets, dtype=np.int64)
     rows = np.asarray(rows)
     if test is not None:
-        test = np.ascontiguousarray(test, dtype=np.float64)
-        ctrl = np.ascontiguousarray(ctrl, dtype=np.float64)
+        test, ctrl = _cube(test), _cube(ctrl)
         if test.ndim != 3 or test.shape[2] != 2 or ctrl.ndim != 3 or ctrl.shape[2] != 2 or ctrl.shape[0] != test.shape[0]:
             raise JacksError(JACKS_E_SHAPE, 'Expecting matched size between control and test data')
         n_rows, n_lines, ctrl_lines = test.shape[0], test.shape[1], ctrl.shape[1]
-    if rows.size and (rows.min() < 0 or rows.max() >= n_rows):
-        raise IndexError('guide row index out of bounds for %d rows' % n_rows)
-    rows = np.ascontiguousarray(rows, dtype=np.int32)
+    rows = _rows(rows, n_rows)
     n_genes = len(offsets) - 1
     T = int(offsets[-1]) if n_genes > 0 else 0
     shapes = dict(x1=((T,), np.float64), x2=((T,), np.float64), w1=((n_genes, n_lines), np.float64),
@@ -341,17 +356,13 @@ def run_screen_host(ctx, offsets, rows, pseudo_offsets, pseudo_rows, test, ctrl,
     pseudo_offsets=None runs the real genes alone (no p-values)."""
     params = params or default_params()
     offsets = np.ascontiguousarray(offsets, dtype=np.int64)
-    test = np.ascontiguousarray(test, dtype=np.float64)
-    ctrl = np.ascontiguousarray(ctrl, dtype=np.float64)
+    test, ctrl = _cube(test), _cube(ctrl)
     if test.ndim != 3 or test.shape[2] != 2 or ctrl.ndim != 3 or ctrl.shape[2] != 2 or ctrl.shape[0] != test.shape[0]:
         raise JacksError(JACKS_E_SHAPE, 'Expecting matched size between control and test data')
     n_rows, n_lines = test.shape[0], test.shape[1]
 
     def index(rows_):
-        rows_ = np.asarray(rows_)
-        if rows_.size and (rows_.min() < 0 or rows_.max() >= n_rows):
-            raise IndexError('guide row index out of bounds for %d rows' % n_rows)
-        return np.ascontiguousarray(rows_, dtype=np.int32)
+        return _rows(rows_, n_rows)
     rows = index(rows)
     n_genes = len(offsets) - 1
     T = int(offsets[-1]) if n_genes > 0 else 0
@@ -408,14 +419,11 @@ def em_lines_host(ctx, offsets, rows, test, ctrl, params=None, fixed_x1=None, fi
     offsets = np.ascontiguousarray(offsets, dtype=np.int64)
     rows = np.asarray(rows)
     if test is not None:
-        test = np.ascontiguousarray(test, dtype=np.float64)
-        ctrl = np.ascontiguousarray(ctrl, dtype=np.float64)
+        test, ctrl = _cube(test), _cube(ctrl)
         if test.ndim != 3 or test.shape[2] != 2 or ctrl.shape != test.shape:
             raise JacksError(JACKS_E_SHAPE, 'Expecting matched size between control and test data')
         n_rows, n_lines = test.shape[0], test.shape[1]
-    if rows.size and (rows.min() < 0 or rows.max() >= n_rows):
-        raise IndexError('guide row index out of bounds for %d rows' % n_rows)
-    rows = np.ascontiguousarray(rows, dtype=np.int32)
+    rows = _rows(rows, n_rows)
     n_genes = len(offsets) - 1
     T = int(offsets[-1]) if n_genes > 0 else 0
     per = dict(x1=T, x2=T, w1=n_genes, w2=n_genes, y=T, tau=T, n_iters=n_genes, bound=n_genes)

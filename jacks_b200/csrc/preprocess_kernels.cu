@@ -309,6 +309,68 @@ __global__ void __launch_bounds__(256) sample_stats_kernel(const double* __restr
     kidx[o] = (int)i;
 }
 
+// The same for many samples at once, tiled 32 guides x 32 samples: consecutive threads take consecutive SAMPLES of one guide
+// (their replicate columns are neighbours in the row, so the reads of the [N][C] matrix and the writes of the cube's mean
+// plane are coalesced; one thread per guide read 8 bytes out of every 6.4 KB row), the keys cross a shared-memory tile and
+// leave coalesced along the guide axis.  Same arithmetic, same order.
+__global__ void __launch_bounds__(256) sample_stats_tiled_kernel(const double* __restrict__ lc, long long N, int C,
+                                                                 const int* __restrict__ col_off, const int* __restrict__ cols,
+                                                                 int S, long long Np, double* __restrict__ data,
+                                                                 double* __restrict__ kmean, double* __restrict__ kvar,
+                                                                 int* __restrict__ kidx) {
+    __shared__ double t_mean[32][33], t_var[32][33];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;          // 32 x 8
+    const long long i0 = (long long)blockIdx.x * 32;
+    const int s0 = blockIdx.y * 32;
+    const int s = s0 + tx;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int ti = ty + 8 * k;
+        const long long i = i0 + ti;
+        double kmv = d_inf(), kvv = d_inf();
+        if (s < S && i < N) {
+            const int c0 = col_off[s], R = col_off[s + 1] - c0;
+            double sum = 0.0, nsum = 0.0;
+            int cnt = 0;
+            for (int r = 0; r < R; ++r) {
+                const double v = lc[i * C + cols[c0 + r]];
+                sum = __dadd_rn(sum, v);
+                if (v == v) { nsum = __dadd_rn(nsum, v); ++cnt; }
+            }
+            const double mean = sum / (double)R;
+            double var = d_nan();
+            if (cnt > 0) {
+                const double nmean = nsum / (double)cnt;
+                double ss = 0.0;
+                for (int r = 0; r < R; ++r) {
+                    const double v = lc[i * C + cols[c0 + r]];
+                    if (v == v) { const double d = __dadd_rn(v, -nmean); ss = __dadd_rn(ss, __dmul_rn(d, d)); }
+                }
+                const double sd = sqrt(ss / (double)cnt);
+                var = __dmul_rn(sd, sd);
+            }
+            data[(i * S + s) * 2 + 0] = mean;
+            if (R < 2) data[(i * S + s) * 2 + 1] = d_nan();
+            kmv = (mean == mean) ? mean : d_inf();
+            kvv = (var == var) ? var : d_inf();
+        }
+        t_mean[ti][tx] = kmv;
+        t_var[ti][tx] = kvv;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int ts = ty + 8 * k;
+        const long long i = i0 + tx;
+        if (s0 + ts < S && i < Np) {
+            const long long o = (long long)(s0 + ts) * Np + i;
+            kmean[o] = t_mean[tx][ts];
+            kvar[o] = t_var[tx][ts];
+            kidx[o] = (i < N) ? (int)i : 0x7fffffff;
+        }
+    }
+}
+
 // ---- segmented stable LSD radix sort of (mean, variance, index) keys ---------------------------------------------------
 // Every sample is one segment of N keys.  The order wanted is Python's tuple order (mean, var, index), preprocess.py:39-40:
 // a stable sort by the variance followed by a stable sort by the mean, starting from index order, gives exactly that.
@@ -466,7 +528,8 @@ __global__ void __launch_bounds__(256) rs_gather_sorted(const double* __restrict
 
 // ---- sliding mean (shifted, as the reference), reverse running max, sqrt, scatter ----------------
 // One CTA per sample.  P = exclusive prefix sums of the sorted variances (global scratch, chunked scan).
-constexpr int kScanThreads = 1024;
+constexpr int kScanThreads = 512;        // four CTAs per SM: the 401 samples of an Avana-shaped screen are resident at once
+constexpr int kScanItems = 8;          // consecutive elements per thread in the chunked scans
 
 __device__ double block_exclusive_scan(double v, double* sh, double* total) {
     // inclusive warp scan
@@ -491,14 +554,21 @@ __device__ double block_exclusive_scan(double v, double* sh, double* total) {
 // scratch for N+1 prefix sums.  Whole CTA (kScanThreads threads) cooperates.
 __device__ void dev_window_smooth(const double* __restrict__ x, long long N, long long window, double* __restrict__ p,
                                   double* __restrict__ m, double* sh) {
-    // exclusive prefix sums p[i] = sum_{t<i} x[t], i = 0..N
+    // exclusive prefix sums p[i] = sum_{t<i} x[t], i = 0..N.  A thread owns kScanItems consecutive elements (64 contiguous
+    // bytes), so a chunk of 8,192 elements costs ONE block-wide scan: 9 instead of 71 rounds of barriers for 72,000 guides.
     double carry = 0.0;
-    for (long long c0 = 0; c0 < N; c0 += kScanThreads) {
-        const long long i = c0 + threadIdx.x;
-        const double v = (i < N) ? x[i] : 0.0;
+    for (long long c0 = 0; c0 < N; c0 += (long long)kScanThreads * kScanItems) {
+        const long long base = c0 + (long long)threadIdx.x * kScanItems;
+        double v[kScanItems], run = 0.0;
+#pragma unroll
+        for (int j = 0; j < kScanItems; ++j) { v[j] = (base + j < N) ? x[base + j] : 0.0; }
+#pragma unroll
+        for (int j = 0; j < kScanItems; ++j) { const double t = v[j]; v[j] = run; run += t; }      // v[j]: sum of my elements before j
         double total;
-        const double ex = block_exclusive_scan(v, sh, &total);
-        if (i < N) p[i] = carry + ex;
+        const double ex = block_exclusive_scan(run, sh, &total) + carry;
+#pragma unroll
+        for (int j = 0; j < kScanItems; ++j)
+            if (base + j < N) p[base + j] = ex + v[j];
         carry += total;
         __syncthreads();
     }
@@ -527,26 +597,48 @@ __device__ void dev_window_smooth(const double* __restrict__ x, long long N, lon
 // Chunked from the end; inside a chunk a segmented max-scan (warp shuffles, then a serial pass over the 32 warp
 // summaries).  Whole CTA cooperates.
 __device__ void dev_reverse_running_max(double* __restrict__ m, long long N) {
+    // A thread owns kScanItems consecutive elements and walks them from the top down; what crosses thread boundaries is
+    // the pair (run leaving my segment at its low end, did my segment hold a NaN), scanned over the threads in reverse
+    // element order exactly as single elements were before.
     __shared__ double s_carry;
     __shared__ double w_last[32];
     __shared__ int w_blocked[32];
     __shared__ double w_in[32];
     if (threadIdx.x == 0) s_carry = d_nan();         // "no carry" marker: the last element has no successor
     __syncthreads();
-    for (long long hi = N; hi > 0; hi -= kScanThreads) {
-        const long long k = hi - 1 - threadIdx.x;                           // thread 0 takes the last element of the chunk
-        const bool live = (k >= 0);
-        const double v = live ? m[k] : d_nan();
-        // forward scan over threadIdx == reverse order in k; a NaN neither receives nor passes on a maximum
+    constexpr long long kChunk = (long long)kScanThreads * kScanItems;
+    for (long long hi = N; hi > 0; hi -= kChunk) {
+        // thread 0 takes the top kScanItems elements of the chunk: [top - kScanItems + 1, top]
+        const long long top = hi - 1 - (long long)threadIdx.x * kScanItems;
+        double out[kScanItems];
+        double run = d_nan();                        // the run inside my segment (NaN = none yet / cut)
+        bool seg_nan = false;
+#pragma unroll
+        for (int j = 0; j < kScanItems; ++j) {       // j = 0 is the TOP element of my segment
+            const long long k = top - j;
+            double v = (k >= 0) ? m[k] : d_nan();
+            if (k < 0) { out[j] = v; continue; }     // below the array: nothing to do (and nothing below it reads my run)
+            if (v == v) {
+                if (run == run && run > v) v = run;
+                run = v;
+            } else {
+                seg_nan = true;
+                run = d_nan();
+            }
+            out[j] = v;
+        }
+        // dead threads (wholly below the array) pass the incoming run through untouched: treat them as NaN-free, empty
+        const bool dead = (top < 0);
+        // inclusive scan of (run, blocked) over the threads; a thread whose segment held a NaN neither receives the incoming
+        // run at its low end nor lets it pass
         const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-        double cur = v;
-        const bool open = (v == v);
-        bool blocked = !(v == v);                  // a NaN was seen in the span covered so far
+        double cur = run;
+        bool blocked = seg_nan;
         for (int o = 1; o < 32; o <<= 1) {
             const double pv = __shfl_up_sync(0xffffffffu, cur, o);
             const int pb = __shfl_up_sync(0xffffffffu, (int)blocked, o);
             if (lane >= o) {
-                if (!blocked && pv == pv && pv > cur && open) cur = pv;
+                if (!blocked && pv == pv && (!(cur == cur) || pv > cur)) cur = pv;
                 blocked = blocked || (pb != 0);
             }
         }
@@ -554,19 +646,36 @@ __device__ void dev_reverse_running_max(double* __restrict__ m, long long N) {
         if (lane == 31) { w_last[warp] = cur; w_blocked[warp] = (int)blocked; }
         __syncthreads();
         if (threadIdx.x == 0) {
-            double run = s_carry;                     // running max entering the chunk (NaN = none)
+            double r = s_carry;                       // running max entering the chunk (NaN = none)
             for (int q = 0; q < (int)(blockDim.x >> 5); ++q) {
-                w_in[q] = run;
+                w_in[q] = r;
                 const double last = w_last[q];
-                if (w_blocked[q]) run = last;          // the warp saw a NaN: the incoming run is cut there
-                else run = (run == run && (!(last == last) || run > last)) ? run : last;
+                if (w_blocked[q]) r = last;            // the warp saw a NaN: the incoming run is cut there
+                else r = (r == r && (!(last == last) || r > last)) ? r : last;
             }
-            s_carry = run;
+            s_carry = r;
         }
         __syncthreads();
-        const double incoming = w_in[warp];
-        if (live && (v == v) && !blocked && incoming == incoming && incoming > cur) cur = incoming;
-        if (live && (v == v)) m[k] = cur;
+        // the run entering MY segment from above: the previous thread's inclusive value, raised by the warp's incoming run
+        // unless a NaN sits between the warp's start and that thread's low end
+        double prev = __shfl_up_sync(0xffffffffu, cur, 1);
+        const int prev_blocked = __shfl_up_sync(0xffffffffu, (int)blocked, 1);
+        const double win = w_in[warp];
+        double incoming;
+        if (lane == 0) incoming = win;
+        else if (prev_blocked) incoming = prev;
+        else incoming = (win == win && (!(prev == prev) || win > prev)) ? win : prev;
+        if (!dead) {
+            bool open = (incoming == incoming);
+#pragma unroll
+            for (int j = 0; j < kScanItems; ++j) {
+                const long long k = top - j;
+                if (k < 0) break;
+                const double v = out[j];
+                if (!(v == v)) { open = false; continue; }        // a NaN stays NaN and ends the incoming run
+                m[k] = (open && incoming > v) ? incoming : v;
+            }
+        }
         __syncthreads();
     }
 }
@@ -757,8 +866,13 @@ int condense_core(JacksCtx* ctx, const double* d_lc, long long N, int C, const i
     cudaError_t e;
     if ((e = cudaMemcpyAsync(d_off, h_off, (S + 1) * sizeof(int), cudaMemcpyHostToDevice, st)) != cudaSuccess) return cuda_fail(e, "H2D offsets");
     if ((e = cudaMemcpyAsync(d_cols, h_cols, nidx * sizeof(int), cudaMemcpyHostToDevice, st)) != cudaSuccess) return cuda_fail(e, "H2D cols");
-    dim3 sg((unsigned)((ld + 255) / 256), (unsigned)S);
-    sample_stats_kernel<<<sg, 256, 0, st>>>(d_lc, N, C, d_off, d_cols, S, ld, d_data, km, kv, ki);
+    if (S >= 8) {
+        dim3 tg((unsigned)((ld + 31) / 32), (unsigned)((S + 31) / 32));
+        sample_stats_tiled_kernel<<<tg, 256, 0, st>>>(d_lc, N, C, d_off, d_cols, S, ld, d_data, km, kv, ki);
+    } else {
+        dim3 sg((unsigned)((ld + 255) / 256), (unsigned)S);
+        sample_stats_kernel<<<sg, 256, 0, st>>>(d_lc, N, C, d_off, d_cols, S, ld, d_data, km, kv, ki);
+    }
     ctx->launches++;
     if (max_rep >= 2) {
         SortScratch w{(unsigned long long*)(base + so[0]), (unsigned long long*)(base + so[1]), (int*)(base + so[2]), (int*)(base + so[3]),

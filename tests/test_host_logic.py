@@ -297,3 +297,33 @@ def test_reference_recipe_imports_the_unmodified_reference():
     from oracle import jacks_oracle as O
     o = O.em_gene(data, err.copy(), np.zeros((2, 3)), err.copy(), n_iter=5)
     assert np.array_equal(w1, o[4]) and np.array_equal(x1, o[2])          # the restatement is bit-exact against it
+
+
+def test_cubes_with_a_raw_plane_and_negative_rows_follow_numpy_semantics():
+    """The reference reads planes 0 and 1 of [N, L, >=2] cubes (infer.py:57-58) and indexes rows with numpy rules."""
+    from jacks_b200 import _native
+    cube = np.arange(2 * 3 * 3, dtype=np.float64).reshape(2, 3, 3)
+    c2 = _native._cube(cube)
+    assert c2.shape == (2, 3, 2) and c2.flags['C_CONTIGUOUS'] and np.array_equal(c2, cube[:, :, :2])
+    assert _native._cube(cube[:, :, :2]).shape == (2, 3, 2)
+    rows = _native._rows([0, -1, 3, -5], 5)
+    assert rows.dtype == np.int32 and rows.tolist() == [0, 4, 3, 0]
+    with pytest.raises(IndexError):
+        _native._rows([5], 5)
+    with pytest.raises(IndexError):
+        _native._rows([-6], 5)
+    assert _native._rows([], 5).size == 0
+
+
+def test_two_part_layout_covers_both_indexes():
+    """dist.two_part_layout: [control block padded to world*k | my real rows], indexes re-based onto it."""
+    from jacks_b200 import dist as jd
+    real = np.array([10, 11, 3, 3, 12, 7])
+    pseudo_all = np.array([7, 2, 9, 2, 7, 5, 9])
+    pseudo_mine = np.array([9, 2, 5])
+    P, R, k, ri, pi = jd.two_part_layout(real, pseudo_mine, pseudo_all, 16, 3)
+    assert P.tolist() == [2, 5, 7, 9] and k == 2 and R.tolist() == [3, 10, 11, 12]
+    cube_rows = np.concatenate([P, np.full(3 * k - len(P), -1), R])
+    assert cube_rows[ri].tolist() == real.tolist() and cube_rows[pi].tolist() == pseudo_mine.tolist()
+    P, R, k, ri, pi = jd.two_part_layout(real, [], [], 16, 2)
+    assert len(P) == 0 and k == 0 and np.unique(real)[ri].tolist() == real.tolist()
