@@ -3,16 +3,20 @@
 Genes are independent (jacks/jacks/infer.py:20-29 carries no state from one gene to the next), so the EM shards by gene
 with NO collective inside the iteration.  The job of one screen (jacks/jacks/jacks_io.py:425-441) runs like this:
 
-  1. every rank takes a contiguous block of the real genes and of the pseudo-genes (balanced by guide count) and uploads
-     ONLY the guide rows those reference -- its slice of the screen plus the few thousand control-guide rows the
-     pseudo-genes draw from -- as a compact cube with a re-based index;
-  2. EM of both blocks on the rank's GPU (the same kernels as the one-GPU call);
+  1. every rank takes a contiguous block of the real genes and of the pseudo-genes (balanced by guide count) and holds a
+     compact cube [control block | rows of my real genes] with a re-based index.  The control block -- the few thousand
+     control-guide rows the pseudo-genes draw from, the same on every rank -- goes up in one slice per rank and ONE
+     all-gather over NVLink completes it; then every rank uploads the rows of its own real genes: nothing goes up twice;
+  2. EM of both blocks on the rank's GPU (the same kernels as the one-GPU call); the pseudo-gene EM starts as soon as the
+     control block is complete, beside the rest of the upload and beside the real-gene EM (side stream);
   3. ONE all-to-all over NCCL / NVLink turns "my genes x all lines" into "all genes x my lines" for E[w] of real and
      pseudo-genes (each rank keeps L/W lines: 1/W of what an all-gather of the pseudo-gene E[w] would move);
   4. the KDE null of a line needs all pseudo-genes of that line and nothing else, so the p-values are line-sharded:
      every rank prepares the null densities of its lines and evaluates every real gene on them;
-  5. ONE gather (a one-sided all-to-all) hands rank `dst` the per-gene results: w1, w2, x1, x2, iteration counts and
-     the p-value column blocks.
+  5. run(): ONE gather (a one-sided all-to-all) hands rank `dst` the per-gene results as device tensors: w1, w2, x1, x2,
+     iteration counts and the p-value column blocks.  run_to_host(): no gather -- a second small all-to-all turns the
+     p-values back into "my genes x all lines" and every rank copies the rows of ITS genes into one shared, page-locked
+     host segment (SharedHostResults) over its own PCIe link.
 
 Nothing is reduced across ranks and every per-line sum runs over the pseudo-genes in their original order, so 1-rank and
 N-rank results are bit-identical.  All buffers between steps 2 and 5 stay on the device; under the gloo backend (CPU
