@@ -672,6 +672,205 @@ __device__ __noinline__ EmStaged<G> em_stage_gene(const double2* __restrict__ te
     return r;
 }
 
+// Lean staging + initialisation for the common launch: PLAIN (no hyper-prior, no 1-D-control fill), one-warp team,
+// the initialising tensor-memory variants.  Same arithmetic as the initialising branch of em_stage_gene, but everything
+// that is uniform per launch is a template parameter and everything that is uniform per gene is hoisted:
+//   ONE_CTRL  one control column serves all lines ([N][1] control; its sd is finite -- the kernel checks and sends genes
+//             with an undefined control sd through em_stage_gene): the control's mean and its variance term
+//             sd_c^2 + 1e-2 are per-guide constants;
+//   the lines every lane owns (l0 + k*32 < L for all lanes, k < n_full) run without predicates, two at a time, through
+//   per-guide pointers that advance by a constant; the last, partial line runs once through the predicated one-line tail;
+//   a staged value that is not finite shows in the initial bound sum (th > 0 for finite data, and y^2 is a term of every
+//   element's contribution), so there is no per-element check.
+// em_stage_gene executed ~560 instructions per two lines at G = 4 (run-time control layout, per-element flags, address
+// arithmetic); this one ~260.
+template <int G> struct EmCtl { double cm[G], cc[G]; };
+template <int G> struct EmX12 { double x1[G], x2[G]; };
+
+template <int G, bool ONE_CTRL, int NB>
+__device__ __forceinline__ void em_stage_lines(const double2 (&t)[NB][G], const double2 (&c)[NB][G], const EmCtl<G>& k,
+                                               const double (&tx1)[G], const double (&x2)[G], const double tps,
+                                               const double two_tps, double (&yv)[NB][G], double (&pdv)[NB][G],
+                                               double (&th)[NB][G], double (&w1)[NB], double (&w2)[NB]) {
+#pragma unroll
+    for (int b = 0; b < NB; ++b)
+#pragma unroll
+        for (int g = 0; g < G; ++g) {
+            const double te = (t[b][g].y != t[b][g].y) ? 2.0 : t[b][g].y;                    // infer.py:58
+            double base;
+            if (ONE_CTRL) {
+                yv[b][g] = t[b][g].x - k.cm[g];
+                base = k.cc[g];
+            } else {
+                double ce = c[b][g].y;
+                if (ce != ce) ce = te;                                                        // infer.py:68
+                yv[b][g] = t[b][g].x - c[b][g].x;
+                base = fma(ce, ce, 1e-2);
+            }
+            pdv[b][g] = two_tps * fma(te, te, base);                                          // pd2 = 2*tau_pr_den, infer.py:70
+        }
+    // th = tau/2 = tps/pd2 (infer.py:83), stage by stage over the NB*G independent elements
+    double r[NB][G], e[NB][G];
+#pragma unroll
+    for (int b = 0; b < NB; ++b)
+#pragma unroll
+        for (int g = 0; g < G; ++g) asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r[b][g]) : "d"(pdv[b][g]));
+#pragma unroll
+    for (int b = 0; b < NB; ++b)
+#pragma unroll
+        for (int g = 0; g < G; ++g) e[b][g] = fma(-pdv[b][g], r[b][g], 1.0);
+#pragma unroll
+    for (int b = 0; b < NB; ++b)
+#pragma unroll
+        for (int g = 0; g < G; ++g) e[b][g] = fma(e[b][g], e[b][g], e[b][g]);
+#pragma unroll
+    for (int b = 0; b < NB; ++b)
+#pragma unroll
+        for (int g = 0; g < G; ++g) th[b][g] = tps * fma(r[b][g], e[b][g], r[b][g]);
+#pragma unroll
+    for (int b = 0; b < NB; ++b) {
+        double hi_, lo_;
+        max_min_median<G>(yv[b], hi_, lo_, w1[b]);                                            // infer.py:81 (finite genes only)
+        w2[b] = w1[b] * w1[b];
+    }
+    (void)tx1; (void)x2;
+}
+
+// The initial sums of one line: the bound sum tau*(y^2 + x2*w2 - 2*x1*w1*y) = tau*(y*(y - 2*x1*w1) + x2*w2)
+// (infer.py:125) and the first X step's row sums, all formed with th = tau/2.
+template <int G>
+__device__ __forceinline__ void em_stage_sums(const double (&yv)[G], const double (&th)[G], const double w1, const double w2,
+                                              const double (&tx1)[G], const double (&x2)[G], double (&acc)[2 * G + 1]) {
+#pragma unroll
+    for (int g = 0; g < G; ++g) {
+        const double bb = fma(yv[g], fma(-tx1[g], w1, yv[g]), x2[g] * w2);
+        acc[2 * G] = fma(th[g], bb, acc[2 * G]);
+        acc[g] = fma(yv[g] * th[g], w1, acc[g]);
+        acc[G + g] = fma(th[g], w2, acc[G + g]);
+    }
+}
+
+template <int G, int TM, bool WS, bool ONE_CTRL>
+__device__ __noinline__ EmStaged<G> em_stage_plain(const double2* __restrict__ test, const double2* __restrict__ ctrl,
+                                                   const int* rows, const EmCtl<G> k, double* __restrict__ ys,
+                                                   double* __restrict__ tpdg, const int L, const int Lp, const int lane,
+                                                   const double tps, uint32_t tpd, uint32_t tth, const int n_warp,
+                                                   const EmX12<G> x, double* __restrict__ w1g, double* __restrict__ w2g) {
+    constexpr int B = (G >= 9) ? 1 : 2;       // lines per batch
+    constexpr int STEP = 32;
+    EmStaged<G> r;
+#pragma unroll
+    for (int i = 0; i < 2 * G + 1; ++i) r.acc[i] = 0.0;
+    const double two_tps = 2.0 * tps;
+    double tx1[G], x2[G];
+    const double2* tp[G];
+    const double2* cp[G];
+    double* yp[G];
+#pragma unroll
+    for (int g = 0; g < G; ++g) {
+        tx1[g] = 2.0 * x.x1[g];
+        x2[g] = x.x2[g];
+        tp[g] = test + (long long)rows[g] * L + lane;
+        cp[g] = ONE_CTRL ? ctrl : ctrl + (long long)rows[g] * L + lane;
+        yp[g] = ys + g * L + lane;
+    }
+    double* wp = w1g + (WS ? 2 * lane : lane);
+    double* w2p = w2g ? w2g + lane : nullptr;
+    double* pp[G];
+    if (TM != 2) {
+#pragma unroll
+        for (int g = 0; g < G; ++g) pp[g] = tpdg + g * Lp + lane;
+    }
+    const int n_full = L / STEP;              // lines that every lane of the warp owns
+    int i = 0;
+#pragma unroll 1
+    for (; i + B <= n_full; i += B) {
+        double2 t[B][G], c[B][G];
+#pragma unroll
+        for (int b = 0; b < B; ++b)
+#pragma unroll
+            for (int g = 0; g < G; ++g) {
+                t[b][g] = tp[g][b * STEP];
+                if (!ONE_CTRL) c[b][g] = cp[g][b * STEP];
+            }
+        double yv[B][G], pdv[B][G], th[B][G], w1[B], w2[B];
+        em_stage_lines<G, ONE_CTRL, B>(t, c, k, tx1, x2, tps, two_tps, yv, pdv, th, w1, w2);
+#pragma unroll
+        for (int b = 0; b < B; ++b) {
+#pragma unroll
+            for (int g = 0; g < G; ++g) yp[g][b * STEP] = yv[b][g];
+            em_stage_sums<G>(yv[b], th[b], w1[b], w2[b], tx1, x2, r.acc);
+            if (WS) reinterpret_cast<double2*>(wp)[b * STEP] = make_double2(w1[b], w2[b]);
+            else {
+                wp[b * STEP] = w1[b];
+                if (w2p) w2p[b * STEP] = w2[b];
+            }
+            if (TM != 2) {
+#pragma unroll
+                for (int g = 0; g < G; ++g) pp[g][b * STEP] = pdv[b][g];
+            }
+        }
+        if (TM == 2) tmem_store<B * G>(tpd, &pdv[0][0]);
+        tmem_store<B * G>(tth, &th[0][0]);
+        tpd += 2 * G * B;
+        tth += 2 * G * B;
+#pragma unroll
+        for (int g = 0; g < G; ++g) {
+            tp[g] += B * STEP;
+            if (!ONE_CTRL) cp[g] += B * STEP;
+            yp[g] += B * STEP;
+            if (TM != 2) pp[g] += B * STEP;
+        }
+        wp += (WS ? 2 : 1) * B * STEP;
+        if (w2p) w2p += B * STEP;
+    }
+    // the left-over lines, one at a time: a full line when n_full is odd, then the warp's partial line
+#pragma unroll 1
+    for (; i < n_warp; ++i) {
+        const bool live = lane + i * STEP < L;
+        double2 t[1][G], c[1][G];
+#pragma unroll
+        for (int g = 0; g < G; ++g) {
+            // a lane without this line reads its own line 0 instead (mode 2 runs at L >= 32) and discards the result
+            t[0][g] = live ? tp[g][0] : test[(long long)rows[g] * L + lane];
+            if (!ONE_CTRL) c[0][g] = live ? cp[g][0] : ctrl[(long long)rows[g] * L + lane];
+        }
+        double yv[1][G], pdv[1][G], th[1][G], w1[1], w2[1];
+        em_stage_lines<G, ONE_CTRL, 1>(t, c, k, tx1, x2, tps, two_tps, yv, pdv, th, w1, w2);
+        if (live) {
+#pragma unroll
+            for (int g = 0; g < G; ++g) yp[g][0] = yv[0][g];
+            em_stage_sums<G>(yv[0], th[0], w1[0], w2[0], tx1, x2, r.acc);
+            if (WS) reinterpret_cast<double2*>(wp)[0] = make_double2(w1[0], w2[0]);
+            else {
+                wp[0] = w1[0];
+                if (w2p) w2p[0] = w2[0];
+            }
+            if (TM != 2) {
+#pragma unroll
+                for (int g = 0; g < G; ++g) pp[g][0] = pdv[0][g];
+            }
+        }
+        if (TM == 2) tmem_store<G>(tpd, &pdv[0][0]);
+        tmem_store<G>(tth, &th[0][0]);
+        tpd += 2 * G;
+        tth += 2 * G;
+#pragma unroll
+        for (int g = 0; g < G; ++g) {
+            tp[g] += STEP;
+            if (!ONE_CTRL) cp[g] += STEP;
+            yp[g] += STEP;
+            if (TM != 2) pp[g] += STEP;
+        }
+        wp += (WS ? 2 : 1) * STEP;
+        if (w2p) w2p += STEP;
+    }
+    tmem_wait_st();
+    // finite <=> every staged value of this lane is (see above)
+    r.bad = !(fabs(r.acc[2 * G]) <= 1.79769313486231570e308);
+    return r;
+}
+
 // Shared memory of one team: y and tau [G][L], the reduction tiles and totals.  tau_pr_den, E[w] and E[w^2]
 // live in global memory (L2): 27.5 KB per gene at G = 4, L = 400 -> 8 genes (two warps per scheduler) per SM.
 __host__ __device__ constexpr long long em_fast_smem_doubles(int G, int W, int L) {
@@ -824,8 +1023,38 @@ __global__ void __launch_bounds__(TM ? kTmemTeams * 32 : W * 32, TM ? JACKS_TM_C
             EmX<G> xv;
 #pragma unroll
             for (int g = 0; g < G; ++g) { xv.x1[g] = x1r[g]; xv.x2[g] = x2r[g]; xv.tx1[g] = 0.0; xv.tx2[g] = 0.0; }
-            const EmStaged<G> sg = em_stage_gene<G, STEP, TM, WS>(a.test, a.ctrl, rows, ys, tpdg, L, Lp, l0, a.ctrl_lines, a.ctrl_rowmean_fill,
-                                                              fill, tps, tbase + pdoff, tbase, n_warp, xv, w1g, w2g);
+            EmStaged<G> sg;
+            bool lean = false;
+#ifndef JACKS_STAGE_OLD
+            if (PLAIN && W == 1 && em_stage_initialises<G, TM>()) {
+                // the common launch: lean staging (em_stage_plain); a gene whose single control column has an undefined sd
+                // (matched rule, infer.py:68: it takes each line's test sd) goes through the general function
+                EmX12<G> xs;
+                EmCtl<G> k;
+#pragma unroll
+                for (int g = 0; g < G; ++g) { xs.x1[g] = x1r[g]; xs.x2[g] = x2r[g]; k.cm[g] = 0.0; k.cc[g] = 0.0; }
+                if (a.ctrl_lines == 1) {
+                    bool cn = false;
+#pragma unroll
+                    for (int g = 0; g < G; ++g) {
+                        const double2 c0 = a.ctrl[rows[g]];
+                        k.cm[g] = c0.x;
+                        k.cc[g] = fma(c0.y, c0.y, 1e-2);
+                        cn |= (c0.y != c0.y);
+                    }
+                    if (!cn) {
+                        sg = em_stage_plain<G, TM, WS, true>(a.test, a.ctrl, rows, k, ys, tpdg, L, Lp, lane, tps, tbase + pdoff, tbase, n_warp, xs, w1g, w2g);
+                        lean = true;
+                    }
+                } else {
+                    sg = em_stage_plain<G, TM, WS, false>(a.test, a.ctrl, rows, k, ys, tpdg, L, Lp, lane, tps, tbase + pdoff, tbase, n_warp, xs, w1g, w2g);
+                    lean = true;
+                }
+            }
+#endif
+            if (!lean)
+                sg = em_stage_gene<G, STEP, TM, WS>(a.test, a.ctrl, rows, ys, tpdg, L, Lp, l0, a.ctrl_lines, a.ctrl_rowmean_fill,
+                                                    fill, tps, tbase + pdoff, tbase, n_warp, xv, w1g, w2g);
             bad = sg.bad;
 #pragma unroll
             for (int i = 0; i < NV; ++i) acc[i] = sg.acc[i];       // the initial sums if staging initialises; otherwise zeros
