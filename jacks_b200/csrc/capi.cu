@@ -547,8 +547,9 @@ struct HostRunOpts {
 
 // Gene ranges of the pipelined host run: contiguous blocks; with p-values on, boundaries sit on multiples of 1,024 genes.
 static int host_run_ranges(int64_t n_genes) {
+    static const int cap = []() { const char* v = getenv("JACKS_HOST_RANGES"); return v ? atoi(v) : 16; }();      // tuning
     int R = 1;
-    if (n_genes >= 4096) R = (int)std::min<int64_t>(16, n_genes / 2048);
+    if (n_genes >= 4096) R = (int)std::min<int64_t>(std::max(1, cap), n_genes / 2048);
     return std::min(R, kMaxRanges);
 }
 static int64_t host_run_bound(int64_t n_genes, int R, int r, bool kde) {

@@ -389,8 +389,12 @@ __device__ __forceinline__ unsigned long long sortable_key(double v) {
 }
 
 // keys[s][i] = image of src[s][i] (or of src[s][idx[s][i]] when idx is given); idx_out[s][i] = i when asked for
+// `gate` (all sort kernels): when given, the launch does nothing unless *gate != 0 (the exact two-key fallback of
+// sort_mean_var is enqueued unconditionally and runs only if the tie repair asked for it -- no host round trip).
 __global__ void __launch_bounds__(256) rs_load_keys(const double* __restrict__ src, const int* __restrict__ idx, long long ld, long long N,
-                                                    unsigned long long* __restrict__ keys, int* __restrict__ idx_out) {
+                                                    unsigned long long* __restrict__ keys, int* __restrict__ idx_out,
+                                                    const int* __restrict__ gate) {
+    if (gate && *gate == 0) return;
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= N) return;
     const long long o = (long long)blockIdx.y * ld;
@@ -400,8 +404,9 @@ __global__ void __launch_bounds__(256) rs_load_keys(const double* __restrict__ s
 }
 
 __global__ void __launch_bounds__(kRsThreads) rs_hist(const unsigned long long* __restrict__ keys, long long ld, long long N, int shift,
-                                                      int nchunk, unsigned* __restrict__ hist) {
+                                                      int nchunk, unsigned* __restrict__ hist, const int* __restrict__ gate) {
     __shared__ unsigned sh[kRsBins];
+    if (gate && *gate == 0) return;
     const int s = blockIdx.y, chunk = blockIdx.x;
     for (int c = threadIdx.x; c < kRsBins; c += kRsThreads) sh[c] = 0;
     __syncthreads();
@@ -415,9 +420,10 @@ __global__ void __launch_bounds__(kRsThreads) rs_hist(const unsigned long long* 
 }
 
 // one CTA per segment: hist[chunk][bin] becomes the position of the first key of (chunk, bin) in the sorted segment
-__global__ void __launch_bounds__(1024) rs_scan(int nchunk, unsigned* __restrict__ hist) {
+__global__ void __launch_bounds__(1024) rs_scan(int nchunk, unsigned* __restrict__ hist, const int* __restrict__ gate) {
     __shared__ unsigned tot[kRsBins];
     __shared__ unsigned wsum[32];
+    if (gate && *gate == 0) return;
     unsigned* h = hist + (long long)blockIdx.x * nchunk * kRsBins;
     constexpr int KMAX = 32;                      // chunks held in registers (131,072 keys per segment); more: serial path
     if (nchunk <= KMAX) {
@@ -472,8 +478,9 @@ __global__ void __launch_bounds__(1024) rs_scan(int nchunk, unsigned* __restrict
 __global__ void __launch_bounds__(kRsThreads) rs_scatter(const unsigned long long* __restrict__ kin, const int* __restrict__ iin,
                                                          long long ld, long long N, int shift, int nchunk,
                                                          const unsigned* __restrict__ hist, unsigned long long* __restrict__ kout,
-                                                         int* __restrict__ iout) {
+                                                         int* __restrict__ iout, const int* __restrict__ gate) {
     extern __shared__ unsigned cnt[];                    // [8 warps][kRsBins]
+    if (gate && *gate == 0) return;
     const int s = blockIdx.y, chunk = blockIdx.x;
     constexpr int W = kRsThreads / 32, SEG = kRsChunk / W;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -517,13 +524,109 @@ __global__ void __launch_bounds__(kRsThreads) rs_scatter(const unsigned long lon
 
 // sorted copies: dm[k] = km[idx[k]], dv[k] = kv[idx[k]]
 __global__ void __launch_bounds__(256) rs_gather_sorted(const double* __restrict__ km, const double* __restrict__ kv, const int* __restrict__ idx,
-                                                        long long ld, long long N, double* __restrict__ dm, double* __restrict__ dv) {
+                                                        long long ld, long long N, double* __restrict__ dm, double* __restrict__ dv,
+                                                        const int* __restrict__ gate) {
+    if (gate && *gate == 0) return;
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= N) return;
     const long long o = (long long)blockIdx.y * ld;
     const int from = idx[o + i];
     dm[o + i] = km[o + from];
     dv[o + i] = kv[o + from];
+}
+
+// Tie repair after a stable sort by the MEAN alone (from index order).  The order wanted is (mean, var, index): only the
+// runs of equal means can be out of order, and inside a run the stable sort has left index order, so a stable sort of
+// the run by the variance finishes the job.  Screens have many such runs (integer counts: two guides with the same
+// unordered pair of counts tie in the mean, and their variances can differ in the last bit) but most are short.
+//   rs_tie_find, one thread per element: the thread at the head of a run measures it (bounded scan) and
+//     * insertion-sorts a run of 2..kTieSelf elements itself (stable; an ordered run costs one comparison per element),
+//     * queues a run of up to kTieWarp elements for a warp, of up to kTieCta elements for a CTA (rs_tie_sort_runs:
+//       rank counting on the variance keys held in shared memory, stable through the position tie-break);
+//     a thread that sees an inversion (same mean, larger variance first) inside a run LONGER than kTieCta raises *gate and
+//     the exact two-key radix sort runs instead (sort_mean_var).  A long run that is already in order -- thousands of
+//     zero-count guides with identical mean and variance -- costs nothing.
+// Keys are compared through their sortable images, exactly as the radix passes see them (-0.0 == +0.0, NaN by bits).
+// The means of a run are equal under that image; they stay where they are (only (var, index) move).
+constexpr int kTieSelf = 16, kTieWarp = 256, kTieCta = 2048;
+struct TieRun { long long at; int len; int pad; };       // at: position in the [S][ld] arrays
+// ctl[0]: gate, ctl[1]: warp-sized runs queued, ctl[2]: CTA-sized runs queued
+__global__ void __launch_bounds__(256) rs_tie_find(const double* __restrict__ km, double* __restrict__ kv, int* __restrict__ idx,
+                                                   long long ld, long long N, int* __restrict__ ctl,
+                                                   TieRun* __restrict__ warp_runs, TieRun* __restrict__ cta_runs, long long warp_cap, long long cta_cap) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    const long long o = (long long)blockIdx.y * ld;
+    const double* m = km + o; double* v = kv + o; int* ix = idx + o;
+    const unsigned long long key = sortable_key(m[i]);
+    const bool tie_next = (i + 1 < N) && sortable_key(m[i + 1]) == key;
+    if (!tie_next) return;                                         // last element of its run (or a run of one)
+    const bool head = (i == 0) || sortable_key(m[i - 1]) != key;
+    if (head) {
+        long long e = i + 2;
+        while (e < N && e - i <= kTieCta && sortable_key(m[e]) == key) ++e;
+        const long long len = e - i;
+        if (len > kTieCta) return;                                 // a long run: its inversions (if any) raise the gate below
+        if (len > kTieSelf) {
+            const bool big = len > kTieWarp;
+            const long long slot = atomicAdd(&ctl[big ? 2 : 1], 1);
+            if (slot < (big ? cta_cap : warp_cap)) { TieRun r; r.at = o + i; r.len = (int)len; r.pad = 0; (big ? cta_runs : warp_runs)[slot] = r; }
+            else ctl[0] = 1;                                       // cannot happen (the lists hold every possible run); stay exact anyway
+            return;
+        }
+        for (long long a = i + 1; a < e; ++a) {                    // stable insertion sort by the variance
+            const double va = v[a];
+            const int ia = ix[a];
+            const unsigned long long ka = sortable_key(va);
+            long long b = a;
+            while (b > i && sortable_key(v[b - 1]) > ka) { v[b] = v[b - 1]; ix[b] = ix[b - 1]; --b; }
+            if (b != a) { v[b] = va; ix[b] = ia; }
+        }
+        return;
+    }
+    // not a head: does the pair (i, i+1) stand in the wrong order inside a run too long to be repaired?  (Inside a shorter
+    // run the head or its helpers may be permuting these very elements: whatever is read here, the run is found short.)
+    if (sortable_key(v[i]) <= sortable_key(v[i + 1])) return;
+    long long h = i;
+    while (h > 0 && i - h <= kTieCta && sortable_key(m[h - 1]) == key) {
+        --h;
+        if (((i - h) & 255) == 0 && *(volatile int*)ctl) return;   // someone else has already asked for the fallback
+    }
+    long long e = i + 2;
+    while (e < N && e - h <= kTieCta && sortable_key(m[e]) == key) ++e;
+    if (e - h > kTieCta) ctl[0] = 1;
+}
+
+// Stable rank-counting sort of the queued runs by the variance key: TEAM threads (a warp or the whole CTA) per run.
+template <bool CTA>
+__global__ void __launch_bounds__(256) rs_tie_sort_runs(double* __restrict__ kv, int* __restrict__ idx, const int* __restrict__ ctl,
+                                                        const TieRun* __restrict__ runs, long long cap) {
+    constexpr int LEN = CTA ? kTieCta : kTieWarp, TEAMS = CTA ? 1 : 8, TEAM = CTA ? 256 : 32;
+    __shared__ unsigned long long s_key[TEAMS][LEN];
+    __shared__ double s_val[TEAMS][LEN];
+    __shared__ int s_idx[TEAMS][LEN];
+    if (ctl[0]) return;                                           // the exact fallback redoes everything
+    const long long n_runs = min((long long)ctl[CTA ? 2 : 1], cap);
+    const int team = CTA ? 0 : (int)(threadIdx.x >> 5), t = CTA ? (int)threadIdx.x : (int)(threadIdx.x & 31);
+    for (long long r = (long long)blockIdx.x * TEAMS + team; r < n_runs; r += (long long)gridDim.x * TEAMS) {
+        const TieRun run = runs[r];
+        double* v = kv + run.at; int* ix = idx + run.at;
+        for (int j = t; j < run.len; j += TEAM) {
+            const double x = v[j];
+            s_val[team][j] = x; s_idx[team][j] = ix[j]; s_key[team][j] = sortable_key(x);
+        }
+        if (CTA) __syncthreads(); else __syncwarp();
+        for (int j = t; j < run.len; j += TEAM) {
+            const unsigned long long kj = s_key[team][j];
+            int rank = 0;
+            for (int k = 0; k < run.len; ++k) {
+                const unsigned long long kk = s_key[team][k];
+                rank += (kk < kj || (kk == kj && k < j)) ? 1 : 0;
+            }
+            v[rank] = s_val[team][j]; ix[rank] = s_idx[team][j];
+        }
+        if (CTA) __syncthreads(); else __syncwarp();
+    }
 }
 
 // ---- sliding mean (shifted, as the reference), reverse running max, sqrt, scatter ----------------
@@ -807,12 +910,18 @@ int normalize_core(JacksCtx* ctx, const double* d_values, long long N, int C, in
 }
 
 // Sort every segment's (mean, var, index) keys: on return km_s / kv_s / ki_s hold the sorted keys.  Scratch from `base`.
-struct SortScratch { unsigned long long* kA; unsigned long long* kB; int* iA; int* iB; unsigned* hist; };
-size_t sort_scratch_bytes(int S, long long ld, Arena* a, size_t o[5]) {
+struct SortScratch { unsigned long long* kA; unsigned long long* kB; int* iA; int* iB; unsigned* hist; int* gate; TieRun* warp_runs; TieRun* cta_runs; };
+__global__ void set_flag_kernel(int* f) { *f = 1; }
+inline long long tie_warp_cap(int S, long long ld) { return (long long)S * (ld / kTieSelf + 1); }
+inline long long tie_cta_cap(int S, long long ld) { return (long long)S * (ld / kTieWarp + 1); }
+size_t sort_scratch_bytes(int S, long long ld, Arena* a, size_t o[8]) {
     const int nchunk = (int)((ld + kRsChunk - 1) / kRsChunk);
     o[0] = a->take((size_t)S * ld * 8); o[1] = a->take((size_t)S * ld * 8);
     o[2] = a->take((size_t)S * ld * 4); o[3] = a->take((size_t)S * ld * 4);
     o[4] = a->take((size_t)S * nchunk * kRsBins * 4);
+    o[5] = a->take(256);
+    o[6] = a->take((size_t)tie_warp_cap(S, ld) * sizeof(TieRun));
+    o[7] = a->take((size_t)tie_cta_cap(S, ld) * sizeof(TieRun));
     return a->off;
 }
 int sort_mean_var(JacksCtx* ctx, cudaStream_t st, const double* km, const double* kv, int S, long long ld, long long N,
@@ -826,18 +935,38 @@ int sort_mean_var(JacksCtx* ctx, cudaStream_t st, const double* km, const double
     dim3 eg((unsigned)((N + 255) / 256), (unsigned)S), cg((unsigned)nchunk, (unsigned)S);
     unsigned long long* kin = w.kA; unsigned long long* kout = w.kB;
     int* iin = w.iA; int* iout = w.iB;
-    for (int which = 0; which < 2; ++which) {              // stable by variance, then stable by mean
-        rs_load_keys<<<eg, 256, 0, st>>>(which == 0 ? kv : km, which == 0 ? nullptr : iin, ld, N, kin, which == 0 ? iin : nullptr);
+    // `which`: 0 stable by the variance from index order, 1 stable by the mean.  An even number of passes: the sorted
+    // keys and indices end in the buffers they started in.
+    auto radix = [&](int which, bool from_index_order, const int* gate) {
+        rs_load_keys<<<eg, 256, 0, st>>>(which == 0 ? kv : km, from_index_order ? nullptr : iin, ld, N, kin, from_index_order ? iin : nullptr, gate);
         ctx->launches++;
         for (int shift = 0; shift < 64; shift += kRsBits) {
-            rs_hist<<<cg, kRsThreads, 0, st>>>(kin, ld, N, shift, nchunk, w.hist);
-            rs_scan<<<S, 1024, 0, st>>>(nchunk, w.hist);
-            rs_scatter<<<cg, kRsThreads, kRsThreads / 32 * kRsBins * 4, st>>>(kin, iin, ld, N, shift, nchunk, w.hist, kout, iout);
+            rs_hist<<<cg, kRsThreads, 0, st>>>(kin, ld, N, shift, nchunk, w.hist, gate);
+            rs_scan<<<S, 1024, 0, st>>>(nchunk, w.hist, gate);
+            rs_scatter<<<cg, kRsThreads, kRsThreads / 32 * kRsBins * 4, st>>>(kin, iin, ld, N, shift, nchunk, w.hist, kout, iout, gate);
             ctx->launches += 3;
             std::swap(kin, kout); std::swap(iin, iout);
         }
+    };
+    static const bool two_key = []() { const char* v = getenv("JACKS_SORT_TWO_KEY"); return v && atoi(v) != 0; }();   // tests: force the fallback
+    // Fast path: ONE stable sort by the mean, then the runs of equal means are put in (var, index) order in place
+    // (rs_tie_repair).  Six radix passes instead of twelve.
+    if ((e = cudaMemsetAsync(w.gate, 0, 4 * sizeof(int), st)) != cudaSuccess) return cuda_fail(e, "memset");
+    if (!two_key) {
+        radix(1, true, nullptr);
+        rs_gather_sorted<<<eg, 256, 0, st>>>(km, kv, iin, ld, N, km_s, kv_s, nullptr);
+        rs_tie_find<<<eg, 256, 0, st>>>(km_s, kv_s, iin, ld, N, w.gate, w.warp_runs, w.cta_runs, tie_warp_cap(S, ld), tie_cta_cap(S, ld));
+        rs_tie_sort_runs<false><<<4 * 148, 256, 0, st>>>(kv_s, iin, w.gate, w.warp_runs, tie_warp_cap(S, ld));
+        rs_tie_sort_runs<true><<<148, 256, 0, st>>>(kv_s, iin, w.gate, w.cta_runs, tie_cta_cap(S, ld));
+        ctx->launches += 4;
+    } else {
+        set_flag_kernel<<<1, 1, 0, st>>>(w.gate);
     }
-    rs_gather_sorted<<<eg, 256, 0, st>>>(km, kv, iin, ld, N, km_s, kv_s);
+    // Exact fallback, enqueued always, run only when the repair met an out-of-order run longer than it handles:
+    // stable by the variance, then stable by the mean (Python's tuple order, preprocess.py:39-40).
+    radix(0, true, w.gate);
+    radix(1, false, w.gate);
+    rs_gather_sorted<<<eg, 256, 0, st>>>(km, kv, iin, ld, N, km_s, kv_s, w.gate);
     ctx->launches++;
     if ((e = cudaGetLastError()) != cudaSuccess) return cuda_fail(e, "sort kernels");
     *ki_sorted = iin;
@@ -854,7 +983,7 @@ int condense_core(JacksCtx* ctx, const double* d_lc, long long N, int C, const i
     const size_t o_kms = a.take((size_t)S * ld * 8), o_kvs = a.take((size_t)S * ld * 8);
     const size_t o_P = a.take((size_t)S * (ld + 1) * 8), o_M = a.take((size_t)S * ld * 8);
     const size_t o_idx = a.take((S + 1 + nidx) * sizeof(int));
-    size_t so[5];
+    size_t so[8];
     sort_scratch_bytes(S, ld, &a, so);
     int rc;
     if ((rc = ctx->pre.reserve(a.off)) != JACKS_OK) return rc;
@@ -876,7 +1005,7 @@ int condense_core(JacksCtx* ctx, const double* d_lc, long long N, int C, const i
     ctx->launches++;
     if (max_rep >= 2) {
         SortScratch w{(unsigned long long*)(base + so[0]), (unsigned long long*)(base + so[1]), (int*)(base + so[2]), (int*)(base + so[3]),
-                      (unsigned*)(base + so[4])};
+                      (unsigned*)(base + so[4]), (int*)(base + so[5]), (TieRun*)(base + so[6]), (TieRun*)(base + so[7])};
         int* kis = nullptr;
         if ((rc = sort_mean_var(ctx, st, km, kv, S, ld, N, w, kms, kvs, &kis)) != JACKS_OK) return rc;
         smooth_monotone_scatter_kernel<<<S, kScanThreads, 0, st>>>(kvs, kis, ld, N, S, (int)window, monotonize ? 1 : 0, d_off,
@@ -1068,7 +1197,7 @@ extern "C" int jacks_posterior_sd_subset_host(JacksCtx* ctx, const double* data,
     if ((rc = ctx->out[6].reserve((size_t)N * sizeof(double))) != JACKS_OK) return rc;            // sd
     if ((rc = ctx->out[7].reserve((size_t)(2 + n_rep) * sizeof(int) + (size_t)N + 16)) != JACKS_OK) return rc;
     Arena ar;
-    size_t so[5];
+    size_t so[8];
     sort_scratch_bytes(1, Np, &ar, so);
     if ((rc = ctx->pre.reserve(ar.off)) != JACKS_OK) return rc;
     cudaStream_t st = ctx->stream;
@@ -1090,7 +1219,7 @@ extern "C" int jacks_posterior_sd_subset_host(JacksCtx* ctx, const double* data,
     {
         char* base = (char*)ctx->pre.p;
         SortScratch w{(unsigned long long*)(base + so[0]), (unsigned long long*)(base + so[1]), (int*)(base + so[2]), (int*)(base + so[3]),
-                      (unsigned*)(base + so[4])};
+                      (unsigned*)(base + so[4]), (int*)(base + so[5]), (TieRun*)(base + so[6]), (TieRun*)(base + so[7])};
         if ((rc = sort_mean_var(ctx, st, km0, kv0, 1, Np, N, w, km, kv, &ki)) != JACKS_OK) return rc;
     }
     double* scratch = (double*)ctx->out[5].p;

@@ -145,3 +145,49 @@ def test_infer_missing_variances_single_replicate(nat):
     err = np.abs(out[:, 1, 1] - ref) / np.abs(ref)
     assert err.max() < 1e-9, err.max()
     assert np.array_equal(out[:, 0, :], data[:, 0, :])
+
+
+@pytest.mark.parametrize('case', ['pairs', 'warp_runs', 'cta_runs', 'long_ordered', 'long_unordered', 'poisson300'])
+def test_posterior_sd_mean_ties_vs_oracle(nat, case):
+    """The sort is ONE stable radix sort by the mean plus a repair of the runs of equal means (by the variance, then the
+    index: Python's tuple order, preprocess.py:39-40).  Every repair path: runs a thread sorts itself (<= 16), runs a warp
+    or a CTA ranks (<= 256, <= 2048), a longer run that is already in order (nothing to do), a longer run that is not (the
+    exact two-key sort takes over), and the bench's Poisson(300) library whose modal count pairs tie ~80 deep."""
+    from oracle import jacks_oracle as O
+    rng = np.random.default_rng(['pairs', 'warp_runs', 'cta_runs', 'long_ordered', 'long_unordered', 'poisson300'].index(case) + 100)
+    N = 6000
+    a = rng.normal(0.0, 1.0, size=N)
+    d = np.abs(rng.normal(0.0, 0.3, size=N))
+    def tie(sel, mean):             # rows `sel` share one mean exactly; their variances stay as drawn
+        a[sel] = mean
+    if case == 'pairs':
+        for k in range(0, 3000, 3):
+            tie(slice(k, k + rng.integers(2, 4)), a[k])
+    elif case == 'warp_runs':
+        for k in range(0, 4000, 400):
+            tie(rng.choice(N, size=int(rng.integers(17, 257)), replace=False), float(k) / 1000.0)
+    elif case == 'cta_runs':
+        tie(rng.choice(N, size=300, replace=False), 0.25)
+        tie(rng.choice(N, size=2048, replace=False), -0.5)
+    elif case == 'long_ordered':
+        sel = np.sort(rng.choice(N, size=3000, replace=False))
+        tie(sel, 0.125)
+        d[sel] = 0.0                # e.g. zero-count guides: identical mean AND variance, index order stands
+    elif case == 'long_unordered':
+        tie(rng.choice(N, size=2500, replace=False), 0.125)
+    if case == 'poisson300':
+        cnt = rng.poisson(300.0, size=(72000, 2)).astype(np.float64)
+        lc = np.log2(cnt + 32.0)
+        lc -= np.median(lc, axis=0)
+    else:
+        # two replicates a -/+ d: the mean is a exactly when d is a multiple of a small power of two
+        d = np.round(d * 1024.0) / 1024.0
+        a = np.round(a * 1024.0) / 1024.0
+        lc = np.stack([a - d, a + d], axis=1)
+        assert np.array_equal(lc.mean(axis=1), a)
+    ctx = nat.context(0)
+    data = nat.condense_host(ctx, lc, [[0, 1]])
+    ref = O.posterior_sd(lc)
+    assert np.array_equal(data[:, 0, 0], lc.mean(axis=1))
+    err = np.abs(data[:, 0, 1] - ref) / np.maximum(np.abs(ref), 1e-300)
+    assert err.max() < 1e-9, (case, err.max())

@@ -29,6 +29,8 @@ def main():
     arows = np.concatenate([rows.astype(np.int32), prows])
     N, L = test.shape[0], test.shape[1]
     d_test = torch.from_numpy(test).to(dev)
+    if os.environ.get('QB_ONE_CTRL', '1') != '0':          # one control column for all lines, as the bench passes it
+        ctrl = np.ascontiguousarray(ctrl[:, :1, :])
     d_ctrl = torch.from_numpy(ctrl).to(dev)
     n_all = len(aoffs) - 1
     T = int(aoffs[-1])
@@ -46,13 +48,13 @@ def main():
             os.environ['JACKS_EM_W'] = shape
         plan = _native.EmPlan(ctx, aoffs, arows, N, L)
         io = _native.EmDeviceIO()
-        io.test, io.ctrl, io.ctrl_lines = d_test.data_ptr(), d_ctrl.data_ptr(), L
+        io.test, io.ctrl, io.ctrl_lines = d_test.data_ptr(), d_ctrl.data_ptr(), int(d_ctrl.shape[1])
         io.w1, io.w2, io.x1, io.x2, io.n_iters = w1.data_ptr(), w2.data_ptr(), x1.data_ptr(), x2.data_ptr(), iters.data_ptr()
         for _ in range(2):
             plan.run_device(params, io, stream)
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        reps = 5
+        reps = int(os.environ.get('QB_REPS', 5))
         e0.record()
         for _ in range(reps):
             plan.run_device(params, io, stream)
