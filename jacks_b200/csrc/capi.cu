@@ -54,6 +54,14 @@ void DevBuf::release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
 
 using namespace jacks;
 
+// JACKS_TRACE: host-side stamps relative to the start of the running screen job
+static std::chrono::steady_clock::time_point g_trace_t0;
+static bool g_trace_on = false;
+static void trace_stamp(const char* what) {
+    if (g_trace_on) fprintf(stderr, "[jacks trace] %-28s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - g_trace_t0).count());
+}
+
+
 namespace {
 
 // Warps per gene of the fast kernel for (G, L); 0 = use the generic kernel.
@@ -206,6 +214,8 @@ int jacks_ctx_create(int device, JacksCtx** out) {
     if ((e = cudaStreamCreateWithFlags(&c->out_stream, cudaStreamNonBlocking)) != cudaSuccess) { delete c; return cuda_fail(e, "cudaStreamCreate"); }
     if ((e = cudaStreamCreateWithFlags(&c->plan_stream, cudaStreamNonBlocking)) != cudaSuccess) { delete c; return cuda_fail(e, "cudaStreamCreate"); }
     if ((e = cudaStreamCreateWithFlags(&c->side_stream, cudaStreamNonBlocking)) != cudaSuccess) { delete c; return cuda_fail(e, "cudaStreamCreate"); }
+    if ((e = cudaStreamCreateWithFlags(&c->cmp_stream, cudaStreamNonBlocking)) != cudaSuccess) { delete c; return cuda_fail(e, "cudaStreamCreate"); }
+    if ((e = cudaStreamCreateWithFlags(&c->out2_stream, cudaStreamNonBlocking)) != cudaSuccess) { delete c; return cuda_fail(e, "cudaStreamCreate"); }
     if ((e = cudaEventCreateWithFlags(&c->side_fork, cudaEventDisableTiming)) != cudaSuccess) { delete c; return cuda_fail(e, "cudaEventCreate"); }
     if ((e = cudaEventCreateWithFlags(&c->side_join, cudaEventDisableTiming)) != cudaSuccess) { delete c; return cuda_fail(e, "cudaEventCreate"); }
     *out = c;
@@ -234,6 +244,8 @@ void jacks_ctx_destroy(JacksCtx* c) {
     if (c->out_stream) cudaStreamDestroy(c->out_stream);
     if (c->plan_stream) cudaStreamDestroy(c->plan_stream);
     if (c->side_stream) cudaStreamDestroy(c->side_stream);
+    if (c->cmp_stream) cudaStreamDestroy(c->cmp_stream);
+    if (c->out2_stream) cudaStreamDestroy(c->out2_stream);
     if (c->side_fork) cudaEventDestroy(c->side_fork);
     if (c->side_join) cudaEventDestroy(c->side_join);
     if (c->res_busy) cudaEventDestroy(c->res_busy);
@@ -245,8 +257,12 @@ int64_t jacks_ctx_launch_count(const JacksCtx* c) { return c ? c->launches : 0; 
 int jacks_ctx_synchronize(JacksCtx* c) {
     if (!c) return fail(JACKS_E_INVALID, "jacks_ctx_synchronize: NULL ctx");
     cudaSetDevice(c->device);
-    const cudaError_t e1 = cudaStreamSynchronize(c->copy_stream), e2 = cudaStreamSynchronize(c->stream),
+    const cudaError_t e0 = cudaStreamSynchronize(c->side_stream), e00a = cudaStreamSynchronize(c->cmp_stream);
+    const cudaError_t e00b = cudaStreamSynchronize(c->plan_stream), e00c = cudaStreamSynchronize(c->out2_stream);
+    const cudaError_t e00 = e00a != cudaSuccess ? e00a : (e00b != cudaSuccess ? e00b : e00c);
+    const cudaError_t e1 = cudaStreamSynchronize(c->copy_stream), e2a = cudaStreamSynchronize(c->stream),
                       e3 = cudaStreamSynchronize(c->out_stream);
+    const cudaError_t e2 = e2a != cudaSuccess ? e2a : (e0 != cudaSuccess ? e0 : e00);
     for (JacksEmPlan* pl : c->pending_plans) jacks_em_plan_destroy(pl);
     c->pending_plans.clear();
     for (cudaEvent_t ev : c->pending_events) cudaEventDestroy(ev);
@@ -289,6 +305,15 @@ int jacks_copy_to_host_async(void* dst_host, const void* src_device, uint64_t by
     return e == cudaSuccess ? JACKS_OK : cuda_fail(e, "cudaMemcpyAsync (device -> host)");
 }
 
+}  // extern "C"
+
+// dst[i] = src[i] for n 16-byte words; src may be pinned HOST memory (zero-copy reads over PCIe)
+__global__ void __launch_bounds__(256) pull_words_kernel(const uint4* __restrict__ src, uint4* __restrict__ dst, size_t n) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) dst[i] = src[i];
+}
+
+extern "C" {
+
 int jacks_em_plan_create(JacksCtx* ctx, const int64_t* gene_offsets, const int32_t* guide_rows, int64_t n_genes,
                          int64_t n_rows, int32_t n_lines, JacksEmPlan** out) {
     if (!ctx || !out) return fail(JACKS_E_INVALID, "jacks_em_plan_create: NULL ctx/out");
@@ -298,16 +323,29 @@ int jacks_em_plan_create(JacksCtx* ctx, const int64_t* gene_offsets, const int32
     if (n_genes >= (1LL << 31)) return fail(JACKS_E_INVALID, "too many genes");
     const int64_t total = n_genes ? gene_offsets[n_genes] : 0;
     if (n_genes && gene_offsets[0] != 0) return fail(JACKS_E_INVALID, "gene_offsets[0] must be 0");
-    int maxG_all = 0;
+    // pass 1 over the genes: guide counts -> bucket sizes (a gene's kind depends only on its guide count)
+    int teamW[kMaxFastG + 1] = {0};
+    for (int G = 1; G <= kMaxFastG; ++G) teamW[G] = choose_team(G, n_lines);
+    long long cnt[kMaxFastG + 1] = {0};
+    long long n_gen = 0, n_big = 0;
+    int gen_maxG = 0, big_maxG = 0;
     for (int64_t g = 0; g < n_genes; ++g) {
         const int64_t G = gene_offsets[g + 1] - gene_offsets[g];
         if (G < 1) return fail(JACKS_E_INVALID, "gene %lld has %lld guides; every gene needs at least one", (long long)g, (long long)G);
         if (G > (1 << 20)) return fail(JACKS_E_INVALID, "gene %lld has too many guides", (long long)g);
-        maxG_all = std::max<int>(maxG_all, (int)G);
+        if (G <= kMaxFastG && teamW[G] > 0) cnt[G]++;
+        else if ((long long)G * n_lines >= kBigGeneElements) { n_big++; big_maxG = std::max(big_maxG, (int)G); }
+        else { n_gen++; gen_maxG = std::max(gen_maxG, (int)G); }
     }
-    for (int64_t i = 0; i < total; ++i)
-        if (guide_rows[i] < 0 || guide_rows[i] >= n_rows)
-            return fail(JACKS_E_INVALID, "guide row %d at position %lld outside [0, %lld)", guide_rows[i], (long long)i, (long long)n_rows);
+    {
+        unsigned bad = 0;                               // branch-free sweep (vectorises); the offender is looked up only on failure
+        const unsigned lim = (unsigned)std::min<int64_t>(n_rows, 0x7fffffff);
+        for (int64_t i = 0; i < total; ++i) bad |= ((unsigned)guide_rows[i] >= lim) ? 1u : 0u;
+        if (bad)
+            for (int64_t i = 0; i < total; ++i)
+                if (guide_rows[i] < 0 || guide_rows[i] >= n_rows)
+                    return fail(JACKS_E_INVALID, "guide row %d at position %lld outside [0, %lld)", guide_rows[i], (long long)i, (long long)n_rows);
+    }
     cudaError_t e = cudaSetDevice(ctx->device);
     if (e != cudaSuccess) return cuda_fail(e, "cudaSetDevice");
 
@@ -323,64 +361,84 @@ int jacks_em_plan_create(JacksCtx* ctx, const int64_t* gene_offsets, const int32
     p->ctx = ctx; p->n_genes = n_genes; p->n_rows = n_rows; p->total_guides = total; p->L = n_lines;
     p->generic = EmBucket{0, 0, 0, 0, 0};
     p->big = EmBucket{0, 0, 0, 0, 0};
-    p->generic_maxG = 0; p->fast_maxG = 0; p->n_fast_genes = 0; p->big_maxG = 0; p->big_grid = 0; p->big_slab = 0;
+    p->generic_maxG = gen_maxG; p->fast_maxG = 0; p->n_fast_genes = 0; p->big_maxG = big_maxG; p->big_grid = 0; p->big_slab = 0;
 
-    // bucket genes by guide count, keeping the caller's order inside each bucket
-    std::vector<std::vector<int>> byG(kMaxFastG + 1);
-    std::vector<int> gen, big;
-    int teamW[kMaxFastG + 1] = {0};
-    for (int G = 1; G <= kMaxFastG; ++G) teamW[G] = choose_team(G, n_lines);
-    for (int64_t g = 0; g < n_genes; ++g) {
-        const int G = (int)(gene_offsets[g + 1] - gene_offsets[g]);
-        if (G <= kMaxFastG && teamW[G] > 0) byG[G].push_back((int)g);
-        else if ((long long)G * n_lines >= kBigGeneElements) { big.push_back((int)g); p->big_maxG = std::max(p->big_maxG, G); }
-        else { gen.push_back((int)g); p->generic_maxG = std::max(p->generic_maxG, G); }
-    }
-    std::vector<int> ids;
-    ids.reserve((size_t)n_genes);
-    std::vector<long long> slot_off;       // gene_offsets[] in bucket-slot order
-    std::vector<int> slot_rows;            // guide rows in bucket-slot order (fast buckets)
-    slot_off.reserve((size_t)n_genes);
-    slot_rows.reserve((size_t)total);
-    // larger G first: the heavier buckets start while the GPU is empty
+    // bucket layout: fast buckets by descending guide count (the heavier buckets start while the GPU is empty), then the
+    // generic bucket, then the CTA-per-gene bucket; inside a bucket the caller's order
+    long long ids_cur[kMaxFastG + 3] = {0}, rows_cur[kMaxFastG + 1] = {0};       // write cursors; [kMaxFastG+1]: generic, [+2]: big
+    long long n_ids = 0, n_slot_rows = 0;
     for (int G = kMaxFastG; G >= 1; --G) {
-        if (byG[G].empty()) continue;
-        EmBucket b{G, teamW[G], (int)byG[G].size(), (int)ids.size(), (long long)slot_rows.size()};
-        ids.insert(ids.end(), byG[G].begin(), byG[G].end());
-        for (int g : byG[G]) {
-            slot_off.push_back(gene_offsets[g]);
-            for (int k = 0; k < G; ++k) slot_rows.push_back(guide_rows[gene_offsets[g] + k]);
-        }
-        p->fast.push_back(b);
+        if (!cnt[G]) continue;
+        p->fast.push_back(EmBucket{G, teamW[G], (int)cnt[G], (int)n_ids, n_slot_rows});
+        ids_cur[G] = n_ids; rows_cur[G] = n_slot_rows;
+        n_ids += cnt[G]; n_slot_rows += cnt[G] * G;
         p->fast_maxG = std::max(p->fast_maxG, G);
-        p->n_fast_genes += b.n;
+        p->n_fast_genes += (int)cnt[G];
     }
-    if (!gen.empty()) {
-        p->generic = EmBucket{0, 0, (int)gen.size(), (int)ids.size(), 0};
-        ids.insert(ids.end(), gen.begin(), gen.end());
-    }
-    if (!big.empty()) {
-        p->big = EmBucket{0, 0, (int)big.size(), (int)ids.size(), 0};
-        ids.insert(ids.end(), big.begin(), big.end());
-        p->big_grid = (int)std::min<long long>((long long)big.size(), 2LL * ctx->n_sm);
+    const long long n_slots = n_ids;                       // fast genes: slot_off entries
+    if (n_gen) { p->generic = EmBucket{0, 0, (int)n_gen, (int)n_ids, 0}; ids_cur[kMaxFastG + 1] = n_ids; n_ids += n_gen; }
+    if (n_big) {
+        p->big = EmBucket{0, 0, (int)n_big, (int)n_ids, 0}; ids_cur[kMaxFastG + 2] = n_ids; n_ids += n_big;
+        p->big_grid = (int)std::min<long long>(n_big, 2LL * ctx->n_sm);
         p->big_slab = em_generic_work_doubles(p->big_maxG, n_lines);
     }
 
     int rc = JACKS_OK;
-    auto up = [&](DevBuf& b, const void* src, size_t bytes) {
-        if (rc != JACKS_OK) return;
-        rc = b.reserve(bytes ? bytes : 8);
-        if (rc == JACKS_OK && bytes) {
-            cudaError_t ee = cudaMemcpyAsync(b.p, src, bytes, cudaMemcpyHostToDevice, ctx->plan_stream);
-            if (ee != cudaSuccess) rc = cuda_fail(ee, "cudaMemcpyAsync(plan)");
+    // The index arrays are built IN the plan's pinned staging and pulled by a copy kernel on the plan stream: a
+    // cudaMemcpyAsync would queue in the copy engine behind whatever upload is in flight (the screen of a screen job).
+    const size_t lens[5] = {n_genes ? (size_t)(n_genes + 1) * sizeof(int64_t) : 0, (size_t)total * sizeof(int32_t), (size_t)n_ids * sizeof(int),
+                            (size_t)n_slots * sizeof(long long), (size_t)n_slot_rows * sizeof(int)};
+    DevBuf* dsts[5] = {&p->b->d_offsets, &p->b->d_rows, &p->b->d_ids, &p->b->d_slot_off, &p->b->d_slot_rows};
+    size_t offs5[5], stage_bytes = 0;
+    for (int i = 0; i < 5; ++i) { offs5[i] = stage_bytes; stage_bytes += (lens[i] + 255) & ~(size_t)255; }
+    if (stage_bytes > p->b->h_cap) {
+        if (p->b->h_stage) cudaFreeHost(p->b->h_stage);
+        p->b->h_stage = nullptr; p->b->h_cap = 0;
+        const size_t want = stage_bytes + stage_bytes / 8 + 4096;
+        if ((e = cudaHostAlloc(&p->b->h_stage, want, cudaHostAllocDefault)) != cudaSuccess) rc = cuda_fail(e, "cudaHostAlloc(plan staging)");
+        else p->b->h_cap = want;
+    }
+    if (rc == JACKS_OK && n_genes > 0) {
+        char* hs = (char*)p->b->h_stage;
+        memcpy(hs + offs5[0], gene_offsets, lens[0]);
+        memcpy(hs + offs5[1], guide_rows, lens[1]);
+        int* s_ids = (int*)(hs + offs5[2]);
+        long long* s_off = (long long*)(hs + offs5[3]);
+        int* s_rows = (int*)(hs + offs5[4]);
+        if (p->fast.size() == 1 && !n_gen && !n_big) {
+            // one bucket holds every gene (a library with a fixed guide count; every pseudo-gene index): slot order is gene order
+            for (int64_t g = 0; g < n_genes; ++g) s_ids[g] = (int)g;
+            memcpy(s_off, gene_offsets, (size_t)n_genes * sizeof(long long));
+            memcpy(s_rows, guide_rows, (size_t)total * sizeof(int));
+        } else {
+            for (int64_t g = 0; g < n_genes; ++g) {
+                const long long o = gene_offsets[g];
+                const int G = (int)(gene_offsets[g + 1] - o);
+                if (G <= kMaxFastG && teamW[G] > 0) {
+                    const long long slot = ids_cur[G]++;
+                    s_ids[slot] = (int)g;
+                    s_off[slot] = o;
+                    int* dst = s_rows + rows_cur[G];
+                    for (int k = 0; k < G; ++k) dst[k] = guide_rows[o + k];
+                    rows_cur[G] += G;
+                } else if ((long long)G * n_lines >= kBigGeneElements) s_ids[ids_cur[kMaxFastG + 2]++] = (int)g;
+                else s_ids[ids_cur[kMaxFastG + 1]++] = (int)g;
+            }
         }
-    };
-    up(p->b->d_offsets, gene_offsets, (size_t)(n_genes + 1) * sizeof(int64_t));
-    up(p->b->d_rows, guide_rows, (size_t)total * sizeof(int32_t));
-    up(p->b->d_ids, ids.data(), ids.size() * sizeof(int));
-    p->h_ids = ids;
-    up(p->b->d_slot_off, slot_off.data(), slot_off.size() * sizeof(long long));
-    up(p->b->d_slot_rows, slot_rows.data(), slot_rows.size() * sizeof(int));
+        p->h_ids.assign(s_ids, s_ids + n_ids);
+    }
+    trace_stamp("    plan: buckets built");
+    void* stage_dev = nullptr;
+    if (rc == JACKS_OK && stage_bytes && (e = cudaHostGetDevicePointer(&stage_dev, p->b->h_stage, 0)) != cudaSuccess) rc = cuda_fail(e, "cudaHostGetDevicePointer");
+    for (int i = 0; i < 5 && rc == JACKS_OK; ++i) {
+        rc = dsts[i]->reserve(lens[i] ? ((lens[i] + 15) & ~(size_t)15) : 16);
+        if (rc != JACKS_OK || !lens[i]) continue;
+        const size_t n16 = (lens[i] + 15) / 16;               // staging slots and device buffers are padded to 16 bytes
+        pull_words_kernel<<<(unsigned)std::min<size_t>((n16 + 255) / 256, 592), 256, 0, ctx->plan_stream>>>(
+            (const uint4*)((const char*)stage_dev + offs5[i]), (uint4*)dsts[i]->p, n16);
+        if ((e = cudaGetLastError()) != cudaSuccess) rc = cuda_fail(e, "pull_words_kernel launch");
+        ctx->launches++;
+    }
     if (rc == JACKS_OK) rc = p->b->d_deferred.reserve((size_t)std::max<int64_t>(n_genes, 1) * sizeof(int));
     if (rc == JACKS_OK) rc = p->b->d_counters.reserve(kCounterInts * sizeof(int));
     if (rc == JACKS_OK && p->fast_maxG > 0)
@@ -388,6 +446,7 @@ int jacks_em_plan_create(JacksCtx* ctx, const int64_t* gene_offsets, const int32
     // generic kernel configurations (and global scratch if a gene's working set exceeds shared memory)
     memset(&p->cfg_generic, 0, sizeof p->cfg_generic);
     memset(&p->cfg_deferred, 0, sizeof p->cfg_deferred);
+    memset(&p->cfg_deferred_small, 0, sizeof p->cfg_deferred_small);
     long long scratch_doubles = (long long)p->big_grid * p->big_slab;
     if (rc == JACKS_OK && p->generic.n > 0) {
         e = em_generic_configure(p->generic_maxG, n_lines, p->generic.n, ctx->n_sm, &p->cfg_generic);
@@ -398,13 +457,18 @@ int jacks_em_plan_create(JacksCtx* ctx, const int64_t* gene_offsets, const int32
         e = em_generic_configure(p->fast_maxG, n_lines, p->n_fast_genes, ctx->n_sm, &p->cfg_deferred);
         if (e != cudaSuccess) rc = cuda_fail(e, "em_generic_configure");
         else scratch_doubles = std::max(scratch_doubles, p->cfg_deferred.scratch_doubles_per_warp * p->cfg_deferred.grid * p->cfg_deferred.warps_per_cta);
+        // beside a resident fast kernel an SM has ~100 KB of shared memory to spare (two TMEM-variant CTAs leave 54 KB, one 140 KB)
+        if (rc == JACKS_OK && (e = em_generic_configure(p->fast_maxG, n_lines, p->n_fast_genes, ctx->n_sm, &p->cfg_deferred_small, 100 * 1024)) != cudaSuccess) rc = cuda_fail(e, "em_generic_configure");
+        else scratch_doubles = std::max(scratch_doubles, p->cfg_deferred_small.scratch_doubles_per_warp * p->cfg_deferred_small.grid * p->cfg_deferred_small.warps_per_cta);
     }
     if (rc == JACKS_OK && scratch_doubles > 0) rc = p->b->d_scratch.reserve((size_t)scratch_doubles * sizeof(double));
+    trace_stamp("    plan: pulls enqueued");
     if (rc == JACKS_OK) {
-        // host vectors go out of scope.  The index goes up on a stream of its own: waiting for it must not wait for
-        // kernels of an earlier asynchronous call (the pseudo-gene EM of a screen job) on the compute stream.
-        e = cudaStreamSynchronize(ctx->plan_stream);
-        if (e != cudaSuccess) rc = cuda_fail(e, "cudaStreamSynchronize(plan)");
+        // The index arrives on a stream of its own and the plan's consumers wait for it ON THE DEVICE (em_plan_wait): the
+        // host does not (the staging belongs to the plan's buffers and lives until they are recycled), and neither do
+        // kernels of an earlier asynchronous call on the compute stream.
+        if (!p->b->ready && (e = cudaEventCreateWithFlags(&p->b->ready, cudaEventDisableTiming)) != cudaSuccess) rc = cuda_fail(e, "cudaEventCreate");
+        else if ((e = cudaEventRecord(p->b->ready, ctx->plan_stream)) != cudaSuccess) rc = cuda_fail(e, "cudaEventRecord");
     }
     if (rc != JACKS_OK) { jacks_em_plan_destroy(p); return rc; }
     *out = p;
@@ -422,8 +486,9 @@ void jacks_em_plan_destroy(JacksEmPlan* p) {
 // Enqueue the EM of the genes with id in [g0, g1) (caller order) on `st`.  `range` selects the counter block;
 // the caller zeroes d_counters before the first range of a run.
 int em_run_range(JacksCtx* ctx, const JacksEmPlan* plan, const JacksEmParams* params, const JacksEmDeviceIO* io,
-                        cudaStream_t st, int64_t g0, int64_t g1, int range) {
+                        cudaStream_t st, int64_t g0, int64_t g1, int range, int grid_limit, bool beside) {
     cudaError_t e;
+    if (plan->b->ready && (e = cudaStreamWaitEvent(st, plan->b->ready, 0)) != cudaSuccess) return cuda_fail(e, "cudaStreamWaitEvent(plan)");
     int* counters = (int*)plan->b->d_counters.p + range * kCountersPerRange;
     EmLaunch a;
     memset(&a, 0, sizeof a);
@@ -457,7 +522,7 @@ int em_run_range(JacksCtx* ctx, const JacksEmPlan* plan, const JacksEmParams* pa
         a.n_work = s1 - s0; a.n_work_dev = nullptr;
         a.work_counter = counters + slot++;
         int grid = 0;
-        e = launch_em_fast(b.G, b.W, a, ctx->n_sm, 0, st, &grid);
+        e = launch_em_fast(b.G, b.W, a, ctx->n_sm, grid_limit, st, &grid);
         if (e != cudaSuccess) return cuda_fail(e, "em_fast_kernel launch");
         ctx->launches++;
         n_fast += s1 - s0;
@@ -492,8 +557,9 @@ int em_run_range(JacksCtx* ctx, const JacksEmPlan* plan, const JacksEmParams* pa
         a.gene_ids = (const int*)plan->b->d_deferred.p + g0;
         a.n_work = n_fast; a.n_work_dev = counters;
         a.work_counter = counters + slot++;
-        a.scratch_stride = plan->cfg_deferred.scratch_doubles_per_warp;
-        e = launch_em_generic(plan->cfg_deferred, a, st);
+        const EmGenericConfig& dcfg = beside ? plan->cfg_deferred_small : plan->cfg_deferred;
+        a.scratch_stride = dcfg.scratch_doubles_per_warp;
+        e = launch_em_generic(dcfg, a, st);
         if (e != cudaSuccess) return cuda_fail(e, "em_generic_kernel (deferred) launch");
         ctx->launches++;
     }
@@ -534,8 +600,28 @@ struct CompactCubes {
     cudaEvent_t ready;
 };
 
+// JACKS_TRACE: device-side timeline of a screen job (timing events recorded on the streams, printed after the synchronise)
+struct TraceMarks {
+    std::vector<std::pair<std::string, cudaEvent_t>> marks;
+    cudaEvent_t t0 = nullptr;
+    void start(cudaStream_t st) { cudaEventCreate(&t0); cudaEventRecord(t0, st); }
+    void mark(const std::string& what, cudaStream_t st) {
+        cudaEvent_t ev; cudaEventCreate(&ev); cudaEventRecord(ev, st); marks.emplace_back(what, ev);
+    }
+    void print() {
+        for (auto& m : marks) {
+            float ms = 0.f;
+            if (cudaEventElapsedTime(&ms, t0, m.second) == cudaSuccess) fprintf(stderr, "[jacks trace]   device %-22s %8.3f ms\n", m.first.c_str(), ms);
+            cudaEventDestroy(m.second);
+        }
+        if (t0) cudaEventDestroy(t0);
+        marks.clear(); t0 = nullptr;
+    }
+};
+
 // What the pipelined host run does besides the plain inferJACKS call.
 struct HostRunOpts {
+    TraceMarks* trace = nullptr;
     int32_t flags = 0;                    // JACKS_KEEP_RESIDENT | JACKS_ASYNC
     const CompactCubes* cc = nullptr;     // run on compact cubes (already enqueued for upload) instead of the resident screen
     bool w1_stays = false;                // E[w] is produced on the device even when io->w1 is NULL (nothing is downloaded for it)
@@ -543,6 +629,12 @@ struct HostRunOpts {
     double* pvals_host = nullptr;         // ... downloaded here, [n_genes, L]
     JacksEmPlan** plan_out = nullptr;     // the (pending) plan: its device outputs stay valid until the next synchronise
     const struct PreUpload* pre = nullptr; // the screen is already on its way up (enqueue_screen_upload): ranges + events
+    cudaStream_t em_stream = nullptr;     // the EM kernels of the ranges run here instead of the compute stream (the p-values
+                                          // stay on the compute stream, behind whatever produces the null there)
+    int grid_limit = 0;                   // em_run_range's grid limit (< 0: leave a share of the SM slots to a parallel run)
+    int ranges = 0;                       // > 0: this many gene ranges instead of host_run_ranges() (1: one launch per bucket --
+                                          // a run that neither waits for an upload nor downloads anything gains nothing from ranges
+                                          // and pays a kernel tail for each)
 };
 
 // Gene ranges of the pipelined host run: contiguous blocks; with p-values on, boundaries sit on multiples of 1,024 genes.
@@ -562,6 +654,7 @@ static int64_t host_run_bound(int64_t n_genes, int R, int r, bool kde) {
 // Upload of a screen enqueued AHEAD of everything else of a screen job (pinned host cubes only: the copies are
 // asynchronous): ev_in[r] fires when the rows of gene range r are on the device.
 struct PreUpload {
+    TraceMarks* trace = nullptr;
     int R = 0;
     std::vector<cudaEvent_t> ev_in;
 };
@@ -597,6 +690,7 @@ static int enqueue_screen_upload(JacksCtx* ctx, const JacksEmHostIO* io, const i
         }
         if ((e = cudaEventCreateWithFlags(&pre->ev_in[r], cudaEventDisableTiming)) != cudaSuccess) return cuda_fail(e, "cudaEventCreate");
         cudaEventRecord(pre->ev_in[r], s_in);
+        if (pre->trace && (r == 0 || r == R - 1 || r == R / 2)) pre->trace->mark("upload range " + std::to_string(r), s_in);
         ctx->pending_events.push_back(pre->ev_in[r]);
     }
     return JACKS_OK;
@@ -641,6 +735,7 @@ static int em_batched_host_compact(JacksCtx* ctx, const JacksEmParams* params, c
     const int64_t U = (int64_t)used.size();
     std::vector<int32_t> rows2((size_t)T);
     for (int64_t i = 0; i < T; ++i) rows2[(size_t)i] = remap[(size_t)guide_rows[i]];
+    trace_stamp("  compact: rows re-based");
     const size_t row_t = (size_t)L * 2 * sizeof(double), row_c = (size_t)io->ctrl_lines * 2 * sizeof(double);
     const bool fx = io->fixed_x1 && io->fixed_x2;
     const size_t bytes = (size_t)U * (row_t + row_c + (fx ? 2 * sizeof(double) : 0));
@@ -659,22 +754,24 @@ static int em_batched_host_compact(JacksCtx* ctx, const JacksEmParams* params, c
     char* st_test = (char*)ctx->cmp_stage;
     char* st_ctrl = st_test + (size_t)U * row_t;
     double* st_fx = (double*)(st_ctrl + (size_t)U * row_c);
-    cudaStream_t s_in = ctx->copy_stream;
+    const bool zero_copy = U > 0 && host_pointer_is_pinned(io->test) && host_pointer_is_pinned(io->ctrl);
+    // pinned cubes: the GPU pulls the rows itself on a stream of its own (nothing of this touches the copy engine, whose
+    // queue may hold a screen-sized upload); pageable cubes: host gather into the staging, one copy on the copy stream
+    cudaStream_t s_in = zero_copy ? ctx->cmp_stream : ctx->copy_stream;
     // the device cube is reused from call to call too: the kernels of the previous compact run (compute stream) may
     // still be reading it, so the refill below is ordered behind them
     if (ctx->cmp_done) cudaStreamWaitEvent(s_in, ctx->cmp_done, 0);
-    const bool zero_copy = U > 0 && host_pointer_is_pinned(io->test) && host_pointer_is_pinned(io->ctrl);
     if (zero_copy) {
-        // the list of rows and the (small) fixed-x gather go through the staging buffer; the cubes are pulled by the GPU
+        // the list of rows stays in the pinned staging (the gather kernel reads it from there) and the (small) fixed-x
+        // gather goes through it too
         long long* st_used = (long long*)ctx->cmp_stage;            // staging is at least U*(row_t+row_c) >= 32*U bytes
         for (int64_t u = 0; u < U; ++u) st_used[u] = used[(size_t)u];
-        if ((rc = ctx->cmp_rows.reserve((size_t)U * sizeof(long long))) != JACKS_OK) return rc;
-        if ((e = cudaMemcpyAsync(ctx->cmp_rows.p, st_used, (size_t)U * sizeof(long long), cudaMemcpyHostToDevice, s_in)) != cudaSuccess) return cuda_fail(e, "H2D used rows");
-        void* dt = nullptr; void* dc = nullptr;
+        void* dt = nullptr; void* dc = nullptr; void* du = nullptr;
         if ((e = cudaHostGetDevicePointer(&dt, (void*)io->test, 0)) != cudaSuccess) return cuda_fail(e, "cudaHostGetDevicePointer");
         if ((e = cudaHostGetDevicePointer(&dc, (void*)io->ctrl, 0)) != cudaSuccess) return cuda_fail(e, "cudaHostGetDevicePointer");
+        if ((e = cudaHostGetDevicePointer(&du, ctx->cmp_stage, 0)) != cudaSuccess) return cuda_fail(e, "cudaHostGetDevicePointer");
         char* dev = (char*)ctx->cmp_dev.p;
-        gather_rows_kernel<<<dim3((unsigned)U, 2), 128, 0, s_in>>>((const double2*)dt, (const double2*)dc, (const long long*)ctx->cmp_rows.p,
+        gather_rows_kernel<<<dim3((unsigned)U, 2), 128, 0, s_in>>>((const double2*)dt, (const double2*)dc, (const long long*)du,
                                                                    (long long)L, (long long)io->ctrl_lines, (double2*)dev,
                                                                    (double2*)(dev + (size_t)U * row_t));
         if ((e = cudaGetLastError()) != cudaSuccess) return cuda_fail(e, "gather_rows_kernel launch");
@@ -708,6 +805,7 @@ static int em_batched_host_compact(JacksCtx* ctx, const JacksEmParams* params, c
         if (bytes && (e = cudaMemcpyAsync(ctx->cmp_dev.p, ctx->cmp_stage, bytes, cudaMemcpyHostToDevice, s_in)) != cudaSuccess) return cuda_fail(e, "H2D compact cube");
     }
     cudaEventRecord(ctx->cmp_ready, s_in);
+    trace_stamp("  compact: gather enqueued");
     CompactCubes cc;
     cc.d_test = (const double*)ctx->cmp_dev.p;
     cc.d_ctrl = (const double*)((const char*)ctx->cmp_dev.p + (size_t)U * row_t);
@@ -758,6 +856,8 @@ static int em_batched_host_core(JacksCtx* ctx, const JacksEmParams* params, cons
     cudaError_t e = cudaSetDevice(ctx->device);
     if (e != cudaSuccess) return cuda_fail(e, "cudaSetDevice");
     cudaStream_t s_k = ctx->stream, s_in = ctx->copy_stream, s_out = ctx->out_stream;
+    cudaStream_t s_em = opt.em_stream ? opt.em_stream : s_k;      // EM kernels; s_k keeps the p-values
+    const bool split = s_em != s_k;
     int rc;
 
     // ---- inputs: upload, or reuse the cubes a previous call left resident -------------------------
@@ -779,14 +879,15 @@ static int em_batched_host_core(JacksCtx* ctx, const JacksEmParams* params, cons
         if (!io->fixed_x1 || !io->fixed_x2) return fail(JACKS_E_INVALID, "fixed_x1 and fixed_x2 go together");
         if ((rc = ctx->res_fx.reserve((size_t)N * 2 * sizeof(double) + 8)) != JACKS_OK) return rc;
         if (N) {
-            if ((e = cudaMemcpyAsync(ctx->res_fx.p, io->fixed_x1, (size_t)N * sizeof(double), cudaMemcpyHostToDevice, s_k)) != cudaSuccess) return cuda_fail(e, "H2D fixed_x1");
-            if ((e = cudaMemcpyAsync((double*)ctx->res_fx.p + N, io->fixed_x2, (size_t)N * sizeof(double), cudaMemcpyHostToDevice, s_k)) != cudaSuccess) return cuda_fail(e, "H2D fixed_x2");
+            if ((e = cudaMemcpyAsync(ctx->res_fx.p, io->fixed_x1, (size_t)N * sizeof(double), cudaMemcpyHostToDevice, s_em)) != cudaSuccess) return cuda_fail(e, "H2D fixed_x1");
+            if ((e = cudaMemcpyAsync((double*)ctx->res_fx.p + N, io->fixed_x2, (size_t)N * sizeof(double), cudaMemcpyHostToDevice, s_em)) != cudaSuccess) return cuda_fail(e, "H2D fixed_x2");
         }
         d_fx1 = (const double*)ctx->res_fx.p; d_fx2 = d_fx1 + N;
     }
 
     JacksEmPlan* plan = nullptr;
     if ((rc = jacks_em_plan_create(ctx, gene_offsets, guide_rows, n_genes, N, L, &plan)) != JACKS_OK) return rc;
+    trace_stamp("  core: plan created");
     const int64_t T = plan->total_guides;
 
     // ---- outputs ------------------------------------------------------------------------------------
@@ -815,25 +916,28 @@ static int em_batched_host_core(JacksCtx* ctx, const JacksEmParams* params, cons
     dio.x1 = (double*)dptr[0]; dio.x2 = (double*)dptr[1]; dio.w1 = (double*)dptr[2]; dio.w2 = (double*)dptr[3];
     dio.y = (double*)dptr[4]; dio.tau = (double*)dptr[5]; dio.n_iters = (int32_t*)dptr[6]; dio.bound = (double*)dptr[7];
     rc = (n_genes > 0) ? em_check_io(plan, params, &dio) : JACKS_OK;
-    if (cc) cudaStreamWaitEvent(s_k, cc->ready, 0);          // the compact cubes are on their way on the copy stream
+    if (cc) cudaStreamWaitEvent(s_em, cc->ready, 0);         // the compact cubes are on their way (copy or gather stream)
 
     // ---- pipeline: gene ranges flow through upload -> kernels -> download on three streams ------------
     // Ranges are contiguous gene blocks.  When the guide rows ascend along the index (a real screen: genes own
     // consecutive rows) each range uploads just the rows up to its last one, so the first kernels start after
     // 1/R of the upload; otherwise (pseudo-genes, arbitrary gathers) everything is uploaded before the kernels.
-    const int R = opt.pre ? opt.pre->R : host_run_ranges(n_genes);
+    const int R = opt.pre ? opt.pre->R : (opt.ranges > 0 ? std::min(opt.ranges, kMaxRanges) : host_run_ranges(n_genes));
     // range r covers genes [gb(r), gb(r+1))
     auto gb = [&](int r) -> int64_t { return host_run_bound(n_genes, R, r, opt.kde != nullptr); };
     bool ascending = upload;
     if (upload && R > 1) {
         for (int64_t i = 1; i < T && ascending; ++i) ascending = guide_rows[i] >= guide_rows[i - 1];
     }
-    std::vector<cudaEvent_t> ev_in(R, nullptr), ev_k(R, nullptr);
+    // ev_in[r]: rows of range r are up; ev_em[r]: its EM has run (only when the EM has a stream of its own); ev_k[r]: all
+    // its kernels have run (EM and p-values)
+    std::vector<cudaEvent_t> ev_in(R, nullptr), ev_k(R, nullptr), ev_em(R, nullptr);
     for (int r = 0; r < R && rc == JACKS_OK; ++r) {
         if ((e = cudaEventCreateWithFlags(&ev_in[r], cudaEventDisableTiming)) != cudaSuccess) rc = cuda_fail(e, "cudaEventCreate");
         else if ((e = cudaEventCreateWithFlags(&ev_k[r], cudaEventDisableTiming)) != cudaSuccess) rc = cuda_fail(e, "cudaEventCreate");
+        else if (split && (e = cudaEventCreateWithFlags(&ev_em[r], cudaEventDisableTiming)) != cudaSuccess) rc = cuda_fail(e, "cudaEventCreate");
     }
-    if (rc == JACKS_OK && (e = cudaMemsetAsync(plan->b->d_counters.p, 0, kCounterInts * sizeof(int), s_k)) != cudaSuccess) rc = cuda_fail(e, "cudaMemsetAsync");
+    if (rc == JACKS_OK && (e = cudaMemsetAsync(plan->b->d_counters.p, 0, kCounterInts * sizeof(int), s_em)) != cudaSuccess) rc = cuda_fail(e, "cudaMemsetAsync");
     cudaEvent_t ev_start = nullptr;
     if (rc == JACKS_OK && upload) {
         // the upload overwrites the resident cubes: it waits for the kernels of earlier calls that READ them -- and for
@@ -841,7 +945,6 @@ static int em_batched_host_core(JacksCtx* ctx, const JacksEmParams* params, cons
         // cube, run while the screen goes up)
         if (ctx->res_busy) cudaStreamWaitEvent(s_in, ctx->res_busy, 0);
     }
-    const bool staged_out = !(keep_resident & JACKS_ASYNC);
     int64_t row_done = 0;        // rows [0, row_done) are already enqueued for upload
     for (int r = 0; r < R && rc == JACKS_OK; ++r) {
         const int64_t g0 = gb(r), g1 = gb(r + 1);
@@ -858,39 +961,50 @@ static int em_batched_host_core(JacksCtx* ctx, const JacksEmParams* params, cons
                 row_done = row_hi;
             }
             cudaEventRecord(ev_in[r], s_in);
-            cudaStreamWaitEvent(s_k, ev_in[r], 0);
+            cudaStreamWaitEvent(s_em, ev_in[r], 0);
         } else if (opt.pre) {
-            cudaStreamWaitEvent(s_k, opt.pre->ev_in[r], 0);
+            cudaStreamWaitEvent(s_em, opt.pre->ev_in[r], 0);
         }
-        if (g1 > g0) rc = em_run_range(ctx, plan, params, &dio, s_k, g0, g1, r);
+        if (g1 > g0) rc = em_run_range(ctx, plan, params, &dio, s_em, g0, g1, r, opt.grid_limit, split);
+        if (opt.trace && (r == 0 || r == R - 1 || r == R / 2)) opt.trace->mark((cc ? "pseudo EM range " : "real EM range ") + std::to_string(r), s_em);
+        if (rc == JACKS_OK && split) {
+            cudaEventRecord(ev_em[r], s_em);
+            cudaStreamWaitEvent(s_k, ev_em[r], 0);
+        }
         if (rc == JACKS_OK && opt.kde && g1 > g0 && dptr[8])
             rc = jacks::kde_eval(ctx, *opt.kde, (const double*)dptr[2] + g0 * L, g1 - g0, (double*)dptr[8] + g0 * L, s_k);
         if (rc != JACKS_OK) break;
         cudaEventRecord(ev_k[r], s_k);
-        if (staged_out) continue;          // downloads follow below, once every range is enqueued
-        cudaStreamWaitEvent(s_out, ev_k[r], 0);
-        const int64_t t0 = gene_offsets[g0], t1 = gene_offsets[g1];
-        for (int i = 0; i < NO && rc == JACKS_OK; ++i) {
-            if (!outs[i].host) continue;
-            if (!dptr[i]) continue;
-            const size_t lo = outs[i].unit * (size_t)(outs[i].per_guide ? t0 : g0), hi = outs[i].unit * (size_t)(outs[i].per_guide ? t1 : g1);
-            if (hi > lo && (e = cudaMemcpyAsync(outs[i].host + lo, dptr[i] + lo, hi - lo, cudaMemcpyDeviceToHost, s_out)) != cudaSuccess) rc = cuda_fail(e, "D2H result");
-        }
+        if (opt.trace && opt.kde && (r == 0 || r == R - 1)) opt.trace->mark("p-values range " + std::to_string(r), s_k);
     }
-    if (staged_out) {
-        // Synchronous call: the host thread drains range r (through the pinned ring when the caller's arrays are
-        // pageable) while the kernels of the later ranges run.
+    // ---- downloads: everything but the p-values as soon as a range's EM has run, the p-values in a second sweep (with
+    // the EM on its own stream they come much later: one in-order download stream must not park the other outputs
+    // behind them).  Synchronous call: the host thread drains range r (through the pinned ring when the caller's arrays
+    // are pageable) while the kernels of the later ranges run.
+    const bool staged_out = !(keep_resident & JACKS_ASYNC);
+    bool any_out[2] = {false, false};     // is there anything to download in sweep 0 / sweep 1?  (if not, the download stream
+    for (int i = 0; i < NO; ++i)          //  must not be made to wait for this run's kernels)
+        if (dptr[i] && outs[i].host) any_out[(split && i == 8) ? 1 : 0] = true;
+    for (int sweep = 0; sweep < (split ? 2 : 1) && rc == JACKS_OK; ++sweep) {
+        if (!any_out[sweep]) continue;
+        cudaStream_t s_out = (sweep == 1) ? ctx->out2_stream : ctx->out_stream;      // the late p-values travel on a stream of their own
         for (int r = 0; r < R && rc == JACKS_OK; ++r) {
             const int64_t g0 = gb(r), g1 = gb(r + 1);
             const int64_t t0 = gene_offsets[g0], t1 = gene_offsets[g1];
-            cudaStreamWaitEvent(s_out, ev_k[r], 0);
+            cudaStreamWaitEvent(s_out, (split && sweep == 0) ? ev_em[r] : ev_k[r], 0);
             for (int i = 0; i < NO && rc == JACKS_OK; ++i) {
                 if (!dptr[i] || !outs[i].host) continue;
+                if (split && (sweep == 0) == (i == 8)) continue;          // sweep 0: all but the p-values; sweep 1: the p-values
                 const size_t lo = outs[i].unit * (size_t)(outs[i].per_guide ? t0 : g0), hi = outs[i].unit * (size_t)(outs[i].per_guide ? t1 : g1);
-                if (hi > lo) rc = ctx->stager.d2h(outs[i].host + lo, dptr[i] + lo, hi - lo, s_out);
+                if (hi <= lo) continue;
+                if (staged_out) rc = ctx->stager.d2h(outs[i].host + lo, dptr[i] + lo, hi - lo, s_out);
+                else if ((e = cudaMemcpyAsync(outs[i].host + lo, dptr[i] + lo, hi - lo, cudaMemcpyDeviceToHost, s_out)) != cudaSuccess) rc = cuda_fail(e, "D2H result");
             }
         }
+        if (opt.trace) opt.trace->mark(std::string(cc ? "pseudo" : "real") + " downloads sweep " + std::to_string(sweep), s_out);
     }
+    if (split && R > 0 && ev_em[R - 1]) cudaStreamWaitEvent(s_k, ev_em[R - 1], 0);      // res_busy below covers the EM stream
+    for (int r = 0; r < R; ++r) if (ev_em[r]) ctx->pending_events.push_back(ev_em[r]);
     for (int r = 0; r < R; ++r) { if (ev_in[r]) ctx->pending_events.push_back(ev_in[r]); if (ev_k[r]) ctx->pending_events.push_back(ev_k[r]); }
     if (ev_start) ctx->pending_events.push_back(ev_start);
     if (!cc) {                    // the last kernel of this call that reads the resident cubes
@@ -979,13 +1093,19 @@ extern "C" int jacks_run_screen_host(JacksCtx* ctx, const JacksEmParams* params,
     jacks::KdeNull nl;
     JacksEmPlan* pplan = nullptr;
     PreUpload pre;
-    static const int upload_first_env = []() { const char* v = getenv("JACKS_SCREEN_UPLOAD_FIRST"); return v ? atoi(v) : 0; }();
+    // Tuning / A-B knobs.  Defaults: the screen starts going up before anything else; the real genes' EM runs on the side
+    // stream BESIDE the pseudo-gene EM, which leaves it 13.5 % of the SM slots (the real genes are 15 % of the EM work and
+    // arrive over the whole upload; run behind the pseudo-genes, their 16 small launches cost 3 ms after the upload's end).
+    static const int upload_first_env = []() { const char* v = getenv("JACKS_SCREEN_UPLOAD_FIRST"); return v ? atoi(v) : 1; }();
+    static const int split_env = []() { const char* v = getenv("JACKS_SCREEN_SPLIT"); return v ? atoi(v) : 1; }();
+    static const int reserve_env = []() { const char* v = getenv("JACKS_SCREEN_RESERVE"); return v ? atoi(v) : 135; }();
     static const bool trace = getenv("JACKS_TRACE") != nullptr;
-    const auto t_start = std::chrono::steady_clock::now();
-    auto stamp = [&](const char* what) {
-        if (trace) fprintf(stderr, "[jacks trace] %-28s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_start).count());
-    };
+    g_trace_t0 = std::chrono::steady_clock::now();
+    g_trace_on = trace;
+    auto stamp = [&](const char* what) { trace_stamp(what); };
     const bool upload_first = upload_first_env && n_pseudo > 0 && host_pointer_is_pinned(rio.test) && host_pointer_is_pinned(rio.ctrl);
+    TraceMarks tm;
+    if (trace) { tm.start(ctx->stream); pre.trace = &tm; }
     if (upload_first) {
         // 0. pinned cubes: the screen starts going up (copy stream, range by range) before any host-side preparation of
         //    the pseudo-gene run; the control rows the pseudo-genes need are pulled by a kernel, not by the copy engine
@@ -1003,8 +1123,12 @@ extern "C" int jacks_run_screen_host(JacksCtx* ctx, const JacksEmParams* params,
         popt.flags = JACKS_ASYNC;
         popt.w1_stays = true;
         popt.plan_out = &pplan;
+        if (trace) popt.trace = &tm;
+        if (split_env && n_genes > 0 && reserve_env > 0 && reserve_env < 900) popt.grid_limit = -reserve_env;
+        if (!io->pseudo_w1 && !io->pseudo_w2 && !io->pseudo_n_iters) popt.ranges = 1;     // nothing comes down: one launch
         if ((rc = em_batched_host_compact(ctx, params, pseudo_offsets, pseudo_rows, n_pseudo, &pio, popt)) != JACKS_OK) { jacks_ctx_synchronize(ctx); return rc; }
         stamp("pseudo-gene EM enqueued");
+        if (trace) { tm.mark("compact cube gathered", ctx->cmp_stream); tm.mark("pseudo EM done", ctx->stream); }
         // 2. null densities from the pseudo-gene E[w], still on the device
         if (want_p && (rc = jacks::kde_null_prepare(ctx, (const double*)pplan->b->out[2].p, n_pseudo, L, io->positive, ctx->stream, &nl)) != JACKS_OK) { jacks_ctx_synchronize(ctx); return rc; }
         if (io->pseudo_pvals) {
@@ -1025,6 +1149,8 @@ extern "C" int jacks_run_screen_host(JacksCtx* ctx, const JacksEmParams* params,
     HostRunOpts ropt;
     ropt.flags = flags;
     if (upload_first) ropt.pre = &pre;
+    if (trace) { ropt.trace = &tm; tm.mark("null densities done", ctx->stream); }
+    if (split_env && n_pseudo > 0) ropt.em_stream = ctx->side_stream;
     if (io->pvals) { ropt.kde = &nl; ropt.pvals_host = io->pvals; }
     stamp("null densities enqueued");
     rc = em_batched_host_core(ctx, params, gene_offsets, guide_rows, n_genes, &rio, ropt);
@@ -1034,6 +1160,7 @@ extern "C" int jacks_run_screen_host(JacksCtx* ctx, const JacksEmParams* params,
         if (rc == JACKS_OK) rc = rs;
     }
     stamp("synchronised");
+    if (trace && !(flags & JACKS_ASYNC)) tm.print();
     return rc;
 }
 
@@ -1051,6 +1178,7 @@ static int em_lines_run(JacksCtx* ctx, const JacksEmPlan* plan, const JacksEmPar
     // the deferred queue holds (gene, line) pairs here: one slot per problem of the fast buckets
     if ((rc = plan->b->d_deferred.reserve((size_t)std::max<int64_t>(plan->n_genes * L, 1) * sizeof(int))) != JACKS_OK) return rc;
     if ((e = cudaMemsetAsync(plan->b->d_counters.p, 0, kCountersPerRange * sizeof(int), st)) != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync");
+    if (plan->b->ready && (e = cudaStreamWaitEvent(st, plan->b->ready, 0)) != cudaSuccess) return cuda_fail(e, "cudaStreamWaitEvent(plan)");
     int* counters = (int*)plan->b->d_counters.p;
     EmLaunch a;
     memset(&a, 0, sizeof a);
@@ -1161,6 +1289,7 @@ int jacks_em_lines_host(JacksCtx* ctx, const JacksEmParams* params, const int64_
     if (!io->w1 && n_genes) return fail(JACKS_E_INVALID, "w1 is required");
     JacksEmPlan* plan = nullptr;
     if ((rc = jacks_em_plan_create(ctx, gene_offsets, guide_rows, n_genes, N, L, &plan)) != JACKS_OK) return rc;
+    trace_stamp("  core: plan created");
     const int64_t T = plan->total_guides;
     // every output has L entries per gene or per guide
     struct Out { char* host; size_t unit; bool per_guide; } outs[8] = {

@@ -29,7 +29,15 @@ struct PlanBufs {
     jacks::DevBuf d_offsets, d_rows, d_ids, d_slot_off, d_slot_rows, d_deferred, d_counters, d_scratch, d_tpd;
     jacks::DevBuf out[9];                   // device-side outputs of a host call that used this plan ([8]: p-values)
     long long sig_genes = -1, sig_guides = -1;   // shape of the last plan served (pool lookups prefer a match)
+    // pinned staging of the index arrays: the GPU pulls them itself (copy kernel on the plan stream), so an index never
+    // queues behind a screen-sized upload in the copy engine
+    void* h_stage = nullptr; size_t h_cap = 0;
+    cudaEvent_t ready = nullptr;          // the index arrays of the plan now served are on the device (plan stream)
     void release() {
+        if (h_stage) cudaFreeHost(h_stage);
+        h_stage = nullptr; h_cap = 0;
+        if (ready) cudaEventDestroy(ready);
+        ready = nullptr;
         for (auto& o : out) o.release();
         d_offsets.release(); d_rows.release(); d_ids.release(); d_slot_off.release(); d_slot_rows.release();
         d_deferred.release(); d_counters.release(); d_scratch.release(); d_tpd.release();
@@ -62,7 +70,10 @@ struct JacksCtx {
     cudaStream_t stream;        // compute + default copies of the host entry points
     cudaStream_t copy_stream;   // host -> device copies of the pipelined host entry points
     cudaStream_t out_stream;    // device -> host copies of the pipelined host entry points
+    cudaStream_t out2_stream = nullptr;   // second download stream: the p-values of a screen job (they become ready long after
+                                          // the other outputs of their range and must not hold those up in an in-order stream)
     cudaStream_t plan_stream = nullptr;   // uploads of gene indexes (jacks_em_plan_create)
+    cudaStream_t cmp_stream = nullptr;    // row gathers of the compact cubes (kernels reading pinned host memory)
     cudaStream_t side_stream = nullptr;   // second kernel stream of jacks_run_screen_device: the pseudo-gene EM runs beside the
     cudaEvent_t side_fork = nullptr;      // real-gene EM, so that its CTAs fill the SMs the other kernel's tail leaves idle
     cudaEvent_t side_join = nullptr;
@@ -123,12 +134,16 @@ struct JacksEmPlan {
     int fast_maxG;
     int n_fast_genes;
     jacks::EmGenericConfig cfg_generic, cfg_deferred;
+    jacks::EmGenericConfig cfg_deferred_small;   // the deferred queue's kernel with CTAs small enough to run BESIDE a resident fast kernel
 };
 
 // Enqueue the EM of the genes with id in [g0, g1) (caller order) on `st`.  `range` selects the counter block
 // (0 .. kMaxRanges-1); the caller zeroes d_counters before the first range of a run.
+// grid_limit: 0 none; > 0 at most that many CTAs; < 0 leave |grid_limit| thousandths of the resident CTA slots free.
+// beside: another (persistent) EM launch is resident while this one runs: the deferred queue's kernel takes its small
+// configuration, or its CTAs would wait for a whole SM and stall the stream.
 int em_run_range(JacksCtx* ctx, const JacksEmPlan* plan, const JacksEmParams* params, const JacksEmDeviceIO* io,
-                 cudaStream_t st, int64_t g0, int64_t g1, int range);
+                 cudaStream_t st, int64_t g0, int64_t g1, int range, int grid_limit = 0, bool beside = false);
 int em_check_io(const JacksEmPlan* plan, const JacksEmParams* params, const JacksEmDeviceIO* io);
 bool host_pointer_is_pinned(const void* p);
 

@@ -89,7 +89,8 @@ __host__ __device__ long long em_generic_work_doubles(int G, int L);
 // Genes at least this big (guides x lines) run one per CTA (em_big_kernel) instead of one per warp.
 constexpr long long kBigGeneElements = 4096;
 cudaError_t launch_em_big(const EmLaunch& a, int grid, long long slab_doubles, cudaStream_t st);
-cudaError_t em_generic_configure(int maxG, int L, long long n_work_cap, int n_sm, EmGenericConfig* cfg);
+// max_smem: shared-memory budget of a CTA (a smaller one lets the kernel's CTAs move in beside a resident fast kernel).
+cudaError_t em_generic_configure(int maxG, int L, long long n_work_cap, int n_sm, EmGenericConfig* cfg, size_t max_smem = 226 * 1024);
 cudaError_t launch_em_generic(const EmGenericConfig& cfg, const EmLaunch& a, cudaStream_t st);
 
 }  // namespace jacks

@@ -35,6 +35,8 @@ cudaError_t launch_tmem(const EmLaunch& a0, int n_sm, int grid_limit, cudaStream
     occ = std::min(occ, 512 / a.tmem_cols);
     occ = std::min(occ, kMaxFastCtasPerSm / kTmemTeams);        // tau_pr_den slabs are provisioned per team
     long long grid = (long long)occ * n_sm;
+    // grid_limit < 0: leave |grid_limit| thousandths of the resident CTA slots to a kernel that runs beside this one
+    if (grid_limit < 0) grid = std::max<long long>(1, grid * (1000 + grid_limit) / 1000);
     const long long want = ((long long)a.n_work + kTmemTeams - 1) / kTmemTeams;
     if (grid > want) grid = want;
     if (grid_limit > 0 && grid > grid_limit) grid = grid_limit;
@@ -96,6 +98,7 @@ cudaError_t launch_inst(const EmLaunch& a, int n_sm, int grid_limit, cudaStream_
     if (occ < 1) return cudaErrorLaunchOutOfResources;
     if (occ > kMaxFastCtasPerSm) occ = kMaxFastCtasPerSm;     // tau_pr_den slabs are provisioned for this many
     long long grid = (long long)occ * n_sm;
+    if (grid_limit < 0) grid = std::max<long long>(1, grid * (1000 + grid_limit) / 1000);
     if (grid > a.n_work) grid = a.n_work;
     if (grid_limit > 0 && grid > grid_limit) grid = grid_limit;
     if (grid < 1) grid = 1;

@@ -588,11 +588,10 @@ cudaError_t launch_em_big(const EmLaunch& a, int grid, long long slab_doubles, c
     return cudaGetLastError();
 }
 
-cudaError_t em_generic_configure(int maxG, int L, long long n_work_cap, int n_sm, EmGenericConfig* cfg) {
+cudaError_t em_generic_configure(int maxG, int L, long long n_work_cap, int n_sm, EmGenericConfig* cfg, size_t max_smem) {
     // Shared-memory budget: as many warps per CTA (<= 8) as fit the largest gene; if not even one
     // fits, keep a slab per warp for the smaller genes of the batch and spill the big ones to the
     // global scratch.
-    const size_t max_smem = 226 * 1024;
     const long long need = em_generic_work_doubles(maxG, L);
     int wpc = 8;
     long long per_warp = need;
