@@ -597,6 +597,142 @@ __global__ void __launch_bounds__(256) rs_tie_find(const double* __restrict__ km
     if (e - h > kTieCta) ctl[0] = 1;
 }
 
+// The common case in one pass: a CTA takes a tile of kTieTile consecutive sorted elements into shared memory, finds the
+// runs of equal means with two block-wide scans (start of my run: max-scan of the head positions; end: reverse min-scan),
+// and every element of a run that lies INSIDE the tile counts its rank among the run's variance keys (shared-memory
+// reads) and moves straight to its place.  No thread walks a run serially -- screens whose counts tie by the thousand
+// (every element of the bench's Poisson(300) library sits in a run) cost ~30 shared-memory compares per element.
+// Runs that cross a tile border are left to their head: measured, then self-sorted or queued as in rs_tie_find; the
+// gate logic for over-long runs is the same.
+constexpr int kTieTile = 1024;          // 4 consecutive elements per thread
+__global__ void __launch_bounds__(256) rs_tie_tile(const double* __restrict__ km, double* __restrict__ kv, int* __restrict__ idx,
+                                                   long long ld, long long N, int* __restrict__ ctl,
+                                                   TieRun* __restrict__ warp_runs, TieRun* __restrict__ cta_runs,
+                                                   long long warp_cap, long long cta_cap) {
+    __shared__ unsigned long long s_key[kTieTile];
+    __shared__ double s_val[kTieTile];
+    __shared__ int s_idx[kTieTile];
+    __shared__ short s_hs[kTieTile], s_he[kTieTile];
+    __shared__ int s_wmax[8], s_wmin[8];
+    constexpr int NONE = -1, INF = 30000;
+    const long long o = (long long)blockIdx.y * ld;
+    const long long t0 = (long long)blockIdx.x * kTieTile;
+    if (t0 >= N) return;
+    const int n = (int)min((long long)kTieTile, N - t0);
+    const double* m = km + o + t0; double* v = kv + o + t0; int* ix = idx + o + t0;
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    const int j0 = 4 * t;
+    // heads: element j starts a run if it is the first of the segment or its mean differs from its predecessor's
+    unsigned long long mk[4], prev = 0;
+    bool head[4];
+    if (j0 < n) prev = (t0 + j0 > 0) ? sortable_key(m[j0 - 1]) : 0;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const int j = j0 + q;
+        mk[q] = (j < n) ? sortable_key(m[j]) : 0;
+        head[q] = (j < n) && ((t0 + j == 0) || mk[q] != (q ? mk[q - 1] : prev));
+    }
+    // does a run end exactly at the tile's end?  (position n acts as a head then)
+    const bool end_is_head = (t0 + n >= N) || sortable_key(m[n]) != sortable_key(m[n - 1]);
+    // start of my run: inclusive max-scan of (head ? j : NONE)
+    int hs[4], run = NONE;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) { if (head[q]) run = j0 + q; hs[q] = run; }
+    int inc = run;
+    for (int d = 1; d < 32; d <<= 1) { const int u = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc = max(inc, u); }
+    if (lane == 31) s_wmax[warp] = inc;
+    // end of my run: first head position AFTER j (reverse exclusive min-scan), INF if none inside the tile
+    int he[4], nxt = INF;
+#pragma unroll
+    for (int q = 3; q >= 0; --q) { he[q] = nxt; if (head[q]) nxt = j0 + q; }
+    if (j0 <= n - 1 && n - 1 < j0 + 4 && end_is_head) {
+        // the thread owning the last element: position n is a head for everything after the last head in my segment
+#pragma unroll
+        for (int q = 0; q < 4; ++q) if (j0 + q < n && he[q] == INF) he[q] = n;
+        if (nxt == INF) nxt = n;
+    }
+    int dec = nxt;
+    for (int d = 1; d < 32; d <<= 1) { const int u = __shfl_down_sync(0xffffffffu, dec, d); if (lane + d < 32) dec = min(dec, u); }
+    if (lane == 0) s_wmin[warp] = dec;
+    __syncthreads();
+    int before = NONE, after = INF;
+    for (int w2 = 0; w2 < warp; ++w2) before = max(before, s_wmax[w2]);
+    for (int w2 = 7; w2 > warp; --w2) after = min(after, s_wmin[w2]);
+    {
+        const int up = __shfl_up_sync(0xffffffffu, inc, 1);             // inclusive max of the lanes before me
+        const int carry = max(before, lane ? up : NONE);
+        const int dn = __shfl_down_sync(0xffffffffu, dec, 1);           // inclusive min of the lanes after me
+        const int carry_r = min(after, lane < 31 ? dn : INF);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) { hs[q] = max(hs[q], carry); if (he[q] == INF) he[q] = carry_r; }
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const int j = j0 + q;
+        if (j < n) {
+            const double x = v[j];
+            s_val[j] = x; s_key[j] = sortable_key(x); s_idx[j] = ix[j];
+            s_hs[j] = (short)hs[q]; s_he[j] = (short)he[q];
+        }
+    }
+    __syncthreads();
+#pragma unroll 1
+    for (int q = 0; q < 4; ++q) {
+        const int j = j0 + q;
+        if (j >= n) break;
+        const int h = hs[q], e = he[q];
+        if (h >= 0 && e <= n) {                                        // my run lies inside the tile
+            if (e - h < 2) continue;
+            const unsigned long long kj = s_key[j];
+            int rank = 0;
+            for (int k = h; k < e; ++k) {
+                const unsigned long long kk = s_key[k];
+                rank += (kk < kj || (kk == kj && k < j)) ? 1 : 0;
+            }
+            if (h + rank != j) { v[h + rank] = s_val[j]; ix[h + rank] = s_idx[j]; }
+            continue;
+        }
+        // my run crosses a tile border
+        const long long i = t0 + j;
+        const double* mg = km + o; double* vg = kv + o; int* ig = idx + o;
+        const unsigned long long key = mk[q];
+        const bool tie_next = (i + 1 < N) && sortable_key(mg[i + 1]) == key;
+        if (!tie_next) continue;
+        if (head[q]) {                                                  // its head sits in this tile: measure, sort or queue it
+            long long ee = i + 2;
+            while (ee < N && ee - i <= kTieCta && sortable_key(mg[ee]) == key) ++ee;
+            const long long len = ee - i;
+            if (len > kTieCta) continue;
+            if (len > kTieSelf) {
+                const bool big = len > kTieWarp;
+                const long long slot = atomicAdd(&ctl[big ? 2 : 1], 1);
+                if (slot < (big ? cta_cap : warp_cap)) { TieRun r; r.at = o + i; r.len = (int)len; r.pad = 0; (big ? cta_runs : warp_runs)[slot] = r; }
+                else ctl[0] = 1;
+                continue;
+            }
+            for (long long a2 = i + 1; a2 < ee; ++a2) {
+                const double va = vg[a2];
+                const int ia = ig[a2];
+                const unsigned long long ka = sortable_key(va);
+                long long b2 = a2;
+                while (b2 > i && sortable_key(vg[b2 - 1]) > ka) { vg[b2] = vg[b2 - 1]; ig[b2] = ig[b2 - 1]; --b2; }
+                if (b2 != a2) { vg[b2] = va; ig[b2] = ia; }
+            }
+            continue;
+        }
+        // not the head: an inversion inside a run too long to be repaired raises the gate
+        if (sortable_key(vg[i]) <= sortable_key(vg[i + 1])) continue;
+        long long hh = i;
+        while (hh > 0 && i - hh <= kTieCta && sortable_key(mg[hh - 1]) == key) {
+            --hh;
+            if (((i - hh) & 255) == 0 && *(volatile int*)ctl) break;
+        }
+        long long ee = i + 2;
+        while (ee < N && ee - hh <= kTieCta && sortable_key(mg[ee]) == key) ++ee;
+        if (ee - hh > kTieCta) ctl[0] = 1;
+    }
+}
+
 // Stable rank-counting sort of the queued runs by the variance key: TEAM threads (a warp or the whole CTA) per run.
 template <bool CTA>
 __global__ void __launch_bounds__(256) rs_tie_sort_runs(double* __restrict__ kv, int* __restrict__ idx, const int* __restrict__ ctl,
@@ -955,7 +1091,9 @@ int sort_mean_var(JacksCtx* ctx, cudaStream_t st, const double* km, const double
     if (!two_key) {
         radix(1, true, nullptr);
         rs_gather_sorted<<<eg, 256, 0, st>>>(km, kv, iin, ld, N, km_s, kv_s, nullptr);
-        rs_tie_find<<<eg, 256, 0, st>>>(km_s, kv_s, iin, ld, N, w.gate, w.warp_runs, w.cta_runs, tie_warp_cap(S, ld), tie_cta_cap(S, ld));
+        static const bool tie_find = []() { const char* v = getenv("JACKS_TIE_FIND"); return v && atoi(v) != 0; }();      // A/B: the per-head version
+        if (tie_find) rs_tie_find<<<eg, 256, 0, st>>>(km_s, kv_s, iin, ld, N, w.gate, w.warp_runs, w.cta_runs, tie_warp_cap(S, ld), tie_cta_cap(S, ld));
+        else rs_tie_tile<<<dim3((unsigned)((N + kTieTile - 1) / kTieTile), (unsigned)S), 256, 0, st>>>(km_s, kv_s, iin, ld, N, w.gate, w.warp_runs, w.cta_runs, tie_warp_cap(S, ld), tie_cta_cap(S, ld));
         rs_tie_sort_runs<false><<<4 * 148, 256, 0, st>>>(kv_s, iin, w.gate, w.warp_runs, tie_warp_cap(S, ld));
         rs_tie_sort_runs<true><<<148, 256, 0, st>>>(kv_s, iin, w.gate, w.cta_runs, tie_cta_cap(S, ld));
         ctx->launches += 4;
