@@ -221,11 +221,14 @@ typedef struct JacksScreenHostIO {
 } JacksScreenHostIO;
 
 /*
- * Host buffers.  Transfers: the rows the pseudo-gene index references (a few thousand control guides) go up first, as a
- * compact cube, so the pseudo-gene EM -- 85 % of the arithmetic at the Avana shape -- and the null densities run while
- * the screen itself is still uploading; the real genes follow range by range behind their rows (EM, p-values, download).
- * The screen is uploaded ONCE; a control shared by all lines is passed as [N, 1, 2] (ctrl_lines = 1).  Downloaded: the
- * real-gene outputs that are non-NULL and the pseudo-gene outputs that are non-NULL.
+ * Host buffers.  Transfers: the screen is uploaded ONCE and starts going up at once (page-locked cubes); the rows the
+ * pseudo-gene index references (a few thousand control guides) are pulled beside it by a kernel into a compact cube, so the
+ * pseudo-gene EM -- 85 % of the arithmetic at the Avana shape -- runs while the screen is still uploading; the real genes'
+ * EM runs beside it on a second stream, range by range behind their rows, each range's outputs going down as soon as it
+ * has run; null densities and p-values follow the last pseudo-gene (DESIGN.md section 6 has the timeline).  Pageable
+ * cubes take the same route through a pinned ring, upload after the pseudo-gene enqueue.  A control shared by all lines is
+ * passed as [N, 1, 2] (ctrl_lines = 1).  Downloaded: the real-gene outputs that are non-NULL and the pseudo-gene outputs
+ * that are non-NULL.
  * flags: JACKS_ASYNC, JACKS_KEEP_RESIDENT as for jacks_em_batched_host.
  */
 JACKS_API int jacks_run_screen_host(JacksCtx* ctx, const JacksEmParams* params,
