@@ -105,6 +105,32 @@ def load_reference():
         return None
 
 
+def load_reference_preprocess():
+    """jacks.preprocess of the unmodified reference (oracle/_ref), or None."""
+    try:
+        import sys as _sys
+        from oracle import make_ref
+        root = make_ref.make()
+        if root is None:
+            return None
+        saved = {k: _sys.modules.pop(k) for k in list(_sys.modules) if k == 'jacks' or k.startswith('jacks.')}
+        _sys.path.insert(0, root)
+        try:
+            import jacks.infer as RI
+            import jacks.preprocess as RP
+            assert os.path.abspath(RP.__file__).startswith(os.path.abspath(root)), RP.__file__
+        finally:
+            _sys.path.remove(root)
+            for k in list(_sys.modules):
+                if k == 'jacks' or k.startswith('jacks.'):
+                    _sys.modules.pop(k)
+            _sys.modules.update(saved)
+        RI.SP = np
+        return RP
+    except Exception:
+        return None
+
+
 def cpu_reference_rate(w, cores, genes_per_core, ref):
     """Gene-inferences/s of the reference's EM on `cores` processes (fork, arrays shared copy-on-write)."""
     import multiprocessing as mp
@@ -344,6 +370,30 @@ def aux_measurements(ctx, torch, dev, stream, w, params, hbm_peak, cpu_pv):
     pre['host_chain_ms'] = (time.perf_counter() - t0) / 3 * 1e3
     pre['host_chain'] = 'jacks_preprocess_host, pinned buffers: %.0f MB up, %.0f MB down per call' % (pin_in.array.nbytes / 1e6, pin_out.array.nbytes / 1e6)
     assert np.array_equal(pin_out.array, data, equal_nan=True)
+    # CPU baseline: the unmodified reference's own functions (preprocess.py:77-96 normalizeLogCounts, :61-67
+    # condense_normalised_counts -> calc_posterior_sd) on ALL guides of the first few samples, one core (the reference's
+    # preprocessing is a serial Python loop over samples), checked against the GPU cube; else the numpy restatement
+    n_s = 6
+    sub = counts[:, :2 * n_s]
+    ref_pre = load_reference_preprocess()
+    t0 = time.perf_counter()
+    if ref_pre is not None:
+        lc_ref = ref_pre.normalizeLogCounts(np.log2(sub + 32.0), normtype='median')
+        cube_ref = ref_pre.condense_normalised_counts(lc_ref, [[2 * s_, 2 * s_ + 1] for s_ in range(n_s)], list(range(n_s)))
+        kind = 'reference'
+    else:
+        from oracle import jacks_oracle as O
+        lc_ref = O.normalize_log_counts(O.log_counts(sub, 32), 'median')
+        cube_ref = O.condense(lc_ref, [[2 * s_, 2 * s_ + 1] for s_ in range(n_s)])
+        kind = 'port'
+    dt = time.perf_counter() - t0
+    err = np.abs(cube_ref[:, :, 1] - data[:, :n_s, 1]) / np.abs(cube_ref[:, :, 1])
+    assert np.abs(cube_ref[:, :, 0] - data[:, :n_s, 0]).max() < 1e-12 and err.max() < 1e-9, (err.max(),)
+    pre['cpu_baseline'] = {'value': N * n_s / dt, 'unit': 'guide-samples/s', 'cores': 1, 'kind': kind, 'seconds': dt,
+                           'sample': 'all %d guides of the first %d samples (%d replicate columns) of the same count matrix: log2, '
+                                     'median normalisation, mean + posterior sd per sample; outputs checked against the GPU cube' % (N, n_s, 2 * n_s)}
+    if 'device_ms' in pre:
+        pre['device_guide_samples_per_s'] = N * (Cc // 2) / (pre['device_ms'] * 1e-3)
     pin_in.free(); pin_out.free()
     out['preprocess'] = pre
     assert np.isfinite(data).all()

@@ -403,11 +403,8 @@ __global__ void __launch_bounds__(256) rs_load_keys(const double* __restrict__ s
     if (idx_out) idx_out[o + i] = (int)i;
 }
 
-__global__ void __launch_bounds__(kRsThreads) rs_hist(const unsigned long long* __restrict__ keys, long long ld, long long N, int shift,
-                                                      int nchunk, unsigned* __restrict__ hist, const int* __restrict__ gate) {
-    __shared__ unsigned sh[kRsBins];
-    if (gate && *gate == 0) return;
-    const int s = blockIdx.y, chunk = blockIdx.x;
+__device__ __forceinline__ void rs_hist_item(const unsigned long long* __restrict__ keys, long long ld, long long N, int shift,
+                                             int nchunk, unsigned* __restrict__ hist, int s, int chunk, unsigned* sh) {
     for (int c = threadIdx.x; c < kRsBins; c += kRsThreads) sh[c] = 0;
     __syncthreads();
     const unsigned long long* row = keys + (long long)s * ld;
@@ -417,6 +414,23 @@ __global__ void __launch_bounds__(kRsThreads) rs_hist(const unsigned long long* 
     __syncthreads();
     unsigned* out = hist + ((long long)s * nchunk + chunk) * kRsBins;
     for (int c = threadIdx.x; c < kRsBins; c += kRsThreads) out[c] = sh[c];
+}
+__global__ void __launch_bounds__(kRsThreads) rs_hist(const unsigned long long* __restrict__ keys, long long ld, long long N, int shift,
+                                                      int nchunk, unsigned* __restrict__ hist) {
+    __shared__ unsigned sh[kRsBins];
+    rs_hist_item(keys, ld, N, shift, nchunk, hist, blockIdx.y, blockIdx.x, sh);
+}
+// The gated twins (fallback of sort_mean_var): a small grid that loops over the (chunk, segment) items.  Their launches
+// are almost always empty, and 7,000 CTAs that return at once -- each with 64 KB of shared memory in the scatter's case --
+// cost 7..22 us a launch, 0.4 ms over the 36 launches of a fallback that does not run.
+__global__ void __launch_bounds__(kRsThreads) rs_hist_gated(const unsigned long long* __restrict__ keys, long long ld, long long N, int shift,
+                                                            int nchunk, int n_seg, unsigned* __restrict__ hist, const int* __restrict__ gate) {
+    __shared__ unsigned sh[kRsBins];
+    if (*gate == 0) return;
+    for (long long wi = blockIdx.x; wi < (long long)nchunk * n_seg; wi += gridDim.x) {
+        rs_hist_item(keys, ld, N, shift, nchunk, hist, (int)(wi / nchunk), (int)(wi % nchunk), sh);
+        __syncthreads();
+    }
 }
 
 // one CTA per segment: hist[chunk][bin] becomes the position of the first key of (chunk, bin) in the sorted segment
@@ -475,13 +489,10 @@ __global__ void __launch_bounds__(1024) rs_scan(int nchunk, unsigned* __restrict
 // Stable scatter: warp w of the CTA owns a contiguous eighth of the chunk and walks it in order, 32 consecutive keys at
 // a time; keys of a group with equal digit take consecutive positions in lane order (match_any); the warp's running
 // count per digit (shared memory, one row per warp) carries on to the next group.
-__global__ void __launch_bounds__(kRsThreads) rs_scatter(const unsigned long long* __restrict__ kin, const int* __restrict__ iin,
-                                                         long long ld, long long N, int shift, int nchunk,
-                                                         const unsigned* __restrict__ hist, unsigned long long* __restrict__ kout,
-                                                         int* __restrict__ iout, const int* __restrict__ gate) {
-    extern __shared__ unsigned cnt[];                    // [8 warps][kRsBins]
-    if (gate && *gate == 0) return;
-    const int s = blockIdx.y, chunk = blockIdx.x;
+__device__ __forceinline__ void rs_scatter_item(const unsigned long long* __restrict__ kin, const int* __restrict__ iin,
+                                                long long ld, long long N, int shift, int nchunk,
+                                                const unsigned* __restrict__ hist, unsigned long long* __restrict__ kout,
+                                                int* __restrict__ iout, int s, int chunk, unsigned* cnt) {
     constexpr int W = kRsThreads / 32, SEG = kRsChunk / W;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     for (int c = threadIdx.x; c < W * kRsBins; c += kRsThreads) cnt[c] = 0;
@@ -519,6 +530,24 @@ __global__ void __launch_bounds__(kRsThreads) rs_scatter(const unsigned long lon
         old = __shfl_sync(0xffffffffu, old, leader);
         if (dig[k] >= 0) { kout[o + old + rank] = key[k]; iout[o + old + rank] = pay[k]; }
         __syncwarp();
+    }
+}
+__global__ void __launch_bounds__(kRsThreads) rs_scatter(const unsigned long long* __restrict__ kin, const int* __restrict__ iin,
+                                                         long long ld, long long N, int shift, int nchunk,
+                                                         const unsigned* __restrict__ hist, unsigned long long* __restrict__ kout,
+                                                         int* __restrict__ iout) {
+    extern __shared__ unsigned cnt[];                    // [8 warps][kRsBins]
+    rs_scatter_item(kin, iin, ld, N, shift, nchunk, hist, kout, iout, blockIdx.y, blockIdx.x, cnt);
+}
+__global__ void __launch_bounds__(kRsThreads) rs_scatter_gated(const unsigned long long* __restrict__ kin, const int* __restrict__ iin,
+                                                               long long ld, long long N, int shift, int nchunk, int n_seg,
+                                                               const unsigned* __restrict__ hist, unsigned long long* __restrict__ kout,
+                                                               int* __restrict__ iout, const int* __restrict__ gate) {
+    extern __shared__ unsigned cnt[];
+    if (*gate == 0) return;
+    for (long long wi = blockIdx.x; wi < (long long)nchunk * n_seg; wi += gridDim.x) {
+        rs_scatter_item(kin, iin, ld, N, shift, nchunk, hist, kout, iout, (int)(wi / nchunk), (int)(wi % nchunk), cnt);
+        __syncthreads();
     }
 }
 
@@ -1065,6 +1094,7 @@ int sort_mean_var(JacksCtx* ctx, cudaStream_t st, const double* km, const double
     cudaError_t e;
     if (!ctx->pre_attr_set) {              // per device
         if ((e = cudaFuncSetAttribute(rs_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, kRsThreads / 32 * kRsBins * 4)) != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute");
+        if ((e = cudaFuncSetAttribute(rs_scatter_gated, cudaFuncAttributeMaxDynamicSharedMemorySize, kRsThreads / 32 * kRsBins * 4)) != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute");
         ctx->pre_attr_set = true;
     }
     const int nchunk = (int)((N + kRsChunk - 1) / kRsChunk);
@@ -1077,9 +1107,16 @@ int sort_mean_var(JacksCtx* ctx, cudaStream_t st, const double* km, const double
         rs_load_keys<<<eg, 256, 0, st>>>(which == 0 ? kv : km, from_index_order ? nullptr : iin, ld, N, kin, from_index_order ? iin : nullptr, gate);
         ctx->launches++;
         for (int shift = 0; shift < 64; shift += kRsBits) {
-            rs_hist<<<cg, kRsThreads, 0, st>>>(kin, ld, N, shift, nchunk, w.hist, gate);
-            rs_scan<<<S, 1024, 0, st>>>(nchunk, w.hist, gate);
-            rs_scatter<<<cg, kRsThreads, kRsThreads / 32 * kRsBins * 4, st>>>(kin, iin, ld, N, shift, nchunk, w.hist, kout, iout, gate);
+            if (!gate) {
+                rs_hist<<<cg, kRsThreads, 0, st>>>(kin, ld, N, shift, nchunk, w.hist);
+                rs_scan<<<S, 1024, 0, st>>>(nchunk, w.hist, nullptr);
+                rs_scatter<<<cg, kRsThreads, kRsThreads / 32 * kRsBins * 4, st>>>(kin, iin, ld, N, shift, nchunk, w.hist, kout, iout);
+            } else {
+                const unsigned wg = (unsigned)std::min<long long>((long long)nchunk * S, 592);
+                rs_hist_gated<<<wg, kRsThreads, 0, st>>>(kin, ld, N, shift, nchunk, S, w.hist, gate);
+                rs_scan<<<S, 1024, 0, st>>>(nchunk, w.hist, gate);
+                rs_scatter_gated<<<wg, kRsThreads, kRsThreads / 32 * kRsBins * 4, st>>>(kin, iin, ld, N, shift, nchunk, S, w.hist, kout, iout, gate);
+            }
             ctx->launches += 3;
             std::swap(kin, kout); std::swap(iin, iout);
         }
@@ -1102,10 +1139,13 @@ int sort_mean_var(JacksCtx* ctx, cudaStream_t st, const double* km, const double
     }
     // Exact fallback, enqueued always, run only when the repair met an out-of-order run longer than it handles:
     // stable by the variance, then stable by the mean (Python's tuple order, preprocess.py:39-40).
-    radix(0, true, w.gate);
-    radix(1, false, w.gate);
-    rs_gather_sorted<<<eg, 256, 0, st>>>(km, kv, iin, ld, N, km_s, kv_s, w.gate);
-    ctx->launches++;
+    static const bool no_fallback = []() { const char* v = getenv("JACKS_SORT_NO_FALLBACK"); return v && atoi(v) != 0; }();   // MEASUREMENT ONLY: what the gated launches cost
+    if (!no_fallback || two_key) {
+        radix(0, true, w.gate);
+        radix(1, false, w.gate);
+        rs_gather_sorted<<<eg, 256, 0, st>>>(km, kv, iin, ld, N, km_s, kv_s, w.gate);
+        ctx->launches++;
+    }
     if ((e = cudaGetLastError()) != cudaSuccess) return cuda_fail(e, "sort kernels");
     *ki_sorted = iin;
     return JACKS_OK;
