@@ -132,3 +132,32 @@ def test_back_to_back_async_compact_calls_do_not_race(nat):
         ctx.synchronize()
         assert np.array_equal(a['w1'], ref1['w1']) and np.array_equal(b['w1'], ref2['w1'])
     ctx.close()
+
+
+@pytest.mark.parametrize('common_ctrl', [False, True])
+def test_screen_host_pinned_cubes_nan_genes(nat, common_ctrl):
+    """The call the bench times: PAGE-LOCKED cubes (the screen goes up first, the gene indexes and the control rows are
+    pulled by kernels, the real-gene EM runs beside the one-launch pseudo-gene EM in the SM slots it leaves, p-values on
+    their own download stream) -- with genes that hold NaN, so that the deferred-queue kernel runs in its co-residable
+    configuration beside the resident pseudo-gene kernel.  Bit for bit against the separate calls on pageable arrays."""
+    offs, rows, poffs, prows, test, ctrl = make_screen(n_genes=5000, n_lines=160, n_pseudo=20000, seed=33)
+    rng = np.random.default_rng(3)
+    for g in rng.choice(len(offs) - 1, size=40, replace=False):           # NaN measurements in 40 real genes
+        r = rows[offs[g]]
+        test[r, rng.integers(0, test.shape[1]), 0] = np.nan
+    if common_ctrl:
+        ctrl = np.ascontiguousarray(ctrl[:, :1, :])
+    ctx = nat.context(0)
+    pt, pc = nat.PinnedArray(test.shape), nat.PinnedArray(ctrl.shape)
+    pt.array[...] = test
+    pc.array[...] = ctrl
+    want = ('x1', 'x2', 'w1', 'w2', 'n_iters', 'pvals')
+    for _ in range(2):                                                    # twice: recycled plan buffers and staging
+        got = nat.run_screen_host(ctx, offs, rows, poffs, prows, pt.array, pc.array, want=want)
+    real = nat.em_batched_host(ctx, offs, rows, test, ctrl, want=('x1', 'x2', 'w1', 'w2', 'n_iters'))
+    pseudo = nat.em_batched_host(ctx, poffs, prows, test, ctrl, want=('w1',))
+    for k in ('x1', 'x2', 'w1', 'w2', 'n_iters'):
+        assert np.array_equal(got[k], real[k], equal_nan=True), k
+    pv = nat.kde_pvalues_host(ctx, real['w1'], pseudo['w1'])
+    assert np.array_equal(got['pvals'], pv, equal_nan=True)
+    pt.free(); pc.free()
