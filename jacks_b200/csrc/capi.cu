@@ -358,6 +358,9 @@ int jacks_em_plan_create(JacksCtx* ctx, const int64_t* gene_offsets, const int32
         ctx->plan_pool.erase(ctx->plan_pool.begin() + pick);
     } else p->b = new PlanBufs();
     p->b->sig_genes = n_genes; p->b->sig_guides = total;
+    // recycled buffers: the copy kernel of the plan they served last must have read the pinned staging (it has, unless
+    // that plan was created and destroyed without anything waiting for it)
+    if (p->b->ready && (e = cudaEventSynchronize(p->b->ready)) != cudaSuccess) { cudaGetLastError(); }
     p->ctx = ctx; p->n_genes = n_genes; p->n_rows = n_rows; p->total_guides = total; p->L = n_lines;
     p->generic = EmBucket{0, 0, 0, 0, 0};
     p->big = EmBucket{0, 0, 0, 0, 0};
@@ -855,7 +858,7 @@ static int em_batched_host_core(JacksCtx* ctx, const JacksEmParams* params, cons
         return fail(JACKS_E_SHAPE, "Expecting matched size between control and test data");
     cudaError_t e = cudaSetDevice(ctx->device);
     if (e != cudaSuccess) return cuda_fail(e, "cudaSetDevice");
-    cudaStream_t s_k = ctx->stream, s_in = ctx->copy_stream, s_out = ctx->out_stream;
+    cudaStream_t s_k = ctx->stream, s_in = ctx->copy_stream;
     cudaStream_t s_em = opt.em_stream ? opt.em_stream : s_k;      // EM kernels; s_k keeps the p-values
     const bool split = s_em != s_k;
     int rc;

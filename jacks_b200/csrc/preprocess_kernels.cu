@@ -395,12 +395,13 @@ __global__ void __launch_bounds__(256) rs_load_keys(const double* __restrict__ s
                                                     unsigned long long* __restrict__ keys, int* __restrict__ idx_out,
                                                     const int* __restrict__ gate) {
     if (gate && *gate == 0) return;
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= N) return;
     const long long o = (long long)blockIdx.y * ld;
-    const long long from = idx ? idx[o + i] : i;
-    keys[o + i] = sortable_key(src[o + from]);
-    if (idx_out) idx_out[o + i] = (int)i;
+    // grid-stride along the segment: one trip on the product path; the gated launches take a few CTAs per segment
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += (long long)gridDim.x * blockDim.x) {
+        const long long from = idx ? idx[o + i] : i;
+        keys[o + i] = sortable_key(src[o + from]);
+        if (idx_out) idx_out[o + i] = (int)i;
+    }
 }
 
 __device__ __forceinline__ void rs_hist_item(const unsigned long long* __restrict__ keys, long long ld, long long N, int shift,
@@ -556,12 +557,12 @@ __global__ void __launch_bounds__(256) rs_gather_sorted(const double* __restrict
                                                         long long ld, long long N, double* __restrict__ dm, double* __restrict__ dv,
                                                         const int* __restrict__ gate) {
     if (gate && *gate == 0) return;
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= N) return;
     const long long o = (long long)blockIdx.y * ld;
-    const int from = idx[o + i];
-    dm[o + i] = km[o + from];
-    dv[o + i] = kv[o + from];
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += (long long)gridDim.x * blockDim.x) {
+        const int from = idx[o + i];
+        dm[o + i] = km[o + from];
+        dv[o + i] = kv[o + from];
+    }
 }
 
 // Tie repair after a stable sort by the MEAN alone (from index order).  The order wanted is (mean, var, index): only the
@@ -641,7 +642,6 @@ __global__ void __launch_bounds__(256) rs_tie_tile(const double* __restrict__ km
     __shared__ unsigned long long s_key[kTieTile];
     __shared__ double s_val[kTieTile];
     __shared__ int s_idx[kTieTile];
-    __shared__ short s_hs[kTieTile], s_he[kTieTile];
     __shared__ int s_wmax[8], s_wmin[8];
     constexpr int NONE = -1, INF = 30000;
     const long long o = (long long)blockIdx.y * ld;
@@ -701,7 +701,6 @@ __global__ void __launch_bounds__(256) rs_tie_tile(const double* __restrict__ km
         if (j < n) {
             const double x = v[j];
             s_val[j] = x; s_key[j] = sortable_key(x); s_idx[j] = ix[j];
-            s_hs[j] = (short)hs[q]; s_he[j] = (short)he[q];
         }
     }
     __syncthreads();
@@ -1099,12 +1098,13 @@ int sort_mean_var(JacksCtx* ctx, cudaStream_t st, const double* km, const double
     }
     const int nchunk = (int)((N + kRsChunk - 1) / kRsChunk);
     dim3 eg((unsigned)((N + 255) / 256), (unsigned)S), cg((unsigned)nchunk, (unsigned)S);
+    dim3 eg_gated((unsigned)std::min<long long>((N + 255) / 256, 4), (unsigned)S);      // grids of the (normally empty) gated launches
     unsigned long long* kin = w.kA; unsigned long long* kout = w.kB;
     int* iin = w.iA; int* iout = w.iB;
     // `which`: 0 stable by the variance from index order, 1 stable by the mean.  An even number of passes: the sorted
     // keys and indices end in the buffers they started in.
     auto radix = [&](int which, bool from_index_order, const int* gate) {
-        rs_load_keys<<<eg, 256, 0, st>>>(which == 0 ? kv : km, from_index_order ? nullptr : iin, ld, N, kin, from_index_order ? iin : nullptr, gate);
+        rs_load_keys<<<gate ? eg_gated : eg, 256, 0, st>>>(which == 0 ? kv : km, from_index_order ? nullptr : iin, ld, N, kin, from_index_order ? iin : nullptr, gate);
         ctx->launches++;
         for (int shift = 0; shift < 64; shift += kRsBits) {
             if (!gate) {
@@ -1143,7 +1143,7 @@ int sort_mean_var(JacksCtx* ctx, cudaStream_t st, const double* km, const double
     if (!no_fallback || two_key) {
         radix(0, true, w.gate);
         radix(1, false, w.gate);
-        rs_gather_sorted<<<eg, 256, 0, st>>>(km, kv, iin, ld, N, km_s, kv_s, w.gate);
+        rs_gather_sorted<<<eg_gated, 256, 0, st>>>(km, kv, iin, ld, N, km_s, kv_s, w.gate);
         ctx->launches++;
     }
     if ((e = cudaGetLastError()) != cudaSuccess) return cuda_fail(e, "sort kernels");
