@@ -374,6 +374,26 @@ JACKS_API int jacks_table_read(const char* path, int64_t data_offset, char delim
 JACKS_API int jacks_table_write(const char* path, const char* header, int64_t n_rows, int32_t n_cols, const char* labels,
                       const int64_t* label_off, const double* values, const uint8_t* blank, int32_t width);
 
+/*
+ * jacks_pseudo_draw: the draws of createPseudoNonessGenes (jacks/jacks/jacks_io.py:256-264) for n_pseudo pseudo-genes,
+ *   consuming the stream of Python's global `random` generator draw for draw: per pseudo-gene one
+ *   random.choice over ALL genes (its guide count is taken), then per guide one random.choice over the control genes
+ *   and one over that gene's guide rows.  random.choice(seq) is seq[_randbelow(len(seq))] with
+ *   _randbelow(n) = rejection sampling of getrandbits(n.bit_length()), i.e. the top bits of one MT19937 output per try
+ *   (CPython Lib/random.py, Modules/_randommodule.c).
+ *   mt_state [625]: the generator's 624 key words and its position, as random.getstate()[1] holds them; updated in
+ *   place to the state after the last draw, so random.setstate() continues the caller's stream exactly where the
+ *   reference's loop would have left it.
+ *   gene_offsets / guide_rows: the gene index (CSR, dict order); ctrl_genes [n_ctrl]: positions of the control genes in
+ *   it, in the iteration order of the control-gene list.  out_offsets [n_pseudo + 1], out_rows [rows_cap]: the
+ *   pseudo-gene index (CSR).  *rows_needed = number of rows drawn; when it exceeds rows_cap the call returns
+ *   JACKS_E_SHAPE, leaves mt_state untouched and the caller retries with a larger buffer.
+ *   An empty sequence under a draw is JACKS_E_INVALID (the reference raises IndexError there).
+ */
+JACKS_API int jacks_pseudo_draw(uint32_t* mt_state, const int64_t* gene_offsets, const int32_t* guide_rows, int64_t n_genes,
+                      const int64_t* ctrl_genes, int64_t n_ctrl, int64_t n_pseudo, int64_t* out_offsets,
+                      int32_t* out_rows, int64_t rows_cap, int64_t* rows_needed);
+
 /* FP64 FMA-pipe peak of the current device in FLOP/s (dependent-chain-free DFMA microbenchmark);
  * bench.py uses it as the roofline denominator because MEASURED_PEAKS.json has no FP64 entry. */
 JACKS_API int jacks_fp64_peak_flops(JacksCtx* ctx, double* flops_out, double* seconds_out);

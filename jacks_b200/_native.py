@@ -113,6 +113,7 @@ def lib():
         L.jacks_table_scan.argtypes = [C.c_char_p, i64, C.POINTER(i64), C.POINTER(i64)]
         L.jacks_table_read.argtypes = [C.c_char_p, i64, C.c_char, i64, i32, vp, vp, vp, i32, vp, vp, vp]
         L.jacks_table_write.argtypes = [C.c_char_p, C.c_char_p, i64, i32, vp, vp, vp, vp, i32]
+        L.jacks_pseudo_draw.argtypes = [vp, vp, vp, i64, vp, i64, i64, vp, vp, i64, C.POINTER(i64)]
         _lib = L
     return _lib
 
@@ -623,3 +624,30 @@ def table_write(path, header, labels, values, width, blank=None):
     mask = None if blank is None else np.ascontiguousarray(blank, dtype=np.uint8)
     check(lib().jacks_table_write(os.fsencode(path), header.encode(), len(enc), values.shape[1] if values.size or len(enc) else 0,
                                   blob, _ptr(offs), _ptr(values), _ptr(mask), int(width)))
+
+
+def pseudo_draw(mt_state, offsets, rows, ctrl_genes, n_pseudo):
+    """jacks_pseudo_draw: the draws of createPseudoNonessGenes on a Mersenne-Twister state.  mt_state: the 625 words of
+    random.getstate()[1]; offsets / rows: the gene index (CSR, dict order); ctrl_genes: positions of the control genes
+    in it, in list order.  Returns (new_state uint32[625], pseudo_offsets int64[n_pseudo + 1], pseudo_rows int32)."""
+    st = np.array(mt_state, dtype=np.uint32)
+    if st.shape != (625,):
+        raise ValueError('expected the 625 state words of random.getstate()[1]')
+    offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+    rows = np.ascontiguousarray(rows, dtype=np.int32)
+    ctrl_genes = np.ascontiguousarray(ctrl_genes, dtype=np.int64)
+    n_genes = len(offsets) - 1
+    n_pseudo = int(n_pseudo)
+    poffs = np.zeros(n_pseudo + 1, dtype=np.int64)
+    mean_g = (int(offsets[-1]) + n_genes - 1) // n_genes if n_genes > 0 else 1
+    cap = n_pseudo * mean_g + (n_pseudo * mean_g) // 4 + 1024
+    need = C.c_int64(0)
+    while True:
+        prows = np.empty(cap, dtype=np.int32)
+        rc = lib().jacks_pseudo_draw(st.ctypes.data, _ptr(offsets), _ptr(rows), n_genes, _ptr(ctrl_genes), len(ctrl_genes),
+                                     n_pseudo, poffs.ctypes.data, prows.ctypes.data, cap, C.byref(need))
+        if rc == JACKS_E_SHAPE and need.value > cap:
+            cap = int(need.value)                 # the state was left untouched: draw again into a buffer that holds them
+            continue
+        check(rc)
+        return st, poffs, prows[:int(need.value)]

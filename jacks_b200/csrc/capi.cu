@@ -389,8 +389,10 @@ int jacks_em_plan_create(JacksCtx* ctx, const int64_t* gene_offsets, const int32
     int rc = JACKS_OK;
     // The index arrays are built IN the plan's pinned staging and pulled by a copy kernel on the plan stream: a
     // cudaMemcpyAsync would queue in the copy engine behind whatever upload is in flight (the screen of a screen job).
+    // one bucket holds every gene: slot order is gene order, and the per-slot arrays ARE the index arrays (no second copy)
+    const bool one_bucket = p->fast.size() == 1 && !n_gen && !n_big;
     const size_t lens[5] = {n_genes ? (size_t)(n_genes + 1) * sizeof(int64_t) : 0, (size_t)total * sizeof(int32_t), (size_t)n_ids * sizeof(int),
-                            (size_t)n_slots * sizeof(long long), (size_t)n_slot_rows * sizeof(int)};
+                            one_bucket ? 0 : (size_t)n_slots * sizeof(long long), one_bucket ? 0 : (size_t)n_slot_rows * sizeof(int)};
     DevBuf* dsts[5] = {&p->b->d_offsets, &p->b->d_rows, &p->b->d_ids, &p->b->d_slot_off, &p->b->d_slot_rows};
     size_t offs5[5], stage_bytes = 0;
     for (int i = 0; i < 5; ++i) { offs5[i] = stage_bytes; stage_bytes += (lens[i] + 255) & ~(size_t)255; }
@@ -408,11 +410,8 @@ int jacks_em_plan_create(JacksCtx* ctx, const int64_t* gene_offsets, const int32
         int* s_ids = (int*)(hs + offs5[2]);
         long long* s_off = (long long*)(hs + offs5[3]);
         int* s_rows = (int*)(hs + offs5[4]);
-        if (p->fast.size() == 1 && !n_gen && !n_big) {
-            // one bucket holds every gene (a library with a fixed guide count; every pseudo-gene index): slot order is gene order
+        if (one_bucket) {
             for (int64_t g = 0; g < n_genes; ++g) s_ids[g] = (int)g;
-            memcpy(s_off, gene_offsets, (size_t)n_genes * sizeof(long long));
-            memcpy(s_rows, guide_rows, (size_t)total * sizeof(int));
         } else {
             for (int64_t g = 0; g < n_genes; ++g) {
                 const long long o = gene_offsets[g];
@@ -442,6 +441,8 @@ int jacks_em_plan_create(JacksCtx* ctx, const int64_t* gene_offsets, const int32
         if ((e = cudaGetLastError()) != cudaSuccess) rc = cuda_fail(e, "pull_words_kernel launch");
         ctx->launches++;
     }
+    p->slot_off = (const long long*)(one_bucket ? p->b->d_offsets.p : p->b->d_slot_off.p);
+    p->slot_rows = (const int*)(one_bucket ? p->b->d_rows.p : p->b->d_slot_rows.p);
     if (rc == JACKS_OK) rc = p->b->d_deferred.reserve((size_t)std::max<int64_t>(n_genes, 1) * sizeof(int));
     if (rc == JACKS_OK) rc = p->b->d_counters.reserve(kCounterInts * sizeof(int));
     if (rc == JACKS_OK && p->fast_maxG > 0)
@@ -520,8 +521,8 @@ int em_run_range(JacksCtx* ctx, const JacksEmPlan* plan, const JacksEmParams* pa
         slots_of(b, &s0, &s1);
         if (s1 <= s0) continue;
         a.gene_ids = (const int*)plan->b->d_ids.p + b.ids_off + s0;
-        a.slot_off = (const long long*)plan->b->d_slot_off.p + b.ids_off + s0;
-        a.slot_rows = (const int*)plan->b->d_slot_rows.p + b.rows_off + (long long)s0 * b.G;
+        a.slot_off = plan->slot_off + b.ids_off + s0;
+        a.slot_rows = plan->slot_rows + b.rows_off + (long long)s0 * b.G;
         a.n_work = s1 - s0; a.n_work_dev = nullptr;
         a.work_counter = counters + slot++;
         int grid = 0;
@@ -736,9 +737,7 @@ static int em_batched_host_compact(JacksCtx* ctx, const JacksEmParams* params, c
     for (int64_t r = 0; r < N; ++r)
         if (remap[(size_t)r] == 0) { remap[(size_t)r] = (int32_t)used.size(); used.push_back(r); }
     const int64_t U = (int64_t)used.size();
-    std::vector<int32_t> rows2((size_t)T);
-    for (int64_t i = 0; i < T; ++i) rows2[(size_t)i] = remap[(size_t)guide_rows[i]];
-    trace_stamp("  compact: rows re-based");
+    trace_stamp("  compact: rows marked");
     const size_t row_t = (size_t)L * 2 * sizeof(double), row_c = (size_t)io->ctrl_lines * 2 * sizeof(double);
     const bool fx = io->fixed_x1 && io->fixed_x2;
     const size_t bytes = (size_t)U * (row_t + row_c + (fx ? 2 * sizeof(double) : 0));
@@ -809,6 +808,11 @@ static int em_batched_host_compact(JacksCtx* ctx, const JacksEmParams* params, c
     }
     cudaEventRecord(ctx->cmp_ready, s_in);
     trace_stamp("  compact: gather enqueued");
+    // the index re-based onto the compact cube -- after the gather is on its way: the pseudo-gene EM of a screen job waits
+    // for those rows (25 MB pulled over a PCIe link the screen upload is using too), not for this loop
+    std::vector<int32_t> rows2((size_t)T);
+    for (int64_t i = 0; i < T; ++i) rows2[(size_t)i] = remap[(size_t)guide_rows[i]];
+    trace_stamp("  compact: rows re-based");
     CompactCubes cc;
     cc.d_test = (const double*)ctx->cmp_dev.p;
     cc.d_ctrl = (const double*)((const char*)ctx->cmp_dev.p + (size_t)U * row_t);
@@ -1200,8 +1204,8 @@ static int em_lines_run(JacksCtx* ctx, const JacksEmPlan* plan, const JacksEmPar
     int64_t n_fast = 0;
     for (const EmBucket& b : plan->fast) {
         a.gene_ids = (const int*)plan->b->d_ids.p + b.ids_off;
-        a.slot_off = (const long long*)plan->b->d_slot_off.p + b.ids_off;
-        a.slot_rows = (const int*)plan->b->d_slot_rows.p + b.rows_off;
+        a.slot_off = plan->slot_off + b.ids_off;
+        a.slot_rows = plan->slot_rows + b.rows_off;
         a.n_work = b.n; a.n_work_dev = nullptr;
         e = launch_em_lines(b.G, a, ctx->n_sm, st);
         if (e != cudaSuccess) return cuda_fail(e, "em_lines_kernel launch");

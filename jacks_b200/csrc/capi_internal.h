@@ -134,6 +134,10 @@ struct JacksEmPlan {
     int fast_maxG;
     int n_fast_genes;
     jacks::EmGenericConfig cfg_generic, cfg_deferred;
+    // per-slot gene offsets and guide rows of the fast buckets: d_slot_off / d_slot_rows, or -- when ONE fast bucket holds
+    // every gene in caller order (a library with a fixed guide count; every pseudo-gene index) -- d_offsets / d_rows themselves
+    const long long* slot_off = nullptr;
+    const int* slot_rows = nullptr;
     jacks::EmGenericConfig cfg_deferred_small;   // the deferred queue's kernel with CTAs small enough to run BESIDE a resident fast kernel
 };
 

@@ -108,7 +108,7 @@ def inferJACKS(gene_index, testdata, ctrldata, fixed_x=None, n_iter=50, apply_w_
 
 
 def inferJACKSScreen(gene_index, pseudo_gene_index, testdata, ctrldata, fixed_x=None, n_iter=50, apply_w_hp=False,
-                     positive=False, device=0, full_pseudo=False):
+                     positive=False, device=0, full_pseudo=False, pseudo_csr=None):
     """The inference job of load_data_and_run in one GPU call (jacks_run_screen_host): what the reference does with
 
         jacks_results = inferJACKS(gene_index, testdata, ctrldata, apply_w_hp=..., fixed_x=...)        (jacks_io.py:425)
@@ -123,7 +123,8 @@ def inferJACKSScreen(gene_index, pseudo_gene_index, testdata, ctrldata, fixed_x=
     if testdata.shape != ctrldata.shape:
         raise Exception(_SHAPE_MSG)
     names, offsets, rows = _native.as_csr(gene_index)
-    pnames, poffsets, prows = _native.as_csr(pseudo_gene_index)
+    # pseudo_csr: (names, offsets, rows) of pseudo_gene_index when its maker already holds it (jacks_io._drawPseudoGenes)
+    pnames, poffsets, prows = pseudo_csr if pseudo_csr is not None else _native.as_csr(pseudo_gene_index)
     testdata, ctrldata = _planes(testdata), _planes(ctrldata)
     if _one_control(ctrldata):
         ctrldata = ctrldata[:, :1, :]

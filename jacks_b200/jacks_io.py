@@ -315,18 +315,60 @@ def loadSgrnaReference(filename):
     return x_ref
 
 
+def _drawPseudoGenes(gene_index, ctrl_geneset, num_psuedo_noness_genes):
+    """The draws of createPseudoNonessGenes: (pseudo_gene_index, csr) with csr = (names, offsets, rows) of the same index,
+    or None when the draws were made by the interpreter.
+
+    The reference makes one random.choice over all genes per pseudo-gene (its guide count) and two per guide (a control
+    gene, one of its guides) -- 900,000 interpreter-level calls at 1e5 pseudo-genes.  Here the state of the global
+    ``random`` generator is handed to jacks_pseudo_draw (csrc/host_io.cpp), which runs the same Mersenne Twister through
+    the same rejection sampling, and the advanced state is put back: same sets, same stream position afterwards.
+    Gene indexes whose entries are not plain integers keep the interpreter loop."""
+    ctrl_geneset_lst = [x for x in ctrl_geneset if x in gene_index]
+    n = int(num_psuedo_noness_genes)
+    state = random.getstate()
+    native = n > 0 and state[0] == 3 and len(state[1]) == 625
+    if native:
+        try:
+            lens = [len(gene_index[g]) for g in gene_index]
+            flat = [r for g in gene_index for r in gene_index[g]]
+            native = all(isinstance(r, (int, np.integer)) for r in flat) and \
+                (len(flat) == 0 or (min(flat) >= -2 ** 31 and max(flat) < 2 ** 31))
+        except TypeError:
+            native = False
+    if not native:
+        pseudo_gene_index = {}
+        all_geneset_lst = [x for x in gene_index]
+        for i in range(n):
+            num_guides = len(gene_index[random.choice(all_geneset_lst)])
+            pseudo_gene_index['JACKS_PSEUDO_GENE_%d' % i] = [random.choice(gene_index[random.choice(ctrl_geneset_lst)])
+                                                             for j in range(num_guides)]
+        return pseudo_gene_index, None
+    offsets = np.zeros(len(lens) + 1, dtype=np.int64)
+    np.cumsum(np.asarray(lens, dtype=np.int64), out=offsets[1:])
+    pos = {g: i for i, g in enumerate(gene_index)}
+    try:
+        new_state, poffs, prows = _native.pseudo_draw(state[1], offsets, np.asarray(flat, dtype=np.int32),
+                                                      [pos[g] for g in ctrl_geneset_lst], n)
+    except _native.JacksError as e:
+        if 'empty sequence' in str(e):
+            raise IndexError('Cannot choose from an empty sequence')          # what random.choice raises in the reference
+        raise
+    random.setstate((state[0], tuple(int(v) for v in new_state), state[2]))
+    names = ['JACKS_PSEUDO_GENE_%d' % i for i in range(n)]
+    lo, rl = poffs.tolist(), prows.tolist()
+    pseudo_gene_index = {names[i]: rl[lo[i]:lo[i + 1]] for i in range(n)}
+    return pseudo_gene_index, (names, poffs, prows)
+
+
 def createPseudoNonessGenes(gene_index, ctrl_geneset, num_psuedo_noness_genes):
     """Pseudo-genes: the guide count of a random gene, then that many guides, each the random guide of a random
     control gene, with replacement (jacks_io.py:256-264).  Consumes the global ``random`` stream draw for draw
     like the reference, so the same seed and the same iteration order of ``ctrl_geneset`` give the same sets."""
-    pseudo_gene_index = {}
-    ctrl_geneset_lst = [x for x in ctrl_geneset if x in gene_index]
-    all_geneset_lst = [x for x in gene_index]
-    for i in range(num_psuedo_noness_genes):
-        num_guides = len(gene_index[random.choice(all_geneset_lst)])
-        pseudo_gene_index['JACKS_PSEUDO_GENE_%d' % i] = [random.choice(gene_index[random.choice(ctrl_geneset_lst)])
-                                                         for j in range(num_guides)]
-    return pseudo_gene_index
+    return _drawPseudoGenes(gene_index, ctrl_geneset, num_psuedo_noness_genes)[0]
+
+
+_createPseudoNonessGenes = createPseudoNonessGenes
 
 
 def getJacksParser():
@@ -432,10 +474,14 @@ def load_data_and_run(sample_spec, gene_spec, ctrl_spec, sgrna_reference_file, x
         # The reference's two inferJACKS calls (jacks_io.py:425, :430) and its p-value pass (:69-89) as ONE job on the GPU:
         # the screen goes up once, the pseudo-gene E[w] feeds the null densities on the device.  The pseudo-genes are
         # drawn first -- the same draws: inference does not touch the random stream.
-        pseudo_gene_index = createPseudoNonessGenes(gene_index, ctrl_geneset, n_pseudo)
+        if createPseudoNonessGenes is _createPseudoNonessGenes:
+            pseudo_gene_index, pseudo_csr = _drawPseudoGenes(gene_index, ctrl_geneset, n_pseudo)
+        else:                                       # replaced by the caller (the tests pin the reference's draws this way)
+            pseudo_gene_index, pseudo_csr = createPseudoNonessGenes(gene_index, ctrl_geneset, n_pseudo), None
         LOG.info('Running JACKS inference on %d pseudogenes' % n_pseudo)
         jacks_results, w1_pvals, pseudo = inferJACKSScreen(gene_index, pseudo_gene_index, testdata, ctrldata, fixed_x=x_reference,
-                                                           apply_w_hp=apply_w_hp, positive=positive, full_pseudo=(fdr is not None))
+                                                           apply_w_hp=apply_w_hp, positive=positive, full_pseudo=(fdr is not None),
+                                                           pseudo_csr=pseudo_csr)
         # no pseudo-gene is ever written (jacks_io.py:131): the reference's '_pseudo_noness' files hold the header only
         writeJacksWResults(outprefix + '_pseudo_noness', {}, sample_ids_without_ctrl, write_types=['', '_std'], positive=positive)
         jacks_pseudo_results = dict(jacks_results)

@@ -80,6 +80,78 @@ def test_pseudo_genes_follow_the_reference_random_stream():
         assert pidx[name] == rows[offs[i]:offs[i + 1]].tolist()
 
 
+def _interpreter_draws(gene_index, ctrl_geneset, n):
+    """The reference's loop, call for call (jacks/jacks/jacks_io.py:256-264)."""
+    out = {}
+    ctrl_lst = [x for x in ctrl_geneset if x in gene_index]
+    all_lst = [x for x in gene_index]
+    for i in range(n):
+        num_guides = len(gene_index[random.choice(all_lst)])
+        out['JACKS_PSEUDO_GENE_%d' % i] = [random.choice(gene_index[random.choice(ctrl_lst)]) for j in range(num_guides)]
+    return out
+
+
+@pytest.mark.parametrize('seed', [0, 1, 12345])
+def test_native_pseudo_draws_equal_the_interpreter_stream(seed):
+    """jacks_pseudo_draw (C-ABI) against random.choice: ragged guide counts incl. one-guide genes (a one-bit draw with
+    rejection), sequence lengths on both sides of a power of two, a stream that crosses several 624-word refills, and
+    the generator left where the interpreter loop leaves it."""
+    rng = np.random.RandomState(seed)
+    gene_index, r = {}, 0
+    for g in range(257 + seed % 7):
+        G = int(rng.choice([1, 1, 2, 3, 4, 5, 8, 16, 17]))
+        gene_index['gene%d' % g] = list(range(r, r + G))
+        r += G
+    ctrl = ['gene%d' % g for g in rng.choice(len(gene_index), 33, replace=False)] + ['not_in_the_index']
+    random.seed(seed)
+    random.random()                               # an odd stream position
+    want = _interpreter_draws(gene_index, ctrl, 700)
+    after_want = [random.random(), random.getrandbits(70), random.gauss(0, 1)]
+    random.seed(seed)
+    random.random()
+    got = jacks_io.createPseudoNonessGenes(gene_index, ctrl, 700)
+    after_got = [random.random(), random.getrandbits(70), random.gauss(0, 1)]
+    assert list(got) == list(want) and got == want
+    assert after_got == after_want
+    names, offs, rows = _native.as_csr(got)
+    assert int(offs[-1]) > 624 * 3
+
+
+def test_native_pseudo_draws_retry_errors_and_fallback():
+    gene_index = {'a': [0, 1, 2], 'b': list(range(3, 3 + 40)), 'c': [43]}
+    # the first buffer guess (mean guide count) is too small when most picks land on the 40-guide gene: the call retries
+    random.seed(3)
+    want = _interpreter_draws(gene_index, ['b'], 2000)
+    random.seed(3)
+    assert jacks_io.createPseudoNonessGenes(gene_index, ['b'], 2000) == want
+    st = np.array(random.getstate()[1], dtype=np.uint32)
+    offs = np.array([0, 3, 43, 44], dtype=np.int64)
+    with pytest.raises(_native.JacksError):          # too small a buffer: JACKS_E_SHAPE, state untouched, rows_needed set
+        import ctypes
+        need = ctypes.c_int64(0)
+        before = st.copy()
+        out_o = np.zeros(11, dtype=np.int64)
+        out_r = np.zeros(2, dtype=np.int32)
+        rows = np.arange(44, dtype=np.int32)
+        cg = np.array([1], dtype=np.int64)
+        rc = _native.lib().jacks_pseudo_draw(st.ctypes.data, offs.ctypes.data, rows.ctypes.data, 3, cg.ctypes.data, 1, 10,
+                                             out_o.ctypes.data, out_r.ctypes.data, 2, ctypes.byref(need))
+        assert rc == _native.JACKS_E_SHAPE and need.value > 2 and (st == before).all()
+        _native.check(rc)
+    # what random.choice raises in the reference: no control gene in the index / no gene at all
+    with pytest.raises(IndexError):
+        jacks_io.createPseudoNonessGenes(gene_index, ['zzz'], 5)
+    with pytest.raises(IndexError):
+        jacks_io.createPseudoNonessGenes({}, [], 5)
+    assert jacks_io.createPseudoNonessGenes(gene_index, ['a'], 0) == {}
+    # entries that are not plain integers keep the interpreter loop (same stream either way)
+    odd = {'a': ['r0', 'r1'], 'b': ['r2']}
+    random.seed(9)
+    want = _interpreter_draws(odd, ['a'], 20)
+    random.seed(9)
+    assert jacks_io.createPseudoNonessGenes(odd, ['a'], 20) == want
+
+
 def test_ranking_and_fdr_sets_match_reference():
     z = load_golden('pvals.npz')
     pv = {str(g): z['pv_neg'][i] for i, g in enumerate(z['order'])}
