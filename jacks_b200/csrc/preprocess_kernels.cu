@@ -523,6 +523,7 @@ __device__ __forceinline__ void rs_scatter_item(const unsigned long long* __rest
     __syncthreads();
 #pragma unroll
     for (int k = 0; k < SEG / 32; ++k) {
+        // (equal digits from kRsBits + 1 ballots instead of MATCH.ANY, which pays in the KDE scatter, measured 3 % slower here)
         const unsigned peers = __match_any_sync(0xffffffffu, dig[k]);
         const int leader = __ffs(peers) - 1;
         const int rank = __popc(peers & ((1u << lane) - 1));
