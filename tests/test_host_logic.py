@@ -399,3 +399,29 @@ def test_two_part_layout_covers_both_indexes():
     assert cube_rows[ri].tolist() == real.tolist() and cube_rows[pi].tolist() == pseudo_mine.tolist()
     P, R, k, ri, pi = jd.two_part_layout(real, [], [], 16, 2)
     assert len(P) == 0 and k == 0 and np.unique(real)[ri].tolist() == real.tolist()
+
+
+def test_native_writer_prints_like_python_percent_e(tmp_path):
+    """jacks_table_write formats with std::to_chars(scientific, 6); Python's '%5e' / '%6e' (the reference's writers,
+    jacks_io.py:91-156) must come out byte for byte: the whole exponent range, subnormals, halfway cases at the seventh
+    digit, exact powers of ten, signed zeros, infinities and NaN."""
+    rng = np.random.RandomState(11)
+    bits = rng.randint(0, 2 ** 63 - 1, size=60000, dtype=np.int64).view(np.float64)
+    bits = bits[np.isfinite(bits)]
+    ties = (rng.randint(-10 ** 7, 10 ** 7, size=20000) * 2 + 1) / 2.0 * 10.0 ** rng.randint(-12, 6, size=20000)
+    small = 10.0 ** -rng.uniform(0, 320, size=20000) * rng.uniform(0.1, 10, size=20000)
+    special = np.array([0.0, -0.0, 1.0, -1.0, 1e-5, 9.9999995e-1, 9.99999949999e7, 1e100, 1e-100, 5e-324, 2.2250738585072014e-308,
+                        1.7976931348623157e308, np.inf, -np.inf, np.nan, 0.5, 1.25e-7, 123456.75, 1234567.5, 12345675.0])
+    vals = np.concatenate([bits, -bits[:1000], ties, small, special])
+    vals = vals[:len(vals) // 4 * 4].reshape(-1, 4)
+    labels = ['row%d' % i for i in range(len(vals))]
+    for width in (5, 6):
+        path = str(tmp_path / ('w%d.txt' % width))
+        _native.table_write(path, 'h\n', labels, vals, width)
+        got = open(path).read().split('\n')
+        assert got[0] == 'h' and got[-1] == ''
+        fmt = '%' + str(width) + 'e'
+        for i, line in enumerate(got[1:-1]):
+            want = labels[i] + '\t' + '\t'.join(fmt % v for v in vals[i])
+            assert line == want, (i, line, want)
+
