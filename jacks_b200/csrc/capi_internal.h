@@ -157,6 +157,7 @@ bool host_pointer_is_pinned(const void* p);
 namespace jacks {
 struct KdeNull {
     double* sT; double* srt; double* stats; int* cell_first; double* loc;     // views into JacksCtx::tmp
+    double* win; double* outv;    // per line: window of the cell table + the null values outside it (kde_pvalues.cu)
     long long ld; int n_lines; int positive; int brute;
 };
 int kde_null_prepare(JacksCtx* ctx, const double* w1_pseudo, int64_t n_pseudo, int32_t n_lines, int32_t positive,

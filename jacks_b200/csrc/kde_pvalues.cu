@@ -168,7 +168,15 @@ constexpr double kCellWidth = 0.25;      // in units of h
 constexpr int kKsat = 34;                // (j - c)/4 >= 8.5: the cell counts fully
 constexpr int kKneg = 48;                // (j - c)/4 <= -12: negligible
 constexpr int kJmin = -20;               // targets below smin - 5 h: direct sum
-constexpr int kMaxCells = 2048;          // source cells per line; a line that needs more falls back to the O(n) sums
+constexpr int kMaxCells = 2048;          // source cells per line; a null whose range needs more keeps its far values outside the table
+// Heavy-tailed nulls.  A range of more than kMaxCells cells (512 bandwidths, i.e. > 54 standard deviations) means a few
+// values far from the rest: the table then covers the window mean +- kWinHalf bandwidths only and the values outside it
+// -- by Chebyshev fewer than n / 27^2, in practice a handful -- are kept, in their original order, in a per-line list
+// whose Phi terms every p-value of the line adds directly.  (Such lines used to fall back to the O(n) sums: 1.3 s instead
+// of 2 ms for the p-values of a screen in which a third of the lines had one such pseudo-gene.)  Only a list that
+// overflows kMaxOut sends its line to the O(n) kernel.
+constexpr double kWinHalf = 255.0;       // in units of h: 2,040 cells
+constexpr int kMaxOut = 2048;            // values outside the window kept per line
 constexpr int kMaxTargets = kMaxCells + kKsat - kJmin;
 constexpr int kPartChunk = 4096;         // null values per CTA of the partition pass
 constexpr int kPartThreads = 256;
@@ -243,7 +251,8 @@ __device__ __forceinline__ double block_min(double v, double* sh) {
 //                +6 = smallest null value, +7 = number of cells (0: the line is evaluated by the O(n) kernel)
 constexpr int kRowThreads = 1024;
 __global__ void __launch_bounds__(kRowThreads) kde_row_stats(double* __restrict__ sT, long long n_pseudo, long long ld,
-                                                             const int* __restrict__ nan_count, double* __restrict__ stats) {
+                                                             const int* __restrict__ nan_count, double* __restrict__ stats,
+                                                             double* __restrict__ win, double* __restrict__ outv) {
     constexpr int kStatsThreads = kRowThreads;           // (shadows the width of the older kde_line_stats kernel)
     __shared__ double sh[kStatsThreads / 32];
     __shared__ int s_base;
@@ -294,21 +303,72 @@ __global__ void __launch_bounds__(kRowThreads) kde_row_stats(double* __restrict_
         for (int i = threadIdx.x; i < n; i += kStatsThreads) c += normcdf((-100.0 - row[i]) / h);
         c = block_sum(c, sh);
     }
+    // the cell table covers [lo, hi]: the whole range, or the window around the mean when the range needs too many cells
+    const double inf = __longlong_as_double(0x7ff0000000000000LL);
+    double lo_t = smin, hi_t = smax;
+    bool usable = (n >= 2 && h > 0.0 && h == h), windowed = false;
+    if (usable) {
+        const double span = (smax - smin) / (h * kCellWidth);
+        if (!(span == span)) usable = false;
+        else if (!(span < (double)(kMaxCells - 1))) {
+            windowed = true;
+            lo_t = fmax(smin, mean - kWinHalf * h);
+            hi_t = fmin(smax, mean + kWinHalf * h);
+        }
+    }
+    int n_out = 0;
+    if (usable && windowed) {
+        // the values outside the window, in their original order (a fixed summation order keeps the p-values
+        // bit-reproducible): block-wide ordered compaction, as for the NaNs above
+        if (threadIdx.x == 0) s_base = 0;
+        __syncthreads();
+        double* ov = outv + (long long)l * kMaxOut;
+        for (long long i0 = 0; i0 < n; i0 += kStatsThreads) {
+            const long long i = i0 + threadIdx.x;
+            double v = 0.0;
+            bool out = false;
+            if (i < n) { v = row[i]; out = (v < lo_t || v > hi_t); }
+            const unsigned m = __ballot_sync(0xffffffffu, out);
+            if (lane == 0) s_cnt[warp] = __popc(m);
+            __syncthreads();
+            int wbase = s_base, total = 0;
+            for (int w = 0; w < kStatsThreads / 32; ++w) { const int cc = s_cnt[w]; if (w < warp) wbase += cc; total += cc; }
+            const int at = wbase + __popc(m & ((1u << lane) - 1));
+            if (out && at < kMaxOut) ov[at] = v;
+            __syncthreads();
+            if (threadIdx.x == 0) s_base += total;
+            __syncthreads();
+        }
+        n_out = s_base;
+        if (n_out > kMaxOut) usable = false;               // (cannot happen below 1.5 M pseudo-genes) -> the O(n) kernel
+    }
     if (threadIdx.x == 0) {
         double nc = 0.0;
-        if (n >= 2 && h > 0.0 && h == h) {
-            const double span = (smax - smin) / (h * kCellWidth);
-            if (span == span && span < (double)(kMaxCells - 1)) nc = floor(span) + 1.0;
-        }
+        if (usable) nc = floor((hi_t - lo_t) / (h * kCellWidth)) + 1.0;
+        if (!(nc >= 1.0 && nc <= (double)kMaxCells)) { nc = 0.0; }
+        const bool w_on = (nc > 0.0 && windowed);
         stats[l * 8 + 0] = h;
         stats[l * 8 + 1] = (double)n;
         stats[l * 8 + 2] = c;
         stats[l * 8 + 3] = wgt;
         stats[l * 8 + 4] = mean;
         stats[l * 8 + 5] = ss;
-        stats[l * 8 + 6] = smin;
+        stats[l * 8 + 6] = w_on ? lo_t : smin;             // origin of the cells
         stats[l * 8 + 7] = nc;
+        win[l * 4 + 0] = w_on ? lo_t : -inf;               // values outside [win0, win1] are not in the table ...
+        win[l * 4 + 1] = w_on ? hi_t : inf;
+        win[l * 4 + 2] = w_on ? (double)n_out : 0.0;       // ... but in the line's list outv[l][0 .. n_out)
+        win[l * 4 + 3] = 0.0;
     }
+}
+
+// Sum of the Phi terms of the null values of a line that lie outside its cell table (none for an ordinary null).
+__device__ __forceinline__ double kde_outlier_sum(double w, double rh, const double* __restrict__ win, const double* __restrict__ outv, int l) {
+    const int n_out = (int)win[l * 4 + 2];
+    double tot = 0.0;
+    const double* ov = outv + (long long)l * kMaxOut;
+    for (int i = 0; i < n_out; ++i) tot += normcdf((w - ov[i]) * rh);
+    return tot;
 }
 
 __device__ __forceinline__ int kde_cell_of(double s, double smin, double inv_delta, int nc) {
@@ -318,7 +378,7 @@ __device__ __forceinline__ int kde_cell_of(double s, double smin, double inv_del
 
 // Partition pass 1: per (line, chunk) histogram of the cell indices.
 __global__ void __launch_bounds__(kPartThreads) kde_cell_hist(const double* __restrict__ sT, long long ld, const double* __restrict__ stats,
-                                                              int nchunk, unsigned* __restrict__ hist) {
+                                                              const double* __restrict__ win, int nchunk, unsigned* __restrict__ hist) {
     __shared__ unsigned sh[kMaxCells];
     const int l = blockIdx.y, chunk = blockIdx.x;
     const int nc = (int)stats[l * 8 + 7];
@@ -330,7 +390,12 @@ __global__ void __launch_bounds__(kPartThreads) kde_cell_hist(const double* __re
     __syncthreads();
     const double* row = sT + (long long)l * ld;
     const int i1 = min(n, (chunk + 1) * kPartChunk);
-    for (int i = chunk * kPartChunk + threadIdx.x; i < i1; i += kPartThreads) atomicAdd(&sh[kde_cell_of(row[i], smin, inv_delta, nc)], 1u);
+    const double wlo = win[l * 4 + 0], whi = win[l * 4 + 1];
+    for (int i = chunk * kPartChunk + threadIdx.x; i < i1; i += kPartThreads) {
+        const double v = row[i];
+        if (v < wlo || v > whi) continue;                 // outside the table: in the line's list (kde_row_stats)
+        atomicAdd(&sh[kde_cell_of(v, smin, inv_delta, nc)], 1u);
+    }
     __syncthreads();
     unsigned* out = hist + ((long long)l * nchunk + chunk) * kMaxCells;
     for (int c = threadIdx.x; c < nc; c += kPartThreads) out[c] = sh[c];
@@ -338,8 +403,8 @@ __global__ void __launch_bounds__(kPartThreads) kde_cell_hist(const double* __re
 
 // Partition pass 2 (one CTA per line): cell_first[c] = points in cells below c; hist[chunk][c] becomes the position of
 // the first point of (chunk, c) in the partitioned row.
-__global__ void __launch_bounds__(1024) kde_cell_scan(const double* __restrict__ stats, int nchunk, unsigned* __restrict__ hist,
-                                                      int* __restrict__ cell_first) {
+__global__ void __launch_bounds__(1024) kde_cell_scan(const double* __restrict__ stats, const double* __restrict__ win, int nchunk,
+                                                      unsigned* __restrict__ hist, int* __restrict__ cell_first) {
     __shared__ unsigned tot[kMaxCells + 1];
     __shared__ unsigned wsum[32];
     const int l = blockIdx.x;
@@ -377,7 +442,7 @@ __global__ void __launch_bounds__(1024) kde_cell_scan(const double* __restrict__
         cf[c] = (int)f;
         for (int k = 0; k < nchunk; ++k) h[(long long)k * kMaxCells + c] += f;
     }
-    if (threadIdx.x == 0) cf[nc] = (int)stats[l * 8 + 1];
+    if (threadIdx.x == 0) cf[nc] = (int)stats[l * 8 + 1] - (int)win[l * 4 + 2];       // the values inside the table
 }
 
 // Lanes of the warp whose `key` (BITS significant bits) equals this lane's: what __match_any_sync returns, from BITS
@@ -404,7 +469,8 @@ __device__ __forceinline__ unsigned warp_match_bits(unsigned key) {
 // consecutive values at a time; the lanes of a group that fall into the same cell take consecutive positions in lane
 // order (match_any), and the warp's running count per cell (shared memory, one row per warp) carries on to the next group.
 __global__ void __launch_bounds__(kPartThreads) kde_cell_scatter(const double* __restrict__ sT, long long ld, const double* __restrict__ stats,
-                                                                 int nchunk, const unsigned* __restrict__ hist, double* __restrict__ srt) {
+                                                                 const double* __restrict__ win, int nchunk, const unsigned* __restrict__ hist,
+                                                                 double* __restrict__ srt) {
     extern __shared__ unsigned cnt[];                    // [8 warps][kMaxCells]
     const int l = blockIdx.y, chunk = blockIdx.x;
     const int nc = (int)stats[l * 8 + 7];
@@ -417,6 +483,7 @@ __global__ void __launch_bounds__(kPartThreads) kde_cell_scatter(const double* _
     for (int c = threadIdx.x; c < W * kMaxCells; c += kPartThreads) if ((c & (kMaxCells - 1)) < nc) cnt[c] = 0;
     __syncthreads();
     const double* row = sT + (long long)l * ld;
+    const double wlo = win[l * 4 + 0], whi = win[l * 4 + 1];
     const int base = chunk * kPartChunk + warp * SEG;
     unsigned* mine = cnt + warp * kMaxCells;
     double v[SEG / 32];
@@ -426,7 +493,10 @@ __global__ void __launch_bounds__(kPartThreads) kde_cell_scatter(const double* _
         const int i = base + k * 32 + lane;
         cell[k] = -1 - lane;                              // past the end: a key of its own, never written
         v[k] = 0.0;
-        if (i < n) { v[k] = row[i]; cell[k] = kde_cell_of(v[k], smin, inv_delta, nc); atomicAdd(&mine[cell[k]], 1u); }
+        if (i < n) {
+            v[k] = row[i];
+            if (!(v[k] < wlo || v[k] > whi)) { cell[k] = kde_cell_of(v[k], smin, inv_delta, nc); atomicAdd(&mine[cell[k]], 1u); }
+        }
     }
     __syncthreads();
     // prefix over the warps of every cell, starting from the chunk's base position
@@ -552,7 +622,8 @@ __device__ __forceinline__ double kde_tail_sum(double w, double z, double rh, in
 // far lower tail are queued (one aggregated atomic per warp) for kde_pvalues_tail: evaluated here they would hold up
 // the 31 other lanes of their warp for a few thousand instructions each.
 __global__ void __launch_bounds__(256) kde_pvalues_fast(const double* __restrict__ w1_genes, long long n_genes, int L,
-                                                        const double* __restrict__ stats, const double* __restrict__ loc, int positive,
+                                                        const double* __restrict__ stats, const double* __restrict__ win,
+                                                        const double* __restrict__ outv, const double* __restrict__ loc, int positive,
                                                         double* __restrict__ pvals, unsigned* __restrict__ tail_count,
                                                         long long* __restrict__ tail_idx) {
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -565,7 +636,7 @@ __global__ void __launch_bounds__(256) kde_pvalues_fast(const double* __restrict
             if (!(wv == wv)) pvals[idx] = wv;
             else {
                 const double w = positive ? -wv : wv;
-                const int n = (int)stats[l * 8 + 1];
+                const int n = (int)stats[l * 8 + 1] - (int)win[l * 4 + 2];          // null values inside the cell table
                 const double cterm = stats[l * 8 + 2], wgt = stats[l * 8 + 3], smin = stats[l * 8 + 6];
                 const double z = (w - smin) / stats[l * 8 + 0];
                 const double jf = floor(z * (1.0 / kCellWidth));
@@ -581,7 +652,10 @@ __global__ void __launch_bounds__(256) kde_pvalues_fast(const double* __restrict
 #pragma unroll
                     for (int m = kP - 1; m >= 0; --m) tot = fma(tot, t, a[m]);
                 }
-                if (!queue) pvals[idx] = (tot - cterm) * wgt;
+                if (!queue) {
+                    if (win[l * 4 + 2] != 0.0) tot += kde_outlier_sum(w, 1.0 / stats[l * 8 + 0], win, outv, l);     // heavy-tailed null
+                    pvals[idx] = (tot - cterm) * wgt;
+                }
             }
         }
     }
@@ -597,7 +671,8 @@ __global__ void __launch_bounds__(256) kde_pvalues_fast(const double* __restrict
 }
 
 __global__ void __launch_bounds__(256) kde_pvalues_tail(const double* __restrict__ w1_genes, int L, const double* __restrict__ srt,
-                                                        long long ld, const double* __restrict__ stats, const int* __restrict__ cell_first,
+                                                        long long ld, const double* __restrict__ stats, const double* __restrict__ win,
+                                                        const double* __restrict__ outv, const int* __restrict__ cell_first,
                                                         int positive, double* __restrict__ pvals, const unsigned* __restrict__ tail_count,
                                                         const long long* __restrict__ tail_idx) {
     const unsigned count = *tail_count;
@@ -608,8 +683,9 @@ __global__ void __launch_bounds__(256) kde_pvalues_tail(const double* __restrict
         const double w = positive ? -wv : wv;
         const double rh = 1.0 / stats[l * 8 + 0];
         const double z = (w - stats[l * 8 + 6]) / stats[l * 8 + 0];
-        const double tot = kde_tail_sum(w, z, rh, (int)stats[l * 8 + 1], (int)stats[l * 8 + 7], cell_first + (long long)l * (kMaxCells + 1),
-                                        srt + (long long)l * ld);
+        double tot = kde_tail_sum(w, z, rh, (int)stats[l * 8 + 1], (int)stats[l * 8 + 7], cell_first + (long long)l * (kMaxCells + 1),
+                                  srt + (long long)l * ld);
+        if (win[l * 4 + 2] != 0.0) tot += kde_outlier_sum(w, rh, win, outv, l);
         pvals[idx] = (tot - stats[l * 8 + 2]) * stats[l * 8 + 3];
     }
 }
@@ -690,6 +766,7 @@ int jacks::kde_null_prepare(JacksCtx* ctx, const double* w1_pseudo, int64_t n_ps
     auto take = [&](size_t bytes) { const size_t o = off; off += (bytes + 255) & ~(size_t)255; return o; };
     const size_t o_sT = take((size_t)ld * L * sizeof(double)), o_srt = take((size_t)ld * L * sizeof(double));
     const size_t o_stats = take(L * 8 * sizeof(double)), o_nan = take(L * sizeof(int));
+    const size_t o_win = take(L * 4 * sizeof(double)), o_outv = take(L * kMaxOut * sizeof(double));
     const size_t o_hist = take(L * nchunk * kMaxCells * sizeof(unsigned)), o_first = take(L * (kMaxCells + 1) * sizeof(int));
     const size_t o_mom = take(L * kMaxCells * kNM * sizeof(double)), o_loc = take(L * kMaxTargets * kNM * sizeof(double));
     const size_t o_tab = take((size_t)kNK * (2 * kP + 1) * sizeof(double));
@@ -700,6 +777,8 @@ int jacks::kde_null_prepare(JacksCtx* ctx, const double* w1_pseudo, int64_t n_ps
     double* sT = (double*)(base + o_sT);
     double* srt = (double*)(base + o_srt);
     double* stats = (double*)(base + o_stats);
+    double* win = (double*)(base + o_win);
+    double* outv = (double*)(base + o_outv);
     int* nan_count = (int*)(base + o_nan);
     unsigned* hist = (unsigned*)(base + o_hist);
     int* cell_first = (int*)(base + o_first);
@@ -716,18 +795,19 @@ int jacks::kde_null_prepare(JacksCtx* ctx, const double* w1_pseudo, int64_t n_ps
     }
     if ((e = cudaMemsetAsync(nan_count, 0, L * sizeof(int), st)) != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync");
     kde_transpose<<<dim3((unsigned)((n_pseudo + 31) / 32), (unsigned)((n_lines + 31) / 32)), 256, 0, st>>>(w1_pseudo, n_pseudo, n_lines, ld, positive ? 1 : 0, sT, nan_count);
-    kde_row_stats<<<n_lines, kRowThreads, 0, st>>>(sT, n_pseudo, ld, nan_count, stats);
+    kde_row_stats<<<n_lines, kRowThreads, 0, st>>>(sT, n_pseudo, ld, nan_count, stats, win, outv);
     ctx->launches += 2;
     if (!brute) {
-        kde_cell_hist<<<dim3((unsigned)nchunk, (unsigned)n_lines), kPartThreads, 0, st>>>(sT, ld, stats, nchunk, hist);
-        kde_cell_scan<<<n_lines, 1024, 0, st>>>(stats, nchunk, hist, cell_first);
-        kde_cell_scatter<<<dim3((unsigned)nchunk, (unsigned)n_lines), kPartThreads, kPartThreads / 32 * kMaxCells * sizeof(unsigned), st>>>(sT, ld, stats, nchunk, hist, srt);
+        kde_cell_hist<<<dim3((unsigned)nchunk, (unsigned)n_lines), kPartThreads, 0, st>>>(sT, ld, stats, win, nchunk, hist);
+        kde_cell_scan<<<n_lines, 1024, 0, st>>>(stats, win, nchunk, hist, cell_first);
+        kde_cell_scatter<<<dim3((unsigned)nchunk, (unsigned)n_lines), kPartThreads, kPartThreads / 32 * kMaxCells * sizeof(unsigned), st>>>(sT, ld, stats, win, nchunk, hist, srt);
         kde_cell_moments<<<dim3(kMaxCells / 8, (unsigned)n_lines), 256, 0, st>>>(srt, ld, stats, cell_first, mom);
         kde_local_expansions<<<dim3((kMaxTargets + kLocThreads - 1) / kLocThreads, (unsigned)n_lines), kLocThreads, 0, st>>>(stats, cell_first, mom, loc);
         ctx->launches += 5;
     }
     if ((e = cudaGetLastError()) != cudaSuccess) return cuda_fail(e, "kde null kernels launch");
     out->sT = sT; out->srt = srt; out->stats = stats; out->cell_first = cell_first; out->loc = loc;
+    out->win = win; out->outv = outv;
     out->ld = ld; out->n_lines = n_lines; out->positive = positive ? 1 : 0; out->brute = brute ? 1 : 0;
     return JACKS_OK;
 }
@@ -744,8 +824,8 @@ int jacks::kde_eval(JacksCtx* ctx, const KdeNull& nl, const double* w1_genes, in
         unsigned* tail_count = (unsigned*)ctx->kde_tail.p;
         long long* tail_idx = (long long*)((char*)ctx->kde_tail.p + 256);
         if ((e = cudaMemsetAsync(tail_count, 0, sizeof(unsigned), st)) != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync");
-        kde_pvalues_fast<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(w1_genes, n_genes, n_lines, nl.stats, nl.loc, nl.positive, pvals, tail_count, tail_idx);
-        kde_pvalues_tail<<<4 * ctx->n_sm, 256, 0, st>>>(w1_genes, n_lines, nl.srt, nl.ld, nl.stats, nl.cell_first, nl.positive, pvals, tail_count, tail_idx);
+        kde_pvalues_fast<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(w1_genes, n_genes, n_lines, nl.stats, nl.win, nl.outv, nl.loc, nl.positive, pvals, tail_count, tail_idx);
+        kde_pvalues_tail<<<4 * ctx->n_sm, 256, 0, st>>>(w1_genes, n_lines, nl.srt, nl.ld, nl.stats, nl.win, nl.outv, nl.cell_first, nl.positive, pvals, tail_count, tail_idx);
         ctx->launches += 2;
     }
     // lines whose range needs more cells than the table holds (far outliers), or everything when forced

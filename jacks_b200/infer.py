@@ -108,7 +108,7 @@ def inferJACKS(gene_index, testdata, ctrldata, fixed_x=None, n_iter=50, apply_w_
 
 
 def inferJACKSScreen(gene_index, pseudo_gene_index, testdata, ctrldata, fixed_x=None, n_iter=50, apply_w_hp=False,
-                     positive=False, device=0, full_pseudo=False, pseudo_csr=None):
+                     positive=False, device=0, full_pseudo=False, pseudo_csr=None, out=None):
     """The inference job of load_data_and_run in one GPU call (jacks_run_screen_host): what the reference does with
 
         jacks_results = inferJACKS(gene_index, testdata, ctrldata, apply_w_hp=..., fixed_x=...)        (jacks_io.py:425)
@@ -123,7 +123,8 @@ def inferJACKSScreen(gene_index, pseudo_gene_index, testdata, ctrldata, fixed_x=
     if testdata.shape != ctrldata.shape:
         raise Exception(_SHAPE_MSG)
     names, offsets, rows = _native.as_csr(gene_index)
-    # pseudo_csr: (names, offsets, rows) of pseudo_gene_index when its maker already holds it (jacks_io._drawPseudoGenes)
+    # pseudo_csr: (names, offsets, rows) of pseudo_gene_index when its maker already holds it (jacks_io._drawPseudoGenes);
+    # out: preallocated result arrays {x1, x2, w1, w2, y, tau, pvals} (jacks_io pre-faults them beside its file writes)
     pnames, poffsets, prows = pseudo_csr if pseudo_csr is not None else _native.as_csr(pseudo_gene_index)
     testdata, ctrldata = _planes(testdata), _planes(ctrldata)
     if _one_control(ctrldata):
@@ -136,7 +137,7 @@ def inferJACKSScreen(gene_index, pseudo_gene_index, testdata, ctrldata, fixed_x=
     r = _native.run_screen_host(_native.context(device), offsets, _rows(rows, N), poffsets, _rows(prows, N), testdata, ctrldata,
                                 params=params, fixed_x1=fx1, fixed_x2=fx2, positive=positive,
                                 want=('x1', 'x2', 'w1', 'w2', 'y', 'tau', 'pvals'),
-                                want_pseudo=('w1', 'w2', 'pvals') if full_pseudo else ())
+                                want_pseudo=('w1', 'w2', 'pvals') if full_pseudo else (), out=out)
     results, pvals = {}, {}
     lo, hi = offsets[:-1].tolist(), offsets[1:].tolist()
     y, tau, x1, x2, w1, w2, pv = r['y'], r['tau'], r['x1'], r['x2'], r['w1'], r['w2'], r['pvals']

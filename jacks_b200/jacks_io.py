@@ -460,6 +460,15 @@ def load_data_and_run(sample_spec, gene_spec, ctrl_spec, sgrna_reference_file, x
     testdata, ctrldata, test_sample_idxs = collateTestControlSamples(data, sample_ids, ctrl_spec)
     sample_ids_without_ctrl = [sample_ids[idx] for idx in test_sample_idxs]
 
+    with_pseudo = n_pseudo > 0 and len(ctrl_geneset) > 0
+    prefault = None
+    if with_pseudo and n_pseudo >= 2:
+        # the result arrays of the screen job (0.63 GB at the Avana shape), touched for the first time on a background thread
+        # while the fold-change files are written: a one-shot process would take those page faults inside the inference call
+        T, n_real, L = sum(len(v) for v in gene_index.values()), len(gene_index), testdata.shape[1]
+        f8 = np.float64
+        prefault = _native.PrefaultedArrays(dict(x1=((T,), f8), x2=((T,), f8), w1=((n_real, L), f8), w2=((n_real, L), f8),
+                                                 y=((T, L), f8), tau=((T, L), f8), pvals=((n_real, L), f8)))
     x_reference = None
     if sgrna_reference_file:
         x_reference = {'X1': np.array([eval(x_ref[x]['X1']) for x in meta[:, 0]]),
@@ -469,7 +478,6 @@ def load_data_and_run(sample_spec, gene_spec, ctrl_spec, sgrna_reference_file, x
         writeFoldChanges(outfile_lfc_std, testdata, ctrldata, meta, sample_ids_without_ctrl, write_std=True)
 
     LOG.info('Running JACKS inference')
-    with_pseudo = n_pseudo > 0 and len(ctrl_geneset) > 0
     if with_pseudo and n_pseudo >= 2:
         # The reference's two inferJACKS calls (jacks_io.py:425, :430) and its p-value pass (:69-89) as ONE job on the GPU:
         # the screen goes up once, the pseudo-gene E[w] feeds the null densities on the device.  The pseudo-genes are
@@ -481,7 +489,7 @@ def load_data_and_run(sample_spec, gene_spec, ctrl_spec, sgrna_reference_file, x
         LOG.info('Running JACKS inference on %d pseudogenes' % n_pseudo)
         jacks_results, w1_pvals, pseudo = inferJACKSScreen(gene_index, pseudo_gene_index, testdata, ctrldata, fixed_x=x_reference,
                                                            apply_w_hp=apply_w_hp, positive=positive, full_pseudo=(fdr is not None),
-                                                           pseudo_csr=pseudo_csr)
+                                                           pseudo_csr=pseudo_csr, out=prefault.take())
         # no pseudo-gene is ever written (jacks_io.py:131): the reference's '_pseudo_noness' files hold the header only
         writeJacksWResults(outprefix + '_pseudo_noness', {}, sample_ids_without_ctrl, write_types=['', '_std'], positive=positive)
         jacks_pseudo_results = dict(jacks_results)

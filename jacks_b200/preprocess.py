@@ -103,7 +103,7 @@ def collateTestControlSamples(data, sample_ids, ctrl_spec):
     """Split the [N, S, 2] cube into test samples and, per test sample, its control (preprocess.py:121-126)."""
     test_sample_idxs = [i for i, x in enumerate(sample_ids) if ctrl_spec[x] != x]
     LOG.info('Collating %d samples' % len(test_sample_idxs))
-    testdata = data[:, test_sample_idxs, :]
+    testdata = np.take(data, test_sample_idxs, axis=1)          # the values of data[:, idxs, :], C-contiguous (fancy indexing promises no layout)
     ctrl_idxs = [sample_ids.index(ctrl_spec[sample_ids[idx]]) for idx in test_sample_idxs]
     if len(ctrl_idxs) > 1 and len(set(ctrl_idxs)) == 1:
         # one control sample for every line (--common_ctrl_sample): the same [N, L, 2] values as the reference's copy,

@@ -53,6 +53,40 @@ def test_pvalues_vs_oracle(nat, n_pseudo, L, n_genes):
         assert rel_close(pv, ref, 1e-10, atol=1e-15 if positive else 0.0) < 1e-10
 
 
+@pytest.mark.parametrize('n_pseudo', [3000, 40000])
+def test_heavy_tailed_null_vs_oracle(nat, n_pseudo):
+    """Nulls whose range needs more cells than the table holds (a few pseudo-genes hundreds of bandwidths from the rest):
+    the table covers a window around the mean, the values outside it are added term by term.  Lines: ordinary, far
+    values below, above, on both sides, one value at the very edge of the window, and a gross outlier that inflates the
+    bandwidth itself.  Genes sit everywhere: below all null values, between the far values and the bulk, in the bulk,
+    above everything.  Against the numpy restatement of gaussian_kde.integrate_box_1d (1e-10), and against the same
+    library forced onto its O(n) sums."""
+    import os
+    from oracle import jacks_oracle as O
+    rng = np.random.default_rng(n_pseudo)
+    L = 6
+    pseudo = rng.normal(0.0, 0.02, size=(n_pseudo, L))
+    pseudo[rng.integers(0, n_pseudo, size=4), 1] = np.array([-3.0, -2.5, -2.9, -7.0])           # far below
+    pseudo[rng.integers(0, n_pseudo, size=3), 2] = np.array([4.0, 2.0, 2.0])                     # far above (a tie)
+    pseudo[rng.integers(0, n_pseudo, size=6), 3] = np.array([-5.0, -1.0, 6.0, 1.5, -1.0, 3.0])   # both sides
+    pseudo[7, 4] = -60.0                                                                           # inflates sigma and h
+    pseudo[11, 5] = 2.0
+    pseudo[13, 5] = np.nan
+    grid = np.concatenate([np.linspace(-8.0, 7.0, 61), np.linspace(-0.1, 0.1, 41), [-70.0, -59.9, 25.0]])
+    genes = np.repeat(grid[:, None], L, axis=1) + rng.normal(0, 1e-3, size=(len(grid), L))
+    ctx = nat.context(0)
+    for positive in (False, True):
+        pv = nat.kde_pvalues_host(ctx, genes, pseudo, positive=positive)
+        ref = O.kde_pvalues(genes, pseudo, positive=positive)
+        assert rel_close(pv, ref, 1e-10, atol=1e-15 if positive else 0.0) < 1e-10
+        os.environ['JACKS_KDE_BRUTE'] = '1'
+        try:
+            brute = nat.kde_pvalues_host(ctx, genes, pseudo, positive=positive)
+        finally:
+            del os.environ['JACKS_KDE_BRUTE']
+        assert rel_close(pv, brute, 1e-10, atol=1e-15 if positive else 0.0) < 1e-10
+
+
 def test_pvalue_properties_full_size(nat):
     """BASELINE size for one line block: 18,000 genes against 100,000 pseudo-genes -- monotone in w, in [0,1],
     negative + positive selection sum to the mass between -100 and 100 (= 1)."""
