@@ -124,6 +124,8 @@ extern "C" int jacks_table_read(const char* path, int64_t data_offset, char deli
     for (int i = 0; i < n_sel; ++i) { if (sel_cols[i] < 0) return fail(JACKS_E_INVALID, "negative column index"); if (sel_cols[i] > max_col) max_col = sel_cols[i]; }
     std::vector<std::vector<int>> want(max_col + 1);          // column -> output slots (a column may be selected twice)
     for (int i = 0; i < n_sel; ++i) want[sel_cols[i]].push_back(i);
+    int last_col = n_sel > 0 ? max_col : 0;                     // nothing beyond this column is asked for
+    for (int k = 0; k < n_str; ++k) if (str_cols[k] > last_col) last_col = str_cols[k];
     const char* b = m.p + data_offset;
     const char* end = m.p + m.n;
     const char* next = b;
@@ -183,6 +185,7 @@ extern "C" int jacks_table_read(const char* path, int64_t data_offset, char deli
                         if (plain) for (int slot : want[col]) { values[r * n_sel + slot] = v; if (not_numeric) not_numeric[r * n_sel + slot] = 0; }
                     }
                 }
+                if (col == last_col) break;                       // (reading guide -> gene pairs off a count table stops at column 1)
                 ++col;
                 if (fe >= e) break;
                 f = fe + 1;
