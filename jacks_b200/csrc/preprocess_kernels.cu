@@ -489,56 +489,70 @@ __global__ void __launch_bounds__(1024) rs_scan(int nchunk, unsigned* __restrict
 
 // Stable scatter: warp w of the CTA owns a contiguous eighth of the chunk and walks it in order, 32 consecutive keys at
 // a time; keys of a group with equal digit take consecutive positions in lane order (match_any); the warp's running
-// count per digit (shared memory, one row per warp) carries on to the next group.
+// count per digit carries on to the next group.
+// The pass waits on memory (ncu: long_scoreboard, 37 % of the warp slots in use with three CTAs per SM), so it is built
+// for occupancy: the per-warp counts are 16-bit, two warps to a word (a warp owns 512 keys, a chunk 4,096; both halves
+// are updated with shared-memory atomics and a half never carries into its neighbour: its final value is at most 4,096)
+// -- 32 KB instead of 64, plus the chunk's 8 KB of first positions -- and the keys are READ TWICE (once to count, once to
+// move; the second time from L2) instead of being held in 64 registers between the two phases.
+constexpr int kRsScatterSmem = (kRsThreads / 64) * kRsBins * 4 + kRsBins * 4;
 __device__ __forceinline__ void rs_scatter_item(const unsigned long long* __restrict__ kin, const int* __restrict__ iin,
                                                 long long ld, long long N, int shift, int nchunk,
                                                 const unsigned* __restrict__ hist, unsigned long long* __restrict__ kout,
                                                 int* __restrict__ iout, int s, int chunk, unsigned* cnt) {
     constexpr int W = kRsThreads / 32, SEG = kRsChunk / W;
+    static_assert(W % 2 == 0 && kRsChunk <= 65535, "two 16-bit counters per word");
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    for (int c = threadIdx.x; c < W * kRsBins; c += kRsThreads) cnt[c] = 0;
+    unsigned* first = cnt + (W / 2) * kRsBins;            // [kRsBins] position of the chunk's first key of a digit
+    const unsigned* hb = hist + ((long long)s * nchunk + chunk) * kRsBins;
+    for (int c = threadIdx.x; c < (W / 2) * kRsBins; c += kRsThreads) cnt[c] = 0;
+    for (int c = threadIdx.x; c < kRsBins; c += kRsThreads) first[c] = hb[c];
     __syncthreads();
     const long long o = (long long)s * ld;
     const long long base = (long long)chunk * kRsChunk + warp * SEG;
-    unsigned* mine = cnt + warp * kRsBins;
-    unsigned long long key[SEG / 32];
-    int pay[SEG / 32], dig[SEG / 32];
-#pragma unroll
+    unsigned* mine = cnt + (warp >> 1) * kRsBins;         // my half: bits 16*(warp & 1) ...
+    const int sh = 16 * (warp & 1);
+#pragma unroll 8
     for (int k = 0; k < SEG / 32; ++k) {
         const long long i = base + k * 32 + lane;
-        dig[k] = -1 - lane;                               // past the end: a digit of its own, never written
-        key[k] = 0; pay[k] = 0;
-        if (i < N) {
-            key[k] = kin[o + i]; pay[k] = iin[o + i];
-            dig[k] = (int)((unsigned)(key[k] >> shift) & (kRsBins - 1));
-            atomicAdd(&mine[dig[k]], 1u);
+        if (i < N) atomicAdd(&mine[(unsigned)(kin[o + i] >> shift) & (kRsBins - 1)], 1u << sh);
+    }
+    __syncthreads();
+    // per digit: exclusive prefix of the warps' counts (offsets inside the chunk's run of that digit)
+    for (int c = threadIdx.x; c < kRsBins; c += kRsThreads) {
+        unsigned run = 0;
+#pragma unroll
+        for (int p = 0; p < W / 2; ++p) {
+            const unsigned t = cnt[p * kRsBins + c];
+            const unsigned lo = run; run += t & 0xffffu;
+            const unsigned hi = run; run += t >> 16;
+            cnt[p * kRsBins + c] = lo | (hi << 16);
         }
     }
     __syncthreads();
-    const unsigned* hb = hist + ((long long)s * nchunk + chunk) * kRsBins;
-    for (int c = threadIdx.x; c < kRsBins; c += kRsThreads) {
-        unsigned run = hb[c];
-        for (int w = 0; w < W; ++w) { const unsigned t = cnt[w * kRsBins + c]; cnt[w * kRsBins + c] = run; run += t; }
-    }
-    __syncthreads();
-#pragma unroll
+#pragma unroll 4
     for (int k = 0; k < SEG / 32; ++k) {
+        const long long i = base + k * 32 + lane;
+        unsigned long long key = 0;
+        int pay = 0, dig = -1 - lane;                     // past the end: a digit of its own, never written
+        if (i < N) { key = kin[o + i]; pay = iin[o + i]; dig = (int)((unsigned)(key >> shift) & (kRsBins - 1)); }
         // (equal digits from kRsBits + 1 ballots instead of MATCH.ANY, which pays in the KDE scatter, measured 3 % slower here)
-        const unsigned peers = __match_any_sync(0xffffffffu, dig[k]);
+        const unsigned peers = __match_any_sync(0xffffffffu, dig);
         const int leader = __ffs(peers) - 1;
         const int rank = __popc(peers & ((1u << lane) - 1));
         unsigned old = 0;
-        if (lane == leader && dig[k] >= 0) { old = mine[dig[k]]; mine[dig[k]] = old + __popc(peers); }
+        if (lane == leader && dig >= 0)
+            old = first[dig] + ((atomicAdd(&mine[dig], (unsigned)__popc(peers) << sh) >> sh) & 0xffffu);
         old = __shfl_sync(0xffffffffu, old, leader);
-        if (dig[k] >= 0) { kout[o + old + rank] = key[k]; iout[o + old + rank] = pay[k]; }
+        if (dig >= 0) { kout[o + old + rank] = key; iout[o + old + rank] = pay; }
         __syncwarp();
     }
 }
-__global__ void __launch_bounds__(kRsThreads) rs_scatter(const unsigned long long* __restrict__ kin, const int* __restrict__ iin,
+__global__ void __launch_bounds__(kRsThreads, 5) rs_scatter(const unsigned long long* __restrict__ kin, const int* __restrict__ iin,
                                                          long long ld, long long N, int shift, int nchunk,
                                                          const unsigned* __restrict__ hist, unsigned long long* __restrict__ kout,
                                                          int* __restrict__ iout) {
-    extern __shared__ unsigned cnt[];                    // [8 warps][kRsBins]
+    extern __shared__ unsigned cnt[];                    // [4 warp pairs][kRsBins] packed counts + [kRsBins] first positions
     rs_scatter_item(kin, iin, ld, N, shift, nchunk, hist, kout, iout, blockIdx.y, blockIdx.x, cnt);
 }
 __global__ void __launch_bounds__(kRsThreads) rs_scatter_gated(const unsigned long long* __restrict__ kin, const int* __restrict__ iin,
@@ -1093,8 +1107,8 @@ int sort_mean_var(JacksCtx* ctx, cudaStream_t st, const double* km, const double
                   const SortScratch& w, double* km_s, double* kv_s, int** ki_sorted) {
     cudaError_t e;
     if (!ctx->pre_attr_set) {              // per device
-        if ((e = cudaFuncSetAttribute(rs_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, kRsThreads / 32 * kRsBins * 4)) != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute");
-        if ((e = cudaFuncSetAttribute(rs_scatter_gated, cudaFuncAttributeMaxDynamicSharedMemorySize, kRsThreads / 32 * kRsBins * 4)) != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute");
+        if ((e = cudaFuncSetAttribute(rs_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, kRsScatterSmem)) != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute");
+        if ((e = cudaFuncSetAttribute(rs_scatter_gated, cudaFuncAttributeMaxDynamicSharedMemorySize, kRsScatterSmem)) != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute");
         ctx->pre_attr_set = true;
     }
     const int nchunk = (int)((N + kRsChunk - 1) / kRsChunk);
@@ -1111,12 +1125,12 @@ int sort_mean_var(JacksCtx* ctx, cudaStream_t st, const double* km, const double
             if (!gate) {
                 rs_hist<<<cg, kRsThreads, 0, st>>>(kin, ld, N, shift, nchunk, w.hist);
                 rs_scan<<<S, 1024, 0, st>>>(nchunk, w.hist, nullptr);
-                rs_scatter<<<cg, kRsThreads, kRsThreads / 32 * kRsBins * 4, st>>>(kin, iin, ld, N, shift, nchunk, w.hist, kout, iout);
+                rs_scatter<<<cg, kRsThreads, kRsScatterSmem, st>>>(kin, iin, ld, N, shift, nchunk, w.hist, kout, iout);
             } else {
                 const unsigned wg = (unsigned)std::min<long long>((long long)nchunk * S, 592);
                 rs_hist_gated<<<wg, kRsThreads, 0, st>>>(kin, ld, N, shift, nchunk, S, w.hist, gate);
                 rs_scan<<<S, 1024, 0, st>>>(nchunk, w.hist, gate);
-                rs_scatter_gated<<<wg, kRsThreads, kRsThreads / 32 * kRsBins * 4, st>>>(kin, iin, ld, N, shift, nchunk, S, w.hist, kout, iout, gate);
+                rs_scatter_gated<<<wg, kRsThreads, kRsScatterSmem, st>>>(kin, iin, ld, N, shift, nchunk, S, w.hist, kout, iout, gate);
             }
             ctx->launches += 3;
             std::swap(kin, kout); std::swap(iin, iout);
