@@ -135,17 +135,19 @@ def writeJacksWResults(outprefix, jacks_results, cell_lines, write_types=[''], c
     for fout in fouts:
         fout.close()
     kept, flags = [], []
-    for w1_mean, gene in ordered_genes:
-        if fdr is not None:
+    if fdr is None:
+        # every line of every gene counts as significant (jacks_io.py:118): no per-line flag lists, nothing blanked
+        kept = [gene for w1_mean, gene in ordered_genes if len(jacks_results[gene][4]) > 0 and 'JACKS_PSEUDO_GENE' not in gene]
+        flags = None
+    else:
+        for w1_mean, gene in ordered_genes:
             sig_gene_flags = [(gene in x) for x in fdr_sets]
-        else:
-            sig_gene_flags = [True for x in jacks_results[gene][4]]
-        if sum(sig_gene_flags) == 0:
-            continue
-        if 'JACKS_PSEUDO_GENE' in gene:
-            continue                                  # pseudo-genes are never written (jacks_io.py:131)
-        kept.append(gene)
-        flags.append(sig_gene_flags)
+            if sum(sig_gene_flags) == 0:
+                continue
+            if 'JACKS_PSEUDO_GENE' in gene:
+                continue                              # pseudo-genes are never written (jacks_io.py:131)
+            kept.append(gene)
+            flags.append(sig_gene_flags)
     L = len(cell_lines)
     W1 = np.array([jacks_results[g][4] for g in kept], dtype=np.float64).reshape(len(kept), L)
     header = u'Gene\t%s\n' % ('\t'.join(cell_lines))
@@ -161,7 +163,8 @@ def writeJacksWResults(outprefix, jacks_results, cell_lines, write_types=[''], c
                 vals = np.sqrt(W2 - W1 ** 2.0)
         elif write_type == '':
             vals = W1
-            blank = ~np.array(flags, dtype=bool).reshape(len(kept), L)
+            if flags is not None:
+                blank = ~np.array(flags, dtype=bool).reshape(len(kept), L)
         else:
             raise Exception('Unrecognised write type: %s' % write_type)
         _native.table_write(outprefix + '_gene%s_JACKS_results.txt' % write_type, header, kept, vals, 5, blank=blank)
