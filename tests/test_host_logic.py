@@ -261,6 +261,34 @@ def test_native_table_reader_matches_csv_module(tmp_path):
     assert pairs[0] == ('g1', 'X') and pairs[3] == ('g4', 'X')
 
 
+def test_native_table_reader_number_forms_and_short_records(tmp_path):
+    """The digit fast path, the strtod path and the early stop at the last requested column: integers of every length a
+    double holds exactly and beyond, signs, floats, exponents, padded cells, empty cells, records shorter than the selected
+    columns, quoted fields beyond the last requested column, and records with both line terminators."""
+    lines = ['id\tgene\ta\tb\tc\td',
+             'r0\tG\t0\t007\t123456789012345\t1234567890123456789',       # 15 digits: fast path; 19 digits: strtod
+             'r1\tG\t+5\t-3\t2.50\t1e-3',
+             'r2\tG\t\t 4\t5 \t.5',                                         # an empty cell, padded cells
+             'r3\tG\t1\t2',                                                  # short record: c and d are missing
+             'r4\tG\t9\t8\t7\t"6,\t""x"""',                                  # a quoted field with a delimiter, last column
+             'r5\tG\t0x10\t1_0\tnan\tinf']                                   # not plain decimal literals: left to eval()
+    p = tmp_path / 't.tab'
+    p.write_bytes(('\r\n'.join(lines[:4]) + '\n' + '\n'.join(lines[4:]) + '\n').encode())
+    labels, v, bad = _native.table_read(str(p), '\t', [2, 3, 4, 5])
+    assert labels == ['r0', 'r1', 'r2', 'r3', 'r4', 'r5']
+    assert v[0].tolist() == [0.0, 7.0, 123456789012345.0, float(1234567890123456789)] and not bad[0].any()
+    assert v[1].tolist() == [5.0, -3.0, 2.5, 1e-3] and not bad[1].any()
+    assert bad[2].tolist() == [True, False, False, False] and v[2, 1:].tolist() == [4.0, 5.0, 0.5]
+    assert bad[3].tolist() == [False, False, True, True] and v[3, :2].tolist() == [1.0, 2.0]
+    assert bad[4].tolist() == [False, False, False, True] and v[4, :3].tolist() == [9.0, 8.0, 7.0]
+    assert bad[5].all()
+    # only the first columns asked for: the rest of every record (incl. the quoted field) is never looked at
+    labels, v, bad = _native.table_read(str(p), '\t', [2], str_cols=(0, 1))
+    assert labels[4] == ('r4', 'G') and v[:, 0].tolist()[:2] == [0.0, 5.0] and bad[:, 0].tolist() == [False, False, True, False, False, True]
+    pairs, v0, _ = _native.table_read(str(p), '\t', [], str_cols=(0, 1))
+    assert pairs == [('r%d' % i, 'G') for i in range(6)] and v0.shape == (6, 0)
+
+
 def test_count_reader_native_equals_python_reader(tmp_path):
     from jacks_b200 import preprocess
     inp = load_golden('small_inputs.npz')
